@@ -1,0 +1,143 @@
+/*
+ * vlmc.h - C ABI of the B200 (sm_100a) calibration-and-masking kernels.
+ *
+ * This is the drop-in boundary for the one hot path of Shwai-He/VLM-Compression:
+ * the per-linear-layer statistics / mask-selection / OBS-sweep / masked-merge code in
+ *   lavis/compression/pruners/{wanda,sparsegpt,dsnot}_pruner.py and
+ *   lavis/peft/src/peft/tuners/lora.py.
+ * The reference has no FFI of its own (it is pure torch), so every entry point below
+ * names the torch call sites (file:line) it replaces.  INTEGRATION.md shows the ctypes
+ * stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch allocates, we never do);
+ *     nothing is retained after the call returns
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); calls are
+ *     asynchronous unless stated otherwise
+ *   - matrices are row-major with an explicit leading dimension in ELEMENTS
+ *   - `ws` is caller-provided scratch of at least vlmc_workspace_bytes() bytes.  The first
+ *     VLMC_WS_COUNTER_BYTES bytes hold inter-CTA tickets: they must be ZERO before the
+ *     first use of a workspace and every call leaves them zero again.  One workspace must
+ *     not be shared by calls running concurrently on different streams.
+ *   - return value: 0 ok; <0 argument / launch error; >0 numerical status
+ *   - there is NO CPU path: host pointers are rejected with VLMC_ERR_NOT_DEVICE
+ */
+#ifndef VLMC_H_
+#define VLMC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLMC_ABI_VERSION 1
+
+enum vlmc_dtype { VLMC_F32 = 0, VLMC_F16 = 1, VLMC_BF16 = 2 };
+
+enum vlmc_status {
+  VLMC_OK = 0,
+  VLMC_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, bad enum            */
+  VLMC_ERR_UNSUPPORTED = -2,  /* shape / alignment outside what the kernels are built for */
+  VLMC_ERR_NOT_DEVICE = -3,   /* a pointer is not CUDA device memory                  */
+  VLMC_ERR_WORKSPACE = -4,    /* ws too small                                         */
+  VLMC_ERR_CUDA = -5,         /* launch failed; see vlmc_last_cuda_error()            */
+  VLMC_NOT_POSDEF = 1         /* Cholesky met a non-positive pivot (caller damps, retries) */
+};
+
+#define VLMC_WS_COUNTER_BYTES 4096
+
+enum vlmc_op {
+  VLMC_OP_SQNORM = 0,       /* (T, C, 0)       */
+  VLMC_OP_DSNOT_STATS = 1,  /* (nseg*S, C, nseg) */
+  VLMC_OP_WANDA_SELECT = 2, /* (R, C, 0)       */
+  VLMC_OP_LORA_MERGE = 3,   /* (R, C, r)       */
+  VLMC_OP_HESSIAN = 4,      /* (T, C, 0)       */
+  VLMC_OP_CHOL = 5,         /* (C, 0, 0)       */
+  VLMC_OP_OBS = 6,          /* (R, C, blocksize) */
+  VLMC_OP_DSNOT_REFINE = 7  /* (R, C, 0)       */
+};
+
+int vlmc_version(void);
+const char* vlmc_status_string(int status);
+/* cudaError_t of the most recent failing launch on this thread (0 if none). */
+int vlmc_last_cuda_error(void);
+size_t vlmc_workspace_bytes(int op, int64_t d0, int64_t d1, int64_t d2);
+
+/*
+ * K1  Wanda calibration statistic.  Replaces WrappedGPT.add_batch, wanda_pruner.py:66-81:
+ *   scaler_row[c] <- scaler_row[c] * n_before/(n_before+b) + (sum_t x[t,c]^2) / (n_before+b)
+ * x: [T, C] row-major activations of one add_batch call (the reference's inp.reshape(-1, C)),
+ * T = b * seq_len.  fp16 / bf16 / fp32 inputs are up-cast to fp32 like wanda_pruner.py:80.
+ * One streaming pass over x, fp32 per-thread partials, fp64 cross-CTA combine (deterministic).
+ */
+int vlmc_sqnorm_accum(const void* x, int dtype, int64_t T, int C, int64_t ldx,
+                      float* scaler_row, double n_before, double b,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * K2  DSnoT calibration statistics.  Replaces WrappedGPT.add_batch, dsnot_pruner.py:79-101.
+ * x is treated as `nseg` consecutive add_batch calls of S rows each, every one with leading
+ * batch dimension b_per_seg (nseg = 1 reproduces a single reference call exactly):
+ *   scaler_row, sum_row : running means over samples of sum_t x^2 and sum_t x   (:96-101)
+ *   mean, var           : token-weighted running means of the per-call mean and
+ *                         per-call BIASED variance                                (:89-93)
+ * ntok_before is the wrapper's ntokens before the call.
+ */
+int vlmc_dsnot_stats(const void* x, int dtype, int64_t nseg, int64_t S, int C, int64_t ldx,
+                     float* scaler_row, float* sum_row, float* mean, float* var,
+                     double n_before, double b_per_seg, double ntok_before,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * K4+K5  Wanda score + per-row unstructured selection.  Replaces wanda_pruner.py:318-341
+ * (LLM path): S = |W| * sqrt(scaler_row) in fp32; in every row the k smallest scores are
+ * pruned, ties going to the LOWER column (torch.sort(stable=True), :332).  k = int(C * p)
+ * is computed by the caller (:336).
+ *   keep_mask [R, ldm] bytes: 1 = kept, 0 = pruned (= module.mask, :339)
+ *   zero_w != 0 writes 0 into pruned weights in place (:341); 0 leaves W untouched (lora_model)
+ *   score_mean (device float, may be NULL): mean(S) (= weight.importance_score, :320)
+ */
+int vlmc_wanda_rowselect(void* W, int dtype, int R, int C, int64_t ldw,
+                         const float* scaler_row, int k, int zero_w,
+                         uint8_t* keep_mask, int64_t ldm, float* score_mean,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * K4+K6  Wanda score + n:m selection.  Replaces the C/m-iteration python loop at
+ * wanda_pruner.py:323-329 (and its ViT copy :671-677): in every group of m consecutive
+ * columns the n smallest scores are pruned; ties go to the lower column.
+ * m in {2,4,8,16}, 0 < n < m, C % m == 0.
+ */
+int vlmc_wanda_nm(void* W, int dtype, int R, int C, int64_t ldw,
+                  const float* scaler_row, int n, int m, int zero_w,
+                  uint8_t* keep_mask, int64_t ldm, float* score_mean,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * K4+K7  Wanda score + whole-matrix threshold (ViT path).  Replaces wanda_pruner.py:682-683:
+ *   thres = sort(S.flatten())[k_global];  prune S < thres   (strict: ties are kept)
+ * k_global = int(R * C * p) computed by the caller.
+ */
+int vlmc_wanda_threshold(void* W, int dtype, int R, int C, int64_t ldw,
+                         const float* scaler_row, int64_t k_global, int zero_w,
+                         uint8_t* keep_mask, int64_t ldm, float* score_mean,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * K14  SparseLoRA masked merge.  Replaces Linear.merge() (sparse branch), lora.py:384-387,
+ * fused with the re-mask of train.py:634-637:
+ *   W[r,c] <- keep_mask[r,c] ? round_to_W_dtype( float(W[r,c]) + scaling * sum_k B[r,k]*A[k,c] ) : 0
+ * A = lora_A.weight [rank, C], B = lora_B.weight [R, rank], both fp32 row-major contiguous.
+ * remask = 0 keeps W[r,c] unchanged where keep_mask is 0 (merge() alone).
+ */
+int vlmc_sparselora_merge(void* W, int dtype, int R, int C, int64_t ldw,
+                          const float* A, const float* B, int rank, float scaling,
+                          const uint8_t* keep_mask, int64_t ldm, int remask,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLMC_H_ */

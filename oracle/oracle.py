@@ -1,0 +1,187 @@
+"""TEST INFRASTRUCTURE ONLY - CPU (numpy) restatement of the reference's calibration-and-masking path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module, and only as the checker (or the timed CPU baseline), never as part of the product
+path: vlmc/ must not import it.
+
+Parity status: PINNED.  The reference ships no tests or golden vectors for this path (SURVEY.md
+section 4), but its modules load unmodified in the build container (oracle/ref_loader.py), so every
+function below is checked against the reference itself: tests/golden/make_golden.py runs the
+reference on seeded inputs and commits the outputs as fixtures (tests/golden/*.npz);
+tests/test_oracle_vs_golden.py replays them through this file, and tests/test_oracle_vs_reference.py
+does the same live whenever /root/reference is present.  The one golden vector the reference itself
+holds, the return_reorder_indice docstring example (dsnot_pruner.py:1882-1893), is checked too.
+
+All arrays are numpy.  Half / bfloat16 tensors are passed as float32 arrays holding the exactly
+up-cast values plus a dtype tag ("f16" | "bf16" | "f32") where an output must be rounded back.
+"""
+import numpy as np
+
+F32 = np.float32
+
+
+# ---------------------------------------------------------------------------------------------
+# dtype helpers (numpy has no bfloat16)
+# ---------------------------------------------------------------------------------------------
+def round_to_dtype(x32, tag):
+    """Round float32 values to `tag` precision (round-to-nearest-even), returned as float32."""
+    x32 = np.asarray(x32, dtype=F32)
+    if tag == "f32":
+        return x32
+    if tag == "f16":
+        return x32.astype(np.float16).astype(F32)
+    if tag == "bf16":
+        u = x32.view(np.uint32).astype(np.uint64)
+        rounded = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+        out = rounded.astype(np.uint32).view(F32)
+        return np.where(np.isnan(x32), x32, out)
+    raise ValueError(tag)
+
+
+# ---------------------------------------------------------------------------------------------
+# a1 / K1  Wanda statistic                      wanda_pruner.py:66-81
+# ---------------------------------------------------------------------------------------------
+def wanda_add_batch(scaler_row, nsamples, x, b):
+    """One WrappedGPT.add_batch call.  x: [T, C] float32 (inp.reshape(-1, C) up-cast, :74,:80).
+
+    scaler_row *= n/(n+b); n += b; scaler_row += ||x[:, c]||_2^2 / n      (:77-81)
+    The reference takes torch.norm(...)**2 (sqrt then square); the restatement sums squares in
+    float64 and rounds once -- the two differ by <= ~2 ulp, far inside 1e-5.
+    """
+    x = np.asarray(x)
+    sq = (x.astype(np.float64) ** 2).sum(axis=0)
+    out = scaler_row.astype(F32) * F32(nsamples / (nsamples + b))
+    nsamples += b
+    out = out + (sq.astype(F32) / F32(nsamples))
+    return out.astype(F32), nsamples
+
+
+# ---------------------------------------------------------------------------------------------
+# a2 / K2  DSnoT statistics                     dsnot_pruner.py:79-101
+# ---------------------------------------------------------------------------------------------
+def dsnot_add_batch(state, x, b):
+    """state: dict(scaler_row, sum_metric_row, mean, var, nsamples, ntokens); x: [T, C] float32.
+
+    mean/var are token-weighted running means of the per-call mean and BIASED variance (:89-93);
+    scaler_row / sum_metric_row are running means over samples of sum x^2 and sum x (:96-101).
+    """
+    x64 = np.asarray(x).astype(np.float64)
+    T = x64.shape[0]
+    mean_inp = x64.mean(axis=0)
+    var_inp = x64.var(axis=0)  # biased (unbiased=False, :90)
+    nt = state["ntokens"]
+    if nt == 0:
+        var, mean = var_inp, mean_inp
+    else:
+        var = (state["var"].astype(np.float64) * nt + var_inp * T) / (nt + T)
+        mean = (state["mean"].astype(np.float64) * nt + mean_inp * T) / (nt + T)
+    n = state["nsamples"]
+    ratio = F32(n / (n + b))
+    scaler = state["scaler_row"].astype(F32) * ratio
+    summ = state["sum_metric_row"].astype(F32) * ratio
+    n += b
+    scaler = scaler + (x64 ** 2).sum(axis=0).astype(F32) / F32(n)
+    summ = summ + x64.sum(axis=0).astype(F32) / F32(n)
+    return dict(scaler_row=scaler.astype(F32), sum_metric_row=summ.astype(F32), mean=mean.astype(F32),
+                var=var.astype(F32), nsamples=n, ntokens=nt + T)
+
+
+# ---------------------------------------------------------------------------------------------
+# a4 / K4-K6  Wanda score + selection            wanda_pruner.py:316-341
+# ---------------------------------------------------------------------------------------------
+def wanda_scores(W32, scaler_row):
+    """|W| * sqrt(scaler_row) in float32: one IEEE sqrt, one IEEE multiply (:318)."""
+    return (np.abs(W32.astype(F32)) * np.sqrt(scaler_row.astype(F32))[None, :]).astype(F32)
+
+
+def score_mean(S):
+    return float(S.astype(np.float64).mean())  # weight.importance_score (:320)
+
+
+def wanda_rowselect(W32, scaler_row, k):
+    """Unstructured LLM path: per row the k = int(C*p) smallest scores are pruned, stable order (:332-337).
+
+    Returns (keep_mask bool [R,C], pruned W float32, importance_score).
+    """
+    S = wanda_scores(W32, scaler_row)
+    order = np.argsort(S, axis=1, kind="stable")  # torch.sort(stable=True): ties -> lower column, NaN last
+    prune = np.zeros(S.shape, dtype=bool)
+    np.put_along_axis(prune, order[:, :k], True, axis=1)
+    Wp = np.where(prune, F32(0), W32.astype(F32))
+    return ~prune, Wp, score_mean(S)
+
+
+def nm_select_scores(S, n, m):
+    """Per group of m consecutive columns mark the n smallest; ties -> lower column.
+
+    The reference uses torch.topk(largest=False) (:329) whose tie-break is implementation-defined
+    (SURVEY F8); the build fixes 'lowest column wins', which equals the reference on tie-free groups.
+    """
+    R, C = S.shape
+    G = S.reshape(R, C // m, m)
+    order = np.argsort(G, axis=2, kind="stable")
+    prune = np.zeros(G.shape, dtype=bool)
+    np.put_along_axis(prune, order[:, :, :n], True, axis=2)
+    return prune.reshape(R, C)
+
+
+def wanda_nm(W32, scaler_row, n, m):
+    S = wanda_scores(W32, scaler_row)
+    prune = nm_select_scores(S, n, m)
+    Wp = np.where(prune, F32(0), W32.astype(F32))
+    return ~prune, Wp, score_mean(S)
+
+
+# ---------------------------------------------------------------------------------------------
+# a5 / K7  ViT whole-matrix threshold            wanda_pruner.py:682-683
+# ---------------------------------------------------------------------------------------------
+def wanda_threshold(W32, scaler_row, k_global):
+    """thres = sort(S.flatten())[k_global]; prune S < thres (strict, ties kept)."""
+    S = wanda_scores(W32, scaler_row)
+    thres = np.partition(S.ravel(), k_global)[k_global]
+    prune = S < thres
+    Wp = np.where(prune, F32(0), W32.astype(F32))
+    return ~prune, Wp, score_mean(S)
+
+
+# ---------------------------------------------------------------------------------------------
+# a8 / K14  SparseLoRA merge + re-mask           lora.py:384-387, train.py:634-637
+# ---------------------------------------------------------------------------------------------
+def sparselora_merge(W32, w_tag, A, B, scaling, keep_mask, remask=True):
+    """W <- round_w( W + (B@A * scaling) * mask ), then W[~mask] = 0.
+
+    fp32 math as torch does it: the rank-r product accumulates k ascending with fused multiply-adds
+    (emulated in float64, exact for one fma, then rounded), `* scaling` and the final add are
+    separately rounded float32 ops, one rounding to W's dtype.
+    """
+    R, C = W32.shape
+    acc = np.zeros((R, C), dtype=F32)
+    for kk in range(A.shape[0]):
+        prod = B[:, kk].astype(np.float64)[:, None] * A[kk].astype(np.float64)[None, :]
+        acc = (prod + acc.astype(np.float64)).astype(F32)  # fma(b, a, acc) rounded once
+    delta = (acc * F32(scaling)).astype(F32)
+    merged = round_to_dtype((W32.astype(F32) + delta).astype(F32), w_tag)
+    out = np.where(keep_mask, merged, F32(0) if remask else W32.astype(F32))
+    return out.astype(F32)
+
+
+# ---------------------------------------------------------------------------------------------
+# return_reorder_indice                          dsnot_pruner.py:1881-1925
+# ---------------------------------------------------------------------------------------------
+def return_reorder_indice(t):
+    """Positions of the negative entries in order, then positions of the positive entries reversed;
+    slots left over (zeros in the input) are filled with index 0, like the reference's inf->0 trick."""
+    t = np.asarray(t)
+    R, C = t.shape
+    out = np.zeros((R, C), dtype=np.int64)
+    for r in range(R):
+        neg = np.nonzero(t[r] < 0)[0]
+        pos = np.nonzero(t[r] > 0)[0]
+        row = np.zeros(C, dtype=np.int64)
+        row[:neg.size] += neg
+        # positive_value is sorted ascending with inf padding, then flipped: positives end up right-aligned
+        # in DEscending index order; inf -> 0
+        if pos.size:
+            row[C - pos.size:] += pos[::-1]
+        out[r] = row
+    return out

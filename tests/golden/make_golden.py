@@ -1,0 +1,200 @@
+"""Generates the committed golden fixtures by running the UNMODIFIED reference (loaded by path through
+oracle/ref_loader.py) on seeded inputs.  Needs /root/reference, so it only runs in the build container:
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+
+The fixtures pin oracle/oracle.py (tests/test_oracle_vs_golden.py, CPU) and the CUDA kernels
+(tests/test_gpu_parity.py, GPU box, where the reference itself is absent).
+Half / bfloat16 tensors are stored as float32 (exact up-cast) next to a dtype tag.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import ref_loader  # noqa: E402
+import toy_model  # noqa: E402
+
+TAG = {torch.float32: "f32", torch.float16: "f16", torch.bfloat16: "bf16"}
+
+
+def f32(t):
+    return t.detach().float().cpu().numpy().copy()   # copy: fp32 CPU tensors would alias the live state
+
+
+def packw(t):
+    """Weights in their own precision: bf16 as raw uint16 bits, f16 / f32 natively (see tests/golden_util.py)."""
+    t = t.detach().cpu()
+    if t.dtype == torch.bfloat16:
+        return t.view(torch.int16).numpy().view(np.uint16)
+    return t.numpy().copy()
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **arrs)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def act(shape, seed, dtype, C):
+    g = torch.Generator().manual_seed(seed)
+    gain = torch.exp(torch.rand(C, generator=g) * 2.77 - 1.386)      # LogUniform[0.25, 4]
+    off = torch.randn(C, generator=g) * 0.3
+    return (torch.randn(shape, generator=g) * gain + off).to(dtype)
+
+
+def gen_wanda_stats(ref):
+    out = {}
+    for tag, dtype in (("bf16", torch.bfloat16), ("f16", torch.float16), ("f32", torch.float32)):
+        C = 96
+        layer = nn.Linear(C, 8, bias=False)
+        w = ref.wanda.WrappedGPT(layer)
+        shapes = [(1, 40, C), (40, C), (3, 17, C), (1, 64, C)]   # 3-D b=1, 2-D, 3-D b=3, again b=1
+        for i, shp in enumerate(shapes):
+            x = act(shp, 10 + i, dtype, C)
+            w.add_batch(x, None)
+            out[f"{tag}_x{i}"] = f32(x)
+            out[f"{tag}_scaler{i}"] = f32(w.scaler_row)
+            out[f"{tag}_n{i}"] = np.int64(w.nsamples)
+    save("wanda_stats.npz", **out)
+
+
+def gen_dsnot_stats(ref):
+    out = {}
+    for tag, dtype in (("bf16", torch.bfloat16), ("f32", torch.float32)):
+        C = 96
+        layer = nn.Linear(C, 8, bias=False)
+        w = ref.dsnot.WrappedGPT(layer)
+        shapes = [(1, 40, C), (1, 40, C), (2, 24, C), (33, C)]
+        for i, shp in enumerate(shapes):
+            x = act(shp, 20 + i, dtype, C)
+            w.add_batch(x, None)
+            out[f"{tag}_x{i}"] = f32(x)
+            for k in ("scaler_row", "sum_metric_row", "mean", "var"):
+                out[f"{tag}_{k}{i}"] = f32(getattr(w, k)).reshape(-1)
+            out[f"{tag}_n{i}"] = np.int64(w.nsamples)
+            out[f"{tag}_ntok{i}"] = np.int64(w.ntokens)
+    save("dsnot_stats.npz", **out)
+
+
+def run_composite(ref, which, cfg, seed=0, **model_kw):
+    """Runs a reference composite pruner on the toy model, recording every per-layer wrapper."""
+    mod = getattr(ref, which)
+    recorded = []
+    orig = mod.WrappedGPT if which != "sparsegpt" else mod.SparseGPT
+
+    class Recording(orig):
+        def __init__(self, layer, *a, **k):
+            super().__init__(layer, *a, **k)
+            recorded.append(self)
+    if which == "sparsegpt":
+        mod.SparseGPT = Recording
+    else:
+        mod.WrappedGPT = Recording
+    try:
+        model = toy_model.ToyBlip(seed=seed, **model_kw).eval()
+        before = {n: p.detach().clone() for n, p in model.named_parameters()}
+        cls = {"wanda": "BLIPT5LayerWandaPruner", "dsnot": "BLIPT5LayerDSnoTPruner",
+               "sparsegpt": "BLIPT5LayerSparseGPTPruner"}[which]
+        pruner = getattr(mod, cls)(model=model, data_loader=toy_model.toy_batches(cfg["num_samples"],
+                                                                                  d_vit=model_kw.get("d_vit", 64)),
+                                   **cfg)
+        pruner.prune()
+    finally:
+        if which == "sparsegpt":
+            mod.SparseGPT = orig
+        else:
+            mod.WrappedGPT = orig
+    return model, before, recorded
+
+
+def collect_layers(model, before, recorded, stat_names, store_after=False):
+    out = {}
+    names = []
+    by_layer = {id(w.layer): w for w in recorded}
+    for name, module in model.named_modules():
+        if type(module) is nn.Linear and id(module) in by_layer:
+            w = by_layer[id(module)]
+            key = name.replace(".", "/")
+            names.append(key)
+            out[f"{key}|W_before"] = packw(before[name + ".weight"])
+            if store_after:
+                out[f"{key}|W_after"] = packw(module.weight)
+            else:   # Wanda / DSnoT only zero weights: W_after == W_before * mask, checked here, not stored
+                assert torch.equal(module.weight, before[name + ".weight"] * module.mask)
+            out[f"{key}|tag"] = np.array(TAG[module.weight.dtype])
+            out[f"{key}|mask"] = np.packbits(module.mask.cpu().numpy(), axis=1)
+            for s in stat_names:
+                v = getattr(w, s, None)
+                if v is not None:
+                    out[f"{key}|{s}"] = f32(v).reshape(-1)
+            sc = getattr(module.weight, "importance_score", None)
+            if sc is not None:
+                out[f"{key}|importance_score"] = np.float64(sc)
+    out["layers"] = np.array(names)
+    return out
+
+
+def gen_wanda_toy(ref):
+    # unstructured: LLM per-row path at 60 % (int() count), ViT whole-matrix path at 50 %
+    cfg = toy_model.pruner_cfg(0.4, 0.5)
+    model, before, rec = run_composite(ref, "wanda", cfg)
+    save("wanda_toy_unstructured.npz", **collect_layers(model, before, rec, ["scaler_row"]))
+    for n, m in ((2, 4), (4, 8)):
+        cfg = toy_model.pruner_cfg(0.5, 0.5, prune_n=n, prune_m=m)
+        model, before, rec = run_composite(ref, "wanda", cfg)
+        save(f"wanda_toy_{n}of{m}.npz", **collect_layers(model, before, rec, ["scaler_row"]))
+
+
+def gen_lora_merge(ref):
+    out = {}
+    torch.manual_seed(5)
+    for tag, dtype in (("bf16", torch.bfloat16), ("f16", torch.float16), ("f32", torch.float32)):
+        for r in (2, 4, 8):
+            lin = ref.lora.Linear(72, 40, r=r, lora_alpha=16, bias=False)
+            lin.weight.data = (torch.randn(40, 72) * 0.05).to(dtype)
+            lin.lora_A.weight.data = torch.randn(r, 72) * 0.1
+            lin.lora_B.weight.data = torch.randn(40, r) * 0.1
+            lin.mask = torch.rand(40, 72) < 0.5
+            lin.sparse = True
+            key = f"{tag}_r{r}"
+            out[f"{key}|W_before"] = f32(lin.weight)
+            out[f"{key}|A"] = f32(lin.lora_A.weight)
+            out[f"{key}|B"] = f32(lin.lora_B.weight)
+            out[f"{key}|mask"] = lin.mask.numpy().copy()
+            out[f"{key}|scaling"] = np.float64(lin.scaling)
+            lin.merge()                                       # lora.py:384-387
+            out[f"{key}|W_merged"] = f32(lin.weight)
+            lin.weight.data[~lin.mask] = 0                    # train.py:634-637
+            out[f"{key}|W_remasked"] = f32(lin.weight)
+    save("lora_merge.npz", **out)
+
+
+def gen_reorder(ref):
+    doc = torch.tensor([[1., -2., 3.], [-2., 2., -4.], [5., 6., -7.], [-6., -7., -4.]])
+    g = torch.Generator().manual_seed(3)
+    rnd = torch.randn(16, 37, generator=g)
+    rnd[rnd.abs() < 0.2] = 0.0
+    save("reorder.npz", doc_in=doc.numpy(), doc_out=ref.dsnot.return_reorder_indice(doc).numpy(),
+         rnd_in=rnd.numpy(), rnd_out=ref.dsnot.return_reorder_indice(rnd).numpy())
+
+
+def main():
+    torch.set_num_threads(8)
+    ref = ref_loader.load()
+    only = set(sys.argv[1:])
+    gens = dict(wanda_stats=gen_wanda_stats, dsnot_stats=gen_dsnot_stats, wanda_toy=gen_wanda_toy,
+                lora_merge=gen_lora_merge, reorder=gen_reorder)
+    for name, fn in gens.items():
+        if not only or name in only:
+            fn(ref)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,105 @@
+"""CPU: oracle/oracle.py replayed against the committed fixtures the reference produced
+(tests/golden/make_golden.py).  This is what pins the oracle; the GPU tests then pin the kernels to it."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+from oracle import oracle
+
+
+def rel_inf(a, b):
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("tag", ["bf16", "f16", "f32"])
+def test_wanda_stats(tag):
+    g = gu.load("wanda_stats.npz")
+    scaler, n = np.zeros(96, np.float32), 0
+    for i in range(4):
+        x = g[f"{tag}_x{i}"]
+        b = 1 if x.ndim == 2 else x.shape[0]
+        scaler, n = oracle.wanda_add_batch(scaler, n, x.reshape(-1, x.shape[-1]), b)
+        assert n == int(g[f"{tag}_n{i}"])
+        assert rel_inf(scaler, g[f"{tag}_scaler{i}"]) < 1e-6     # north_star: 1e-5 relative
+
+
+@pytest.mark.parametrize("tag", ["bf16", "f32"])
+def test_dsnot_stats(tag):
+    g = gu.load("dsnot_stats.npz")
+    st = dict(scaler_row=np.zeros(96, np.float32), sum_metric_row=np.zeros(96, np.float32),
+              mean=np.zeros(96, np.float32), var=np.zeros(96, np.float32), nsamples=0, ntokens=0)
+    for i in range(4):
+        x = g[f"{tag}_x{i}"]
+        b = 1 if x.ndim == 2 else x.shape[0]
+        st = oracle.dsnot_add_batch(st, x.reshape(-1, x.shape[-1]), b)
+        assert st["nsamples"] == int(g[f"{tag}_n{i}"]) and st["ntokens"] == int(g[f"{tag}_ntok{i}"])
+        for k in ("scaler_row", "sum_metric_row", "mean", "var"):
+            assert rel_inf(st[k], g[f"{tag}_{k}{i}"]) < 2e-6, (k, i)
+
+
+def _is_vit(key):
+    return key.startswith("visual_encoder")
+
+
+def test_wanda_unstructured_masks_bit_exact():
+    g = gu.load("wanda_toy_unstructured.npz")
+    for key in g["layers"]:
+        L = gu.layer(g, key)
+        R, C = L["W_before"].shape
+        if _is_vit(key):     # whole-matrix threshold, 50 %
+            keep, Wp, mean = oracle.wanda_threshold(L["W_before"], L["scaler_row"], int(R * C * 0.5))
+        else:                # per-row, keep 0.4 -> sparsity 1 - 0.4
+            keep, Wp, mean = oracle.wanda_rowselect(L["W_before"], L["scaler_row"], int(C * (1 - 0.4)))
+        assert np.array_equal(keep, L["mask"]), key
+        assert np.array_equal(Wp, L["W_after"]), key
+        assert abs(mean - float(L["importance_score"])) <= 2e-6 * abs(mean), key
+
+
+@pytest.mark.parametrize("n,m", [(2, 4), (4, 8)])
+def test_wanda_nm_masks(n, m):
+    g = gu.load(f"wanda_toy_{n}of{m}.npz")
+    for key in g["layers"]:
+        L = gu.layer(g, key)
+        keep, Wp, _ = oracle.wanda_nm(L["W_before"], L["scaler_row"], n, m)
+        S = oracle.wanda_scores(L["W_before"], L["scaler_row"])
+        G = S.reshape(S.shape[0], -1, m)
+        tie_free = np.array([[len(set(row.tolist())) == m for row in grp] for grp in G])
+        # bit-exact wherever the group has no tied scores (torch.topk's tie-break is unspecified);
+        # on tied groups the pruned SCORE multiset must still agree
+        km, kr = keep.reshape(G.shape), L["mask"].reshape(G.shape)
+        assert np.array_equal(km[tie_free], kr[tie_free]), key
+        assert (~km).sum(-1).min() == n and (~km).sum(-1).max() == n
+        tied = ~tie_free
+        if tied.any():
+            a = np.sort(np.where(~km, G, np.inf)[tied], axis=-1)
+            b = np.sort(np.where(~kr, G, np.inf)[tied], axis=-1)
+            assert np.array_equal(a, b), key
+
+
+def test_lora_merge():
+    g = gu.load("lora_merge.npz")
+    worst = 0
+    for tag in ("bf16", "f16", "f32"):
+        for r in (2, 4, 8):
+            k = f"{tag}_r{r}"
+            mask = g[f"{k}|mask"]
+            scaling = float(g[f"{k}|scaling"])
+            merged = oracle.sparselora_merge(g[f"{k}|W_before"], tag, g[f"{k}|A"], g[f"{k}|B"], scaling, mask, remask=False)
+            remasked = oracle.sparselora_merge(g[f"{k}|W_before"], tag, g[f"{k}|A"], g[f"{k}|B"], scaling, mask, remask=True)
+            ref_m, ref_r = g[f"{k}|W_merged"], g[f"{k}|W_remasked"]
+            assert np.array_equal(remasked == 0, ref_r == 0) or tag == "f32"
+            assert np.array_equal(merged[~mask], ref_m[~mask])        # untouched outside the mask
+            assert np.array_equal(remasked[~mask], np.zeros_like(remasked[~mask]))
+            # the rank-r product's summation order is a BLAS detail: allow 1 ulp of the W dtype on rare entries
+            ulp = {"bf16": 2.0 ** -8, "f16": 2.0 ** -11, "f32": 2.0 ** -23}[tag]
+            err = np.abs(merged - ref_m) / np.maximum(np.abs(ref_m), 1e-3)
+            assert err.max() <= 2 * ulp, (k, err.max())
+            worst = max(worst, float((merged != ref_m).mean()))
+    assert worst < 0.02
+
+
+def test_return_reorder_indice_docstring_vector():
+    g = gu.load("reorder.npz")
+    assert np.array_equal(oracle.return_reorder_indice(g["doc_in"]), g["doc_out"])
+    assert np.array_equal(g["doc_out"], np.array([[1, 2, 0], [0, 2, 1], [2, 1, 0], [0, 1, 2]]))  # dsnot_pruner.py:1882-1893
+    assert np.array_equal(oracle.return_reorder_indice(g["rnd_in"]), g["rnd_out"])

@@ -1,0 +1,287 @@
+// K1 / K2: per-input-channel calibration statistics, one streaming pass over the activations.
+//
+// Replaces WrappedGPT.add_batch of the reference:
+//   Wanda  lavis/compression/pruners/wanda_pruner.py:66-81   (scaler_row)
+//   DSnoT  lavis/compression/pruners/dsnot_pruner.py:79-101  (scaler_row, sum_metric_row, mean, var)
+//
+// Layout: x is [T, C] row-major (what the reference reaches with inp.reshape(-1, C); its .t() is a
+// view, so the reduction there runs over a strided dimension).  Here a CTA owns a tile of
+// 64 x 16 B columns and a contiguous chunk of rows; every warp reads 512 contiguous bytes per row,
+// 4 rows in flight per thread, fp32 partials in registers.  Partials of all row chunks go to the
+// workspace; the last CTA to finish a column tile (ticket counter) combines them in fp64 in a
+// fixed order, so the result is deterministic, and applies the running-average update.
+//
+// HBM-bound: algorithmic bytes = T*C*sizeof(x) (+ a few vectors of C floats).
+#include "common.cuh"
+
+namespace vlmc {
+
+constexpr int kCX = 64;   // column-vector lanes per CTA
+constexpr int kRY = 4;    // row lanes per CTA
+constexpr int kStatsThreads = kCX * kRY;
+constexpr int kUnroll = 4;
+
+struct StatsParams {
+  const void* x;
+  int64_t ldx;
+  int C;
+  int64_t S;             // rows per segment
+  int64_t nseg;
+  int chunks_per_seg;
+  int rows_per_chunk;
+  float* part;           // [kinds][nchunks][C]
+  unsigned int* tickets; // one per column tile, zero on entry, zero on exit
+  // running-average state
+  float* scaler_row;
+  float* sum_row;
+  float* mean;
+  float* var;
+  double n_before, b_per_seg, ntok_before;
+};
+
+template <typename T, bool DSNOT>
+__global__ void __launch_bounds__(kStatsThreads)
+colstats_kernel(const StatsParams p) {
+  constexpr int V = Elem<T>::kVec;
+  const int tx = threadIdx.x % kCX;
+  const int ty = threadIdx.x / kCX;
+  const int col0 = (blockIdx.x * kCX + tx) * V;
+  const bool col_ok = col0 < p.C;
+  const int64_t nchunks = p.nseg * p.chunks_per_seg;
+  const int64_t chunk = blockIdx.y;
+  const int64_t seg = chunk / p.chunks_per_seg;
+  const int64_t cis = chunk % p.chunks_per_seg;
+  const int64_t r0 = seg * p.S + cis * (int64_t)p.rows_per_chunk;
+  int64_t r1 = r0 + p.rows_per_chunk;
+  const int64_t seg_end = (seg + 1) * p.S;
+  if (r1 > seg_end) r1 = seg_end;
+
+  const T* xp = reinterpret_cast<const T*>(p.x) + col0;
+
+  float a0[V], a1[V], x0[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { a0[i] = 0.f; a1[i] = 0.f; x0[i] = 0.f; }
+
+  if (col_ok && r0 < r1) {
+    if (DSNOT) {
+      // shift by the chunk's first row: keeps sum(d^2) - sum(d)^2/n free of cancellation
+      uint4 v = ld_stream(xp + r0 * p.ldx);
+      Elem<T>::unpack(v, x0);
+    }
+    int64_t r = r0 + ty;
+    for (; r + (kUnroll - 1) * kRY < r1; r += kUnroll * kRY) {
+      uint4 v[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream(xp + (r + u * kRY) * p.ldx);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        float f[V];
+        Elem<T>::unpack(v[u], f);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          if (DSNOT) {
+            float d = f[i] - x0[i];
+            a0[i] += d;
+            a1[i] = fmaf(d, d, a1[i]);
+          } else {
+            a1[i] = fmaf(f[i], f[i], a1[i]);
+          }
+        }
+      }
+    }
+    for (; r < r1; r += kRY) {
+      uint4 v = ld_stream(xp + r * p.ldx);
+      float f[V];
+      Elem<T>::unpack(v, f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        if (DSNOT) {
+          float d = f[i] - x0[i];
+          a0[i] += d;
+          a1[i] = fmaf(d, d, a1[i]);
+        } else {
+          a1[i] = fmaf(f[i], f[i], a1[i]);
+        }
+      }
+    }
+  }
+
+  // combine the kRY row lanes of one column through shared memory
+  __shared__ float red[2][kRY][kCX * V + 4];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    red[1][ty][tx * V + i] = a1[i];
+    if (DSNOT) red[0][ty][tx * V + i] = a0[i];
+  }
+  __syncthreads();
+  if (ty == 0 && col_ok) {
+    float* part_sq = p.part + (size_t)chunk * p.C + col0;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float s1 = 0.f;
+#pragma unroll
+      for (int y = 0; y < kRY; ++y) s1 += red[1][y][tx * V + i];
+      part_sq[i] = s1;
+    }
+    if (DSNOT) {
+      float* part_s = p.part + ((size_t)nchunks + chunk) * p.C + col0;
+      float* part_x0 = p.part + ((size_t)2 * nchunks + chunk) * p.C + col0;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float s0 = 0.f;
+#pragma unroll
+        for (int y = 0; y < kRY; ++y) s0 += red[0][y][tx * V + i];
+        part_s[i] = s0;
+        part_x0[i] = x0[i];
+      }
+    }
+  }
+
+  // ticket: the last CTA of this column tile finalises
+  __shared__ unsigned int s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[blockIdx.x], 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned int)(nchunks - 1)) return;
+  __threadfence();
+
+  const double n_after = p.n_before + p.b_per_seg * (double)p.nseg;
+  const float ratio = (float)(p.n_before / n_after);
+  const float n_after_f = (float)n_after;
+  const int tile_c0 = blockIdx.x * kCX * V;
+  for (int c = tile_c0 + threadIdx.x; c < tile_c0 + kCX * V && c < p.C; c += kStatsThreads) {
+    if (!DSNOT) {
+      double tot = 0.0;
+      for (int64_t k = 0; k < nchunks; ++k) tot += (double)__ldcg(p.part + (size_t)k * p.C + c);
+      // wanda_pruner.py:77,81 -- scaler_row *= n/(n+b); scaler_row += ||x||^2 / (n+b)
+      float s = __fmul_rn(p.scaler_row[c], ratio);
+      p.scaler_row[c] = __fadd_rn(s, __fdiv_rn((float)tot, n_after_f));
+    } else {
+      double tot_sq = 0.0, tot_s = 0.0, var_acc = 0.0, mean_acc = 0.0;
+      for (int64_t sg = 0; sg < p.nseg; ++sg) {
+        // Chan merge of this segment's chunks -> per-call mean and biased variance
+        double n = 0.0, mu = 0.0, m2 = 0.0;
+        for (int ck = 0; ck < p.chunks_per_seg; ++ck) {
+          const int64_t k = sg * p.chunks_per_seg + ck;
+          int64_t rr0 = ck * (int64_t)p.rows_per_chunk;
+          int64_t rr1 = rr0 + p.rows_per_chunk;
+          if (rr1 > p.S) rr1 = p.S;
+          if (rr1 <= rr0) continue;
+          const double nb = (double)(rr1 - rr0);
+          const double sd2 = (double)__ldcg(p.part + (size_t)k * p.C + c);
+          const double sd = (double)__ldcg(p.part + ((size_t)nchunks + k) * p.C + c);
+          const double xs = (double)__ldcg(p.part + ((size_t)2 * nchunks + k) * p.C + c);
+          const double mub = xs + sd / nb;
+          const double m2b = sd2 - sd * sd / nb;
+          tot_s += sd + nb * xs;
+          tot_sq += sd2 + 2.0 * xs * sd + nb * xs * xs;
+          const double nn = n + nb;
+          const double delta = mub - mu;
+          m2 += m2b + delta * delta * n * nb / nn;
+          mu += delta * nb / nn;
+          n = nn;
+        }
+        var_acc += m2;           // = S * biased var of the call
+        mean_acc += mu * n;
+      }
+      // dsnot_pruner.py:89-93 -- token-weighted running means of the per-call mean / variance
+      const double tok_call = (double)p.S * (double)p.nseg;
+      const double tok_after = p.ntok_before + tok_call;
+      if (p.ntok_before == 0.0) {
+        p.var[c] = (float)(var_acc / tok_call);
+        p.mean[c] = (float)(mean_acc / tok_call);
+      } else {
+        p.var[c] = (float)(((double)p.var[c] * p.ntok_before + var_acc) / tok_after);
+        p.mean[c] = (float)(((double)p.mean[c] * p.ntok_before + mean_acc) / tok_after);
+      }
+      // dsnot_pruner.py:96-101
+      float s = __fmul_rn(p.scaler_row[c], ratio);
+      p.scaler_row[c] = __fadd_rn(s, __fdiv_rn((float)tot_sq, n_after_f));
+      float m = __fmul_rn(p.sum_row[c], ratio);
+      p.sum_row[c] = __fadd_rn(m, __fdiv_rn((float)tot_s, n_after_f));
+    }
+  }
+  if (threadIdx.x == 0) p.tickets[blockIdx.x] = 0u;  // leave the workspace clean
+}
+
+struct StatsPlan {
+  int coltiles, chunks_per_seg, rows_per_chunk;
+  int64_t nchunks;
+  size_t bytes;
+};
+
+static StatsPlan plan_stats(int dtype, int64_t nseg, int64_t S, int C, int kinds) {
+  StatsPlan pl;
+  const int V = dtype == VLMC_F32 ? 4 : 8;
+  pl.coltiles = (C + kCX * V - 1) / (kCX * V);
+  const int64_t target_ctas = (int64_t)kNumSMs * 8;  // 8 x 256 threads resident per SM
+  int64_t want = target_ctas / pl.coltiles;
+  if (want < 1) want = 1;
+  int64_t cps = want / nseg;
+  if (cps < 1) cps = 1;
+  const int64_t min_rows = kRY * kUnroll * 2;
+  int64_t max_cps = (S + min_rows - 1) / min_rows;
+  if (cps > max_cps) cps = max_cps;
+  if (cps < 1) cps = 1;
+  pl.rows_per_chunk = (int)((S + cps - 1) / cps);
+  pl.chunks_per_seg = (int)((S + pl.rows_per_chunk - 1) / pl.rows_per_chunk);
+  pl.nchunks = nseg * pl.chunks_per_seg;
+  pl.bytes = VLMC_WS_COUNTER_BYTES + (size_t)kinds * pl.nchunks * C * sizeof(float);
+  return pl;
+}
+
+size_t stats_workspace_bytes(int dsnot, int64_t T, int C, int64_t nseg) {
+  if (nseg < 1) nseg = 1;
+  // dtype only changes the tile count; take the fp32 plan (more tiles, fewer chunks) as the bound
+  size_t a = plan_stats(VLMC_F32, nseg, T / nseg, C, dsnot ? 3 : 1).bytes;
+  size_t b = plan_stats(VLMC_F16, nseg, T / nseg, C, dsnot ? 3 : 1).bytes;
+  return a > b ? a : b;
+}
+
+template <bool DSNOT>
+static int launch_stats(const void* x, int dtype, int64_t nseg, int64_t S, int C, int64_t ldx,
+                        float* scaler_row, float* sum_row, float* mean, float* var,
+                        double n_before, double b_per_seg, double ntok_before,
+                        void* ws, size_t ws_bytes, void* stream) {
+  if (!x || !scaler_row || !ws || nseg < 1 || S < 1 || C < 1 || ldx < C) return VLMC_ERR_BAD_ARG;
+  if (DSNOT && (!sum_row || !mean || !var)) return VLMC_ERR_BAD_ARG;
+  if (dtype != VLMC_F32 && dtype != VLMC_F16 && dtype != VLMC_BF16) return VLMC_ERR_BAD_ARG;
+  const int V = dtype == VLMC_F32 ? 4 : 8;
+  if (C % V != 0 || ldx % V != 0 || ((uintptr_t)x & 15) != 0) return VLMC_ERR_UNSUPPORTED;
+  if (!is_device_ptr(x) || !is_device_ptr(scaler_row) || !is_device_ptr(ws)) return VLMC_ERR_NOT_DEVICE;
+  StatsPlan pl = plan_stats(dtype, nseg, S, C, DSNOT ? 3 : 1);
+  if (ws_bytes < pl.bytes) return VLMC_ERR_WORKSPACE;
+  if (pl.coltiles * sizeof(unsigned int) > VLMC_WS_COUNTER_BYTES) return VLMC_ERR_UNSUPPORTED;
+  if (pl.nchunks > 65535) return VLMC_ERR_UNSUPPORTED;
+
+  StatsParams p;
+  p.x = x; p.ldx = ldx; p.C = C; p.S = S; p.nseg = nseg;
+  p.chunks_per_seg = pl.chunks_per_seg; p.rows_per_chunk = pl.rows_per_chunk;
+  p.tickets = reinterpret_cast<unsigned int*>(ws);
+  p.part = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + VLMC_WS_COUNTER_BYTES);
+  p.scaler_row = scaler_row; p.sum_row = sum_row; p.mean = mean; p.var = var;
+  p.n_before = n_before; p.b_per_seg = b_per_seg; p.ntok_before = ntok_before;
+
+  dim3 grid(pl.coltiles, (unsigned)pl.nchunks);
+  cudaStream_t st = (cudaStream_t)stream;
+  VLMC_DISPATCH_DTYPE(dtype, (colstats_kernel<scalar_t, DSNOT><<<grid, kStatsThreads, 0, st>>>(p)));
+  return check_launch();
+}
+
+}  // namespace vlmc
+
+extern "C" int vlmc_sqnorm_accum(const void* x, int dtype, int64_t T, int C, int64_t ldx,
+                                 float* scaler_row, double n_before, double b,
+                                 void* ws, size_t ws_bytes, void* stream) {
+  return vlmc::launch_stats<false>(x, dtype, 1, T, C, ldx, scaler_row, nullptr, nullptr, nullptr,
+                                   n_before, b, 0.0, ws, ws_bytes, stream);
+}
+
+extern "C" int vlmc_dsnot_stats(const void* x, int dtype, int64_t nseg, int64_t S, int C, int64_t ldx,
+                                float* scaler_row, float* sum_row, float* mean, float* var,
+                                double n_before, double b_per_seg, double ntok_before,
+                                void* ws, size_t ws_bytes, void* stream) {
+  return vlmc::launch_stats<true>(x, dtype, nseg, S, C, ldx, scaler_row, sum_row, mean, var,
+                                  n_before, b_per_seg, ntok_before, ws, ws_bytes, stream);
+}

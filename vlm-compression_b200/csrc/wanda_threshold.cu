@@ -1,0 +1,297 @@
+// K7: Wanda score + whole-matrix threshold (ViT path).
+//
+// Replaces lavis/compression/pruners/wanda_pruner.py:682-683
+//   thres = torch.sort(W_metric.flatten())[0][int(numel * p)] ;  W_mask = W_metric < thres
+// i.e. a full device sort of up to 8.65 M keys, by an exact counting select: every pass counts the
+// scores below 8 pivots (3 quartile points that guarantee a 4x shrink of the bracket + 5
+// interpolated ones that close in on the target rank); W (<= 17 MB) stays L2-resident between
+// passes.  All CTAs replay the pass history from the workspace, so there is no host
+// synchronisation between launches; passes after convergence exit immediately.
+#include "common.cuh"
+
+namespace vlmc {
+
+int launch_mean_finalize(const float* part, int n, double denom, float* out, cudaStream_t st);
+
+constexpr int kThrThreads = 256;
+constexpr int kThrPasses = 18;
+constexpr int kThrPivots = 8;
+constexpr int kThrCap = 2048;
+
+typedef unsigned long long ull;
+
+struct ThrState {
+  ull counts[kThrPasses][kThrPivots];
+  unsigned int cand_cnt;
+  uint32_t v;
+  uint32_t cand[kThrCap];
+};
+
+struct Bracket { uint32_t lo, hi; ull glo, ghi; };
+
+__device__ __forceinline__ bool thr_done(const Bracket& b) {
+  return (b.ghi - b.glo) <= (ull)kThrCap || (b.hi - b.lo) == 1u;
+}
+
+__device__ __forceinline__ uint32_t thr_clamp(double x, uint32_t lo, uint32_t hi) {
+  if (!(x > (double)lo + 1.0)) return lo + 1;
+  if (!(x < (double)hi - 1.0)) return hi - 1;
+  return (uint32_t)x;
+}
+
+__device__ void thr_pivots(const Bracket& b, ull k, uint32_t* p) {
+  const double w = (double)(b.hi - b.lo), lo = (double)b.lo;
+  p[0] = thr_clamp(lo + 0.25 * w, b.lo, b.hi);
+  p[1] = thr_clamp(lo + 0.50 * w, b.lo, b.hi);
+  p[2] = thr_clamp(lo + 0.75 * w, b.lo, b.hi);
+  const double f = ((double)(k - b.glo) - 0.5) / (double)(b.ghi - b.glo);
+  const double e = lo + f * w;
+  p[3] = thr_clamp(e - w * 0.0625, b.lo, b.hi);
+  p[4] = thr_clamp(e - w * (1.0 / 256.0), b.lo, b.hi);
+  p[5] = thr_clamp(e, b.lo, b.hi);
+  p[6] = thr_clamp(e + w * (1.0 / 256.0), b.lo, b.hi);
+  p[7] = thr_clamp(e + w * 0.0625, b.lo, b.hi);
+}
+
+// state of the search after `npass` completed passes
+__device__ Bracket thr_replay(const ThrState* st, int npass, ull n, ull k) {
+  Bracket b{0u, 0xffffffffu, 0ull, n};
+  for (int ps = 0; ps < npass; ++ps) {
+    if (thr_done(b)) break;
+    uint32_t p[kThrPivots];
+    thr_pivots(b, k, p);
+    for (int i = 0; i < kThrPivots; ++i) {
+      const ull c = st->counts[ps][i];
+      if (c <= k - 1) { if (p[i] > b.lo) { b.lo = p[i]; b.glo = c; } }
+      else            { if (p[i] < b.hi) { b.hi = p[i]; b.ghi = c; } }
+    }
+  }
+  return b;
+}
+
+__global__ void sqrt_kernel(const float* __restrict__ s, float* __restrict__ sq, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) sq[c] = __fsqrt_rn(s[c]);
+}
+
+template <typename T>
+__device__ __forceinline__ void load_keys(const T* W, int64_t ldw, int cvecs, int64_t vec,
+                                          const float* __restrict__ sq, uint32_t* keys, float* fsum) {
+  constexpr int V = Elem<T>::kVec;
+  const int64_t row = vec / cvecs;
+  const int col = (int)(vec % cvecs) * V;
+  uint4 v = *reinterpret_cast<const uint4*>(W + row * ldw + col);
+  float f[V];
+  Elem<T>::unpack(v, f);
+  const float4* sp = reinterpret_cast<const float4*>(sq + col);
+  float sv[V];
+#pragma unroll
+  for (int q = 0; q < V / 4; ++q) {
+    float4 t = __ldg(sp + q);
+    sv[4 * q] = t.x; sv[4 * q + 1] = t.y; sv[4 * q + 2] = t.z; sv[4 * q + 3] = t.w;
+  }
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    const float s = __fmul_rn(fabsf(f[e]), sv[e]);
+    keys[e] = __float_as_uint(s);
+    if (fsum) *fsum += s;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThrThreads)
+thr_count_kernel(const T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ sq,
+                 ull k, ThrState* st, int pass) {
+  constexpr int V = Elem<T>::kVec;
+  __shared__ uint32_t sp[kThrPivots];
+  __shared__ int s_done;
+  __shared__ unsigned int s_cnt[kThrPivots];
+  const ull n = (ull)R * (ull)C;
+  if (threadIdx.x == 0) {
+    Bracket b = thr_replay(st, pass, n, k);
+    s_done = thr_done(b) ? 1 : 0;
+    if (!s_done) { uint32_t p[kThrPivots]; thr_pivots(b, k, p); for (int i = 0; i < kThrPivots; ++i) sp[i] = p[i]; }
+  }
+  if (threadIdx.x < kThrPivots) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  if (s_done) return;
+  uint32_t p[kThrPivots];
+#pragma unroll
+  for (int i = 0; i < kThrPivots; ++i) p[i] = sp[i];
+  unsigned int cnt[kThrPivots] = {};
+  const int cvecs = C / V;
+  const int64_t nvec = (int64_t)R * cvecs;
+  for (int64_t vec = (int64_t)blockIdx.x * kThrThreads + threadIdx.x; vec < nvec;
+       vec += (int64_t)gridDim.x * kThrThreads) {
+    uint32_t keys[V];
+    load_keys<T>(W, ldw, cvecs, vec, sq, keys, nullptr);
+#pragma unroll
+    for (int e = 0; e < V; ++e)
+#pragma unroll
+      for (int i = 0; i < kThrPivots; ++i) cnt[i] += keys[e] < p[i] ? 1u : 0u;
+  }
+#pragma unroll
+  for (int i = 0; i < kThrPivots; ++i) {
+    unsigned int c = __reduce_add_sync(0xffffffffu, cnt[i]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt[i], c);
+  }
+  __syncthreads();
+  if (threadIdx.x < kThrPivots) atomicAdd(&st->counts[pass][threadIdx.x], (ull)s_cnt[threadIdx.x]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThrThreads)
+thr_gather_kernel(const T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ sq,
+                  ull k, ThrState* st) {
+  constexpr int V = Elem<T>::kVec;
+  __shared__ uint32_t s_lo, s_hi;
+  __shared__ int s_skip;
+  if (threadIdx.x == 0) {
+    Bracket b = thr_replay(st, kThrPasses, (ull)R * (ull)C, k);
+    s_lo = b.lo; s_hi = b.hi;
+    s_skip = (b.hi - b.lo == 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_skip) return;
+  const uint32_t lo = s_lo, hi = s_hi;
+  const int cvecs = C / V;
+  const int64_t nvec = (int64_t)R * cvecs;
+  for (int64_t vec = (int64_t)blockIdx.x * kThrThreads + threadIdx.x; vec < nvec;
+       vec += (int64_t)gridDim.x * kThrThreads) {
+    uint32_t keys[V];
+    load_keys<T>(W, ldw, cvecs, vec, sq, keys, nullptr);
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      if (keys[e] >= lo && keys[e] < hi) {
+        const unsigned int slot = atomicAdd(&st->cand_cnt, 1u);
+        if (slot < (unsigned)kThrCap) st->cand[slot] = keys[e];
+      }
+    }
+  }
+}
+
+// one CTA: the (k-1-glo)-th smallest candidate is the threshold value
+__global__ void __launch_bounds__(1024)
+thr_resolve_kernel(int R, int C, ull k, ThrState* st) {
+  __shared__ uint32_t s_cand[kThrCap];
+  __shared__ Bracket s_b;
+  if (threadIdx.x == 0) s_b = thr_replay(st, kThrPasses, (ull)R * (ull)C, k);
+  __syncthreads();
+  const Bracket b = s_b;
+  if (b.hi - b.lo == 1u) {
+    if (threadIdx.x == 0) st->v = b.lo;
+    return;
+  }
+  const int m = (int)(b.ghi - b.glo);
+  for (int i = threadIdx.x; i < m; i += blockDim.x) s_cand[i] = st->cand[i];
+  __syncthreads();
+  const int target = (int)(k - 1 - b.glo);
+  for (int t = threadIdx.x; t < m; t += blockDim.x) {
+    const uint32_t kt = s_cand[t];
+    int less = 0, leq = 0;
+    for (int j = 0; j < m; ++j) { less += s_cand[j] < kt ? 1 : 0; leq += s_cand[j] <= kt ? 1 : 0; }
+    if (less <= target && target < leq) st->v = kt;  // all writers store the same value
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThrThreads)
+thr_apply_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ sq,
+                 const ThrState* st, int zero_w, uint8_t* __restrict__ mask, int64_t ldm,
+                 float* __restrict__ part_sum) {
+  constexpr int V = Elem<T>::kVec;
+  const uint32_t v = st->v;
+  const int cvecs = C / V;
+  const int64_t nvec = (int64_t)R * cvecs;
+  float lsum = 0.f;
+  for (int64_t vec = (int64_t)blockIdx.x * kThrThreads + threadIdx.x; vec < nvec;
+       vec += (int64_t)gridDim.x * kThrThreads) {
+    uint32_t keys[V];
+    load_keys<T>(W, ldw, cvecs, vec, sq, keys, &lsum);
+    const int64_t row = vec / cvecs;
+    const int col = (int)(vec % cvecs) * V;
+    uint32_t mb[V / 4] = {};
+    bool any = false;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const bool pr = keys[e] < v;   // strict: ties with the threshold are kept (:683)
+      any |= pr;
+      mb[e / 4] |= (pr ? 0u : 1u) << (8 * (e % 4));
+    }
+    uint8_t* mp = mask + row * ldm + col;
+    if (V == 8) st_stream8(mp, make_uint2(mb[0], mb[V / 4 - 1]));
+    else st_stream4(mp, mb[0]);
+    if (zero_w && any) {
+      T* wp = W + row * ldw + col;
+      uint4 wv = *reinterpret_cast<const uint4*>(wp);
+      uint32_t* wr = reinterpret_cast<uint32_t*>(&wv);
+      if (sizeof(T) == 4) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) if (keys[e] < v) wr[e] = 0u;
+      } else {
+#pragma unroll
+        for (int e = 0; e < V; ++e) if (keys[e] < v) wr[e / 2] &= (e & 1) ? 0x0000ffffu : 0xffff0000u;
+      }
+      st_stream(wp, wv);
+    }
+  }
+  __shared__ float fred[kThrThreads / 32];
+  lsum = warp_sum(lsum);
+  if ((threadIdx.x & 31) == 0) fred[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < kThrThreads / 32; ++w) s += fred[w];
+    part_sum[blockIdx.x] = s;
+  }
+}
+
+size_t threshold_workspace_bytes(int R, int C) {
+  return VLMC_WS_COUNTER_BYTES + align_up((size_t)C * sizeof(float), 256) +
+         align_up((size_t)kNumSMs * 8 * sizeof(float), 256) + align_up(sizeof(ThrState), 256);
+}
+
+}  // namespace vlmc
+
+extern "C" int vlmc_wanda_threshold(void* W, int dtype, int R, int C, int64_t ldw,
+                                    const float* scaler_row, int64_t k_global, int zero_w,
+                                    uint8_t* keep_mask, int64_t ldm, float* score_mean,
+                                    void* ws, size_t ws_bytes, void* stream) {
+  using namespace vlmc;
+  if (!W || !scaler_row || !keep_mask || !ws || R < 1 || C < 1 || ldw < C || ldm < C) return VLMC_ERR_BAD_ARG;
+  if (dtype != VLMC_F32 && dtype != VLMC_F16 && dtype != VLMC_BF16) return VLMC_ERR_BAD_ARG;
+  if (k_global < 0 || k_global >= (int64_t)R * C) return VLMC_ERR_BAD_ARG;  // sorted[k] must exist
+  const int V = dtype == VLMC_F32 ? 4 : 8;
+  if (C % 8 != 0 || ldw % V != 0 || ldm % V != 0 || ((uintptr_t)W & 15) != 0 || ((uintptr_t)keep_mask & 7) != 0)
+    return VLMC_ERR_UNSUPPORTED;
+  if (!is_device_ptr(W) || !is_device_ptr(scaler_row) || !is_device_ptr(keep_mask) || !is_device_ptr(ws))
+    return VLMC_ERR_NOT_DEVICE;
+  if (ws_bytes < threshold_workspace_bytes(R, C)) return VLMC_ERR_WORKSPACE;
+  char* base = reinterpret_cast<char*>(ws) + VLMC_WS_COUNTER_BYTES;
+  float* sq = reinterpret_cast<float*>(base);
+  base += align_up((size_t)C * sizeof(float), 256);
+  float* part = reinterpret_cast<float*>(base);
+  base += align_up((size_t)kNumSMs * 8 * sizeof(float), 256);
+  ThrState* st = reinterpret_cast<ThrState*>(base);
+  cudaStream_t s = (cudaStream_t)stream;
+  const ull k = (ull)k_global + 1;  // 1-indexed rank of the threshold value
+
+  if (cudaMemsetAsync(st, 0, sizeof(ThrState), s) != cudaSuccess) return check_launch();
+  sqrt_kernel<<<(C + 255) / 256, 256, 0, s>>>(scaler_row, sq, C);
+  const int64_t nvec = (int64_t)R * (C / V);
+  int grid = kNumSMs * 8;
+  if ((int64_t)grid * kThrThreads > nvec) grid = (int)((nvec + kThrThreads - 1) / kThrThreads);
+  for (int pass = 0; pass < kThrPasses; ++pass) {
+    VLMC_DISPATCH_DTYPE(dtype, (thr_count_kernel<scalar_t><<<grid, kThrThreads, 0, s>>>(
+                                   reinterpret_cast<const scalar_t*>(W), ldw, R, C, sq, k, st, pass)));
+  }
+  VLMC_DISPATCH_DTYPE(dtype, (thr_gather_kernel<scalar_t><<<grid, kThrThreads, 0, s>>>(
+                                 reinterpret_cast<const scalar_t*>(W), ldw, R, C, sq, k, st)));
+  thr_resolve_kernel<<<1, 1024, 0, s>>>(R, C, k, st);
+  VLMC_DISPATCH_DTYPE(dtype, (thr_apply_kernel<scalar_t><<<grid, kThrThreads, 0, s>>>(
+                                 reinterpret_cast<scalar_t*>(W), ldw, R, C, sq, st, zero_w, keep_mask, ldm, part)));
+  int rc = check_launch();
+  if (rc) return rc;
+  if (score_mean) return launch_mean_finalize(part, grid, (double)R * (double)C, score_mean, s);
+  return VLMC_OK;
+}

@@ -1,0 +1,143 @@
+"""The per-block calibration skeleton the three composite pruners share.
+
+Reference: T5LayerWandaPruner._prune (wanda_pruner.py:275-354), VITLayerWandaPruner._prune (:627-699)
+and their SparseGPT / DSnoT copies (sparsegpt_pruner.py:405-459, dsnot_pruner.py:312-770).  The
+reference repeats this loop six times; here it is one function parameterised by
+  make_wrapper(module) -> object with add_batch(inp, out)   (the per-layer statistics wrapper)
+  prune_linear(name, module, wrapper, sparsity)            (mask selection / OBS sweep for one linear)
+Orchestration only: all arithmetic happens in the wrappers' CUDA kernels.
+"""
+import gc
+
+import torch
+import torch.nn as nn
+
+
+def get_module_recursive(base, module_to_process):
+    """wanda_pruner.py:16-26."""
+    for part in [p for p in module_to_process.split(".") if p]:
+        base = getattr(base, part)
+    return base
+
+
+def prunable_types():
+    from vlmc.peft.lora import Linear as LoraLinear
+    return [nn.Linear, LoraLinear]
+
+
+def find_layers(module, layers=None, name=""):
+    """wanda_pruner.py:29-48: leaves whose exact type is prunable, keyed by dotted name."""
+    layers = prunable_types() if layers is None else layers
+    if type(module) in layers:
+        return {name: module}
+    found = {}
+    for child_name, child in module.named_children():
+        found.update(find_layers(child, layers, f"{name}.{child_name}" if name else child_name))
+    return found
+
+
+_T5_KEYS = ["attention_mask", "position_bias", "encoder_attention_mask", "encoder_decoder_position_bias",
+            "layer_head_mask", "cross_attn_layer_head_mask", "encoder_hidden_states"]
+_OPT_KEYS = ["attention_mask", "layer_head_mask"]
+_LLM_KEYS = ["attention_mask", "position_ids"]
+
+
+class _StopForward(ValueError):
+    pass
+
+
+def capture_block_inputs(pruner, model, dataloader, model_prefix, n_samples, module_to_process, lora_model, vit):
+    """Swap block 0 for a catcher and run the model until n_samples inputs are recorded.
+
+    wanda_pruner.py:213-273 (T5 / LLM keys :224-236) and :583-625 (ViT: rel_pos_bias).
+    """
+    layers = get_module_recursive(model, module_to_process)
+    inps, caches = [], []
+    if vit:
+        keys = None
+    elif "t5_model" in pruner.model_prefix:
+        keys = _T5_KEYS
+    elif "opt_model" in pruner.model_prefix:
+        keys = _OPT_KEYS
+    else:
+        keys = _LLM_KEYS
+
+    class Catcher(nn.Module):
+        def __init__(self, module):
+            super().__init__()
+            self.module = module
+
+        def forward(self, inp, *args, dense=True, **kwargs):
+            inp.requires_grad = False
+            inps.append(inp)
+            if vit:
+                rel = args[0] if args else kwargs.get("rel_pos_bias")
+                cache = {"rel_pos_bias": rel}
+            else:
+                cache = {k: kwargs[k] for k in keys}
+            if lora_model:
+                cache["dense"] = dense
+            caches.append(cache)
+            raise _StopForward
+
+    layers[0] = Catcher(layers[0])
+    seen = 0
+    try:
+        for batch in dataloader:
+            if seen >= n_samples:
+                break
+            seen += batch["image"].shape[0] if "image" in batch else len(batch["text_input"])
+            try:
+                pruner.forward_to_cache(model, batch, lora_model)
+            except ValueError:
+                pass
+    finally:
+        layers[0] = layers[0].module
+    return inps, [None] * len(inps), caches
+
+
+def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_samples, sparsity_ratio,
+                 lora_model, vit, make_wrapper, prune_linear):
+    stem = getattr(model, model_prefix, None)
+    cfg = getattr(stem, "config", None) if not vit else None
+    use_cache = getattr(cfg, "use_cache", None)
+    if cfg is not None:
+        cfg.use_cache = False
+    with torch.no_grad():
+        inps, outs, caches = capture_block_inputs(pruner, model, dataloader, model_prefix, n_samples,
+                                                  module_to_process, lora_model, vit)
+    n_samples = min(n_samples, len(inps))
+    layers = get_module_recursive(model, module_to_process)
+
+    def run_block(layer):
+        for j in range(n_samples):
+            with torch.no_grad():
+                ctx = model.maybe_autocast() if vit else model.maybe_autocast(dtype=torch.bfloat16)
+                with ctx:
+                    out = layer(inps[j], **caches[j])
+                    outs[j] = out if vit else out[0]
+
+    for i in range(len(layers)):
+        layer = layers[i]
+        subset = find_layers(layer)
+        wrapped = {name: make_wrapper(subset[name]) for name in subset}
+        handles = [subset[name].register_forward_hook(
+            (lambda nm: lambda _, inp, out: wrapped[nm].add_batch(inp[0].data, out.data))(name))
+            for name in wrapped]
+        run_block(layer)
+        for h in handles:
+            h.remove()
+        for name in subset:
+            key = f"{module_to_process}.{i}.{name}.weight"
+            prune_linear(i, name, subset[name], wrapped[name], sparsity_ratio[key],
+                         expected_nsamples=len(inps) * inps[0].shape[0])
+        pruner.finish_block(subset, wrapped)
+        run_block(layer)
+        inps, outs = outs, inps
+
+    if cfg is not None:
+        cfg.use_cache = use_cache
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()
+    gc.collect()
+    return model

@@ -1,0 +1,153 @@
+"""Wanda pruner: same entry points and per-layer wrapper as lavis/compression/pruners/wanda_pruner.py,
+with the statistics and the mask selection running in sm_100a kernels (include/vlmc.h).
+
+  WrappedGPT                  <- wanda_pruner.py:51-81   (scaler_row accumulation, K1)
+  BLIPT5LayerWandaPruner      <- wanda_pruner.py:796-1044 (registered as "blipt5_wanda_pruner")
+  per-linear score + select   <- wanda_pruner.py:316-341 (LLM/T5: per-row, K5/K6), :664-687 (ViT: K7/K6)
+"""
+import torch
+import torch.nn as nn
+
+from vlmc import native
+from vlmc.common.registry import registry
+from vlmc.compression.pruners.layer_single_base_pruner import LayerWiseBasePruner
+from vlmc.compression.pruners.layerwise import find_layers, get_module_recursive, prune_blocks  # noqa: F401
+from vlmc.compression.pruners.utils import print_time
+
+
+class WrappedGPT:
+    """Per-linear Wanda statistics (wanda_pruner.py:51-81).
+
+    scaler_row[c] is the running mean over samples of sum_t x[t, c]^2; `nsamples` counts the leading
+    batch dimension, not tokens (:71,:77-78).  add_batch is one kernel launch (vlmc_sqnorm_accum).
+    """
+
+    def __init__(self, layer, layer_id=0, layer_name="none"):
+        self.layer = layer
+        self.dev = self.layer.weight.device
+        self.rows = layer.weight.data.shape[0]
+        self.columns = layer.weight.data.shape[1]
+        self.scaler_row = torch.zeros((self.columns), device=self.dev)
+        self.nsamples = 0
+        self.layer_id = layer_id
+        self.layer_name = layer_name
+
+    def add_batch(self, inp, out=None):
+        if len(inp.shape) == 2:
+            inp = inp.unsqueeze(0)
+        b = inp.shape[0]
+        native.sqnorm_accum(inp, self.scaler_row, self.nsamples, b)
+        self.nsamples += b
+
+
+def wanda_prune_linear(module, scaler_row, sparsity, prune_n=0, prune_m=0, lora_model=False, whole_matrix=False):
+    """Score + select + apply for one linear (wanda_pruner.py:316-341 / :664-687).
+
+    Sets module.mask (True = kept) and zeroes pruned weights in place unless lora_model.
+    Returns the device scalar mean(|W| * sqrt(scaler_row)) (the reference's importance_score).
+    """
+    W = module.weight.data
+    if prune_n != 0:
+        keep, mean = native.wanda_nm(W, scaler_row, prune_n, prune_m, zero_w=not lora_model)
+    elif whole_matrix:
+        keep, mean = native.wanda_threshold(W, scaler_row, int(W.numel() * sparsity), zero_w=not lora_model)
+    else:
+        keep, mean = native.wanda_rowselect(W, scaler_row, int(W.shape[1] * sparsity), zero_w=not lora_model)
+    setattr(module, "mask", keep)
+    return mean
+
+
+@registry.register_pruner("blipt5_wanda_pruner")
+class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
+    pruner_name = "blipt5_wanda_pruner"
+
+    def __init__(self, model, data_loader, t5_prune_spec=None, vit_prune_spec=None, t5_pruning_method=None,
+                 vit_pruning_method=None, t5_importance_scores_cache=None, t5_keep_indices_or_masks_cache=None,
+                 vit_importance_scores_cache=None, vit_keep_indices_or_masks_cache=None,
+                 importance_scores_cache=None, keep_indices_or_masks_cache=None, is_strct_pruning=False,
+                 num_samples=64, is_global=False, t5_model_prefix="t5_model", vit_model_prefix="visual_encoder",
+                 sparsity_ratio_granularity=None, max_sparsity_per_layer=0.8, score_method="obd_avg",
+                 num_data_first_stage=128, num_noise=1, sparsity_dict=None, noise_eps=1e-3,
+                 prune_per_model=False, peft_postfix="", prune_n=0, prune_m=0, **kwargs):
+        super().__init__(model=model, data_loader=data_loader, prune_spec=None, is_strct_pruning=is_strct_pruning,
+                         importance_scores_cache=importance_scores_cache,
+                         keep_indices_or_masks_cache=keep_indices_or_masks_cache, is_global=is_global,
+                         num_samples=num_samples, model_prefix=f"{vit_model_prefix}+{t5_model_prefix}",
+                         sparsity_ratio_granularity=sparsity_ratio_granularity,
+                         max_sparsity_per_layer=max_sparsity_per_layer, score_method=score_method,
+                         num_data_first_stage=num_data_first_stage, num_noise=num_noise,
+                         sparsity_dict=sparsity_dict, noise_eps=noise_eps, prune_per_model=prune_per_model,
+                         prune_n=prune_n, prune_m=prune_m)
+        self.t5_prune_spec = t5_prune_spec
+        self.vit_prune_spec = vit_prune_spec
+        self.peft_postfix = peft_postfix
+        self.vit_dense = True
+        self.llm_dense = True
+        assert t5_pruning_method is not None
+        assert vit_pruning_method is not None
+        self.t5_model_prefix = t5_model_prefix
+        self.vit_model_prefix = vit_model_prefix
+        self._pending_scores = []
+
+    # ---- hooks the shared block loop calls ------------------------------------------------------
+    def forward_to_cache(self, model, batch, lora_model=False):
+        if lora_model:
+            return model(batch, vit_dense=self.vit_dense, llm_dense=self.llm_dense)
+        return model(batch)
+
+    def make_wrapper(self, module):
+        return WrappedGPT(module)
+
+    def _prune_linear(self, vit, lora_model):
+        def fn(i, name, module, wrapper, sparsity, expected_nsamples):
+            assert wrapper.nsamples == expected_nsamples
+            mean = wanda_prune_linear(module, wrapper.scaler_row, sparsity, self.prune_n, self.prune_m,
+                                      lora_model=lora_model, whole_matrix=vit)
+            self._pending_scores.append((module, mean))
+        return fn
+
+    def finish_block(self, subset, wrapped):
+        # one host sync per block instead of the reference's full-matrix .cpu() per linear (:320)
+        if self._pending_scores:
+            vals = torch.cat([m for _, m in self._pending_scores]).tolist()
+            for (module, _), v in zip(self._pending_scores, vals):
+                setattr(module.weight, "importance_score", v)
+            self._pending_scores = []
+
+    def _prune(self, model, dataloader, model_prefix, module_to_process, n_samples, sparsity_ratio,
+               lora_model=False, vit=False):
+        return prune_blocks(self, model, dataloader, model_prefix, module_to_process, n_samples, sparsity_ratio,
+                            lora_model, vit, self.make_wrapper, self._prune_linear(vit, lora_model))
+
+    # ---- entry point (wanda_pruner.py:947-1044) -------------------------------------------------
+    @print_time
+    def prune(self, importance_scores=None, keep_indices_or_masks=None, lora_model=False):
+        dtype_record, requires_grad_record, device = self.model_setup_and_record_attributes(self.model)
+        global_sparsity_dict = None
+        _, vit_keep_ratio, _, _ = self.convert_spec_to_list(self.vit_prune_spec)
+        _, t5_keep_ratio, _, _ = self.convert_spec_to_list(self.t5_prune_spec)
+        if self.sparsity_ratio_granularity not in [None, "none"]:
+            global_sparsity_dict = self.get_sparsity(1 - t5_keep_ratio, self.sparsity_ratio_granularity)
+        self.vit_dense = float(vit_keep_ratio) < 1.0
+        self.llm_dense = float(t5_keep_ratio) < 1.0
+
+        if self.vit_prune_spec is not None and float(vit_keep_ratio) < 1.0:
+            sparsity = global_sparsity_dict if global_sparsity_dict not in [None, "none"] \
+                else self.get_sparsity(1 - vit_keep_ratio, None)
+            self.model = self._prune(self.model, self.data_loader, self.vit_model_prefix,
+                                     f"{self.vit_model_prefix}.blocks", self.num_samples, sparsity,
+                                     lora_model=lora_model, vit=True)
+
+        if self.t5_prune_spec is not None and float(t5_keep_ratio) < 1.0:
+            sparsity = global_sparsity_dict if global_sparsity_dict is not None \
+                else self.get_sparsity(1 - t5_keep_ratio, None)
+            if "t5_model" in self.t5_model_prefix:
+                stacks = [f"{self.t5_model_prefix}.encoder.block", f"{self.t5_model_prefix}.decoder.block"]
+            else:
+                stacks = [f"{self.t5_model_prefix}{self.peft_postfix}.model.layers"]
+            for stack in stacks:
+                self.model = self._prune(self.model, self.data_loader, self.t5_model_prefix, stack,
+                                         self.num_samples, sparsity, lora_model=lora_model, vit=False)
+
+        self.model_reset(self.model, dtype_record, requires_grad_record, device)
+        return self.model, global_sparsity_dict

@@ -1,0 +1,228 @@
+"""ctypes binding of libvlmc.so (include/vlmc.h) for torch tensors.
+
+PyTorch is plumbing here: it owns device memory and streams; every statistic, selection and
+update runs in the hand-written sm_100a kernels behind the C ABI.  There is no CPU path and no
+fallback: a missing library or a non-CUDA tensor raises.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libvlmc.so")
+
+F32, F16, BF16 = 0, 1, 2
+_DTYPES = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+
+OP_SQNORM, OP_DSNOT_STATS, OP_WANDA_SELECT, OP_LORA_MERGE, OP_HESSIAN, OP_CHOL, OP_OBS, OP_DSNOT_REFINE = range(8)
+WS_COUNTER_BYTES = 4096
+NOT_POSDEF = 1
+
+
+class VlmcError(RuntimeError):
+    def __init__(self, fn, status, detail=""):
+        self.status = status
+        super().__init__(f"{fn} failed: status {status} ({detail})")
+
+
+_lib = None
+_lock = threading.Lock()
+
+_vp, _i, _i64, _d, _f, _sz = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double,
+                              ctypes.c_float, ctypes.c_size_t)
+
+# name -> (restype, argtypes); must list every symbol include/vlmc.h declares
+SIGNATURES = {
+    "vlmc_version": (_i, []),
+    "vlmc_status_string": (ctypes.c_char_p, [_i]),
+    "vlmc_last_cuda_error": (_i, []),
+    "vlmc_workspace_bytes": (_sz, [_i, _i64, _i64, _i64]),
+    "vlmc_sqnorm_accum": (_i, [_vp, _i, _i64, _i, _i64, _vp, _d, _d, _vp, _sz, _vp]),
+    "vlmc_dsnot_stats": (_i, [_vp, _i, _i64, _i64, _i, _i64, _vp, _vp, _vp, _vp, _d, _d, _d, _vp, _sz, _vp]),
+    "vlmc_wanda_rowselect": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "vlmc_wanda_nm": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "vlmc_wanda_threshold": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "vlmc_sparselora_merge": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _f, _vp, _i64, _i, _vp]),
+}
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Loads the CUDA extension; fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(_LIB_PATH):
+            raise ImportError(
+                f"{_LIB_PATH} not found: build it with `python vlm-compression_b200/build.py` "
+                "(there is no CPU or PyTorch fallback for this path)")
+        lib = ctypes.CDLL(_LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name, None)
+            if fn is None:
+                continue  # reported by tests/test_abi.py; calling it raises AttributeError
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _check(fn, status):
+    if status < 0:
+        lib = load()
+        detail = lib.vlmc_status_string(status).decode()
+        if status == -5:
+            detail += f", cudaError {lib.vlmc_last_cuda_error()}"
+        raise VlmcError(fn, status, detail)
+    return status
+
+
+def _dtype(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"vlmc kernels take float32/float16/bfloat16, got {t.dtype}") from None
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vlmc has no CPU path: tensors must live on a CUDA device "
+                               f"(got device {t.device})")
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+# one zero-initialised workspace per (device, stream); kernels leave the ticket area zero
+_workspaces = {}
+
+
+def workspace(ref, nbytes):
+    key = (ref.device.index, _stream(ref))
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=ref.device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _rows2d(x):
+    """View activations as [T, C] rows without copying when possible (reference: inp.reshape(-1, C))."""
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    return x2
+
+
+def sqnorm_accum(x, scaler_row, n_before, b):
+    """K1: scaler_row <- scaler_row*n/(n+b) + sum_t x[t,:]^2/(n+b)   (wanda_pruner.py:77-81)."""
+    _require_cuda(x, scaler_row)
+    lib = load()
+    x2 = _rows2d(x)
+    T, C = x2.shape
+    need = lib.vlmc_workspace_bytes(OP_SQNORM, T, C, 0)
+    ws = workspace(x2, need)
+    with torch.cuda.device(x2.device):
+        st = lib.vlmc_sqnorm_accum(x2.data_ptr(), _dtype(x2), T, C, x2.stride(0), scaler_row.data_ptr(),
+                                   float(n_before), float(b), ws.data_ptr(), ws.numel(), _stream(x2))
+    _check("vlmc_sqnorm_accum", st)
+
+
+def dsnot_stats(x, scaler_row, sum_row, mean, var, n_before, b_per_seg, ntok_before, nseg=1):
+    """K2: DSnoT statistics (dsnot_pruner.py:79-101); x = nseg consecutive calls of equal length."""
+    _require_cuda(x, scaler_row, sum_row, mean, var)
+    lib = load()
+    x2 = _rows2d(x)
+    T, C = x2.shape
+    if T % nseg:
+        raise ValueError("rows must divide evenly into segments")
+    need = lib.vlmc_workspace_bytes(OP_DSNOT_STATS, T, C, nseg)
+    ws = workspace(x2, need)
+    with torch.cuda.device(x2.device):
+        st = lib.vlmc_dsnot_stats(x2.data_ptr(), _dtype(x2), nseg, T // nseg, C, x2.stride(0),
+                                  scaler_row.data_ptr(), sum_row.data_ptr(), mean.data_ptr(), var.data_ptr(),
+                                  float(n_before), float(b_per_seg), float(ntok_before),
+                                  ws.data_ptr(), ws.numel(), _stream(x2))
+    _check("vlmc_dsnot_stats", st)
+
+
+def _select_common(W, scaler_row, keep_mask):
+    _require_cuda(W, scaler_row, keep_mask)
+    if W.dim() != 2 or W.stride(1) != 1:
+        raise ValueError("W must be a 2-D row-major weight")
+    R, C = W.shape
+    if keep_mask is None:
+        keep_mask = torch.empty((R, C), dtype=torch.bool, device=W.device)
+    if keep_mask.dtype != torch.bool or keep_mask.shape != W.shape or keep_mask.stride(1) != 1:
+        raise ValueError("keep_mask must be a bool tensor shaped like W")
+    lib = load()
+    ws = workspace(W, lib.vlmc_workspace_bytes(OP_WANDA_SELECT, R, C, 0))
+    score_mean = torch.empty(1, dtype=torch.float32, device=W.device)
+    return lib, R, C, keep_mask, ws, score_mean
+
+
+def wanda_rowselect(W, scaler_row, k, zero_w=True, keep_mask=None):
+    """K4+K5 (wanda_pruner.py:318-341).  Returns (keep_mask bool [R,C], score_mean 1-elem tensor)."""
+    lib, R, C, keep_mask, ws, score_mean = _select_common(W, scaler_row, keep_mask)
+    with torch.cuda.device(W.device):
+        st = lib.vlmc_wanda_rowselect(W.data_ptr(), _dtype(W), R, C, W.stride(0), scaler_row.data_ptr(), int(k),
+                                      int(bool(zero_w)), keep_mask.data_ptr(), keep_mask.stride(0),
+                                      score_mean.data_ptr(), ws.data_ptr(), ws.numel(), _stream(W))
+    _check("vlmc_wanda_rowselect", st)
+    return keep_mask, score_mean
+
+
+def wanda_nm(W, scaler_row, n, m, zero_w=True, keep_mask=None):
+    """K4+K6 (wanda_pruner.py:323-329)."""
+    lib, R, C, keep_mask, ws, score_mean = _select_common(W, scaler_row, keep_mask)
+    with torch.cuda.device(W.device):
+        st = lib.vlmc_wanda_nm(W.data_ptr(), _dtype(W), R, C, W.stride(0), scaler_row.data_ptr(), int(n), int(m),
+                               int(bool(zero_w)), keep_mask.data_ptr(), keep_mask.stride(0),
+                               score_mean.data_ptr(), ws.data_ptr(), ws.numel(), _stream(W))
+    _check("vlmc_wanda_nm", st)
+    return keep_mask, score_mean
+
+
+def wanda_threshold(W, scaler_row, k_global, zero_w=True, keep_mask=None):
+    """K4+K7 (wanda_pruner.py:682-683)."""
+    lib, R, C, keep_mask, ws, score_mean = _select_common(W, scaler_row, keep_mask)
+    with torch.cuda.device(W.device):
+        st = lib.vlmc_wanda_threshold(W.data_ptr(), _dtype(W), R, C, W.stride(0), scaler_row.data_ptr(),
+                                      int(k_global), int(bool(zero_w)), keep_mask.data_ptr(),
+                                      keep_mask.stride(0), score_mean.data_ptr(), ws.data_ptr(), ws.numel(),
+                                      _stream(W))
+    _check("vlmc_wanda_threshold", st)
+    return keep_mask, score_mean
+
+
+def sparselora_merge(W, A, B, scaling, keep_mask, remask=True):
+    """K14 (lora.py:384-387 + train.py:634-637), in place on W."""
+    _require_cuda(W, A, B, keep_mask)
+    if W.dim() != 2 or W.stride(1) != 1:
+        raise ValueError("W must be a 2-D row-major weight")
+    if A.dtype != torch.float32 or B.dtype != torch.float32:
+        raise TypeError("lora_A / lora_B must be float32")
+    A = A.contiguous()
+    B = B.contiguous()
+    R, C = W.shape
+    rank = A.shape[0]
+    if A.shape != (rank, C) or B.shape != (R, rank):
+        raise ValueError("lora_A must be [r, C] and lora_B [R, r]")
+    if keep_mask.dtype != torch.bool or keep_mask.shape != W.shape or keep_mask.stride(1) != 1:
+        raise ValueError("mask must be a bool tensor shaped like W")
+    lib = load()
+    with torch.cuda.device(W.device):
+        st = lib.vlmc_sparselora_merge(W.data_ptr(), _dtype(W), R, C, W.stride(0), A.data_ptr(), B.data_ptr(),
+                                       rank, float(scaling), keep_mask.data_ptr(), keep_mask.stride(0),
+                                       int(bool(remask)), _stream(W))
+    _check("vlmc_sparselora_merge", st)
+    return W

@@ -1,0 +1,81 @@
+"""Multi-GPU plan for the path (new: the reference runs independent replicas).
+
+  phase 1  calibration tokens are split across ranks; every rank accumulates its own running means
+           with the same kernels; ONE all-reduce(SUM) of a packed fp32 buffer per block merges them
+           (mean over all samples = sum_r mean_r * n_r / sum_r n_r)
+  phase 2  output rows are split across ranks for mask selection (rows are independent for the per-row
+           and n:m rules); an all-gather returns the pruned weights and masks to every rank
+
+torch.distributed (NCCL over NVLink on the box, gloo in the CPU tests) is the plumbing; the statistics and
+selection stay in the CUDA kernels.  The functions take the kernel entry points as arguments so the CPU
+tests can drive the sharding / collective logic with the numpy oracle standing in for the device code.
+"""
+import torch
+import torch.distributed as dist
+
+
+def row_range(rows, rank, world):
+    """Contiguous, balanced split of `rows` output rows; the first rows % world ranks get one extra."""
+    base, extra = divmod(rows, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def sample_range(n_samples, rank, world):
+    return row_range(n_samples, rank, world)
+
+
+def merge_running_means(stats, n_local, group=None, n_total=None):
+    """All-reduce a list of per-rank running means (each the mean over this rank's n_local samples) into the
+    mean over all samples, in place, with one packed collective.  Returns the global sample count
+    (pass n_total when every rank already knows it: that avoids a host sync)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return n_local
+    dev = stats[0].device
+    flat = torch.cat([s.reshape(-1).float() * float(n_local) for s in stats] +
+                     [torch.full((1,), float(n_local), device=dev)])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    n_total = float(flat[-1].item()) if n_total is None else float(n_total)
+    off = 0
+    for s in stats:
+        k = s.numel()
+        s.copy_((flat[off:off + k] / n_total).reshape(s.shape))
+        off += k
+    return int(round(n_total))
+
+
+def merge_token_means(means, ntok_local, group=None, ntok_total=None):
+    """Same for token-weighted means (DSnoT mean / var)."""
+    return merge_running_means(means, ntok_local, group, ntok_total)
+
+
+def gather_rows(full, rank, world, group=None):
+    """All-gather the row shards of `full` [R, ...] in place: rank r owns rows row_range(R, r, world)."""
+    if not dist.is_initialized() or world == 1:
+        return full
+    R = full.shape[0]
+    if R % world == 0:
+        s, e = row_range(R, rank, world)
+        dist.all_gather_into_tensor(full, full[s:e].clone(), group=group)
+    else:
+        for r in range(world):
+            s, e = row_range(R, r, world)
+            if e > s:
+                dist.broadcast(full[s:e], src=dist.get_global_rank(group, r) if group else r, group=group)
+    return full
+
+
+def prune_linear_row_sharded(weight, scaler_row, select_fn, rank, world, group=None):
+    """Phase 2 for one linear.  select_fn(W_rows, scaler_row, keep_rows_out) -> score_mean (1-elem tensor) runs
+    the selection kernel on this rank's row shard in place; returns (keep_mask [R, C], score_mean tensor)."""
+    R, C = weight.shape
+    s, e = row_range(R, rank, world)
+    keep = torch.empty((R, C), dtype=torch.bool, device=weight.device)
+    mean = torch.zeros(1, dtype=torch.float32, device=weight.device)
+    if e > s:
+        mean = select_fn(weight[s:e], scaler_row, keep[s:e]) * float(e - s)
+    if dist.is_initialized() and world > 1:
+        gather_rows(weight, rank, world, group)
+        gather_rows(keep.view(torch.uint8), rank, world, group)
+        dist.all_reduce(mean, op=dist.ReduceOp.SUM, group=group)
+    return keep, mean / float(R)

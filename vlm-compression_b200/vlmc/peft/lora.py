@@ -1,0 +1,89 @@
+"""SparseLoRA linear layer: the slice of lavis/peft/src/peft/tuners/lora.py (:265-394) on the hot path.
+
+Kept verbatim from the reference interface: `mask` (registered bool buffer, True = kept), `sparse`,
+`scaling`, `lora_A`, `lora_B`, `fan_in_fan_out`, `merge()`, `forward(x, dense=False)`.
+merge() + the re-mask of train.py:634-637 run as ONE kernel (vlmc_sparselora_merge, K14).
+The masked training forward (lora.py:359-382) is a "next" row and is expressed with
+torch ops here; it is not part of the measured path.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from vlmc import native
+
+
+def transpose(weight, fan_in_fan_out):
+    return weight.T if fan_in_fan_out else weight
+
+
+class LoraLayer:
+    def __init__(self, r, lora_alpha, lora_dropout, merge_weights):
+        self.r = r
+        self.lora_alpha = lora_alpha
+        self.lora_dropout = nn.Dropout(p=lora_dropout) if lora_dropout > 0.0 else (lambda x: x)
+        self.merged = False
+        self.merge_weights = merge_weights
+        self.disable_adapters = False
+
+
+class Linear(nn.Linear, LoraLayer):
+    def __init__(self, in_features, out_features, r=0, lora_alpha=1, lora_dropout=0.0, fan_in_fan_out=False,
+                 merge_weights=True, **kwargs):
+        nn.Linear.__init__(self, in_features, out_features, **kwargs)
+        LoraLayer.__init__(self, r=r, lora_alpha=lora_alpha, lora_dropout=lora_dropout, merge_weights=merge_weights)
+        self.fan_in_fan_out = fan_in_fan_out
+        if r > 0:
+            self.lora_A = nn.Linear(in_features, r, bias=False)
+            self.lora_B = nn.Linear(r, out_features, bias=False)
+            self.scaling = self.lora_alpha / self.r
+            self.weight.requires_grad = False
+        self.reset_parameters()
+        if fan_in_fan_out:
+            self.weight.data = self.weight.data.T
+        self.register_buffer("mask", torch.ones_like(self.weight.data).bool())   # lora.py:317
+        self.sparse = False
+
+    def reset_parameters(self):
+        nn.Linear.reset_parameters(self)
+        self.reset_peft()
+
+    def reset_peft(self):
+        if hasattr(self, "lora_A"):
+            nn.init.kaiming_uniform_(self.lora_A.weight, a=math.sqrt(5))
+            nn.init.zeros_(self.lora_B.weight)
+
+    def forward(self, x, dense=False):
+        previous_dtype = self.weight.dtype
+        if dense or self.disable_adapters or not (self.r > 0 and not self.merged):
+            result = F.linear(x, transpose(self.weight, self.fan_in_fan_out), bias=self.bias)
+        else:
+            delta = transpose((self.lora_B.weight @ self.lora_A.weight).to(previous_dtype),
+                              self.fan_in_fan_out) * self.scaling
+            if self.sparse:      # lora.py:364-369
+                w = (self.weight + delta) * self.mask
+            else:                # lora.py:370-375
+                w = self.weight * self.mask + delta
+            result = F.linear(x, transpose(w, self.fan_in_fan_out), bias=self.bias)
+        if result.dtype != previous_dtype:
+            result = result.to(previous_dtype)
+        return result
+
+    def merge(self, remask=False):
+        """lora.py:384-394.  sparse: W += (B@A * scaling) * mask, one fused kernel; remask=True also
+        applies train.py:634-637 (W[~mask] = 0) in the same pass."""
+        if self.fan_in_fan_out:
+            raise NotImplementedError("fan_in_fan_out weights are not on the InstructBLIP path")
+        if self.sparse:
+            native.sparselora_merge(self.weight.data, self.lora_A.weight.data.float(),
+                                    self.lora_B.weight.data.float(), self.scaling, self.mask, remask=remask)
+        else:
+            # dense-delta branch (lora.py:388-391): W[~mask] = 0 ; W += B@A * scaling  -- same kernel run
+            # with an all-ones merge mask after the re-mask
+            self.weight.data[~self.mask] = 0
+            ones = torch.ones_like(self.mask)
+            native.sparselora_merge(self.weight.data, self.lora_A.weight.data.float(),
+                                    self.lora_B.weight.data.float(), self.scaling, ones, remask=False)
+        self.reset_peft()
