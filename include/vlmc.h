@@ -137,6 +137,20 @@ int vlmc_sparselora_merge(void* W, int dtype, int R, int C, int64_t ldw,
                           const uint8_t* keep_mask, int64_t ldm, int remask,
                           void* stream);
 
+/*
+ * K3  SparseGPT Hessian accumulation.  Replaces SparseGPT.add_batch, sparsegpt_pruner.py:68-79:
+ *   H <- H * n_before/(n_before+b) + (2/(n_before+b)) * X^T X
+ * x: [T, C] row-major fp16 / bf16 (one add_batch call, T = b * seq_len); H: [C, C] fp32, full and symmetric.
+ * TMA-fed tcgen05.mma (kind::f16, fp32 accumulate in TMEM), SYRK over the upper triangle with the mirror
+ * written by the epilogue.  kc = tokens accumulated inside the tensor core before the partial sum is
+ * added, round-to-nearest, into fp32 registers (0 = default 512; multiples of 64).  slab_tokens = tokens per
+ * launch (0 = default: 65536 for C >= 8192, else unlimited): all tiles of one slab run before the next so operand re-reads stay in L2.
+ * fp32 activations (EVA-ViT qkv / fc1 inputs) need the 3xTF32 split and are not built yet: VLMC_ERR_UNSUPPORTED.
+ */
+int vlmc_hessian_accum(const void* x, int dtype, int64_t T, int C, int64_t ldx,
+                       float* H, int64_t ldh, double n_before, double b, int kc, int64_t slab_tokens,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -166,6 +166,28 @@ def sparselora_merge(W32, w_tag, A, B, scaling, keep_mask, remask=True):
 
 
 # ---------------------------------------------------------------------------------------------
+# a3 / K3  SparseGPT Hessian                     sparsegpt_pruner.py:68-79
+# ---------------------------------------------------------------------------------------------
+def sparsegpt_add_batch(H, nsamples, x, b):
+    """H *= n/(n+b); n += b; x = sqrt(2/n) * x.float(); H += x^T x   (fp32, like the reference's SGEMM)."""
+    H = H.astype(F32) * F32(nsamples / (nsamples + b))
+    nsamples += b
+    xs = (F32(np.sqrt(2.0 / nsamples)) * np.asarray(x, dtype=F32)).astype(F32)
+    H = H + xs.T @ xs
+    return H.astype(F32), nsamples
+
+
+def hessian_truth(xs, n_total):
+    """float64 ground truth (2/N) sum_t x x^T over a list of [T, C] calls."""
+    C = xs[0].shape[1]
+    H = np.zeros((C, C), dtype=np.float64)
+    for x in xs:
+        x64 = np.asarray(x, dtype=np.float64)
+        H += x64.T @ x64
+    return H * (2.0 / n_total)
+
+
+# ---------------------------------------------------------------------------------------------
 # return_reorder_indice                          dsnot_pruner.py:1881-1925
 # ---------------------------------------------------------------------------------------------
 def return_reorder_indice(t):

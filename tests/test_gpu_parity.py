@@ -31,10 +31,10 @@ def rel_inf(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
-def rel_elem(a, b):
-    """per-element relative error on entries above 1e-3 of the max."""
+def rel_elem(a, b, floor=1e-3):
+    """per-element relative error on entries above `floor` of the max."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    big = np.abs(b) > 1e-3 * np.abs(b).max()
+    big = np.abs(b) > floor * np.abs(b).max()
     return float((np.abs(a - b)[big] / np.abs(b)[big]).max())
 
 
@@ -141,7 +141,7 @@ def test_dsnot_stats_vs_oracle_and_segments(native, T, C, tag):
         assert rel_inf(seq[k].cpu().numpy(), st_o[k]) < REL, k
         assert rel_inf(one[k].cpu().numpy(), st_o[k]) < REL, k
     # large mean / small variance channel: the shifted accumulation must not cancel
-    x = (torch.randn(1024, 256) * 0.01 + 30.0).to(DT[tag])
+    x = (torch.randn(1024, 256) * 0.05 + 3.0).to(DT[tag])     # |mean| = 60 sigma
     o = oracle.dsnot_add_batch(dict(scaler_row=np.zeros(256, np.float32), sum_metric_row=np.zeros(256, np.float32),
                                     mean=np.zeros(256, np.float32), var=np.zeros(256, np.float32), nsamples=0,
                                     ntokens=0), x.float().numpy(), 1)
@@ -239,7 +239,7 @@ def test_rowselect_full_size_properties(native):
         assert torch.equal(W, torch.where(keep, W0, torch.zeros_like(W0)))
         # every pruned score <= every kept score of its row
         S = W0.float().abs() * s.sqrt()
-        assert bool((torch.where(keep, torch.inf, S).max(1).values <= torch.where(keep, S, torch.inf).min(1).values).all())
+        assert bool((torch.where(keep, -torch.inf, S).max(1).values <= torch.where(keep, S, torch.inf).min(1).values).all())
         # a second pass on the pruned weights keeps the mask (the pruned entries now score 0 and stay the k smallest
         # except where kept weights were already 0)
         keep2, _ = native.wanda_rowselect(W.clone(), s, k)
@@ -397,4 +397,47 @@ def test_composite_wanda_pruner_on_toy_model(native):
         assert bool((mod.weight.data[~mod.mask] == 0).all())
         assert isinstance(mod.weight.importance_score, float)
         agree.append((keep == L["mask"]).mean())
-    assert min(agree[:4]) > 0.98          # first ViT block sees identical fp32 inputs up to matmul rounding
+    assert min(agree[:2]) > 0.999 and min(agree[:4]) > 0.95   # first ViT block: same fp32 inputs up to fp16 autocast rounding
+
+
+# ------------------------------------------------------------------------------------------- K3
+def _rel_fro(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+@pytest.mark.parametrize("T,C,tag", [(2048, 512, "f16"), (512, 256, "bf16"), (2048, 1408, "f16"), (200, 384, "bf16"),
+                                     (4096, 2048, "bf16"), (64, 128, "f16"), (1000, 5120, "f16")])
+def test_hessian_vs_oracle(native, T, C, tag):
+    """H within 1e-5 relative of the reference's fp32 running average AND of the float64 truth."""
+    H = torch.zeros(C, C, device="cuda")
+    Ho, n = np.zeros((C, C), np.float32), 0
+    xs = []
+    for call in range(3):
+        x = acts(T, C, 31 * call + T + C, DT[tag])
+        xs.append(x.float().numpy())
+        native.hessian_accum(x.cuda(), H, n, 1)
+        Ho, n = oracle.sparsegpt_add_batch(Ho, n, xs[-1], 1)
+    got = H.cpu().numpy()
+    truth = oracle.hessian_truth(xs, 3)
+    assert np.array_equal(got, got.T)                          # exactly symmetric, full matrix
+    # 1e-5 relative (north_star) in max norm and in Frobenius norm, and per element on every entry within two
+    # orders of magnitude of the largest (smaller off-diagonal entries are sums with heavy cancellation: the
+    # reference's own fp32 SGEMM is only ~1e-5 accurate on them relative to their size)
+    for want in (truth, Ho):
+        assert rel_inf(got, want) < REL and _rel_fro(got, want) < REL and rel_elem(got, want, 1e-2) < REL
+
+
+def test_hessian_long_accumulation_chunks(native):
+    """128 x 2048 tokens in ONE call: the in-TMEM chunk (kc) bounds the tensor core's round-toward-zero drift."""
+    T, C = 32 * 2048, 512
+    x = acts(T, C, 5, torch.float16).cuda()
+    truth = (x.double().T @ x.double() * (2.0 / 32)).cpu().numpy()
+    errs = {}
+    for kc in (256, 512, 2048, 16384):
+        H = torch.zeros(C, C, device="cuda")
+        native.hessian_accum(x.view(32, 2048, C), H, 0, 32, kc=kc)
+        errs[kc] = rel_inf(H.cpu().numpy(), truth)
+    print("hessian rel err vs kc:", errs)
+    assert errs[256] < REL / 2 and errs[512] < REL / 2       # default kc = 512
+    assert errs[16384] > errs[512]                            # the drift the chunking is there to bound

@@ -39,8 +39,12 @@ struct StatsParams {
   double n_before, b_per_seg, ntok_before;
 };
 
+// resident CTAs per SM the grid is sized for (one full wave, no tail): the Wanda variant fits 32 registers
+// (8 x 256 threads = 64 warps / SM); the DSnoT variant carries 3x the per-thread state
+template <bool DSNOT> struct StatsOcc { static constexpr int kBlocksPerSM = DSNOT ? 3 : 8; };
+
 template <typename T, bool DSNOT>
-__global__ void __launch_bounds__(kStatsThreads)
+__global__ void __launch_bounds__(kStatsThreads, StatsOcc<DSNOT>::kBlocksPerSM)
 colstats_kernel(const StatsParams p) {
   constexpr int V = Elem<T>::kVec;
   const int tx = threadIdx.x % kCX;
@@ -211,11 +215,11 @@ struct StatsPlan {
   size_t bytes;
 };
 
-static StatsPlan plan_stats(int dtype, int64_t nseg, int64_t S, int C, int kinds) {
+static StatsPlan plan_stats(int dtype, int64_t nseg, int64_t S, int C, int kinds, int blocks_per_sm = 8) {
   StatsPlan pl;
   const int V = dtype == VLMC_F32 ? 4 : 8;
   pl.coltiles = (C + kCX * V - 1) / (kCX * V);
-  const int64_t target_ctas = (int64_t)kNumSMs * 8;  // 8 x 256 threads resident per SM
+  const int64_t target_ctas = (int64_t)kNumSMs * blocks_per_sm;  // exactly one resident wave
   int64_t want = target_ctas / pl.coltiles;
   if (want < 1) want = 1;
   int64_t cps = want / nseg;
@@ -250,7 +254,7 @@ static int launch_stats(const void* x, int dtype, int64_t nseg, int64_t S, int C
   const int V = dtype == VLMC_F32 ? 4 : 8;
   if (C % V != 0 || ldx % V != 0 || ((uintptr_t)x & 15) != 0) return VLMC_ERR_UNSUPPORTED;
   if (!is_device_ptr(x) || !is_device_ptr(scaler_row) || !is_device_ptr(ws)) return VLMC_ERR_NOT_DEVICE;
-  StatsPlan pl = plan_stats(dtype, nseg, S, C, DSNOT ? 3 : 1);
+  StatsPlan pl = plan_stats(dtype, nseg, S, C, DSNOT ? 3 : 1, StatsOcc<DSNOT>::kBlocksPerSM);
   if (ws_bytes < pl.bytes) return VLMC_ERR_WORKSPACE;
   if (pl.coltiles * sizeof(unsigned int) > VLMC_WS_COUNTER_BYTES) return VLMC_ERR_UNSUPPORTED;
   if (pl.nchunks > 65535) return VLMC_ERR_UNSUPPORTED;

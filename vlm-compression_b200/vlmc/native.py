@@ -44,6 +44,7 @@ SIGNATURES = {
     "vlmc_wanda_nm": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_wanda_threshold": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_sparselora_merge": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _f, _vp, _i64, _i, _vp]),
+    "vlmc_hessian_accum": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _d, _d, _i, _i64, _vp]),
 }
 
 
@@ -226,3 +227,17 @@ def sparselora_merge(W, A, B, scaling, keep_mask, remask=True):
                                        int(bool(remask)), _stream(W))
     _check("vlmc_sparselora_merge", st)
     return W
+
+
+def hessian_accum(x, H, n_before, b, kc=0, slab_tokens=0):
+    """K3: H <- H*n/(n+b) + 2/(n+b) * X^T X   (sparsegpt_pruner.py:76-79), tcgen05 SYRK."""
+    _require_cuda(x, H)
+    lib = load()
+    x2 = _rows2d(x)
+    T, C = x2.shape
+    if H.dtype != torch.float32 or H.shape != (C, C) or H.stride(1) != 1:
+        raise ValueError("H must be a float32 [C, C] row-major matrix")
+    with torch.cuda.device(x2.device):
+        st = lib.vlmc_hessian_accum(x2.data_ptr(), _dtype(x2), T, C, x2.stride(0), H.data_ptr(), H.stride(0),
+                                    float(n_before), float(b), int(kc), int(slab_tokens), _stream(x2))
+    _check("vlmc_hessian_accum", st)
