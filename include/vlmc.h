@@ -151,6 +151,39 @@ int vlmc_hessian_accum(const void* x, int dtype, int64_t T, int C, int64_t ldx,
                        float* H, int64_t ldh, double n_before, double b, int kc, int64_t slab_tokens,
                        void* stream);
 
+/*
+ * K10 prologue.  Replaces sparsegpt_pruner.py:95-96 and :111: channels whose diag(H) is 0 get H[c,c] = 1
+ * (dead_out[c] = 1, may be NULL; the caller zeroes those weight columns, :97) and
+ * *damp_out = percdamp * mean(diag(H)).  vlmc_hessian_add_damp adds *damp to the diagonal (the retry step, :126-128).
+ */
+int vlmc_hessian_prepare(float* H, int C, int64_t ldh, float percdamp, float* damp_out, uint8_t* dead_out,
+                         void* stream);
+int vlmc_hessian_add_damp(float* H, int C, int64_t ldh, const float* damp, void* stream);
+
+/*
+ * K10  U = upper Cholesky factor of H^-1 (H^-1 = U^T U).  Replaces the cholesky -> cholesky_inverse ->
+ * cholesky(upper=True) chain of sparsegpt_pruner.py:114-157 with one blocked Cholesky of the flipped matrix and
+ * one triangular inverse (same U mathematically, 2/3 C^3 flops).  H is not modified.  *status (device int) is set
+ * to 0, or to VLMC_NOT_POSDEF when a pivot is non-positive / NaN: the caller then damps and retries exactly like
+ * the reference's while-loop.  The function itself returns 0 in both cases (it does not synchronise).
+ */
+int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U, int64_t ldu, int* status,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * K11-K13  The column-block OBS sweep.  Replaces sparsegpt_pruner.py:160-215: per 128-column block the
+ * unstructured mask (score <= k-th smallest block score, k = int(R*128*sparsity)) or the n:m mask, the 128
+ * sequential error-propagation steps, and the lazy trailing update W[:, i2:] -= Err1 @ U[i1:i2, i2:].
+ * W (fp16 / bf16 / fp32, [R, C]) is overwritten with the compensated sparse weights (math in fp32, one rounding).
+ * dead: optional [C] bytes from vlmc_hessian_prepare (those input channels are zeroed first, :97).
+ * keep_mask (optional) receives 1 = kept / 0 = pruned; importance_score (optional) = mean(W^2 / diag(U)^2), :163-165.
+ * blocksize must be 128.
+ */
+int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu,
+                   const uint8_t* dead, double sparsity, int prune_n, int prune_m, int blocksize,
+                   uint8_t* keep_mask, int64_t ldm, float* importance_score,
+                   void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

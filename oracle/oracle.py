@@ -188,6 +188,84 @@ def hessian_truth(xs, n_total):
 
 
 # ---------------------------------------------------------------------------------------------
+# a7 / K10-K13  SparseGPT.fasterprune             sparsegpt_pruner.py:81-215
+# ---------------------------------------------------------------------------------------------
+def _chol_retry(H, damp, upper):
+    """cholesky with the reference's conditional damping: add `damp` to the diagonal only after a failure or
+    NaNs, cumulatively (:114-128, :143-157).  Returns (factor, number of damping steps)."""
+    from scipy.linalg import lapack
+    steps = 0
+    while True:
+        c, info = lapack.spotrf(H, lower=0 if upper else 1, clean=1)
+        if info == 0 and not np.isnan(c).any():
+            return c.astype(F32), steps
+        H = H.copy()
+        H[np.diag_indices_from(H)] += F32(damp)
+        steps += 1
+        if steps > 200:
+            raise RuntimeError("damping did not make the matrix positive definite")
+
+
+def sparsegpt_inverse_factor(H, percdamp=0.01):
+    """U = cholesky(cholesky_inverse(cholesky(H)), upper=True) in float32 LAPACK, plus the dead-channel rule.
+    Returns (U, dead mask, damping steps of the first factorisation)."""
+    from scipy.linalg import lapack
+    H = np.array(H, dtype=F32)
+    dead = np.diag(H) == 0                                   # :95
+    H[dead, dead] = 1                                        # :96
+    damp = F32(percdamp) * np.mean(np.diag(H), dtype=F32)    # :111
+    L, steps = _chol_retry(H, damp, upper=False)             # :114-128
+    Hinv, info = lapack.spotri(L, lower=1)                   # :131  cholesky_inverse
+    Hinv = np.tril(Hinv) + np.tril(Hinv, -1).T
+    damp2 = F32(percdamp) * np.mean(np.abs(np.diag(Hinv)), dtype=F32)   # :143
+    U, _ = _chol_retry(Hinv.astype(F32), damp2, upper=True)  # :146-157
+    return np.triu(U).astype(F32), dead, steps
+
+
+def sparsegpt_fasterprune(W32, w_tag, H, sparsity, prune_n=0, prune_m=0, blocksize=128, percdamp=0.01, U=None,
+                          dead=None):
+    """The column-block OBS sweep (:160-215) in float32.  Returns (pruned W rounded to w_tag, importance score, U)."""
+    if U is None:
+        U, dead, _ = sparsegpt_inverse_factor(H, percdamp)
+    W = np.array(W32, dtype=F32)
+    if dead is not None:
+        W[:, dead] = 0                                       # :97
+    R, C = W.shape
+    dU = np.diag(U).astype(F32)
+    score = float(((W ** 2) / (dU[None, :] ** 2)).astype(np.float64).mean())      # :160-165
+    for i1 in range(0, C, blocksize):
+        i2 = min(i1 + blocksize, C)
+        count = i2 - i1
+        W1 = W[:, i1:i2].copy()
+        Q1 = np.zeros_like(W1)
+        Err1 = np.zeros_like(W1)
+        U1 = U[i1:i2, i1:i2]
+        d1 = np.diag(U1).astype(F32)
+        if prune_n == 0:
+            tmp = ((W1 * W1) / ((d1 * d1)[None, :])).astype(F32)
+            thresh = np.partition(tmp.ravel(), int(tmp.size * sparsity))[int(tmp.size * sparsity)]   # :184
+            mask1 = tmp <= thresh                                                                    # :185
+        else:
+            mask1 = np.zeros(W1.shape, dtype=bool)
+        for i in range(count):
+            w = W1[:, i]
+            d = U1[i, i]
+            if prune_n != 0 and i % prune_m == 0:
+                grp = ((W1[:, i:i + prune_m] ** 2) / ((d1[i:i + prune_m] ** 2)[None, :])).astype(F32)   # :194
+                order = np.argsort(grp, axis=1, kind="stable")[:, :prune_n]       # ties -> lower column (SURVEY F8)
+                np.put_along_axis(mask1[:, i:i + prune_m], order, True, axis=1)
+            q = np.where(mask1[:, i], F32(0), w).astype(F32)
+            Q1[:, i] = q
+            err = ((w - q) / d).astype(F32)
+            W1[:, i:] = (W1[:, i:] - (err[:, None] * U1[i, i:][None, :]).astype(F32)).astype(F32)   # :204
+            Err1[:, i] = err
+        W[:, i1:i2] = Q1
+        if i2 < C:
+            W[:, i2:] = (W[:, i2:] - Err1 @ U[i1:i2, i2:]).astype(F32)             # :210
+    return round_to_dtype(W, w_tag), score, U
+
+
+# ---------------------------------------------------------------------------------------------
 # return_reorder_indice                          dsnot_pruner.py:1881-1925
 # ---------------------------------------------------------------------------------------------
 def return_reorder_indice(t):

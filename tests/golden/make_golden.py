@@ -176,6 +176,42 @@ def gen_lora_merge(ref):
     save("lora_merge.npz", **out)
 
 
+def gen_sparsegpt(ref):
+    """The reference's SparseGPT class on one linear: add_batch x3 then fasterprune, in three regimes."""
+    out = {}
+    cases = {
+        # name: (R, C, tokens per call, weight dtype, act dtype, sparsity, n, m, dead channel)
+        "unstr_bf16": (40, 256, 384, torch.bfloat16, torch.bfloat16, 0.5, 0, 0, False),
+        "nm24_f16": (40, 256, 384, torch.float16, torch.float16, 0.0, 2, 4, False),
+        "damped_bf16": (24, 256, 64, torch.bfloat16, torch.bfloat16, 0.5, 0, 0, False),     # 192 tokens < C: not PD
+        "dead_f16": (24, 128, 256, torch.float16, torch.float16, 0.6, 0, 0, True),
+        "ragged_f32": (16, 200, 512, torch.float32, torch.float16, 0.5, 0, 0, False),        # C % 128 != 0
+    }
+    for name, (R, C, T, wdt, adt, sp, n, m, dead) in cases.items():
+        g = torch.Generator().manual_seed(sum(map(ord, name)))
+        lin = nn.Linear(C, R, bias=False)
+        lin.weight.data = (torch.randn(R, C, generator=g) * 0.05).to(wdt)
+        sg = ref.sparsegpt.SparseGPT(lin)
+        for i in range(3):
+            x = act((1, T, C), 40 + i, adt, C)
+            if dead:
+                x[..., 5] = 0
+                x[..., 77] = 0
+            sg.add_batch(x, None)
+            if name == "unstr_bf16":        # activations are kept for one case only (the others pin fasterprune on H)
+                out[f"{name}|x{i}"] = packw(x)
+        out[f"{name}|H"] = f32(sg.H)
+        out[f"{name}|W_before"] = f32(lin.weight)
+        out[f"{name}|tag"] = np.array(TAG[wdt])
+        out[f"{name}|atag"] = np.array(TAG[adt])
+        out[f"{name}|cfg"] = np.array([sp, n, m], dtype=np.float64)
+        sg.fasterprune(sp, prune_n=n, prune_m=m, percdamp=0.01, blocksize=128)
+        out[f"{name}|W_after"] = f32(lin.weight)
+        out[f"{name}|importance_score"] = np.float64(lin.weight.importance_score)
+    out["cases"] = np.array(list(cases))
+    save("sparsegpt.npz", **out)
+
+
 def gen_reorder(ref):
     doc = torch.tensor([[1., -2., 3.], [-2., 2., -4.], [5., 6., -7.], [-6., -7., -4.]])
     g = torch.Generator().manual_seed(3)
@@ -190,7 +226,7 @@ def main():
     ref = ref_loader.load()
     only = set(sys.argv[1:])
     gens = dict(wanda_stats=gen_wanda_stats, dsnot_stats=gen_dsnot_stats, wanda_toy=gen_wanda_toy,
-                lora_merge=gen_lora_merge, reorder=gen_reorder)
+                lora_merge=gen_lora_merge, sparsegpt=gen_sparsegpt, reorder=gen_reorder)
     for name, fn in gens.items():
         if not only or name in only:
             fn(ref)

@@ -441,3 +441,122 @@ def test_hessian_long_accumulation_chunks(native):
     print("hessian rel err vs kc:", errs)
     assert errs[256] < REL / 2 and errs[512] < REL / 2       # default kc = 512
     assert errs[16384] > errs[512]                            # the drift the chunking is there to bound
+
+
+# ------------------------------------------------------------------------------------------- K10-K13 SparseGPT
+def _factor(native, H, percdamp=0.01):
+    damp, dead = native.hessian_prepare(H, percdamp)
+    steps = 0
+    while True:
+        U, status = native.chol_inv_upper(H)
+        if status.item() == 0:
+            return U, dead, steps
+        native.hessian_add_damp(H, damp)
+        steps += 1
+        assert steps < 100
+
+
+@pytest.mark.parametrize("C,T", [(128, 512), (200, 1024), (256, 1024), (1408, 6000), (2048, 8192)])
+def test_chol_inv_upper_vs_fp64(native, C, T):
+    x = acts(T, C, C, torch.float16).cuda()
+    H = torch.zeros(C, C, device="cuda")
+    native.hessian_accum(x, H, 0, 1)
+    H0 = H.clone()
+    U, status = native.chol_inv_upper(H)
+    assert status.item() == 0 and torch.equal(H, H0)               # H is not modified
+    assert float(U.tril(-1).abs().max()) == 0.0                    # exactly upper triangular
+    Uref = torch.linalg.cholesky(torch.linalg.inv(H.double()), upper=True)
+    assert float((U.double() - Uref).abs().max() / Uref.abs().max()) < 1e-5
+    # and against the reference's own 3-step fp32 LAPACK chain (oracle)
+    Uo, _, _ = oracle.sparsegpt_inverse_factor(H.cpu().numpy())
+    assert rel_inf(U.cpu().numpy(), Uo) < 1e-4
+
+
+def test_chol_not_posdef_then_damped(native):
+    """Fewer tokens than channels: the first attempt must report NOT_POSDEF, the damped retries must succeed
+    (reference: conditional, cumulative damping, sparsegpt_pruner.py:114-128)."""
+    g = gu.load("sparsegpt.npz")
+    H = torch.from_numpy(g["damped_bf16|H"]).cuda()
+    U, status = native.chol_inv_upper(H)
+    assert status.item() == native.NOT_POSDEF
+    U, dead, steps = _factor(native, H)
+    _, _, steps_ref = oracle.sparsegpt_inverse_factor(g["damped_bf16|H"])
+    assert steps == steps_ref >= 1
+    assert int(dead.sum()) == 0
+
+
+def test_sparsegpt_golden(native):
+    """vlmc SparseGPT (add_batch on the tensor cores -> chol_inv_upper -> obs_sweep) against the reference's
+    fasterprune outputs: <= 1e-3 relative Frobenius, >= 99.9 % mask agreement (north_star)."""
+    from vlmc.compression.pruners.sparsegpt_pruner import SparseGPT
+    g = gu.load("sparsegpt.npz")
+    for name in g["cases"]:
+        sp, n, m = g[f"{name}|cfg"]
+        tag = str(g[f"{name}|tag"])
+        R, C = g[f"{name}|W_before"].shape
+        lin = torch.nn.Linear(C, R, bias=False).cuda()
+        lin.weight.data = gu.to_torch(g[f"{name}|W_before"], tag, "cuda")
+        sg = SparseGPT(lin)
+        if name == "unstr_bf16":          # full wrapper path including the Hessian kernel
+            for i in range(3):
+                sg.add_batch(gu.to_torch(gu.unpack_w(g[f"{name}|x{i}"], "bf16"), "bf16", "cuda"), None)
+            assert sg.nsamples == 3
+            assert rel_inf(sg.H.cpu().numpy(), g[f"{name}|H"]) < REL
+        else:
+            sg.H = torch.from_numpy(g[f"{name}|H"]).cuda()
+        sg.fasterprune(sp, prune_n=int(n), prune_m=int(m), percdamp=0.01, blocksize=128)
+        got = lin.weight.data.float().cpu().numpy()
+        ref = g[f"{name}|W_after"]
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-3, name
+        assert ((got == 0) == (ref == 0)).mean() >= 0.999, name
+        assert abs(lin.weight.importance_score - float(g[f"{name}|importance_score"])) < 1e-4 * abs(lin.weight.importance_score)
+        assert lin.weight.dtype == DT[tag]
+
+
+@pytest.mark.parametrize("R,C,sp,n,m", [(96, 512, 0.5, 0, 0), (64, 384, 0.7, 0, 0), (80, 512, 0.0, 2, 4),
+                                        (48, 256, 0.0, 4, 8), (300, 1408, 0.5, 0, 0)])
+def test_obs_sweep_vs_oracle_same_factor(native, R, C, sp, n, m):
+    """The sweep alone (same U fed to both): masks bit-exact, weights to fp32 rounding of the trailing GEMM."""
+    x = acts(4 * C, C, R, torch.bfloat16).cuda()
+    H = torch.zeros(C, C, device="cuda")
+    native.hessian_accum(x, H, 0, 1)
+    U, dead, _ = _factor(native, H)
+    W0 = weights(R, C, 77, torch.bfloat16, 0.05)
+    W = W0.clone().cuda()
+    keep, score = native.obs_sweep(W, U, sp, n, m, dead=dead, want_mask=True)
+    Wo, so, _ = oracle.sparsegpt_fasterprune(W0.float().numpy(), "bf16", None, sp, n, m, U=U.cpu().numpy(),
+                                             dead=dead.cpu().numpy().astype(bool))
+    got = W.float().cpu().numpy()
+    assert ((got == 0) == (Wo == 0)).mean() >= 0.9999
+    assert np.linalg.norm(got - Wo) / np.linalg.norm(Wo) < 1e-4
+    assert np.array_equal(keep.cpu().numpy(), got != 0) or (W0 == 0).any()
+    assert abs(score.item() - so) < 1e-4 * abs(so)
+    if n:
+        assert bool((keep.view(R, C // m, m).sum(-1) == m - n).all())
+    else:
+        nblk = C // 128
+        per_block = (~keep).view(R, nblk, 128).sum((0, 2))
+        assert bool((per_block >= int(R * 128 * sp) + 1).all())     # `<=` threshold: at least k+1 per block (:185)
+
+
+def test_sparsegpt_full_size_properties(native):
+    """Vicuna-7B q_proj size: 2:4 structure exact, unstructured per-block counts, output error no worse than
+    magnitude pruning at the same sparsity (the point of the OBS compensation)."""
+    R = C = 4096
+    x = acts(4 * C, C, 3, torch.float16).cuda()
+    H = torch.zeros(C, C, device="cuda")
+    native.hessian_accum(x, H, 0, 1)
+    U, dead, steps = _factor(native, H)
+    assert steps == 0
+    W0 = (torch.randn(R, C, device="cuda") * 0.02).half()
+    W = W0.clone()
+    keep, _ = native.obs_sweep(W, U, 0.0, 2, 4, dead=dead, want_mask=True)
+    assert bool((keep.view(R, C // 4, 4).sum(-1) == 2).all())
+    assert bool((W[~keep] == 0).all())
+    xs = x[:2048].float()
+    err_obs = float(((xs @ (W.float() - W0.float()).T) ** 2).sum())
+    Wmag = W0.clone()
+    idx = W0.abs().view(R, C // 4, 4).argsort(-1)[..., :2]
+    Wmag.view(R, C // 4, 4).scatter_(-1, idx, 0)
+    err_mag = float(((xs @ (Wmag.float() - W0.float()).T) ** 2).sum())
+    assert err_obs < 0.8 * err_mag

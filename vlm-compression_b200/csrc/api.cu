@@ -5,6 +5,8 @@ namespace vlmc {
 thread_local int g_last_cuda_error = 0;
 size_t stats_workspace_bytes(int dsnot, int64_t T, int C, int64_t nseg);
 size_t threshold_workspace_bytes(int R, int C);
+size_t chol_workspace_bytes(int C);
+size_t obs_workspace_bytes(int R, int C);
 }  // namespace vlmc
 
 extern "C" int vlmc_version(void) { return VLMC_ABI_VERSION; }
@@ -37,6 +39,9 @@ extern "C" size_t vlmc_workspace_bytes(int op, int64_t d0, int64_t d1, int64_t d
       return a > b ? a : b;
     }
     case VLMC_OP_LORA_MERGE: return VLMC_WS_COUNTER_BYTES;
+    case VLMC_OP_HESSIAN: return VLMC_WS_COUNTER_BYTES;
+    case VLMC_OP_CHOL: return chol_workspace_bytes((int)d0);
+    case VLMC_OP_OBS: return obs_workspace_bytes((int)d0, (int)d1);
     default: return 0;
   }
 }

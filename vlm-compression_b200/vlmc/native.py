@@ -44,6 +44,10 @@ SIGNATURES = {
     "vlmc_wanda_nm": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_wanda_threshold": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_sparselora_merge": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _f, _vp, _i64, _i, _vp]),
+    "vlmc_hessian_prepare": (_i, [_vp, _i, _i64, _f, _vp, _vp, _vp]),
+    "vlmc_hessian_add_damp": (_i, [_vp, _i, _i64, _vp, _vp]),
+    "vlmc_chol_inv_upper": (_i, [_vp, _i, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "vlmc_obs_sweep": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp, _d, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_hessian_accum": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _d, _d, _i, _i64, _vp]),
 }
 
@@ -241,3 +245,63 @@ def hessian_accum(x, H, n_before, b, kc=0, slab_tokens=0):
         st = lib.vlmc_hessian_accum(x2.data_ptr(), _dtype(x2), T, C, x2.stride(0), H.data_ptr(), H.stride(0),
                                     float(n_before), float(b), int(kc), int(slab_tokens), _stream(x2))
     _check("vlmc_hessian_accum", st)
+
+
+def hessian_prepare(H, percdamp):
+    """sparsegpt_pruner.py:95-96,111: fix dead channels in place; returns (damp 1-elem tensor, dead uint8 [C])."""
+    _require_cuda(H)
+    lib = load()
+    C = H.shape[0]
+    damp = torch.empty(1, dtype=torch.float32, device=H.device)
+    dead = torch.empty(C, dtype=torch.uint8, device=H.device)
+    with torch.cuda.device(H.device):
+        st = lib.vlmc_hessian_prepare(H.data_ptr(), C, H.stride(0), float(percdamp), damp.data_ptr(), dead.data_ptr(),
+                                      _stream(H))
+    _check("vlmc_hessian_prepare", st)
+    return damp, dead
+
+
+def hessian_add_damp(H, damp):
+    _require_cuda(H, damp)
+    lib = load()
+    with torch.cuda.device(H.device):
+        st = lib.vlmc_hessian_add_damp(H.data_ptr(), H.shape[0], H.stride(0), damp.data_ptr(), _stream(H))
+    _check("vlmc_hessian_add_damp", st)
+
+
+def chol_inv_upper(H, U=None):
+    """K10: returns (U, status tensor).  status.item() == NOT_POSDEF means: damp and retry."""
+    _require_cuda(H)
+    lib = load()
+    C = H.shape[0]
+    if H.dtype != torch.float32 or H.shape != (C, C) or H.stride(1) != 1:
+        raise ValueError("H must be a float32 [C, C] row-major matrix")
+    if U is None:
+        U = torch.empty((C, C), dtype=torch.float32, device=H.device)
+    status = torch.zeros(1, dtype=torch.int32, device=H.device)
+    ws = workspace(H, lib.vlmc_workspace_bytes(OP_CHOL, C, 0, 0))
+    with torch.cuda.device(H.device):
+        st = lib.vlmc_chol_inv_upper(H.data_ptr(), C, H.stride(0), U.data_ptr(), U.stride(0), status.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), _stream(H))
+    _check("vlmc_chol_inv_upper", st)
+    return U, status
+
+
+def obs_sweep(W, U, sparsity, prune_n=0, prune_m=0, dead=None, blocksize=128, want_mask=False):
+    """K11-K13 (sparsegpt_pruner.py:160-215), in place on W.  Returns (keep_mask or None, importance 1-elem tensor)."""
+    _require_cuda(W, U, dead)
+    if W.dim() != 2 or W.stride(1) != 1:
+        raise ValueError("W must be a 2-D row-major weight")
+    lib = load()
+    R, C = W.shape
+    keep = torch.empty((R, C), dtype=torch.bool, device=W.device) if want_mask else None
+    score = torch.empty(1, dtype=torch.float32, device=W.device)
+    ws = workspace(W, lib.vlmc_workspace_bytes(OP_OBS, R, C, blocksize))
+    with torch.cuda.device(W.device):
+        st = lib.vlmc_obs_sweep(W.data_ptr(), _dtype(W), R, C, W.stride(0), U.data_ptr(), U.stride(0),
+                                dead.data_ptr() if dead is not None else None, float(sparsity), int(prune_n),
+                                int(prune_m), int(blocksize), keep.data_ptr() if keep is not None else None,
+                                keep.stride(0) if keep is not None else 0, score.data_ptr(), ws.data_ptr(), ws.numel(),
+                                _stream(W))
+    _check("vlmc_obs_sweep", st)
+    return keep, score
