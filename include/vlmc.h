@@ -56,7 +56,7 @@ enum vlmc_op {
   VLMC_OP_HESSIAN = 4,      /* (T, C, 0)       */
   VLMC_OP_CHOL = 5,         /* (C, 0, 0)       */
   VLMC_OP_OBS = 6,          /* (R, C, blocksize) */
-  VLMC_OP_DSNOT_REFINE = 7  /* (R, C, 0)       */
+  VLMC_OP_DSNOT_REFINE = 7  /* (R, C, max_cycle_time) */
 };
 
 int vlmc_version(void);
@@ -183,6 +183,41 @@ int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, const float* U
                    const uint8_t* dead, double sparsity, int prune_n, int prune_m, int blocksize,
                    uint8_t* keep_mask, int64_t ldm, float* importance_score,
                    void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * K8+K9  DSnoT mask refinement.  Replaces the per-linear body of the DSnoT pruners, dsnot_pruner.py:359-755 (T5 / LLM)
+ * and :1092-1485 (ViT): DSnoT_metric = W * sum_metric_row, the Wanda (or magnitude) initial mask, the three stable row
+ * orderings + return_reorder_indice (:555-612, :1881-1925) and the prune / regrow cycle loop (:650-751; n:m :407-552).
+ * Two passes, because the reference's `while any(update_mask)` couples all rows through the number of executed cycles:
+ *   _walk   per row: initial selection, ordered candidate prefixes, the cycle loop; records every cycle's
+ *           (pruned column, regrown column) in ws and atomically maxes *ncycles (device int, zeroed by the call).
+ *           When rows are sharded across GPUs the caller all-reduces (MAX) *ncycles between the two passes.
+ *   _apply  per row: initial mask + the recorded writes of the first *ncycles cycles -> keep_mask (1 = kept) and,
+ *           if zero_w, zeroed weights (:753-755).  Same ws as _walk.
+ * vlmc_dsnot_refine runs both back to back (one device).
+ *   k                  unstructured prune count per row = round(C * sparsity) (python round, :562); ignored for n:m
+ *   prune_n, prune_m   0,0 = unstructured; otherwise n of every m consecutive columns, m <= 8
+ *   pow_of_var, max_cycle_time (<= 128), update_threshold, without_same_sign: the reference's knobs (:1629-1636)
+ *   initial_magnitude  0: initial_method "wanda" (:370-374); 1: "magnitude" (:375-376)
+ *   argmin_rule        tie-break of topk(1, largest=False) at :517 when a whole group is +inf: 0 lowest column,
+ *                      1 what torch's CPU kernel returns (std::nth_element order) - matches the CPU reference
+ *   ref_fixup          1: as shipped, the block at :734-740 writes every swap back; 0: upstream DSnoT
+ * Unsupported (the reference indexes out of bounds there): C < max_cycle_time, C - k < max_cycle_time.
+ */
+int vlmc_dsnot_refine_walk(const void* W, int dtype, int R, int C, int64_t ldw, const float* scaler_row,
+                           const float* sum_metric_row, const float* var, int k, int prune_n, int prune_m,
+                           float pow_of_var, int max_cycle_time, float update_threshold, int without_same_sign,
+                           int initial_magnitude, int argmin_rule, int* ncycles, void* ws, size_t ws_bytes,
+                           void* stream);
+int vlmc_dsnot_refine_apply(void* W, int dtype, int R, int C, int64_t ldw, const float* scaler_row,
+                            int prune_n, int prune_m, int initial_magnitude, int max_cycle_time,
+                            const int* ncycles, int ref_fixup, int zero_w, uint8_t* keep_mask, int64_t ldm,
+                            void* ws, size_t ws_bytes, void* stream);
+int vlmc_dsnot_refine(void* W, int dtype, int R, int C, int64_t ldw, const float* scaler_row,
+                      const float* sum_metric_row, const float* var, int k, int prune_n, int prune_m,
+                      float pow_of_var, int max_cycle_time, float update_threshold, int without_same_sign,
+                      int initial_magnitude, int argmin_rule, int ref_fixup, int zero_w, uint8_t* keep_mask,
+                      int64_t ldm, int* ncycles, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -285,3 +285,203 @@ def return_reorder_indice(t):
             row[C - pos.size:] += pos[::-1]
         out[r] = row
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# a6 / K8-K9  DSnoT refine                        dsnot_pruner.py:359-755 (ViT copy :1092-1485)
+# ---------------------------------------------------------------------------------------------
+def _rowsum_f32(a):
+    """torch.sum(x, dim=1, keepdim=True) on float32: accumulated wide, rounded once (the kernels do the same)."""
+    return a.astype(np.float64).sum(axis=1, keepdims=True).astype(F32)
+
+
+def _take(a, idx):
+    return np.take_along_axis(a, idx, axis=1)
+
+
+def torch_cpu_argmin(vals):
+    """Index torch.topk(vals, 1, largest=False) returns on CPU for a short row (dsnot_pruner.py:517).
+
+    For n < 64 ATen calls std::nth_element(begin, begin, end) on (value, index) pairs (TopKImpl.h); with tied
+    minima the winner is whatever libstdc++'s introselect leaves in front, so that algorithm is restated here
+    (median-of-3 pivot to front, unguarded Hoare partition, insertion sort below 4 elements).  NaN sorts last.
+    """
+    q = [(float(v), i) for i, v in enumerate(vals)]
+
+    def lt(x, y):
+        return (y[0] != y[0] and x[0] == x[0]) or x[0] < y[0]
+
+    first, last, nth = 0, len(q), 0
+    depth = 2 * (len(q).bit_length() - 1)
+    while last - first > 3:
+        if depth == 0:      # heap-select fallback: unreachable for the group widths used here (m <= 32)
+            best = first
+            for i in range(first + 1, last):
+                if lt(q[i], q[best]):
+                    best = i
+            q[first], q[best] = q[best], q[first]
+            return q[first][1]
+        depth -= 1
+        mid = first + (last - first) // 2
+        a, b, c = first + 1, mid, last - 1
+        if lt(q[a], q[b]):
+            pick = b if lt(q[b], q[c]) else (c if lt(q[a], q[c]) else a)
+        else:
+            pick = a if lt(q[a], q[c]) else (c if lt(q[b], q[c]) else b)
+        q[first], q[pick] = q[pick], q[first]
+        lo, hi = first + 1, last
+        while True:
+            while lt(q[lo], q[first]):
+                lo += 1
+            hi -= 1
+            while lt(q[first], q[hi]):
+                hi -= 1
+            if not lo < hi:
+                break
+            q[lo], q[hi] = q[hi], q[lo]
+            lo += 1
+        if lo <= nth:
+            first = lo
+        else:
+            last = lo
+    for i in range(first + 1, last):       # insertion sort of the last <= 3 candidates
+        j = i
+        while j > first and lt(q[j], q[j - 1]):
+            q[j], q[j - 1] = q[j - 1], q[j]
+            j -= 1
+    return q[nth][1]
+
+
+def _group_argmin(block, rule):
+    """Row-wise argmin of [R, m]; rule 'lowest' = lowest index among tied minima, 'torch_cpu' = torch_cpu_argmin."""
+    am = np.argmin(block, axis=1)
+    if rule == "lowest":
+        return am
+    mn = block[np.arange(block.shape[0]), am]
+    tied = (block == mn[:, None]).sum(axis=1) > 1
+    for r in np.nonzero(tied)[0]:
+        am[r] = torch_cpu_argmin(block[r])
+    return am
+
+
+def dsnot_refine(W32, scaler_row, sum_metric_row, var, sparsity_num=0, prune_n=0, prune_m=0, pow_of_var=1.0,
+                 max_cycle_time=100, update_threshold=0.1, without_same_sign=True, initial_method="wanda",
+                 ref_fixup=True, argmin_rule="torch_cpu"):
+    """One linear's DSnoT mask.  Returns (keep_mask bool [R, C], cycles executed).
+
+    sparsity_num = round(C * p) is computed by the caller (:562; python round, not int - SURVEY F5).
+    ref_fixup=True reproduces the shipped reference including the block at :734-740 that writes the swap back
+    (SURVEY F4); False gives the upstream DSnoT behaviour (that block excised).  The n:m branch has no such block.
+    Tie-breaks: the unstable per-group sort at :423 is taken as lowest-column-first; the topk at :517
+    meets structural ties (groups whose members were all set to +inf) and follows argmin_rule.
+    """
+    W = np.asarray(W32, dtype=F32)
+    R, C = W.shape
+    D = (W * sum_metric_row.astype(F32)[None, :]).astype(F32)                       # :368 DSnoT_metric
+    wanda = (np.abs(W) * np.sqrt(scaler_row.astype(F32))[None, :]).astype(F32)
+    initial = wanda.copy() if initial_method == "wanda" else np.abs(W).astype(F32)  # :370-376
+    mask = np.zeros((R, C), dtype=bool)                                             # True = pruned (:405)
+    thr = F32(update_threshold)
+    rows = np.arange(R)[:, None]
+    varp = None
+    if pow_of_var:
+        varp = var.astype(F32).reshape(1, -1) if pow_of_var == 1 else \
+            np.power(var.astype(F32).reshape(1, -1), F32(pow_of_var)).astype(F32)
+    max_cycle_time = int(max_cycle_time)
+
+    def sign(x):
+        return np.sign(x).astype(F32)
+
+    if prune_n != 0:
+        m, n = prune_m, prune_n
+        G = initial.reshape(R, C // m, m)
+        order = np.argsort(G, axis=2, kind="stable") + (np.arange(C // m) * m)[None, :, None]   # :420-424
+        prune_idx = order[:, :, :n].reshape(R, -1)
+        res_idx = order[:, :, n:].reshape(R, -1)
+        np.put_along_axis(mask, prune_idx, True, axis=1)                            # :438
+        reg = D.copy()
+        np.put_along_axis(reg, res_idx, F32(0), axis=1)                             # :442
+        err = _rowsum_f32(reg)                                                      # :444
+        sign0 = sign(err)
+        if varp is not None:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                reg = (reg / varp).astype(F32)                                      # :447-451
+        reg_order = np.argsort(reg, axis=1, kind="stable")                          # :453 (NaN last, like torch)
+        ptr = np.zeros((R, 2), dtype=np.int64)
+        ptr[:, 1] = C - 1
+        step = np.array([1, -1], dtype=np.int64)
+        np.put_along_axis(initial, prune_idx, F32(np.inf), axis=1)                  # :469
+        upd = np.ones((R, 1), dtype=bool)
+        cycles = 0
+        while upd.any() and cycles < max_cycle_time:                                # :476-479 (1..max inclusive)
+            cycles += 1
+            which = (err > 0).astype(np.int64)                                      # :483
+            p = _take(ptr, which)
+            rg = _take(reg_order, p)
+            rm = _take(D, rg)
+            start = rg - rg % m                                                     # :502
+            blk = start + np.arange(m)[None, :]
+            pr = start + _group_argmin(_take(initial, blk), argmin_rule)[:, None]    # :513-521 topk(1, smallest)
+            pm = _take(D, pr)
+            after = ((err + pm).astype(F32) - rm).astype(F32)                       # :525
+            upd = upd & (sign0 == sign(after)) & (np.abs(err) > thr)                # :527
+            np.put_along_axis(initial, pr, F32(np.inf), axis=1)                     # :529 (max + 1 == inf)
+            np.put_along_axis(mask, pr, upd, axis=1)                                # :531
+            np.put_along_axis(mask, rg, ~upd, axis=1)                               # :532
+            err = (err + np.where(upd, pm, F32(0))).astype(F32)                     # :534
+            err = (err - np.where(upd, rm, F32(0))).astype(F32)                     # :539
+            np.put_along_axis(ptr, which, p + step[which], axis=1)                  # :545
+        return ~mask, cycles
+
+    k = int(sparsity_num)
+    order0 = np.argsort(initial, axis=1, kind="stable")                             # :555
+    prune_idx, res_idx = order0[:, :k], order0[:, k:]
+    np.put_along_axis(mask, prune_idx, True, axis=1)                                # :581
+    wm = wanda.copy()
+    np.put_along_axis(wm, prune_idx, F32(np.inf), axis=1)                           # :586
+    wres = np.argsort(wm, axis=1, kind="stable")[:, :C - k]                         # :587-591
+    reorder = return_reorder_indice(_take(D, wres))                                 # :592
+    prune_block = _take(wres, reorder)                                              # :595
+    reg = D.copy()
+    np.put_along_axis(reg, res_idx, F32(0), axis=1)                                 # :600
+    err = _rowsum_f32(reg)                                                          # :601
+    sign0 = sign(err)
+    if varp is not None:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            reg = (reg / varp).astype(F32)                                          # :604-608
+    reg_order = np.argsort(reg, axis=1, kind="stable")                              # :610
+    ptr_r = np.zeros((R, 2), dtype=np.int64)
+    ptr_r[:, 1] = C - 1
+    ptr_p = np.zeros((R, 2), dtype=np.int64)
+    ptr_p[:, 1] = prune_block.shape[1] - 1
+    step = np.array([1, -1], dtype=np.int64)
+    upd = np.ones((R, 1), dtype=bool)
+    cycles = 0
+    while upd.any() and cycles < max_cycle_time:                                    # :650
+        cycles += 1
+        wr = (err > 0).astype(np.int64)                                             # :654
+        p = _take(ptr_r, wr)
+        rg = _take(reg_order, p)                                                    # raises IndexError like torch (F12)
+        rm = _take(D, rg)
+        np.put_along_axis(ptr_r, wr, p + step[wr], axis=1)                          # :673
+        wp = (err < 0).astype(np.int64)                                             # :683
+        q = _take(ptr_p, wp)
+        if (q < 0).any() or (q >= prune_block.shape[1]).any():
+            raise IndexError("prune pointer out of range (reference fails the same way, SURVEY F12)")
+        pr = _take(prune_block, q)
+        pm = _take(D, pr)
+        np.put_along_axis(ptr_p, wp, q + step[wp], axis=1)                          # :703
+        after = ((err + pm).astype(F32) - rm).astype(F32)                           # :713
+        if without_same_sign:
+            upd = upd & (np.abs(err) > thr)                                         # :717-720
+        else:
+            upd = upd & (np.abs(err) > thr) & (sign0 == sign(after))                # :722-729
+        np.put_along_axis(mask, pr, upd, axis=1)                                    # :731
+        np.put_along_axis(mask, rg, ~upd, axis=1)                                   # :732
+        if ref_fixup:                                                               # :734-740
+            sub_p, sub_r = _take(mask, pr), _take(mask, rg)
+            np.put_along_axis(mask, pr, sub_p & ~upd, axis=1)
+            np.put_along_axis(mask, rg, upd | (sub_r & ~upd), axis=1)
+        err = (err + np.where(upd, pm, F32(0))).astype(F32)                         # :742
+        err = (err - np.where(upd, rm, F32(0))).astype(F32)                         # :747
+    return ~mask, cycles

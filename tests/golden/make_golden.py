@@ -98,6 +98,7 @@ def run_composite(ref, which, cfg, seed=0, **model_kw):
     else:
         mod.WrappedGPT = Recording
     try:
+        torch.manual_seed(seed)          # biases / embeddings come from the global generator
         model = toy_model.ToyBlip(seed=seed, **model_kw).eval()
         before = {n: p.detach().clone() for n, p in model.named_parameters()}
         cls = {"wanda": "BLIPT5LayerWandaPruner", "dsnot": "BLIPT5LayerDSnoTPruner",
@@ -150,6 +151,56 @@ def gen_wanda_toy(ref):
         cfg = toy_model.pruner_cfg(0.5, 0.5, prune_n=n, prune_m=m)
         model, before, rec = run_composite(ref, "wanda", cfg)
         save(f"wanda_toy_{n}of{m}.npz", **collect_layers(model, before, rec, ["scaler_row"]))
+
+
+DSNOT_TOY = dict(d_llm=296, ff=488, n_llm=1, n_vit=0)      # round(C*0.6) != int(C*0.6) for both widths
+
+
+def _excise_fixup(text):
+    """dsnot_pruner.py with the swap write-back block (:734-740 and its ViT copy) removed = upstream DSnoT."""
+    lines = text.split("\n")
+    out, skip = [], 0
+    for ln in lines:
+        if "sub_mask_prune = torch.gather(weight_mask, 1, pruning_indice)" in ln:
+            skip = 7                                   # the 6 statements + the blank line between them
+        if skip:
+            skip -= 1
+            continue
+        out.append(ln)
+    assert len(lines) - len(out) == 14, len(lines) - len(out)
+    return "\n".join(out)
+
+
+def gen_dsnot_toy(ref):
+    """Reference composite DSnoT pruner on a 1-layer toy LLM (rows need > 100 kept and pruned columns).
+    All cases share the model seed, so W_before and the statistics are stored once; each case adds its masks."""
+    stats = ["scaler_row", "sum_metric_row", "mean", "var"]
+    upstream = ref_loader.load(patch_source={"dsnot_pruner": _excise_fixup})
+    cases = {
+        # name: (module namespace, cfg overrides)
+        "shipped_unstr60": (ref, dict()),
+        "upstream_unstr60": (upstream, dict()),
+        "upstream_unstr60_samesign": (upstream, dict(without_same_sign=False)),
+        "upstream_unstr60_magnitude": (upstream, dict(initial_method="magnitude")),
+        "shipped_2of4": (ref, dict(prune_n=2, prune_m=4)),
+        "shipped_4of8": (ref, dict(prune_n=4, prune_m=8)),
+        "shipped_without_dsnot": (ref, dict(without_DSnoT=True)),
+    }
+    out = {}
+    for name, (ns, extra) in cases.items():
+        cfg = toy_model.pruner_cfg(0.4, 1.0, **extra)
+        model, before, rec = run_composite(ns, "dsnot", cfg, **DSNOT_TOY)
+        got = collect_layers(model, before, rec, stats)
+        if "layers" not in out:
+            out.update({k: v for k, v in got.items() if not k.endswith("|mask")})
+        else:
+            for k in got:
+                if k.endswith("|W_before") or k.split("|")[-1] in stats:
+                    assert np.array_equal(out[k], got[k]), k
+        for key in got["layers"]:
+            out[f"{name}|{key}|mask"] = got[f"{key}|mask"]
+    out["cases"] = np.array(list(cases))
+    save("dsnot_toy.npz", **out)
 
 
 def gen_lora_merge(ref):
@@ -226,7 +277,7 @@ def main():
     ref = ref_loader.load()
     only = set(sys.argv[1:])
     gens = dict(wanda_stats=gen_wanda_stats, dsnot_stats=gen_dsnot_stats, wanda_toy=gen_wanda_toy,
-                lora_merge=gen_lora_merge, sparsegpt=gen_sparsegpt, reorder=gen_reorder)
+                dsnot_toy=gen_dsnot_toy, lora_merge=gen_lora_merge, sparsegpt=gen_sparsegpt, reorder=gen_reorder)
     for name, fn in gens.items():
         if not only or name in only:
             fn(ref)

@@ -34,3 +34,22 @@ def to_torch(w32, tag, device="cpu"):
     import torch
     dt = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}[tag]
     return torch.from_numpy(np.ascontiguousarray(w32)).to(dt).to(device)
+
+
+DSNOT_CASES = {   # golden case -> oracle / kernel keyword arguments (tests/golden/make_golden.py gen_dsnot_toy)
+    "shipped_unstr60": dict(),
+    "upstream_unstr60": dict(ref_fixup=False),
+    "upstream_unstr60_samesign": dict(ref_fixup=False, without_same_sign=False),
+    "upstream_unstr60_magnitude": dict(ref_fixup=False, initial_method="magnitude"),
+    "shipped_2of4": dict(prune_n=2, prune_m=4),
+    "shipped_4of8": dict(prune_n=4, prune_m=8),
+}
+
+
+def dsnot_layer(npz, case, key):
+    """(W float32, dtype tag, stats dict, reference keep mask) of one linear of one DSnoT golden case."""
+    tag = str(npz[f"{key}|tag"])
+    W = unpack_w(npz[f"{key}|W_before"], tag)
+    keep = np.unpackbits(npz[f"{case}|{key}|mask"], axis=1)[:, :W.shape[1]].astype(bool)
+    stats = {s: npz[f"{key}|{s}"] for s in ("scaler_row", "sum_metric_row", "var")}
+    return W, tag, stats, keep

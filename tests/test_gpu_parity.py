@@ -560,3 +560,158 @@ def test_sparsegpt_full_size_properties(native):
     Wmag.view(R, C // 4, 4).scatter_(-1, idx, 0)
     err_mag = float(((xs @ (Wmag.float() - W0.float()).T) ** 2).sum())
     assert err_obs < 0.8 * err_mag
+
+
+# ------------------------------------------------------------------------------------------- K8 + K9 DSnoT refine
+def _dsnot_stats(C, seed, positive=False):
+    g = torch.Generator().manual_seed(seed)
+    scal = (torch.exp(torch.rand(C, generator=g) * 4 - 2) * 50).float()
+    summ = (torch.randn(C, generator=g) * 20).float()
+    if positive:
+        summ = summ.abs() + 0.5
+    var = (torch.exp(torch.rand(C, generator=g) * 3 - 2)).float()
+    return scal, summ, var
+
+
+def _run_dsnot(native, W32, tag, scal, summ, var, k, **kw):
+    W = gu.to_torch(W32, tag, "cuda")
+    keep, ncyc = native.dsnot_refine(W, scal.cuda(), summ.cuda(), var.cuda(), k, **kw)
+    torch.cuda.synchronize()
+    return keep.cpu().numpy(), int(ncyc.item()), W.float().cpu().numpy()
+
+
+@pytest.mark.parametrize("case", list(gu.DSNOT_CASES))
+def test_dsnot_refine_golden(native, case):
+    """The reference's own masks (CPU run, committed fixture), bit-exact, for every linear of the toy layer."""
+    g = gu.load("dsnot_toy.npz")
+    cfg = dict(gu.DSNOT_CASES[case])
+    for key in g["layers"]:
+        W32, tag, st, ref_keep = gu.dsnot_layer(g, case, key)
+        k = round(W32.shape[1] * 0.6)
+        keep, ncyc, Wp = _run_dsnot(native, W32, tag, torch.from_numpy(st["scaler_row"]), torch.from_numpy(st["sum_metric_row"]),
+                                    torch.from_numpy(st["var"]), k, **cfg)
+        assert np.array_equal(keep, ref_keep), (case, key, int((keep != ref_keep).sum()))
+        assert np.array_equal(Wp, np.where(ref_keep, W32, np.float32(0)))
+
+
+@pytest.mark.parametrize("R,C,tag,p,kw", [
+    (96, 4096, "f16", 0.6, dict(ref_fixup=False)),
+    (64, 11008, "f16", 0.6, dict(ref_fixup=False)),
+    (64, 1408, "f32", 0.5, dict(ref_fixup=False, without_same_sign=False)),
+    (48, 2048, "bf16", 0.5, dict(ref_fixup=True)),
+    (64, 4096, "f16", 0.0, dict(prune_n=2, prune_m=4)),
+    (64, 2048, "bf16", 0.0, dict(prune_n=4, prune_m=8)),
+    (40, 1024, "f16", 0.7, dict(ref_fixup=False, initial_method="magnitude", pow_of_var=0.5, max_cycle_time=64)),
+    (40, 1024, "f16", 0.7, dict(ref_fixup=False, pow_of_var=0.0, update_threshold=0.01)),
+])
+def test_dsnot_refine_vs_oracle(native, R, C, tag, p, kw):
+    W = weights(R, C, 21, DT[tag]).float().numpy()
+    scal, summ, var = _dsnot_stats(C, 22)
+    k = round(C * p)
+    okw = dict(kw)
+    keep, ncyc, Wp = _run_dsnot(native, W, tag, scal, summ, var, k, **kw)
+    keep_o, cyc_o = oracle.dsnot_refine(W, scal.numpy(), summ.numpy(), var.numpy(), sparsity_num=k, **okw)
+    assert ncyc == cyc_o
+    assert np.array_equal(keep, keep_o), int((keep != keep_o).sum())
+    assert np.array_equal(Wp, np.where(keep_o, W, np.float32(0)))
+
+
+def test_dsnot_refine_pointer_leaves_its_sign_class(native):
+    """All-positive DSnoT metric on the kept side and few negatives among the pruned: the prune pointer walks through
+    the reorder filler (wanda_res_indices[0]) into the far end of the positive list and the regrow pointer into the
+    kept (zero) region - the paths that need the far lists and the tie ordering by column."""
+    R, C, tag = 32, 512, "f16"
+    g = torch.Generator().manual_seed(5)
+    W = (torch.rand(R, C, generator=g) * 0.04 + 0.001).half()          # all weights positive
+    W[:, ::7] *= -1                                                       # a few negative columns
+    W = W.float().numpy()
+    scal, summ, var = _dsnot_stats(C, 6, positive=True)
+    var[5] = 0.0                                                          # 0/0 -> NaN sorts last, x/0 -> inf
+    k = round(C * 0.5)
+    for kw in (dict(ref_fixup=False), dict(ref_fixup=True), dict(ref_fixup=False, without_same_sign=False)):
+        keep, ncyc, _ = _run_dsnot(native, W, tag, scal, summ, var, k, **kw)
+        keep_o, cyc_o = oracle.dsnot_refine(W, scal.numpy(), summ.numpy(), var.numpy(), sparsity_num=k, **kw)
+        assert ncyc == cyc_o and np.array_equal(keep, keep_o), (kw, int((keep != keep_o).sum()))
+
+
+def test_dsnot_refine_nm_exhausted_groups_and_tie_rules(native):
+    """Narrow rows make the regrow pointer run out of negatives, so groups fill up with +inf and topk(1) meets
+    structural ties: both tie rules must follow the oracle's."""
+    R, C, tag = 48, 160, "f16"
+    W = weights(R, C, 31, DT[tag]).float().numpy()
+    scal, summ, var = _dsnot_stats(C, 32)
+    for n, m in ((2, 4), (4, 8)):
+        for rule, name in ((0, "lowest"), (1, "torch_cpu")):
+            keep, ncyc, _ = _run_dsnot(native, W, tag, scal, summ, var, 0, prune_n=n, prune_m=m, argmin_rule=rule)
+            keep_o, cyc_o = oracle.dsnot_refine(W, scal.numpy(), summ.numpy(), var.numpy(), prune_n=n, prune_m=m,
+                                                argmin_rule=name)
+            assert ncyc == cyc_o and np.array_equal(keep, keep_o), (n, m, name, int((keep != keep_o).sum()))
+
+
+def test_dsnot_refine_ties_and_zero_weights(native):
+    """Quantised scores (many exact ties, zero weights with +-0 metrics): stable (score, column) order everywhere."""
+    R, C, tag = 24, 1024, "f16"
+    g = torch.Generator().manual_seed(9)
+    W = (torch.randint(-3, 4, (R, C), generator=g).float() * 0.01).numpy()
+    scal = torch.full((C,), 4.0)
+    summ = (torch.randint(-2, 3, (C,), generator=g).float() * 3.0)
+    var = torch.full((C,), 0.5)
+    k = round(C * 0.4)
+    for kw in (dict(ref_fixup=False), dict(ref_fixup=True)):
+        keep, ncyc, _ = _run_dsnot(native, W, tag, scal, summ, var, k, **kw)
+        keep_o, cyc_o = oracle.dsnot_refine(W, scal.numpy(), summ.numpy(), var.numpy(), sparsity_num=k, **kw)
+        assert ncyc == cyc_o and np.array_equal(keep, keep_o), (kw, int((keep != keep_o).sum()))
+
+
+def test_dsnot_refine_rejects_what_the_reference_cannot_index(native):
+    W = weights(8, 128, 1, torch.float16).cuda()
+    scal, summ, var = (t.cuda() for t in _dsnot_stats(128, 2))
+    with pytest.raises(native.VlmcError):
+        native.dsnot_refine(W, scal, summ, var, 64)           # 64 kept columns < 100 cycles (SURVEY F12)
+
+
+def test_dsnot_refine_full_size_properties(native):
+    """Vicuna down_proj / q_proj shapes at 60 %: as shipped the mask IS the Wanda mask at round(C*p); upstream
+    semantics keep the per-row count; n:m keeps exactly n pruned per group; lora_model leaves W untouched."""
+    for R, C in ((4096, 11008), (4096, 4096)):
+        W0 = weights(R, C, 41, torch.float16).cuda()
+        scal, summ, var = (t.cuda() for t in _dsnot_stats(C, 42))
+        k = round(C * 0.6)
+        W = W0.clone()
+        keep, _ = native.dsnot_refine(W, scal, summ, var, k, ref_fixup=True)
+        Ww = W0.clone()
+        keep_w, _ = native.wanda_rowselect(Ww, scal, k)
+        assert torch.equal(keep, keep_w) and torch.equal(W, Ww)
+        W = W0.clone()
+        keep_u, ncyc = native.dsnot_refine(W, scal, summ, var, k, ref_fixup=False)
+        assert bool(((~keep_u).sum(1) == k).all()) and 1 <= int(ncyc.item()) <= 100
+        assert int((keep_u != keep_w).sum()) > 0
+        assert torch.equal(W, W0 * keep_u)
+        W = W0.clone()
+        keep_n, _ = native.dsnot_refine(W, scal, summ, var, 0, prune_n=2, prune_m=4, zero_w=False)
+        assert torch.equal(W, W0)
+        assert bool(((~keep_n).view(R, C // 4, 4).sum(2) == 2).all())
+        # the refinement must not increase |reconstruction error| summed over rows (what DSnoT minimises)
+        D = W0.float() * summ[None, :]
+        e_w = (D * (~keep_w)).sum(1).abs().sum().item()
+        e_u = (D * (~keep_u)).sum(1).abs().sum().item()
+        assert e_u < e_w
+
+
+def test_composite_dsnot_pruner_on_toy_model(native):
+    import toy_model
+    import vlmc.compression as comp
+    torch.manual_seed(0)
+    model = toy_model.ToyBlip(d_llm=296, ff=488, n_llm=1, n_vit=0).eval().cuda()
+    pruner = comp.load_pruner("blipt5_dsnot_pruner", model, toy_model.toy_batches(8, device="cuda"),
+                              cfg=toy_model.pruner_cfg(0.4, 1.0))
+    model, _ = pruner.prune()
+    g = gu.load("dsnot_toy.npz")
+    for key in g["layers"]:
+        mod = model.get_submodule(key.replace("/", "."))
+        W32, tag, st, ref_keep = gu.dsnot_layer(g, "shipped_unstr60", key)
+        C = W32.shape[1]
+        keep = mod.mask.cpu().numpy()
+        assert ((~keep).sum(1) == round(C * 0.6)).all()
+        assert bool((mod.weight.data[~mod.mask] == 0).all())
+        assert (keep == ref_keep).mean() > 0.99      # GPU forward: activations differ from the CPU run in the last bits

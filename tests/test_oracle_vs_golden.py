@@ -127,3 +127,54 @@ def test_sparsegpt_hessian_and_fasterprune():
     _, dead, steps = oracle.sparsegpt_inverse_factor(g["damped_bf16|H"])
     assert steps >= 1                                      # fewer tokens than channels: the retry loop must fire
     assert oracle.sparsegpt_inverse_factor(g["dead_f16|H"])[1].sum() == 2
+
+
+# ------------------------------------------------------------------------------------------- DSnoT refine
+@pytest.mark.parametrize("case", list(gu.DSNOT_CASES))
+def test_dsnot_refine_masks_bit_exact(case):
+    """oracle.dsnot_refine against the reference composite DSnoT pruner's masks: as shipped (write-back block
+    :734-740 active, unstructured and n:m) and with that block excised at load time (upstream semantics)."""
+    g = gu.load("dsnot_toy.npz")
+    for key in g["layers"]:
+        W, tag, st, ref_keep = gu.dsnot_layer(g, case, key)
+        keep, cycles = oracle.dsnot_refine(W, st["scaler_row"], st["sum_metric_row"], st["var"],
+                                           sparsity_num=round(W.shape[1] * 0.6), **gu.DSNOT_CASES[case])
+        assert np.array_equal(keep, ref_keep), (case, key, int((keep != ref_keep).sum()))
+        assert 1 <= cycles <= 100
+
+
+def test_dsnot_shipped_unstructured_is_the_wanda_mask_with_round():
+    """SURVEY F4 + F5: as shipped, unstructured DSnoT returns the Wanda mask at round(C*p) (not int(C*p))."""
+    g = gu.load("dsnot_toy.npz")
+    for case in ("shipped_unstr60", "shipped_without_dsnot"):
+        for key in g["layers"]:
+            W, tag, st, ref_keep = gu.dsnot_layer(g, case, key)
+            C = W.shape[1]
+            assert round(C * 0.6) == int(C * 0.6) + 1
+            keep, _, _ = oracle.wanda_rowselect(W, st["scaler_row"], round(C * 0.6))
+            assert np.array_equal(keep, ref_keep)
+
+
+def test_torch_cpu_argmin_rule_matters_only_on_tied_groups():
+    """The two n:m layers whose walk exhausts a group (all members +inf) need the torch-CPU tie rule; every other
+    layer is tie-free and both rules give the reference mask."""
+    g = gu.load("dsnot_toy.npz")
+    differing = []
+    for case in ("shipped_2of4", "shipped_4of8"):
+        for key in g["layers"]:
+            W, tag, st, ref_keep = gu.dsnot_layer(g, case, key)
+            keep, _ = oracle.dsnot_refine(W, st["scaler_row"], st["sum_metric_row"], st["var"],
+                                          argmin_rule="lowest", **gu.DSNOT_CASES[case])
+            if not np.array_equal(keep, ref_keep):
+                differing.append((case, key.split("/")[-1]))
+    assert differing == [("shipped_2of4", "gate_proj"), ("shipped_4of8", "q_proj")]
+
+
+def test_torch_cpu_argmin_against_torch():
+    import torch
+    g = torch.Generator().manual_seed(0)
+    for m in (4, 8, 16):
+        for _ in range(400):
+            x = torch.randint(0, 3, (m,), generator=g).float()
+            x[torch.rand(m, generator=g) < 0.4] = float("inf")
+            assert oracle.torch_cpu_argmin(x.numpy()) == torch.topk(x[None], 1, dim=1, largest=False)[1].item()

@@ -3,6 +3,7 @@ from vlmc.common.registry import registry
 from vlmc.compression.pruners.layer_single_base_pruner import BasePruner  # noqa: F401
 from vlmc.compression.pruners.wanda_pruner import BLIPT5LayerWandaPruner  # noqa: F401
 from vlmc.compression.pruners.sparsegpt_pruner import BLIPT5LayerSparseGPTPruner  # noqa: F401
+from vlmc.compression.pruners.dsnot_pruner import BLIPT5LayerDSnoTPruner  # noqa: F401
 
 __all__ = ["BasePruner", "load_pruner"]
 

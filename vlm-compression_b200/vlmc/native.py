@@ -49,6 +49,11 @@ SIGNATURES = {
     "vlmc_chol_inv_upper": (_i, [_vp, _i, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_obs_sweep": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp, _d, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_hessian_accum": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _d, _d, _i, _i64, _vp]),
+    "vlmc_dsnot_refine_walk": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _i, _i, _f, _i, _f, _i, _i, _i, _vp, _vp,
+                                    _sz, _vp]),
+    "vlmc_dsnot_refine_apply": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i64, _vp, _sz, _vp]),
+    "vlmc_dsnot_refine": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _i, _i, _f, _i, _f, _i, _i, _i, _i, _i, _vp,
+                               _i64, _vp, _vp, _sz, _vp]),
 }
 
 
@@ -305,3 +310,44 @@ def obs_sweep(W, U, sparsity, prune_n=0, prune_m=0, dead=None, blocksize=128, wa
                                 _stream(W))
     _check("vlmc_obs_sweep", st)
     return keep, score
+
+
+def dsnot_refine(W, scaler_row, sum_metric_row, var, k, prune_n=0, prune_m=0, pow_of_var=1.0, max_cycle_time=100,
+                 update_threshold=0.1, without_same_sign=True, initial_method="wanda", argmin_rule=1, ref_fixup=True,
+                 zero_w=True, keep_mask=None, reduce_ncycles=None):
+    """K8+K9 (dsnot_pruner.py:359-755), in place on W.  Returns (keep_mask bool [R,C], ncycles 1-elem int tensor).
+
+    reduce_ncycles: optional callable(tensor) run between the two passes - the MAX all-reduce of the executed cycle
+    count when the rows of one linear are sharded across ranks."""
+    _require_cuda(W, scaler_row, sum_metric_row, var, keep_mask)
+    if W.dim() != 2 or W.stride(1) != 1:
+        raise ValueError("W must be a 2-D row-major weight")
+    if initial_method not in ("wanda", "magnitude"):
+        raise NotImplementedError("initial_method must be 'wanda' or 'magnitude' (the reference's 'sparsegpt' "
+                                  "branch is dead code: no Hessian is ever accumulated, SURVEY F11)")
+    R, C = W.shape
+    if keep_mask is None:
+        keep_mask = torch.empty((R, C), dtype=torch.bool, device=W.device)
+    if keep_mask.dtype != torch.bool or keep_mask.shape != W.shape or keep_mask.stride(1) != 1:
+        raise ValueError("keep_mask must be a bool tensor shaped like W")
+    lib = load()
+    mc = int(max_cycle_time)
+    ws = workspace(W, lib.vlmc_workspace_bytes(OP_DSNOT_REFINE, R, C, mc))
+    ncyc = torch.zeros(1, dtype=torch.int32, device=W.device)
+    var = var.reshape(-1)
+    common = (int(prune_n), int(prune_m))
+    with torch.cuda.device(W.device):
+        st = lib.vlmc_dsnot_refine_walk(W.data_ptr(), _dtype(W), R, C, W.stride(0), scaler_row.data_ptr(),
+                                        sum_metric_row.data_ptr(), var.data_ptr(), int(k), *common,
+                                        float(pow_of_var or 0.0), mc, float(update_threshold),
+                                        int(bool(without_same_sign)), int(initial_method == "magnitude"),
+                                        int(argmin_rule), ncyc.data_ptr(), ws.data_ptr(), ws.numel(), _stream(W))
+        _check("vlmc_dsnot_refine_walk", st)
+        if reduce_ncycles is not None:
+            reduce_ncycles(ncyc)
+        st = lib.vlmc_dsnot_refine_apply(W.data_ptr(), _dtype(W), R, C, W.stride(0), scaler_row.data_ptr(), *common,
+                                         int(initial_method == "magnitude"), mc, ncyc.data_ptr(), int(bool(ref_fixup)),
+                                         int(bool(zero_w)), keep_mask.data_ptr(), keep_mask.stride(0), ws.data_ptr(),
+                                         ws.numel(), _stream(W))
+        _check("vlmc_dsnot_refine_apply", st)
+    return keep_mask, ncyc
