@@ -7,12 +7,16 @@
 //     n:m: every m-th column the n smallest of the group, on the already compensated W1         (:193-195)
 //     128 sequential steps: q = masked w ; err = (w-q)/d ; W1[:, i:] -= err (x) U1[i, i:]        (:189-205) K12
 //     W[:, i2:] -= Err1 @ U[i1:i2, i2:]                                                         (:210)     K13
-// The reference issues ~8 launches per COLUMN (~90 k per down_proj) and one flatten-sort per block.  Here one
-// cooperative kernel per block does K11 + K12: a thread owns one weight row (rows are independent given U), the
-// row and the U1 tile live in shared memory, the block-wide k-th value is found by counting passes with a
-// grid barrier (exact, no sort), and the finished columns are written straight to the fp16/bf16 weight.
-// The lazy trailing update is the fp32 GEMM of sgemm.cuh.
-#include <cooperative_groups.h>
+// The reference issues ~8 launches per COLUMN (~90 k per down_proj) and one flatten-sort per block.  Here a block is
+//   K11  obs_hist_kernel<0,1,2>  exact k-th smallest of the R x 128 block scores by an 11/11/10-bit radix select:
+//                                per-CTA shared-memory histograms flushed to a global one, three stream-ordered
+//                                passes, no sort and no host round trip.  (When rows are sharded over GPUs these
+//                                three 8 KB histograms are the only data exchanged per block)
+//   K12  obs_sweep_kernel        one WARP per weight row, the row's 128 columns in registers (4 per lane), the
+//                                U1 tile in shared memory; the 128 sequential steps broadcast the pivot column by
+//                                shuffle, only pruned columns (err != 0) cost an update.  Writes the finished
+//                                columns to the fp16/bf16 weight, the fp32 working copy, Err1 and the keep mask.
+//   K13  the lazy trailing update, the fp32 GEMM of sgemm.cuh.
 #include "sgemm.cuh"
 
 namespace vlmc {
@@ -20,55 +24,13 @@ namespace vlmc {
 int launch_mean_finalize(const float* part, int n, double denom, float* out, cudaStream_t st);
 
 constexpr int kOB = 128;            // column block (the reference's blocksize default, the only one the scripts use)
-constexpr int kObsThreads = 128;    // rows per CTA
-constexpr int kObsPivots = 8;
-constexpr int kObsPasses = 20;
-constexpr int kObsCap = 512;
+constexpr int kObsBins = 2048;
+constexpr int kObsThreads = 256;
+constexpr int kObsMaxM = 16;
 
 typedef unsigned long long ull;
 
-struct ObsSelState {
-  ull counts[kObsPasses][kObsPivots];
-  unsigned int cand_cnt;
-  unsigned int bar;
-  uint32_t cand[kObsCap];
-};
-
-struct ObsBracket { uint32_t lo, hi; ull glo, ghi; };
-
-__device__ __forceinline__ uint32_t obs_clamp(double x, uint32_t lo, uint32_t hi) {
-  if (!(x > (double)lo + 1.0)) return lo + 1;
-  if (!(x < (double)hi - 1.0)) return hi - 1;
-  return (uint32_t)x;
-}
-
-__device__ void obs_pivots(const ObsBracket& b, ull k, uint32_t* p) {
-  const double w = (double)(b.hi - b.lo), lo = (double)b.lo;
-  p[0] = obs_clamp(lo + 0.25 * w, b.lo, b.hi);
-  p[1] = obs_clamp(lo + 0.50 * w, b.lo, b.hi);
-  p[2] = obs_clamp(lo + 0.75 * w, b.lo, b.hi);
-  const double f = ((double)(k - b.glo) - 0.5) / (double)(b.ghi - b.glo);
-  const double e = lo + f * w;
-  p[3] = obs_clamp(e - w * 0.0625, b.lo, b.hi);
-  p[4] = obs_clamp(e - w * (1.0 / 256.0), b.lo, b.hi);
-  p[5] = obs_clamp(e, b.lo, b.hi);
-  p[6] = obs_clamp(e + w * (1.0 / 256.0), b.lo, b.hi);
-  p[7] = obs_clamp(e + w * 0.0625, b.lo, b.hi);
-}
-
-// all CTAs are co-resident (cooperative launch): arrive + spin on a monotonically increasing counter
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks, unsigned int& epoch) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    epoch += 1;
-    __threadfence();
-    atomicAdd(bar, 1u);
-    const unsigned int target = epoch * nblocks;
-    while (*reinterpret_cast<volatile unsigned int*>(bar) < target) { __nanosleep(32); }
-    __threadfence();
-  }
-  __syncthreads();
-}
+struct ObsHist { unsigned int h[3][kObsBins]; };
 
 template <typename T> __device__ __forceinline__ T from_float(float v);
 template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
@@ -125,168 +87,179 @@ struct ObsParams {
   float* Err;          // [R, kOB]
   uint8_t* keep;       // optional [R, ldm]
   int64_t ldm;
-  ull kth;             // unstructured: 1-indexed rank of the threshold value among the R*bs block scores
+  unsigned int kth;    // unstructured: 1-indexed rank of the threshold value among the R*bs block scores
   int prune_n, prune_m;
-  ObsSelState* sel;
-  int rows_per_cta;
+  ObsHist* hist;       // this block's three histograms (zero on entry)
 };
 
-template <typename T>
-__global__ void __launch_bounds__(kObsThreads, 1)
-obs_block_kernel(const ObsParams p) {
-  extern __shared__ __align__(16) float osm[];
-  float* Us = osm;                              // [kOB][kOB]  U1 tile (row i broadcast-read)
-  float* Ws = Us + kOB * kOB;                   // [kOB][kObsThreads]  row-private: Ws[j * 128 + tid]
-  uint32_t* Ks = reinterpret_cast<uint32_t*>(Ws + kOB * kObsThreads);   // [kOB][kObsThreads]  score bits
-  __shared__ uint32_t s_piv[kObsPivots];
-  __shared__ unsigned int s_cnt[kObsPivots];
-  __shared__ ull s_glob[kObsPivots];
-  __shared__ uint32_t s_v;
-  __shared__ uint32_t s_cand[kObsCap];
+// score of one weight: w^2 / d^2 with the reference's roundings (:183); non-negative, so bit order = value order
+__device__ __forceinline__ uint32_t obs_key(float w, float d2) {
+  return __float_as_uint(__fdiv_rn(__fmul_rn(w, w), d2));
+}
 
+// bin holding the kk-th (1-indexed) entry of a global histogram and the count before it; every thread returns both
+__device__ void obs_find_bin(const unsigned int* __restrict__ gh, unsigned int kk, unsigned int* s_scan,
+                             unsigned int& bin, unsigned int& before) {
   const int tid = threadIdx.x;
-  const int bs = p.bs;
-  const int row = blockIdx.x * p.rows_per_cta + tid;
-  const bool active = tid < p.rows_per_cta && row < p.R;
-
-  for (int idx = tid; idx < bs * bs; idx += kObsThreads) {
-    const int i = idx / bs, j = idx % bs;
-    Us[i * kOB + j] = p.U[(int64_t)(p.i1 + i) * p.ldu + p.i1 + j];
+  constexpr int per = kObsBins / kObsThreads;
+  unsigned int c[per];
+  unsigned int local = 0;
+#pragma unroll
+  for (int j = 0; j < per; ++j) { c[j] = __ldcg(gh + tid * per + j); local += c[j]; }
+  unsigned int incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += t;
   }
-  if (active) {
-    const float* wr = p.W32 + (int64_t)row * p.C + p.i1;
-    for (int j = 0; j < bs; j += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(wr + j);
-      Ws[(j + 0) * kObsThreads + tid] = v.x; Ws[(j + 1) * kObsThreads + tid] = v.y;
-      Ws[(j + 2) * kObsThreads + tid] = v.z; Ws[(j + 3) * kObsThreads + tid] = v.w;
+  __syncthreads();
+  if ((tid & 31) == 31) s_scan[tid >> 5] = incl;
+  __syncthreads();
+  unsigned int wbase = 0;
+  for (int w = 0; w < (tid >> 5); ++w) wbase += s_scan[w];
+  incl += wbase;
+  const unsigned int excl = incl - local;
+  __syncthreads();
+  if (excl < kk && kk <= incl) {
+    unsigned int run = excl;
+#pragma unroll
+    for (int j = 0; j < per; ++j) {
+      if (kk <= run + c[j]) { s_scan[16] = tid * per + j; s_scan[17] = run; break; }
+      run += c[j];
     }
   }
   __syncthreads();
+  bin = s_scan[16];
+  before = s_scan[17];
+}
 
-  uint32_t mbits[kOB / 32] = {};      // bit j set = column j of this row is pruned
-  unsigned int epoch = 0;
-
-  if (p.prune_n == 0) {
-    // ---- K11: exact k-th smallest of the R x bs block scores, mask = score <= that value ----
-    for (int j = 0; j < bs; ++j) {
-      uint32_t key = 0xffffffffu;
-      if (active) {
-        const float w = Ws[j * kObsThreads + tid], d = Us[j * kOB + j];
-        key = __float_as_uint(__fdiv_rn(__fmul_rn(w, w), __fmul_rn(d, d)));
-      }
-      Ks[j * kObsThreads + tid] = key;
-    }
-    const ull n = (ull)p.R * (ull)bs;
-    ObsBracket b{0u, 0xffffffffu, 0ull, n};
-    int pass = 0;
-    while (!((b.ghi - b.glo) <= (ull)kObsCap || (b.hi - b.lo) == 1u) && pass < kObsPasses) {
-      if (tid == 0) { uint32_t pv[kObsPivots]; obs_pivots(b, p.kth, pv); for (int i = 0; i < kObsPivots; ++i) { s_piv[i] = pv[i]; s_cnt[i] = 0; } }
-      __syncthreads();
-      uint32_t pv[kObsPivots];
+// K11 pass PASS: histogram of bits [21,32) / [10,21) / [0,10) of the block scores that match the bins chosen so far
+template <int PASS>
+__global__ void __launch_bounds__(kObsThreads)
+obs_hist_kernel(const ObsParams p) {
+  __shared__ unsigned int sh[kObsBins];
+  __shared__ unsigned int s_scan[32];
+  __shared__ float s_d2[kOB];
+  const int tid = threadIdx.x;
+  for (int b = tid; b < kObsBins; b += kObsThreads) sh[b] = 0;
+  if (tid < kOB) {
+    const float d = tid < p.bs ? p.U[(int64_t)(p.i1 + tid) * p.ldu + p.i1 + tid] : 1.f;
+    s_d2[tid] = __fmul_rn(d, d);
+  }
+  unsigned int b1 = 0, b2 = 0, before = 0, kk = p.kth;
+  if (PASS >= 1) { obs_find_bin(p.hist->h[0], kk, s_scan, b1, before); kk -= before; }
+  if (PASS >= 2) { obs_find_bin(p.hist->h[1], kk, s_scan, b2, before); kk -= before; }
+  __syncthreads();
+  const int vec_per_row = p.bs >> 2;
+  const int64_t nvec = (int64_t)p.R * vec_per_row;
+  for (int64_t idx = (int64_t)blockIdx.x * kObsThreads + tid; idx < nvec; idx += (int64_t)gridDim.x * kObsThreads) {
+    const int row = (int)(idx / vec_per_row), c4 = (int)(idx % vec_per_row) * 4;
+    const float4 w = *reinterpret_cast<const float4*>(p.W32 + (int64_t)row * p.C + p.i1 + c4);
+    const float ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int i = 0; i < kObsPivots; ++i) pv[i] = s_piv[i];
-      unsigned int cnt[kObsPivots] = {};
-      for (int j = 0; j < bs; ++j) {
-        const uint32_t key = Ks[j * kObsThreads + tid];
-#pragma unroll
-        for (int i = 0; i < kObsPivots; ++i) cnt[i] += key < pv[i] ? 1u : 0u;
-      }
-#pragma unroll
-      for (int i = 0; i < kObsPivots; ++i) {
-        const unsigned int c = __reduce_add_sync(0xffffffffu, cnt[i]);
-        if ((tid & 31) == 0) atomicAdd(&s_cnt[i], c);
-      }
-      __syncthreads();
-      if (tid < kObsPivots) atomicAdd(&p.sel->counts[pass][tid], (ull)s_cnt[tid]);
-      grid_barrier(&p.sel->bar, gridDim.x, epoch);
-      if (tid < kObsPivots) s_glob[tid] = *reinterpret_cast<volatile ull*>(&p.sel->counts[pass][tid]);
-      __syncthreads();
-#pragma unroll
-      for (int i = 0; i < kObsPivots; ++i) {
-        const ull c = s_glob[i];
-        if (c <= p.kth - 1) { if (pv[i] > b.lo) { b.lo = pv[i]; b.glo = c; } }
-        else                { if (pv[i] < b.hi) { b.hi = pv[i]; b.ghi = c; } }
-      }
-      ++pass;
-      __syncthreads();
-    }
-    uint32_t v = b.lo;
-    if (b.hi - b.lo != 1u) {
-      // gather the <= kObsCap candidates in [lo, hi) and rank them (every CTA does the same tiny ranking)
-      for (int j = 0; j < bs; ++j) {
-        const uint32_t key = Ks[j * kObsThreads + tid];
-        if (key >= b.lo && key < b.hi) {
-          const unsigned int slot = atomicAdd(&p.sel->cand_cnt, 1u);
-          if (slot < (unsigned)kObsCap) p.sel->cand[slot] = key;
-        }
-      }
-      grid_barrier(&p.sel->bar, gridDim.x, epoch);
-      const int m = (int)(b.ghi - b.glo);
-      for (int i = tid; i < m && i < kObsCap; i += kObsThreads) s_cand[i] = *reinterpret_cast<volatile uint32_t*>(&p.sel->cand[i]);
-      __syncthreads();
-      const int target = (int)(p.kth - 1 - b.glo);
-      for (int t = tid; t < m && t < kObsCap; t += kObsThreads) {
-        const uint32_t kt = s_cand[t];
-        int less = 0, leq = 0;
-        for (int j = 0; j < m; ++j) { less += s_cand[j] < kt ? 1 : 0; leq += s_cand[j] <= kt ? 1 : 0; }
-        if (less <= target && target < leq) s_v = kt;
-      }
-      __syncthreads();
-      v = s_v;
-    }
-    if (active) {
-      for (int j = 0; j < bs; ++j)
-        if (Ks[j * kObsThreads + tid] <= v) mbits[j >> 5] |= 1u << (j & 31);   // `<=` (:185)
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t key = obs_key(ww[e], s_d2[c4 + e]);
+      if (PASS == 0) atomicAdd(&sh[key >> 21], 1u);
+      else if (PASS == 1) { if ((key >> 21) == b1) atomicAdd(&sh[(key >> 10) & 0x7ffu], 1u); }
+      else { if ((key >> 21) == b1 && ((key >> 10) & 0x7ffu) == b2) atomicAdd(&sh[key & 0x3ffu], 1u); }
     }
   }
+  __syncthreads();
+  for (int b = tid; b < kObsBins; b += kObsThreads)
+    if (sh[b]) atomicAdd(&p.hist->h[PASS][b], sh[b]);
+}
 
-  // ---- K12: 128 sequential column steps, the row stays in this thread's shared-memory column ----
-  if (active) {
-    float* er = p.Err + (int64_t)row * kOB;
-    for (int i = 0; i < bs; ++i) {
-      if (p.prune_n != 0 && (i % p.prune_m) == 0) {
-        // n:m on the compensated weights: the n smallest w^2/d^2 of columns [i, i+m), ties -> lower column
-        const int m = p.prune_m;
-        for (int a = 0; a < m && i + a < bs; ++a) {
-          const float wa = Ws[(i + a) * kObsThreads + tid], da = Us[(i + a) * kOB + i + a];
-          const float ka = __fdiv_rn(__fmul_rn(wa, wa), __fmul_rn(da, da));
-          int rank = 0;
-          for (int c = 0; c < m && i + c < bs; ++c) {
-            if (c == a) continue;
-            const float wc = Ws[(i + c) * kObsThreads + tid], dc = Us[(i + c) * kOB + i + c];
-            const float kc2 = __fdiv_rn(__fmul_rn(wc, wc), __fmul_rn(dc, dc));
-            rank += (kc2 < ka || (kc2 == ka && c < a)) ? 1 : 0;
+// K12 (+ the tail of K11): one warp per row
+template <typename T>
+__global__ void __launch_bounds__(kObsThreads)
+obs_sweep_kernel(const ObsParams p) {
+  extern __shared__ __align__(16) float Us[];                  // [kOB][kOB] U1 tile, zero padded
+  __shared__ unsigned int s_scan[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bs = p.bs;
+  for (int idx = tid; idx < kOB * kOB / 4; idx += kObsThreads) {
+    const int i = idx / (kOB / 4), j = (idx % (kOB / 4)) * 4;
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < bs && j < bs) u = *reinterpret_cast<const float4*>(p.U + (int64_t)(p.i1 + i) * p.ldu + p.i1 + j);
+    *reinterpret_cast<float4*>(Us + i * kOB + j) = u;
+  }
+  uint32_t v = 0;
+  if (p.prune_n == 0) {
+    unsigned int b1, b2, b3, before, kk = p.kth;
+    obs_find_bin(p.hist->h[0], kk, s_scan, b1, before); kk -= before;
+    obs_find_bin(p.hist->h[1], kk, s_scan, b2, before); kk -= before;
+    obs_find_bin(p.hist->h[2], kk, s_scan, b3, before);
+    v = (b1 << 21) | (b2 << 10) | b3;                          // the k-th smallest block score, exactly (:184)
+  }
+  __syncthreads();
+  const bool act = 4 * lane < bs;
+  const int m = p.prune_m, n = p.prune_n;
+
+  for (int row = blockIdx.x * (kObsThreads / 32) + warp; row < p.R; row += gridDim.x * (kObsThreads / 32)) {
+    float* w32 = p.W32 + (int64_t)row * p.C + p.i1 + 4 * lane;
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    if (act) { const float4 t = *reinterpret_cast<const float4*>(w32); w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w; }
+    uint32_t mbits = 0;                                          // bit e: column 4*lane+e of this row is pruned
+    if (n == 0 && act) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d = Us[(4 * lane + e) * kOB + 4 * lane + e];
+        if (obs_key(w[e], __fmul_rn(d, d)) <= v) mbits |= 1u << e;     // `<=` (:185)
+      }
+    }
+    uint32_t word[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) word[c] = __ballot_sync(0xffffffffu, (mbits >> c) & 1u);
+    float er[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int q = 0; q < (bs >> 2); ++q) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int i = 4 * q + c;
+        if (n != 0 && (i % m) == 0) {
+          // n:m on the compensated weights: the n smallest w^2/d^2 of columns [i, i+m), ties -> lower column (:193-195)
+          float keys[kObsMaxM];
+          for (int a = 0; a < m; ++a) {
+            const int col = i + a, cc = col & 3;
+            const float mine = cc == 0 ? w[0] : (cc == 1 ? w[1] : (cc == 2 ? w[2] : w[3]));
+            const float wa = __shfl_sync(0xffffffffu, mine, col >> 2);
+            const float da = col < bs ? Us[col * kOB + col] : 1.f;
+            keys[a] = col < bs ? __fdiv_rn(__fmul_rn(wa, wa), __fmul_rn(da, da)) : __int_as_float(0x7f800000);
           }
-          if (rank < p.prune_n) mbits[(i + a) >> 5] |= 1u << ((i + a) & 31);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int a = 4 * lane + e - i;
+            if (a >= 0 && a < m) {
+              int rank = 0;
+              for (int b = 0; b < m; ++b) rank += (keys[b] < keys[a] || (keys[b] == keys[a] && b < a)) ? 1 : 0;
+              if (rank < n) mbits |= 1u << e;
+            }
+          }
+#pragma unroll
+          for (int c2 = 0; c2 < 4; ++c2) word[c2] = __ballot_sync(0xffffffffu, (mbits >> c2) & 1u);
         }
-      }
-      const float w = Ws[i * kObsThreads + tid];
-      const bool pr = (mbits[i >> 5] >> (i & 31)) & 1u;
-      const float q = pr ? 0.f : w;
-      const float d = Us[i * kOB + i];
-      const float err = __fdiv_rn(__fsub_rn(w, q), d);
-      er[i] = err;
-      Ws[i * kObsThreads + tid] = q;                 // Q1[:, i]
-      if (err != 0.f) {
-        for (int j = i + 1; j < bs; ++j) {
-          const float u = Us[i * kOB + j];
-          // product and subtraction rounded separately, like the reference's outer-product matmul + in-place sub
-          Ws[j * kObsThreads + tid] = __fsub_rn(Ws[j * kObsThreads + tid], __fmul_rn(err, u));
-        }
+        if (!((word[c] >> q) & 1u)) continue;                   // kept column: q = w, err = 0, nothing to propagate
+        const float wi = __shfl_sync(0xffffffffu, w[c], q);
+        const float err = __fdiv_rn(wi, Us[i * kOB + i]);       // (w - 0) / d (:202)
+        const float4 u = *reinterpret_cast<const float4*>(Us + i * kOB + 4 * lane);
+        // product and subtraction rounded separately, like the reference's outer-product matmul + in-place sub (:204);
+        // U1[i, j < i] is exactly 0, so finished columns are untouched
+        w[0] = __fsub_rn(w[0], __fmul_rn(err, u.x)); w[1] = __fsub_rn(w[1], __fmul_rn(err, u.y));
+        w[2] = __fsub_rn(w[2], __fmul_rn(err, u.z)); w[3] = __fsub_rn(w[3], __fmul_rn(err, u.w));
+        if (lane == q) { w[c] = 0.f; er[c] = err; }             // Q1[:, i] = 0, Err1[:, i] = err
       }
     }
-    for (int i = bs; i < kOB; ++i) er[i] = 0.f;
-    // finished columns -> weight tensor (one rounding to its dtype), fp32 working copy, optional keep mask
-    T* wo = reinterpret_cast<T*>(p.Wout) + (int64_t)row * p.ldw + p.i1;
-    float* w32 = p.W32 + (int64_t)row * p.C + p.i1;
-    for (int j = 0; j < bs; ++j) {
-      const float q = Ws[j * kObsThreads + tid];
-      wo[j] = from_float<T>(q);
-      w32[j] = q;
-    }
-    if (p.keep) {
-      uint8_t* kp = p.keep + (int64_t)row * p.ldm + p.i1;
-      for (int j = 0; j < bs; ++j) kp[j] = ((mbits[j >> 5] >> (j & 31)) & 1u) ? 0 : 1;
+    *reinterpret_cast<float4*>(p.Err + (int64_t)row * kOB + 4 * lane) = make_float4(er[0], er[1], er[2], er[3]);
+    if (act) {
+      *reinterpret_cast<float4*>(w32) = make_float4(w[0], w[1], w[2], w[3]);
+      T* wo = reinterpret_cast<T*>(p.Wout) + (int64_t)row * p.ldw + p.i1 + 4 * lane;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) wo[e] = from_float<T>(w[e]);
+      if (p.keep) {
+        uint8_t* kp = p.keep + (int64_t)row * p.ldm + p.i1 + 4 * lane;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) kp[e] = ((mbits >> e) & 1u) ? 0 : 1;
+      }
     }
   }
 }
@@ -294,7 +267,7 @@ obs_block_kernel(const ObsParams p) {
 size_t obs_workspace_bytes(int R, int C) {
   const int nblk = (C + kOB - 1) / kOB;
   return VLMC_WS_COUNTER_BYTES + align_up((size_t)R * C * sizeof(float), 256) + align_up((size_t)R * kOB * sizeof(float), 256) +
-         align_up((size_t)nblk * sizeof(ObsSelState), 256) + align_up((size_t)kNumSMs * 64 * sizeof(float), 256);
+         align_up((size_t)nblk * sizeof(ObsHist), 256) + align_up((size_t)kNumSMs * 64 * sizeof(float), 256);
 }
 
 }  // namespace vlmc
@@ -307,10 +280,11 @@ extern "C" int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, con
   if (!W || !U || !ws || R < 1 || C < 1 || ldw < C || ldu < C) return VLMC_ERR_BAD_ARG;
   if (dtype != VLMC_F32 && dtype != VLMC_F16 && dtype != VLMC_BF16) return VLMC_ERR_BAD_ARG;
   if (blocksize != kOB) return VLMC_ERR_UNSUPPORTED;
-  if (prune_n < 0 || (prune_n > 0 && (prune_m <= prune_n || prune_m > 32 || kOB % prune_m != 0))) return VLMC_ERR_BAD_ARG;
+  if (prune_n < 0 || (prune_n > 0 && (prune_m <= prune_n || prune_m > kObsMaxM || kOB % prune_m != 0))) return VLMC_ERR_BAD_ARG;
   if (prune_n == 0 && !(sparsity >= 0.0 && sparsity < 1.0)) return VLMC_ERR_BAD_ARG;
   if ((C & 3) || (ldu & 3) || ((uintptr_t)U & 15)) return VLMC_ERR_UNSUPPORTED;
   if (keep_mask && ldm < C) return VLMC_ERR_BAD_ARG;
+  if ((uint64_t)R * kOB >= 0xffffffffull) return VLMC_ERR_UNSUPPORTED;
   if (!is_device_ptr(W) || !is_device_ptr(U) || !is_device_ptr(ws)) return VLMC_ERR_NOT_DEVICE;
   if (ws_bytes < obs_workspace_bytes(R, C)) return VLMC_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
@@ -321,11 +295,11 @@ extern "C" int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, con
   base += align_up((size_t)R * C * sizeof(float), 256);
   float* Err = reinterpret_cast<float*>(base);
   base += align_up((size_t)R * kOB * sizeof(float), 256);
-  ObsSelState* sel = reinterpret_cast<ObsSelState*>(base);
-  base += align_up((size_t)nblk * sizeof(ObsSelState), 256);
+  ObsHist* hist = reinterpret_cast<ObsHist*>(base);
+  base += align_up((size_t)nblk * sizeof(ObsHist), 256);
   float* part = reinterpret_cast<float*>(base);
 
-  if (cudaMemsetAsync(sel, 0, (size_t)nblk * sizeof(ObsSelState), st) != cudaSuccess) return check_launch();
+  if (prune_n == 0 && cudaMemsetAsync(hist, 0, (size_t)nblk * sizeof(ObsHist), st) != cudaSuccess) return check_launch();
   {
     dim3 grid((C + 255) / 256, R < 64 ? R : 64);
     VLMC_DISPATCH_DTYPE(dtype, (obs_upcast_kernel<scalar_t><<<grid, 256, 0, st>>>(
@@ -337,19 +311,18 @@ extern "C" int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, con
     }
   }
 
-  const size_t smem = (size_t)(kOB * kOB + 2 * kOB * kObsThreads) * sizeof(float);
-  void* kern = nullptr;
-  switch (dtype) {
-    case VLMC_F32: kern = (void*)obs_block_kernel<float>; break;
-    case VLMC_F16: kern = (void*)obs_block_kernel<__half>; break;
-    default: kern = (void*)obs_block_kernel<__nv_bfloat16>; break;
+  const size_t smem = (size_t)kOB * kOB * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(obs_sweep_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(obs_sweep_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(obs_sweep_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return check_launch();
+    attr_set = true;
   }
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
-
-  int rows_per_cta = (R + kNumSMs - 1) / kNumSMs;
-  if (rows_per_cta > kObsThreads) rows_per_cta = kObsThreads;   // more rows than 148 x 128: see the grid check below
-  const int grid = (R + rows_per_cta - 1) / rows_per_cta;
-  if (grid > kNumSMs) return VLMC_ERR_UNSUPPORTED;              // the grid barrier needs every CTA resident
+  const int rows_per_cta = kObsThreads / 32;
+  int sweep_grid = (R + rows_per_cta - 1) / rows_per_cta;
+  if (sweep_grid > kNumSMs * 3) sweep_grid = kNumSMs * 3;
 
   for (int blk = 0; blk < nblk; ++blk) {
     ObsParams p;
@@ -357,13 +330,19 @@ extern "C" int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, con
     p.i1 = blk * kOB;
     p.bs = (C - p.i1 < kOB) ? (C - p.i1) : kOB;
     p.Err = Err; p.keep = keep_mask; p.ldm = ldm;
-    p.kth = (ull)((double)((ull)R * (ull)p.bs) * sparsity) + 1;   // int(numel * sparsity) is the 0-indexed rank (:184)
+    p.kth = (unsigned int)((ull)((double)((ull)R * (ull)p.bs) * sparsity)) + 1u;   // int(numel * sparsity) is the 0-indexed rank (:184)
     p.prune_n = prune_n; p.prune_m = prune_m;
-    p.sel = sel + blk;
-    p.rows_per_cta = rows_per_cta;
-    void* args[] = {&p};
-    cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kObsThreads), args, smem, st);
-    if (e != cudaSuccess) { g_last_cuda_error = (int)e; return VLMC_ERR_CUDA; }
+    p.hist = hist + blk;
+    if (prune_n == 0) {
+      const int64_t nvec = (int64_t)R * (p.bs >> 2);
+      int hgrid = (int)((nvec + kObsThreads * 4 - 1) / (kObsThreads * 4));
+      if (hgrid > kNumSMs * 4) hgrid = kNumSMs * 4;
+      if (hgrid < 1) hgrid = 1;
+      obs_hist_kernel<0><<<hgrid, kObsThreads, 0, st>>>(p);
+      obs_hist_kernel<1><<<hgrid, kObsThreads, 0, st>>>(p);
+      obs_hist_kernel<2><<<hgrid, kObsThreads, 0, st>>>(p);
+    }
+    VLMC_DISPATCH_DTYPE(dtype, (obs_sweep_kernel<scalar_t><<<sweep_grid, kObsThreads, smem, st>>>(p)));
     const int i2 = p.i1 + p.bs;
     if (i2 < C) {
       // K13: W[:, i2:] -= Err1 @ U[i1:i2, i2:]
