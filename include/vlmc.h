@@ -185,6 +185,25 @@ int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, const float* U
                    void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * K11-K13 in steps, for runs that shard the OUTPUT ROWS of one linear across GPUs (rows are independent given U, except
+ * for the unstructured block threshold, which is a k-th value over all rows x 128 columns).  Each rank holds
+ * R of the rows_total rows.  `hist` is caller memory, [ceil(C/128)][3][2048] uint32, zero before vlmc_obs_begin
+ * (NULL = a private buffer inside ws, single device).  Per block b the sequence is
+ *     for pass in 0,1,2:  vlmc_obs_block_hist(b, pass)   then SUM-all-reduce hist[b][pass] over the row shards
+ *     vlmc_obs_block_finish(b)                            (threshold from the three histograms, sweep, trailing update)
+ * and the three 8 KB histograms are the only data exchanged.  n:m needs no histogram and no exchange.
+ * vlmc_obs_begin: fp32 working copy of W (dead channels zeroed) and, if importance_sum != NULL, the SUM of
+ * W^2 / diag(U)^2 over this rank's rows (device float; the caller reduces and divides by the element count).
+ */
+int vlmc_obs_begin(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu,
+                   const uint8_t* dead, float* importance_sum, void* ws, size_t ws_bytes, void* stream);
+int vlmc_obs_block_hist(int R, int C, const float* U, int64_t ldu, int blk, int pass, int64_t rows_total,
+                        double sparsity, unsigned int* hist, void* ws, size_t ws_bytes, void* stream);
+int vlmc_obs_block_finish(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu, int blk,
+                          int64_t rows_total, double sparsity, int prune_n, int prune_m, uint8_t* keep_mask,
+                          int64_t ldm, unsigned int* hist, void* ws, size_t ws_bytes, void* stream);
+
+/*
  * K8+K9  DSnoT mask refinement.  Replaces the per-linear body of the DSnoT pruners, dsnot_pruner.py:359-755 (T5 / LLM)
  * and :1092-1485 (ViT): DSnoT_metric = W * sum_metric_row, the Wanda (or magnitude) initial mask, the three stable row
  * orderings + return_reorder_indice (:555-612, :1881-1925) and the prune / regrow cycle loop (:650-751; n:m :407-552).

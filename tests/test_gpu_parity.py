@@ -715,3 +715,59 @@ def test_composite_dsnot_pruner_on_toy_model(native):
         assert ((~keep).sum(1) == round(C * 0.6)).all()
         assert bool((mod.weight.data[~mod.mask] == 0).all())
         assert (keep == ref_keep).mean() > 0.99      # GPU forward: activations differ from the CPU run in the last bits
+
+
+# ------------------------------------------------------------------------------------------- row-sharded OBS sweep
+def test_obs_row_shard_single_rank_equals_full_sweep(native):
+    R, C = 160, 640
+    x = acts(4 * C, C, 5, torch.bfloat16).cuda()
+    H = torch.zeros(C, C, device="cuda")
+    native.hessian_accum(x, H, 0, 1)
+    U, dead, _ = _factor(native, H)
+    W0 = weights(R, C, 78, torch.float16, 0.05).cuda()
+    for sp, n, m in ((0.5, 0, 0), (0.0, 2, 4)):
+        Wa, Wb = W0.clone(), W0.clone()
+        ka, sa = native.obs_sweep(Wa, U, sp, n, m, dead=dead, want_mask=True)
+        kb, sb = native.obs_sweep_row_shard(Wb, U, sp, R, lambda t: t, n, m, dead=dead, want_mask=True)
+        assert torch.equal(Wa, Wb) and torch.equal(ka, kb)
+        assert abs(sa.item() - sb.item()) < 1e-6 * abs(sa.item())
+
+
+def test_obs_row_shards_in_lockstep_equal_the_unsharded_sweep(native):
+    """Two row shards driven in lockstep on one GPU, their block histograms summed between passes (what the
+    all-reduce does across ranks): pruned weights and masks must equal the unsharded sweep bit for bit."""
+    lib = native.load()
+    R, C, sp = 224, 512, 0.5
+    x = acts(4 * C, C, 6, torch.bfloat16).cuda()
+    H = torch.zeros(C, C, device="cuda")
+    native.hessian_accum(x, H, 0, 1)
+    U, dead, _ = _factor(native, H)
+    W0 = weights(R, C, 79, torch.bfloat16, 0.05).cuda()
+    Wfull = W0.clone()
+    keep_full, _ = native.obs_sweep(Wfull, U, sp, dead=dead, want_mask=True)
+    W = W0.clone()
+    keep = torch.empty((R, C), dtype=torch.bool, device="cuda")
+    bounds = [(0, 96), (96, R)]                                  # uneven on purpose
+    nblk = C // 128
+    st = torch.cuda.current_stream().cuda_stream
+    shards = []
+    for s, e in bounds:
+        ws = torch.zeros(lib.vlmc_workspace_bytes(native.OP_OBS, e - s, C, 128), dtype=torch.uint8, device="cuda")
+        hist = torch.zeros((nblk, 3, 2048), dtype=torch.int32, device="cuda")
+        shards.append((W[s:e], keep[s:e], ws, hist))
+        assert lib.vlmc_obs_begin(W[s:e].data_ptr(), native.BF16, e - s, C, W.stride(0), U.data_ptr(), U.stride(0),
+                                  dead.data_ptr(), None, ws.data_ptr(), ws.numel(), st) == 0
+    for blk in range(nblk):
+        for ps in range(3):
+            for Ws, ks, ws, hist in shards:
+                assert lib.vlmc_obs_block_hist(Ws.shape[0], C, U.data_ptr(), U.stride(0), blk, ps, R, sp,
+                                               hist.data_ptr(), ws.data_ptr(), ws.numel(), st) == 0
+            total = sum(h[blk, ps] for *_, h in shards)
+            for *_, h in shards:
+                h[blk, ps].copy_(total)
+        for Ws, ks, ws, hist in shards:
+            assert lib.vlmc_obs_block_finish(Ws.data_ptr(), native.BF16, Ws.shape[0], C, W.stride(0), U.data_ptr(),
+                                             U.stride(0), blk, R, sp, 0, 0, ks.data_ptr(), keep.stride(0),
+                                             hist.data_ptr(), ws.data_ptr(), ws.numel(), st) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(W, Wfull) and torch.equal(keep, keep_full)

@@ -272,11 +272,26 @@ size_t obs_workspace_bytes(int R, int C) {
 
 }  // namespace vlmc
 
-extern "C" int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu,
-                              const uint8_t* dead, double sparsity, int prune_n, int prune_m, int blocksize,
-                              uint8_t* keep_mask, int64_t ldm, float* importance_score,
-                              void* ws, size_t ws_bytes, void* stream) {
-  using namespace vlmc;
+namespace vlmc {
+
+struct ObsLayout { float* W32; float* Err; ObsHist* hist; float* part; };
+static ObsLayout obs_carve(void* ws, int R, int C) {
+  const int nblk = (C + kOB - 1) / kOB;
+  char* base = reinterpret_cast<char*>(ws) + VLMC_WS_COUNTER_BYTES;
+  ObsLayout l;
+  l.W32 = reinterpret_cast<float*>(base);
+  base += align_up((size_t)R * C * sizeof(float), 256);
+  l.Err = reinterpret_cast<float*>(base);
+  base += align_up((size_t)R * kOB * sizeof(float), 256);
+  l.hist = reinterpret_cast<ObsHist*>(base);
+  base += align_up((size_t)nblk * sizeof(ObsHist), 256);
+  l.part = reinterpret_cast<float*>(base);
+  return l;
+}
+
+static int obs_checks(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu, double sparsity,
+                      int prune_n, int prune_m, int blocksize, const uint8_t* keep_mask, int64_t ldm, void* ws,
+                      size_t ws_bytes) {
   if (!W || !U || !ws || R < 1 || C < 1 || ldw < C || ldu < C) return VLMC_ERR_BAD_ARG;
   if (dtype != VLMC_F32 && dtype != VLMC_F16 && dtype != VLMC_BF16) return VLMC_ERR_BAD_ARG;
   if (blocksize != kOB) return VLMC_ERR_UNSUPPORTED;
@@ -287,30 +302,76 @@ extern "C" int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, con
   if ((uint64_t)R * kOB >= 0xffffffffull) return VLMC_ERR_UNSUPPORTED;
   if (!is_device_ptr(W) || !is_device_ptr(U) || !is_device_ptr(ws)) return VLMC_ERR_NOT_DEVICE;
   if (ws_bytes < obs_workspace_bytes(R, C)) return VLMC_ERR_WORKSPACE;
+  return VLMC_OK;
+}
+
+static ObsParams obs_block_params(const ObsLayout& l, void* W, int R, int C, int64_t ldw, const float* U, int64_t ldu,
+                                  int blk, int64_t rows_total, double sparsity, int prune_n, int prune_m,
+                                  uint8_t* keep_mask, int64_t ldm, unsigned int* hist) {
+  ObsParams p;
+  p.W32 = l.W32; p.Wout = W; p.ldw = ldw; p.R = R; p.C = C; p.U = U; p.ldu = ldu;
+  p.i1 = blk * kOB;
+  p.bs = (C - p.i1 < kOB) ? (C - p.i1) : kOB;
+  p.Err = l.Err; p.keep = keep_mask; p.ldm = ldm;
+  // int(numel * sparsity) is the 0-indexed rank of the threshold (:184); numel counts the rows of ALL shards
+  p.kth = (unsigned int)((ull)((double)((ull)rows_total * (ull)p.bs) * sparsity)) + 1u;
+  p.prune_n = prune_n; p.prune_m = prune_m;
+  p.hist = hist ? reinterpret_cast<ObsHist*>(hist) + blk : l.hist + blk;
+  return p;
+}
+
+}  // namespace vlmc
+
+extern "C" int vlmc_obs_begin(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu,
+                              const uint8_t* dead, float* importance_sum, void* ws, size_t ws_bytes, void* stream) {
+  using namespace vlmc;
+  int rc = obs_checks(W, dtype, R, C, ldw, U, ldu, 0.0, 0, 0, kOB, nullptr, 0, ws, ws_bytes);
+  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-
+  ObsLayout l = obs_carve(ws, R, C);
   const int nblk = (C + kOB - 1) / kOB;
-  char* base = reinterpret_cast<char*>(ws) + VLMC_WS_COUNTER_BYTES;
-  float* W32 = reinterpret_cast<float*>(base);
-  base += align_up((size_t)R * C * sizeof(float), 256);
-  float* Err = reinterpret_cast<float*>(base);
-  base += align_up((size_t)R * kOB * sizeof(float), 256);
-  ObsHist* hist = reinterpret_cast<ObsHist*>(base);
-  base += align_up((size_t)nblk * sizeof(ObsHist), 256);
-  float* part = reinterpret_cast<float*>(base);
-
-  if (prune_n == 0 && cudaMemsetAsync(hist, 0, (size_t)nblk * sizeof(ObsHist), st) != cudaSuccess) return check_launch();
-  {
-    dim3 grid((C + 255) / 256, R < 64 ? R : 64);
-    VLMC_DISPATCH_DTYPE(dtype, (obs_upcast_kernel<scalar_t><<<grid, 256, 0, st>>>(
-                                   reinterpret_cast<const scalar_t*>(W), ldw, W32, R, C, dead)));
-    if (importance_score) {
-      obs_importance_kernel<<<grid, 256, 0, st>>>(W32, R, C, U, ldu, part);
-      int rc = launch_mean_finalize(part, grid.x * grid.y, (double)R * (double)C, importance_score, st);
-      if (rc) return rc;
-    }
+  if (cudaMemsetAsync(l.hist, 0, (size_t)nblk * sizeof(ObsHist), st) != cudaSuccess) return check_launch();
+  dim3 grid((C + 255) / 256, R < 64 ? R : 64);
+  VLMC_DISPATCH_DTYPE(dtype, (obs_upcast_kernel<scalar_t><<<grid, 256, 0, st>>>(
+                                 reinterpret_cast<const scalar_t*>(W), ldw, l.W32, R, C, dead)));
+  if (importance_sum) {
+    obs_importance_kernel<<<grid, 256, 0, st>>>(l.W32, R, C, U, ldu, l.part);
+    rc = launch_mean_finalize(l.part, grid.x * grid.y, 1.0, importance_sum, st);   // sum; the caller divides by numel
+    if (rc) return rc;
   }
+  return check_launch();
+}
 
+extern "C" int vlmc_obs_block_hist(int R, int C, const float* U, int64_t ldu, int blk, int pass, int64_t rows_total,
+                                   double sparsity, unsigned int* hist, void* ws, size_t ws_bytes, void* stream) {
+  using namespace vlmc;
+  if (!U || !ws || R < 1 || C < 1 || blk < 0 || blk * kOB >= C || pass < 0 || pass > 2 || rows_total < R)
+    return VLMC_ERR_BAD_ARG;
+  if (ws_bytes < obs_workspace_bytes(R, C)) return VLMC_ERR_WORKSPACE;
+  if ((uint64_t)rows_total * kOB >= 0xffffffffull) return VLMC_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  ObsLayout l = obs_carve(ws, R, C);
+  ObsParams p = obs_block_params(l, nullptr, R, C, C, U, ldu, blk, rows_total, sparsity, 0, 0, nullptr, 0, hist);
+  const int64_t nvec = (int64_t)R * (p.bs >> 2);
+  int hgrid = (int)((nvec + kObsThreads * 4 - 1) / (kObsThreads * 4));
+  if (hgrid > kNumSMs * 4) hgrid = kNumSMs * 4;
+  if (hgrid < 1) hgrid = 1;
+  if (pass == 0) obs_hist_kernel<0><<<hgrid, kObsThreads, 0, st>>>(p);
+  else if (pass == 1) obs_hist_kernel<1><<<hgrid, kObsThreads, 0, st>>>(p);
+  else obs_hist_kernel<2><<<hgrid, kObsThreads, 0, st>>>(p);
+  return check_launch();
+}
+
+extern "C" int vlmc_obs_block_finish(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu, int blk,
+                                     int64_t rows_total, double sparsity, int prune_n, int prune_m, uint8_t* keep_mask,
+                                     int64_t ldm, unsigned int* hist, void* ws, size_t ws_bytes, void* stream) {
+  using namespace vlmc;
+  int rc = obs_checks(W, dtype, R, C, ldw, U, ldu, sparsity, prune_n, prune_m, kOB, keep_mask, ldm, ws, ws_bytes);
+  if (rc) return rc;
+  if (blk < 0 || blk * kOB >= C || rows_total < R) return VLMC_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  ObsLayout l = obs_carve(ws, R, C);
+  ObsParams p = obs_block_params(l, W, R, C, ldw, U, ldu, blk, rows_total, sparsity, prune_n, prune_m, keep_mask, ldm, hist);
   const size_t smem = (size_t)kOB * kOB * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
@@ -323,32 +384,39 @@ extern "C" int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, con
   const int rows_per_cta = kObsThreads / 32;
   int sweep_grid = (R + rows_per_cta - 1) / rows_per_cta;
   if (sweep_grid > kNumSMs * 3) sweep_grid = kNumSMs * 3;
-
-  for (int blk = 0; blk < nblk; ++blk) {
-    ObsParams p;
-    p.W32 = W32; p.Wout = W; p.ldw = ldw; p.R = R; p.C = C; p.U = U; p.ldu = ldu;
-    p.i1 = blk * kOB;
-    p.bs = (C - p.i1 < kOB) ? (C - p.i1) : kOB;
-    p.Err = Err; p.keep = keep_mask; p.ldm = ldm;
-    p.kth = (unsigned int)((ull)((double)((ull)R * (ull)p.bs) * sparsity)) + 1u;   // int(numel * sparsity) is the 0-indexed rank (:184)
-    p.prune_n = prune_n; p.prune_m = prune_m;
-    p.hist = hist + blk;
-    if (prune_n == 0) {
-      const int64_t nvec = (int64_t)R * (p.bs >> 2);
-      int hgrid = (int)((nvec + kObsThreads * 4 - 1) / (kObsThreads * 4));
-      if (hgrid > kNumSMs * 4) hgrid = kNumSMs * 4;
-      if (hgrid < 1) hgrid = 1;
-      obs_hist_kernel<0><<<hgrid, kObsThreads, 0, st>>>(p);
-      obs_hist_kernel<1><<<hgrid, kObsThreads, 0, st>>>(p);
-      obs_hist_kernel<2><<<hgrid, kObsThreads, 0, st>>>(p);
-    }
-    VLMC_DISPATCH_DTYPE(dtype, (obs_sweep_kernel<scalar_t><<<sweep_grid, kObsThreads, smem, st>>>(p)));
-    const int i2 = p.i1 + p.bs;
-    if (i2 < C) {
-      // K13: W[:, i2:] -= Err1 @ U[i1:i2, i2:]
-      int rc = sgemm(false, R, C - i2, kOB, -1.f, Err, kOB, U + (int64_t)p.i1 * ldu + i2, ldu, 1.f, W32 + i2, C, 0, st);
-      if (rc) return rc;
-    }
+  VLMC_DISPATCH_DTYPE(dtype, (obs_sweep_kernel<scalar_t><<<sweep_grid, kObsThreads, smem, st>>>(p)));
+  const int i2 = p.i1 + p.bs;
+  if (i2 < C) {
+    // K13: W[:, i2:] -= Err1 @ U[i1:i2, i2:]
+    rc = sgemm(false, R, C - i2, kOB, -1.f, l.Err, kOB, U + (int64_t)p.i1 * ldu + i2, ldu, 1.f, l.W32 + i2, C, 0, st);
+    if (rc) return rc;
   }
   return check_launch();
+}
+
+extern "C" int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu,
+                              const uint8_t* dead, double sparsity, int prune_n, int prune_m, int blocksize,
+                              uint8_t* keep_mask, int64_t ldm, float* importance_score,
+                              void* ws, size_t ws_bytes, void* stream) {
+  using namespace vlmc;
+  int rc = obs_checks(W, dtype, R, C, ldw, U, ldu, sparsity, prune_n, prune_m, blocksize, keep_mask, ldm, ws, ws_bytes);
+  if (rc) return rc;
+  rc = vlmc_obs_begin(W, dtype, R, C, ldw, U, ldu, dead, importance_score, ws, ws_bytes, stream);
+  if (rc) return rc;
+  if (importance_score) {   // vlmc_obs_begin left the sum: mean = sum / numel (:163-165)
+    rc = launch_mean_finalize(importance_score, 1, (double)R * (double)C, importance_score, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  const int nblk = (C + kOB - 1) / kOB;
+  for (int blk = 0; blk < nblk; ++blk) {
+    if (prune_n == 0)
+      for (int pass = 0; pass < 3; ++pass) {
+        rc = vlmc_obs_block_hist(R, C, U, ldu, blk, pass, R, sparsity, nullptr, ws, ws_bytes, stream);
+        if (rc) return rc;
+      }
+    rc = vlmc_obs_block_finish(W, dtype, R, C, ldw, U, ldu, blk, R, sparsity, prune_n, prune_m, keep_mask, ldm,
+                               nullptr, ws, ws_bytes, stream);
+    if (rc) return rc;
+  }
+  return VLMC_OK;
 }

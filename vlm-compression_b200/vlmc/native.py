@@ -49,6 +49,10 @@ SIGNATURES = {
     "vlmc_chol_inv_upper": (_i, [_vp, _i, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_obs_sweep": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp, _d, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_hessian_accum": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _d, _d, _i, _i64, _vp]),
+    "vlmc_obs_begin": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "vlmc_obs_block_hist": (_i, [_i, _i, _vp, _i64, _i, _i, _i64, _d, _vp, _vp, _sz, _vp]),
+    "vlmc_obs_block_finish": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _i64, _d, _i, _i, _vp, _i64, _vp, _vp, _sz,
+                                   _vp]),
     "vlmc_dsnot_refine_walk": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _i, _i, _f, _i, _f, _i, _i, _i, _vp, _vp,
                                     _sz, _vp]),
     "vlmc_dsnot_refine_apply": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i64, _vp, _sz, _vp]),
@@ -310,6 +314,46 @@ def obs_sweep(W, U, sparsity, prune_n=0, prune_m=0, dead=None, blocksize=128, wa
                                 _stream(W))
     _check("vlmc_obs_sweep", st)
     return keep, score
+
+
+def obs_sweep_row_shard(W, U, sparsity, rows_total, reduce_sum, prune_n=0, prune_m=0, dead=None, want_mask=False):
+    """K11-K13 on this rank's row shard of one linear (in place on W, a [R_local, C] view).
+
+    reduce_sum(tensor): in-place SUM all-reduce over the ranks that hold the other rows; called on the three 8 KB
+    block histograms (unstructured only) and once on the importance-score sum.  Returns (keep or None, importance
+    score 1-elem tensor = mean over all rows_total rows)."""
+    _require_cuda(W, U, dead)
+    if W.dim() != 2 or W.stride(1) != 1:
+        raise ValueError("W must be a 2-D row-major weight")
+    lib = load()
+    R, C = W.shape
+    nblk = (C + 127) // 128
+    keep = torch.empty((R, C), dtype=torch.bool, device=W.device) if want_mask else None
+    score = torch.zeros(1, dtype=torch.float32, device=W.device)
+    ws = workspace(W, lib.vlmc_workspace_bytes(OP_OBS, R, C, 128))
+    hist = torch.zeros((nblk, 3, 2048), dtype=torch.int32, device=W.device) if prune_n == 0 else None
+    st = _stream(W)
+    args_u = (U.data_ptr(), U.stride(0))
+    with torch.cuda.device(W.device):
+        _check("vlmc_obs_begin", lib.vlmc_obs_begin(W.data_ptr(), _dtype(W), R, C, W.stride(0), *args_u,
+                                                    dead.data_ptr() if dead is not None else None, score.data_ptr(),
+                                                    ws.data_ptr(), ws.numel(), st))
+        reduce_sum(score)
+        for blk in range(nblk):
+            if prune_n == 0:
+                for ps in range(3):
+                    _check("vlmc_obs_block_hist",
+                           lib.vlmc_obs_block_hist(R, C, *args_u, blk, ps, int(rows_total), float(sparsity),
+                                                   hist.data_ptr(), ws.data_ptr(), ws.numel(), st))
+                    reduce_sum(hist[blk, ps])
+            _check("vlmc_obs_block_finish",
+                   lib.vlmc_obs_block_finish(W.data_ptr(), _dtype(W), R, C, W.stride(0), *args_u, blk, int(rows_total),
+                                             float(sparsity), int(prune_n), int(prune_m),
+                                             keep.data_ptr() if keep is not None else None,
+                                             keep.stride(0) if keep is not None else 0,
+                                             hist.data_ptr() if hist is not None else None, ws.data_ptr(), ws.numel(),
+                                             st))
+    return keep, score / float(rows_total * C)
 
 
 def dsnot_refine(W, scaler_row, sum_metric_row, var, k, prune_n=0, prune_m=0, pow_of_var=1.0, max_cycle_time=100,
