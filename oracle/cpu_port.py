@@ -52,3 +52,100 @@ def lora_merge(W, A, B, scaling, mask):
     W += ((B @ A) * scaling) * mask
     W[~mask] = 0
     return W
+
+
+class SparseGPTPort:
+    """sparsegpt_pruner.py:55-215: Hessian accumulation + fasterprune, the reference's op sequence on CPU tensors."""
+
+    def __init__(self, weight):
+        self.W = weight                      # [R, C] in its own dtype, pruned in place
+        self.rows, self.columns = weight.shape
+        self.H = torch.zeros((self.columns, self.columns))
+        self.nsamples = 0
+
+    def add_batch(self, inp):                                       # :68-79
+        if inp.dim() == 2:
+            inp = inp.unsqueeze(0)
+        b = inp.shape[0]
+        inp = inp.reshape(-1, inp.shape[-1]).t()
+        self.H *= self.nsamples / (self.nsamples + b)
+        self.nsamples += b
+        inp = (2 / self.nsamples) ** 0.5 * inp.float()
+        self.H += inp.matmul(inp.t())
+
+    @staticmethod
+    def _chol(H, damp, upper):                                      # :114-128 / :146-157: damp only after a failure
+        while True:
+            L, info = torch.linalg.cholesky_ex(H, upper=upper)
+            if int(info) == 0 and not torch.isnan(L).any():
+                return L
+            H[torch.arange(H.shape[0]), torch.arange(H.shape[0])] += damp
+
+    def fasterprune(self, sparsity, prune_n=0, prune_m=0, blocksize=128, percdamp=.01):
+        W = self.W.clone().float()
+        H = self.H
+        dead = torch.diag(H) == 0
+        H[dead, dead] = 1
+        W[:, dead] = 0
+        L = self._chol(H, percdamp * torch.mean(torch.diag(H)), False)
+        H = torch.cholesky_inverse(L)
+        Hinv = self._chol(H, percdamp * torch.mean(torch.abs(torch.diag(H))), True)
+        score = torch.mean(W ** 2 / (torch.diag(Hinv).reshape(1, -1)) ** 2).item()
+        for i1 in range(0, self.columns, blocksize):                # :169-210
+            i2 = min(i1 + blocksize, self.columns)
+            count = i2 - i1
+            W1 = W[:, i1:i2].clone()
+            Q1 = torch.zeros_like(W1)
+            Err1 = torch.zeros_like(W1)
+            Hinv1 = Hinv[i1:i2, i1:i2]
+            if prune_n == 0:
+                tmp = W1 ** 2 / (torch.diag(Hinv1).reshape(1, -1)) ** 2
+                thresh = torch.sort(tmp.flatten())[0][int(tmp.numel() * sparsity)]
+                mask1 = tmp <= thresh
+            else:
+                mask1 = torch.zeros_like(W1) == 1
+            for i in range(count):
+                w = W1[:, i]
+                d = Hinv1[i, i]
+                if prune_n != 0 and i % prune_m == 0:
+                    tmp = W1[:, i:i + prune_m] ** 2 / (torch.diag(Hinv1)[i:i + prune_m].reshape(1, -1)) ** 2
+                    mask1.scatter_(1, i + torch.topk(tmp, prune_n, dim=1, largest=False)[1], True)
+                q = w.clone()
+                q[mask1[:, i]] = 0
+                Q1[:, i] = q
+                err1 = (w - q) / d
+                W1[:, i:] -= err1.unsqueeze(1).matmul(Hinv1[i, i:].unsqueeze(0))
+                Err1[:, i] = err1
+            W[:, i1:i2] = Q1
+            W[:, i2:] -= Err1.matmul(Hinv[i1:i2, i2:])
+        self.W.copy_(W.to(self.W.dtype))
+        return score
+
+
+class DSnoTStat:
+    """dsnot_pruner.py:58-101."""
+
+    def __init__(self, columns):
+        self.scaler_row = torch.zeros(columns)
+        self.sum_metric_row = torch.zeros(columns)
+        self.mean = torch.zeros(columns)
+        self.var = torch.zeros(columns)
+        self.nsamples = 0
+        self.ntokens = 0
+
+    def add_batch(self, inp):
+        if inp.dim() == 2:
+            inp = inp.unsqueeze(0)
+        b = inp.shape[0]
+        inp = inp.reshape(-1, inp.shape[-1]).t().type(torch.float32)
+        mean_inp = torch.mean(inp, dim=1, keepdim=True)
+        var_inp = torch.var(inp, dim=1, unbiased=False, keepdim=True)
+        n = inp.shape[1]
+        self.var = var_inp if self.ntokens == 0 else (self.var * self.ntokens + var_inp * n) / (self.ntokens + n)
+        self.mean = mean_inp if self.ntokens == 0 else (self.mean * self.ntokens + mean_inp * n) / (self.ntokens + n)
+        self.ntokens += n
+        self.scaler_row *= self.nsamples / (self.nsamples + b)
+        self.sum_metric_row *= self.nsamples / (self.nsamples + b)
+        self.nsamples += b
+        self.scaler_row += torch.norm(inp, p=2, dim=1) ** 2 / self.nsamples
+        self.sum_metric_row += torch.sum(inp, dim=1) / self.nsamples

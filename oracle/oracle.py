@@ -223,8 +223,9 @@ def sparsegpt_inverse_factor(H, percdamp=0.01):
 
 
 def sparsegpt_fasterprune(W32, w_tag, H, sparsity, prune_n=0, prune_m=0, blocksize=128, percdamp=0.01, U=None,
-                          dead=None):
-    """The column-block OBS sweep (:160-215) in float32.  Returns (pruned W rounded to w_tag, importance score, U)."""
+                          dead=None, kth_fn=None):
+    """The column-block OBS sweep (:160-215) in float32.  Returns (pruned W rounded to w_tag, importance score, U).
+    kth_fn(tmp, k) -> threshold replaces the local k-th value when W32 is only a row shard (multi-rank tests)."""
     if U is None:
         U, dead, _ = sparsegpt_inverse_factor(H, percdamp)
     W = np.array(W32, dtype=F32)
@@ -243,7 +244,8 @@ def sparsegpt_fasterprune(W32, w_tag, H, sparsity, prune_n=0, prune_m=0, blocksi
         d1 = np.diag(U1).astype(F32)
         if prune_n == 0:
             tmp = ((W1 * W1) / ((d1 * d1)[None, :])).astype(F32)
-            thresh = np.partition(tmp.ravel(), int(tmp.size * sparsity))[int(tmp.size * sparsity)]   # :184
+            kk = int(tmp.size * sparsity)
+            thresh = np.partition(tmp.ravel(), kk)[kk] if kth_fn is None else kth_fn(tmp, kk)          # :184
             mask1 = tmp <= thresh                                                                    # :185
         else:
             mask1 = np.zeros(W1.shape, dtype=bool)
@@ -366,12 +368,14 @@ def _group_argmin(block, rule):
 
 def dsnot_refine(W32, scaler_row, sum_metric_row, var, sparsity_num=0, prune_n=0, prune_m=0, pow_of_var=1.0,
                  max_cycle_time=100, update_threshold=0.1, without_same_sign=True, initial_method="wanda",
-                 ref_fixup=True, argmin_rule="torch_cpu"):
+                 ref_fixup=True, argmin_rule="torch_cpu", force_cycles=None):
     """One linear's DSnoT mask.  Returns (keep_mask bool [R, C], cycles executed).
 
     sparsity_num = round(C * p) is computed by the caller (:562; python round, not int - SURVEY F5).
     ref_fixup=True reproduces the shipped reference including the block at :734-740 that writes the swap back
     (SURVEY F4); False gives the upstream DSnoT behaviour (that block excised).  The n:m branch has no such block.
+    force_cycles: run exactly that many cycles instead of `while any(update_mask)` - what a row shard does once the
+    executed-cycle count of the whole matrix is known (multi-rank tests).
     Tie-breaks: the unstable per-group sort at :423 is taken as lowest-column-first; the topk at :517
     meets structural ties (groups whose members were all set to +inf) and follows argmin_rule.
     """
@@ -413,7 +417,7 @@ def dsnot_refine(W32, scaler_row, sum_metric_row, var, sparsity_num=0, prune_n=0
         np.put_along_axis(initial, prune_idx, F32(np.inf), axis=1)                  # :469
         upd = np.ones((R, 1), dtype=bool)
         cycles = 0
-        while upd.any() and cycles < max_cycle_time:                                # :476-479 (1..max inclusive)
+        while (upd.any() if force_cycles is None else cycles < force_cycles) and cycles < max_cycle_time:   # :476-479
             cycles += 1
             which = (err > 0).astype(np.int64)                                      # :483
             p = _take(ptr, which)
@@ -457,7 +461,7 @@ def dsnot_refine(W32, scaler_row, sum_metric_row, var, sparsity_num=0, prune_n=0
     step = np.array([1, -1], dtype=np.int64)
     upd = np.ones((R, 1), dtype=bool)
     cycles = 0
-    while upd.any() and cycles < max_cycle_time:                                    # :650
+    while (upd.any() if force_cycles is None else cycles < force_cycles) and cycles < max_cycle_time:   # :650
         cycles += 1
         wr = (err > 0).astype(np.int64)                                             # :654
         p = _take(ptr_r, wr)

@@ -62,3 +62,14 @@ def test_lora_linear_interface(built_lib):
     lin.mask = torch.rand(16, 32) < 0.5
     w = (lin.weight + (lin.lora_B.weight @ lin.lora_A.weight) * lin.scaling) * lin.mask
     assert torch.allclose(lin(x), x @ w.T, atol=1e-5)
+
+
+def test_factorisation_assignment_is_balanced_and_deterministic():
+    from vlmc import parallel
+    cols = [4096, 4096, 4096, 4096, 4096, 4096, 11008]          # q k v o gate up down
+    for world in (1, 2, 4, 8):
+        owner = parallel.assign_factorisations(cols, world)
+        assert owner == parallel.assign_factorisations(cols, world) and max(owner) < world
+        load = [sum(c ** 3 for c, o in zip(cols, owner) if o == r) for r in range(world)]
+        assert max(load) == 11008 ** 3 or world == 1           # the big one is alone as soon as there are 2 ranks
+    assert parallel.row_range(10, 0, 4) == (0, 3) and parallel.row_range(10, 3, 4) == (8, 10)

@@ -1,0 +1,154 @@
+"""CPU, world_size 2 over gloo: the sharding / collective logic of vlmc.parallel with the numpy oracle
+standing in for the CUDA kernels.  What is checked is the protocol: token shards + ONE sum all-reduce reproduce the
+single-rank statistics, row shards + all-gather reproduce the single-rank masks / weights, the SparseGPT block
+threshold is a k-th value over ALL shards' rows, DSnoT's executed-cycle count is a MAX over shards."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+WORLD = 2
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, port, fn_name, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(WORLD))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    try:
+        globals()[fn_name](rank, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn_name):
+    out = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_worker, args=(_free_port(), fn_name, out), nprocs=WORLD, join=True)
+    assert all(out.get(r) == "ok" for r in range(WORLD)), dict(out)
+
+
+def _data(seed, n_seq=6, S=24, C=128, R=40):
+    g = torch.Generator().manual_seed(seed)
+    xs = [(torch.randn(S, C, generator=g) * (1 + 0.1 * j)).numpy().astype(np.float32) for j in range(n_seq)]
+    W = (torch.randn(R, C, generator=g) * 0.05).numpy().astype(np.float32)
+    return xs, W
+
+
+def _wanda(rank, out):
+    from oracle import oracle
+    from vlmc import parallel
+    xs, W = _data(1)
+    N, C = len(xs), W.shape[1]
+    # single-rank truth: the reference's running mean over all sequences
+    s_ref, n = np.zeros(C, np.float32), 0
+    for x in xs:
+        s_ref, n = oracle.wanda_add_batch(s_ref, n, x, 1)
+    keep_ref, W_ref, mean_ref = oracle.wanda_nm(W, s_ref, 2, 4)
+
+    def accum(x_local, state, n_before, b):          # stands in for native.sqnorm_accum(x, s, 0, N)
+        s, _ = oracle.wanda_add_batch(state.numpy(), n_before, np.concatenate(x_local), b)
+        state.copy_(torch.from_numpy(s))
+    a, b = parallel.sample_range(N, rank, WORLD)
+    s = parallel.sharded_accumulate(accum, xs[a:b], torch.zeros(C), N)
+    assert np.abs(s.numpy() - s_ref).max() <= 1e-5 * np.abs(s_ref).max()
+
+    def select(Wr, scal, keep_rows):                 # stands in for native.wanda_nm on the row shard
+        k, Wp, m = oracle.wanda_nm(Wr.numpy(), scal.numpy(), 2, 4)
+        Wr.copy_(torch.from_numpy(Wp))
+        keep_rows.copy_(torch.from_numpy(k))
+        return torch.tensor([m], dtype=torch.float32)
+    Wt = torch.from_numpy(W.copy())
+    keep, mean = parallel.prune_linear_row_sharded(Wt, torch.from_numpy(s_ref), select, rank, WORLD)
+    assert np.array_equal(keep.numpy(), keep_ref) and np.array_equal(Wt.numpy(), W_ref)
+    assert abs(mean.item() - mean_ref) < 1e-5 * mean_ref
+    out[rank] = "ok"
+
+
+def _sparsegpt(rank, out):
+    from oracle import oracle
+    from vlmc import parallel
+    xs, W = _data(2, n_seq=8, S=64, C=256, R=48)
+    N, (R, C) = len(xs), W.shape
+    H_ref, n = np.zeros((C, C), np.float32), 0
+    for x in xs:
+        H_ref, n = oracle.sparsegpt_add_batch(H_ref, n, x, 1)
+    U_ref, dead_ref, _ = oracle.sparsegpt_inverse_factor(H_ref)
+    W_ref, _, _ = oracle.sparsegpt_fasterprune(W, "f32", None, 0.5, U=U_ref, dead=dead_ref)
+
+    def accum(x_local, state, n_before, b):          # raw partial sum with the global divisor 2/N
+        X = np.concatenate(x_local).astype(np.float64)
+        state.copy_(torch.from_numpy((X.T @ X * (2.0 / b)).astype(np.float32)))
+    a, b = parallel.sample_range(N, rank, WORLD)
+    H = parallel.sharded_accumulate(accum, xs[a:b], torch.zeros(C, C), N)
+    assert np.abs(H.numpy() - H_ref).max() <= 1e-5 * np.abs(H_ref).max()
+
+    # two Hessians -> one factorisation per rank, factors broadcast
+    calls = []
+
+    def factor(Hm):
+        calls.append(1)
+        U, dead, _ = oracle.sparsegpt_inverse_factor(Hm.numpy())
+        return torch.from_numpy(U), torch.from_numpy(dead.astype(np.uint8))
+    facs = parallel.factor_all([torch.from_numpy(H_ref), torch.from_numpy(H_ref * 2)], factor,
+                               lambda Hm: (torch.empty(C, C), torch.empty(C, dtype=torch.uint8)), rank, WORLD)
+    assert len(calls) == 1
+    assert np.array_equal(facs[0][0].numpy(), U_ref)
+    assert np.allclose(facs[1][0].numpy(), U_ref / np.sqrt(2), rtol=1e-4, atol=1e-6)
+
+    # row-sharded sweep: the block threshold must be the k-th value over the rows of BOTH shards
+    def sweep(Wr, U, dead, rows_total, reduce_sum):
+        def kth_over_all_shards(tmp, k_unused):
+            k = int(rows_total * tmp.shape[1] * 0.5)
+            parts = [None] * WORLD
+            dist.all_gather_object(parts, tmp.ravel())
+            allv = np.concatenate(parts)
+            return np.partition(allv, k)[k]
+        Wp, _, _ = oracle.sparsegpt_fasterprune(Wr.numpy(), "f32", None, 0.5, U=U.numpy(), dead=dead.numpy().astype(bool),
+                                                kth_fn=kth_over_all_shards)
+        Wr.copy_(torch.from_numpy(Wp))
+    Wt = torch.from_numpy(W.copy())
+    parallel.obs_rows_sharded(Wt, torch.from_numpy(U_ref), torch.from_numpy(dead_ref.astype(np.uint8)), sweep, rank, WORLD)
+    assert np.array_equal(Wt.numpy(), W_ref)
+    out[rank] = "ok"
+
+
+def _dsnot(rank, out):
+    from oracle import oracle
+    from vlmc import parallel
+    g = torch.Generator().manual_seed(3)
+    R, C = 24, 320
+    W = (torch.randn(R, C, generator=g) * 0.05).numpy().astype(np.float32)
+    scal = (torch.rand(C, generator=g) * 50 + 1).numpy()
+    summ = (torch.randn(C, generator=g) * 20).numpy()
+    var = (torch.rand(C, generator=g) + 0.2).numpy()
+    k = round(C * 0.6)
+    keep_ref, cyc_ref = oracle.dsnot_refine(W, scal, summ, var, sparsity_num=k, ref_fixup=False)
+    s, e = parallel.row_range(R, rank, WORLD)
+    # a shard on its own may stop earlier than the whole matrix: the executed-cycle count is a MAX over shards
+    _, cyc_local = oracle.dsnot_refine(W[s:e], scal, summ, var, sparsity_num=k, ref_fixup=False)
+    t = parallel.allreduce_max(torch.tensor([cyc_local]))
+    assert int(t.item()) == cyc_ref
+    keep_local, _ = oracle.dsnot_refine(W[s:e], scal, summ, var, sparsity_num=k, ref_fixup=False,
+                                        force_cycles=int(t.item()))
+    full = torch.zeros(R, C, dtype=torch.uint8)
+    full[s:e] = torch.from_numpy(keep_local.astype(np.uint8))
+    parallel.gather_rows(full, rank, WORLD)
+    assert np.array_equal(full.numpy().astype(bool), keep_ref)
+    # running means merge: per-rank means weighted by the sample counts
+    means = [torch.full((4,), float(rank + 1))]
+    parallel.merge_running_means(means, n_local=rank + 1, n_total=3)
+    assert torch.allclose(means[0], torch.full((4,), (1 * 1 + 2 * 2) / 3.0))
+    out[rank] = "ok"
+
+
+@pytest.mark.parametrize("fn", ["_wanda", "_sparsegpt", "_dsnot"])
+def test_two_ranks(fn, built_lib):
+    _run(fn)

@@ -79,3 +79,68 @@ def prune_linear_row_sharded(weight, scaler_row, select_fn, rank, world, group=N
         gather_rows(keep.view(torch.uint8), rank, world, group)
         dist.all_reduce(mean, op=dist.ReduceOp.SUM, group=group)
     return keep, mean / float(R)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SparseGPT: tokens sharded for H, factorisations spread over ranks, rows sharded for the OBS sweep
+# ---------------------------------------------------------------------------------------------------------------
+def assign_factorisations(columns, world):
+    """Which rank factorises which Hessian: longest-processing-time-first on the C^3 cost.
+    columns: list of C per linear (in layer order).  Returns a list of owner ranks, deterministic on every rank."""
+    load = [0.0] * world
+    owner = [0] * len(columns)
+    for i in sorted(range(len(columns)), key=lambda i: (-columns[i], i)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        owner[i] = r
+        load[r] += float(columns[i]) ** 3
+    return owner
+
+
+def allreduce_sum(t, group=None):
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def allreduce_max(t, group=None):
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t
+
+
+def broadcast_from(t, owner, group=None):
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(t, src=dist.get_global_rank(group, owner) if group else owner, group=group)
+    return t
+
+
+def sharded_accumulate(accum_fn, x_local, state, n_total, group=None):
+    """Phase 1 for any statistic that is a plain mean over samples (scaler_row, H): every rank runs ONE accumulation
+    over its own sequences with the divisor of the whole calibration set (accum_fn(x_local, state, n_before=0,
+    b=n_total)), so the partial results simply add: one SUM all-reduce, no rescaling pass."""
+    accum_fn(x_local, state, 0, n_total)
+    return allreduce_sum(state, group)
+
+
+def factor_all(Hs, factor_fn, alloc_fn, rank, world, group=None):
+    """Phase 2 of SparseGPT: the (sequential) Cholesky-inverse chains of one block are independent of each other, so
+    they are spread over the ranks and the factors broadcast.  factor_fn(H) -> (U, dead) runs the damping loop;
+    alloc_fn(H) -> (U, dead) returns empty receive buffers.  Returns [(U, dead)] for every Hessian on every rank."""
+    owners = assign_factorisations([H.shape[0] for H in Hs], world)
+    out = []
+    for H, owner in zip(Hs, owners):
+        out.append(factor_fn(H) if owner == rank else alloc_fn(H))
+    for (U, dead), owner in zip(out, owners):
+        broadcast_from(U, owner, group)
+        broadcast_from(dead, owner, group)
+    return out
+
+
+def obs_rows_sharded(weight, U, dead, sweep_fn, rank, world, group=None):
+    """Phase 3: rank r sweeps rows row_range(R, r, world) of `weight` in place; sweep_fn(W_rows, U, dead, rows_total,
+    reduce_sum) exchanges only the block histograms (unstructured) through reduce_sum.  Pruned rows are gathered."""
+    R = weight.shape[0]
+    s, e = row_range(R, rank, world)
+    if e > s:
+        sweep_fn(weight[s:e], U, dead, R, lambda t: allreduce_sum(t, group))
+    return gather_rows(weight, rank, world, group)
