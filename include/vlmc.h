@@ -171,6 +171,20 @@ int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U, int64_t ld
                         void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * K13 / K10 building block: fp32-accurate GEMM on the tensor cores (3xTF32 split, tcgen05 + TMEM + TMA).
+ * Replaces the fp32 torch.matmul of sparsegpt_pruner.py:210 (W[:, i2:] -= Err1 @ Hinv[i1:i2, i2:]) and the GEMMs inside
+ * cuSOLVER's potrf / potri behind :114-157.
+ *   C[M,N] = beta * C + alpha * A[M,K] * op(B)      A row-major [M,K]; b_nk != 0: B row-major [N,K] (C = A B^T),
+ *                                                   else B row-major [K,N]
+ *   tri != 0: only tiles touching the lower triangle are computed (symmetric rank-k update of a lower triangle)
+ *   kc: K elements accumulated inside the tensor core between round-to-nearest flushes (0 = 128; multiples of 32)
+ * K, N, lda, ldb, ldc multiples of 4; pointers 16-byte aligned.
+ */
+int vlmc_gemm_tf32x3(int b_nk, int M, int N, int K, float alpha, const float* A, int64_t lda,
+                     const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int tri, int kc,
+                     void* stream);
+
+/*
  * K11-K13  The column-block OBS sweep.  Replaces sparsegpt_pruner.py:160-215: per 128-column block the
  * unstructured mask (score <= k-th smallest block score, k = int(R*128*sparsity)) or the n:m mask, the 128
  * sequential error-propagation steps, and the lazy trailing update W[:, i2:] -= Err1 @ U[i1:i2, i2:].

@@ -9,9 +9,10 @@
 //   chol_lower   right-looking blocked (128): diagonal block factor + its inverse in one CTA (shared memory),
 //                panel = GEMM with the block inverse, trailing symmetric update = GEMM on lower tiles only
 //   tri inverse  recursive doubling: [[A,0],[B,D]]^-1 = [[A^-1,0],[-D^-1 B A^-1, D^-1]], two GEMMs per merge
-// GEMMs are true fp32 (sgemm.cuh), like the reference's fp32 cuSOLVER/cuBLAS path.  A non-positive or NaN pivot
+// GEMMs run on the tensor cores with the 3xTF32 split (gemm3x.cu): fp32-grade accuracy, like the reference's fp32
+// cuSOLVER/cuBLAS path.  A non-positive or NaN pivot
 // sets *status = VLMC_NOT_POSDEF; the caller adds percdamp * mean(diag H) and retries (reference :114-128).
-#include "sgemm.cuh"
+#include "gemm3x.cuh"
 
 namespace vlmc {
 
@@ -174,11 +175,11 @@ extern "C" int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U,
     if (below > 0) {
       float* panel = F + (int64_t)(k0 + bs) * ldf + k0;
       // panel <- panel * L_kk^-T   (C = A B^T with B = L_kk^-1 stored [N,K])
-      rc = sgemm(true, below, bs, bs, 1.f, panel, ldf, U + (int64_t)k0 * ldu + k0, ldu, 0.f, panel, ldf, 0, st);
+      rc = gemm3x(true, below, bs, bs, 1.f, panel, ldf, U + (int64_t)k0 * ldu + k0, ldu, 0.f, panel, ldf, 0, 0, st);
       if (rc) return rc;
       // trailing <- trailing - panel panel^T on the lower tiles
       float* trail = F + (int64_t)(k0 + bs) * ldf + (k0 + bs);
-      rc = sgemm(true, below, below, bs, -1.f, panel, ldf, panel, ldf, 1.f, trail, ldf, 1, st);
+      rc = gemm3x(true, below, below, bs, -1.f, panel, ldf, panel, ldf, 1.f, trail, ldf, 1, 0, st);
       if (rc) return rc;
     }
   }
@@ -196,10 +197,10 @@ extern "C" int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U,
       const int a = starts[q], b = ends[q], c = ends[q + 1];   // left [a,b), right [b,c)
       const int m = c - b, n = b - a;
       // X = L[b:c, a:b] * Li[a:b, a:b]
-      rc = sgemm(false, m, n, n, 1.f, F + (int64_t)b * ldf + a, ldf, U + (int64_t)a * ldu + a, ldu, 0.f, X, n, 0, st);
+      rc = gemm3x(false, m, n, n, 1.f, F + (int64_t)b * ldf + a, ldf, U + (int64_t)a * ldu + a, ldu, 0.f, X, n, 0, 0, st);
       if (rc) return rc;
       // Li[b:c, a:b] = -Li[b:c, b:c] * X
-      rc = sgemm(false, m, n, m, -1.f, U + (int64_t)b * ldu + b, ldu, X, n, 0.f, U + (int64_t)b * ldu + a, ldu, 0, st);
+      rc = gemm3x(false, m, n, m, -1.f, U + (int64_t)b * ldu + b, ldu, X, n, 0.f, U + (int64_t)b * ldu + a, ldu, 0, 0, st);
       if (rc) return rc;
       starts[out] = a; ends[out] = c; ++out;
     }

@@ -1,0 +1,16 @@
+// fp32-accurate GEMM on the 5th-gen tensor cores (3xTF32 split), the building block of K10 and K13.
+#pragma once
+#include "common.cuh"
+
+namespace vlmc {
+
+// C[M,N] = beta * C + alpha * A[M,K] * op(B)
+//   A row-major [M,K];  b_nk: B row-major [N,K] (C = A B^T), else B row-major [K,N]
+//   tri = 1: only the tiles that touch the lower triangle (column block start <= last row of the tile) are computed
+//   kc: K elements accumulated inside the tensor core between round-to-nearest flushes into registers (0 = 128)
+// Requirements: K, N, lda, ldb, ldc multiples of 4; A, B, C 16-byte aligned.  A or B may alias C only when every
+// output tile reads exactly the operand rows it overwrites (N <= tile width: the panel solve of the Cholesky).
+int gemm3x(bool b_nk, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb,
+           float beta, float* C, int64_t ldc, int tri, int kc, cudaStream_t st);
+
+}  // namespace vlmc

@@ -16,8 +16,8 @@
 //                                U1 tile in shared memory; the 128 sequential steps broadcast the pivot column by
 //                                shuffle, only pruned columns (err != 0) cost an update.  Writes the finished
 //                                columns to the fp16/bf16 weight, the fp32 working copy, Err1 and the keep mask.
-//   K13  the lazy trailing update, the fp32 GEMM of sgemm.cuh.
-#include "sgemm.cuh"
+//   K13  the lazy trailing update on the tensor cores: the 3xTF32 tcgen05 GEMM of gemm3x.cu (fp32-grade accuracy).
+#include "gemm3x.cuh"
 
 namespace vlmc {
 
@@ -388,7 +388,7 @@ extern "C" int vlmc_obs_block_finish(void* W, int dtype, int R, int C, int64_t l
   const int i2 = p.i1 + p.bs;
   if (i2 < C) {
     // K13: W[:, i2:] -= Err1 @ U[i1:i2, i2:]
-    rc = sgemm(false, R, C - i2, kOB, -1.f, l.Err, kOB, U + (int64_t)p.i1 * ldu + i2, ldu, 1.f, l.W32 + i2, C, 0, st);
+    rc = gemm3x(false, R, C - i2, kOB, -1.f, l.Err, kOB, U + (int64_t)p.i1 * ldu + i2, ldu, 1.f, l.W32 + i2, C, 0, 0, st);
     if (rc) return rc;
   }
   return check_launch();

@@ -47,6 +47,7 @@ SIGNATURES = {
     "vlmc_hessian_prepare": (_i, [_vp, _i, _i64, _f, _vp, _vp, _vp]),
     "vlmc_hessian_add_damp": (_i, [_vp, _i, _i64, _vp, _vp]),
     "vlmc_chol_inv_upper": (_i, [_vp, _i, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "vlmc_gemm_tf32x3": (_i, [_i, _i, _i, _i, _f, _vp, _i64, _vp, _i64, _f, _vp, _i64, _i, _i, _vp]),
     "vlmc_obs_sweep": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp, _d, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_hessian_accum": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _d, _d, _i, _i64, _vp]),
     "vlmc_obs_begin": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
@@ -294,6 +295,23 @@ def chol_inv_upper(H, U=None):
                                      ws.data_ptr(), ws.numel(), _stream(H))
     _check("vlmc_chol_inv_upper", st)
     return U, status
+
+
+def gemm_tf32x3(A, B, C=None, alpha=1.0, beta=0.0, b_nk=False, tri=False, kc=0):
+    """C = beta * C + alpha * A @ (B.T if b_nk else B) in fp32 on the tensor cores (3xTF32 split, gemm3x.cu).
+    A, B, C may be views with a row stride (last dim contiguous)."""
+    _require_cuda(A, B, C)
+    M, K = A.shape
+    N = B.shape[0] if b_nk else B.shape[1]
+    assert (B.shape[1] if b_nk else B.shape[0]) == K
+    if C is None:
+        C = torch.empty(M, N, device=A.device, dtype=torch.float32)
+    for t in (A, B, C):
+        assert t.dtype == torch.float32 and t.stride(-1) == 1
+    _check("vlmc_gemm_tf32x3", load().vlmc_gemm_tf32x3(
+        int(b_nk), M, N, K, float(alpha), A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), float(beta),
+        C.data_ptr(), C.stride(0), int(tri), int(kc), _stream(A)))
+    return C
 
 
 def obs_sweep(W, U, sparsity, prune_n=0, prune_m=0, dead=None, blocksize=128, want_mask=False):
