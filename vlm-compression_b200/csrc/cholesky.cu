@@ -39,53 +39,152 @@ __global__ void flip_to_upper_kernel(float* __restrict__ U, int64_t ldu, int C) 
   }
 }
 
-// One CTA: factor the bs x bs diagonal block at (k0,k0) of F in shared memory (left-looking, one thread per
-// row), write L_kk back, and write L_kk^-1 (lower, zero above the diagonal) into Li at the same position.
-__global__ void __launch_bounds__(kPotrfThreads)
+// One CTA factors the bs x bs diagonal block at (k0,k0) of F and inverts the factor, all in shared memory:
+// writes L_kk back to F and L_kk^-1 (lower, zero above the diagonal) to Li at the same position.
+// Thread t owns ROW t of the block.  Columns are processed 16 at a time: the thread's 16 entries live in registers,
+// the update with all previous columns is a left-looking pass over a transposed copy of L (one private value + four
+// broadcast 16-byte loads per k, 16 independent FMAs), the 16 columns themselves are a right-looking sweep with ONE
+// __syncthreads per column (the pivot column is exchanged through a double-buffered 16-float line).  The inverse
+// needs no synchronisation at all: thread c owns COLUMN c of L^-1 and forward-substitutes 16 rows at a time.
+// Blocks smaller than 128 are padded with the identity.
+constexpr int kPB = 16;
+constexpr int kLdS = kNB + 1;
+constexpr size_t kPotrfSmem = ((size_t)kNB * kLdS + 2 * (size_t)kNB * kNB + 2 * kPB + kNB) * sizeof(float);
+
+constexpr int kPotrfIoThreads = 512;     // all warps move the block in and out; the first 128 threads compute
+
+__device__ __forceinline__ void potrf_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kPotrfIoThreads)
 potrf_block_kernel(float* F, int64_t ldf, float* Li, int64_t ldi, int k0, int bs, int* status) {
-  extern __shared__ float sm[];
-  float (*S)[kNB + 1] = reinterpret_cast<float (*)[kNB + 1]>(sm);
-  float (*X)[kNB + 1] = reinterpret_cast<float (*)[kNB + 1]>(sm + kNB * (kNB + 1));
+  extern __shared__ __align__(16) float sm[];
+  float* S = sm;                          // [128][129]  A, then L, row-major
+  float* St = S + kNB * kLdS;             // [128][128]  St[k][row] = L[row][k]
+  float* Xs = St + kNB * kNB;             // [128][128]  Xs[k][c] = (L^-1)[k][c]
+  float* colbuf = Xs + kNB * kNB;         // [2][16]
+  float* invd = colbuf + 2 * kPB;         // [128]  1 / L[k][k]
   const int t = threadIdx.x;
-  for (int idx = t; idx < bs * bs; idx += kPotrfThreads) {
-    const int i = idx / bs, j = idx % bs;
-    S[i][j] = (j <= i) ? F[(int64_t)(k0 + i) * ldf + k0 + j] : 0.f;
-    X[i][j] = 0.f;
+  {
+    // 128 x 128 block = 4096 float4, 8 per thread, all loads in flight together (k0, ldf are multiples of 4)
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = t + u * kPotrfIoThreads, i = idx >> 5, j4 = (idx & 31) * 4;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < bs && j4 <= i) v[u] = *reinterpret_cast<const float4*>(F + (int64_t)(k0 + i) * ldf + k0 + j4);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = t + u * kPotrfIoThreads, i = idx >> 5, j4 = (idx & 31) * 4;
+      const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j4 + q;
+        S[i * kLdS + j] = (i < bs && j <= i) ? e[q] : (i == j ? 1.f : 0.f);
+      }
+      *reinterpret_cast<float4*>(Xs + idx * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   __syncthreads();
-  bool bad = false;
-  for (int j = 0; j < bs; ++j) {
-    // row t >= j: s = F[t][j] - sum_{k<j} L[t][k] L[j][k]
-    float s = 0.f;
-    if (t >= j && t < bs) {
-      s = S[t][j];
-      for (int k = 0; k < j; ++k) s = fmaf(-S[t][k], S[j][k], s);
+
+  if (t < kPotrfThreads) {
+    bool bad = false;
+    const int wend = (t | 31) + 1;          // rows of this warp end here: nothing to do once c0 >= wend
+#pragma unroll 1
+    for (int c0 = 0; c0 < kNB; c0 += kPB) {
+      float a[kPB];
+#pragma unroll
+      for (int c = 0; c < kPB; ++c) a[c] = S[t * kLdS + c0 + c];
+      // left-looking: a[c] -= sum_{k < c0} L[t][k] * L[c0 + c][k]
+      if (c0 < wend) {
+#pragma unroll 4
+        for (int k = 0; k < c0; ++k) {
+          const float lk = St[k * kNB + t];
+          const float4* rp = reinterpret_cast<const float4*>(St + k * kNB + c0);
+          const float4 r0 = rp[0], r1 = rp[1], r2 = rp[2], r3 = rp[3];
+          const float r[kPB] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w, r3.x, r3.y, r3.z, r3.w};
+#pragma unroll
+          for (int c = 0; c < kPB; ++c) a[c] = fmaf(-lk, r[c], a[c]);
+        }
+      }
+      // the 16 columns of this block, right-looking, one barrier per column
+#pragma unroll
+      for (int j = 0; j < kPB; ++j) {
+        float* buf = colbuf + (j & 1) * kPB;
+        if (t >= c0 + j && t < c0 + kPB) buf[t - c0] = a[j];
+        potrf_bar();
+        float d = buf[j];
+        if (!(d > 0.f) || !isfinite(d)) { bad = true; d = 1.f; }
+        const float piv = sqrtf(d);
+        const float inv = 1.f / piv;
+        if (t == c0 + j) { a[j] = piv; invd[c0 + j] = inv; }
+        else a[j] *= inv;                                   // L[t][c0 + j] for t > c0 + j (rows above are never stored)
+#pragma unroll
+        for (int c = j + 1; c < kPB; ++c) a[c] = fmaf(-a[j], buf[c] * inv, a[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < kPB; ++c) {
+        const bool low = t >= c0 + c;
+        if (low) S[t * kLdS + c0 + c] = a[c];
+        St[(c0 + c) * kNB + t] = low ? a[c] : 0.f;
+      }
+      potrf_bar();
     }
-    __syncthreads();
-    if (t == j) {
-      if (!(s > 0.f) || !isfinite(s)) { bad = true; s = 1.f; }
-      S[j][j] = sqrtf(s);
-    }
-    __syncthreads();
-    if (t > j && t < bs) S[t][j] = s / S[j][j];
-    __syncthreads();   // column j is final before any thread starts the dot products of column j + 1
-  }
-  if (bad) atomicMax(status, (int)VLMC_NOT_POSDEF);
-  // inverse: thread c solves L x = e_c by forward substitution (column c of L^-1)
-  if (t < bs) {
+    if (bad && t == 0) atomicMax(status, (int)VLMC_NOT_POSDEF);
+
+    // inverse: column c = t of X = L^-1 by blocked forward substitution; reads only L and this thread's own column
     const int c = t;
-    X[c][c] = 1.f / S[c][c];
-    for (int i = c + 1; i < bs; ++i) {
-      float s = 0.f;
-      for (int k = c; k < i; ++k) s = fmaf(S[i][k], X[k][c], s);
-      X[i][c] = -s / S[i][i];
+    const int kbeg = (t >> 5) * 32;                       // X[k][c] = 0 for k < c; uniform per warp
+#pragma unroll 1
+    for (int r0 = kbeg; r0 < kNB; r0 += kPB) {
+      float acc[kPB];
+#pragma unroll
+      for (int r = 0; r < kPB; ++r) acc[r] = 0.f;
+#pragma unroll 4
+      for (int k = kbeg; k < r0; ++k) {
+        const float xk = Xs[k * kNB + c];
+        const float4* rp = reinterpret_cast<const float4*>(St + k * kNB + r0);
+        const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2], q3 = rp[3];
+        const float l[kPB] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+        for (int r = 0; r < kPB; ++r) acc[r] = fmaf(l[r], xk, acc[r]);
+      }
+      float x[kPB];
+#pragma unroll
+      for (int r = 0; r < kPB; ++r) {
+        float sacc = ((r0 + r == c) ? 1.f : 0.f) - acc[r];
+#pragma unroll
+        for (int q = 0; q < r; ++q) sacc = fmaf(-S[(r0 + r) * kLdS + r0 + q], x[q], sacc);
+        x[r] = sacc * invd[r0 + r];
+      }
+#pragma unroll
+      for (int r = 0; r < kPB; ++r) Xs[(r0 + r) * kNB + c] = x[r];
     }
   }
   __syncthreads();
-  for (int idx = t; idx < bs * bs; idx += kPotrfThreads) {
-    const int i = idx / bs, j = idx % bs;
-    if (j <= i) F[(int64_t)(k0 + i) * ldf + k0 + j] = S[i][j];
-    Li[(int64_t)(k0 + i) * ldi + k0 + j] = (j <= i) ? X[i][j] : 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int idx = t + u * kPotrfIoThreads, i = idx >> 5, j4 = (idx & 31) * 4;
+    if (i < bs && j4 < bs) {                              // bs is a multiple of 4
+      float4 lo, xo;
+      float* lp = &lo.x;
+      float* xp = &xo.x;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = j4 + q;
+        lp[q] = S[i * kLdS + j];
+        xp[q] = (j <= i) ? Xs[i * kNB + j] : 0.f;
+      }
+      if (j4 <= i) {
+        float* fp = F + (int64_t)(k0 + i) * ldf + k0 + j4;
+        if (j4 + 3 <= i) *reinterpret_cast<float4*>(fp) = lo;
+        else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (j4 + q <= i) fp[q] = lp[q];
+        }
+      }
+      *reinterpret_cast<float4*>(Li + (int64_t)(k0 + i) * ldi + k0 + j4) = xo;
+    }
   }
 }
 
@@ -155,7 +254,7 @@ extern "C" int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U,
   const int nb = (C + kNB - 1) / kNB;
 
   static bool attr_set = false;
-  const int potrf_smem = 2 * kNB * (kNB + 1) * sizeof(float);
+  const int potrf_smem = (int)kPotrfSmem;
   if (!attr_set) {
     if (cudaFuncSetAttribute(potrf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, potrf_smem) != cudaSuccess)
       return check_launch();
@@ -170,7 +269,7 @@ extern "C" int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U,
   for (int k = 0; k < nb; ++k) {
     const int k0 = k * kNB;
     const int bs = (C - k0 < kNB) ? (C - k0) : kNB;
-    potrf_block_kernel<<<1, kPotrfThreads, potrf_smem, st>>>(F, ldf, U, ldu, k0, bs, status);
+    potrf_block_kernel<<<1, kPotrfIoThreads, potrf_smem, st>>>(F, ldf, U, ldu, k0, bs, status);
     const int below = C - k0 - bs;
     if (below > 0) {
       float* panel = F + (int64_t)(k0 + bs) * ldf + k0;
@@ -197,10 +296,10 @@ extern "C" int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U,
       const int a = starts[q], b = ends[q], c = ends[q + 1];   // left [a,b), right [b,c)
       const int m = c - b, n = b - a;
       // X = L[b:c, a:b] * Li[a:b, a:b]
-      rc = gemm3x(false, m, n, n, 1.f, F + (int64_t)b * ldf + a, ldf, U + (int64_t)a * ldu + a, ldu, 0.f, X, n, 0, 0, st);
+      rc = gemm3x(false, m, n, n, 1.f, F + (int64_t)b * ldf + a, ldf, U + (int64_t)a * ldu + a, ldu, 0.f, X, n, 0, 0, st, 1);
       if (rc) return rc;
       // Li[b:c, a:b] = -Li[b:c, b:c] * X
-      rc = gemm3x(false, m, n, m, -1.f, U + (int64_t)b * ldu + b, ldu, X, n, 0.f, U + (int64_t)b * ldu + a, ldu, 0, 0, st);
+      rc = gemm3x(false, m, n, m, -1.f, U + (int64_t)b * ldu + b, ldu, X, n, 0.f, U + (int64_t)b * ldu + a, ldu, 0, 0, st, 2);
       if (rc) return rc;
       starts[out] = a; ends[out] = c; ++out;
     }

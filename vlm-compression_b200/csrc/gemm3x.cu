@@ -50,6 +50,7 @@ struct G3Params {
   int M, N, K;
   float alpha, beta;
   int tri, kc;
+  int kmode;         // 0 dense; 1: B[k][j] == 0 for k < j (lower-triangular [K,N]); 2: A[i][k] == 0 for k > i
   int nbi, nbj, ntiles;
 };
 
@@ -86,6 +87,18 @@ __device__ __forceinline__ void g3_tile(int t, const G3Params& p, int& bi, int& 
     t -= cnt;
   }
   bj = 0;  // unreachable for t < ntiles
+}
+
+// k-slices [sb, se) of tile (bi, bj) that can be non-zero (structural zeros of a triangular operand are skipped)
+template <int TN>
+__device__ __forceinline__ void g3_krange(const G3Params& p, int bi, int bj, int nslices, int& sb, int& se) {
+  sb = 0; se = nslices;
+  if (p.kmode == 1) {
+    sb = (bj * TN) / kG3K;
+  } else if (p.kmode == 2) {
+    const int e = (bi * kG3M + kG3M + kG3K - 1) / kG3K;
+    if (e < se) se = e;
+  }
 }
 
 __device__ __forceinline__ void g3_split(const uint4& raw, uint4& hi, uint4& lo) {
@@ -136,7 +149,6 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ 
 
   const int nslices = (p.K + kG3K - 1) / kG3K;
   const int slices_per_chunk = CHUNKED ? p.kc / kG3K : nslices;
-  const int nchunks = (nslices + slices_per_chunk - 1) / slices_per_chunk;
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -146,7 +158,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ 
         int bi, bj;
         g3_tile<TN>(t, p, bi, bj);
         const int m0 = bi * kG3M, n0 = bj * TN;
-        for (int ks = 0; ks < nslices; ++ks) {
+        int sbeg, send;
+        g3_krange<TN>(p, bi, bj, nslices, sbeg, send);
+        for (int ks = sbeg; ks < send; ++ks) {
           const int k0 = ks * kG3K;
           mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
@@ -169,10 +183,12 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ 
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-        for (int ch = 0; ch < nchunks; ++ch) {
-          const int sbeg = ch * slices_per_chunk;
+        int bi, bj, tb, te;
+        g3_tile<TN>(t, p, bi, bj);
+        g3_krange<TN>(p, bi, bj, nslices, tb, te);
+        for (int sbeg = tb; sbeg < te; sbeg += slices_per_chunk) {
           int send = sbeg + slices_per_chunk;
-          if (send > nslices) send = nslices;
+          if (send > te) send = te;
           mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * TN;
@@ -206,7 +222,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ 
     const int ct = threadIdx.x - kG3CvtWarp0 * 32;
     int stage = 0; uint32_t phase = 0;
     for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-      for (int ks = 0; ks < nslices; ++ks) {
+      int bi, bj, tb, te;
+      g3_tile<TN>(t, p, bi, bj);
+      g3_krange<TN>(p, bi, bj, nslices, tb, te);
+      for (int ks = tb; ks < te; ++ks) {
         mbar_wait(&bars->full[stage], phase);
         uint8_t* sa = smem + stage * kStageBytes;
         uint8_t* sb = sa + 2 * kG3ABytes;
@@ -286,6 +305,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ 
         float sum[kCols];
 #pragma unroll
         for (int c = 0; c < kCols; ++c) sum[c] = 0.f;
+        int tb, te;
+        g3_krange<TN>(p, bi, bj, nslices, tb, te);
+        const int nchunks = (te - tb + slices_per_chunk - 1) / slices_per_chunk;
         for (int ch = 0; ch < nchunks; ++ch) {
           mbar_wait(&bars->tmem_full[acc], acc_phase);
           tc_fence_after();
@@ -392,13 +414,14 @@ static int g3_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t 
 }
 
 int gemm3x(bool b_nk, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb,
-           float beta, float* C, int64_t ldc, int tri, int kc, cudaStream_t st) {
+           float beta, float* C, int64_t ldc, int tri, int kc, cudaStream_t st, int kmode) {
   if (M <= 0 || N <= 0) return VLMC_OK;
   if (K <= 0 || !A || !B || !C) return VLMC_ERR_BAD_ARG;
   if ((K & 3) || (N & 3) || (lda & 3) || (ldb & 3) || (ldc & 3) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15) ||
       ((uintptr_t)C & 15))
     return VLMC_ERR_UNSUPPORTED;
   if (kc <= 0) kc = 128;
+  if (kmode < 0 || kmode > 2 || (kmode == 1 && b_nk)) return VLMC_ERR_BAD_ARG;
   kc = (kc + kG3K - 1) / kG3K * kG3K;
   const bool chunked = K > kc;
   const int TN = (!chunked && N > 128) ? 256 : 128;
@@ -411,7 +434,7 @@ int gemm3x(bool b_nk, int M, int N, int K, float alpha, const float* A, int64_t 
   if (rc) return rc;
 
   G3Params p;
-  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.tri = tri; p.kc = kc;
+  p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.tri = tri; p.kc = kc; p.kmode = kmode;
   p.nbi = p.nbj = p.ntiles = 0;
   if (chunked) return b_nk ? g3_launch<128, false, true>(amap, bmap, p, st) : g3_launch<128, true, true>(amap, bmap, p, st);
   if (TN == 256) return b_nk ? g3_launch<256, false, false>(amap, bmap, p, st) : g3_launch<256, true, false>(amap, bmap, p, st);
@@ -426,5 +449,5 @@ extern "C" int vlmc_gemm_tf32x3(int b_nk, int M, int N, int K, float alpha, cons
   using namespace vlmc;
   if (!A || !B || !C || M < 1 || N < 1 || K < 1 || lda < K || ldc < N || ldb < (b_nk ? K : N)) return VLMC_ERR_BAD_ARG;
   if (!is_device_ptr(A) || !is_device_ptr(B) || !is_device_ptr(C)) return VLMC_ERR_NOT_DEVICE;
-  return gemm3x(b_nk != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kc, (cudaStream_t)stream);
+  return gemm3x(b_nk != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kc, (cudaStream_t)stream, 0);
 }
