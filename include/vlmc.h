@@ -126,6 +126,22 @@ int vlmc_wanda_threshold(void* W, int dtype, int R, int C, int64_t ldw,
                          void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * Multi-GPU mask exchange (new: the reference prunes independent replicas).  When the output rows of a linear
+ * are split across GPUs each rank computes module.mask (wanda_pruner.py:339) for its rows only; the weights
+ * are replicated, so ranks exchange the masks as BITS (1 bit per weight) and zero their own replica (:341) locally.
+ *   vlmc_mask_pack          keep_mask [R, ldm] bytes (0/1) -> bits [R, ldb] bytes; bit e of byte j = column 8j + e
+ *   vlmc_mask_apply_packed  bits -> keep_mask bytes (may be NULL) and, if zero_w, W[r,c] = 0 where the bit is 0.
+ *                           The bits of row r are at bits + (r / rows_per_seg) * seg_stride + (r % rows_per_seg) * ldb:
+ *                           an all-gathered buffer laid out [rank][this linear's row shard] is consumed in ONE call
+ *                           (rows_per_seg = R / world, seg_stride = bytes per rank); rows_per_seg <= 0: one segment.
+ * C must be a multiple of 16.
+ */
+int vlmc_mask_pack(const uint8_t* keep_mask, int R, int C, int64_t ldm, uint8_t* bits, int64_t ldb, void* stream);
+int vlmc_mask_apply_packed(void* W, int dtype, int R, int C, int64_t ldw, const uint8_t* bits, int64_t ldb,
+                           int rows_per_seg, int64_t seg_stride, uint8_t* keep_mask, int64_t ldm, int zero_w,
+                           void* stream);
+
+/*
  * K14  SparseLoRA masked merge.  Replaces Linear.merge() (sparse branch), lora.py:384-387,
  * fused with the re-mask of train.py:634-637:
  *   W[r,c] <- keep_mask[r,c] ? round_to_W_dtype( float(W[r,c]) + scaling * sum_k B[r,k]*A[k,c] ) : 0

@@ -284,6 +284,55 @@ def test_nm_full_size_properties(native):
     assert torch.equal(W, torch.where(keep, W0, torch.zeros_like(W0)))
 
 
+# ------------------------------------------------------------------------------------------- mask exchange (8e)
+@pytest.mark.parametrize("R,C,tag", [(40, 4096, "f16"), (17, 1408, "bf16"), (9, 2048, "f32"), (1376, 4096, "f16")])
+def test_mask_pack_and_apply_packed(native, R, C, tag):
+    """bits == numpy.packbits(bitorder=little) of the mask; apply(bits) rebuilds the mask bytes and zeroes exactly
+    the pruned weights - the row-sharded exchange (1 bit / weight) gives what the selecting rank has."""
+    g = torch.Generator().manual_seed(R + C)
+    keep = torch.rand(R, C, generator=g) < 0.5
+    keep[0] = True
+    keep[1] = False
+    W = weights(R, C, 5, DT[tag])
+    bits = native.mask_pack(keep.cuda())
+    want = np.packbits(keep.numpy().astype(np.uint8), axis=1, bitorder="little")
+    assert np.array_equal(bits.cpu().numpy(), want)
+    Wc = W.clone().cuda()
+    keep2 = torch.empty(R, C, dtype=torch.bool, device="cuda")
+    native.mask_apply_packed(Wc, bits, keep2)
+    assert torch.equal(keep2.cpu(), keep)
+    assert torch.equal(Wc.cpu(), torch.where(keep, W, torch.zeros_like(W)))
+    # strided row shard of a larger matrix, mask only
+    big = torch.zeros(R + 3, C, dtype=torch.bool, device="cuda")
+    native.mask_apply_packed(Wc, bits, big[2:2 + R], zero_w=False)
+    assert torch.equal(big[2:2 + R].cpu(), keep) and not bool(big[:2].any()) and not bool(big[2 + R:].any())
+
+
+def test_nm_row_shards_with_packed_exchange_equal_full(native):
+    """Two row shards selected separately, exchanged as bits, equal the unsharded 2:4 selection (mask and weights)."""
+    R, C = 256, 4096
+    W0 = weights(R, C, 11, torch.float16).cuda()
+    s = scaler(C, 4).cuda()
+    Wfull = W0.clone()
+    keep_full, _ = native.wanda_nm(Wfull, s, 2, 4)
+    halves = []
+    for r in range(2):
+        Wr = W0.clone()                                       # this rank's replica
+        keep = torch.zeros(R, C, dtype=torch.bool, device="cuda")
+        a, b = r * R // 2, (r + 1) * R // 2
+        native.wanda_nm(Wr[a:b], s, 2, 4, keep_mask=keep[a:b])
+        halves.append((Wr, keep, native.mask_pack(keep[a:b])))
+    pad = 64                                                  # bytes between the two ranks' segments
+    n = (R // 2) * (C // 8)
+    gathered = torch.zeros(2 * (n + pad), dtype=torch.uint8, device="cuda")
+    for r in range(2):
+        gathered[r * (n + pad): r * (n + pad) + n] = halves[r][2].reshape(-1)
+    for r in range(2):
+        Wr, keep, _ = halves[r]
+        native.mask_apply_packed(Wr, gathered, keep, True, rows_per_seg=R // 2, seg_stride=n + pad)
+        assert torch.equal(keep, keep_full) and torch.equal(Wr, Wfull)
+
+
 # ------------------------------------------------------------------------------------------- K7
 @pytest.mark.parametrize("R,C,tag,p", [(4224, 1408, "f16", 0.5), (1408, 6144, "f16", 0.5), (192, 64, "f32", 0.5),
                                        (6144, 1408, "bf16", 0.6), (64, 128, "f32", 0.3), (1408, 1408, "f16", 0.1)])

@@ -72,6 +72,43 @@ def _wanda(rank, out):
     out[rank] = "ok"
 
 
+def _wanda_packed(rank, out):
+    """Row shards + ONE all-gather of bit-packed masks for several linears: same masks / weights as one rank."""
+    from oracle import oracle
+    from vlmc import parallel
+    g = torch.Generator().manual_seed(7)
+    shapes = [(8, 64), (12, 32), (4, 128)]
+    Ws = [(torch.randn(R, C, generator=g) * 0.05).numpy().astype(np.float32) for R, C in shapes]
+    scal = [(torch.rand(C, generator=g) * 9 + 1).numpy() for _, C in shapes]
+    refs = [oracle.wanda_nm(W, s, 2, 4) for W, s in zip(Ws, scal)]
+
+    def make_select(i):
+        def select(Wr, keep_rows):                   # stands in for native.wanda_nm on the row shard
+            k, Wp, m = oracle.wanda_nm(Wr.numpy(), scal[i], 2, 4)
+            Wr.copy_(torch.from_numpy(Wp))
+            keep_rows.copy_(torch.from_numpy(k))
+            return torch.tensor([m], dtype=torch.float32)
+        return select
+
+    def pack(keep_rows, bits):                       # stands in for native.mask_pack
+        bits.copy_(torch.from_numpy(np.packbits(keep_rows.numpy().astype(np.uint8), axis=1, bitorder="little")))
+
+    def apply(Wf, bits, keep, rows_per_seg, seg_stride):     # stands in for native.mask_apply_packed
+        R, C = Wf.shape
+        b = bits.numpy()
+        rows = [b[g * seg_stride: g * seg_stride + rows_per_seg * (C // 8)].reshape(rows_per_seg, C // 8)
+                for g in range(R // rows_per_seg)]
+        k = np.unpackbits(np.concatenate(rows), axis=1, bitorder="little").astype(bool)
+        keep.copy_(torch.from_numpy(k))
+        Wf.mul_(torch.from_numpy(k.astype(np.float32)))
+    Wt = [torch.from_numpy(W.copy()) for W in Ws]
+    res = parallel.prune_block_rows_packed(Wt, [make_select(i) for i in range(3)], pack, apply, rank, WORLD)
+    for (keep, mean), W, (keep_ref, W_ref, mean_ref) in zip(res, Wt, refs):
+        assert np.array_equal(keep.numpy(), keep_ref) and np.array_equal(W.numpy(), W_ref)
+        assert abs(mean.item() - mean_ref) < 1e-5 * mean_ref
+    out[rank] = "ok"
+
+
 def _sparsegpt(rank, out):
     from oracle import oracle
     from vlmc import parallel
@@ -149,6 +186,6 @@ def _dsnot(rank, out):
     out[rank] = "ok"
 
 
-@pytest.mark.parametrize("fn", ["_wanda", "_sparsegpt", "_dsnot"])
+@pytest.mark.parametrize("fn", ["_wanda", "_wanda_packed", "_sparsegpt", "_dsnot"])
 def test_two_ranks(fn, built_lib):
     _run(fn)

@@ -43,6 +43,8 @@ SIGNATURES = {
     "vlmc_wanda_rowselect": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_wanda_nm": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_wanda_threshold": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "vlmc_mask_pack": (_i, [_vp, _i, _i, _i64, _vp, _i64, _vp]),
+    "vlmc_mask_apply_packed": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _i64, _vp, _i64, _i, _vp]),
     "vlmc_sparselora_merge": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _f, _vp, _i64, _i, _vp]),
     "vlmc_hessian_prepare": (_i, [_vp, _i, _i64, _f, _vp, _vp, _vp]),
     "vlmc_hessian_add_damp": (_i, [_vp, _i, _i64, _vp, _vp]),
@@ -217,6 +219,34 @@ def wanda_threshold(W, scaler_row, k_global, zero_w=True, keep_mask=None):
                                       _stream(W))
     _check("vlmc_wanda_threshold", st)
     return keep_mask, score_mean
+
+
+def mask_pack(keep_mask, bits=None):
+    """keep_mask [R, C] bool/uint8 -> bits [R, C // 8] uint8 (bit e of byte j = column 8 j + e)."""
+    _require_cuda(keep_mask, bits)
+    R, C = keep_mask.shape
+    if bits is None:
+        bits = torch.empty((R, C // 8), dtype=torch.uint8, device=keep_mask.device)
+    with torch.cuda.device(keep_mask.device):
+        st = load().vlmc_mask_pack(keep_mask.data_ptr(), R, C, keep_mask.stride(0), bits.data_ptr(), bits.stride(0),
+                                   _stream(keep_mask))
+    _check("vlmc_mask_pack", st)
+    return bits
+
+
+def mask_apply_packed(W, bits, keep_mask=None, zero_w=True, rows_per_seg=0, seg_stride=0):
+    """bits -> keep_mask bytes (optional) and zeroed weights (in place on W [R, C]).  bits is [R, C // 8], or, with
+    rows_per_seg > 0, a flat uint8 buffer in which the rows [g * rows_per_seg, (g + 1) * rows_per_seg) start at byte
+    g * seg_stride (the [rank][row shard] layout of one all-gather)."""
+    _require_cuda(W, bits, keep_mask)
+    R, C = W.shape
+    ldb = bits.stride(0) if bits.dim() == 2 else C // 8
+    with torch.cuda.device(W.device):
+        st = load().vlmc_mask_apply_packed(W.data_ptr(), _dtype(W), R, C, W.stride(0), bits.data_ptr(), ldb,
+                                           int(rows_per_seg), int(seg_stride), keep_mask.data_ptr() if keep_mask is not None else None,
+                                           keep_mask.stride(0) if keep_mask is not None else 0, int(zero_w), _stream(W))
+    _check("vlmc_mask_apply_packed", st)
+    return keep_mask
 
 
 def sparselora_merge(W, A, B, scaling, keep_mask, remask=True):

@@ -81,6 +81,61 @@ def prune_linear_row_sharded(weight, scaler_row, select_fn, rank, world, group=N
     return keep, mean / float(R)
 
 
+def exchange_rows_packed(weight, keep, pack_fn, apply_fn, rank, world, group=None):
+    """One linear whose row shard [row_range(R, rank, world)] of `keep` (mask bytes) and `weight` (zeroed) is final on
+    this rank: all-gather the shard masks as bits and expand / apply the other shards locally (see
+    prune_block_rows_packed).  Falls back to gathering bytes when the rows do not split evenly."""
+    R, C = weight.shape
+    if not dist.is_initialized() or world == 1:
+        return keep
+    if R % world or C % 16:
+        gather_rows(weight, rank, world, group)
+        gather_rows(keep.view(torch.uint8), rank, world, group)
+        return keep
+    s, e = row_range(R, rank, world)
+    n = (e - s) * (C // 8)
+    allbits = torch.empty(world * n, dtype=torch.uint8, device=weight.device)
+    mine = allbits[rank * n:(rank + 1) * n]
+    pack_fn(keep[s:e], mine.view(e - s, C // 8))
+    dist.all_gather_into_tensor(allbits, mine.clone(), group=group)
+    apply_fn(weight, allbits, keep, R // world, n)
+    return keep
+
+
+def prune_block_rows_packed(weights, select_fns, pack_fn, apply_fn, rank, world, group=None):
+    """Phase 2 for ALL linears of a block with ONE collective.  Every rank runs select_fns[i](W_rows, keep_rows) ->
+    score_mean on its row shard of weights[i] (mask bytes + zeroed rows, in place), packs those mask rows to bits
+    (pack_fn(keep_rows, bits_out)), all ranks all-gather the bits of all linears in one call (1 bit per weight: the
+    weights are replicated, only the decision travels) and expand them with apply_fn(W, bits, keep,
+    rows_per_seg, seg_stride), which also zeroes the pruned weights of the local replica.  Returns [(keep [R, C] bool, score_mean)].
+    Needs R % world == 0 and C % 16 == 0 for every linear (callers fall back to prune_linear_row_sharded otherwise)."""
+    dev = weights[0].device
+    shapes = [tuple(w.shape) for w in weights]
+    assert all(R % world == 0 and C % 16 == 0 for R, C in shapes)
+    sizes = [(R // world) * (C // 8) for R, C in shapes]
+    offs = [0]
+    for n in sizes:
+        offs.append(offs[-1] + n)
+    mine = torch.empty(offs[-1], dtype=torch.uint8, device=dev)
+    keeps, means = [], torch.zeros(len(weights), dtype=torch.float32, device=dev)
+    for i, (w, (R, C)) in enumerate(zip(weights, shapes)):
+        s, e = row_range(R, rank, world)
+        keep = torch.empty((R, C), dtype=torch.bool, device=dev)
+        m = select_fns[i](w[s:e], keep[s:e])
+        means[i:i + 1] = m.reshape(1) * (float(e - s) / float(R))
+        pack_fn(keep[s:e], mine[offs[i]:offs[i + 1]].view(e - s, C // 8))
+        keeps.append(keep)
+    if dist.is_initialized() and world > 1:
+        allbits = torch.empty(world * offs[-1], dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allbits, mine, group=group)
+        dist.all_reduce(means, op=dist.ReduceOp.SUM, group=group)
+        # buffer layout [rank][linear shard]: ONE expand-and-zero call per linear covers the rows of every rank
+        # (re-applying the own shard is idempotent)
+        for i, (w, (R, C)) in enumerate(zip(weights, shapes)):
+            apply_fn(w, allbits[offs[i]:], keeps[i], R // world, offs[-1])
+    return [(k, means[i:i + 1]) for i, k in enumerate(keeps)]
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # SparseGPT (SURVEY 8e): tokens sharded for H, factorisations spread over ranks, rows sharded for the OBS sweep
 # ---------------------------------------------------------------------------------------------------------------
