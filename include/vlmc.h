@@ -156,12 +156,13 @@ int vlmc_sparselora_merge(void* W, int dtype, int R, int C, int64_t ldw,
 /*
  * K3  SparseGPT Hessian accumulation.  Replaces SparseGPT.add_batch, sparsegpt_pruner.py:68-79:
  *   H <- H * n_before/(n_before+b) + (2/(n_before+b)) * X^T X
- * x: [T, C] row-major fp16 / bf16 (one add_batch call, T = b * seq_len); H: [C, C] fp32, full and symmetric.
+ * x: [T, C] row-major fp16 / bf16 / fp32 (one add_batch call, T = b * seq_len); H: [C, C] fp32, full and symmetric.
  * TMA-fed tcgen05.mma (kind::f16, fp32 accumulate in TMEM), SYRK over the upper triangle with the mirror
  * written by the epilogue.  kc = tokens accumulated inside the tensor core before the partial sum is
  * added, round-to-nearest, into fp32 registers (0 = default 512; multiples of 64).  slab_tokens = tokens per
  * launch (0 = default: 65536 for C >= 8192, else unlimited): all tiles of one slab run before the next so operand re-reads stay in L2.
- * fp32 activations (EVA-ViT qkv / fc1 inputs) need the 3xTF32 split and are not built yet: VLMC_ERR_UNSUPPORTED.
+ * fp32 activations (EVA-ViT qkv / fc1 inputs under autocast) are not exact tensor-core operands: they run as a 3xTF32
+ * split GEMM (tcgen05 kind::tf32, hi/lo split on chip, full square instead of SYRK; kc capped at 256, default 128).
  */
 int vlmc_hessian_accum(const void* x, int dtype, int64_t T, int C, int64_t ldx,
                        float* H, int64_t ldh, double n_before, double b, int kc, int64_t slab_tokens,

@@ -477,6 +477,25 @@ def test_hessian_vs_oracle(native, T, C, tag):
         assert rel_inf(got, want) < REL and _rel_fro(got, want) < REL and rel_elem(got, want, 1e-2) < REL
 
 
+@pytest.mark.parametrize("T,C", [(257, 1408), (771, 1408), (2048, 512), (100, 128), (4112, 6144)])
+def test_hessian_fp32_activations(native, T, C):
+    """fp32 activations (EVA-ViT qkv / fc1 inputs under autocast; 257 tokens per image): 3xTF32 split
+    GEMM.  Same 1e-5 bars against the reference's fp32 running average and the float64 truth."""
+    H = torch.zeros(C, C, device="cuda")
+    Ho, n = np.zeros((C, C), np.float32), 0
+    xs = []
+    for call in range(3):
+        x = acts(T, C, 17 * call + T + C, torch.float32)
+        xs.append(x.numpy())
+        native.hessian_accum(x.cuda(), H, n, 1)
+        Ho, n = oracle.sparsegpt_add_batch(Ho, n, xs[-1], 1)
+    got = H.cpu().numpy()
+    truth = oracle.hessian_truth(xs, 3)
+    assert np.abs(got - got.T).max() <= 2e-6 * np.abs(got).max()         # two tiles, two summation orders
+    for want in (truth, Ho):
+        assert rel_inf(got, want) < REL and _rel_fro(got, want) < REL and rel_elem(got, want, 1e-2) < REL
+
+
 def test_hessian_long_accumulation_chunks(native):
     """128 x 2048 tokens in ONE call: the in-TMEM chunk (kc) bounds the tensor core's round-toward-zero drift."""
     T, C = 32 * 2048, 512

@@ -113,7 +113,7 @@ __device__ __forceinline__ void g3_split(const uint4& raw, uint4& hi, uint4& lo)
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-template <int TN, bool B_MN, bool CHUNKED>
+template <int TN, bool B_MN, bool CHUNKED, bool A_MN>
 __global__ void __launch_bounds__(kG3Threads, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap, const G3Params p,
               const uint32_t idesc) {
@@ -166,7 +166,12 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ 
           uint8_t* sa = smem + stage * kStageBytes;
           uint8_t* sb = sa + 2 * kG3ABytes;
           mbar_expect_tx(&bars->full[stage], kG3ABytes + kBBytes);
-          tma_load_2d(sa, &amap, &bars->full[stage], k0, m0);
+          if (A_MN) {
+#pragma unroll
+            for (int q = 0; q < kG3M / 32; ++q) tma_load_2d(sa + q * (kG3K * 128), &amap, &bars->full[stage], m0 + q * 32, k0);
+          } else {
+            tma_load_2d(sa, &amap, &bars->full[stage], k0, m0);
+          }
           if (B_MN) {
 #pragma unroll
             for (int q = 0; q < TN / 32; ++q) tma_load_2d(sb + q * (kG3K * 128), &bmap, &bars->full[stage], n0 + q * 32, k0);
@@ -200,8 +205,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ 
             const uint32_t sb = sa + 2 * kG3ABytes;
 #pragma unroll
             for (int kk = 0; kk < kG3K / 8; ++kk) {
-              const uint64_t a_hi = g3_desc_k(sa + kk * 32);
-              const uint64_t a_lo = g3_desc_k(sa + kG3ABytes + kk * 32);
+              const uint64_t a_hi = A_MN ? g3_desc_mn(sa + kk * 1024) : g3_desc_k(sa + kk * 32);
+              const uint64_t a_lo = A_MN ? g3_desc_mn(sa + kG3ABytes + kk * 1024) : g3_desc_k(sa + kG3ABytes + kk * 32);
               const uint64_t b_hi = B_MN ? g3_desc_mn(sb + kk * 1024) : g3_desc_k(sb + kk * 32);
               const uint64_t b_lo = B_MN ? g3_desc_mn(sb + kBBytes + kk * 1024) : g3_desc_k(sb + kBBytes + kk * 32);
               tc_mma_tf32(d_tmem, a_lo, b_hi, idesc, accumulate);    // small terms first
@@ -370,9 +375,9 @@ template <int TN> constexpr size_t g3_smem() {
   return G3Cfg<TN>::kStages * G3Cfg<TN>::kStageBytes + kG3EpiWarps * 4096 + sizeof(G3Barriers) + 1024;
 }
 
-template <int TN, bool B_MN, bool CHUNKED>
+template <int TN, bool B_MN, bool CHUNKED, bool A_MN = false>
 static int g3_launch(const CUtensorMap& amap, const CUtensorMap& bmap, G3Params p, cudaStream_t st) {
-  auto kern = gemm3x_kernel<TN, B_MN, CHUNKED>;
+  auto kern = gemm3x_kernel<TN, B_MN, CHUNKED, A_MN>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g3_smem<TN>()) != cudaSuccess)
@@ -391,7 +396,7 @@ static int g3_launch(const CUtensorMap& amap, const CUtensorMap& bmap, G3Params 
     p.ntiles = p.nbi * p.nbj;
   }
   // fp32 accumulate, A and B TF32, A K-major, B K-major or MN-major, N = TN, M = 128 (cute::UMMA::InstrDescriptor)
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                          ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(kG3M >> 4) << 24);
   const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
   kern<<<grid, kG3Threads, g3_smem<TN>(), st>>>(amap, bmap, p, idesc);
@@ -414,20 +419,23 @@ static int g3_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t 
 }
 
 int gemm3x(bool b_nk, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb,
-           float beta, float* C, int64_t ldc, int tri, int kc, cudaStream_t st, int kmode) {
+           float beta, float* C, int64_t ldc, int tri, int kc, cudaStream_t st, int kmode, bool a_km) {
   if (M <= 0 || N <= 0) return VLMC_OK;
   if (K <= 0 || !A || !B || !C) return VLMC_ERR_BAD_ARG;
-  if ((K & 3) || (N & 3) || (lda & 3) || (ldb & 3) || (ldc & 3) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15) ||
+  // K is the contiguous dimension of a K-major operand only: [K,M] / [K,N] operands take any K
+  if (a_km && (b_nk || kmode != 0 || (M & 3))) return VLMC_ERR_UNSUPPORTED;
+  if ((!(a_km && !b_nk) && (K & 3)) || (N & 3) || (lda & 3) || (ldb & 3) || (ldc & 3) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15) ||
       ((uintptr_t)C & 15))
     return VLMC_ERR_UNSUPPORTED;
   if (kc <= 0) kc = 128;
   if (kmode < 0 || kmode > 2 || (kmode == 1 && b_nk)) return VLMC_ERR_BAD_ARG;
   kc = (kc + kG3K - 1) / kG3K * kG3K;
   const bool chunked = K > kc;
-  const int TN = (!chunked && N > 128) ? 256 : 128;
+  const int TN = (!chunked && N > 128 && !a_km) ? 256 : 128;
 
   CUtensorMap amap, bmap;
-  int rc = g3_map(&amap, A, (uint64_t)K, (uint64_t)M, lda, kG3K, kG3M, CU_TENSOR_MAP_SWIZZLE_128B);
+  int rc = a_km ? g3_map(&amap, A, (uint64_t)M, (uint64_t)K, lda, 32, kG3K, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                : g3_map(&amap, A, (uint64_t)K, (uint64_t)M, lda, kG3K, kG3M, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   if (b_nk) rc = g3_map(&bmap, B, (uint64_t)K, (uint64_t)N, ldb, kG3K, (uint32_t)TN, CU_TENSOR_MAP_SWIZZLE_128B);
   else rc = g3_map(&bmap, B, (uint64_t)N, (uint64_t)K, ldb, 32, kG3K, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
@@ -436,6 +444,10 @@ int gemm3x(bool b_nk, int M, int N, int K, float alpha, const float* A, int64_t 
   G3Params p;
   p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.alpha = alpha; p.beta = beta; p.tri = tri; p.kc = kc; p.kmode = kmode;
   p.nbi = p.nbj = p.ntiles = 0;
+  if (a_km) {   // A given as [K,M] (A^T B products: the fp32-activation Hessian X^T X)
+    if (chunked) return g3_launch<128, true, true, true>(amap, bmap, p, st);
+    return g3_launch<128, true, false, true>(amap, bmap, p, st);
+  }
   if (chunked) return b_nk ? g3_launch<128, false, true>(amap, bmap, p, st) : g3_launch<128, true, true>(amap, bmap, p, st);
   if (TN == 256) return b_nk ? g3_launch<256, false, false>(amap, bmap, p, st) : g3_launch<256, true, false>(amap, bmap, p, st);
   return b_nk ? g3_launch<128, false, false>(amap, bmap, p, st) : g3_launch<128, true, false>(amap, bmap, p, st);
@@ -449,5 +461,5 @@ extern "C" int vlmc_gemm_tf32x3(int b_nk, int M, int N, int K, float alpha, cons
   using namespace vlmc;
   if (!A || !B || !C || M < 1 || N < 1 || K < 1 || lda < K || ldc < N || ldb < (b_nk ? K : N)) return VLMC_ERR_BAD_ARG;
   if (!is_device_ptr(A) || !is_device_ptr(B) || !is_device_ptr(C)) return VLMC_ERR_NOT_DEVICE;
-  return gemm3x(b_nk != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kc, (cudaStream_t)stream, 0);
+  return gemm3x(b_nk != 0, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, tri, kc, (cudaStream_t)stream, 0, false);
 }

@@ -22,6 +22,7 @@
 //   warp 2      TMEM allocator   512 columns = 2 accumulator buffers (chunk n+1 overlaps the drain of chunk n)
 //   warps 4-11  epilogue         tcgen05.ld -> fp32 register accumulators -> fused H update (+ mirror)
 #include "tc.cuh"
+#include "gemm3x.cuh"
 
 namespace vlmc {
 
@@ -235,7 +236,19 @@ extern "C" int vlmc_hessian_accum(const void* x, int dtype, int64_t T, int C, in
                                   void* stream) {
   using namespace vlmc;
   if (!x || !H || T < 1 || C < 1 || ldx < C || ldh < C || b <= 0) return VLMC_ERR_BAD_ARG;
-  if (dtype != VLMC_F16 && dtype != VLMC_BF16) return VLMC_ERR_UNSUPPORTED;   // fp32 activations: see DESIGN.md
+  if (dtype == VLMC_F32) {
+    // fp32 activations (EVA-ViT qkv / fc1 inputs): fp32 values are not exact tensor-core operands, so the
+    // contraction runs as the 3xTF32 split GEMM  H = ratio * H + scale * X^T X  (gemm3x.cu, A and B both = X, [K,M] / [K,N]).
+    if (C % 4 != 0 || ldx % 4 != 0 || ldh % 4 != 0 || ((uintptr_t)x & 15) != 0 || ((uintptr_t)H & 15) != 0)
+      return VLMC_ERR_UNSUPPORTED;
+    if (T > 0x7fffffff) return VLMC_ERR_UNSUPPORTED;
+    if (!is_device_ptr(x) || !is_device_ptr(H)) return VLMC_ERR_NOT_DEVICE;
+    const double n_after32 = n_before + b;
+    const float* xf = reinterpret_cast<const float*>(x);
+    return gemm3x(false, C, C, (int)T, (float)(2.0 / n_after32), xf, ldx, xf, ldx, (float)(n_before / n_after32), H, ldh, 0,
+                  kc > 0 ? (kc < 256 ? kc : 256) : 128, (cudaStream_t)stream, 0, true);
+  }
+  if (dtype != VLMC_F16 && dtype != VLMC_BF16) return VLMC_ERR_BAD_ARG;
   if (C % 8 != 0 || ldx % 8 != 0 || ldh % 4 != 0 || ((uintptr_t)x & 15) != 0 || ((uintptr_t)H & 15) != 0)
     return VLMC_ERR_UNSUPPORTED;
   if (T > 0x7fffffff) return VLMC_ERR_UNSUPPORTED;
