@@ -467,6 +467,8 @@ def run_gpu(args):
                                   "roofline": roofline_of(r, pk)} for m, r in others.items()}
         if "cuda_graph_error" in main:
             out["config"]["cuda_graph_error"] = main["cuda_graph_error"]
+        if world == 1 and args.all_methods and args.method == "wanda_nm":
+            out["workloads"] = {"config2_instructblip_flant5xl_wanda_2of4": full_model_wanda_nm(torch, native, dev)}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.method)
         print(json.dumps(out), flush=True)
@@ -616,6 +618,65 @@ def run_e2e_sharded(torch, native, parallel, dev, args, rank, world, host_in, ho
     torch.cuda.synchronize()
     wall = (time.perf_counter() - wall0) * 1e3
     return {"ms": max(t0.elapsed_time(t1), wall) / k, "h2d": h2d, "d2h": d2h, "steps": k}
+
+
+# ------------------------------------------------------------------------------------------------ config 2
+# BASELINE.json configs[1]: Wanda 2:4 on the full InstructBLIP-FlanT5-XL (EVA ViT-g + FlanT5-XL), 1 B200, SURVEY 8(d).
+VIT_BLOCK = [("qkv", 4224, 1408, "f32"), ("proj", 1408, 1408, "f16"), ("fc1", 6144, 1408, "f32"), ("fc2", 1408, 6144, "f16")]
+T5_ENC = [(n, 2048, 2048, "bf16") for n in ("q", "k", "v", "o")] + [("wi_0", 5120, 2048, "bf16"), ("wi_1", 5120, 2048, "bf16"),
+                                                                   ("wo", 2048, 5120, "bf16")]
+T5_DEC = [(f"{a}.{n}", 2048, 2048, "bf16") for a in ("self", "cross") for n in ("q", "k", "v", "o")] + T5_ENC[4:]
+FULL_MODEL = [("eva_vit_g", VIT_BLOCK, 39, 257, "f16"), ("t5_encoder", T5_ENC, 24, 512, "bf16"),
+              ("t5_decoder", T5_DEC, 24, 512, "bf16")]
+
+
+def full_model_wanda_nm(torch, native, dev, reps=2):
+    """Every linear of every block: WrappedGPT statistics over its 128-sequence calibration input, then 2:4 selection.
+    Inputs rotate through buffers larger than L2; ViT qkv / fc1 inputs are fp32 (nn.LayerNorm under autocast), the
+    rest half precision.  Returns seconds per model and the bytes streamed."""
+    dt = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}
+    g = torch.Generator(device=dev).manual_seed(7)
+    plan, total_bytes, total_weights = [], 0, 0
+    for name, linears, nblocks, seq, wtag in FULL_MODEL:
+        T = N_SEQ * seq
+        acts, wts = {}, []
+        for _, R, C, xtag in linears:
+            key = (C, xtag)
+            if key not in acts:        # 3 rotating copies, each >= 93 MB: consecutive uses never hit in L2
+                acts[key] = [torch.randn(T, C, device=dev, generator=g, dtype=torch.float32).to(dt[xtag]) for _ in range(3)]
+        for _ in range(4):             # 4 rotating weight sets per block type
+            wts.append([(torch.randn(R, C, device=dev, generator=g) * 0.02).to(dt[wtag]) for _, R, C, _ in linears])
+        plan.append((linears, nblocks, acts, wts, T))
+        for _, R, C, xtag in linears:
+            total_bytes += nblocks * (T * C * (4 if xtag == "f32" else 2) + R * C * 5)
+            total_weights += nblocks * R * C
+
+    def one_model():
+        use = 0
+        for linears, nblocks, acts, wts, T in plan:
+            for b in range(nblocks):
+                W = wts[b % len(wts)]
+                for i, (_, R, C, xtag) in enumerate(linears):
+                    x = acts[(C, xtag)][use % 3]
+                    use += 1
+                    s = torch.zeros(C, device=dev, dtype=torch.float32)
+                    native.sqnorm_accum(x.view(N_SEQ, -1, C), s, 0, N_SEQ)
+                    native.wanda_nm(W[i], s, 2, 4)
+    one_model()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        one_model()
+    b.record()
+    torch.cuda.synchronize()
+    sec = a.elapsed_time(b) / reps / 1e3
+    del plan
+    torch.cuda.empty_cache()
+    return {"value": sec, "unit": "s/model", "workload": "Wanda 2:4 on full InstructBLIP-FlanT5-XL: 39 EVA ViT-g blocks (fp16, "
+            "128x257 tokens, fp32 qkv/fc1 inputs) + 24 + 24 FlanT5-XL blocks (bf16, 128x512 tokens), random init",
+            "linears": sum(len(l) * n for _, l, n, _, _ in FULL_MODEL), "weights": total_weights,
+            "algorithmic_bytes": total_bytes, "achieved_gbs": total_bytes / sec / 1e9, "reps": reps}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm

@@ -35,7 +35,7 @@ extern "C" size_t vlmc_workspace_bytes(int op, int64_t d0, int64_t d1, int64_t d
     case VLMC_OP_WANDA_SELECT: {
       // row sums (rowselect) or per-CTA partial sums (n:m, threshold): R floats bound both
       size_t parts = (size_t)(d0 > kNumSMs * 32 ? d0 : kNumSMs * 32);
-      size_t a = VLMC_WS_COUNTER_BYTES + parts * sizeof(float) + 4096;
+      size_t a = VLMC_WS_COUNTER_BYTES + (parts + (size_t)d1) * sizeof(float) + 4096;   // + sqrt(scaler_row) [C]
       size_t b = threshold_workspace_bytes((int)d0, (int)d1);
       return a > b ? a : b;
     }

@@ -7,57 +7,21 @@
 //   n:m: python loop over C/m groups of torch.topk          (:323-329)   -> nm_kernel
 //   module.mask = ~W_mask ; W[W_mask] = 0                  (:339-341)
 //
-// rowselect: one CTA (128 threads) owns a row; the fp32 score bits live in REGISTERS
-// (non-negative floats order like their uint32 bit patterns).  The k-th smallest
-// (score, column) pair is found by counting passes: 4 pivots per pass, counts packed in
-// 16-bit lanes and reduced with redux.sync + one __syncthreads.  The first pass of a row
-// is seeded from the previous row's threshold rescaled by the row mean, so iid rows
-// converge in 1-2 passes; the bracket is closed exactly by ranking the <=128 remaining
-// candidates on (score, column), which also gives the stable-sort tie-break.
+// rowselect: one WARP streams a row; only a short candidate list is kept on chip (see the kernel).
 // HBM-bound: 5 B/weight for fp16/bf16 (read W, write W, write mask).
+#include <type_traits>
 #include "common.cuh"
 
 namespace vlmc {
 
-constexpr int kSelThreads = 128;
+constexpr int kSelThreads = 128;          // n:m kernel
 constexpr int kSelWarps = kSelThreads / 32;
-constexpr int kCap = 128;  // candidates ranked exhaustively
+constexpr int kRsWarps = 4;               // rowselect: rows in flight per CTA (one per warp)
+constexpr int kRsList = 24;               // per-lane candidate list capacity
+constexpr int kRsCap = 32;                // candidates ranked exhaustively: one per lane
 
 __device__ __forceinline__ uint32_t redux_add(uint32_t v) {
   return __reduce_add_sync(0xffffffffu, v);
-}
-
-struct SelShared {
-  uint32_t red[2][kSelWarps][2];
-  float fred[kSelWarps];
-  uint32_t cand_key[kCap];
-  int cand_idx[kCap];
-  int cand_cnt;
-  uint32_t v;
-  int iv;
-};
-
-// counts of keys < p[0..3] over the whole CTA; every thread gets all four
-template <int KPT>
-__device__ __forceinline__ void count4(const uint32_t (&keys)[KPT], const uint32_t (&p)[4],
-                                       int (&c)[4], SelShared& sh, int& parity) {
-  uint32_t a = 0, b = 0;
-#pragma unroll
-  for (int i = 0; i < KPT; ++i) {
-    const uint32_t key = keys[i];
-    a += (key < p[0] ? 1u : 0u) + (key < p[1] ? 0x10000u : 0u);
-    b += (key < p[2] ? 1u : 0u) + (key < p[3] ? 0x10000u : 0u);
-  }
-  a = redux_add(a);
-  b = redux_add(b);
-  const int warp = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { sh.red[parity][warp][0] = a; sh.red[parity][warp][1] = b; }
-  __syncthreads();
-  a = 0; b = 0;
-#pragma unroll
-  for (int w = 0; w < kSelWarps; ++w) { a += sh.red[parity][w][0]; b += sh.red[parity][w][1]; }
-  parity ^= 1;
-  c[0] = a & 0xffff; c[1] = a >> 16; c[2] = b & 0xffff; c[3] = b >> 16;
 }
 
 __device__ __forceinline__ uint32_t clampu(double x, uint32_t lo, uint32_t hi) {
@@ -67,181 +31,417 @@ __device__ __forceinline__ uint32_t clampu(double x, uint32_t lo, uint32_t hi) {
   return (uint32_t)x;
 }
 
-template <typename T, int KPT>
-__global__ void __launch_bounds__(kSelThreads)
-rowselect_kernel(T* __restrict__ W, int64_t ldw, int R, int C,
-                 const float* __restrict__ scaler_row, int k, int zero_w,
-                 uint8_t* __restrict__ mask, int64_t ldm, float* __restrict__ row_sum) {
+// prmt.b32 in its default mode: selector nibble bit 3 replicates the sign bit of the selected byte over the whole byte
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+__global__ void sqrt_vec_kernel(const float* __restrict__ s, float* __restrict__ out, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) out[i] = __fsqrt_rn(s[i]);
+}
+
+// Next four pivots inside the bracket (lo, hi) that holds the k-th smallest key (m keys in it, glo below it).
+__device__ __forceinline__ void rs_pivots(uint32_t lo, uint32_t hi, int glo, int m, int k, int C, bool uniform,
+                                          uint32_t (&p)[4]) {
+  const uint32_t w = hi - lo;
+  if (uniform || (m > C / 2 && w > (1u << 26))) {
+    // uniform 5-way split of the bit range: shrinks it 5x per pass whatever the distribution
+    const double q = (double)w * 0.2;
+    p[0] = clampu(lo + q, lo, hi);       p[1] = clampu(lo + 2.0 * q, lo, hi);
+    p[2] = clampu(lo + 3.0 * q, lo, hi); p[3] = clampu(lo + 4.0 * q, lo, hi);
+  } else {
+    // interpolate inside the bracket; inner pivots ~ +-8 keys, outer ~ +-64 keys at uniform density
+    const double f = ((double)(k - glo) - 0.5) / (double)m;
+    const double e = (double)lo + f * (double)w;
+    double d1 = (double)w * (8.0 / (double)m), d2 = (double)w * (64.0 / (double)m);
+    if (d2 > (double)w * 0.25) d2 = (double)w * 0.25;
+    if (d1 > d2 * 0.25) d1 = d2 * 0.25;
+    p[0] = clampu(e - d2, lo, hi); p[1] = clampu(e - d1, lo, hi);
+    p[2] = clampu(e + d1, lo, hi); p[3] = clampu(e + d2, lo, hi);
+  }
+}
+
+__device__ __forceinline__ void rs_update(const uint32_t (&p)[4], const int (&c)[4], int k, uint32_t& lo, uint32_t& hi,
+                                          int& glo, int& ghi) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (c[i] <= k - 1) { if (p[i] > lo) { lo = p[i]; glo = c[i]; } }
+    else               { if (p[i] < hi) { hi = p[i]; ghi = c[i]; } }
+  }
+}
+
+// One warp: estimate the per-row threshold from a sample of 32 weight vectors spread over the matrix (row and column
+// strided): the k/C quantile of the sample's scores by bit-space bisection.  Seeds the first row of every warp of
+// rowselect_kernel; a miss only costs that row an extra pass.
+template <typename T>
+__global__ void __launch_bounds__(32)
+rowselect_seed_kernel(const T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ sq, int k,
+                      uint32_t* __restrict__ seed) {
   constexpr int V = Elem<T>::kVec;
-  constexpr int NV = KPT / V;
-  extern __shared__ float sq[];  // sqrt(scaler_row), [C]
-  __shared__ SelShared sh;
-
-  for (int c = threadIdx.x; c < C; c += kSelThreads) sq[c] = __fsqrt_rn(scaler_row[c]);
-  __syncthreads();
-
-  int parity = 0;
-  float hint_ratio = -1.f;  // previous threshold / previous row mean
-
-  for (int row = blockIdx.x; row < R; row += gridDim.x) {
-    T* wrow = W + (int64_t)row * ldw;
-    uint32_t keys[KPT];
-    float lsum = 0.f;
+  const int lane = threadIdx.x;
+  const int nvec = C / V;
+  const int vi = (int)(((int64_t)lane * nvec) / 32) % (nvec > 0 ? nvec : 1);
+  const int row = (int)(((int64_t)lane * R) / 32);
+  float f[V];
+  Elem<T>::unpack(*reinterpret_cast<const uint4*>(W + (int64_t)row * ldw + vi * V), f);
+  uint32_t sk[V];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int col = (j * kSelThreads + threadIdx.x) * V;
-      if (col < C) {
-        uint4 v = ld_stream(wrow + col);
-        float f[V];
-        Elem<T>::unpack(v, f);
+  for (int e = 0; e < V; ++e) sk[e] = __float_as_uint(__fmul_rn(fabsf(f[e]), sq[vi * V + e]));
+  const int ns = 32 * V;
+  int ks = (int)(((int64_t)k * ns + C / 2) / C);
+  if (ks < 1) ks = 1;
+  if (ks > ns) ks = ns;
+  uint32_t slo = 0u, shi = 0x7f800000u;
+  while (shi - slo > 65536u) {
+    const double q = (double)(shi - slo) * 0.2;
+    const uint32_t sp[4] = {clampu(slo + q, slo, shi), clampu(slo + 2.0 * q, slo, shi), clampu(slo + 3.0 * q, slo, shi),
+                            clampu(slo + 4.0 * q, slo, shi)};
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-          const float s = __fmul_rn(fabsf(f[e]), sq[col + e]);
-          keys[j * V + e] = __float_as_uint(s);
-          lsum += s;
-        }
-      } else {
+    for (int e = 0; e < V; ++e) {
+      c0 += sk[e] < sp[0] ? 1u : 0u; c1 += sk[e] < sp[1] ? 1u : 0u;
+      c2 += sk[e] < sp[2] ? 1u : 0u; c3 += sk[e] < sp[3] ? 1u : 0u;
+    }
+    const int sc[4] = {(int)redux_add(c0), (int)redux_add(c1), (int)redux_add(c2), (int)redux_add(c3)};
 #pragma unroll
-        for (int e = 0; e < V; ++e) keys[j * V + e] = 0xffffffffu;
+    for (int i = 0; i < 4; ++i) {
+      if (sc[i] <= ks - 1) { if (sp[i] > slo) slo = sp[i]; }
+      else                 { if (sp[i] < shi) shi = sp[i]; }
+    }
+  }
+  if (lane == 0) *seed = slo + ((shi - slo) >> 1);
+}
+
+// rowselect: ONE WARP owns a row and STREAMS it; nothing of the row is kept on chip except a short candidate list.
+//   pass 1  (HBM)  score every weight (fp32 score bits: non-negative floats order like their uint32 patterns), count the
+//                  scores below four pivots seeded from the previous row's threshold, and append the scores that fall
+//                  between the outer pivots (~10 % of the row) to per-lane lists in shared memory
+//   narrow         counting passes over the lists only (a dozen keys per lane) until <= 32 candidates remain, which are
+//                  ranked exactly on (score, column): the stable-sort tie-break of torch.sort(stable=True)
+//   apply   (L2)   re-stream the row, recompute the scores, write the mask bytes and the zeroed weights
+// If the seeded bracket misses (first row of a warp, outlier rows) or a lane's list overflows, pass 1 is repeated from
+// L2 with pivots chosen inside the shrinking bracket.  No CTA barrier, ~6 KB of shared memory per warp: 32 warps per
+// SM hide each other's load and reduction latencies.  HBM traffic: 5 B/weight for fp16/bf16.
+template <typename T>
+__global__ void __launch_bounds__(kRsWarps * 32, 4)
+rowselect_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ sq, int k, int zero_w,
+                 uint8_t* __restrict__ mask, int64_t ldm, float* __restrict__ row_sum, const uint32_t* __restrict__ seed) {
+  constexpr int V = Elem<T>::kVec;     // weights per 16-byte vector
+  __shared__ uint2 lists[kRsWarps][kRsList][32];     // (score bits, column)
+  __shared__ uint2 cand[kRsWarps][kRsCap];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint2 (*mylist)[32] = lists[warp];
+  uint2* mycand = cand[warp];
+  const int nvec = C / V;              // 16-byte vectors per row
+  uint32_t prev_v = seed ? *seed : 0u; // previous row's threshold; a warp's first row starts from the sample estimate
+  bool from_sample = true;
+  float rd = 786432.f * sqrtf(4096.f / (float)C);
+  rd = rd < 200000.f ? 200000.f : (rd > 1400000.f ? 1400000.f : rd);
+  const uint32_t row_dlt = (uint32_t)rd;
+
+  // score bits of the V weights of vector `vi`
+  auto score = [&](const uint4& wv, int col, uint32_t (&key)[V], float& lsum) {
+    float f[V];
+    Elem<T>::unpack(wv, f);
+#pragma unroll
+    for (int q = 0; q < V / 4; ++q) {
+      const float4 sv = __ldg(reinterpret_cast<const float4*>(sq + col) + q);
+      const float se[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float sc = __fmul_rn(fabsf(f[q * 4 + e]), se[e]);
+        key[q * 4 + e] = __float_as_uint(sc);
+        lsum += sc;
       }
     }
-    // row sum (importance score + pivot hint)
-    lsum = warp_sum(lsum);
-    if ((threadIdx.x & 31) == 0) sh.fred[threadIdx.x >> 5] = lsum;
-    if (threadIdx.x == 0) sh.cand_cnt = 0;
-    __syncthreads();
-    float rsum = 0.f;
-#pragma unroll
-    for (int w = 0; w < kSelWarps; ++w) rsum += sh.fred[w];
-    if (threadIdx.x == 0 && row_sum) row_sum[row] = rsum;
-    const float rmean = rsum / (float)C;
+  };
 
+  for (int row = blockIdx.x * kRsWarps + warp; row < R; row += gridDim.x * kRsWarps) {
+    T* wrow = W + (int64_t)row * ldw;
     uint32_t v = 0;
     int iv = -1;  // prune (key < v) || (key == v && col <= iv)
-    if (k >= C) {
-      v = 0xffffffffu; iv = 0x7fffffff;
-    } else if (k > 0) {
+    bool need_sum = true;
+    bool ties_all_pruned = false;   // every key equal to v has col <= iv: enables the one-compare apply
+
+    // one streaming pass: counts of keys < p[0..3] -> c, keys in [cl, ch) -> lists; returns false on list overflow.
+    // two == true: only the outer pivots p[0], p[3] are counted (the seeded pass: [cl, ch) = [p[0], p[3]))
+    auto stream = [&](auto two_tag, const uint32_t (&p)[4], uint32_t cl, uint32_t ch, int (&c)[4], int& lcount) -> bool {
+      constexpr bool kTwo = decltype(two_tag)::value;
+      uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+      float lsum = 0.f;
+      lcount = 0;
+      for (int j0 = lane; j0 < nvec; j0 += 128) {
+        uint4 wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j0 + u * 32 < nvec) wv[u] = need_sum ? ld_stream(wrow + (j0 + u * 32) * V)
+                                                   : *reinterpret_cast<const uint4*>(wrow + (j0 + u * 32) * V);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int col = (j0 + u * 32) * V;
+          if (j0 + u * 32 < nvec) {
+            uint32_t key[V];
+            score(wv[u], col, key, lsum);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+              const bool l0 = key[e] < p[0], l3 = key[e] < p[3];
+              c0 += l0 ? 1u : 0u; c3 += l3 ? 1u : 0u;
+              if (!kTwo) { c1 += key[e] < p[1] ? 1u : 0u; c2 += key[e] < p[2] ? 1u : 0u; }
+              const bool in = kTwo ? (!l0 && l3) : (key[e] >= cl && key[e] < ch);
+              if (in) {
+                if (lcount < kRsList) mylist[lcount][lane] = make_uint2(key[e], (uint32_t)(col + e));
+                ++lcount;
+              }
+            }
+          }
+        }
+      }
+      c[0] = (int)redux_add(c0); c[3] = (int)redux_add(c3);
+      if (kTwo) { c[1] = c[0]; c[2] = c[3]; }
+      else { c[1] = (int)redux_add(c1); c[2] = (int)redux_add(c2); }
+      if (need_sum) {
+        const float rsum = warp_sum(lsum);
+        if (lane == 0 && row_sum) row_sum[row] = rsum;
+        need_sum = false;
+      }
+      return __ballot_sync(0xffffffffu, lcount > kRsList) == 0u;
+    };
+    using Two = std::integral_constant<bool, true>;
+    using Four = std::integral_constant<bool, false>;
+
+    if (k >= C || k <= 0) {
+      if (k >= C) { v = 0xffffffffu; iv = 0x7fffffff; }
+      if (row_sum) {   // the importance score still needs the row sum
+        const uint32_t p[4] = {1u, 2u, 3u, 4u};
+        int c[4], lc;
+        stream(Four{}, p, 0u, 0u, c, lc);
+      }
+    } else {
       uint32_t lo = 0, hi = 0xffffffffu;
-      int glo = 0, ghi = C;
-      bool first = true;
-      while (true) {
-        const int m = ghi - glo;
-        if (m <= kCap || hi - lo == 1u) break;
-        const uint32_t w = hi - lo;
+      int glo = 0, ghi = C;      // count(key < lo) = glo <= k - 1 < ghi = count(key < hi)
+      uint32_t cl = 0, ch = 0;   // keys in [cl, ch) are on the lists, cb = count(key < cl)
+      int cb = 0, lcount = 0;
+      bool have = false, uniform = false, first = true, seeded = false, wide = false;
+      int missed = 0;            // after a seeded pass: +1 threshold above the bracket, -1 below
+      uint32_t seed_dlt = 0u;
+      while (hi - lo > 1u) {
         uint32_t p[4];
-        const float hv = hint_ratio * rmean;
-        if (first && hint_ratio > 0.f && hv > 0.f && hv < 3.0e38f) {
-          const double e = (double)__float_as_uint(hv);
-          p[0] = clampu(e - 524288.0, lo, hi); p[1] = clampu(e - 65536.0, lo, hi);
-          p[2] = clampu(e + 65536.0, lo, hi);  p[3] = clampu(e + 524288.0, lo, hi);
-        } else if (m > C / 2 && w > (1u << 26)) {
-          const double q = (double)w * 0.2;
-          p[0] = clampu(lo + q, lo, hi);       p[1] = clampu(lo + 2.0 * q, lo, hi);
-          p[2] = clampu(lo + 3.0 * q, lo, hi); p[3] = clampu(lo + 4.0 * q, lo, hi);
+        const int m = ghi - glo;
+        if (first && prev_v > 4194304u && prev_v < 0x7f000000u) {
+          // two pivots around the seed, everything between them collected: +-6.7 % around the previous row's
+          // threshold, +-12 % around the matrix-wide sample estimate for a warp's first row
+          // (the row-to-row spread of the threshold and the room on the lists both shrink with sqrt(C))
+          const uint32_t dlt = from_sample ? 1400000u : row_dlt;
+          seed_dlt = dlt;
+          p[0] = prev_v - dlt; p[1] = p[0]; p[3] = prev_v + dlt; p[2] = p[3];
+          seeded = true;
+          if (from_sample && C > 6144) {   // too many keys in a +-12 % band for the lists: count only, collect next pass
+            p[1] = prev_v - 350000u; p[2] = prev_v + 350000u;
+            cl = 0u; ch = 0u;
+            seeded = false;
+            wide = true;
+          } else {
+            cl = p[0]; ch = p[3];
+          }
+        } else if (missed != 0 && m > 8 * 32) {
+          // the seeded bracket missed: exponential search away from the seed on the side the threshold lies (one
+          // pass instead of a ~6-pass uniform search of the whole bit range)
+          const double d = (double)seed_dlt;
+          const double e = (double)prev_v;
+          if (missed > 0) {
+            p[0] = clampu(e + 2.5 * d, lo, hi); p[1] = clampu(e + 6.0 * d, lo, hi);
+            p[2] = clampu(e + 15.0 * d, lo, hi); p[3] = clampu(e + 40.0 * d, lo, hi);
+          } else {
+            p[3] = clampu(e - 2.5 * d, lo, hi); p[2] = clampu(e - 6.0 * d, lo, hi);
+            p[1] = clampu(e - 15.0 * d, lo, hi); p[0] = clampu(e - 40.0 * d, lo, hi);
+          }
+          cl = 0u; ch = 0u;
+          missed = 0;
         } else {
-          const double f = ((double)(k - glo) - 0.5) / (double)m;
-          const double e = (double)lo + f * (double)w;
-          const double d1 = (double)w * (1.0 / 64.0), d2 = (double)w * 0.125;
-          p[0] = clampu(e - d2, lo, hi); p[1] = clampu(e - d1, lo, hi);
-          p[2] = clampu(e + d1, lo, hi); p[3] = clampu(e + d2, lo, hi);
+          rs_pivots(lo, hi, glo, m, k, C, uniform, p);
+          if (m <= 8 * 32) { cl = lo; ch = hi; }     // the whole bracket fits the lists
+          else { cl = p[0]; ch = p[3]; }
         }
         first = false;
         int c[4];
-        count4<KPT>(keys, p, c, sh, parity);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (c[i] <= k - 1) { if (p[i] > lo) { lo = p[i]; glo = c[i]; } }
-          else               { if (p[i] < hi) { hi = p[i]; ghi = c[i]; } }
-        }
+        const bool fits = seeded ? stream(Two{}, p, cl, ch, c, lcount) : stream(Four{}, p, cl, ch, c, lcount);
+        if (seeded || wide) missed = (k - 1 >= c[3]) ? 1 : ((c[0] > k - 1) ? -1 : 0);
+        seeded = false;
+        wide = false;
+        const bool whole = cl == lo && ch == hi;
+        const int below = whole ? glo : c[0];
+        const bool inside = whole || (ch != 0u && c[0] <= k - 1 && k - 1 < c[3]);
+        rs_update(p, c, k, lo, hi, glo, ghi);
+        if (fits && inside) { have = true; cb = below; break; }
+        uniform = !uniform && (ghi - glo) * 4 > m;   // interpolation stalled (skewed keys): one uniform pass next
       }
-      const int m = ghi - glo;
-      if (m <= kCap) {
-        // gather the candidates lo <= key < hi and rank them on (key, column)
-#pragma unroll
-        for (int i = 0; i < KPT; ++i) {
-          const uint32_t key = keys[i];
-          if (key >= lo && key < hi) {
-            const int slot = atomicAdd(&sh.cand_cnt, 1);
-            sh.cand_key[slot] = key;
-            sh.cand_idx[slot] = ((i / V) * kSelThreads + threadIdx.x) * V + (i % V);
+      __syncwarp();
+      if (have) {
+        // ---- narrow on the lists: entries are (key, col) with key in [cl, ch); the bracket (lo, hi) is inside it
+        const int ln = lcount;
+        uniform = false;
+        while (ghi - glo > kRsCap && hi - lo > 1u) {
+          const int m = ghi - glo;
+          uint32_t p[4];
+          rs_pivots(lo, hi, glo, m, k, C, uniform, p);
+          uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+          for (int i = 0; i < ln; ++i) {
+            const uint32_t key = mylist[i][lane].x;
+            c0 += key < p[0] ? 1u : 0u; c1 += key < p[1] ? 1u : 0u;
+            c2 += key < p[2] ? 1u : 0u; c3 += key < p[3] ? 1u : 0u;
           }
+          const int c[4] = {cb + (int)redux_add(c0), cb + (int)redux_add(c1), cb + (int)redux_add(c2), cb + (int)redux_add(c3)};
+          rs_update(p, c, k, lo, hi, glo, ghi);
+          uniform = !uniform && (ghi - glo) * 4 > m;
         }
-        __syncthreads();
-        if (threadIdx.x < m) {
-          const uint32_t kt = sh.cand_key[threadIdx.x];
-          const int it = sh.cand_idx[threadIdx.x];
-          int rank = 0;
-          for (int j = 0; j < m; ++j) {
-            const uint32_t kj = sh.cand_key[j];
-            rank += (kj < kt || (kj == kt && sh.cand_idx[j] < it)) ? 1 : 0;
+        const int m = ghi - glo;
+        if (m <= kRsCap) {
+          // compact the survivors lo <= key < hi and rank them on (key, column), one per lane
+          int base = 0;
+          const int lmax = __reduce_max_sync(0xffffffffu, ln);
+          for (int i = 0; i < lmax; ++i) {
+            const uint2 ent = i < ln ? mylist[i][lane] : make_uint2(0xffffffffu, 0u);
+            const bool in = ent.x >= lo && ent.x < hi;
+            const uint32_t bal = __ballot_sync(0xffffffffu, in);
+            if (in) mycand[base + __popc(bal & ((1u << lane) - 1u))] = ent;
+            base += __popc(bal);
           }
-          if (rank == k - 1 - glo) { sh.v = kt; sh.iv = it; }
+          __syncwarp();
+          bool hit = false;
+          uint2 mine = make_uint2(0u, 0u);
+          if (lane < m) {
+            mine = mycand[lane];
+            int rank = 0;
+            for (int j = 0; j < m; ++j) {
+              const uint2 o = mycand[j];
+              rank += (o.x < mine.x || (o.x == mine.x && o.y < mine.y)) ? 1 : 0;
+            }
+            hit = rank == k - 1 - glo;
+          }
+          const int src = __ffs(__ballot_sync(0xffffffffu, hit)) - 1;
+          v = __shfl_sync(0xffffffffu, mine.x, src);
+          iv = (int)__shfl_sync(0xffffffffu, mine.y, src);
+          // all keys equal to v are among the m candidates (they lie in [lo, hi)): is any of them kept?
+          ties_all_pruned = __ballot_sync(0xffffffffu, lane < m && mine.x == v && (int)mine.y > iv) == 0u;
+        } else {
+          // more than 32 exact ties at the threshold value, all on the lists: bisect on the column index
+          v = lo;
+          const int r = k - glo;  // how many of the ties are pruned (lowest columns first)
+          int qlo = 0, qhi = C;   // count(key==v && col < qlo) < r <= count(key==v && col < qhi)
+          while (qhi - qlo > 1) {
+            const int qm = (qlo + qhi) >> 1;
+            uint32_t cnt = 0;
+            for (int i = 0; i < ln; ++i) {
+              const uint2 o = mylist[i][lane];
+              cnt += (o.x == v && (int)o.y < qm) ? 1u : 0u;
+            }
+            cnt = redux_add(cnt);
+            if ((int)cnt < r) qlo = qm; else qhi = qm;
+          }
+          iv = qlo;  // columns <= qlo with key == v are exactly the r lowest ties
         }
-        __syncthreads();
-        v = sh.v; iv = sh.iv;
       } else {
-        // more than kCap exact ties at the threshold value: bisect on the column index
+        // hi - lo == 1: every key of the bracket equals lo and there are too many for the lists (all-zero rows, dead
+        // channels): bisect on the column index with streaming counts
         v = lo;
-        const int r = k - glo;  // how many of the ties are pruned (lowest columns first)
-        int qlo = 0, qhi = C;   // count(key==v && col < qlo) < r <= count(key==v && col < qhi)
+        const int r = k - glo;
+        int qlo = 0, qhi = C;
         while (qhi - qlo > 1) {
-          const int q = (qlo + qhi) >> 1;
+          const int qm = (qlo + qhi) >> 1;
           uint32_t cnt = 0;
+          float dummy = 0.f;
+          for (int j = lane; j < nvec; j += 32) {
+            const uint4 wv = *reinterpret_cast<const uint4*>(wrow + j * V);
+            uint32_t key[V];
+            score(wv, j * V, key, dummy);
 #pragma unroll
-          for (int i = 0; i < KPT; ++i) {
-            const int col = ((i / V) * kSelThreads + threadIdx.x) * V + (i % V);
-            cnt += (keys[i] == v && col < q) ? 1u : 0u;
+            for (int e = 0; e < V; ++e) cnt += (key[e] == v && j * V + e < qm) ? 1u : 0u;
           }
           cnt = redux_add(cnt);
-          if ((threadIdx.x & 31) == 0) sh.red[parity][threadIdx.x >> 5][0] = cnt;
-          __syncthreads();
-          cnt = 0;
-#pragma unroll
-          for (int w2 = 0; w2 < kSelWarps; ++w2) cnt += sh.red[parity][w2][0];
-          parity ^= 1;
-          if ((int)cnt < r) qlo = q; else qhi = q;
+          if ((int)cnt < r) qlo = qm; else qhi = qm;
         }
-        iv = qlo;  // columns <= qlo with key == v are exactly the r lowest ties
+        iv = qlo;
       }
-      const float vf = __uint_as_float(v);
-      hint_ratio = (rmean > 0.f && vf > 0.f && vf < 3.0e38f) ? vf / rmean : -1.f;
+      prev_v = v;
+      from_sample = false;
     }
 
-    // apply: mask bytes (1 = keep) and zeroed weights
+    // ---- apply: re-stream the row (L2), mask bytes (1 = keep) and zeroed weights.
+    // Fast form: when every tie at the threshold is pruned (nearly always: a single key equals v) the rule
+    // "key < v or (key == v and col <= iv)" is "key < v + 1"; keys are < 2^31, so the sign bit of key - (v + 1) is the
+    // prune flag and byte permutes turn four of them into mask bytes / 16-bit weight masks without a compare.
     uint8_t* mrow = mask + (int64_t)row * ldm;
+    const bool fast = ties_all_pruned && v < 0x7fffffffu;
+    const uint32_t vcut = v + 1u;
+    for (int j0 = lane; j0 < nvec; j0 += 128) {
+      uint4 wv[4];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int col = (j * kSelThreads + threadIdx.x) * V;
-      if (col < C) {
-        uint32_t mb[V / 4] = {};
-        bool any = false;
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u * 32 < nvec) wv[u] = *reinterpret_cast<const uint4*>(wrow + (j0 + u * 32) * V);
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-          const uint32_t key = keys[j * V + e];
-          const bool pr = (key < v) || (key == v && (col + e) <= iv);
-          any |= pr;
-          mb[e / 4] |= (pr ? 0u : 1u) << (8 * (e % 4));
-        }
-        if (V == 8) st_stream8(mrow + col, make_uint2(mb[0], mb[V / 4 - 1]));
-        else st_stream4(mrow + col, mb[0]);
-        if (zero_w && any) {
-          uint4 wv = *reinterpret_cast<const uint4*>(wrow + col);  // L2 hit: the row was just streamed
-          float f[V];
-          Elem<T>::unpack(wv, f);
-          uint32_t* wr = reinterpret_cast<uint32_t*>(&wv);
-          if (sizeof(T) == 4) {
+      for (int u = 0; u < 4; ++u) {
+        const int col = (j0 + u * 32) * V;
+        if (j0 + u * 32 < nvec) {
+          uint32_t key[V];
+          float dummy = 0.f;
+          score(wv[u], col, key, dummy);
+          uint32_t mb[V / 4];
+          uint32_t* wr = reinterpret_cast<uint32_t*>(&wv[u]);
+          if (fast) {
+            uint32_t d[V];
 #pragma unroll
-            for (int e = 0; e < V; ++e) if (!((mb[e / 4] >> (8 * (e % 4))) & 1u)) wr[e] = 0u;
+            for (int e = 0; e < V; ++e) d[e] = key[e] - vcut;                       // sign bit set <=> pruned
+#pragma unroll
+            for (int q = 0; q < V / 4; ++q) {
+              const uint32_t t01 = __byte_perm(d[q * 4], d[q * 4 + 1], 0x0073);      // top bytes of d0, d1
+              const uint32_t t23 = __byte_perm(d[q * 4 + 2], d[q * 4 + 3], 0x0073);
+              const uint32_t tops = __byte_perm(t01, t23, 0x5410);                   // [d0 d1 d2 d3] top bytes
+              mb[q] = ((tops >> 7) & 0x01010101u) ^ 0x01010101u;                     // 1 = keep
+            }
+            if (zero_w) {
+              if (sizeof(T) == 4) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) wr[e] &= ~(uint32_t)((int32_t)d[e] >> 31);
+              } else {
+#pragma unroll
+                for (int e = 0; e < V; e += 2)   // sign-replicated top bytes -> 0xffff per pruned half
+                  wr[e / 2] &= ~prmt(d[e], d[e + 1], 0xffbbu);
+              }
+            }
           } else {
 #pragma unroll
-            for (int e = 0; e < V; ++e)
-              if (!((mb[e / 4] >> (8 * (e % 4))) & 1u)) wr[e / 2] &= (e & 1) ? 0x0000ffffu : 0xffff0000u;
+            for (int q = 0; q < V / 4; ++q) mb[q] = 0u;
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+              const bool pr = (key[e] < v) || (key[e] == v && (col + e) <= iv);
+              mb[e / 4] |= (pr ? 0u : 1u) << (8 * (e % 4));
+            }
+            if (zero_w) {
+              if (sizeof(T) == 4) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) if (!((mb[e / 4] >> (8 * (e % 4))) & 1u)) wr[e] = 0u;
+              } else {
+#pragma unroll
+                for (int e = 0; e < V; ++e)
+                  if (!((mb[e / 4] >> (8 * (e % 4))) & 1u)) wr[e / 2] &= (e & 1) ? 0x0000ffffu : 0xffff0000u;
+              }
+            }
           }
-          st_stream(wrow + col, wv);
+          if (V == 8) st_stream8(mrow + col, make_uint2(mb[0], mb[V / 4 - 1]));
+          else st_stream4(mrow + col, mb[0]);
+          if (zero_w) {
+            bool any = false;
+#pragma unroll
+            for (int q = 0; q < V / 4; ++q) any |= mb[q] != 0x01010101u;
+            if (any) st_stream(wrow + col, wv[u]);
+          }
         }
       }
     }
-    __syncthreads();  // sh.cand_cnt / sh.v reuse
+    __syncwarp();
   }
 }
 
@@ -260,56 +460,68 @@ nm_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict_
   for (int e = 0; e < E; ++e) sq[e] = ok ? __fsqrt_rn(scaler_row[col + e]) : 0.f;
   float lsum = 0.f;
   if (ok) {
-    for (int row = blockIdx.y; row < R; row += gridDim.y) {
-      T* wp = W + (int64_t)row * ldw + col;
-      uint4 wv[NVEC];
+    constexpr int kRows = 4;               // rows in flight per thread: kRows x NVEC 16-byte loads before any use
+    for (int row0 = blockIdx.y; row0 < R; row0 += gridDim.y * kRows) {
+      uint4 wv[kRows][NVEC];
 #pragma unroll
-      for (int q = 0; q < NVEC; ++q) wv[q] = ld_stream(wp + q * V);
-      uint32_t keys[E];
+      for (int r = 0; r < kRows; ++r) {
+        const int row = row0 + r * gridDim.y;
+        if (row < R) {
 #pragma unroll
-      for (int q = 0; q < NVEC; ++q) {
-        float f[V];
-        Elem<T>::unpack(wv[q], f);
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-          const float s = __fmul_rn(fabsf(f[e]), sq[q * V + e]);
-          keys[q * V + e] = __float_as_uint(s);
-          lsum += s;
+          for (int q = 0; q < NVEC; ++q) wv[r][q] = ld_stream(W + (int64_t)row * ldw + col + q * V);
         }
       }
-      bool pr[E];
 #pragma unroll
-      for (int g = 0; g < E / M; ++g) {
+      for (int r = 0; r < kRows; ++r) {
+        const int row = row0 + r * gridDim.y;
+        if (row >= R) break;
+        T* wp = W + (int64_t)row * ldw + col;
+        uint32_t keys[E];
 #pragma unroll
-        for (int a = 0; a < M; ++a) {
-          int rank = 0;
+        for (int q = 0; q < NVEC; ++q) {
+          float f[V];
+          Elem<T>::unpack(wv[r][q], f);
 #pragma unroll
-          for (int b = 0; b < M; ++b) {
-            if (b < a) rank += keys[g * M + b] <= keys[g * M + a] ? 1 : 0;
-            if (b > a) rank += keys[g * M + b] < keys[g * M + a] ? 1 : 0;
+          for (int e = 0; e < V; ++e) {
+            const float s = __fmul_rn(fabsf(f[e]), sq[q * V + e]);
+            keys[q * V + e] = __float_as_uint(s);
+            lsum += s;
           }
-          pr[g * M + a] = rank < n;
         }
-      }
-      uint8_t* mp = mask + (int64_t)row * ldm + col;
+        bool pr[E];
 #pragma unroll
-      for (int q = 0; q < NVEC; ++q) {
-        uint32_t mb[V / 4] = {};
+        for (int g = 0; g < E / M; ++g) {
 #pragma unroll
-        for (int e = 0; e < V; ++e) mb[e / 4] |= (pr[q * V + e] ? 0u : 1u) << (8 * (e % 4));
-        if (V == 8) st_stream8(mp + q * V, make_uint2(mb[0], mb[V / 4 - 1]));
-        else st_stream4(mp + q * V, mb[0]);
-        if (zero_w) {
-          uint32_t* wr = reinterpret_cast<uint32_t*>(&wv[q]);
-          if (sizeof(T) == 4) {
+          for (int a = 0; a < M; ++a) {
+            int rank = 0;
 #pragma unroll
-            for (int e = 0; e < V; ++e) if (pr[q * V + e]) wr[e] = 0u;
-          } else {
-#pragma unroll
-            for (int e = 0; e < V; ++e)
-              if (pr[q * V + e]) wr[e / 2] &= (e & 1) ? 0x0000ffffu : 0xffff0000u;
+            for (int b = 0; b < M; ++b) {
+              if (b < a) rank += keys[g * M + b] <= keys[g * M + a] ? 1 : 0;
+              if (b > a) rank += keys[g * M + b] < keys[g * M + a] ? 1 : 0;
+            }
+            pr[g * M + a] = rank < n;
           }
-          st_stream(wp + q * V, wv[q]);
+        }
+        uint8_t* mp = mask + (int64_t)row * ldm + col;
+#pragma unroll
+        for (int q = 0; q < NVEC; ++q) {
+          uint32_t mb[V / 4] = {};
+#pragma unroll
+          for (int e = 0; e < V; ++e) mb[e / 4] |= (pr[q * V + e] ? 0u : 1u) << (8 * (e % 4));
+          if (V == 8) st_stream8(mp + q * V, make_uint2(mb[0], mb[V / 4 - 1]));
+          else st_stream4(mp + q * V, mb[0]);
+          if (zero_w) {
+            uint32_t* wr = reinterpret_cast<uint32_t*>(&wv[r][q]);
+            if (sizeof(T) == 4) {
+#pragma unroll
+              for (int e = 0; e < V; ++e) if (pr[q * V + e]) wr[e] = 0u;
+            } else {
+#pragma unroll
+              for (int e = 0; e < V; ++e)
+                if (pr[q * V + e]) wr[e / 2] &= (e & 1) ? 0x0000ffffu : 0xffff0000u;
+            }
+            st_stream(wp + q * V, wv[r][q]);
+          }
         }
       }
     }
@@ -360,22 +572,18 @@ static int sel_common_checks(void* W, int dtype, int R, int C, int64_t ldw, cons
   return VLMC_OK;
 }
 
-template <typename T, int KPT>
-static int launch_rowselect(void* W, int R, int C, int64_t ldw, const float* scaler_row, int k, int zero_w,
-                            uint8_t* mask, int64_t ldm, float* row_sum, cudaStream_t st) {
-  const size_t smem = (size_t)C * sizeof(float);
-  auto kern = rowselect_kernel<T, KPT>;
-  if (smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return check_launch();
-  }
+template <typename T>
+static int launch_rowselect(void* W, int R, int C, int64_t ldw, const float* sq, int k, int zero_w,
+                            uint8_t* mask, int64_t ldm, float* row_sum, uint32_t* seed, cudaStream_t st) {
+  auto kern = rowselect_kernel<T>;
+  rowselect_seed_kernel<T><<<1, 32, 0, st>>>(reinterpret_cast<const T*>(W), ldw, R, C, sq, k, seed);
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSelThreads, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRsWarps * 32, 0);
   if (per_sm < 1) per_sm = 1;
   int grid = kNumSMs * per_sm;
-  if (grid > R) grid = R;
-  kern<<<grid, kSelThreads, smem, st>>>(reinterpret_cast<T*>(W), ldw, R, C, scaler_row, k, zero_w,
-                                        mask, ldm, row_sum);
+  const int need = (R + kRsWarps - 1) / kRsWarps;
+  if (grid > need) grid = need;
+  kern<<<grid, kRsWarps * 32, 0, st>>>(reinterpret_cast<T*>(W), ldw, R, C, sq, k, zero_w, mask, ldm, row_sum, seed);
   return check_launch();
 }
 
@@ -389,20 +597,14 @@ extern "C" int vlmc_wanda_rowselect(void* W, int dtype, int R, int C, int64_t ld
   int rc = sel_common_checks(W, dtype, R, C, ldw, scaler_row, keep_mask, ldm, ws);
   if (rc) return rc;
   if (k < 0) return VLMC_ERR_BAD_ARG;
-  if (C > kSelThreads * 128) return VLMC_ERR_UNSUPPORTED;  // row must fit the register file of one CTA
-  if (ws_bytes < VLMC_WS_COUNTER_BYTES + (size_t)R * sizeof(float)) return VLMC_ERR_WORKSPACE;
+  if (ws_bytes < VLMC_WS_COUNTER_BYTES + ((size_t)R + (size_t)C + 8) * sizeof(float)) return VLMC_ERR_WORKSPACE;
   float* row_sum = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + VLMC_WS_COUNTER_BYTES);
+  uint32_t* seed = reinterpret_cast<uint32_t*>(row_sum + R);
+  float* sq = row_sum + R + 4;                 // sqrt(scaler_row), computed once per call instead of once per CTA
+  if (((uintptr_t)sq & 15) != 0) sq += 4 - (((uintptr_t)sq >> 2) & 3);
   cudaStream_t st = (cudaStream_t)stream;
-  const int kpt_needed = (C + kSelThreads - 1) / kSelThreads;
-#define VLMC_ROWSEL(KPT)                                                                          \
-  VLMC_DISPATCH_DTYPE(dtype, rc = (launch_rowselect<scalar_t, KPT>(W, R, C, ldw, scaler_row, k,   \
-                                                                   zero_w, keep_mask, ldm, row_sum, st)))
-  if (kpt_needed <= 16) { VLMC_ROWSEL(16); }
-  else if (kpt_needed <= 32) { VLMC_ROWSEL(32); }
-  else if (kpt_needed <= 48) { VLMC_ROWSEL(48); }
-  else if (kpt_needed <= 88) { VLMC_ROWSEL(88); }
-  else { VLMC_ROWSEL(128); }
-#undef VLMC_ROWSEL
+  sqrt_vec_kernel<<<(C + 255) / 256, 256, 0, st>>>(scaler_row, sq, C);
+  VLMC_DISPATCH_DTYPE(dtype, rc = (launch_rowselect<scalar_t>(W, R, C, ldw, sq, k, zero_w, keep_mask, ldm, row_sum, seed, st)));
   if (rc) return rc;
   if (score_mean) return launch_mean_finalize(row_sum, R, (double)R * (double)C, score_mean, st);
   return VLMC_OK;
