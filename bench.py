@@ -42,12 +42,13 @@ LINEARS = [  # name, rows, cols, input id
 ]
 INPUT_DIMS = {"attn_in": D, "attn_out": D, "mlp_in": D, "mlp_mid": FF}
 N_SEQ, SEQ_LEN = 128, 2048
-METHODS = ["wanda_nm", "wanda_unstructured", "sparsegpt", "dsnot"]
+METHODS = ["wanda_nm", "wanda_unstructured", "sparsegpt", "dsnot", "dsnot_elided"]
 METRIC, UNIT = "s_per_vicuna7b_block_pruned", "s/block"
 WORKLOAD = {
     "wanda_nm": "Wanda 2:4", "wanda_unstructured": "Wanda 50% unstructured (per-row)",
     "sparsegpt": "SparseGPT 50% unstructured (blocksize 128, percdamp 0.01)",
-    "dsnot": "Wanda-initialised DSnoT refine at 60% (reference semantics)",
+    "dsnot": "Wanda-initialised DSnoT refine at 60% (reference semantics, swap loop executed)",
+    "dsnot_elided": "Wanda-initialised DSnoT at 60% (reference semantics; the self-cancelling swap loop elided: same masks)",
 }
 
 
@@ -213,7 +214,7 @@ def step_wanda(ctx, weights, inputs, method):
     return masks
 
 
-def step_dsnot(ctx, weights, inputs):
+def step_dsnot(ctx, weights, inputs, elide=False):
     torch, native, parallel = ctx.torch, ctx.native, ctx.parallel
     stats = {}
     for name, R, C, inp in LINEARS:
@@ -234,9 +235,13 @@ def step_dsnot(ctx, weights, inputs):
         s, e = parallel.row_range(R, ctx.rank, ctx.world)
         keep = torch.empty((R, C), dtype=torch.bool, device=ctx.dev)
         st = stats[name]
-        ctx.timed("dsnot_refine", (e - s) * C * 7, lambda: native.dsnot_refine(
-            W[s:e], st[0], st[1], st[3], round(C * 0.6), keep_mask=keep[s:e],
-            reduce_ncycles=parallel.allreduce_max if ctx.world > 1 else None))
+        if elide:      # shipped semantics: the swaps are written back, the mask is the initial selection
+            ctx.timed("wanda_select", (e - s) * C * 5, lambda: native.wanda_rowselect(
+                W[s:e], st[0], round(C * 0.6), keep_mask=keep[s:e]))
+        else:
+            ctx.timed("dsnot_refine", (e - s) * C * 7, lambda: native.dsnot_refine(
+                W[s:e], st[0], st[1], st[3], round(C * 0.6), keep_mask=keep[s:e],
+                reduce_ncycles=parallel.allreduce_max if ctx.world > 1 else None))
         ctx.launches += 2
         if ctx.world > 1:      # masks travel as bits; the replicated weights are zeroed locally
             parallel.exchange_rows_packed(
@@ -286,12 +291,12 @@ def step_sparsegpt(ctx, weights, inputs):
 def run_step(ctx, method, weights, inputs):
     if method == "sparsegpt":
         return step_sparsegpt(ctx, weights, inputs)
-    if method == "dsnot":
-        return step_dsnot(ctx, weights, inputs)
+    if method in ("dsnot", "dsnot_elided"):
+        return step_dsnot(ctx, weights, inputs, elide=method == "dsnot_elided")
     return step_wanda(ctx, weights, inputs, method)
 
 
-GRAPH_METHODS = ("wanda_nm", "wanda_unstructured", "dsnot")   # no host round trip inside the step (SparseGPT's
+GRAPH_METHODS = ("wanda_nm", "wanda_unstructured", "dsnot", "dsnot_elided")   # no host round trip inside the step (SparseGPT's
                                                                 # conditional damping reads a status word)
 
 
@@ -484,6 +489,9 @@ def run_e2e(torch, native, parallel, dev, args, rank, world, dev_inputs):
     from vlmc.compression.pruners.sparsegpt_pruner import SparseGPT
     from vlmc.compression.pruners import dsnot_pruner
     method = args.method
+    elide = method == "dsnot_elided"
+    if elide:
+        method = "dsnot"
     n_local = next(iter(dev_inputs.values())).shape[0]
     chunk = min(8, n_local)
     host_in = {}
@@ -554,7 +562,7 @@ def run_e2e(torch, native, parallel, dev, args, rank, world, dev_inputs):
                 host_out_w[name].copy_(wr.layer.weight.data, non_blocking=True)
                 continue
             if method == "dsnot":
-                dsnot_pruner.dsnot_prune_linear(wr.layer, wr, 0.6)
+                dsnot_pruner.dsnot_prune_linear(wr.layer, wr, 0.6, elide_noop_swaps=elide)
             elif method == "wanda_nm":
                 from vlmc.compression.pruners.wanda_pruner import wanda_prune_linear
                 wanda_prune_linear(wr.layer, wr.scaler_row, 0.5, 2, 4)
@@ -670,13 +678,30 @@ def full_model_wanda_nm(torch, native, dev, reps=2):
         one_model()
     b.record()
     torch.cuda.synchronize()
-    sec = a.elapsed_time(b) / reps / 1e3
+    eager_sec = a.elapsed_time(b) / reps / 1e3
+    sec, graphed = eager_sec, False
+    try:    # ~2400 launches of 30-100 us kernels: replayed from one CUDA graph the host leaves the timed region
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            one_model()
+        g.replay()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        sec, graphed = a.elapsed_time(b) / reps / 1e3, True
+        del g
+    except Exception:  # noqa: BLE001
+        torch.cuda.synchronize()
     del plan
     torch.cuda.empty_cache()
     return {"value": sec, "unit": "s/model", "workload": "Wanda 2:4 on full InstructBLIP-FlanT5-XL: 39 EVA ViT-g blocks (fp16, "
             "128x257 tokens, fp32 qkv/fc1 inputs) + 24 + 24 FlanT5-XL blocks (bf16, 128x512 tokens), random init",
             "linears": sum(len(l) * n for _, l, n, _, _ in FULL_MODEL), "weights": total_weights,
-            "algorithmic_bytes": total_bytes, "achieved_gbs": total_bytes / sec / 1e9, "reps": reps}
+            "algorithmic_bytes": total_bytes, "achieved_gbs": total_bytes / sec / 1e9, "reps": reps,
+            "cuda_graph": graphed, "eager_s_per_model": eager_sec}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -685,6 +710,8 @@ def cpu_block_seconds(method, threads, budget="small"):
     whole block.  Returns (seconds per block, description of the sample)."""
     import torch
     from oracle import cpu_port
+    if method == "dsnot_elided":
+        method = "dsnot"
     torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(0)
     xs = {inp: (torch.randn(SEQ_LEN, C, generator=g)).half() for inp, C in INPUT_DIMS.items()}

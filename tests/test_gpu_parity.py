@@ -766,6 +766,26 @@ def test_dsnot_refine_full_size_properties(native):
         assert e_u < e_w
 
 
+def test_dsnot_elided_swaps_equal_the_executed_loop(native):
+    """Shipped semantics, unstructured: skipping the (self-cancelling) swap loop gives the same mask and weights as
+    executing it; with upstream semantics the option has no effect."""
+    from vlmc.compression.pruners import dsnot_pruner as dp
+    R, C = 96, 1408
+    W0 = weights(R, C, 21, torch.float16)
+    x = acts(3 * 512, C, 5, torch.float16).cuda().view(3, 512, C)
+    outs = []
+    for elide in (False, True):
+        lin = torch.nn.Linear(C, R, bias=False).cuda().half()
+        lin.weight.data.copy_(W0)
+        wr = dp.WrappedGPT(lin)
+        for j in range(3):
+            wr.add_batch(x[j:j + 1], None)
+        dp.dsnot_prune_linear(lin, wr, 0.6, elide_noop_swaps=elide)
+        outs.append((lin.mask.clone(), lin.weight.data.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert int((~outs[0][0]).sum(1).max()) == round(C * 0.6)
+
+
 def test_composite_dsnot_pruner_on_toy_model(native):
     import toy_model
     import vlmc.compression as comp

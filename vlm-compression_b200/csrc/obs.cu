@@ -98,10 +98,11 @@ __device__ __forceinline__ uint32_t obs_key(float w, float d2) {
 }
 
 // bin holding the kk-th (1-indexed) entry of a global histogram and the count before it; every thread returns both
+template <int NT>
 __device__ void obs_find_bin(const unsigned int* __restrict__ gh, unsigned int kk, unsigned int* s_scan,
                              unsigned int& bin, unsigned int& before) {
   const int tid = threadIdx.x;
-  constexpr int per = kObsBins / kObsThreads;
+  constexpr int per = kObsBins / NT;
   unsigned int c[per];
   unsigned int local = 0;
 #pragma unroll
@@ -147,8 +148,8 @@ obs_hist_kernel(const ObsParams p) {
     s_d2[tid] = __fmul_rn(d, d);
   }
   unsigned int b1 = 0, b2 = 0, before = 0, kk = p.kth;
-  if (PASS >= 1) { obs_find_bin(p.hist->h[0], kk, s_scan, b1, before); kk -= before; }
-  if (PASS >= 2) { obs_find_bin(p.hist->h[1], kk, s_scan, b2, before); kk -= before; }
+  if (PASS >= 1) { obs_find_bin<kObsThreads>(p.hist->h[0], kk, s_scan, b1, before); kk -= before; }
+  if (PASS >= 2) { obs_find_bin<kObsThreads>(p.hist->h[1], kk, s_scan, b2, before); kk -= before; }
   __syncthreads();
   const int vec_per_row = p.bs >> 2;
   const int64_t nvec = (int64_t)p.R * vec_per_row;
@@ -170,14 +171,16 @@ obs_hist_kernel(const ObsParams p) {
 }
 
 // K12 (+ the tail of K11): one warp per row
+constexpr int kSweepThreads = 512;   // 16 rows per CTA share one 64 KB U1 tile: 2 CTAs = 32 rows in flight per SM
+
 template <typename T>
-__global__ void __launch_bounds__(kObsThreads)
+__global__ void __launch_bounds__(kSweepThreads)
 obs_sweep_kernel(const ObsParams p) {
   extern __shared__ __align__(16) float Us[];                  // [kOB][kOB] U1 tile, zero padded
   __shared__ unsigned int s_scan[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bs = p.bs;
-  for (int idx = tid; idx < kOB * kOB / 4; idx += kObsThreads) {
+  for (int idx = tid; idx < kOB * kOB / 4; idx += kSweepThreads) {
     const int i = idx / (kOB / 4), j = (idx % (kOB / 4)) * 4;
     float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i < bs && j < bs) u = *reinterpret_cast<const float4*>(p.U + (int64_t)(p.i1 + i) * p.ldu + p.i1 + j);
@@ -186,16 +189,16 @@ obs_sweep_kernel(const ObsParams p) {
   uint32_t v = 0;
   if (p.prune_n == 0) {
     unsigned int b1, b2, b3, before, kk = p.kth;
-    obs_find_bin(p.hist->h[0], kk, s_scan, b1, before); kk -= before;
-    obs_find_bin(p.hist->h[1], kk, s_scan, b2, before); kk -= before;
-    obs_find_bin(p.hist->h[2], kk, s_scan, b3, before);
+    obs_find_bin<kSweepThreads>(p.hist->h[0], kk, s_scan, b1, before); kk -= before;
+    obs_find_bin<kSweepThreads>(p.hist->h[1], kk, s_scan, b2, before); kk -= before;
+    obs_find_bin<kSweepThreads>(p.hist->h[2], kk, s_scan, b3, before);
     v = (b1 << 21) | (b2 << 10) | b3;                          // the k-th smallest block score, exactly (:184)
   }
   __syncthreads();
   const bool act = 4 * lane < bs;
   const int m = p.prune_m, n = p.prune_n;
 
-  for (int row = blockIdx.x * (kObsThreads / 32) + warp; row < p.R; row += gridDim.x * (kObsThreads / 32)) {
+  for (int row = blockIdx.x * (kSweepThreads / 32) + warp; row < p.R; row += gridDim.x * (kSweepThreads / 32)) {
     float* w32 = p.W32 + (int64_t)row * p.C + p.i1 + 4 * lane;
     float w[4] = {0.f, 0.f, 0.f, 0.f};
     if (act) { const float4 t = *reinterpret_cast<const float4*>(w32); w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w; }
@@ -381,10 +384,10 @@ extern "C" int vlmc_obs_block_finish(void* W, int dtype, int R, int C, int64_t l
       return check_launch();
     attr_set = true;
   }
-  const int rows_per_cta = kObsThreads / 32;
+  const int rows_per_cta = kSweepThreads / 32;
   int sweep_grid = (R + rows_per_cta - 1) / rows_per_cta;
-  if (sweep_grid > kNumSMs * 3) sweep_grid = kNumSMs * 3;
-  VLMC_DISPATCH_DTYPE(dtype, (obs_sweep_kernel<scalar_t><<<sweep_grid, kObsThreads, smem, st>>>(p)));
+  if (sweep_grid > kNumSMs * 2) sweep_grid = kNumSMs * 2;
+  VLMC_DISPATCH_DTYPE(dtype, (obs_sweep_kernel<scalar_t><<<sweep_grid, kSweepThreads, smem, st>>>(p)));
   const int i2 = p.i1 + p.bs;
   if (i2 < C) {
     // K13: W[:, i2:] -= Err1 @ U[i1:i2, i2:]

@@ -67,16 +67,21 @@ def return_reorder_indice(input_tensor):
 
 def dsnot_prune_linear(module, wrapper, sparsity, prune_n=0, prune_m=0, lora_model=False, initial_method="wanda",
                        pow_of_var_regrowing=1.0, max_cycle_time=100, update_threshold=0.1, without_same_sign=True,
-                       without_DSnoT=False, ref_fixup=True, argmin_rule=1, reduce_ncycles=None):
+                       without_DSnoT=False, ref_fixup=True, argmin_rule=1, reduce_ncycles=None, elide_noop_swaps=False):
     """One linear (dsnot_pruner.py:359-755).  Sets module.mask (True = kept), zeroes pruned weights unless lora_model.
-    Returns the executed cycle count (1-elem int tensor) or None when nothing ran."""
+    Returns the executed cycle count (1-elem int tensor) or None when nothing ran.
+
+    elide_noop_swaps: with the shipped reference semantics (ref_fixup) every unstructured swap is written back by
+    :734-740, and the candidates always come from the initial kept / pruned sets, so the final mask IS the initial
+    selection (tests assert the equality).  True skips the cycle loop and runs the initial selection only -
+    same mask, same weights, no cycle count.  Off by default: the default path executes what the reference executes."""
     W = module.weight.data
     C = W.shape[1]
     if prune_n == 0:
         if sparsity == 0.:
             return None                                          # :560-561 `continue`: the layer is left untouched
         k = round(C * sparsity)                                  # :562 (python round, SURVEY F5)
-        if without_DSnoT:                                        # :577-578: the initial mask only
+        if without_DSnoT or (elide_noop_swaps and ref_fixup):    # :577-578: the initial mask only
             scal = wrapper.scaler_row if initial_method == "wanda" else torch.ones_like(wrapper.scaler_row)
             keep, _ = native.wanda_rowselect(W, scal, k, zero_w=not lora_model)
             setattr(module, "mask", keep)
@@ -98,7 +103,7 @@ class BLIPT5LayerDSnoTPruner(BLIPT5LayerWandaPruner):
 
     def __init__(self, model, data_loader, initial_method="wanda", skip_layer=None, skip_sub_layer=None,
                  pow_of_var_regrowing=1., max_cycle_time=1e2, update_threshold=0.1, without_same_sign=True,
-                 without_DSnoT=False, upstream_semantics=False, **kwargs):
+                 without_DSnoT=False, upstream_semantics=False, elide_noop_swaps=False, **kwargs):
         super().__init__(model, data_loader, **kwargs)
         self.pow_of_var_regrowing = pow_of_var_regrowing
         self.without_same_sign = without_same_sign
@@ -111,6 +116,7 @@ class BLIPT5LayerDSnoTPruner(BLIPT5LayerWandaPruner):
         # False (default): bit-for-bit the shipped reference, whose write-back block (:734-740) turns the unstructured
         # swaps into no-ops.  True: the upstream DSnoT behaviour (that block removed).
         self.upstream_semantics = upstream_semantics
+        self.elide_noop_swaps = elide_noop_swaps          # see dsnot_prune_linear
 
     def make_wrapper(self, module):
         return WrappedGPT(module, initial_method=self.initial_method)
@@ -122,5 +128,5 @@ class BLIPT5LayerDSnoTPruner(BLIPT5LayerWandaPruner):
                                initial_method=self.initial_method, pow_of_var_regrowing=self.pow_of_var_regrowing,
                                max_cycle_time=self.max_cycle_time, update_threshold=self.update_threshold,
                                without_same_sign=self.without_same_sign, without_DSnoT=self.without_DSnoT,
-                               ref_fixup=not self.upstream_semantics)
+                               ref_fixup=not self.upstream_semantics, elide_noop_swaps=self.elide_noop_swaps)
         return fn
