@@ -42,14 +42,28 @@ LINEARS = [  # name, rows, cols, input id
 ]
 INPUT_DIMS = {"attn_in": D, "attn_out": D, "mlp_in": D, "mlp_mid": FF}
 N_SEQ, SEQ_LEN = 128, 2048
-METHODS = ["wanda_nm", "wanda_unstructured", "sparsegpt", "dsnot", "dsnot_elided"]
+METHODS = ["wanda_nm", "wanda_unstructured", "sparsegpt", "dsnot", "dsnot_elided", "wanda_nm_shared", "sparsegpt_shared"]
 METRIC, UNIT = "s_per_vicuna7b_block_pruned", "s/block"
 WORKLOAD = {
     "wanda_nm": "Wanda 2:4", "wanda_unstructured": "Wanda 50% unstructured (per-row)",
     "sparsegpt": "SparseGPT 50% unstructured (blocksize 128, percdamp 0.01)",
     "dsnot": "Wanda-initialised DSnoT refine at 60% (reference semantics, swap loop executed)",
     "dsnot_elided": "Wanda-initialised DSnoT at 60% (reference semantics; the self-cancelling swap loop elided: same masks)",
+    "wanda_nm_shared": "Wanda 2:4, statistics of linears fed by the same activations (q/k/v, gate/up) accumulated once "
+                       "(4 accumulations per block instead of 7; same masks)",
+    "sparsegpt_shared": "SparseGPT 50% unstructured (blocksize 128, percdamp 0.01), Hessians of linears fed by the same "
+                        "activations accumulated and factorised once (4 per block instead of 7; same weights)",
 }
+
+
+def stat_groups(shared):
+    """[(leader linear, [member linears])]: per linear like the reference's hooks, or one group per distinct input."""
+    if not shared:
+        return [(n, [n]) for n, *_ in LINEARS]
+    by_inp = {}
+    for n, _, _, inp in LINEARS:
+        by_inp.setdefault(inp, []).append(n)
+    return [(m[0], m) for m in by_inp.values()]
 
 
 def peaks():
@@ -131,7 +145,8 @@ class Ctx:
     """Everything a step needs: torch, the bindings, rank / world, persistent device buffers."""
 
     def __init__(self, torch, native, parallel, dev, rank, world, calib_batch):
-        self.torch, self.native, self.parallel = torch, native, parallel
+        from vlmc import schedule
+        self.torch, self.native, self.parallel, self.schedule = torch, native, parallel, schedule
         self.dev, self.rank, self.world, self.calib_batch = dev, rank, world, calib_batch
         self.events = None          # list of (tag, start, end, work) when kernel timing is on
         self.launches = 0
@@ -171,27 +186,37 @@ def accumulate(ctx, fn, x, state, work_per_seq, tag):
         ctx.launches += 1
 
 
-def step_wanda(ctx, weights, inputs, method):
+def step_wanda(ctx, weights, inputs, method, shared=False):
     torch, native, parallel = ctx.torch, ctx.native, ctx.parallel
+    shape = {n: (R, C, inp) for n, R, C, inp in LINEARS}
     scalers = {}
-    for name, R, C, inp in LINEARS:                       # phase 1: statistics (per-linear API, no de-duplication)
+    for leader, members in stat_groups(shared):           # phase 1: statistics (per-linear API unless `shared`)
+        _, C, inp = shape[leader]
         s = torch.zeros(C, device=ctx.dev, dtype=torch.float32)
         accumulate(ctx, native.sqnorm_accum, inputs[inp], s, SEQ_LEN * C * 2, "sqnorm_accum")
-        scalers[name] = s
+        for m in members:
+            scalers[m] = s
     if ctx.world > 1:
-        flat = torch.cat(list(scalers.values()))
+        uniq = list({id(s): s for s in scalers.values()}.values())
+        flat = torch.cat(uniq)
         parallel.allreduce_sum(flat)
         off = 0
-        for s in scalers.values():
+        for s in uniq:
             s.copy_(flat[off:off + s.numel()])
             off += s.numel()
     masks = {}
+    if method == "wanda_nm":
+        # phase 2, n:m: a group decision needs its m scores and nothing else, and the pruned weights + masks must end
+        # up on EVERY rank anyway (5 B/weight to rewrite the replica) - exactly the traffic of running the selection
+        # itself.  So every rank selects on its whole replica: no row split, no exchange, identical results.
+        for name, R, C, _ in LINEARS:
+            masks[name] = ctx.timed("wanda_select", R * C * 5, lambda: native.wanda_nm(weights[name], scalers[name], 2, 4)[0])
+            ctx.launches += 2
+        return masks
     if ctx.world > 1 and all(R % ctx.world == 0 for _, R, _, _ in LINEARS):
-        # phase 2, sharded: select on this rank's rows, ONE all-gather of the bit-packed masks of all 7 linears,
-        # the other rows of the replicated weights are zeroed locally from the received bits
+        # phase 2, per-row top-k, sharded: select on this rank's rows, ONE all-gather of the bit-packed masks of all 7
+        # linears, the other rows of the replicated weights are zeroed locally from the received bits
         def make_sel(name, C):
-            if method == "wanda_nm":
-                return lambda Wr, keep: native.wanda_nm(Wr, scalers[name], 2, 4, keep_mask=keep)[1]
             return lambda Wr, keep: native.wanda_rowselect(Wr, scalers[name], int(C * 0.5), keep_mask=keep)[1]
         names = [n for n, *_ in LINEARS]
         total = sum(R * C for _, R, C, _ in LINEARS)
@@ -202,12 +227,8 @@ def step_wanda(ctx, weights, inputs, method):
         ctx.launches += 7 * 3
         return {n: k for n, (k, _) in zip(names, res)}
     for name, R, C, _ in LINEARS:                         # phase 2: score + select + apply on this rank's rows
-        if method == "wanda_nm":
-            def sel(Wr, s, keep):
-                return native.wanda_nm(Wr, s, 2, 4, keep_mask=keep)[1]
-        else:
-            def sel(Wr, s, keep, C=C):
-                return native.wanda_rowselect(Wr, s, int(C * 0.5), keep_mask=keep)[1]
+        def sel(Wr, s, keep, C=C):
+            return native.wanda_rowselect(Wr, s, int(C * 0.5), keep_mask=keep)[1]
         masks[name], _ = ctx.timed("wanda_select", R * C * 5 // ctx.world, lambda: parallel.prune_linear_row_sharded(
             weights[name], scalers[name], sel, ctx.rank, ctx.world))
         ctx.launches += 2
@@ -252,51 +273,53 @@ def step_dsnot(ctx, weights, inputs, elide=False):
     return masks
 
 
-def step_sparsegpt(ctx, weights, inputs):
-    torch, native, parallel = ctx.torch, ctx.native, ctx.parallel
+def step_sparsegpt(ctx, weights, inputs, shared=False):
+    """Phase 1: H = (2/N) sum X^T X on the tensor cores (tokens split over ranks, SUM all-reduce).
+    Phase 2 + 3: the factorisation and the OBS sweep of a linear are sequential chains of small kernels, independent
+    between linears: on one GPU they run concurrently, one stream per chain (vlmc.schedule); on several GPUs WHOLE
+    linears are spread over the ranks (longest chain first), each rank runs its chains concurrently and the pruned
+    weights are broadcast from their owners - no per-column-block exchange, no broadcast of U."""
+    torch, native, parallel, schedule = ctx.torch, ctx.native, ctx.parallel, ctx.schedule
     H, U = ctx.sparsegpt_buffers()
-    for name, R, C, inp in LINEARS:                       # phase 1: H = (2/N) sum X^T X on the tensor cores
-        accumulate(ctx, native.hessian_accum, inputs[inp], H[name], 2.0 * SEQ_LEN * C * C, "hessian_accum")
+    shape = {n: (R, C, inp) for n, R, C, inp in LINEARS}
+    Hof = {}
+    for leader, members in stat_groups(shared):
+        _, C, inp = shape[leader]
+        accumulate(ctx, native.hessian_accum, inputs[inp], H[leader], 2.0 * SEQ_LEN * C * C, "hessian_accum")
         if ctx.world > 1:
-            parallel.allreduce_sum(H[name])
-
-    def factor(Hm, Um):                                   # sparsegpt_pruner.py:95-157 (host damping loop)
-        damp, dead = native.hessian_prepare(Hm, 0.01)
-        while True:
-            _, status = native.chol_inv_upper(Hm, Um)
-            ctx.launches += 1
-            if status.item() == 0:
-                return Um, dead
-            native.hessian_add_damp(Hm, damp)
-
+            parallel.allreduce_sum(H[leader])
+        for m in members:
+            Hof[m] = leader
     names = [n for n, *_ in LINEARS]
-    ubuf = {id(H[n]): U[n] for n in names}
-    owners = parallel.assign_factorisations([c for _, _, c, _ in LINEARS], ctx.world)
-    flop = sum(2.0 / 3.0 * c ** 3 for (_, _, c, _), o in zip(LINEARS, owners) if o == ctx.rank)
-    facs = ctx.timed("chol_inv_upper", flop, lambda: parallel.factor_all(
-        [H[n] for n in names], lambda Hm: factor(Hm, ubuf[id(Hm)]),
-        lambda Hm: (ubuf[id(Hm)], torch.empty(Hm.shape[0], dtype=torch.uint8, device=ctx.dev)), ctx.rank, ctx.world))
-    for (name, R, C, _), (Um, dead) in zip(LINEARS, facs):     # phase 3: OBS sweep on this rank's rows
-        def sweep(Wr, Uu, dd, rows_total, reduce_sum):
-            if ctx.world == 1:
-                native.obs_sweep(Wr, Uu, 0.5, dead=dd)
-            else:
-                native.obs_sweep_row_shard(Wr, Uu, 0.5, rows_total, reduce_sum, dead=dd)
-        ctx.timed("obs_sweep", float(R) * C * C / ctx.world, lambda: parallel.obs_rows_sharded(
-            weights[name], Um, dead, sweep, ctx.rank, ctx.world))
-        ctx.launches += 5 * ((C + 127) // 128)
+
+    def run(indices):
+        mine = [names[i] for i in indices]
+        leaders = list(dict.fromkeys(Hof[n] for n in mine))
+        flop = sum(2.0 / 3.0 * shape[l][1] ** 3 for l in leaders)
+        facs = ctx.timed("chol_inv_upper", flop, lambda: schedule.factor_concurrent(
+            [H[l] for l in leaders], 0.01, [U[l] for l in leaders]))
+        fac = dict(zip(leaders, facs))
+        ctx.launches += len(leaders)
+        flop = sum(float(shape[n][0]) * shape[n][1] ** 2 for n in mine)
+        ctx.timed("obs_sweep", flop, lambda: schedule.sweep_concurrent(
+            [(weights[n], *fac[Hof[n]], 0.5, 0, 0) for n in mine]))
+        ctx.launches += sum(5 * ((shape[n][1] + 127) // 128) for n in mine)
+    parallel.prune_linears_task_parallel([weights[n] for n in names], run, ctx.rank, ctx.world)
     return None
 
 
 def run_step(ctx, method, weights, inputs):
+    shared = method.endswith("_shared")
+    if shared:
+        method = method[:-len("_shared")]
     if method == "sparsegpt":
-        return step_sparsegpt(ctx, weights, inputs)
+        return step_sparsegpt(ctx, weights, inputs, shared)
     if method in ("dsnot", "dsnot_elided"):
         return step_dsnot(ctx, weights, inputs, elide=method == "dsnot_elided")
-    return step_wanda(ctx, weights, inputs, method)
+    return step_wanda(ctx, weights, inputs, method, shared)
 
 
-GRAPH_METHODS = ("wanda_nm", "wanda_unstructured", "dsnot", "dsnot_elided")   # no host round trip inside the step (SparseGPT's
+GRAPH_METHODS = ("wanda_nm", "wanda_unstructured", "dsnot", "dsnot_elided", "wanda_nm_shared")   # no host round trip inside the step (SparseGPT's
                                                                 # conditional damping reads a status word)
 
 
@@ -397,8 +420,8 @@ def roofline_of(res, pk):
         "wanda_select": ("hbm", "nm_kernel / rowselect_kernel: 5 B per weight"),
         "dsnot_refine": ("hbm", "dsnot_walk_kernel + dsnot_apply_kernel: 7 B per weight (latency-bound, see DESIGN.md)"),
         "hessian_accum": ("tensor", "hessian_syrk_kernel (vlmc_hessian_accum): 2*T*C^2 logical flop per call (SYRK executes half)"),
-        "chol_inv_upper": ("tensor", "blocked Cholesky + triangular inverse, 2/3 C^3 flop per Hessian (fp32 SIMT GEMMs today)"),
-        "obs_sweep": ("tensor", "OBS block sweep + trailing fp32 GEMM: R*C^2 flop per linear (fp32 SIMT GEMM today)"),
+        "chol_inv_upper": ("tensor", "blocked Cholesky + triangular inverse (3xTF32 tcgen05 GEMMs, the chains of the block run concurrently): 2/3 C^3 flop per Hessian"),
+        "obs_sweep": ("tensor", "OBS block sweeps + trailing 3xTF32 tcgen05 GEMMs (the chains of the block run concurrently): R*C^2 flop per linear"),
     }[tag]
     bound, desc = info
     if bound == "hbm":
@@ -489,6 +512,9 @@ def run_e2e(torch, native, parallel, dev, args, rank, world, dev_inputs):
     from vlmc.compression.pruners.sparsegpt_pruner import SparseGPT
     from vlmc.compression.pruners import dsnot_pruner
     method = args.method
+    shared = method.endswith("_shared")
+    if shared:
+        method = method[:-len("_shared")]
     elide = method == "dsnot_elided"
     if elide:
         method = "dsnot"
@@ -546,7 +572,7 @@ def run_e2e(torch, native, parallel, dev, args, rank, world, dev_inputs):
                     ready = torch.cuda.Event()
                     ready.record(copy_stream)
                 main.wait_event(ready)
-                for u in users:                      # per-linear API: each linear reads the chunk itself
+                for u in (users[:1] if shared else users):   # per-linear API: each linear reads the chunk itself
                     if method == "dsnot":            # one reference call per sequence (var is a mean of per-call variances)
                         for q in range(n):
                             wrappers[u].add_batch(b[q:q + 1], None)
@@ -554,13 +580,23 @@ def run_e2e(torch, native, parallel, dev, args, rank, world, dev_inputs):
                         wrappers[u].add_batch(b[:n], None)
                 free[ci % 2] = torch.cuda.Event()
                 free[ci % 2].record(main)
-        for name, R, C, _ in LINEARS:
-            wr = wrappers[name]
-            if method == "sparsegpt":
-                wr.fasterprune(0.5, percdamp=0.01, blocksize=128)
+        if method == "sparsegpt":         # the block's chains run concurrently (sparsegpt_pruner.fasterprune_block)
+            from vlmc.compression.pruners.sparsegpt_pruner import fasterprune_block
+            ws = [wrappers[name] for name, *_ in LINEARS]
+            if shared:                    # what layerwise.InputSharing does in the driver: followers adopt the leader's H
+                for leader, members in stat_groups(True):
+                    for m in members[1:]:
+                        wrappers[m].H = wrappers[leader].H
+            fasterprune_block(ws, [0.5] * len(ws), percdamp=0.01, blocksize=128)
+            for wr, (name, *_) in zip(ws, LINEARS):
                 wr.free()
                 host_out_w[name].copy_(wr.layer.weight.data, non_blocking=True)
-                continue
+            return
+        for name, R, C, _ in LINEARS:
+            wr = wrappers[name]
+            if shared and method != "sparsegpt":
+                lead = next(l for l, ms in stat_groups(True) if name in ms)
+                wr.scaler_row, wr.nsamples = wrappers[lead].scaler_row, wrappers[lead].nsamples
             if method == "dsnot":
                 dsnot_pruner.dsnot_prune_linear(wr.layer, wr, 0.6, elide_noop_swaps=elide)
             elif method == "wanda_nm":
@@ -710,6 +746,8 @@ def cpu_block_seconds(method, threads, budget="small"):
     whole block.  Returns (seconds per block, description of the sample)."""
     import torch
     from oracle import cpu_port
+    if method.endswith("_shared"):        # the reference has no such mode: its per-linear schedule is the baseline
+        method = method[:-len("_shared")]
     if method == "dsnot_elided":
         method = "dsnot"
     torch.set_num_threads(threads)

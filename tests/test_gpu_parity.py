@@ -859,3 +859,74 @@ def test_obs_row_shards_in_lockstep_equal_the_unsharded_sweep(native):
                                              hist.data_ptr(), ws.data_ptr(), ws.numel(), st) == 0
     torch.cuda.synchronize()
     assert torch.equal(W, Wfull) and torch.equal(keep, keep_full)
+
+
+# ------------------------------------------------------------------------------------------- block-level scheduling
+def test_sparsegpt_block_concurrent_equals_one_by_one(native):
+    """vlmc.schedule: the factorisation + sweep chains of a block on concurrent streams (one H shared by two linears,
+    one H that is NOT positive definite and needs the reference's damping retries) give bit for bit the weights of
+    SparseGPT.fasterprune called one linear after the other."""
+    from vlmc.compression.pruners.sparsegpt_pruner import SparseGPT, fasterprune_block
+    specs = [(192, 256, 1024, "q"), (320, 256, 1024, "q"), (96, 512, 2048, "o"), (128, 384, 96, "bad")]   # R, C, T, input id
+    xs = {}
+    for R, C, T, inp in specs:
+        if inp not in xs:
+            xs[inp] = acts(T, C, 900 + C + T, torch.float16).cuda()
+
+    def build(shared):
+        ws = []
+        for i, (R, C, T, inp) in enumerate(specs):
+            lin = torch.nn.Linear(C, R, bias=False).cuda().half()
+            lin.weight.data.copy_(weights(R, C, 500 + i, torch.float16, 0.05))
+            w = SparseGPT(lin)
+            w.add_batch(xs[inp].unsqueeze(0))
+            ws.append(w)
+        if shared:          # what layerwise.InputSharing does: the second "q" linear adopts the first one's H
+            ws[1].H = ws[0].H
+        return ws
+
+    ref = build(False)
+    for w in ref:
+        w.fasterprune(0.5, percdamp=0.01, blocksize=128)
+    for shared in (False, True):
+        got = build(shared)
+        fasterprune_block(got, [0.5] * len(got), percdamp=0.01, blocksize=128)
+        for a, b in zip(ref, got):
+            assert torch.equal(a.layer.weight.data, b.layer.weight.data)
+            assert abs(a.layer.weight.importance_score - b.layer.weight.importance_score) <= 1e-6 * abs(a.layer.weight.importance_score)
+    assert bool((ref[3].layer.weight.data == 0).float().mean() > 0.45)
+
+
+@pytest.mark.parametrize("name", ["blipt5_wanda_pruner", "blipt5_dsnot_pruner", "blipt5_sparsegpt_pruner"])
+def test_shared_inputs_give_the_per_linear_result(native, name, monkeypatch):
+    """Driver level: q/k/v and gate/up of the toy LLaMA layer are fed the same tensor; with share_inputs
+    the statistics kernel runs once per distinct input and the followers adopt the leader's state.  Weights and masks
+    must equal the per-linear schedule bit for bit, and the kernel must really have run fewer times."""
+    import toy_model
+    import vlmc.compression as comp
+    calls = {"n": 0}
+    target = {"blipt5_wanda_pruner": "sqnorm_accum", "blipt5_dsnot_pruner": "dsnot_stats",
+              "blipt5_sparsegpt_pruner": "hessian_accum"}[name]
+    real = getattr(native, target)
+
+    def counted(*a, **k):
+        calls["n"] += 1
+        return real(*a, **k)
+    monkeypatch.setattr(native, target, counted)
+    out = {}
+    for share in (False, True):
+        calls["n"] = 0
+        model = toy_model.ToyBlip(d_llm=296, ff=488, n_llm=2, n_vit=0).eval().cuda()
+        pruner = comp.load_pruner(name, model, toy_model.toy_batches(6, device="cuda"),
+                                  cfg=toy_model.pruner_cfg(0.4, 1.0, share_inputs=share))
+        model, _ = pruner.prune()
+        out[share] = (calls["n"], {k: v.detach().clone() for k, v in model.state_dict().items()},
+                      {n: m.mask.clone() for n, m in model.named_modules() if hasattr(m, "mask") and torch.is_tensor(m.mask)})
+    n_per, sd_per, masks_per = out[False]
+    n_shared, sd_shared, masks_shared = out[True]
+    assert n_per == 2 * 6 * 7 and n_shared == 2 * 6 * 4          # layers x samples x (linears | distinct inputs)
+    for k in sd_per:
+        assert torch.equal(sd_per[k], sd_shared[k]), k
+    assert masks_per.keys() == masks_shared.keys()
+    for k in masks_per:
+        assert torch.equal(masks_per[k], masks_shared[k]), k

@@ -73,3 +73,53 @@ def test_factorisation_assignment_is_balanced_and_deterministic():
         load = [sum(c ** 3 for c, o in zip(cols, owner) if o == r) for r in range(world)]
         assert max(load) == 11008 ** 3 or world == 1           # the big one is alone as soon as there are 2 ranks
     assert parallel.row_range(10, 0, 4) == (0, 3) and parallel.row_range(10, 3, 4) == (8, 10)
+
+
+def test_input_sharing_routes_by_tensor_identity():
+    """layerwise.InputSharing: a linear is a follower only when it sees the very tensor its leader saw (same storage,
+    shape, strides, dtype, version); equal VALUES at another address, a view with other strides or an in-place update
+    in between must not share.  The grouping is fixed by the first sample and must not change afterwards."""
+    import pytest
+    import torch
+    from vlmc.compression.pruners.layerwise import InputSharing, adopt_statistics
+    sh = InputSharing()
+    h = torch.randn(1, 6, 8)
+    sh.begin_forward()
+    assert sh.route("q", h) and not sh.route("k", h) and not sh.route("v", h)
+    assert sh.route("o", h.clone())                      # equal values, other storage
+    assert sh.route("t", h.transpose(1, 2))              # same storage, other shape / strides
+    h.add_(1.0)                                          # in-place update bumps the version counter
+    assert sh.route("gate", h) and not sh.route("up", h)
+    assert sh.leader == {"k": "q", "v": "q", "up": "gate"}
+    sh.begin_forward()                                   # next sample: same grouping is fine ...
+    h2 = torch.randn(1, 6, 8)
+    assert sh.route("q", h2) and not sh.route("k", h2)
+    with pytest.raises(RuntimeError):                    # ... a follower that suddenly sees its own tensor is not
+        sh.route("v", torch.randn(1, 6, 8))
+
+    class Wrap:
+        pass
+    lead, fol = Wrap(), Wrap()
+    lead.scaler_row, lead.nsamples = torch.ones(8), 3
+    fol.scaler_row, fol.nsamples = torch.zeros(8), 0
+    adopt_statistics(fol, lead)
+    assert fol.scaler_row is lead.scaler_row and fol.nsamples == 3 and fol._shared is lead._shared
+
+
+def test_linear_assignment_spreads_the_chains():
+    """parallel.assign_linears (SparseGPT on several GPUs: whole linears per rank): deterministic, every linear owned,
+    the longest chain (down_proj, C = 11008) alone on its rank once there are enough ranks."""
+    from vlmc import parallel
+    shapes = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
+    for world in (1, 2, 3, 4, 8):
+        own = parallel.assign_linears(shapes, world)
+        assert own == parallel.assign_linears(shapes, world)
+        assert len(own) == 7 and all(0 <= o < world for o in own)
+        if world >= 4:
+            assert own.count(own[6]) == 1
+        if world >= 7:
+            assert len(set(own)) == 7
+    loads = [0.0, 0.0]
+    for s, o in zip(shapes, parallel.assign_linears(shapes, 2)):
+        loads[o] += parallel.chain_cost_ms(*s)
+    assert max(loads) / sum(loads) < 0.6

@@ -157,6 +157,37 @@ def _sparsegpt(rank, out):
     out[rank] = "ok"
 
 
+def _sparsegpt_linears(rank, out):
+    """Whole linears per rank (vlmc.parallel.prune_linears_task_parallel): every linear is pruned by exactly one rank,
+    by the unsharded algorithm, and every rank ends up with every pruned weight."""
+    from oracle import oracle
+    from vlmc import parallel
+    g = torch.Generator().manual_seed(11)
+    shapes = [(24, 128), (40, 128), (16, 256)]
+    Ws, Hs = [], []
+    for R, C in shapes:
+        X = torch.randn(4 * C, C, generator=g).numpy().astype(np.float64)
+        Hs.append((X.T @ X * (2.0 / 4)).astype(np.float32))
+        Ws.append((torch.randn(R, C, generator=g) * 0.05).numpy().astype(np.float32))
+    refs = []
+    for W, H in zip(Ws, Hs):
+        U, dead, _ = oracle.sparsegpt_inverse_factor(H.copy())
+        refs.append(oracle.sparsegpt_fasterprune(W, "f32", None, 0.5, U=U, dead=dead)[0])
+    Wt = [torch.from_numpy(W.copy()) for W in Ws]
+    ran = []
+
+    def run(indices):
+        for i in indices:
+            ran.append(i)
+            U, dead, _ = oracle.sparsegpt_inverse_factor(Hs[i].copy())
+            Wt[i].copy_(torch.from_numpy(oracle.sparsegpt_fasterprune(Ws[i], "f32", None, 0.5, U=U, dead=dead)[0]))
+    owners = parallel.prune_linears_task_parallel(Wt, run, rank, WORLD)
+    assert sorted(ran) == [i for i, o in enumerate(owners) if o == rank] and len(set(owners)) == WORLD
+    for W, ref in zip(Wt, refs):
+        assert np.array_equal(W.numpy(), ref)
+    out[rank] = "ok"
+
+
 def _dsnot(rank, out):
     from oracle import oracle
     from vlmc import parallel
@@ -186,6 +217,6 @@ def _dsnot(rank, out):
     out[rank] = "ok"
 
 
-@pytest.mark.parametrize("fn", ["_wanda", "_wanda_packed", "_sparsegpt", "_dsnot"])
+@pytest.mark.parametrize("fn", ["_wanda", "_wanda_packed", "_sparsegpt", "_sparsegpt_linears", "_dsnot"])
 def test_two_ranks(fn, built_lib):
     _run(fn)

@@ -46,6 +46,54 @@ class _StopForward(ValueError):
     pass
 
 
+class InputSharing:
+    """Linears of a block that are fed THE SAME tensor (q/k/v, gate/up, wi_0/wi_1, cross-attention k/v) have identical
+    statistics; the reference accumulates each of them separately (one hook per linear, wanda_pruner.py:300-311).
+    Here the first linear that sees a tensor (the leader) runs the kernel and the others adopt its state after the
+    pass: one read of X - and, for SparseGPT, one Hessian and one factorisation - per distinct input.
+    Same tensor = same storage address, shape, strides, dtype and version counter while a reference to the leader's
+    tensor is held (so the allocator cannot hand the address to another activation).  Results are bit-identical to
+    per-linear accumulation because the same kernel would read the same bytes."""
+
+    def __init__(self):
+        self.seen = []          # this forward pass: (tensor, version, leader name)
+        self.leader = {}        # follower name -> leader name, fixed by the first pass
+        self.leaders = set()
+
+    def begin_forward(self):
+        self.seen = []
+
+    def route(self, name, x):
+        """True when `name` must accumulate x itself, False when a leader already did."""
+        found = None
+        for t, ver, lead in self.seen:
+            if (t.data_ptr() == x.data_ptr() and t.shape == x.shape and t.stride() == x.stride()
+                    and t.dtype == x.dtype and t._version == ver):
+                found = lead
+                break
+        if found is None:
+            self.seen.append((x, x._version, name))
+            if name in self.leader:
+                raise RuntimeError(f"{name} shared its input with {self.leader[name]} on an earlier sample but not now")
+            self.leaders.add(name)
+            return True
+        if name in self.leaders or self.leader.setdefault(name, found) != found:
+            raise RuntimeError(f"the input sharing of {name} changed between calibration samples")
+        return False
+
+
+def adopt_statistics(follower, leader):
+    """The follower wrapper takes the leader's accumulated state BY REFERENCE (same tensors)."""
+    for attr in ("scaler_row", "nsamples", "sum_metric_row", "mean", "var", "ntokens", "H"):
+        if hasattr(leader, attr):
+            setattr(follower, attr, getattr(leader, attr))
+    group = getattr(leader, "_shared", None)
+    if group is None:
+        group = {}
+        leader._shared = group
+    follower._shared = group
+
+
 def capture_block_inputs(pruner, model, dataloader, model_prefix, n_samples, module_to_process, lora_model, vit):
     """Swap block 0 for a catcher and run the model until n_samples inputs are recorded.
 
@@ -109,8 +157,12 @@ def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_s
     n_samples = min(n_samples, len(inps))
     layers = get_module_recursive(model, module_to_process)
 
+    share = InputSharing() if getattr(pruner, "share_inputs", True) else None
+
     def run_block(layer):
         for j in range(n_samples):
+            if share is not None:
+                share.begin_forward()
             with torch.no_grad():
                 ctx = model.maybe_autocast() if vit else model.maybe_autocast(dtype=torch.bfloat16)
                 with ctx:
@@ -121,12 +173,22 @@ def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_s
         layer = layers[i]
         subset = find_layers(layer)
         wrapped = {name: make_wrapper(subset[name]) for name in subset}
-        handles = [subset[name].register_forward_hook(
-            (lambda nm: lambda _, inp, out: wrapped[nm].add_batch(inp[0].data, out.data))(name))
-            for name in wrapped]
+        if share is not None:
+            share.leader, share.leaders = {}, set()
+
+        def make_hook(nm):
+            def hook(_, inp, out):
+                if share is None or share.route(nm, inp[0]):
+                    wrapped[nm].add_batch(inp[0].data, out.data)
+            return hook
+        handles = [subset[name].register_forward_hook(make_hook(name)) for name in wrapped]
         run_block(layer)
         for h in handles:
             h.remove()
+        if share is not None:
+            share.begin_forward()                       # drop the references to the last sample's activations
+            for follower, leader in share.leader.items():
+                adopt_statistics(wrapped[follower], wrapped[leader])
         for name in subset:
             key = f"{module_to_process}.{i}.{name}.weight"
             prune_linear(i, name, subset[name], wrapped[name], sparsity_ratio[key],

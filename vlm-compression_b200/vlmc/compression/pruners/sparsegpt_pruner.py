@@ -3,13 +3,16 @@
   SparseGPT.add_batch    <- :68-79    H accumulation on the tensor cores (vlmc_hessian_accum, K3)
   SparseGPT.fasterprune  <- :81-215   dead channels + conditional damping loop (host, like the reference) around
                                       vlmc_chol_inv_upper (K10) and vlmc_obs_sweep (K11-K13)
+  fasterprune_block      <- :441-452  the reference's `for name in subset: fasterprune; free` loop: the chains of the
+                                      block's linears are independent and run concurrently (vlmc.schedule), linears
+                                      that share their input share one H and one factor
   BLIPT5LayerSparseGPTPruner <- :1005-1091, registered as "blipt5_sparsegpt_pruner"; also drives
                                       llm_model.model.layers, which the reference cannot
 """
 import torch
 import torch.nn as nn
 
-from vlmc import native
+from vlmc import native, schedule
 from vlmc.common.registry import registry
 from vlmc.compression.pruners.wanda_pruner import BLIPT5LayerWandaPruner
 
@@ -36,13 +39,19 @@ class SparseGPT:
     def fasterprune(self, sparsity, prune_n=0, prune_m=0, blocksize=128, percdamp=.01):
         H = self.H
         del self.H
-        damp, dead = native.hessian_prepare(H, percdamp)            # :95-96, :111
-        U = None
-        while True:                                                 # :114-128: damp only after a failed attempt
-            U, status = native.chol_inv_upper(H, U)
-            if status.item() == 0:
-                break
-            native.hessian_add_damp(H, damp)
+        group = getattr(self, "_shared", None)       # set when several linears adopted one H (layerwise.InputSharing)
+        if group is not None and group.get("percdamp") == percdamp and group.get("H") is H:
+            U, dead = group["U"], group["dead"]                     # the same H was factorised for a sibling linear
+        else:
+            damp, dead = native.hessian_prepare(H, percdamp)        # :95-96, :111
+            U = None
+            while True:                                             # :114-128: damp only after a failed attempt
+                U, status = native.chol_inv_upper(H, U)
+                if status.item() == 0:
+                    break
+                native.hessian_add_damp(H, damp)
+            if group is not None:
+                group.update(H=H, U=U, dead=dead, percdamp=percdamp)
         _, score = native.obs_sweep(self.layer.weight.data, U, sparsity, prune_n, prune_m, dead=dead,
                                     blocksize=blocksize)
         setattr(self.layer.weight, "importance_score", score.item())
@@ -50,7 +59,23 @@ class SparseGPT:
 
     def free(self):
         self.H = None
+        self._shared = None
         torch.cuda.empty_cache()
+
+
+def fasterprune_block(wrappers, sparsities, prune_n=0, prune_m=0, blocksize=128, percdamp=.01):
+    """fasterprune for ALL linears of one block (the reference's loop at :441-452), scheduled as concurrent chains:
+    every distinct H is prepared and factorised on its own stream (one host sync for all status words, damping only
+    for the ones that failed, :114-128), then every OBS sweep runs on its own stream.  Per linear the kernels and their
+    order are exactly those of SparseGPT.fasterprune, so the weights are bit-identical to calling it one by one."""
+    items = []
+    for w, sp in zip(wrappers, sparsities):
+        items.append((w.layer.weight.data, w.H, sp, prune_n, prune_m))
+    scores, _ = schedule.sparsegpt_block(items, percdamp, blocksize)
+    for w, v in zip(wrappers, scores.tolist()):
+        setattr(w.layer.weight, "importance_score", v)
+        del w.H
+    torch.cuda.synchronize()                                        # :212
 
 
 @registry.register_pruner("blipt5_sparsegpt_pruner")
@@ -63,9 +88,20 @@ class BLIPT5LayerSparseGPTPruner(BLIPT5LayerWandaPruner):
     def _prune_linear(self, vit, lora_model):
         def fn(i, name, module, wrapper, sparsity, expected_nsamples):
             assert wrapper.nsamples == expected_nsamples
-            wrapper.fasterprune(sparsity, prune_n=self.prune_n, prune_m=self.prune_m, percdamp=0.01, blocksize=128)
-            wrapper.free()
+            self._pending.append((wrapper, sparsity))               # pruned together in finish_block
         return fn
+
+    def finish_block(self, subset, wrapped):
+        pending, self._pending = getattr(self, "_pending", []), []
+        if pending:
+            fasterprune_block([w for w, _ in pending], [s for _, s in pending], prune_n=self.prune_n,
+                              prune_m=self.prune_m, percdamp=0.01, blocksize=128)
+            for w, _ in pending:
+                w.free()
+
+    def _prune(self, *args, **kwargs):
+        self._pending = []
+        return super()._prune(*args, **kwargs)
 
     def prune(self, importance_scores=None, keep_indices_or_masks=None):
         return super().prune(importance_scores, keep_indices_or_masks, lora_model=False)

@@ -68,7 +68,7 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
                  num_samples=64, is_global=False, t5_model_prefix="t5_model", vit_model_prefix="visual_encoder",
                  sparsity_ratio_granularity=None, max_sparsity_per_layer=0.8, score_method="obd_avg",
                  num_data_first_stage=128, num_noise=1, sparsity_dict=None, noise_eps=1e-3,
-                 prune_per_model=False, peft_postfix="", prune_n=0, prune_m=0, **kwargs):
+                 prune_per_model=False, peft_postfix="", prune_n=0, prune_m=0, share_inputs=True, **kwargs):
         super().__init__(model=model, data_loader=data_loader, prune_spec=None, is_strct_pruning=is_strct_pruning,
                          importance_scores_cache=importance_scores_cache,
                          keep_indices_or_masks_cache=keep_indices_or_masks_cache, is_global=is_global,
@@ -88,6 +88,9 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
         self.t5_model_prefix = t5_model_prefix
         self.vit_model_prefix = vit_model_prefix
         self._pending_scores = []
+        # linears fed by the same tensor accumulate their statistics once (layerwise.InputSharing); False restores
+        # the reference's one-accumulation-per-linear schedule.  The results are identical either way.
+        self.share_inputs = share_inputs
 
     # ---- hooks the shared block loop calls ------------------------------------------------------
     def forward_to_cache(self, model, batch, lora_model=False):

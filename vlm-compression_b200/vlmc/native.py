@@ -287,13 +287,14 @@ def hessian_accum(x, H, n_before, b, kc=0, slab_tokens=0):
     _check("vlmc_hessian_accum", st)
 
 
-def hessian_prepare(H, percdamp):
-    """sparsegpt_pruner.py:95-96,111: fix dead channels in place; returns (damp 1-elem tensor, dead uint8 [C])."""
+def hessian_prepare(H, percdamp, damp=None, dead=None):
+    """sparsegpt_pruner.py:95-96,111: fix dead channels in place; returns (damp 1-elem tensor, dead uint8 [C]).
+    damp / dead may be passed in (callers that run on a side stream allocate them on the main one)."""
     _require_cuda(H)
     lib = load()
     C = H.shape[0]
-    damp = torch.empty(1, dtype=torch.float32, device=H.device)
-    dead = torch.empty(C, dtype=torch.uint8, device=H.device)
+    damp = torch.empty(1, dtype=torch.float32, device=H.device) if damp is None else damp
+    dead = torch.empty(C, dtype=torch.uint8, device=H.device) if dead is None else dead
     with torch.cuda.device(H.device):
         st = lib.vlmc_hessian_prepare(H.data_ptr(), C, H.stride(0), float(percdamp), damp.data_ptr(), dead.data_ptr(),
                                       _stream(H))
@@ -309,7 +310,7 @@ def hessian_add_damp(H, damp):
     _check("vlmc_hessian_add_damp", st)
 
 
-def chol_inv_upper(H, U=None):
+def chol_inv_upper(H, U=None, status=None):
     """K10: returns (U, status tensor).  status.item() == NOT_POSDEF means: damp and retry."""
     _require_cuda(H)
     lib = load()
@@ -318,7 +319,8 @@ def chol_inv_upper(H, U=None):
         raise ValueError("H must be a float32 [C, C] row-major matrix")
     if U is None:
         U = torch.empty((C, C), dtype=torch.float32, device=H.device)
-    status = torch.zeros(1, dtype=torch.int32, device=H.device)
+    if status is None:       # the kernel clears it first
+        status = torch.empty(1, dtype=torch.int32, device=H.device)
     ws = workspace(H, lib.vlmc_workspace_bytes(OP_CHOL, C, 0, 0))
     with torch.cuda.device(H.device):
         st = lib.vlmc_chol_inv_upper(H.data_ptr(), C, H.stride(0), U.data_ptr(), U.stride(0), status.data_ptr(),
@@ -344,15 +346,18 @@ def gemm_tf32x3(A, B, C=None, alpha=1.0, beta=0.0, b_nk=False, tri=False, kc=0):
     return C
 
 
-def obs_sweep(W, U, sparsity, prune_n=0, prune_m=0, dead=None, blocksize=128, want_mask=False):
-    """K11-K13 (sparsegpt_pruner.py:160-215), in place on W.  Returns (keep_mask or None, importance 1-elem tensor)."""
+def obs_sweep(W, U, sparsity, prune_n=0, prune_m=0, dead=None, blocksize=128, want_mask=False, score=None, keep=None):
+    """K11-K13 (sparsegpt_pruner.py:160-215), in place on W.  Returns (keep_mask or None, importance 1-elem tensor).
+    score / keep may be passed in (pre-allocated outputs)."""
     _require_cuda(W, U, dead)
     if W.dim() != 2 or W.stride(1) != 1:
         raise ValueError("W must be a 2-D row-major weight")
     lib = load()
     R, C = W.shape
-    keep = torch.empty((R, C), dtype=torch.bool, device=W.device) if want_mask else None
-    score = torch.empty(1, dtype=torch.float32, device=W.device)
+    if keep is None and want_mask:
+        keep = torch.empty((R, C), dtype=torch.bool, device=W.device)
+    if score is None:
+        score = torch.empty(1, dtype=torch.float32, device=W.device)
     ws = workspace(W, lib.vlmc_workspace_bytes(OP_OBS, R, C, blocksize))
     with torch.cuda.device(W.device):
         st = lib.vlmc_obs_sweep(W.data_ptr(), _dtype(W), R, C, W.stride(0), U.data_ptr(), U.stride(0),

@@ -151,6 +151,42 @@ def assign_factorisations(columns, world):
     return owner
 
 
+def chain_cost_ms(R, C):
+    """Rough duration of one linear's SparseGPT chain on one B200 (measured, r01): the blocked Cholesky + triangular
+    inverse (latency-bound panels: 4.1 ms at C=4096, 20.6 ms at C=11008) plus the OBS sweep (C/128 dependent blocks of
+    ~0.13 ms, wider with more rows).  Only the ORDER of the costs matters for the assignment."""
+    return 4.1 * (C / 4096.0) ** 1.63 + 0.13 * ((C + 127) // 128) * max(1.0, R / 4096.0) ** 0.5
+
+
+def assign_linears(shapes, world):
+    """Which rank runs the factorisation + sweep chain of which linear: longest-processing-time-first on
+    chain_cost_ms.  shapes: [(R, C)] in layer order.  Returns a list of owner ranks, deterministic on every rank."""
+    load = [0.0] * world
+    owner = [0] * len(shapes)
+    for i in sorted(range(len(shapes)), key=lambda i: (-chain_cost_ms(*shapes[i]), i)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        owner[i] = r
+        load[r] += chain_cost_ms(*shapes[i])
+    return owner
+
+
+def prune_linears_task_parallel(weights, run_fn, rank, world, group=None, extra=None):
+    """SparseGPT phase 2 + 3 on several GPUs: WHOLE linears are spread over the ranks (assign_linears) - each chain
+    (factorisation, then column-block sweep) stays on one GPU, so nothing is exchanged per column block and no factor
+    travels - and the pruned weights are broadcast from their owners.  run_fn(indices) prunes weights[i] in place for
+    the linears this rank owns.  extra: optional list of per-linear tensors (masks) broadcast alongside.
+    Returns the owner list."""
+    owners = assign_linears([tuple(w.shape) for w in weights], world)
+    mine = [i for i, o in enumerate(owners) if o == rank]
+    if mine:
+        run_fn(mine)
+    for i, o in enumerate(owners):
+        broadcast_from(weights[i], o, group)
+        if extra is not None and extra[i] is not None:
+            broadcast_from(extra[i], o, group)
+    return owners
+
+
 def allreduce_sum(t, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)

@@ -1,0 +1,117 @@
+"""Stream-level scheduling of the independent chains of one transformer block.
+
+The reference prunes the linears of a block one after the other (sparsegpt_pruner.py:441-452: for name in subset:
+fasterprune; free).  Each SparseGPT.fasterprune is a SEQUENTIAL chain - blocked Cholesky (C/128 dependent panels),
+then the column-block OBS sweep (C/128 dependent blocks) - whose kernels are small (one CTA for a diagonal block, a
+few dozen tiles for a panel) and leave most of the 148 SMs idle.  The chains of different linears are independent
+of each other, so here they run CONCURRENTLY, one CUDA stream per chain, forked from and joined to the caller's
+stream with events.  Nothing about the arithmetic changes: the same kernels in the same per-chain order, so the
+results are bit-identical to the one-after-the-other schedule (tests/test_gpu_parity.py).
+
+  factor_concurrent    all distinct Hessians of a block: dead channels + damp value + chol_inv_upper, ONE host
+                       sync for all status words, the reference's damp-and-retry loop (:114-128) only for the
+                       ones that failed
+  sweep_concurrent     all OBS sweeps of a block
+  sparsegpt_block      both, for a list of (W, H) items whose H may be shared (q/k/v, gate/up): factorised once
+
+Outputs that outlive the fork (U, dead, scores) are allocated on the caller's stream BEFORE the fork, so the caching
+allocator never hands their memory to another stream; per-stream scratch comes from native.workspace (keyed by stream).
+"""
+import torch
+
+from vlmc import native
+
+_pools = {}
+
+
+def side_streams(device, n):
+    """n persistent side streams of `device` (created once: native.workspace keys its scratch by stream)."""
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    pool = _pools.setdefault(idx, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
+class Fork:
+    """with Fork(device, n) as f:  for i in range(n): with f.stream(i): ...enqueue chain i...
+    On exit the caller's stream waits for every side stream."""
+
+    def __init__(self, device, n):
+        self.device = torch.device(device)
+        self.n = n
+
+    def __enter__(self):
+        self.main = torch.cuda.current_stream(self.device)
+        self.streams = side_streams(self.device, self.n)
+        start = torch.cuda.Event()
+        start.record(self.main)
+        for s in self.streams:
+            s.wait_event(start)
+        return self
+
+    def stream(self, i):
+        return torch.cuda.stream(self.streams[i % self.n])
+
+    def __exit__(self, *exc):
+        for s in self.streams:
+            done = torch.cuda.Event()
+            done.record(s)
+            self.main.wait_event(done)
+        return False
+
+
+def factor_concurrent(Hs, percdamp=0.01, Us=None, max_retries=64):
+    """[(U, dead)] for a list of DISTINCT Hessians (each modified in place like the reference: dead diagonal -> 1,
+    damping added only after a failed attempt, sparsegpt_pruner.py:95-96,111-128).  Us: optional output buffers."""
+    dev = Hs[0].device
+    n = len(Hs)
+    Us = [torch.empty_like(H) for H in Hs] if Us is None else Us
+    damps = torch.empty(n, dtype=torch.float32, device=dev)
+    status = torch.empty(n, dtype=torch.int32, device=dev)
+    deads = [torch.empty(H.shape[0], dtype=torch.uint8, device=dev) for H in Hs]
+    order = sorted(range(n), key=lambda i: -Hs[i].shape[0])      # longest chain first
+    with Fork(dev, n) as f:
+        for slot, i in enumerate(order):
+            with f.stream(slot):
+                native.hessian_prepare(Hs[i], percdamp, damps[i:i + 1], deads[i])
+                native.chol_inv_upper(Hs[i], Us[i], status[i:i + 1])
+    failed = [i for i, s in enumerate(status.tolist()) if s != 0]      # the ONE host sync of the phase
+    for i in failed:                                                     # :114-128, cumulative damping per retry
+        for _ in range(max_retries):
+            native.hessian_add_damp(Hs[i], damps[i:i + 1])
+            native.chol_inv_upper(Hs[i], Us[i], status[i:i + 1])
+            if status[i].item() == 0:
+                break
+        else:
+            raise RuntimeError("Hessian stayed non-positive-definite after damping")
+    return list(zip(Us, deads))
+
+
+def sweep_concurrent(items, blocksize=128):
+    """items: [(W, U, dead, sparsity, prune_n, prune_m)], W pruned in place (obs_sweep).  Returns the importance
+    scores as one [n] device tensor."""
+    dev = items[0][0].device
+    n = len(items)
+    scores = torch.empty(n, dtype=torch.float32, device=dev)
+    order = sorted(range(n), key=lambda i: -items[i][0].shape[1])
+    with Fork(dev, n) as f:
+        for slot, i in enumerate(order):
+            W, U, dead, sparsity, pn, pm = items[i]
+            with f.stream(slot):
+                native.obs_sweep(W, U, sparsity, pn, pm, dead=dead, blocksize=blocksize, score=scores[i:i + 1])
+    return scores
+
+
+def sparsegpt_block(items, percdamp=0.01, blocksize=128, Us=None):
+    """items: [(W, H, sparsity, prune_n, prune_m)].  Items that hold THE SAME H tensor (linears fed by the same
+    activations) are factorised once.  Returns (scores [n] device tensor, {id(H): (U, dead)})."""
+    distinct, seen = [], {}
+    for _, H, *_ in items:
+        if id(H) not in seen:
+            seen[id(H)] = len(distinct)
+            distinct.append(H)
+    facs = factor_concurrent(distinct, percdamp, Us)
+    scores = sweep_concurrent([(W, *facs[seen[id(H)]], sp, pn, pm) for W, H, sp, pn, pm in items], blocksize)
+    return scores, {id(H): facs[seen[id(H)]] for H in distinct}
