@@ -209,10 +209,12 @@ def step_wanda(ctx, weights, inputs, method, shared=False):
         # phase 2, n:m: a group decision needs its m scores and nothing else, and the pruned weights + masks must end
         # up on EVERY rank anyway (5 B/weight to rewrite the replica) - exactly the traffic of running the selection
         # itself.  So every rank selects on its whole replica: no row split, no exchange, identical results.
-        for name, R, C, _ in LINEARS:
-            masks[name] = ctx.timed("wanda_select", R * C * 5, lambda: native.wanda_nm(weights[name], scalers[name], 2, 4)[0])
-            ctx.launches += 2
-        return masks
+        # ... and all 7 linears go through ONE launch (vlmc_wanda_nm_batch): one ramp-up and one drain per block.
+        names = [n for n, *_ in LINEARS]
+        keeps, _ = ctx.timed("wanda_select", sum(R * C for _, R, C, _ in LINEARS) * 5, lambda: native.wanda_nm_batch(
+            [weights[n] for n in names], [scalers[n] for n in names], 2, 4))
+        ctx.launches += 2
+        return dict(zip(names, keeps))
     if ctx.world > 1 and all(R % ctx.world == 0 for _, R, _, _ in LINEARS):
         # phase 2, per-row top-k, sharded: select on this rank's rows, ONE all-gather of the bit-packed masks of all 7
         # linears, the other rows of the replicated weights are zeroed locally from the received bits
@@ -374,7 +376,8 @@ def time_method(ctx, method, inputs, steps, warmup, sample_clocks, dist, use_gra
         k["spans"] += 1
     ctx.events = None
     out = {"ms_per_step": eager_ms, "eager_ms_per_step": eager_ms, "launches": ctx.launches, "kernels": kern,
-           "clocks": clocks, "steps": steps, "cuda_graph": False, "weight_sets": nsets}
+           "clocks": clocks, "steps": steps, "cuda_graph": False, "weight_sets": nsets, "world": ctx.world,
+           "calib_batch": ctx.calib_batch, "shared": method.endswith("_shared")}
 
     # ---- pass B: CUDA graphs
     if use_graph and method in GRAPH_METHODS:
@@ -390,6 +393,13 @@ def time_method(ctx, method, inputs, steps, warmup, sample_clocks, dist, use_gra
                     run_step(ctx, method, w, inputs)
                 pool = g.pool()
                 graphs.append(g)
+            # the first launch of an instantiated graph uploads it to the device: do that outside the timed region,
+            # then restore the weights the warm replay pruned (the selection kernels are data dependent)
+            for g in graphs:
+                g.replay()
+            for si, w in enumerate(wsets):
+                for name, t in make_block(torch, ctx.dev, seed=100 + si).items():
+                    w[name].copy_(t)
             barrier()
             sampler = ClockSampler(ctx.dev.index)
 
@@ -410,6 +420,22 @@ def time_method(ctx, method, inputs, steps, warmup, sample_clocks, dist, use_gra
     return out
 
 
+def ncu_traffic(tag, res):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/ncu_traffic.json),
+    averaged over the launches of one step; None when no capture matches the timed launches."""
+    if tag != "sqnorm_accum" or res.get("world", 1) != 1 or res.get("calib_batch") != N_SEQ:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            cap = json.load(f)["sqnorm_accum"]["bytes_per_launch"]
+        dims = [INPUT_DIMS[inp] for _, _, _, inp in LINEARS]
+        if res.get("shared"):
+            dims = list(INPUT_DIMS.values())
+        return sum(cap[f"T{N_SEQ * SEQ_LEN}_C{c}"] for c in dims) / len(dims)
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def roofline_of(res, pk):
     """The span with the largest share of the step -> roofline object (HBM GB/s or tensor TFLOP/s)."""
     total = res["eager_ms_per_step"] * res["steps"]      # spans were timed in the eager pass
@@ -417,7 +443,7 @@ def roofline_of(res, pk):
     info = {
         "sqnorm_accum": ("hbm", "colstats_kernel<half,0> (vlmc_sqnorm_accum): T*C*2 B per launch"),
         "dsnot_stats": ("hbm", "colstats_kernel<half,1> (vlmc_dsnot_stats): T*C*2 B per launch"),
-        "wanda_select": ("hbm", "nm_kernel / rowselect_kernel: 5 B per weight"),
+        "wanda_select": ("hbm", "nm_batch_kernel (all linears of the block in one launch) / rowselect_kernel: 5 B per weight"),
         "dsnot_refine": ("hbm", "dsnot_walk_kernel + dsnot_apply_kernel: 7 B per weight (latency-bound, see DESIGN.md)"),
         "hessian_accum": ("tensor", "hessian_syrk_kernel (vlmc_hessian_accum): 2*T*C^2 logical flop per call (SYRK executes half)"),
         "chol_inv_upper": ("tensor", "blocked Cholesky + triangular inverse (3xTF32 tcgen05 GEMMs, the chains of the block run concurrently): 2/3 C^3 flop per Hessian"),
@@ -431,7 +457,7 @@ def roofline_of(res, pk):
         achieved = k["work"] / (k["ms"] * 1e-3) / 1e12
         peak, unit = pk["tensor"], "TFLOP/s"
     return {"bound": bound, "kernel": desc, "achieved": achieved, "peak": peak, "peak_source": pk["source"],
-            "unit": unit, "frac": achieved / peak if achieved else None, "traffic": None, "spans": k["spans"],
+            "unit": unit, "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(tag, res), "spans": k["spans"],
             "avg_span_ms": k["ms"] / max(k["spans"], 1), "share_of_step": k["ms"] / total,
             "spans_ms_per_step": {t: v["ms"] / res["steps"] for t, v in res["kernels"].items()}}
 
@@ -600,13 +626,19 @@ def run_e2e(torch, native, parallel, dev, args, rank, world, dev_inputs):
             if method == "dsnot":
                 dsnot_pruner.dsnot_prune_linear(wr.layer, wr, 0.6, elide_noop_swaps=elide)
             elif method == "wanda_nm":
-                from vlmc.compression.pruners.wanda_pruner import wanda_prune_linear
-                wanda_prune_linear(wr.layer, wr.scaler_row, 0.5, 2, 4)
+                continue                       # pruned below, the whole block in one launch
             else:
                 from vlmc.compression.pruners.wanda_pruner import wanda_prune_linear
                 wanda_prune_linear(wr.layer, wr.scaler_row, 0.5)
             host_out_w[name].copy_(wr.layer.weight.data, non_blocking=True)
             host_out_m[name].copy_(wr.layer.mask, non_blocking=True)
+        if method == "wanda_nm":
+            from vlmc.compression.pruners.wanda_pruner import wanda_prune_block_nm
+            ws = [wrappers[name] for name, *_ in LINEARS]
+            wanda_prune_block_nm([w.layer for w in ws], [w.scaler_row for w in ws], 2, 4)
+            for wr, (name, *_) in zip(ws, LINEARS):
+                host_out_w[name].copy_(wr.layer.weight.data, non_blocking=True)
+                host_out_m[name].copy_(wr.layer.mask, non_blocking=True)
 
     if world > 1:
         return run_e2e_sharded(torch, native, parallel, dev, args, rank, world, host_in, host_w, host_out_w,
@@ -700,12 +732,14 @@ def full_model_wanda_nm(torch, native, dev, reps=2):
         for linears, nblocks, acts, wts, T in plan:
             for b in range(nblocks):
                 W = wts[b % len(wts)]
+                scal = []
                 for i, (_, R, C, xtag) in enumerate(linears):
                     x = acts[(C, xtag)][use % 3]
                     use += 1
                     s = torch.zeros(C, device=dev, dtype=torch.float32)
                     native.sqnorm_accum(x.view(N_SEQ, -1, C), s, 0, N_SEQ)
-                    native.wanda_nm(W[i], s, 2, 4)
+                    scal.append(s)
+                native.wanda_nm_batch(W, scal, 2, 4)      # the block's linears in one launch
     one_model()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

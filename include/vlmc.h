@@ -116,6 +116,23 @@ int vlmc_wanda_nm(void* W, int dtype, int R, int C, int64_t ldw,
                   void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * K4+K6 for ALL linears of one transformer block in one launch (the per-block loop at
+ * wanda_pruner.py:313-347 calls the selection once per linear; the matrices are 34-90 MB, so launched one by one
+ * the kernels are short enough for ramp-up and drain to cost a third of their time).  `items` is a HOST array of
+ * `count` (<= 16) descriptors, read during the call; every pointer inside is a device pointer.  Same results as
+ * `count` calls of vlmc_wanda_nm (score_mean up to fp32 summation order).  score_mean may be NULL per item.
+ */
+typedef struct vlmc_select_item {
+  void* W; int64_t ldw; int R; int C;
+  const float* scaler_row;      /* [C] fp32, 16-byte aligned */
+  uint8_t* keep_mask; int64_t ldm;
+  float* score_mean;            /* 1 float or NULL */
+} vlmc_select_item;
+size_t vlmc_wanda_nm_batch_workspace_bytes(const vlmc_select_item* items, int count, int dtype, int m);
+int vlmc_wanda_nm_batch(const vlmc_select_item* items, int count, int dtype, int n, int m, int zero_w,
+                        void* ws, size_t ws_bytes, void* stream);
+
+/*
  * K4+K7  Wanda score + whole-matrix threshold (ViT path).  Replaces wanda_pruner.py:682-683:
  *   thres = sort(S.flatten())[k_global];  prune S < thres   (strict: ties are kept)
  * k_global = int(R * C * p) computed by the caller.

@@ -1,0 +1,11 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1
+tail -15 gpurun_out/pytest_gpu.log
+timeout 300 python scripts/stats_probe.py > gpurun_out/stats_probe.log 2>&1
+cat gpurun_out/stats_probe.log
+timeout 300 python scripts/chol_probe.py > gpurun_out/chol_probe.log 2>&1
+cat gpurun_out/chol_probe.log
+timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+tail -c 600 gpurun_out/bench_default.err

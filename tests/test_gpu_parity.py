@@ -916,6 +916,7 @@ def test_shared_inputs_give_the_per_linear_result(native, name, monkeypatch):
     out = {}
     for share in (False, True):
         calls["n"] = 0
+        torch.manual_seed(0)                     # the toy model's biases and norms use the global generator
         model = toy_model.ToyBlip(d_llm=296, ff=488, n_llm=2, n_vit=0).eval().cuda()
         pruner = comp.load_pruner(name, model, toy_model.toy_batches(6, device="cuda"),
                                   cfg=toy_model.pruner_cfg(0.4, 1.0, share_inputs=share))
@@ -930,3 +931,45 @@ def test_shared_inputs_give_the_per_linear_result(native, name, monkeypatch):
     assert masks_per.keys() == masks_shared.keys()
     for k in masks_per:
         assert torch.equal(masks_per[k], masks_shared[k]), k
+
+
+@pytest.mark.parametrize("tag,n,m", [("f16", 2, 4), ("bf16", 4, 8), ("f32", 2, 4), ("f16", 1, 2), ("bf16", 5, 16), ("f32", 3, 8)])
+def test_wanda_nm_batch_equals_per_linear(native, tag, n, m):
+    """vlmc_wanda_nm_batch (all linears of a block in one launch) against vlmc_wanda_nm called per linear: masks and
+    zeroed weights bit for bit, score means to fp32 summation order; ragged shapes (rows not a multiple of the
+    16-row work unit, columns not a multiple of the 1024-column tile) and lora_model (zero_w = 0) included."""
+    shapes = [(48, 1024), (37, 2064), (5, 48), (130, 3120), (16, 16), (257, 1040)]
+    Ws = [weights(R, C, 300 + i, DT[tag], 0.05).cuda() for i, (R, C) in enumerate(shapes)]
+    Ws[1][3].zero_()                                        # an all-zero row: every group is a tie
+    scal = [scaler(C, 40 + i).cuda() for i, (_, C) in enumerate(shapes)]
+    for zero_w in (True, False):
+        ref = []
+        for W, s in zip(Ws, scal):
+            Wc = W.clone()
+            keep, mean = native.wanda_nm(Wc, s, n, m, zero_w=zero_w)
+            ref.append((Wc, keep, mean.item()))
+        Wb = [W.clone() for W in Ws]
+        keeps, means = native.wanda_nm_batch(Wb, scal, n, m, zero_w=zero_w)
+        torch.cuda.synchronize()
+        for (Wr, kr, mr), W, k, mv in zip(ref, Wb, keeps, means.tolist()):
+            assert torch.equal(kr, k) and torch.equal(Wr, W)
+            assert abs(mv - mr) <= 1e-5 * abs(mr)
+            assert bool((k.view(k.shape[0], -1, m).sum(-1) == m - n).all())
+
+
+def test_wanda_nm_batch_vicuna_block(native):
+    """The 7 linears of a Vicuna-7B layer in one launch: 2:4 structure everywhere, pruned weights zero, kept weights
+    untouched, and the per-linear kernel agrees."""
+    shapes = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Ws = [(torch.randn(R, C, device="cuda", generator=g) * 0.02).half() for R, C in shapes]
+    scal = [scaler(C, 60 + i).cuda() for i, (_, C) in enumerate(shapes)]
+    W0 = [W.clone() for W in Ws]
+    keeps, means = native.wanda_nm_batch(Ws, scal, 2, 4)
+    for W, Wo, k, s in zip(Ws, W0, keeps, scal):
+        assert bool((k.view(k.shape[0], -1, 4).sum(-1) == 2).all())
+        assert bool((W[~k] == 0).all()) and torch.equal(W[k], Wo[k])
+    Wc = W0[6].clone()
+    kr, mr = native.wanda_nm(Wc, scal[6], 2, 4)
+    assert torch.equal(kr, keeps[6]) and torch.equal(Wc, Ws[6])
+    assert abs(means[6].item() - mr.item()) <= 1e-5 * abs(mr.item())

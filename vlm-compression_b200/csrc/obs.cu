@@ -12,11 +12,12 @@
 //                                per-CTA shared-memory histograms flushed to a global one, three stream-ordered
 //                                passes, no sort and no host round trip.  (When rows are sharded over GPUs these
 //                                three 8 KB histograms are the only data exchanged per block)
-//   K12  obs_sweep_kernel        one WARP per weight row, the row's 128 columns in registers (4 per lane), the
+//   K12  obs_sweep4_kernel       four weight rows per warp (8 lanes x 16 registers hold a row's 128 columns), the
 //                                U1 tile in shared memory; the 128 sequential steps broadcast the pivot column by
-//                                shuffle, only pruned columns (err != 0) cost an update.  Writes the finished
-//                                columns to the fp16/bf16 weight, the fp32 working copy, Err1 and the keep mask.
+//                                shuffle inside the lane group.  Writes the finished columns to the fp16/bf16
+//                                weight, the fp32 working copy, Err1 and the keep mask.
 //   K13  the lazy trailing update on the tensor cores: the 3xTF32 tcgen05 GEMM of gemm3x.cu (fp32-grade accuracy).
+#include <cstdlib>
 #include "gemm3x.cuh"
 
 namespace vlmc {
@@ -170,101 +171,193 @@ obs_hist_kernel(const ObsParams p) {
     if (sh[b]) atomicAdd(&p.hist->h[PASS][b], sh[b]);
 }
 
-// K12 (+ the tail of K11): one warp per row
-constexpr int kSweepThreads = 512;   // 16 rows per CTA share one 64 KB U1 tile: 2 CTAs = 32 rows in flight per SM
+// K12 (+ the tail of K11), four rows per warp.  A warp per row is instruction-issue bound: ~60 instructions per
+// column step of bookkeeping that is identical for every row (measured: 39.5 us per 4096-row block).  Here a row belongs to EIGHT lanes
+// (lane l of the group holds the float4s at columns 32 t + 4 l, t = 0..3), so one warp carries four rows through the
+// same 128 steps and the bookkeeping is shared: ~10 instructions per row and step.  The pivot column of every row
+// comes from a shuffle inside its lane group; rows that keep the column run the update with err = 0, which leaves
+// every value bit-identical (w - 0 * u == w), and the whole step is skipped when all four rows keep it.  Column
+// slices that are finished for every row of the warp (t < t0) are skipped statically.  Same arithmetic, same
+// roundings and the same order per row as the reference (:189-205).
+constexpr int kSw4Threads = 256;
+constexpr int kSw4RowsPerCta = (kSw4Threads / 32) * 4;
 
-template <typename T>
-__global__ void __launch_bounds__(kSweepThreads)
-obs_sweep_kernel(const ObsParams p) {
+template <int M>   // 0: unstructured (threshold from the block histograms), else the m of n:m
+__global__ void __launch_bounds__(kSw4Threads, 3)
+obs_sweep4_kernel(const ObsParams p, int dtype, int vec_ok) {
   extern __shared__ __align__(16) float Us[];                  // [kOB][kOB] U1 tile, zero padded
   __shared__ unsigned int s_scan[32];
+  __shared__ float s_d[kOB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bs = p.bs;
-  for (int idx = tid; idx < kOB * kOB / 4; idx += kSweepThreads) {
+  for (int idx = tid; idx < kOB * kOB / 4; idx += kSw4Threads) {
     const int i = idx / (kOB / 4), j = (idx % (kOB / 4)) * 4;
     float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < bs && j < bs) u = *reinterpret_cast<const float4*>(p.U + (int64_t)(p.i1 + i) * p.ldu + p.i1 + j);
+    if (i < bs && j < bs && j + 3 >= i) u = *reinterpret_cast<const float4*>(p.U + (int64_t)(p.i1 + i) * p.ldu + p.i1 + j);
     *reinterpret_cast<float4*>(Us + i * kOB + j) = u;
   }
+  if (tid < kOB) s_d[tid] = tid < bs ? p.U[(int64_t)(p.i1 + tid) * p.ldu + p.i1 + tid] : 1.f;
   uint32_t v = 0;
-  if (p.prune_n == 0) {
+  if (M == 0) {
     unsigned int b1, b2, b3, before, kk = p.kth;
-    obs_find_bin<kSweepThreads>(p.hist->h[0], kk, s_scan, b1, before); kk -= before;
-    obs_find_bin<kSweepThreads>(p.hist->h[1], kk, s_scan, b2, before); kk -= before;
-    obs_find_bin<kSweepThreads>(p.hist->h[2], kk, s_scan, b3, before);
+    obs_find_bin<kSw4Threads>(p.hist->h[0], kk, s_scan, b1, before); kk -= before;
+    obs_find_bin<kSw4Threads>(p.hist->h[1], kk, s_scan, b2, before); kk -= before;
+    obs_find_bin<kSw4Threads>(p.hist->h[2], kk, s_scan, b3, before);
     v = (b1 << 21) | (b2 << 10) | b3;                          // the k-th smallest block score, exactly (:184)
   }
   __syncthreads();
-  const bool act = 4 * lane < bs;
-  const int m = p.prune_m, n = p.prune_n;
+  const int g = lane >> 3, l = lane & 7, gbase = lane & ~7;
+  const int n = p.prune_n;
+  const float4* Us4 = reinterpret_cast<const float4*>(Us);
 
-  for (int row = blockIdx.x * (kSweepThreads / 32) + warp; row < p.R; row += gridDim.x * (kSweepThreads / 32)) {
-    float* w32 = p.W32 + (int64_t)row * p.C + p.i1 + 4 * lane;
-    float w[4] = {0.f, 0.f, 0.f, 0.f};
-    if (act) { const float4 t = *reinterpret_cast<const float4*>(w32); w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w; }
-    uint32_t mbits = 0;                                          // bit e: column 4*lane+e of this row is pruned
-    if (n == 0 && act) {
+  for (int row0 = (blockIdx.x * (kSw4Threads / 32) + warp) * 4; row0 < p.R; row0 += gridDim.x * kSw4RowsPerCta) {
+    const int row = row0 + g;
+    const bool valid = row < p.R;
+    float* w32 = p.W32 + (int64_t)row * p.C + p.i1 + 4 * l;
+    float w[4][4];
+    uint32_t mbits = 0;                                          // bit 4 t + e: column 32 t + 4 l + e of this row is pruned
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float d = Us[(4 * lane + e) * kOB + 4 * lane + e];
-        if (obs_key(w[e], __fmul_rn(d, d)) <= v) mbits |= 1u << e;     // `<=` (:185)
+    for (int t = 0; t < 4; ++t) {
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid && 32 * t + 4 * l < bs) x = *reinterpret_cast<const float4*>(w32 + 32 * t);
+      w[t][0] = x.x; w[t][1] = x.y; w[t][2] = x.z; w[t][3] = x.w;
+      if (M == 0 && valid && 32 * t + 4 * l < bs) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float d = s_d[32 * t + 4 * l + e];
+          if (obs_key(w[t][e], __fmul_rn(d, d)) <= v) mbits |= 1u << (4 * t + e);     // `<=` (:185)
+        }
       }
     }
-    uint32_t word[4];
+    float er[4][4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) word[c] = __ballot_sync(0xffffffffu, (mbits >> c) & 1u);
-    float er[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) er[t][e] = 0.f;
+
+#pragma unroll
+    for (int t0 = 0; t0 < 4; ++t0) {
+      if (32 * t0 < bs) {
 #pragma unroll 1
-    for (int q = 0; q < (bs >> 2); ++q) {
+        for (int li = 0; li < 8; ++li) {
+          const int ib = 32 * t0 + 4 * li;
+          if (ib >= bs) break;
+          if (M >= 8 && (ib % M) == 0) {
+            // n:m over M >= 8 columns: lanes li .. li + M/4 - 1 of every group hold the group's columns in slot t0
+            float kown[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int i = 4 * q + c;
-        if (n != 0 && (i % m) == 0) {
-          // n:m on the compensated weights: the n smallest w^2/d^2 of columns [i, i+m), ties -> lower column (:193-195)
-          float keys[kObsMaxM];
-          for (int a = 0; a < m; ++a) {
-            const int col = i + a, cc = col & 3;
-            const float mine = cc == 0 ? w[0] : (cc == 1 ? w[1] : (cc == 2 ? w[2] : w[3]));
-            const float wa = __shfl_sync(0xffffffffu, mine, col >> 2);
-            const float da = col < bs ? Us[col * kOB + col] : 1.f;
-            keys[a] = col < bs ? __fdiv_rn(__fmul_rn(wa, wa), __fmul_rn(da, da)) : __int_as_float(0x7f800000);
-          }
+            for (int e = 0; e < 4; ++e) {
+              const int col = 32 * t0 + 4 * l + e;
+              const float d = s_d[col];
+              kown[e] = col < bs ? __fdiv_rn(__fmul_rn(w[t0][e], w[t0][e]), __fmul_rn(d, d)) : __int_as_float(0x7f800000);
+            }
+            float keys[M >= 8 ? M : 8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int a = 4 * lane + e - i;
-            if (a >= 0 && a < m) {
-              int rank = 0;
-              for (int b = 0; b < m; ++b) rank += (keys[b] < keys[a] || (keys[b] == keys[a] && b < a)) ? 1 : 0;
-              if (rank < n) mbits |= 1u << e;
+            for (int a = 0; a < M; ++a) keys[a] = __shfl_sync(0xffffffffu, kown[a & 3], gbase + ((li + (a >> 2)) & 7));
+            const int mypos = 4 * (l - li);                      // position of this lane's first column in the group
+            if (mypos >= 0 && mypos < M) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                int rank = 0;
+#pragma unroll
+                for (int b = 0; b < M; ++b)
+                  rank += (keys[b] < kown[e] || (keys[b] == kown[e] && b < mypos + e)) ? 1 : 0;
+                if (rank < n) mbits |= 1u << (4 * t0 + e);
+              }
             }
           }
+          uint32_t pm = 0;
+          if (M == 0 || M >= 8) pm = __shfl_sync(0xffffffffu, mbits, gbase + li);
 #pragma unroll
-          for (int c2 = 0; c2 < 4; ++c2) word[c2] = __ballot_sync(0xffffffffu, (mbits >> c2) & 1u);
+          for (int e = 0; e < 4; ++e) {
+            const int i = ib + e;
+            if (M == 2 || M == 4) {
+              if ((e % M) == 0) {
+                // n:m inside one float4: the owning lane ranks its own (already compensated) weights (:193-195)
+                if (l == li) {
+                  float keys[4];
+#pragma unroll
+                  for (int a = 0; a < M; ++a) {
+                    const float d = s_d[i + a];
+                    keys[a] = __fdiv_rn(__fmul_rn(w[t0][(e + a) & 3], w[t0][(e + a) & 3]), __fmul_rn(d, d));
+                  }
+#pragma unroll
+                  for (int a = 0; a < M; ++a) {
+                    int rank = 0;
+#pragma unroll
+                    for (int b = 0; b < M; ++b) rank += (keys[b] < keys[a] || (keys[b] == keys[a] && b < a)) ? 1 : 0;
+                    if (rank < n) mbits |= 1u << (4 * t0 + ((e + a) & 3));
+                  }
+                }
+                pm = __shfl_sync(0xffffffffu, mbits, gbase + li);
+              }
+            }
+            const float wi = __shfl_sync(0xffffffffu, w[t0][e], gbase + li);
+            const bool pruned = (pm >> (4 * t0 + e)) & 1u;
+            if (!__any_sync(0xffffffffu, pruned)) continue;      // every row of the warp keeps column i: nothing to propagate
+            const float err = pruned ? __fdiv_rn(wi, s_d[i]) : 0.f;      // (w - 0) / d (:202); kept: err = 0
+            // product and subtraction rounded separately, like the reference's outer product + in-place sub (:204);
+            // U1[i, j < i] is exactly 0, so finished columns are untouched
+#pragma unroll
+            for (int t = t0; t < 4; ++t) {
+              const float4 u = Us4[i * (kOB / 4) + 8 * t + l];
+              w[t][0] = __fsub_rn(w[t][0], __fmul_rn(err, u.x)); w[t][1] = __fsub_rn(w[t][1], __fmul_rn(err, u.y));
+              w[t][2] = __fsub_rn(w[t][2], __fmul_rn(err, u.z)); w[t][3] = __fsub_rn(w[t][3], __fmul_rn(err, u.w));
+            }
+            if (l == li && pruned) { w[t0][e] = 0.f; er[t0][e] = err; }     // Q1[:, i] = 0, Err1[:, i] = err
+          }
         }
-        if (!((word[c] >> q) & 1u)) continue;                   // kept column: q = w, err = 0, nothing to propagate
-        const float wi = __shfl_sync(0xffffffffu, w[c], q);
-        const float err = __fdiv_rn(wi, Us[i * kOB + i]);       // (w - 0) / d (:202)
-        const float4 u = *reinterpret_cast<const float4*>(Us + i * kOB + 4 * lane);
-        // product and subtraction rounded separately, like the reference's outer-product matmul + in-place sub (:204);
-        // U1[i, j < i] is exactly 0, so finished columns are untouched
-        w[0] = __fsub_rn(w[0], __fmul_rn(err, u.x)); w[1] = __fsub_rn(w[1], __fmul_rn(err, u.y));
-        w[2] = __fsub_rn(w[2], __fmul_rn(err, u.z)); w[3] = __fsub_rn(w[3], __fmul_rn(err, u.w));
-        if (lane == q) { w[c] = 0.f; er[c] = err; }             // Q1[:, i] = 0, Err1[:, i] = err
       }
     }
-    *reinterpret_cast<float4*>(p.Err + (int64_t)row * kOB + 4 * lane) = make_float4(er[0], er[1], er[2], er[3]);
-    if (act) {
-      *reinterpret_cast<float4*>(w32) = make_float4(w[0], w[1], w[2], w[3]);
-      T* wo = reinterpret_cast<T*>(p.Wout) + (int64_t)row * p.ldw + p.i1 + 4 * lane;
+    if (valid) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) wo[e] = from_float<T>(w[e]);
-      if (p.keep) {
-        uint8_t* kp = p.keep + (int64_t)row * p.ldm + p.i1 + 4 * lane;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) kp[e] = ((mbits >> e) & 1u) ? 0 : 1;
+      for (int t = 0; t < 4; ++t) {
+        const int col = 32 * t + 4 * l;
+        *reinterpret_cast<float4*>(p.Err + (int64_t)row * kOB + col) = make_float4(er[t][0], er[t][1], er[t][2], er[t][3]);
+        if (col < bs) {
+          *reinterpret_cast<float4*>(w32 + 32 * t) = make_float4(w[t][0], w[t][1], w[t][2], w[t][3]);
+          const int64_t off = (int64_t)row * p.ldw + p.i1 + col;
+          if (dtype == VLMC_F32) {
+            float* wo = reinterpret_cast<float*>(p.Wout) + off;
+            if (vec_ok) *reinterpret_cast<float4*>(wo) = make_float4(w[t][0], w[t][1], w[t][2], w[t][3]);
+            else { wo[0] = w[t][0]; wo[1] = w[t][1]; wo[2] = w[t][2]; wo[3] = w[t][3]; }
+          } else if (dtype == VLMC_F16) {
+            __half* wo = reinterpret_cast<__half*>(p.Wout) + off;
+            const __half2 a = __floats2half2_rn(w[t][0], w[t][1]), b = __floats2half2_rn(w[t][2], w[t][3]);
+            if (vec_ok) *reinterpret_cast<uint2*>(wo) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+            else { wo[0] = __low2half(a); wo[1] = __high2half(a); wo[2] = __low2half(b); wo[3] = __high2half(b); }
+          } else {
+            __nv_bfloat16* wo = reinterpret_cast<__nv_bfloat16*>(p.Wout) + off;
+            const __nv_bfloat162 a = __floats2bfloat162_rn(w[t][0], w[t][1]), b = __floats2bfloat162_rn(w[t][2], w[t][3]);
+            if (vec_ok) *reinterpret_cast<uint2*>(wo) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+            else { wo[0] = __low2bfloat16(a); wo[1] = __high2bfloat16(a); wo[2] = __low2bfloat16(b); wo[3] = __high2bfloat16(b); }
+          }
+          if (p.keep) {
+            uint8_t* kp = p.keep + (int64_t)row * p.ldm + p.i1 + col;
+            const uint32_t mb = (mbits >> (4 * t)) & 0xfu;
+            const uint32_t bytes = ((mb & 1u) ? 0u : 1u) | ((mb & 2u) ? 0u : 0x100u) | ((mb & 4u) ? 0u : 0x10000u) | ((mb & 8u) ? 0u : 0x1000000u);
+            if (vec_ok) *reinterpret_cast<uint32_t*>(kp) = bytes;
+            else { kp[0] = bytes & 1u; kp[1] = (bytes >> 8) & 1u; kp[2] = (bytes >> 16) & 1u; kp[3] = (bytes >> 24) & 1u; }
+          }
+        }
       }
     }
   }
+}
+
+template <int M>
+static int launch_sweep4(const ObsParams& p, int dtype, int vec_ok, cudaStream_t st) {
+  auto kern = obs_sweep4_kernel<M>;
+  const size_t smem = (size_t)kOB * kOB * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch();
+    attr_set = true;
+  }
+  int grid = (p.R + kSw4RowsPerCta - 1) / kSw4RowsPerCta;
+  if (grid > kNumSMs * 3) grid = kNumSMs * 3;
+  kern<<<grid, kSw4Threads, smem, st>>>(p, dtype, vec_ok);
+  return check_launch();
 }
 
 size_t obs_workspace_bytes(int R, int C) {
@@ -357,7 +450,8 @@ extern "C" int vlmc_obs_block_hist(int R, int C, const float* U, int64_t ldu, in
   ObsParams p = obs_block_params(l, nullptr, R, C, C, U, ldu, blk, rows_total, sparsity, 0, 0, nullptr, 0, hist);
   const int64_t nvec = (int64_t)R * (p.bs >> 2);
   int hgrid = (int)((nvec + kObsThreads * 4 - 1) / (kObsThreads * 4));
-  if (hgrid > kNumSMs * 4) hgrid = kNumSMs * 4;
+  static const int hmul = [] { const char* e = getenv("VLMC_OBS_HGRID"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 16 ? v : 4; }();
+  if (hgrid > kNumSMs * hmul) hgrid = kNumSMs * hmul;
   if (hgrid < 1) hgrid = 1;
   if (pass == 0) obs_hist_kernel<0><<<hgrid, kObsThreads, 0, st>>>(p);
   else if (pass == 1) obs_hist_kernel<1><<<hgrid, kObsThreads, 0, st>>>(p);
@@ -375,19 +469,19 @@ extern "C" int vlmc_obs_block_finish(void* W, int dtype, int R, int C, int64_t l
   cudaStream_t st = (cudaStream_t)stream;
   ObsLayout l = obs_carve(ws, R, C);
   ObsParams p = obs_block_params(l, W, R, C, ldw, U, ldu, blk, rows_total, sparsity, prune_n, prune_m, keep_mask, ldm, hist);
-  const size_t smem = (size_t)kOB * kOB * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(obs_sweep_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(obs_sweep_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(obs_sweep_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return check_launch();
-    attr_set = true;
+  // 8-byte weight stores / 4-byte mask stores need aligned rows; otherwise the kernel stores element by element
+  const int esz = elem_size(dtype);
+  const int vec_ok = ((ldw * esz) % (4 * esz) == 0) && (((uintptr_t)W) % (4 * esz) == 0) &&
+                     (!keep_mask || ((ldm % 4 == 0) && (((uintptr_t)keep_mask) % 4 == 0)));
+  switch (prune_n == 0 ? 0 : prune_m) {
+    case 0: rc = launch_sweep4<0>(p, dtype, vec_ok, st); break;
+    case 2: rc = launch_sweep4<2>(p, dtype, vec_ok, st); break;
+    case 4: rc = launch_sweep4<4>(p, dtype, vec_ok, st); break;
+    case 8: rc = launch_sweep4<8>(p, dtype, vec_ok, st); break;
+    case 16: rc = launch_sweep4<16>(p, dtype, vec_ok, st); break;
+    default: return VLMC_ERR_UNSUPPORTED;
   }
-  const int rows_per_cta = kSweepThreads / 32;
-  int sweep_grid = (R + rows_per_cta - 1) / rows_per_cta;
-  if (sweep_grid > kNumSMs * 2) sweep_grid = kNumSMs * 2;
-  VLMC_DISPATCH_DTYPE(dtype, (obs_sweep_kernel<scalar_t><<<sweep_grid, kSweepThreads, smem, st>>>(p)));
+  if (rc) return rc;
   const int i2 = p.i1 + p.bs;
   if (i2 < C) {
     // K13: W[:, i2:] -= Err1 @ U[i1:i2, i2:]

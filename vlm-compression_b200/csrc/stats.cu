@@ -12,13 +12,12 @@
 // fixed order, so the result is deterministic, and applies the running-average update.
 //
 // HBM-bound: algorithmic bytes = T*C*sizeof(x) (+ a few vectors of C floats).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace vlmc {
 
-constexpr int kCX = 64;   // column-vector lanes per CTA
-constexpr int kRY = 4;    // row lanes per CTA
-constexpr int kStatsThreads = kCX * kRY;
+constexpr int kStatsThreads = 256;   // = column-vector lanes (CX) x row lanes (RY) per CTA
 constexpr int kUnroll = 4;
 
 struct StatsParams {
@@ -41,12 +40,13 @@ struct StatsParams {
 
 // resident CTAs per SM the grid is sized for (one full wave, no tail): the Wanda variant fits 32 registers
 // (8 x 256 threads = 64 warps / SM); the DSnoT variant carries 3x the per-thread state
-template <bool DSNOT> struct StatsOcc { static constexpr int kBlocksPerSM = DSNOT ? 3 : 8; };
+template <bool DSNOT> struct StatsOcc { static constexpr int kBlocksPerSM = DSNOT ? 4 : 8; };
 
-template <typename T, bool DSNOT>
+template <typename T, bool DSNOT, int kCX>
 __global__ void __launch_bounds__(kStatsThreads, StatsOcc<DSNOT>::kBlocksPerSM)
 colstats_kernel(const StatsParams p) {
   constexpr int V = Elem<T>::kVec;
+  constexpr int kRY = kStatsThreads / kCX;
   const int tx = threadIdx.x % kCX;
   const int ty = threadIdx.x / kCX;
   const int col0 = (blockIdx.x * kCX + tx) * V;
@@ -215,9 +215,17 @@ struct StatsPlan {
   size_t bytes;
 };
 
+static int stats_cx() {
+  // column lanes per CTA (x 16 B = contiguous bytes a CTA reads per row); tuning knob for the probe scripts
+  const char* e = getenv("VLMC_STATS_CX");
+  const int v = e ? atoi(e) : 64;
+  return (v == 16 || v == 32 || v == 64 || v == 128 || v == 256) ? v : 64;
+}
+
 static StatsPlan plan_stats(int dtype, int64_t nseg, int64_t S, int C, int kinds, int blocks_per_sm = 8) {
   StatsPlan pl;
   const int V = dtype == VLMC_F32 ? 4 : 8;
+  const int kCX = stats_cx(), kRY = kStatsThreads / kCX;
   pl.coltiles = (C + kCX * V - 1) / (kCX * V);
   const int64_t target_ctas = (int64_t)kNumSMs * blocks_per_sm;  // exactly one resident wave
   int64_t want = target_ctas / pl.coltiles;
@@ -269,7 +277,13 @@ static int launch_stats(const void* x, int dtype, int64_t nseg, int64_t S, int C
 
   dim3 grid(pl.coltiles, (unsigned)pl.nchunks);
   cudaStream_t st = (cudaStream_t)stream;
-  VLMC_DISPATCH_DTYPE(dtype, (colstats_kernel<scalar_t, DSNOT><<<grid, kStatsThreads, 0, st>>>(p)));
+  switch (stats_cx()) {
+    case 16: VLMC_DISPATCH_DTYPE(dtype, (colstats_kernel<scalar_t, DSNOT, 16><<<grid, kStatsThreads, 0, st>>>(p))); break;
+    case 32: VLMC_DISPATCH_DTYPE(dtype, (colstats_kernel<scalar_t, DSNOT, 32><<<grid, kStatsThreads, 0, st>>>(p))); break;
+    case 128: VLMC_DISPATCH_DTYPE(dtype, (colstats_kernel<scalar_t, DSNOT, 128><<<grid, kStatsThreads, 0, st>>>(p))); break;
+    case 256: VLMC_DISPATCH_DTYPE(dtype, (colstats_kernel<scalar_t, DSNOT, 256><<<grid, kStatsThreads, 0, st>>>(p))); break;
+    default: VLMC_DISPATCH_DTYPE(dtype, (colstats_kernel<scalar_t, DSNOT, 64><<<grid, kStatsThreads, 0, st>>>(p))); break;
+  }
   return check_launch();
 }
 

@@ -538,6 +538,141 @@ nm_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict_
   }
 }
 
+// ---- n:m, all linears of a block in ONE launch ----------------------------------------------
+// A Vicuna-7B block is 7 matrices of 34-90 MB; launched one by one each kernel lives 15-40 us and its ramp-up and
+// drain cost as much as a third of that.  Here the block is one list of work units (kNmbRows rows x 1024 columns of
+// one matrix) that a single grid of resident CTAs walks with a fixed stride: one ramp, one drain, every CTA within
+// one unit of the others at the end.  Per unit: the same loads, ranks and stores as nm_kernel.
+constexpr int kNmbMax = 16;       // matrices per launch
+constexpr int kNmbRows = 16;      // rows per work unit (4 in flight x 4)
+struct NmBatchItem {
+  void* W; int64_t ldw; int R, C; const float* scaler_row; uint8_t* mask; int64_t ldm;
+  int coltiles;                   // ceil(C / (kSelThreads * E))
+};
+struct NmBatch {
+  NmBatchItem it[kNmbMax];
+  int unit_begin[kNmbMax + 1];    // units of item i: [unit_begin[i], unit_begin[i+1])
+  int count;
+};
+
+template <typename T, int M>
+__global__ void __launch_bounds__(kSelThreads, (M <= 8 && sizeof(T) == 2) ? 8 : 3)
+nm_batch_kernel(const __grid_constant__ NmBatch b, int n, int zero_w, float* __restrict__ part_sum) {
+  constexpr int V = Elem<T>::kVec;
+  constexpr int E = (M > V) ? M : V;
+  constexpr int NVEC = E / V;
+  const int total = b.unit_begin[b.count];
+  const int warp = threadIdx.x >> 5;
+  for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    int p = 0;
+    while (unit >= b.unit_begin[p + 1]) ++p;
+    const NmBatchItem& it = b.it[p];
+    const int local = unit - b.unit_begin[p];
+    const int ct = local % it.coltiles, rb = local / it.coltiles;
+    const int col = (ct * kSelThreads + threadIdx.x) * E;
+    float lsum = 0.f;
+    if (col < it.C) {
+      T* W = reinterpret_cast<T*>(it.W);
+      float sq[E];
+#pragma unroll
+      for (int q = 0; q < E / 4; ++q) {
+        const float4 sv = __ldg(reinterpret_cast<const float4*>(it.scaler_row + col) + q);
+        sq[q * 4] = __fsqrt_rn(sv.x); sq[q * 4 + 1] = __fsqrt_rn(sv.y);
+        sq[q * 4 + 2] = __fsqrt_rn(sv.z); sq[q * 4 + 3] = __fsqrt_rn(sv.w);
+      }
+      const int row_begin = rb * kNmbRows;
+      const int row_end = row_begin + kNmbRows < it.R ? row_begin + kNmbRows : it.R;
+      constexpr int kRows = 4;
+      for (int row0 = row_begin; row0 < row_end; row0 += kRows) {
+        uint4 wv[kRows][NVEC];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          if (row0 + r < row_end) {
+#pragma unroll
+            for (int q = 0; q < NVEC; ++q) wv[r][q] = ld_stream(W + (int64_t)(row0 + r) * it.ldw + col + q * V);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          const int row = row0 + r;
+          if (row >= row_end) break;
+          T* wp = W + (int64_t)row * it.ldw + col;
+          uint32_t keys[E];
+#pragma unroll
+          for (int q = 0; q < NVEC; ++q) {
+            float f[V];
+            Elem<T>::unpack(wv[r][q], f);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+              const float sc = __fmul_rn(fabsf(f[e]), sq[q * V + e]);
+              keys[q * V + e] = __float_as_uint(sc);
+              lsum += sc;
+            }
+          }
+          bool pr[E];
+#pragma unroll
+          for (int g = 0; g < E / M; ++g) {
+#pragma unroll
+            for (int a = 0; a < M; ++a) {
+              int rank = 0;
+#pragma unroll
+              for (int c = 0; c < M; ++c) {
+                if (c < a) rank += keys[g * M + c] <= keys[g * M + a] ? 1 : 0;
+                if (c > a) rank += keys[g * M + c] < keys[g * M + a] ? 1 : 0;
+              }
+              pr[g * M + a] = rank < n;
+            }
+          }
+          uint8_t* mp = it.mask + (int64_t)row * it.ldm + col;
+#pragma unroll
+          for (int q = 0; q < NVEC; ++q) {
+            uint32_t mb[V / 4] = {};
+#pragma unroll
+            for (int e = 0; e < V; ++e) mb[e / 4] |= (pr[q * V + e] ? 0u : 1u) << (8 * (e % 4));
+            if (V == 8) st_stream8(mp + q * V, make_uint2(mb[0], mb[V / 4 - 1]));
+            else st_stream4(mp + q * V, mb[0]);
+            if (zero_w) {
+              uint32_t* wr = reinterpret_cast<uint32_t*>(&wv[r][q]);
+              if (sizeof(T) == 4) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) if (pr[q * V + e]) wr[e] = 0u;
+              } else {
+#pragma unroll
+                for (int e = 0; e < V; ++e)
+                  if (pr[q * V + e]) wr[e / 2] &= (e & 1) ? 0x0000ffffu : 0xffff0000u;
+              }
+              st_stream(wp + q * V, wv[r][q]);
+            }
+          }
+        }
+      }
+    }
+    // one partial per (unit, warp): no CTA barrier between units, fixed summation order in the finalize
+    lsum = warp_sum(lsum);
+    if ((threadIdx.x & 31) == 0) part_sum[(int64_t)unit * kSelWarps + warp] = lsum;
+  }
+}
+
+struct NmBatchOut { float* out[kNmbMax]; double denom[kNmbMax]; int begin[kNmbMax + 1]; };
+
+// grid = items: item i sums its partials [begin[i], begin[i+1]) in a fixed order -> mean
+__global__ void __launch_bounds__(256)
+mean_finalize_batch_kernel(const float* __restrict__ part, const __grid_constant__ NmBatchOut o) {
+  __shared__ double sred[8];
+  const int i = blockIdx.x;
+  if (!o.out[i]) return;
+  double s = 0.0;
+  for (int j = o.begin[i] + threadIdx.x; j < o.begin[i + 1]; j += 256) s += (double)part[j];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sred[w];
+    *o.out[i] = (float)(t / o.denom[i]);
+  }
+}
+
 // partial sums -> mean, single CTA, fixed order => deterministic
 __global__ void __launch_bounds__(256)
 mean_finalize_kernel(const float* __restrict__ part, int n, double denom, float* __restrict__ out) {
@@ -646,5 +781,80 @@ extern "C" int vlmc_wanda_nm(void* W, int dtype, int R, int C, int64_t ldw,
   rc = check_launch();
   if (rc) return rc;
   if (score_mean) return launch_mean_finalize(part, nparts, (double)R * (double)C, score_mean, st);
+  return VLMC_OK;
+}
+
+extern "C" size_t vlmc_wanda_nm_batch_workspace_bytes(const vlmc_select_item* items, int count, int dtype, int m) {
+  using namespace vlmc;
+  if (!items || count < 1) return 0;
+  const int V = dtype == VLMC_F32 ? 4 : 8;
+  const int E = m > V ? m : V;
+  size_t units = 0;
+  for (int i = 0; i < count; ++i) {
+    const size_t coltiles = ((size_t)items[i].C / E + kSelThreads - 1) / kSelThreads;
+    units += coltiles * (((size_t)items[i].R + kNmbRows - 1) / kNmbRows);
+  }
+  return VLMC_WS_COUNTER_BYTES + units * kSelWarps * sizeof(float);
+}
+
+extern "C" int vlmc_wanda_nm_batch(const vlmc_select_item* items, int count, int dtype, int n, int m, int zero_w,
+                                   void* ws, size_t ws_bytes, void* stream) {
+  using namespace vlmc;
+  if (!items || count < 1 || count > kNmbMax) return VLMC_ERR_BAD_ARG;
+  if (!(m == 2 || m == 4 || m == 8 || m == 16)) return VLMC_ERR_UNSUPPORTED;
+  if (n <= 0 || n >= m) return VLMC_ERR_BAD_ARG;
+  const int V = dtype == VLMC_F32 ? 4 : 8;
+  const int E = m > V ? m : V;
+  NmBatch b;
+  NmBatchOut o;
+  b.count = count;
+  b.unit_begin[0] = 0;
+  o.begin[0] = 0;
+  bool any_mean = false;
+  for (int i = 0; i < count; ++i) {
+    const vlmc_select_item& s = items[i];
+    int rc = sel_common_checks(s.W, dtype, s.R, s.C, s.ldw, s.scaler_row, s.keep_mask, s.ldm, ws);
+    if (rc) return rc;
+    if (s.C % m != 0 || s.C % E != 0 || ((uintptr_t)s.scaler_row & 15) != 0) return VLMC_ERR_UNSUPPORTED;
+    NmBatchItem& it = b.it[i];
+    it.W = s.W; it.ldw = s.ldw; it.R = s.R; it.C = s.C; it.scaler_row = s.scaler_row; it.mask = s.keep_mask; it.ldm = s.ldm;
+    it.coltiles = (s.C / E + kSelThreads - 1) / kSelThreads;
+    const int64_t units = (int64_t)it.coltiles * ((s.R + kNmbRows - 1) / kNmbRows);
+    if (b.unit_begin[i] + units > 0x7fffffff / kSelWarps) return VLMC_ERR_UNSUPPORTED;
+    b.unit_begin[i + 1] = b.unit_begin[i] + (int)units;
+    o.begin[i + 1] = b.unit_begin[i + 1] * kSelWarps;
+    o.out[i] = s.score_mean;
+    o.denom[i] = (double)s.R * (double)s.C;
+    if (s.score_mean) {
+      if (!is_device_ptr(s.score_mean)) return VLMC_ERR_NOT_DEVICE;
+      any_mean = true;
+    }
+  }
+  const int total = b.unit_begin[count];
+  if (ws_bytes < VLMC_WS_COUNTER_BYTES + (size_t)total * kSelWarps * sizeof(float)) return VLMC_ERR_WORKSPACE;
+  float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + VLMC_WS_COUNTER_BYTES);
+  cudaStream_t st = (cudaStream_t)stream;
+  // every CTA resident from the start: the fixed-stride walk then ends within one unit everywhere
+#define VLMC_NMB(MM)                                                                                         \
+  VLMC_DISPATCH_DTYPE(dtype, {                                                                               \
+    int per_sm = 1;                                                                                          \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nm_batch_kernel<scalar_t, MM>, kSelThreads, 0);   \
+    int grid = kNumSMs * (per_sm < 1 ? 1 : per_sm);                                                          \
+    if (grid > total) grid = total;                                                                          \
+    nm_batch_kernel<scalar_t, MM><<<grid, kSelThreads, 0, st>>>(b, n, zero_w, part);                         \
+  })
+  switch (m) {
+    case 2: VLMC_NMB(2); break;
+    case 4: VLMC_NMB(4); break;
+    case 8: VLMC_NMB(8); break;
+    default: VLMC_NMB(16); break;
+  }
+#undef VLMC_NMB
+  int rc = check_launch();
+  if (rc) return rc;
+  if (any_mean) {
+    mean_finalize_batch_kernel<<<count, 256, 0, st>>>(part, o);
+    return check_launch();
+  }
   return VLMC_OK;
 }

@@ -40,6 +40,26 @@ class WrappedGPT:
         self.nsamples += b
 
 
+def wanda_prune_block_nm(modules, scaler_rows, prune_n, prune_m, lora_model=False):
+    """n:m score + select + apply for ALL linears of one block in one launch per dtype (vlmc_wanda_nm_batch); the
+    reference's per-linear loop (wanda_pruner.py:313-347) with identical masks and weights.  Sets module.mask;
+    returns the importance scores as a list of 1-element device tensors (one per module)."""
+    out = [None] * len(modules)
+    groups = {}
+    for i, mod in enumerate(modules):
+        W = mod.weight.data
+        groups.setdefault((W.dtype, W.device), []).append(i)
+    for idx in groups.values():
+        for c0 in range(0, len(idx), 16):
+            chunk = idx[c0:c0 + 16]
+            keeps, means = native.wanda_nm_batch([modules[i].weight.data for i in chunk], [scaler_rows[i] for i in chunk],
+                                                 prune_n, prune_m, zero_w=not lora_model)
+            for j, i in enumerate(chunk):
+                setattr(modules[i], "mask", keeps[j])
+                out[i] = means[j:j + 1]
+    return out
+
+
 def wanda_prune_linear(module, scaler_row, sparsity, prune_n=0, prune_m=0, lora_model=False, whole_matrix=False):
     """Score + select + apply for one linear (wanda_pruner.py:316-341 / :664-687).
 
@@ -88,6 +108,7 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
         self.t5_model_prefix = t5_model_prefix
         self.vit_model_prefix = vit_model_prefix
         self._pending_scores = []
+        self._pending_nm = []
         # linears fed by the same tensor accumulate their statistics once (layerwise.InputSharing); False restores
         # the reference's one-accumulation-per-linear schedule.  The results are identical either way.
         self.share_inputs = share_inputs
@@ -104,12 +125,21 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
     def _prune_linear(self, vit, lora_model):
         def fn(i, name, module, wrapper, sparsity, expected_nsamples):
             assert wrapper.nsamples == expected_nsamples
+            if self.prune_n != 0:                   # n:m: the whole block in one launch (finish_block)
+                self._pending_nm.append((module, wrapper.scaler_row, lora_model))
+                return
             mean = wanda_prune_linear(module, wrapper.scaler_row, sparsity, self.prune_n, self.prune_m,
                                       lora_model=lora_model, whole_matrix=vit)
             self._pending_scores.append((module, mean))
         return fn
 
     def finish_block(self, subset, wrapped):
+        if self._pending_nm:
+            mods = [m for m, _, _ in self._pending_nm]
+            means = wanda_prune_block_nm(mods, [s for _, s, _ in self._pending_nm], self.prune_n, self.prune_m,
+                                         lora_model=self._pending_nm[0][2])
+            self._pending_scores.extend(zip(mods, means))
+            self._pending_nm = []
         # one host sync per block instead of the reference's full-matrix .cpu() per linear (:320)
         if self._pending_scores:
             vals = torch.cat([m for _, m in self._pending_scores]).tolist()

@@ -42,6 +42,8 @@ SIGNATURES = {
     "vlmc_dsnot_stats": (_i, [_vp, _i, _i64, _i64, _i, _i64, _vp, _vp, _vp, _vp, _d, _d, _d, _vp, _sz, _vp]),
     "vlmc_wanda_rowselect": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_wanda_nm": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "vlmc_wanda_nm_batch_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
+    "vlmc_wanda_nm_batch": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "vlmc_wanda_threshold": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_mask_pack": (_i, [_vp, _i, _i, _i64, _vp, _i64, _vp]),
     "vlmc_mask_apply_packed": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _i64, _vp, _i64, _i, _vp]),
@@ -207,6 +209,42 @@ def wanda_nm(W, scaler_row, n, m, zero_w=True, keep_mask=None):
                                score_mean.data_ptr(), ws.data_ptr(), ws.numel(), _stream(W))
     _check("vlmc_wanda_nm", st)
     return keep_mask, score_mean
+
+
+class SelectItem(ctypes.Structure):
+    """vlmc_select_item (include/vlmc.h)."""
+    _fields_ = [("W", _vp), ("ldw", _i64), ("R", _i), ("C", _i), ("scaler_row", _vp), ("keep_mask", _vp),
+                ("ldm", _i64), ("score_mean", _vp)]
+
+
+def wanda_nm_batch(Ws, scaler_rows, n, m, zero_w=True, keep_masks=None):
+    """K4+K6 for all linears of a block in ONE launch (vlmc_wanda_nm_batch).  Ws: list of 2-D weights of one dtype on
+    one device; scaler_rows: matching [C] fp32 tensors.  Returns ([keep_mask], score_means [len(Ws)] device tensor);
+    same masks and weights as len(Ws) calls of wanda_nm."""
+    if not Ws:
+        return [], None
+    dev, dt = Ws[0].device, Ws[0].dtype
+    _require_cuda(*Ws, *scaler_rows)
+    if keep_masks is None:
+        keep_masks = [torch.empty(W.shape, dtype=torch.bool, device=dev) for W in Ws]
+    means = torch.empty(len(Ws), dtype=torch.float32, device=dev)
+    items = (SelectItem * len(Ws))()
+    for i, (W, s, k) in enumerate(zip(Ws, scaler_rows, keep_masks)):
+        if W.dim() != 2 or W.stride(1) != 1 or W.dtype != dt or W.device != dev:
+            raise ValueError("weights must be 2-D row-major tensors of one dtype on one device")
+        if k.dtype != torch.bool or k.shape != W.shape or k.stride(1) != 1:
+            raise ValueError("keep_mask must be a bool tensor shaped like W")
+        if s.dtype != torch.float32 or s.numel() != W.shape[1]:
+            raise ValueError("scaler_row must be float32 [C]")
+        items[i] = SelectItem(W.data_ptr(), W.stride(0), W.shape[0], W.shape[1], s.data_ptr(), k.data_ptr(), k.stride(0),
+                              means[i:i + 1].data_ptr())
+    lib = load()
+    ws = workspace(Ws[0], lib.vlmc_wanda_nm_batch_workspace_bytes(items, len(Ws), _DTYPES[dt], int(m)))
+    with torch.cuda.device(dev):
+        st = lib.vlmc_wanda_nm_batch(items, len(Ws), _dtype(Ws[0]), int(n), int(m), int(bool(zero_w)), ws.data_ptr(),
+                                     ws.numel(), _stream(Ws[0]))
+    _check("vlmc_wanda_nm_batch", st)
+    return keep_masks, means
 
 
 def wanda_threshold(W, scaler_row, k_global, zero_w=True, keep_mask=None):
