@@ -485,7 +485,7 @@ def run_gpu(args):
     if args.all_methods:
         for m in METHODS:
             if m != args.method:
-                r = time_method(ctx, m, inputs, 2, 3, False, dist, not args.no_graph)
+                r = time_method(ctx, m, inputs, 2, 3, rank == 0, dist, not args.no_graph)
                 others[m] = r
     ctx.H = ctx.U = None
     torch.cuda.empty_cache()
@@ -518,7 +518,7 @@ def run_gpu(args):
         if others:
             out["methods"] = {m: {"value": r["ms_per_step"] / 1e3, "unit": UNIT, "steps": r["steps"],
                                   "cuda_graph": r["cuda_graph"], "eager_ms_per_step": r["eager_ms_per_step"],
-                                  "roofline": roofline_of(r, pk)} for m, r in others.items()}
+                                  "clocks": r["clocks"], "roofline": roofline_of(r, pk)} for m, r in others.items()}
         if "cuda_graph_error" in main:
             out["config"]["cuda_graph_error"] = main["cuda_graph_error"]
         if world == 1 and args.all_methods and args.method == "wanda_nm":

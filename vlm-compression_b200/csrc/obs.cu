@@ -17,7 +17,6 @@
 //                                shuffle inside the lane group.  Writes the finished columns to the fp16/bf16
 //                                weight, the fp32 working copy, Err1 and the keep mask.
 //   K13  the lazy trailing update on the tensor cores: the 3xTF32 tcgen05 GEMM of gemm3x.cu (fp32-grade accuracy).
-#include <cstdlib>
 #include "gemm3x.cuh"
 
 namespace vlmc {
@@ -172,11 +171,11 @@ obs_hist_kernel(const ObsParams p) {
 }
 
 // K12 (+ the tail of K11), four rows per warp.  A warp per row is instruction-issue bound: ~60 instructions per
-// column step of bookkeeping that is identical for every row (measured: 39.5 us per 4096-row block).  Here a row belongs to EIGHT lanes
+// column step of bookkeeping that is identical for every row (measured: 39.5 us per 4096-row block; this kernel: 27.5 us).  Here a row belongs to EIGHT lanes
 // (lane l of the group holds the float4s at columns 32 t + 4 l, t = 0..3), so one warp carries four rows through the
 // same 128 steps and the bookkeeping is shared: ~10 instructions per row and step.  The pivot column of every row
 // comes from a shuffle inside its lane group; rows that keep the column run the update with err = 0, which leaves
-// every value bit-identical (w - 0 * u == w), and the whole step is skipped when all four rows keep it.  Column
+// every value bit-identical (w - 0 * u == w).  Column
 // slices that are finished for every row of the warp (t < t0) are skipped statically.  Same arithmetic, same
 // roundings and the same order per row as the reference (:189-205).
 constexpr int kSw4Threads = 256;
@@ -187,9 +186,10 @@ __global__ void __launch_bounds__(kSw4Threads, 3)
 obs_sweep4_kernel(const ObsParams p, int dtype, int vec_ok) {
   extern __shared__ __align__(16) float Us[];                  // [kOB][kOB] U1 tile, zero padded
   __shared__ unsigned int s_scan[32];
-  __shared__ float s_d[kOB];
+  __shared__ __align__(16) float s_d[kOB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bs = p.bs;
+#pragma unroll 4
   for (int idx = tid; idx < kOB * kOB / 4; idx += kSw4Threads) {
     const int i = idx / (kOB / 4), j = (idx % (kOB / 4)) * 4;
     float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -242,7 +242,7 @@ obs_sweep4_kernel(const ObsParams p, int dtype, int vec_ok) {
         for (int li = 0; li < 8; ++li) {
           const int ib = 32 * t0 + 4 * li;
           if (ib >= bs) break;
-          if (M >= 8 && (ib % M) == 0) {
+          if (M >= 8 && (ib % (M >= 8 ? M : 8)) == 0) {
             // n:m over M >= 8 columns: lanes li .. li + M/4 - 1 of every group hold the group's columns in slot t0
             float kown[4];
 #pragma unroll
@@ -268,11 +268,13 @@ obs_sweep4_kernel(const ObsParams p, int dtype, int vec_ok) {
           }
           uint32_t pm = 0;
           if (M == 0 || M >= 8) pm = __shfl_sync(0xffffffffu, mbits, gbase + li);
+          const float4 d4 = *reinterpret_cast<const float4*>(s_d + ib);     // diagonal of the four pivots of this lane slot
+          const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int i = ib + e;
             if (M == 2 || M == 4) {
-              if ((e % M) == 0) {
+              if ((e % ((M == 2 || M == 4) ? M : 4)) == 0) {
                 // n:m inside one float4: the owning lane ranks its own (already compensated) weights (:193-195)
                 if (l == li) {
                   float keys[4];
@@ -294,8 +296,10 @@ obs_sweep4_kernel(const ObsParams p, int dtype, int vec_ok) {
             }
             const float wi = __shfl_sync(0xffffffffu, w[t0][e], gbase + li);
             const bool pruned = (pm >> (4 * t0 + e)) & 1u;
-            if (!__any_sync(0xffffffffu, pruned)) continue;      // every row of the warp keeps column i: nothing to propagate
-            const float err = pruned ? __fdiv_rn(wi, s_d[i]) : 0.f;      // (w - 0) / d (:202); kept: err = 0
+            // (w - 0) / d (:202); rows that keep the column get err = 0.  No branch: the quotient is computed by every
+            // lane and selected, so the step is one straight dependency chain shuffle -> divide -> multiply -> subtract
+            const float quot = __fdiv_rn(wi, dd[e]);
+            const float err = pruned ? quot : 0.f;
             // product and subtraction rounded separately, like the reference's outer product + in-place sub (:204);
             // U1[i, j < i] is exactly 0, so finished columns are untouched
 #pragma unroll
@@ -450,8 +454,7 @@ extern "C" int vlmc_obs_block_hist(int R, int C, const float* U, int64_t ldu, in
   ObsParams p = obs_block_params(l, nullptr, R, C, C, U, ldu, blk, rows_total, sparsity, 0, 0, nullptr, 0, hist);
   const int64_t nvec = (int64_t)R * (p.bs >> 2);
   int hgrid = (int)((nvec + kObsThreads * 4 - 1) / (kObsThreads * 4));
-  static const int hmul = [] { const char* e = getenv("VLMC_OBS_HGRID"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 16 ? v : 4; }();
-  if (hgrid > kNumSMs * hmul) hgrid = kNumSMs * hmul;
+  if (hgrid > kNumSMs * 4) hgrid = kNumSMs * 4;
   if (hgrid < 1) hgrid = 1;
   if (pass == 0) obs_hist_kernel<0><<<hgrid, kObsThreads, 0, st>>>(p);
   else if (pass == 1) obs_hist_kernel<1><<<hgrid, kObsThreads, 0, st>>>(p);

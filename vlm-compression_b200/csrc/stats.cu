@@ -6,13 +6,12 @@
 //
 // Layout: x is [T, C] row-major (what the reference reaches with inp.reshape(-1, C); its .t() is a
 // view, so the reduction there runs over a strided dimension).  Here a CTA owns a tile of
-// 64 x 16 B columns and a contiguous chunk of rows; every warp reads 512 contiguous bytes per row,
-// 4 rows in flight per thread, fp32 partials in registers.  Partials of all row chunks go to the
+// kCX x 16 B columns (512 B for Wanda, 256 B for DSnoT) and a contiguous chunk of rows; its 256 threads cover
+// 256 / kCX rows per step, 4 steps in flight per thread, fp32 partials in registers.  Partials of all row chunks go to the
 // workspace; the last CTA to finish a column tile (ticket counter) combines them in fp64 in a
 // fixed order, so the result is deterministic, and applies the running-average update.
 //
 // HBM-bound: algorithmic bytes = T*C*sizeof(x) (+ a few vectors of C floats).
-#include <cstdlib>
 #include "common.cuh"
 
 namespace vlmc {
@@ -215,17 +214,15 @@ struct StatsPlan {
   size_t bytes;
 };
 
-static int stats_cx() {
-  // column lanes per CTA (x 16 B = contiguous bytes a CTA reads per row); tuning knob for the probe scripts
-  const char* e = getenv("VLMC_STATS_CX");
-  const int v = e ? atoi(e) : 64;
-  return (v == 16 || v == 32 || v == 64 || v == 128 || v == 256) ? v : 64;
-}
+// column lanes per CTA (x 16 B = contiguous bytes a CTA reads per row).  Measured on B200 at T = 262144 fp16 rows
+// (scripts/stats_probe.py): Wanda 32 lanes (512 B x 8 rows per step) 6.52 TB/s at C = 4096 and 7.21 TB/s at C = 11008
+// vs 5.93 / 7.09 with 64 lanes; DSnoT 16 lanes 4.93 / 6.16 TB/s vs 3.77 / 5.28 with 64.
+template <bool DSNOT> struct StatsTile { static constexpr int kCX = DSNOT ? 16 : 32; };
 
 static StatsPlan plan_stats(int dtype, int64_t nseg, int64_t S, int C, int kinds, int blocks_per_sm = 8) {
   StatsPlan pl;
   const int V = dtype == VLMC_F32 ? 4 : 8;
-  const int kCX = stats_cx(), kRY = kStatsThreads / kCX;
+  const int kCX = kinds == 3 ? StatsTile<true>::kCX : StatsTile<false>::kCX, kRY = kStatsThreads / kCX;
   pl.coltiles = (C + kCX * V - 1) / (kCX * V);
   const int64_t target_ctas = (int64_t)kNumSMs * blocks_per_sm;  // exactly one resident wave
   int64_t want = target_ctas / pl.coltiles;
@@ -277,13 +274,7 @@ static int launch_stats(const void* x, int dtype, int64_t nseg, int64_t S, int C
 
   dim3 grid(pl.coltiles, (unsigned)pl.nchunks);
   cudaStream_t st = (cudaStream_t)stream;
-  switch (stats_cx()) {
-    case 16: VLMC_DISPATCH_DTYPE(dtype, (colstats_kernel<scalar_t, DSNOT, 16><<<grid, kStatsThreads, 0, st>>>(p))); break;
-    case 32: VLMC_DISPATCH_DTYPE(dtype, (colstats_kernel<scalar_t, DSNOT, 32><<<grid, kStatsThreads, 0, st>>>(p))); break;
-    case 128: VLMC_DISPATCH_DTYPE(dtype, (colstats_kernel<scalar_t, DSNOT, 128><<<grid, kStatsThreads, 0, st>>>(p))); break;
-    case 256: VLMC_DISPATCH_DTYPE(dtype, (colstats_kernel<scalar_t, DSNOT, 256><<<grid, kStatsThreads, 0, st>>>(p))); break;
-    default: VLMC_DISPATCH_DTYPE(dtype, (colstats_kernel<scalar_t, DSNOT, 64><<<grid, kStatsThreads, 0, st>>>(p))); break;
-  }
+  VLMC_DISPATCH_DTYPE(dtype, (colstats_kernel<scalar_t, DSNOT, StatsTile<DSNOT>::kCX><<<grid, kStatsThreads, 0, st>>>(p)));
   return check_launch();
 }
 
