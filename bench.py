@@ -190,20 +190,20 @@ def step_wanda(ctx, weights, inputs, method, shared=False):
     torch, native, parallel = ctx.torch, ctx.native, ctx.parallel
     shape = {n: (R, C, inp) for n, R, C, inp in LINEARS}
     scalers = {}
-    for leader, members in stat_groups(shared):           # phase 1: statistics (per-linear API unless `shared`)
+    groups = stat_groups(shared)
+    # the scaler_rows of the block are views of ONE packed fp32 buffer: one memset, and on several GPUs one in-place
+    # all-reduce (no gather / scatter copies around the collective)
+    flat = torch.zeros(sum(shape[l][1] for l, _ in groups), device=ctx.dev, dtype=torch.float32)
+    off = 0
+    for leader, members in groups:                        # phase 1: statistics (per-linear API unless `shared`)
         _, C, inp = shape[leader]
-        s = torch.zeros(C, device=ctx.dev, dtype=torch.float32)
+        s = flat[off:off + C]
+        off += C
         accumulate(ctx, native.sqnorm_accum, inputs[inp], s, SEQ_LEN * C * 2, "sqnorm_accum")
         for m in members:
             scalers[m] = s
     if ctx.world > 1:
-        uniq = list({id(s): s for s in scalers.values()}.values())
-        flat = torch.cat(uniq)
         parallel.allreduce_sum(flat)
-        off = 0
-        for s in uniq:
-            s.copy_(flat[off:off + s.numel()])
-            off += s.numel()
     masks = {}
     if method == "wanda_nm":
         # phase 2, n:m: a group decision needs its m scores and nothing else, and the pruned weights + masks must end
@@ -485,7 +485,8 @@ def run_gpu(args):
     if args.all_methods:
         for m in METHODS:
             if m != args.method:
-                r = time_method(ctx, m, inputs, 2, 3, rank == 0, dist, not args.no_graph)
+                # the millisecond methods get enough steps to average out rank skew; SparseGPT steps are ~0.1 s each
+                r = time_method(ctx, m, inputs, 2 if m.startswith("sparsegpt") else 10, 3, rank == 0, dist, not args.no_graph)
                 others[m] = r
     ctx.H = ctx.U = None
     torch.cuda.empty_cache()
