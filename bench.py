@@ -523,7 +523,8 @@ def run_gpu(args):
         if "cuda_graph_error" in main:
             out["config"]["cuda_graph_error"] = main["cuda_graph_error"]
         if world == 1 and args.all_methods and args.method == "wanda_nm":
-            out["workloads"] = {"config2_instructblip_flant5xl_wanda_2of4": full_model_wanda_nm(torch, native, dev)}
+            out["workloads"] = {"config2_instructblip_flant5xl_wanda_2of4": full_model_wanda_nm(torch, native, dev),
+                                "config5_sparselora_and_hessian_sweep": config5_lora_and_hessian_sweep(torch, native, dev, inputs)}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.method)
         print(json.dumps(out), flush=True)
@@ -773,6 +774,60 @@ def full_model_wanda_nm(torch, native, dev, reps=2):
             "linears": sum(len(l) * n for _, l, n, _, _ in FULL_MODEL), "weights": total_weights,
             "algorithmic_bytes": total_bytes, "achieved_gbs": total_bytes / sec / 1e9, "reps": reps,
             "cuda_graph": graphed, "eager_s_per_model": eager_sec}
+
+
+# ------------------------------------------------------------------------------------------------ config 5
+def config5_lora_and_hessian_sweep(torch, native, dev, inputs):
+    """BASELINE.json configs[4]: (i) SparseLoRA masked merge (K14) and the masked-forward weight build (K15) over the 7
+    linears of a Vicuna-7B block (r = 8, random 50 % mask), 5 B / weight each; (ii) Hessian accumulation at calibration
+    scales 128..1024 x 2048 tokens for C = 4096 and C = 11008 (the resident 128-sequence input is fed repeatedly with a
+    growing n_before: same kernel work as a longer calibration set)."""
+    g = torch.Generator(device=dev).manual_seed(11)
+    out = {}
+    items = []
+    for name, R, C, _ in LINEARS:
+        W = (torch.randn(R, C, device=dev, generator=g) * 0.02).half()
+        A = torch.randn(8, C, device=dev, generator=g) * 0.1
+        B = torch.randn(R, 8, device=dev, generator=g) * 0.1
+        M = torch.rand(R, C, device=dev, generator=g) < 0.5
+        items.append((W, A, B, M, torch.empty_like(W)))
+    nbytes = sum(W.numel() for W, *_ in items) * 5
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    ms = timed(lambda: [native.sparselora_merge(W, A, B, 2.0, M, remask=True) for W, A, B, M, _ in items])
+    out["sparselora_merge_block"] = {"ms": ms, "achieved_gbs": nbytes / ms / 1e6, "bytes": nbytes}
+    ms = timed(lambda: [native.sparselora_effective_weight(W, A, B, 2.0, M, True, out=o) for W, A, B, M, o in items])
+    out["sparselora_forward_weight_block"] = {"ms": ms, "achieved_gbs": nbytes / ms / 1e6, "bytes": nbytes}
+    del items
+    sweep = {}
+    for inp, C in (("attn_in", D), ("mlp_mid", FF)):
+        x = inputs[inp]
+        H = torch.zeros(C, C, device=dev)
+        native.hessian_accum(x, H, 0, N_SEQ)
+        for nseq in (128, 256, 512, 1024):
+            reps = nseq // N_SEQ
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for r in range(reps):
+                native.hessian_accum(x, H, r * N_SEQ, N_SEQ)
+            b.record()
+            torch.cuda.synchronize()
+            t = a.elapsed_time(b)
+            sweep[f"C{C}_T{nseq}x{SEQ_LEN}"] = {"ms": t, "logical_tflops": 2.0 * nseq * SEQ_LEN * C * C / t / 1e9}
+        del H
+    out["hessian_accum_sweep"] = sweep
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm

@@ -171,6 +171,29 @@ int vlmc_sparselora_merge(void* W, int dtype, int R, int C, int64_t ldw,
                           void* stream);
 
 /*
+ * K15  SparseLoRA masked training forward, the weight part.  Replaces the weight expression of Linear.forward
+ * (r > 0, not merged), lora.py:364-375, that the reference re-materialises every step:
+ *   sparse != 0:  out = ((W + ((B @ A).to(dtype) * scaling)) * mask)        (:364-369)
+ *   sparse == 0:  out = ( W * mask + ((B @ A).to(dtype) * scaling))         (:370-375)
+ * with the reference's roundings (product cast to W's dtype, scaled in that dtype, added in that dtype).  W is not
+ * modified; out [R, C] has W's dtype.  y = F.linear(x, out, bias) stays a library GEMM.
+ */
+int vlmc_sparselora_effective_weight(const void* W, int dtype, int R, int C, int64_t ldw, const float* A,
+                                     const float* B, int rank, float scaling, const uint8_t* keep_mask,
+                                     int64_t ldm, int sparse, void* out, int64_t ldo, void* stream);
+
+/*
+ * K16  LoRA gradients of that forward.  G [R, C] (W's dtype) is the gradient w.r.t. the effective weight
+ * (dy^T x, a library GEMM).  The reference's autograd masks G (sparse only), scales it in W's dtype, casts to fp32 and
+ * runs two rank-r GEMMs; here  E = float(round_dtype(G * mask * scaling)),  dB [R, rank] = E A^T,
+ * dA [rank, C] = B^T E  in one call (fp32 accumulation, fixed order).  rank <= 16.
+ */
+size_t vlmc_sparselora_lora_grads_workspace_bytes(int R, int C, int rank);
+int vlmc_sparselora_lora_grads(const void* G, int dtype, int R, int C, int64_t ldg, const uint8_t* keep_mask,
+                               int64_t ldm, int sparse, const float* A, const float* B, int rank, float scaling,
+                               float* dA, float* dB, void* ws, size_t ws_bytes, void* stream);
+
+/*
  * K3  SparseGPT Hessian accumulation.  Replaces SparseGPT.add_batch, sparsegpt_pruner.py:68-79:
  *   H <- H * n_before/(n_before+b) + (2/(n_before+b)) * X^T X
  * x: [T, C] row-major fp16 / bf16 / fp32 (one add_batch call, T = b * seq_len); H: [C, C] fp32, full and symmetric.

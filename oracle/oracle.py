@@ -166,6 +166,40 @@ def sparselora_merge(W32, w_tag, A, B, scaling, keep_mask, remask=True):
 
 
 # ---------------------------------------------------------------------------------------------
+# f-2 / K15, K16  SparseLoRA masked training forward and its LoRA gradients      lora.py:359-382
+# ---------------------------------------------------------------------------------------------
+def _lora_product(A, B):
+    """B @ A in float32, k ascending with fused multiply-adds (see sparselora_merge)."""
+    acc = np.zeros((B.shape[0], A.shape[1]), dtype=F32)
+    for kk in range(A.shape[0]):
+        prod = B[:, kk].astype(np.float64)[:, None] * A[kk].astype(np.float64)[None, :]
+        acc = (prod + acc.astype(np.float64)).astype(F32)
+    return acc
+
+
+def sparselora_effective_weight(W32, w_tag, A, B, scaling, keep_mask, sparse=True):
+    """The weight Linear.forward hands to F.linear (lora.py:364-375), with torch's roundings in W's dtype:
+    (B @ A).to(dtype), * scaling, W + ., * mask   (sparse)   or   W * mask + .   (not sparse)."""
+    d = round_to_dtype(_lora_product(A, B), w_tag)
+    d = round_to_dtype((d * F32(scaling)).astype(F32), w_tag)
+    W32 = W32.astype(F32)
+    if sparse:
+        return np.where(keep_mask, round_to_dtype((W32 + d).astype(F32), w_tag), F32(0)).astype(F32)
+    return round_to_dtype((np.where(keep_mask, W32, F32(0)) + d).astype(F32), w_tag)
+
+
+def sparselora_lora_grads(G32, w_tag, A, B, scaling, keep_mask, sparse=True):
+    """Autograd of that expression w.r.t. lora_A / lora_B given G = dL/dW_eff (in W's dtype): mask (sparse only), scale
+    in W's dtype, cast to float32, dB = E A^T, dA = B^T E.  Returned in float64-accumulated float32 (the truth the
+    kernels are compared with at 1e-5)."""
+    E = np.where(keep_mask, G32, F32(0)) if sparse else G32
+    E = round_to_dtype((E.astype(F32) * F32(scaling)).astype(F32), w_tag).astype(np.float64)
+    dB = (E @ A.astype(np.float64).T).astype(F32)
+    dA = (B.astype(np.float64).T @ E).astype(F32)
+    return dA, dB
+
+
+# ---------------------------------------------------------------------------------------------
 # a3 / K3  SparseGPT Hessian                     sparsegpt_pruner.py:68-79
 # ---------------------------------------------------------------------------------------------
 def sparsegpt_add_batch(H, nsamples, x, b):

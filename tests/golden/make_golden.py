@@ -227,6 +227,42 @@ def gen_lora_merge(ref):
     save("lora_merge.npz", **out)
 
 
+def gen_lora_forward(ref):
+    """The reference's lora.Linear forward (r > 0, not merged) and its autograd backward, both weight expressions."""
+    out = {}
+    torch.manual_seed(6)
+    R, C, T = 40, 72, 9
+    for tag, dtype in (("bf16", torch.bfloat16), ("f16", torch.float16), ("f32", torch.float32)):
+        for r in (2, 8):
+            for sparse in (True, False):
+                lin = ref.lora.Linear(C, R, r=r, lora_alpha=16, bias=False)
+                lin.weight.data = (torch.randn(R, C) * 0.05).to(dtype)
+                lin.lora_A.weight.data = torch.randn(r, C) * 0.1
+                lin.lora_B.weight.data = torch.randn(R, r) * 0.1
+                lin.mask = torch.rand(R, C) < 0.5
+                lin.sparse = sparse
+                key = f"{tag}_r{r}_{'sparse' if sparse else 'dense'}"
+                out[f"{key}|W"] = f32(lin.weight)
+                out[f"{key}|A"] = f32(lin.lora_A.weight)
+                out[f"{key}|B"] = f32(lin.lora_B.weight)
+                out[f"{key}|mask"] = lin.mask.numpy().copy()
+                out[f"{key}|scaling"] = np.float64(lin.scaling)
+                with torch.no_grad():                          # F.linear(I, W_eff) = W_eff^T exactly
+                    out[f"{key}|W_eff"] = f32(lin(torch.eye(C, dtype=dtype)).T)
+                x = (torch.randn(T, C) * 0.5).to(dtype).requires_grad_(True)
+                gy = (torch.randn(T, R) * 0.5).to(dtype)
+                y = lin(x)
+                y.backward(gy)
+                out[f"{key}|x"] = f32(x)
+                out[f"{key}|gy"] = f32(gy)
+                out[f"{key}|y"] = f32(y)
+                out[f"{key}|G"] = f32(gy.t() @ x.detach())     # dL/dW_eff as F.linear's backward forms it
+                out[f"{key}|dx"] = f32(x.grad)
+                out[f"{key}|dA"] = f32(lin.lora_A.weight.grad)
+                out[f"{key}|dB"] = f32(lin.lora_B.weight.grad)
+    save("lora_forward.npz", **out)
+
+
 def gen_sparsegpt(ref):
     """The reference's SparseGPT class on one linear: add_batch x3 then fasterprune, in three regimes."""
     out = {}
@@ -277,7 +313,8 @@ def main():
     ref = ref_loader.load()
     only = set(sys.argv[1:])
     gens = dict(wanda_stats=gen_wanda_stats, dsnot_stats=gen_dsnot_stats, wanda_toy=gen_wanda_toy,
-                dsnot_toy=gen_dsnot_toy, lora_merge=gen_lora_merge, sparsegpt=gen_sparsegpt, reorder=gen_reorder)
+                dsnot_toy=gen_dsnot_toy, lora_merge=gen_lora_merge, lora_forward=gen_lora_forward, sparsegpt=gen_sparsegpt,
+                reorder=gen_reorder)
     for name, fn in gens.items():
         if not only or name in only:
             fn(ref)

@@ -973,3 +973,128 @@ def test_wanda_nm_batch_vicuna_block(native):
     kr, mr = native.wanda_nm(Wc, scal[6], 2, 4)
     assert torch.equal(kr, keeps[6]) and torch.equal(Wc, Ws[6])
     assert abs(means[6].item() - mr.item()) <= 1e-5 * abs(mr.item())
+
+
+def test_qformer_blocks_are_pruned_with_the_per_linear_rule(native):
+    """vlmc extension (the reference never prunes the Q-Former): with a qformer_prune_spec the BertLayers
+    under Qformer.bert.encoder.layer - called positionally, cross-attention keys / values fed the image embeddings -
+    go through the same capture / hook / select loop.  Checked against the oracle on statistics recomputed from the
+    layer inputs recorded by forward hooks: masks bit-exact, every linear of every layer pruned, the rest untouched."""
+    import toy_model
+    import vlmc.compression as comp
+    torch.manual_seed(0)
+    model = toy_model.ToyBlip(n_vit=1, n_llm=1, n_qformer=2).eval().cuda()
+    batches = toy_model.toy_batches(6, device="cuda")
+    layers = model.Qformer.bert.encoder.layer
+    names = [n for n, m in layers[0].named_modules() if isinstance(m, torch.nn.Linear)]
+    assert len(names) == 10
+    llm_before = {k: v.clone() for k, v in model.llm_model.state_dict().items()}
+    W0 = {(i, n): layers[i].get_submodule(n).weight.data.clone() for i in range(2) for n in names}
+    pruner = comp.load_pruner("blipt5_wanda_pruner", model, batches,
+                              cfg=toy_model.pruner_cfg(1.0, 1.0, qformer_prune_spec="12-0.5-1.0-1.0"))
+    model, _ = pruner.prune()
+    for k, v in model.llm_model.state_dict().items():
+        assert torch.equal(v, llm_before[k])                 # keep ratio 1.0: the language model is not touched
+    # layer 0 saw the unpruned model: recompute its statistics with hooks on a fresh copy and ask the oracle
+    torch.manual_seed(0)
+    fresh = toy_model.ToyBlip(n_vit=1, n_llm=1, n_qformer=2).eval().cuda()
+    seen = {n: [] for n in names}
+    hooks = [fresh.Qformer.bert.encoder.layer[0].get_submodule(n).register_forward_hook(
+        (lambda nm: lambda _, inp, out: seen[nm].append(inp[0].detach().float().cpu().numpy()))(n)) for n in names]
+    with torch.no_grad():
+        for b in batches:
+            fresh(b)
+    for h in hooks:
+        h.remove()
+    for n in names:
+        s, cnt = np.zeros(W0[(0, n)].shape[1], np.float32), 0
+        for x in seen[n]:
+            s, cnt = oracle.wanda_add_batch(s, cnt, x.reshape(-1, x.shape[-1]), 1)
+        C = W0[(0, n)].shape[1]
+        keep_o, Wp_o, _ = oracle.wanda_rowselect(W0[(0, n)].float().cpu().numpy(), s, int(C * 0.5))
+        mod = layers[0].get_submodule(n)
+        agree = (mod.mask.cpu().numpy() == keep_o).mean()
+        assert agree > 0.995, (n, agree)                     # statistics recomputed on the host in another order
+        assert bool(((~mod.mask).sum(1) == int(C * 0.5)).all())
+    for i in range(2):
+        for n in names:
+            mod = layers[i].get_submodule(n)
+            assert bool((mod.weight.data[~mod.mask] == 0).all()) and torch.equal(mod.weight.data[mod.mask], W0[(i, n)][mod.mask])
+            assert isinstance(mod.weight.importance_score, float)
+
+
+# ------------------------------------------------------------------------------------------- K15 / K16 (SURVEY 8f-2)
+LORA_FWD_KEYS = [f"{t}_r{r}_{m}" for t in ("bf16", "f16", "f32") for r in (2, 8) for m in ("sparse", "dense")]
+
+
+@pytest.mark.parametrize("key", LORA_FWD_KEYS)
+def test_lora_forward_golden(native, key):
+    """The reference's lora.Linear forward weight and autograd gradients (committed fixture) through K15 / K16."""
+    g = gu.load("lora_forward.npz")
+    tag, sparse = key.split("_")[0], key.endswith("sparse")
+    ulp = {"bf16": 2.0 ** -8, "f16": 2.0 ** -11, "f32": 2.0 ** -23}[tag]
+    W = torch.from_numpy(g[f"{key}|W"]).to(DT[tag]).cuda()
+    A, B = torch.from_numpy(g[f"{key}|A"]).cuda(), torch.from_numpy(g[f"{key}|B"]).cuda()
+    mask, s = torch.from_numpy(g[f"{key}|mask"]).cuda(), float(g[f"{key}|scaling"])
+    W0 = W.clone()
+    weff = native.sparselora_effective_weight(W, A, B, s, mask, sparse).float().cpu().numpy()
+    assert torch.equal(W, W0)                                              # the frozen weight is not touched
+    want = oracle.sparselora_effective_weight(g[f"{key}|W"], tag, g[f"{key}|A"], g[f"{key}|B"], s, g[f"{key}|mask"], sparse)
+    assert np.array_equal(weff, want)                                      # bit-exact vs the oracle
+    ref = g[f"{key}|W_eff"]
+    assert (np.abs(weff - ref) / np.maximum(np.abs(ref), 1e-3)).max() <= 2 * ulp and (weff != ref).mean() < 0.02
+    G = torch.from_numpy(g[f"{key}|G"]).to(DT[tag]).cuda()
+    dA, dB = native.sparselora_lora_grads(G, A, B, s, mask, sparse)
+    for got, name in ((dA, "dA"), (dB, "dB")):
+        w = g[f"{key}|{name}"]
+        assert np.abs(got.cpu().numpy() - w).max() <= 1e-5 * max(np.abs(w).max(), 1e-6), name
+
+
+@pytest.mark.parametrize("tag,r,sparse", [("bf16", 8, True), ("f16", 4, True), ("f32", 8, False), ("bf16", 16, False)])
+def test_lora_linear_module_forward_backward(native, tag, r, sparse):
+    """vlmc.peft.lora.Linear (K15 + library GEMM + K16 behind an autograd.Function) against the reference's expression
+    evaluated with torch ops on the same device: outputs to 1 ulp of the dtype, input / LoRA gradients to GEMM
+    tolerance.  Ragged sizes, bias, 3-D input."""
+    from vlmc.peft.lora import Linear as LoraLinear
+    torch.manual_seed(r)
+    R, C = 200, 328
+    lin = LoraLinear(C, R, r=r, lora_alpha=16, bias=True).cuda()
+    lin.weight.data = (torch.randn(R, C, device="cuda") * 0.05).to(DT[tag])
+    lin.bias.data = (torch.randn(R, device="cuda") * 0.1).to(DT[tag])
+    lin.lora_B.weight.data.normal_(0, 0.1)
+    lin.mask = torch.rand(R, C, device="cuda") < 0.5
+    lin.sparse = sparse
+    x = (torch.randn(3, 7, C, device="cuda") * 0.5).to(DT[tag]).requires_grad_(True)
+    gy = (torch.randn(3, 7, R, device="cuda") * 0.5).to(DT[tag])
+    y = lin(x)
+    y.backward(gy)
+    got = (y.detach().float(), x.grad.float(), lin.lora_A.weight.grad.clone(), lin.lora_B.weight.grad.clone())
+    x2 = x.detach().clone().requires_grad_(True)
+    lin.lora_A.weight.grad = lin.lora_B.weight.grad = None
+    delta = (lin.lora_B.weight @ lin.lora_A.weight).to(DT[tag]) * lin.scaling            # lora.py:364-375
+    w = (lin.weight + delta) * lin.mask if sparse else lin.weight * lin.mask + delta
+    y2 = torch.nn.functional.linear(x2, w, lin.bias)
+    y2.backward(gy)
+    want = (y2.detach().float(), x2.grad.float(), lin.lora_A.weight.grad, lin.lora_B.weight.grad)
+    tol = {"bf16": 2e-2, "f16": 3e-3, "f32": 2e-5}[tag]
+    for a, b, name in zip(got, want, ("y", "dx", "dA", "dB")):
+        err = float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+        assert err <= tol, (name, err)
+    assert lin.weight.grad is None and not lin.weight.requires_grad
+
+
+def test_lora_forward_vicuna_size_properties(native):
+    """gate_proj size: B = 0 gives W * M exactly; the LoRA gradients are linear in G and vanish where the mask is 0."""
+    R, C, r = 11008, 4096, 8
+    W = (torch.randn(R, C, device="cuda") * 0.02).half()
+    A = torch.randn(r, C, device="cuda") * 0.1
+    B = torch.randn(R, r, device="cuda") * 0.1
+    mask = torch.rand(R, C, device="cuda") < 0.5
+    assert torch.equal(native.sparselora_effective_weight(W, A, torch.zeros_like(B), 2.0, mask, True), W * mask)
+    G = (torch.randn(R, C, device="cuda") * 0.01).half()
+    dA, dB = native.sparselora_lora_grads(G, A, B, 2.0, mask, True)
+    dA0, dB0 = native.sparselora_lora_grads(G * ~mask, A, B, 2.0, mask, True)
+    assert float(dA0.abs().max()) == 0.0 and float(dB0.abs().max()) == 0.0
+    E = (G * mask).float() * 2.0
+    assert float((dB - E @ A.T).abs().max()) <= 1e-4 * float(dB.abs().max())
+    assert float((dA - B.T @ E).abs().max()) <= 1e-4 * float(dA.abs().max())

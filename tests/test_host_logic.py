@@ -60,8 +60,9 @@ def test_lora_linear_interface(built_lib):
     lin.sparse = True
     lin.lora_B.weight.data.normal_()
     lin.mask = torch.rand(16, 32) < 0.5
-    w = (lin.weight + (lin.lora_B.weight @ lin.lora_A.weight) * lin.scaling) * lin.mask
-    assert torch.allclose(lin(x), x @ w.T, atol=1e-5)
+    import pytest
+    with pytest.raises(RuntimeError, match="no CPU path"):      # the masked forward is K15 / K16: CUDA tensors only
+        lin(x)
 
 
 def test_factorisation_assignment_is_balanced_and_deterministic():

@@ -178,3 +178,28 @@ def test_torch_cpu_argmin_against_torch():
             x = torch.randint(0, 3, (m,), generator=g).float()
             x[torch.rand(m, generator=g) < 0.4] = float("inf")
             assert oracle.torch_cpu_argmin(x.numpy()) == torch.topk(x[None], 1, dim=1, largest=False)[1].item()
+
+
+def test_lora_forward():
+    """the oracle's effective weight and LoRA gradients against the reference's lora.Linear forward and
+    its autograd backward (tests/golden/lora_forward.npz)."""
+    g = gu.load("lora_forward.npz")
+    worst = 0.0
+    for tag in ("bf16", "f16", "f32"):
+        ulp = {"bf16": 2.0 ** -8, "f16": 2.0 ** -11, "f32": 2.0 ** -23}[tag]
+        for r in (2, 8):
+            for sparse in (True, False):
+                k = f"{tag}_r{r}_{'sparse' if sparse else 'dense'}"
+                mask, scaling = g[f"{k}|mask"], float(g[f"{k}|scaling"])
+                weff = oracle.sparselora_effective_weight(g[f"{k}|W"], tag, g[f"{k}|A"], g[f"{k}|B"], scaling, mask, sparse)
+                ref = g[f"{k}|W_eff"]
+                if sparse:
+                    assert np.array_equal(weff[~mask], np.zeros_like(weff[~mask])) and not ref[~mask].any()
+                # the rank-r product's summation order is a BLAS detail: 1 ulp of the W dtype on rare entries
+                err = np.abs(weff - ref) / np.maximum(np.abs(ref), 1e-3)
+                assert err.max() <= 2 * ulp, (k, err.max())
+                worst = max(worst, float((weff != ref).mean()))
+                dA, dB = oracle.sparselora_lora_grads(g[f"{k}|G"], tag, g[f"{k}|A"], g[f"{k}|B"], scaling, mask, sparse)
+                for got, want in ((dA, g[f"{k}|dA"]), (dB, g[f"{k}|dB"])):
+                    assert np.abs(got - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-6), k
+    assert worst < 0.02

@@ -70,14 +70,61 @@ class ToyLlamaLayer(nn.Module):
         return (x,)
 
 
+class ToyBertLayer(nn.Module):
+    """Q-Former style layer (lavis/models/blip2_models/Qformer.py BertLayer): self-attention over the queries, cross
+    attention to the image embeddings, feed forward; called POSITIONALLY by its encoder and returns a tuple."""
+
+    def __init__(self, d, d_enc, hidden):
+        super().__init__()
+        self.attention = nn.Module()
+        self.attention.self = nn.Module()
+        for n in ("query", "key", "value"):
+            setattr(self.attention.self, n, nn.Linear(d, d))
+        self.attention.output = nn.Module()
+        self.attention.output.dense = nn.Linear(d, d)
+        self.crossattention = nn.Module()
+        self.crossattention.self = nn.Module()
+        self.crossattention.self.query = nn.Linear(d, d)
+        self.crossattention.self.key = nn.Linear(d_enc, d)
+        self.crossattention.self.value = nn.Linear(d_enc, d)
+        self.crossattention.output = nn.Module()
+        self.crossattention.output.dense = nn.Linear(d, d)
+        self.intermediate_query = nn.Module()
+        self.intermediate_query.dense = nn.Linear(d, hidden)
+        self.output_query = nn.Module()
+        self.output_query.dense = nn.Linear(hidden, d)
+
+    @staticmethod
+    def _attend(q, k, v):
+        return torch.softmax(q @ k.transpose(-1, -2) / q.shape[-1] ** 0.5, dim=-1) @ v
+
+    def forward(self, hidden_states, attention_mask=None, head_mask=None, encoder_hidden_states=None,
+                encoder_attention_mask=None, past_key_value=None, output_attentions=False, query_length=0):
+        a = self.attention.self
+        h = hidden_states + self.attention.output.dense(
+            self._attend(a.query(hidden_states), a.key(hidden_states), a.value(hidden_states)))
+        c = self.crossattention.self
+        h = h + self.crossattention.output.dense(
+            self._attend(c.query(h), c.key(encoder_hidden_states), c.value(encoder_hidden_states)))
+        h = h + self.output_query.dense(F.gelu(self.intermediate_query.dense(h)))
+        return (h,)
+
+
 class ToyBlip(nn.Module):
     def __init__(self, d_vit=64, vit_hidden=128, n_vit=2, d_llm=64, ff=176, n_llm=2, llm_dtype=torch.bfloat16,
-                 seed=0):
+                 seed=0, n_qformer=0, d_q=48, n_query=8):
         super().__init__()
         g = torch.Generator().manual_seed(seed)
         self.visual_encoder = nn.Module()
         self.visual_encoder.blocks = nn.ModuleList([ToyViTBlock(d_vit, vit_hidden) for _ in range(n_vit)])
-        self.bridge = nn.Linear(d_vit, d_llm)
+        self.n_qformer = n_qformer
+        if n_qformer:
+            self.Qformer = nn.Module()
+            self.Qformer.bert = nn.Module()
+            self.Qformer.bert.encoder = nn.Module()
+            self.Qformer.bert.encoder.layer = nn.ModuleList([ToyBertLayer(d_q, d_vit, 2 * d_q) for _ in range(n_qformer)])
+            self.query_tokens = nn.Parameter(torch.zeros(1, n_query, d_q))
+        self.bridge = nn.Linear(d_q if n_qformer else d_vit, d_llm)
         self.llm_model = nn.Module()
         self.llm_model.config = types.SimpleNamespace(use_cache=True)
         self.llm_model.model = nn.Module()
@@ -100,6 +147,11 @@ class ToyBlip(nn.Module):
         x = batch["image"]
         for blk in self.visual_encoder.blocks:
             x = blk(x, None)
+        if self.n_qformer:
+            q = self.query_tokens.expand(x.shape[0], -1, -1)
+            for layer in self.Qformer.bert.encoder.layer:      # positional call, like BertEncoder.forward
+                q = layer(q, None, None, x, None, None, False, q.shape[1])[0]
+            x = q
         vis = self.bridge(x).to(self.llm_dtype)
         txt = self.embed(batch["text_ids"])
         h = torch.cat([vis, txt], dim=1)
@@ -120,6 +172,7 @@ def toy_batches(n, d_vit=64, n_img_tok=12, n_txt=20, seed=100, device="cpu"):
 
 
 def pruner_cfg(t5_keep, vit_keep, prune_n=0, prune_m=0, num_samples=8, **extra):
+    """extra: e.g. qformer_prune_spec="12-0.5-1.0-1.0" (vlmc extension), share_inputs=False."""
     cfg = dict(t5_prune_spec=f"24-{t5_keep}-1.0-1.0", vit_prune_spec=f"39-{vit_keep}-1.0-1.0",
                t5_pruning_method="none", vit_pruning_method="none", t5_model_prefix="llm_model",
                vit_model_prefix="visual_encoder", num_samples=num_samples, sparsity_ratio_granularity=None,

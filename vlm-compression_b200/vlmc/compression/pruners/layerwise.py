@@ -7,6 +7,7 @@ reference repeats this loop six times; here it is one function parameterised by
   prune_linear(name, module, wrapper, sparsity)            (mask selection / OBS sweep for one linear)
 Orchestration only: all arithmetic happens in the wrappers' CUDA kernels.
 """
+import contextlib
 import gc
 
 import torch
@@ -94,14 +95,15 @@ def adopt_statistics(follower, leader):
     follower._shared = group
 
 
-def capture_block_inputs(pruner, model, dataloader, model_prefix, n_samples, module_to_process, lora_model, vit):
+def capture_block_inputs(pruner, model, dataloader, model_prefix, n_samples, module_to_process, lora_model, vit,
+                         replay_all_args=False):
     """Swap block 0 for a catcher and run the model until n_samples inputs are recorded.
 
     wanda_pruner.py:213-273 (T5 / LLM keys :224-236) and :583-625 (ViT: rel_pos_bias).
     """
     layers = get_module_recursive(model, module_to_process)
     inps, caches = [], []
-    if vit:
+    if vit or replay_all_args:
         keys = None
     elif "t5_model" in pruner.model_prefix:
         keys = _T5_KEYS
@@ -118,6 +120,11 @@ def capture_block_inputs(pruner, model, dataloader, model_prefix, n_samples, mod
         def forward(self, inp, *args, dense=True, **kwargs):
             inp.requires_grad = False
             inps.append(inp)
+            if replay_all_args:
+                # Q-Former (BertEncoder calls its layers positionally): every argument after the hidden states is
+                # recorded and replayed as is
+                caches.append({"__args__": args, **kwargs})
+                raise _StopForward
             if vit:
                 rel = args[0] if args else kwargs.get("rel_pos_bias")
                 cache = {"rel_pos_bias": rel}
@@ -145,15 +152,15 @@ def capture_block_inputs(pruner, model, dataloader, model_prefix, n_samples, mod
 
 
 def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_samples, sparsity_ratio,
-                 lora_model, vit, make_wrapper, prune_linear):
+                 lora_model, vit, make_wrapper, prune_linear, replay_all_args=False):
     stem = getattr(model, model_prefix, None)
-    cfg = getattr(stem, "config", None) if not vit else None
+    cfg = getattr(stem, "config", None) if not (vit or replay_all_args) else None
     use_cache = getattr(cfg, "use_cache", None)
     if cfg is not None:
         cfg.use_cache = False
     with torch.no_grad():
         inps, outs, caches = capture_block_inputs(pruner, model, dataloader, model_prefix, n_samples,
-                                                  module_to_process, lora_model, vit)
+                                                  module_to_process, lora_model, vit, replay_all_args)
     n_samples = min(n_samples, len(inps))
     layers = get_module_recursive(model, module_to_process)
 
@@ -164,9 +171,13 @@ def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_s
             if share is not None:
                 share.begin_forward()
             with torch.no_grad():
-                ctx = model.maybe_autocast() if vit else model.maybe_autocast(dtype=torch.bfloat16)
+                if replay_all_args:          # Q-Former: runs in its own dtype, outside autocast
+                    ctx = contextlib.nullcontext()
+                else:
+                    ctx = model.maybe_autocast() if vit else model.maybe_autocast(dtype=torch.bfloat16)
                 with ctx:
-                    out = layer(inps[j], **caches[j])
+                    kw = dict(caches[j])
+                    out = layer(inps[j], *kw.pop("__args__", ()), **kw)
                     outs[j] = out if vit else out[0]
 
     for i in range(len(layers)):

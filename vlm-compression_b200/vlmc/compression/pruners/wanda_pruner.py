@@ -88,7 +88,8 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
                  num_samples=64, is_global=False, t5_model_prefix="t5_model", vit_model_prefix="visual_encoder",
                  sparsity_ratio_granularity=None, max_sparsity_per_layer=0.8, score_method="obd_avg",
                  num_data_first_stage=128, num_noise=1, sparsity_dict=None, noise_eps=1e-3,
-                 prune_per_model=False, peft_postfix="", prune_n=0, prune_m=0, share_inputs=True, **kwargs):
+                 prune_per_model=False, peft_postfix="", prune_n=0, prune_m=0, share_inputs=True,
+                 qformer_prune_spec=None, qformer_model_prefix="Qformer", **kwargs):
         super().__init__(model=model, data_loader=data_loader, prune_spec=None, is_strct_pruning=is_strct_pruning,
                          importance_scores_cache=importance_scores_cache,
                          keep_indices_or_masks_cache=keep_indices_or_masks_cache, is_global=is_global,
@@ -112,6 +113,11 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
         # linears fed by the same tensor accumulate their statistics once (layerwise.InputSharing); False restores
         # the reference's one-accumulation-per-linear schedule.  The results are identical either way.
         self.share_inputs = share_inputs
+        # EXTENSION (no reference behaviour to match): the reference never prunes the Q-Former (its pruners
+        # walk visual_encoder.blocks, t5/llm layers or OPT layers only).  With a "<layers>-<keep>-1.0-1.0" spec the 12
+        # BertLayers under <prefix>.bert.encoder.layer are pruned with the same per-linear rule as the language model.
+        self.qformer_prune_spec = qformer_prune_spec
+        self.qformer_model_prefix = qformer_model_prefix
 
     # ---- hooks the shared block loop calls ------------------------------------------------------
     def forward_to_cache(self, model, batch, lora_model=False):
@@ -148,9 +154,10 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
             self._pending_scores = []
 
     def _prune(self, model, dataloader, model_prefix, module_to_process, n_samples, sparsity_ratio,
-               lora_model=False, vit=False):
+               lora_model=False, vit=False, replay_all_args=False):
         return prune_blocks(self, model, dataloader, model_prefix, module_to_process, n_samples, sparsity_ratio,
-                            lora_model, vit, self.make_wrapper, self._prune_linear(vit, lora_model))
+                            lora_model, vit, self.make_wrapper, self._prune_linear(vit, lora_model),
+                            replay_all_args=replay_all_args)
 
     # ---- entry point (wanda_pruner.py:947-1044) -------------------------------------------------
     @print_time
@@ -170,6 +177,15 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
             self.model = self._prune(self.model, self.data_loader, self.vit_model_prefix,
                                      f"{self.vit_model_prefix}.blocks", self.num_samples, sparsity,
                                      lora_model=lora_model, vit=True)
+
+        if self.qformer_prune_spec is not None:
+            _, q_keep_ratio, _, _ = self.convert_spec_to_list(self.qformer_prune_spec)
+            if float(q_keep_ratio) < 1.0:
+                sparsity = global_sparsity_dict if global_sparsity_dict not in [None, "none"] \
+                    else self.get_sparsity(1 - q_keep_ratio, None)
+                self.model = self._prune(self.model, self.data_loader, self.qformer_model_prefix,
+                                         f"{self.qformer_model_prefix}.bert.encoder.layer", self.num_samples, sparsity,
+                                         lora_model=lora_model, vit=False, replay_all_args=True)
 
         if self.t5_prune_spec is not None and float(t5_keep_ratio) < 1.0:
             sparsity = global_sparsity_dict if global_sparsity_dict is not None \

@@ -48,6 +48,9 @@ SIGNATURES = {
     "vlmc_mask_pack": (_i, [_vp, _i, _i, _i64, _vp, _i64, _vp]),
     "vlmc_mask_apply_packed": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _i64, _vp, _i64, _i, _vp]),
     "vlmc_sparselora_merge": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _f, _vp, _i64, _i, _vp]),
+    "vlmc_sparselora_effective_weight": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _f, _vp, _i64, _i, _vp, _i64, _vp]),
+    "vlmc_sparselora_lora_grads_workspace_bytes": (_sz, [_i, _i, _i]),
+    "vlmc_sparselora_lora_grads": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "vlmc_hessian_prepare": (_i, [_vp, _i, _i64, _f, _vp, _vp, _vp]),
     "vlmc_hessian_add_damp": (_i, [_vp, _i, _i64, _vp, _vp]),
     "vlmc_chol_inv_upper": (_i, [_vp, _i, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
@@ -309,6 +312,52 @@ def sparselora_merge(W, A, B, scaling, keep_mask, remask=True):
                                        int(bool(remask)), _stream(W))
     _check("vlmc_sparselora_merge", st)
     return W
+
+
+def _lora_common(W, A, B, keep_mask):
+    _require_cuda(W, A, B, keep_mask)
+    if W.dim() != 2 or W.stride(1) != 1:
+        raise ValueError("W must be a 2-D row-major tensor")
+    if A.dtype != torch.float32 or B.dtype != torch.float32:
+        raise TypeError("lora_A / lora_B must be float32")
+    R, C = W.shape
+    rank = A.shape[0]
+    if A.shape != (rank, C) or B.shape != (R, rank):
+        raise ValueError("lora_A must be [r, C] and lora_B [R, r]")
+    if keep_mask is not None and (keep_mask.dtype != torch.bool or keep_mask.shape != W.shape or keep_mask.stride(1) != 1):
+        raise ValueError("mask must be a bool tensor shaped like W")
+    return R, C, rank, A.contiguous(), B.contiguous()
+
+
+def sparselora_effective_weight(W, A, B, scaling, keep_mask, sparse=True, out=None):
+    """K15 (lora.py:364-375): the weight of the masked training forward, (W + s*BA) * M or W * M + s*BA, in W's dtype.
+    W is left untouched; returns `out` [R, C]."""
+    R, C, rank, A, B = _lora_common(W, A, B, keep_mask)
+    if out is None:
+        out = torch.empty((R, C), dtype=W.dtype, device=W.device)
+    _require_cuda(out)
+    with torch.cuda.device(W.device):
+        st = load().vlmc_sparselora_effective_weight(W.data_ptr(), _dtype(W), R, C, W.stride(0), A.data_ptr(), B.data_ptr(),
+                                                     rank, float(scaling), keep_mask.data_ptr(), keep_mask.stride(0),
+                                                     int(bool(sparse)), out.data_ptr(), out.stride(0), _stream(W))
+    _check("vlmc_sparselora_effective_weight", st)
+    return out
+
+
+def sparselora_lora_grads(G, A, B, scaling, keep_mask, sparse=True):
+    """K16: (dA [r, C], dB [R, r]) fp32 from G = dL/dW_eff [R, C] (W's dtype): the autograd of K15's expression."""
+    R, C, rank, A, B = _lora_common(G, A, B, keep_mask if sparse else None)
+    lib = load()
+    dA = torch.empty((rank, C), dtype=torch.float32, device=G.device)
+    dB = torch.empty((R, rank), dtype=torch.float32, device=G.device)
+    ws = workspace(G, lib.vlmc_sparselora_lora_grads_workspace_bytes(R, C, rank))
+    with torch.cuda.device(G.device):
+        st = lib.vlmc_sparselora_lora_grads(G.data_ptr(), _dtype(G), R, C, G.stride(0),
+                                            keep_mask.data_ptr() if sparse else None, keep_mask.stride(0) if sparse else 0,
+                                            int(bool(sparse)), A.data_ptr(), B.data_ptr(), rank, float(scaling),
+                                            dA.data_ptr(), dB.data_ptr(), ws.data_ptr(), ws.numel(), _stream(G))
+    _check("vlmc_sparselora_lora_grads", st)
+    return dA, dB
 
 
 def hessian_accum(x, H, n_before, b, kc=0, slab_tokens=0):

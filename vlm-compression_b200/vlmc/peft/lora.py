@@ -3,8 +3,9 @@
 Kept verbatim from the reference interface: `mask` (registered bool buffer, True = kept), `sparse`,
 `scaling`, `lora_A`, `lora_B`, `fan_in_fan_out`, `merge()`, `forward(x, dense=False)`.
 merge() + the re-mask of train.py:634-637 run as ONE kernel (vlmc_sparselora_merge, K14).
-The masked training forward (lora.py:359-382) is a "next" row and is expressed with
-torch ops here; it is not part of the measured path.
+The masked training forward (lora.py:359-382) builds its weight with ONE kernel per step
+(vlmc_sparselora_effective_weight, K15) instead of ~5 elementwise passes over [R, C], and its backward gets the LoRA
+gradients from vlmc_sparselora_lora_grads (K16); the two dense GEMMs of a step stay library GEMMs.
 """
 import math
 
@@ -17,6 +18,38 @@ from vlmc import native
 
 def transpose(weight, fan_in_fan_out):
     return weight.T if fan_in_fan_out else weight
+
+
+class _MaskedLoRALinear(torch.autograd.Function):
+    """y = F.linear(x, W_eff, bias) with W_eff = (W + s*BA) * M (sparse) or W * M + s*BA (lora.py:364-375).
+    W_eff is rebuilt in backward (one K15 pass) instead of being kept alive between forward and backward."""
+
+    @staticmethod
+    def forward(ctx, x, W, A, B, bias, mask, scaling, sparse):
+        Af, Bf = A.detach().float(), B.detach().float()
+        w_eff = native.sparselora_effective_weight(W.detach(), Af, Bf, scaling, mask, sparse)
+        ctx.save_for_backward(x, W, A, B, mask)
+        ctx.scaling, ctx.sparse, ctx.has_bias = scaling, sparse, bias is not None
+        return F.linear(x, w_eff, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W, A, B, mask = ctx.saved_tensors
+        Af, Bf = A.detach().float(), B.detach().float()
+        gx = dA = dB = gbias = None
+        gy2 = gy.reshape(-1, gy.shape[-1])
+        if ctx.needs_input_grad[0]:
+            w_eff = native.sparselora_effective_weight(W.detach(), Af, Bf, ctx.scaling, mask, ctx.sparse)
+            gx = (gy2 @ w_eff).reshape(x.shape)
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            G = gy2.t() @ x.reshape(-1, x.shape[-1]).to(gy2.dtype)          # dL/dW_eff, in the layer's dtype like autograd
+            if G.dtype != W.dtype:
+                G = G.to(W.dtype)
+            dA, dB = native.sparselora_lora_grads(G.contiguous(), Af, Bf, ctx.scaling, mask, ctx.sparse)
+            dA, dB = dA.to(A.dtype), dB.to(B.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[4]:
+            gbias = gy2.sum(0)
+        return gx, None, dA, dB, gbias, None, None, None
 
 
 class LoraLayer:
@@ -60,13 +93,15 @@ class Linear(nn.Linear, LoraLayer):
         if dense or self.disable_adapters or not (self.r > 0 and not self.merged):
             result = F.linear(x, transpose(self.weight, self.fan_in_fan_out), bias=self.bias)
         else:
-            delta = transpose((self.lora_B.weight @ self.lora_A.weight).to(previous_dtype),
-                              self.fan_in_fan_out) * self.scaling
-            if self.sparse:      # lora.py:364-369
-                w = (self.weight + delta) * self.mask
-            else:                # lora.py:370-375
-                w = self.weight * self.mask + delta
-            result = F.linear(x, transpose(w, self.fan_in_fan_out), bias=self.bias)
+            # one fused kernel builds the masked, LoRA-corrected weight (K15); K16 serves the backward.  No host path.
+            if self.fan_in_fan_out or self.r > 16:
+                raise NotImplementedError("fan_in_fan_out layouts and ranks above 16 are not on the InstructBLIP path")
+            if not self.weight.is_cuda:
+                raise RuntimeError("vlmc has no CPU path: the masked LoRA forward needs CUDA tensors "
+                                   f"(got device {self.weight.device})")
+            result = _MaskedLoRALinear.apply(x.to(previous_dtype) if x.dtype != previous_dtype else x, self.weight,
+                                             self.lora_A.weight, self.lora_B.weight, self.bias, self.mask,
+                                             float(self.scaling), bool(self.sparse))
         if result.dtype != previous_dtype:
             result = result.to(previous_dtype)
         return result
