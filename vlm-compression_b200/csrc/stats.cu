@@ -155,8 +155,18 @@ colstats_kernel(const StatsParams p) {
   const int tile_c0 = blockIdx.x * kCX * V;
   for (int c = tile_c0 + threadIdx.x; c < tile_c0 + kCX * V && c < p.C; c += kStatsThreads) {
     if (!DSNOT) {
+      // the partials of all chunks, added in chunk order; loads are issued 16 at a time so the (serial, last-CTA) tail
+      // of the launch costs ~nchunks/16 L2 round trips instead of nchunks
       double tot = 0.0;
-      for (int64_t k = 0; k < nchunks; ++k) tot += (double)__ldcg(p.part + (size_t)k * p.C + c);
+      int64_t k = 0;
+      for (; k + 16 <= nchunks; k += 16) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldcg(p.part + (size_t)(k + u) * p.C + c);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) tot += (double)v[u];
+      }
+      for (; k < nchunks; ++k) tot += (double)__ldcg(p.part + (size_t)k * p.C + c);
       // wanda_pruner.py:77,81 -- scaler_row *= n/(n+b); scaler_row += ||x||^2 / (n+b)
       float s = __fmul_rn(p.scaler_row[c], ratio);
       p.scaler_row[c] = __fadd_rn(s, __fdiv_rn((float)tot, n_after_f));
