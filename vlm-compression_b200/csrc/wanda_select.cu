@@ -73,9 +73,12 @@ __device__ __forceinline__ void rs_update(const uint32_t (&p)[4], const int (&c)
   }
 }
 
-// One warp: estimate the per-row threshold from a sample of 32 weight vectors spread over the matrix (row and column
-// strided): the k/C quantile of the sample's scores by bit-space bisection.  Seeds the first row of every warp of
-// rowselect_kernel; a miss only costs that row an extra pass.
+// One warp: estimate the per-row threshold from a sample of 128 weight vectors (4 per lane, 1024 scores for 16-bit
+// weights) spread over the matrix (row and column strided): the k/C quantile of the sample's scores by bit-space
+// bisection.  Seeds the first row of every warp of rowselect_kernel; a miss only costs that row an extra pass.  With
+// ~2 rows per warp at R = 4096 more than half of all rows ARE first rows, so the estimate has to be good enough for the
+// same narrow bracket the row-to-row seeding uses (1024 samples: ~1.6 % of probability mass at the median).
+constexpr int kSeedVecs = 4;
 template <typename T>
 __global__ void __launch_bounds__(32)
 rowselect_seed_kernel(const T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ sq, int k,
@@ -83,14 +86,18 @@ rowselect_seed_kernel(const T* __restrict__ W, int64_t ldw, int R, int C, const 
   constexpr int V = Elem<T>::kVec;
   const int lane = threadIdx.x;
   const int nvec = C / V;
-  const int vi = (int)(((int64_t)lane * nvec) / 32) % (nvec > 0 ? nvec : 1);
-  const int row = (int)(((int64_t)lane * R) / 32);
-  float f[V];
-  Elem<T>::unpack(*reinterpret_cast<const uint4*>(W + (int64_t)row * ldw + vi * V), f);
-  uint32_t sk[V];
+  uint32_t sk[kSeedVecs * V];
 #pragma unroll
-  for (int e = 0; e < V; ++e) sk[e] = __float_as_uint(__fmul_rn(fabsf(f[e]), sq[vi * V + e]));
-  const int ns = 32 * V;
+  for (int u = 0; u < kSeedVecs; ++u) {
+    const int s = lane * kSeedVecs + u;                       // sample index 0 .. 127
+    const int vi = (int)(((int64_t)s * nvec) / (32 * kSeedVecs)) % (nvec > 0 ? nvec : 1);
+    const int row = (int)(((int64_t)((s * 37) % (32 * kSeedVecs)) * R) / (32 * kSeedVecs));   // rows decorrelated from columns
+    float f[V];
+    Elem<T>::unpack(*reinterpret_cast<const uint4*>(W + (int64_t)row * ldw + vi * V), f);
+#pragma unroll
+    for (int e = 0; e < V; ++e) sk[u * V + e] = __float_as_uint(__fmul_rn(fabsf(f[e]), sq[vi * V + e]));
+  }
+  const int ns = 32 * kSeedVecs * V;
   int ks = (int)(((int64_t)k * ns + C / 2) / C);
   if (ks < 1) ks = 1;
   if (ks > ns) ks = ns;
@@ -101,7 +108,7 @@ rowselect_seed_kernel(const T* __restrict__ W, int64_t ldw, int R, int C, const 
                             clampu(slo + 4.0 * q, slo, shi)};
     uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
+    for (int e = 0; e < kSeedVecs * V; ++e) {
       c0 += sk[e] < sp[0] ? 1u : 0u; c1 += sk[e] < sp[1] ? 1u : 0u;
       c2 += sk[e] < sp[2] ? 1u : 0u; c3 += sk[e] < sp[3] ? 1u : 0u;
     }
@@ -224,7 +231,7 @@ rowselect_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* __re
       int glo = 0, ghi = C;      // count(key < lo) = glo <= k - 1 < ghi = count(key < hi)
       uint32_t cl = 0, ch = 0;   // keys in [cl, ch) are on the lists, cb = count(key < cl)
       int cb = 0, lcount = 0;
-      bool have = false, uniform = false, first = true, seeded = false, wide = false;
+      bool have = false, uniform = false, first = true, seeded = false;
       int missed = 0;            // after a seeded pass: +1 threshold above the bracket, -1 below
       uint32_t seed_dlt = 0u;
       while (hi - lo > 1u) {
@@ -232,20 +239,13 @@ rowselect_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* __re
         const int m = ghi - glo;
         if (first && prev_v > 4194304u && prev_v < 0x7f000000u) {
           // two pivots around the seed, everything between them collected: +-6.7 % around the previous row's
-          // threshold, +-12 % around the matrix-wide sample estimate for a warp's first row
+          // threshold, +-10 % around the matrix-wide sample estimate for a warp's first row
           // (the row-to-row spread of the threshold and the room on the lists both shrink with sqrt(C))
-          const uint32_t dlt = from_sample ? 1400000u : row_dlt;
+          const uint32_t dlt = from_sample ? row_dlt + (row_dlt >> 1) : row_dlt;
           seed_dlt = dlt;
           p[0] = prev_v - dlt; p[1] = p[0]; p[3] = prev_v + dlt; p[2] = p[3];
           seeded = true;
-          if (from_sample && C > 6144) {   // too many keys in a +-12 % band for the lists: count only, collect next pass
-            p[1] = prev_v - 350000u; p[2] = prev_v + 350000u;
-            cl = 0u; ch = 0u;
-            seeded = false;
-            wide = true;
-          } else {
-            cl = p[0]; ch = p[3];
-          }
+          cl = p[0]; ch = p[3];
         } else if (missed != 0 && m > 8 * 32) {
           // the seeded bracket missed: exponential search away from the seed on the side the threshold lies (one
           // pass instead of a ~6-pass uniform search of the whole bit range)
@@ -268,9 +268,8 @@ rowselect_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* __re
         first = false;
         int c[4];
         const bool fits = seeded ? stream(Two{}, p, cl, ch, c, lcount) : stream(Four{}, p, cl, ch, c, lcount);
-        if (seeded || wide) missed = (k - 1 >= c[3]) ? 1 : ((c[0] > k - 1) ? -1 : 0);
+        if (seeded) missed = (k - 1 >= c[3]) ? 1 : ((c[0] > k - 1) ? -1 : 0);
         seeded = false;
-        wide = false;
         const bool whole = cl == lo && ch == hi;
         const int below = whole ? glo : c[0];
         const bool inside = whole || (ch != 0u && c[0] <= k - 1 && k - 1 < c[3]);
