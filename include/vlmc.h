@@ -194,6 +194,15 @@ int vlmc_sparselora_lora_grads(const void* G, int dtype, int R, int C, int64_t l
                                float* dA, float* dB, void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * K17  Non-zero element counts of up to 64 tensors of one dtype per call ("Remaining Proportion",
+ * evaluate_old.py:331-334: sum((param != 0).float().sum() for param in model.parameters())).  `items` is a HOST array
+ * read during the call; out[i] (device, uint64) receives the count of items[i].  x != 0 as torch evaluates it (-0.0 is
+ * zero, NaN is not).  Tensors must be contiguous; any element alignment.
+ */
+typedef struct vlmc_tensor_item { const void* ptr; int64_t numel; } vlmc_tensor_item;
+int vlmc_count_nonzero_batch(const vlmc_tensor_item* items, int count, int dtype, unsigned long long* out, void* stream);
+
+/*
  * K3  SparseGPT Hessian accumulation.  Replaces SparseGPT.add_batch, sparsegpt_pruner.py:68-79:
  *   H <- H * n_before/(n_before+b) + (2/(n_before+b)) * X^T X
  * x: [T, C] row-major fp16 / bf16 / fp32 (one add_batch call, T = b * seq_len); H: [C, C] fp32, full and symmetric.

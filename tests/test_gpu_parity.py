@@ -1098,3 +1098,32 @@ def test_lora_forward_vicuna_size_properties(native):
     E = (G * mask).float() * 2.0
     assert float((dB - E @ A.T).abs().max()) <= 1e-4 * float(dB.abs().max())
     assert float((dA - B.T @ E).abs().max()) <= 1e-4 * float(dA.abs().max())
+
+
+# ------------------------------------------------------------------------------------------- K17
+def test_count_nonzero_matches_the_reference_expression(native):
+    """vlmc_count_nonzero_batch against evaluate_old.py:331-334, sum((param != 0).float().sum()): mixed dtypes, ragged
+    sizes, unaligned views, -0.0 (zero) and NaN (not zero), more than 64 tensors, an empty tensor."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    ts = []
+    for i in range(70):
+        n = [1, 7, 16, 1000, 16384, 16385, 70001][i % 7]
+        dt = [torch.float16, torch.bfloat16, torch.float32][i % 3]
+        t = torch.randn(n + 3, device="cuda", generator=g).to(dt)
+        t[torch.rand(n + 3, device="cuda", generator=g) < 0.4] = 0
+        ts.append(t[1 + (i % 2): 1 + (i % 2) + n])             # odd offsets: not 16-byte aligned
+    ts[5][:4] = torch.tensor([-0.0, float("nan"), 0.0, float("inf")], device="cuda").to(ts[5].dtype)
+    ts.append(torch.empty(0, device="cuda"))
+    ts.append((torch.randn(300, 500, device="cuda", generator=g) * (torch.rand(300, 500, device="cuda", generator=g) < 0.5)).half().t())
+    got = native.count_nonzero(ts).cpu().tolist()
+    want = [int((t != 0).float().sum().item()) for t in ts]
+    assert got == want
+    from vlmc import checkpoint
+    import toy_model
+    torch.manual_seed(0)
+    model = toy_model.ToyBlip(n_vit=1, n_llm=1).eval().cuda()
+    model.llm_model.model.layers[0].mlp.down_proj.weight.data[:, ::2] = 0
+    pct, nz, total = checkpoint.remaining_proportion(model)
+    ref_nz = sum((p != 0).float().sum() for p in model.parameters())
+    assert nz == int(ref_nz.item()) and total == sum(p.numel() for p in model.parameters())
+    assert abs(pct - float(ref_nz) / total * 100) < 1e-9

@@ -124,3 +124,38 @@ def test_linear_assignment_spreads_the_chains():
     for s, o in zip(shapes, parallel.assign_linears(shapes, 2)):
         loads[o] += parallel.chain_cost_ms(*s)
     assert max(loads) / sum(loads) < 0.6
+
+
+def test_pruned_checkpoint_layout_matches_the_reference_flow(tmp_path, built_lib):
+    """vlmc.checkpoint writes the four artefacts of evaluate_old.py:336-378 under the same folders and names,
+    and its loaders apply the reference's prefix rules (:246-290)."""
+    import torch
+    import yaml
+    import toy_model
+    from vlmc import checkpoint
+    torch.manual_seed(0)
+    model = toy_model.ToyBlip(n_vit=1, n_llm=1).eval()
+    lin = model.llm_model.model.layers[0].mlp.down_proj
+    lin.weight.data[:, ::2] = 0
+    setattr(lin.weight, "importance_score", 0.25)
+    paths = checkpoint.save_pruned_model(model, "job7", "blipt5_wanda_pruner", sparsity_dict={"a.weight": 0.5},
+                                         start_time=None, root=str(tmp_path))
+    assert paths["pruned_checkpoint"].endswith("pruned_checkpoint/V+L/blipt5_wanda_pruner/job7.pth")
+    assert paths["sparsity_dict"].endswith("sparsity_dict/job7.yaml")
+    assert paths["training_statistics"].endswith("training_statistics/job7.yaml")
+    assert paths["importance_scores"].endswith("importance_scores/job7.pth")
+    assert yaml.safe_load(open(paths["sparsity_dict"])) == {"a.weight": 0.5}
+    assert set(yaml.safe_load(open(paths["training_statistics"]))) == {"memory", "time"}
+    assert torch.load(paths["importance_scores"]) == {"llm_model.model.layers.0.mlp.down_proj.weight": 0.25}
+    state = torch.load(paths["pruned_checkpoint"])
+    assert set(state) == set(model.state_dict())
+    # loaders: a fresh model takes the pruned language model (prefix stripped) and vision tower (missing keys tolerated)
+    fresh = toy_model.ToyBlip(n_vit=1, n_llm=1, seed=1).eval()
+    assert checkpoint.load_pruned_language_model(fresh, paths["pruned_checkpoint"]) == "llm_model"
+    assert torch.equal(fresh.llm_model.model.layers[0].mlp.down_proj.weight, lin.weight)
+    vis = {("visual." + k): v for k, v in model.visual_encoder.state_dict().items() if "qkv" in k}
+    vis["visual.not_in_model"] = torch.zeros(1)
+    torch.save(vis, tmp_path / "vit.pth")
+    assert checkpoint.load_pruned_vision_model(fresh, str(tmp_path / "vit.pth")) == "visual."
+    assert torch.equal(fresh.visual_encoder.blocks[0].attn.qkv.weight, model.visual_encoder.blocks[0].attn.qkv.weight)
+    assert not torch.equal(fresh.visual_encoder.blocks[0].mlp.fc1.weight, model.visual_encoder.blocks[0].mlp.fc1.weight)

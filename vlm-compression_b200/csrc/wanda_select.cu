@@ -714,9 +714,11 @@ static int launch_rowselect(void* W, int R, int C, int64_t ldw, const float* sq,
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRsWarps * 32, 0);
   if (per_sm < 1) per_sm = 1;
-  int grid = kNumSMs * per_sm;
-  const int need = (R + kRsWarps - 1) / kRsWarps;
-  if (grid > need) grid = need;
+  // every warp gets the same number of rows (the last wave of a 1.7-rows-per-warp split would idle a quarter of the warps)
+  const int resident_warps = kNumSMs * per_sm * kRsWarps;
+  const int rows_per_warp = (R + resident_warps - 1) / resident_warps;
+  int grid = (R + kRsWarps * rows_per_warp - 1) / (kRsWarps * rows_per_warp);
+  if (grid < 1) grid = 1;
   kern<<<grid, kRsWarps * 32, 0, st>>>(reinterpret_cast<T*>(W), ldw, R, C, sq, k, zero_w, mask, ldm, row_sum, seed);
   return check_launch();
 }

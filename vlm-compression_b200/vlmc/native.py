@@ -51,6 +51,7 @@ SIGNATURES = {
     "vlmc_sparselora_effective_weight": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _f, _vp, _i64, _i, _vp, _i64, _vp]),
     "vlmc_sparselora_lora_grads_workspace_bytes": (_sz, [_i, _i, _i]),
     "vlmc_sparselora_lora_grads": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
+    "vlmc_count_nonzero_batch": (_i, [_vp, _i, _i, _vp, _vp]),
     "vlmc_hessian_prepare": (_i, [_vp, _i, _i64, _f, _vp, _vp, _vp]),
     "vlmc_hessian_add_damp": (_i, [_vp, _i, _i64, _vp, _vp]),
     "vlmc_chol_inv_upper": (_i, [_vp, _i, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
@@ -312,6 +313,42 @@ def sparselora_merge(W, A, B, scaling, keep_mask, remask=True):
                                        int(bool(remask)), _stream(W))
     _check("vlmc_sparselora_merge", st)
     return W
+
+
+class TensorItem(ctypes.Structure):
+    """vlmc_tensor_item (include/vlmc.h)."""
+    _fields_ = [("ptr", _vp), ("numel", _i64)]
+
+
+def count_nonzero(tensors):
+    """K17: number of non-zero elements of every tensor (evaluate_old.py:331-334), as one int64 device tensor
+    [len(tensors)] in the order given.  Tensors of one device; float32 / float16 / bfloat16; non-contiguous ones are
+    copied.  64 tensors of one dtype per launch."""
+    tensors = list(tensors)
+    if not tensors:
+        return torch.zeros(0, dtype=torch.int64)
+    _require_cuda(*tensors)
+    dev = tensors[0].device
+    out = torch.zeros(len(tensors), dtype=torch.int64, device=dev)
+    lib = load()
+    by_dtype = {}
+    for i, t in enumerate(tensors):
+        by_dtype.setdefault(_dtype(t), []).append(i)
+    keep = []                                              # contiguous copies must outlive the launches
+    with torch.cuda.device(dev):
+        for dt, idx in by_dtype.items():
+            for c0 in range(0, len(idx), 64):
+                chunk = idx[c0:c0 + 64]
+                items = (TensorItem * len(chunk))()
+                for j, i in enumerate(chunk):
+                    t = tensors[i] if tensors[i].is_contiguous() else tensors[i].contiguous()
+                    keep.append(t)
+                    items[j] = TensorItem(t.data_ptr() if t.numel() else None, t.numel())
+                part = torch.empty(len(chunk), dtype=torch.int64, device=dev)
+                _check("vlmc_count_nonzero_batch",
+                       lib.vlmc_count_nonzero_batch(items, len(chunk), dt, part.data_ptr(), _stream(part)))
+                out[torch.tensor(chunk, device=dev)] = part
+    return out
 
 
 def _lora_common(W, A, B, keep_mask):
