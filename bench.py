@@ -812,6 +812,9 @@ def config5_lora_and_hessian_sweep(torch, native, dev, inputs):
         return a.elapsed_time(b) / reps
     ms = timed(lambda: [native.sparselora_merge(W, A, B, 2.0, M, remask=True) for W, A, B, M, _ in items])
     out["sparselora_merge_block"] = {"ms": ms, "achieved_gbs": nbytes / ms / 1e6, "bytes": nbytes}
+    ms = timed(lambda: native.sparselora_merge_batch([i[0] for i in items], [i[1] for i in items], [i[2] for i in items],
+                                                     [2.0] * len(items), [i[3] for i in items], remask=True))
+    out["sparselora_merge_block_one_launch"] = {"ms": ms, "achieved_gbs": nbytes / ms / 1e6, "bytes": nbytes}
     ms = timed(lambda: [native.sparselora_effective_weight(W, A, B, 2.0, M, True, out=o) for W, A, B, M, o in items])
     out["sparselora_forward_weight_block"] = {"ms": ms, "achieved_gbs": nbytes / ms / 1e6, "bytes": nbytes}
     del items

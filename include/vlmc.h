@@ -171,6 +171,17 @@ int vlmc_sparselora_merge(void* W, int dtype, int R, int C, int64_t ldw,
                           void* stream);
 
 /*
+ * K14 for up to 16 LoRA linears in one launch (train.py:626-637 merges module by module).  `items` is a HOST array
+ * read during the call.  rank <= 8; same results as vlmc_sparselora_merge per item.
+ */
+typedef struct vlmc_merge_item {
+  void* W; int64_t ldw; int R; int C;
+  const float* A; const float* B; int rank; float scaling;
+  const uint8_t* keep_mask; int64_t ldm;
+} vlmc_merge_item;
+int vlmc_sparselora_merge_batch(const vlmc_merge_item* items, int count, int dtype, int remask, void* stream);
+
+/*
  * K15  SparseLoRA masked training forward, the weight part.  Replaces the weight expression of Linear.forward
  * (r > 0, not merged), lora.py:364-375, that the reference re-materialises every step:
  *   sparse != 0:  out = ((W + ((B @ A).to(dtype) * scaling)) * mask)        (:364-369)

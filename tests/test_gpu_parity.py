@@ -1127,3 +1127,24 @@ def test_count_nonzero_matches_the_reference_expression(native):
     ref_nz = sum((p != 0).float().sum() for p in model.parameters())
     assert nz == int(ref_nz.item()) and total == sum(p.numel() for p in model.parameters())
     assert abs(pct - float(ref_nz) / total * 100) < 1e-9
+
+
+@pytest.mark.parametrize("tag", ["bf16", "f16", "f32"])
+def test_merge_batch_equals_per_linear(native, tag):
+    """vlmc_sparselora_merge_batch (several LoRA linears in one launch) against vlmc_sparselora_merge per linear:
+    bit for bit, ragged shapes, mixed ranks (a rank above 8 takes the per-linear kernel), with and without re-mask."""
+    shapes = [(48, 1024, 8), (37, 2064, 4), (130, 3120, 2), (70, 48, 8), (257, 1040, 12), (64, 64, 1)]
+    g = torch.Generator(device="cuda").manual_seed(9)
+    Ws = [weights(R, C, 700 + i, DT[tag], 0.05).cuda() for i, (R, C, _) in enumerate(shapes)]
+    As = [torch.randn(r, C, device="cuda", generator=g) * 0.1 for _, C, r in shapes]
+    Bs = [torch.randn(R, r, device="cuda", generator=g) * 0.1 for R, _, r in shapes]
+    Ms = [torch.rand(R, C, device="cuda", generator=g) < 0.5 for R, C, _ in shapes]
+    sc = [16.0 / r for _, _, r in shapes]
+    for remask in (True, False):
+        ref = [W.clone() for W in Ws]
+        for W, A, B, s, M in zip(ref, As, Bs, sc, Ms):
+            native.sparselora_merge(W, A, B, s, M, remask=remask)
+        got = [W.clone() for W in Ws]
+        native.sparselora_merge_batch(got, As, Bs, sc, Ms, remask=remask)
+        for a, b in zip(ref, got):
+            assert torch.equal(a, b)

@@ -67,6 +67,85 @@ lora_merge_kernel(T* __restrict__ W, int64_t ldw, int R, int C,
   }
 }
 
+// ---- all LoRA linears of a block (or of the model, 16 at a time) in ONE launch -------------------------------------
+// train.py:626-637 merges module by module; the matrices are 34-90 MB, so one launch per linear spends a third of its
+// time ramping up and draining (measured: 7 launches, 2.6 TB/s).  Same walk as nm_batch_kernel: the linears are one
+// list of work units (kMbRows rows x 1024 columns) that a fully resident grid strides over.
+constexpr int kMbMax = 16;
+constexpr int kMbRows = 64;       // rows per unit: the rank x 8 A values a thread keeps in registers are reloaded per unit
+struct MergeBatchItem {
+  void* W; int64_t ldw; int R, C; const float* A; const float* B; int rank; float scaling;
+  const uint8_t* mask; int64_t ldm; int coltiles;
+};
+struct MergeBatch { MergeBatchItem it[kMbMax]; int unit_begin[kMbMax + 1]; int count; };
+
+template <typename T>
+__global__ void __launch_bounds__(kMergeThreads)
+lora_merge_batch_kernel(const __grid_constant__ MergeBatch b, int remask) {
+  constexpr int V = Elem<T>::kVec;
+  constexpr int RK = kMaxRankRegs;
+  const int total = b.unit_begin[b.count];
+  for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    int p = 0;
+    while (unit >= b.unit_begin[p + 1]) ++p;
+    const MergeBatchItem& it = b.it[p];
+    const int local = unit - b.unit_begin[p];
+    const int ct = local % it.coltiles, rb = local / it.coltiles;
+    const int col = (ct * kMergeThreads + threadIdx.x) * V;
+    if (col >= it.C) continue;
+    float a[RK][V];
+#pragma unroll
+    for (int kk = 0; kk < RK; ++kk)
+#pragma unroll
+      for (int q = 0; q < V; q += 4) {
+        float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kk < it.rank) av = __ldg(reinterpret_cast<const float4*>(it.A + (int64_t)kk * it.C + col + q));
+        a[kk][q] = av.x; a[kk][q + 1] = av.y; a[kk][q + 2] = av.z; a[kk][q + 3] = av.w;
+      }
+    T* W = reinterpret_cast<T*>(it.W);
+    const int row_end = (rb + 1) * kMbRows < it.R ? (rb + 1) * kMbRows : it.R;
+    constexpr int kRows = 4;                 // rows in flight per thread
+    for (int row0 = rb * kMbRows; row0 < row_end; row0 += kRows) {
+      uint4 wv[kRows];
+      uint2 mv[kRows];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        if (row0 + r < row_end) {
+          wv[r] = ld_stream(W + (int64_t)(row0 + r) * it.ldw + col);
+          const uint8_t* mp = it.mask + (int64_t)(row0 + r) * it.ldm + col;
+          if (V == 8) mv[r] = *reinterpret_cast<const uint2*>(mp);
+          else mv[r] = make_uint2(*reinterpret_cast<const uint32_t*>(mp), 0u);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const int row = row0 + r;
+        if (row >= row_end) break;
+        const uint32_t mb[2] = {mv[r].x, mv[r].y};
+        float f[V], acc[V];
+        Elem<T>::unpack(wv[r], f);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = 0.f;
+        const float* brow = it.B + (int64_t)row * it.rank;
+#pragma unroll
+        for (int kk = 0; kk < RK; ++kk) {
+          const float bv = kk < it.rank ? __ldg(brow + kk) : 0.f;
+#pragma unroll
+          for (int e = 0; e < V; ++e) acc[e] = fmaf(bv, a[kk][e], acc[e]);   // k ascending, like SGEMM
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const bool keep = (mb[e / 4] >> (8 * (e % 4))) & 0xffu;
+          const float delta = __fmul_rn(acc[e], it.scaling);
+          const float merged = __fadd_rn(f[e], delta);
+          f[e] = keep ? merged : (remask ? 0.f : f[e]);
+        }
+        st_stream(W + (int64_t)row * it.ldw + col, Elem<T>::pack(f));
+      }
+    }
+  }
+}
+
 }  // namespace vlmc
 
 extern "C" int vlmc_sparselora_merge(void* W, int dtype, int R, int C, int64_t ldw,
@@ -96,5 +175,41 @@ extern "C" int vlmc_sparselora_merge(void* W, int dtype, int R, int C, int64_t l
     VLMC_DISPATCH_DTYPE(dtype, (lora_merge_kernel<scalar_t, 0><<<grid, kMergeThreads, 0, st>>>(
                                    reinterpret_cast<scalar_t*>(W), ldw, R, C, A, B, rank, scaling, keep_mask, ldm, remask)));
   }
+  return check_launch();
+}
+
+extern "C" int vlmc_sparselora_merge_batch(const vlmc_merge_item* items, int count, int dtype, int remask, void* stream) {
+  using namespace vlmc;
+  if (!items || count < 1 || count > kMbMax) return VLMC_ERR_BAD_ARG;
+  if (dtype != VLMC_F32 && dtype != VLMC_F16 && dtype != VLMC_BF16) return VLMC_ERR_BAD_ARG;
+  const int V = dtype == VLMC_F32 ? 4 : 8;
+  MergeBatch b;
+  b.count = count;
+  b.unit_begin[0] = 0;
+  for (int i = 0; i < count; ++i) {
+    const vlmc_merge_item& s = items[i];
+    if (!s.W || !s.A || !s.B || !s.keep_mask || s.R < 1 || s.C < 1 || s.rank < 1 || s.ldw < s.C || s.ldm < s.C) return VLMC_ERR_BAD_ARG;
+    if (s.rank > kMaxRankRegs) return VLMC_ERR_UNSUPPORTED;     // larger ranks: vlmc_sparselora_merge per linear
+    if (s.C % V != 0 || s.ldw % V != 0 || s.ldm % V != 0 || ((uintptr_t)s.W & 15) != 0 || ((uintptr_t)s.keep_mask & 7) != 0 ||
+        ((uintptr_t)s.A & 15) != 0 || s.C % 4 != 0)
+      return VLMC_ERR_UNSUPPORTED;
+    if (!is_device_ptr(s.W) || !is_device_ptr(s.A) || !is_device_ptr(s.B) || !is_device_ptr(s.keep_mask)) return VLMC_ERR_NOT_DEVICE;
+    MergeBatchItem& it = b.it[i];
+    it.W = s.W; it.ldw = s.ldw; it.R = s.R; it.C = s.C; it.A = s.A; it.B = s.B; it.rank = s.rank; it.scaling = s.scaling;
+    it.mask = s.keep_mask; it.ldm = s.ldm;
+    it.coltiles = (s.C / V + kMergeThreads - 1) / kMergeThreads;
+    const int64_t units = (int64_t)it.coltiles * ((s.R + kMbRows - 1) / kMbRows);
+    if (b.unit_begin[i] + units > 0x7fffffff) return VLMC_ERR_UNSUPPORTED;
+    b.unit_begin[i + 1] = b.unit_begin[i] + (int)units;
+  }
+  const int total = b.unit_begin[count];
+  cudaStream_t st = (cudaStream_t)stream;
+  VLMC_DISPATCH_DTYPE(dtype, {
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lora_merge_batch_kernel<scalar_t>, kMergeThreads, 0);
+    int grid = kNumSMs * (per_sm < 1 ? 1 : per_sm);
+    if (grid > total) grid = total;
+    lora_merge_batch_kernel<scalar_t><<<grid, kMergeThreads, 0, st>>>(b, remask);
+  });
   return check_launch();
 }

@@ -48,6 +48,7 @@ SIGNATURES = {
     "vlmc_mask_pack": (_i, [_vp, _i, _i, _i64, _vp, _i64, _vp]),
     "vlmc_mask_apply_packed": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _i64, _vp, _i64, _i, _vp]),
     "vlmc_sparselora_merge": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _f, _vp, _i64, _i, _vp]),
+    "vlmc_sparselora_merge_batch": (_i, [_vp, _i, _i, _i, _vp]),
     "vlmc_sparselora_effective_weight": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _f, _vp, _i64, _i, _vp, _i64, _vp]),
     "vlmc_sparselora_lora_grads_workspace_bytes": (_sz, [_i, _i, _i]),
     "vlmc_sparselora_lora_grads": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
@@ -313,6 +314,39 @@ def sparselora_merge(W, A, B, scaling, keep_mask, remask=True):
                                        int(bool(remask)), _stream(W))
     _check("vlmc_sparselora_merge", st)
     return W
+
+
+class MergeItem(ctypes.Structure):
+    """vlmc_merge_item (include/vlmc.h)."""
+    _fields_ = [("W", _vp), ("ldw", _i64), ("R", _i), ("C", _i), ("A", _vp), ("B", _vp), ("rank", _i), ("scaling", _f),
+                ("keep_mask", _vp), ("ldm", _i64)]
+
+
+def sparselora_merge_batch(Ws, As, Bs, scalings, keep_masks, remask=True):
+    """K14 for several LoRA linears of one dtype in one launch per 16 (train.py:626-637 merges module by module).
+    Same results as sparselora_merge per linear; ranks above 8 fall back to the per-linear kernel."""
+    keep = []
+    todo = []
+    for W, A, B, s, M in zip(Ws, As, Bs, scalings, keep_masks):
+        R, C, rank, A, B = _lora_common(W, A, B, M)
+        if rank > 8:
+            sparselora_merge(W, A, B, s, M, remask=remask)
+            continue
+        keep += [A, B]
+        todo.append(MergeItem(W.data_ptr(), W.stride(0), R, C, A.data_ptr(), B.data_ptr(), rank, float(s), M.data_ptr(),
+                              M.stride(0)))
+    if not todo:
+        return
+    lib = load()
+    dt, ref = _dtype(Ws[0]), Ws[0]
+    if any(_dtype(W) != dt for W in Ws):
+        raise TypeError("all weights of one call must share a dtype")
+    with torch.cuda.device(ref.device):
+        for c0 in range(0, len(todo), 16):
+            chunk = todo[c0:c0 + 16]
+            items = (MergeItem * len(chunk))(*chunk)
+            _check("vlmc_sparselora_merge_batch",
+                   lib.vlmc_sparselora_merge_batch(items, len(chunk), dt, int(bool(remask)), _stream(ref)))
 
 
 class TensorItem(ctypes.Structure):

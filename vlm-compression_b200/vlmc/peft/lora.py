@@ -122,3 +122,21 @@ class Linear(nn.Linear, LoraLayer):
             native.sparselora_merge(self.weight.data, self.lora_A.weight.data.float(),
                                     self.lora_B.weight.data.float(), self.scaling, ones, remask=False)
         self.reset_peft()
+
+
+def merge_all(modules, remask=False):
+    """Linear.merge() for many SparseLoRA linears at once (train.py:626-637 loops over the modules): the sparse ones go
+    through vlmc_sparselora_merge_batch, 16 per launch and dtype; the rest merge one by one.  Same results as calling
+    merge() on each module."""
+    batch = {}
+    for m in modules:
+        if m.sparse and not m.fan_in_fan_out and m.r <= 8 and m.weight.is_cuda:
+            batch.setdefault((m.weight.dtype, m.weight.device), []).append(m)
+        else:
+            m.merge(remask=remask)
+    for ms in batch.values():
+        native.sparselora_merge_batch([m.weight.data for m in ms], [m.lora_A.weight.data.float() for m in ms],
+                                      [m.lora_B.weight.data.float() for m in ms], [m.scaling for m in ms],
+                                      [m.mask for m in ms], remask=remask)
+        for m in ms:
+            m.reset_peft()
