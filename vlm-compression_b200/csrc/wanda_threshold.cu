@@ -3,10 +3,11 @@
 // Replaces lavis/compression/pruners/wanda_pruner.py:682-683
 //   thres = torch.sort(W_metric.flatten())[0][int(numel * p)] ;  W_mask = W_metric < thres
 // i.e. a full device sort of up to 8.65 M keys, by an exact counting select: every pass counts the
-// scores below 8 pivots (3 quartile points that guarantee a 4x shrink of the bracket + 5
-// interpolated ones that close in on the target rank); W (<= 17 MB) stays L2-resident between
-// passes.  All CTAs replay the pass history from the workspace, so there is no host
-// synchronisation between launches; passes after convergence exit immediately.
+// scores below 16 pivots (7 octile points that guarantee an 8x shrink of the bracket + 9 around the
+// expected position of the target rank: a sampled estimate on the first pass, interpolation
+// afterwards); W (<= 17 MB) stays L2-resident between passes.  The last CTA of a pass folds the counts
+// into the bracket kept in the workspace, so there is no host synchronisation between launches and
+// passes after convergence exit at once (typically 2 passes do work).
 #include "common.cuh"
 
 namespace vlmc {
@@ -14,20 +15,27 @@ namespace vlmc {
 int launch_mean_finalize(const float* part, int n, double denom, float* out, cudaStream_t st);
 
 constexpr int kThrThreads = 256;
-constexpr int kThrPasses = 18;
-constexpr int kThrPivots = 8;
+constexpr int kThrPasses = 12;       // worst case: 8x shrink of a 32-bit range per pass (octile pivots) -> 11 passes
+constexpr int kThrPivots = 16;
 constexpr int kThrCap = 2048;
 
 typedef unsigned long long ull;
 
+struct Bracket { uint32_t lo, hi; ull glo, ghi; };
+
+// search state in the workspace.  The LAST CTA of a counting pass folds the pass's counts into the bracket, so the next
+// pass (and the gather / resolve / apply kernels) read the bracket instead of replaying the pivot history.
 struct ThrState {
-  ull counts[kThrPasses][kThrPivots];
+  ull counts[kThrPivots];
+  Bracket b;
+  int converged;
+  int passes;                 // counting passes that did work (diagnostic)
+  unsigned int ticket;
+  uint32_t seed;              // sampled estimate of the threshold key (0: none)
   unsigned int cand_cnt;
   uint32_t v;
   uint32_t cand[kThrCap];
 };
-
-struct Bracket { uint32_t lo, hi; ull glo, ghi; };
 
 __device__ __forceinline__ bool thr_done(const Bracket& b) {
   return (b.ghi - b.glo) <= (ull)kThrCap || (b.hi - b.lo) == 1u;
@@ -39,34 +47,35 @@ __device__ __forceinline__ uint32_t thr_clamp(double x, uint32_t lo, uint32_t hi
   return (uint32_t)x;
 }
 
-__device__ void thr_pivots(const Bracket& b, ull k, uint32_t* p) {
+// 16 pivots inside the bracket (lo, hi): 7 octile points of the bit range (an 8x shrink whatever the data) and 9 points
+// around the expected position of the target rank: the sampled estimate on the first pass, linear interpolation of the
+// rank inside the bracket afterwards, at geometrically growing offsets.
+__device__ void thr_pivots(const Bracket& b, ull k, uint32_t seed, bool first, uint32_t* p) {
   const double w = (double)(b.hi - b.lo), lo = (double)b.lo;
-  p[0] = thr_clamp(lo + 0.25 * w, b.lo, b.hi);
-  p[1] = thr_clamp(lo + 0.50 * w, b.lo, b.hi);
-  p[2] = thr_clamp(lo + 0.75 * w, b.lo, b.hi);
-  const double f = ((double)(k - b.glo) - 0.5) / (double)(b.ghi - b.glo);
-  const double e = lo + f * w;
-  p[3] = thr_clamp(e - w * 0.0625, b.lo, b.hi);
-  p[4] = thr_clamp(e - w * (1.0 / 256.0), b.lo, b.hi);
-  p[5] = thr_clamp(e, b.lo, b.hi);
-  p[6] = thr_clamp(e + w * (1.0 / 256.0), b.lo, b.hi);
-  p[7] = thr_clamp(e + w * 0.0625, b.lo, b.hi);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) p[i] = thr_clamp(lo + (double)(i + 1) * 0.125 * w, b.lo, b.hi);
+  double e, unit;
+  if (first && seed != 0u) {
+    e = (double)seed;
+    unit = 4096.0;                    // key bits: 2^-11 of a binade = 0.034 % in value; offsets up to +-2^21 bits = +-19 %
+  } else {
+    const double f = ((double)(k - b.glo) - 0.5) / (double)(b.ghi - b.glo);
+    e = lo + f * w;
+    unit = w * (1.0 / 4096.0);
+  }
+  p[7] = thr_clamp(e, b.lo, b.hi);
+  p[8] = thr_clamp(e - unit, b.lo, b.hi);        p[9] = thr_clamp(e + unit, b.lo, b.hi);
+  p[10] = thr_clamp(e - 8.0 * unit, b.lo, b.hi);  p[11] = thr_clamp(e + 8.0 * unit, b.lo, b.hi);
+  p[12] = thr_clamp(e - 64.0 * unit, b.lo, b.hi); p[13] = thr_clamp(e + 64.0 * unit, b.lo, b.hi);
+  p[14] = thr_clamp(e - 512.0 * unit, b.lo, b.hi); p[15] = thr_clamp(e + 512.0 * unit, b.lo, b.hi);
 }
 
-// state of the search after `npass` completed passes
-__device__ Bracket thr_replay(const ThrState* st, int npass, ull n, ull k) {
-  Bracket b{0u, 0xffffffffu, 0ull, n};
-  for (int ps = 0; ps < npass; ++ps) {
-    if (thr_done(b)) break;
-    uint32_t p[kThrPivots];
-    thr_pivots(b, k, p);
-    for (int i = 0; i < kThrPivots; ++i) {
-      const ull c = st->counts[ps][i];
-      if (c <= k - 1) { if (p[i] > b.lo) { b.lo = p[i]; b.glo = c; } }
-      else            { if (p[i] < b.hi) { b.hi = p[i]; b.ghi = c; } }
-    }
+__global__ void thr_init_kernel(ThrState* st, ull n) {
+  if (threadIdx.x < kThrPivots) st->counts[threadIdx.x] = 0ull;
+  if (threadIdx.x == 0) {
+    st->b = Bracket{0u, 0xffffffffu, 0ull, n};
+    st->converged = 0; st->passes = 0; st->ticket = 0u; st->seed = 0u; st->cand_cnt = 0u; st->v = 0u;
   }
-  return b;
 }
 
 __global__ void sqrt_kernel(const float* __restrict__ s, float* __restrict__ sq, int C) {
@@ -98,6 +107,47 @@ __device__ __forceinline__ void load_keys(const T* W, int64_t ldw, int cvecs, in
   }
 }
 
+// one warp: the k/n quantile of 1024 (16-bit) / 512 (fp32) sampled scores, by bisection in key-bit space
+template <typename T>
+__global__ void __launch_bounds__(32)
+thr_seed_kernel(const T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ sq, ull k, ThrState* st) {
+  constexpr int V = Elem<T>::kVec;
+  constexpr int kVecs = 4;
+  const int lane = threadIdx.x;
+  const int cvecs = C / V;
+  uint32_t sk[kVecs * V];
+#pragma unroll
+  for (int u = 0; u < kVecs; ++u) {
+    const int sidx = lane * kVecs + u;
+    const int64_t row = ((int64_t)((sidx * 37) % 128) * R) / 128;
+    const int64_t cv = ((int64_t)sidx * cvecs) / 128;
+    load_keys<T>(W, ldw, cvecs, row * cvecs + cv, sq, sk + u * V, nullptr);
+  }
+  const int ns = 32 * kVecs * V;
+  const ull n = (ull)R * (ull)C;
+  int ks = (int)(((double)k / (double)n) * ns + 0.5);
+  if (ks < 1) ks = 1;
+  if (ks > ns) ks = ns;
+  uint32_t slo = 0u, shi = 0x7f800000u;
+  while (shi - slo > 4096u) {
+    const double q = (double)(shi - slo) * 0.2;
+    const uint32_t sp[4] = {thr_clamp(slo + q, slo, shi), thr_clamp(slo + 2.0 * q, slo, shi), thr_clamp(slo + 3.0 * q, slo, shi),
+                            thr_clamp(slo + 4.0 * q, slo, shi)};
+    uint32_t c[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < kVecs * V; ++e)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[i] += sk[e] < sp[i] ? 1u : 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int sc = (int)__reduce_add_sync(0xffffffffu, c[i]);
+      if (sc <= ks - 1) { if (sp[i] > slo) slo = sp[i]; }
+      else              { if (sp[i] < shi) shi = sp[i]; }
+    }
+  }
+  if (lane == 0) st->seed = slo + ((shi - slo) >> 1);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThrThreads)
 thr_count_kernel(const T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ sq,
@@ -106,11 +156,15 @@ thr_count_kernel(const T* __restrict__ W, int64_t ldw, int R, int C, const float
   __shared__ uint32_t sp[kThrPivots];
   __shared__ int s_done;
   __shared__ unsigned int s_cnt[kThrPivots];
-  const ull n = (ull)R * (ull)C;
+  __shared__ unsigned int s_last;
   if (threadIdx.x == 0) {
-    Bracket b = thr_replay(st, pass, n, k);
-    s_done = thr_done(b) ? 1 : 0;
-    if (!s_done) { uint32_t p[kThrPivots]; thr_pivots(b, k, p); for (int i = 0; i < kThrPivots; ++i) sp[i] = p[i]; }
+    s_done = *reinterpret_cast<volatile int*>(&st->converged);
+    if (!s_done) {
+      const Bracket b = st->b;
+      uint32_t p[kThrPivots];
+      thr_pivots(b, k, st->seed, pass == 0, p);
+      for (int i = 0; i < kThrPivots; ++i) sp[i] = p[i];
+    }
   }
   if (threadIdx.x < kThrPivots) s_cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -136,7 +190,27 @@ thr_count_kernel(const T* __restrict__ W, int64_t ldw, int R, int C, const float
     if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt[i], c);
   }
   __syncthreads();
-  if (threadIdx.x < kThrPivots) atomicAdd(&st->counts[pass][threadIdx.x], (ull)s_cnt[threadIdx.x]);
+  if (threadIdx.x < kThrPivots) atomicAdd(&st->counts[threadIdx.x], (ull)s_cnt[threadIdx.x]);
+  // last CTA of the pass: fold the counts into the bracket, clear them for the next pass
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    Bracket b = st->b;
+    for (int i = 0; i < kThrPivots; ++i) {
+      const ull c = *reinterpret_cast<volatile ull*>(&st->counts[i]);
+      if (c <= k - 1) { if (p[i] > b.lo) { b.lo = p[i]; b.glo = c; } }
+      else            { if (p[i] < b.hi) { b.hi = p[i]; b.ghi = c; } }
+      st->counts[i] = 0ull;
+    }
+    st->b = b;
+    st->passes = pass + 1;
+    st->converged = thr_done(b) ? 1 : 0;
+    st->ticket = 0u;
+  }
 }
 
 template <typename T>
@@ -147,7 +221,7 @@ thr_gather_kernel(const T* __restrict__ W, int64_t ldw, int R, int C, const floa
   __shared__ uint32_t s_lo, s_hi;
   __shared__ int s_skip;
   if (threadIdx.x == 0) {
-    Bracket b = thr_replay(st, kThrPasses, (ull)R * (ull)C, k);
+    const Bracket b = st->b;
     s_lo = b.lo; s_hi = b.hi;
     s_skip = (b.hi - b.lo == 1u) ? 1 : 0;
   }
@@ -175,7 +249,7 @@ __global__ void __launch_bounds__(1024)
 thr_resolve_kernel(int R, int C, ull k, ThrState* st) {
   __shared__ uint32_t s_cand[kThrCap];
   __shared__ Bracket s_b;
-  if (threadIdx.x == 0) s_b = thr_replay(st, kThrPasses, (ull)R * (ull)C, k);
+  if (threadIdx.x == 0) s_b = st->b;
   __syncthreads();
   const Bracket b = s_b;
   if (b.hi - b.lo == 1u) {
@@ -276,8 +350,9 @@ extern "C" int vlmc_wanda_threshold(void* W, int dtype, int R, int C, int64_t ld
   cudaStream_t s = (cudaStream_t)stream;
   const ull k = (ull)k_global + 1;  // 1-indexed rank of the threshold value
 
-  if (cudaMemsetAsync(st, 0, sizeof(ThrState), s) != cudaSuccess) return check_launch();
+  thr_init_kernel<<<1, 32, 0, s>>>(st, (ull)R * (ull)C);
   sqrt_kernel<<<(C + 255) / 256, 256, 0, s>>>(scaler_row, sq, C);
+  VLMC_DISPATCH_DTYPE(dtype, (thr_seed_kernel<scalar_t><<<1, 32, 0, s>>>(reinterpret_cast<const scalar_t*>(W), ldw, R, C, sq, k, st)));
   const int64_t nvec = (int64_t)R * (C / V);
   int grid = kNumSMs * 8;
   if ((int64_t)grid * kThrThreads > nvec) grid = (int)((nvec + kThrThreads - 1) / kThrThreads);
