@@ -186,6 +186,24 @@ def accumulate(ctx, fn, x, state, work_per_seq, tag):
         ctx.launches += 1
 
 
+class _NoFork:
+    """Same interface as vlmc.schedule.Fork, everything on the current stream."""
+
+    def __enter__(self):
+        return self
+
+    def stream(self, i):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def __exit__(self, *exc):
+        return False
+
+
+def schedule_fork(ctx, n):
+    return ctx.schedule.Fork(ctx.dev, n) if n > 1 else _NoFork()
+
+
 def step_wanda(ctx, weights, inputs, method, shared=False):
     torch, native, parallel = ctx.torch, ctx.native, ctx.parallel
     shape = {n: (R, C, inp) for n, R, C, inp in LINEARS}
@@ -195,13 +213,19 @@ def step_wanda(ctx, weights, inputs, method, shared=False):
     # all-reduce (no gather / scatter copies around the collective)
     flat = torch.zeros(sum(shape[l][1] for l, _ in groups), device=ctx.dev, dtype=torch.float32)
     off = 0
-    for leader, members in groups:                        # phase 1: statistics (per-linear API unless `shared`)
-        _, C, inp = shape[leader]
-        s = flat[off:off + C]
-        off += C
-        accumulate(ctx, native.sqnorm_accum, inputs[inp], s, SEQ_LEN * C * 2, "sqnorm_accum")
-        for m in members:
-            scalers[m] = s
+    # phase 1: statistics (per-linear API unless `shared`).  The accumulations are independent of each other: they
+    # alternate between two streams so that the ramp-up of one launch covers the drain + finalize of the previous one
+    # (each stream has its own scratch).  Per-span events (eager pass only) need the launches on one stream.
+    nstreams = 1 if ctx.events is not None else 2
+    with schedule_fork(ctx, nstreams) as fk:
+        for gi, (leader, members) in enumerate(groups):
+            _, C, inp = shape[leader]
+            s = flat[off:off + C]
+            off += C
+            with fk.stream(gi):
+                accumulate(ctx, native.sqnorm_accum, inputs[inp], s, SEQ_LEN * C * 2, "sqnorm_accum")
+            for m in members:
+                scalers[m] = s
     if ctx.world > 1:
         parallel.allreduce_sum(flat)
     masks = {}
@@ -240,15 +264,18 @@ def step_wanda(ctx, weights, inputs, method, shared=False):
 def step_dsnot(ctx, weights, inputs, elide=False):
     torch, native, parallel = ctx.torch, ctx.native, ctx.parallel
     stats = {}
-    for name, R, C, inp in LINEARS:
-        st = [torch.zeros(C, device=ctx.dev) for _ in range(4)]       # scaler_row, sum_metric_row, mean, var
-        x = inputs[inp]
-        n_local = x.shape[0]
-        # every sequence is one reference add_batch call (nseg segments): var is a mean of per-call variances
-        ctx.timed("dsnot_stats", x.numel() * 2, lambda: native.dsnot_stats(x, st[0], st[1], st[2], st[3], 0, 1, 0,
-                                                                           nseg=n_local))
-        ctx.launches += 1
-        stats[name] = st
+    nstreams = 1 if ctx.events is not None else 2          # see step_wanda: independent accumulations on two streams
+    with schedule_fork(ctx, nstreams) as fk:
+        for li, (name, R, C, inp) in enumerate(LINEARS):
+            st = [torch.zeros(C, device=ctx.dev) for _ in range(4)]       # scaler_row, sum_metric_row, mean, var
+            x = inputs[inp]
+            n_local = x.shape[0]
+            # every sequence is one reference add_batch call (nseg segments): var is a mean of per-call variances
+            with fk.stream(li):
+                ctx.timed("dsnot_stats", x.numel() * 2, lambda: native.dsnot_stats(x, st[0], st[1], st[2], st[3], 0, 1, 0,
+                                                                                   nseg=n_local))
+            ctx.launches += 1
+            stats[name] = st
     if ctx.world > 1:
         n_local = next(iter(inputs.values())).shape[0]
         parallel.merge_running_means([t for st in stats.values() for t in st], n_local, n_total=N_SEQ)
