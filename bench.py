@@ -84,18 +84,22 @@ class ClockSampler:
         self.index, self.sm, self.reasons, self.max_mhz = index, [], set(), None
         self._stop = threading.Event()
         self._thread = None
-
-    def start(self):
-        try:
+        self._nvml = self._handle = None
+        try:        # NVML is initialised HERE (~10 ms), not inside the timed region; start() only starts the thread
             import pynvml
             pynvml.nvmlInit()
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
             idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[0].isdigit() else self.index
-            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM)
+            self._nvml = pynvml
         except Exception as e:  # noqa: BLE001
             self.reasons.add(f"nvml unavailable: {type(e).__name__}")
+
+    def start(self):
+        if self._nvml is None:
             return
+        pynvml, h = self._nvml, self._handle
         names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
         def loop():
@@ -264,8 +268,9 @@ def step_wanda(ctx, weights, inputs, method, shared=False):
 def step_dsnot(ctx, weights, inputs, elide=False):
     torch, native, parallel = ctx.torch, ctx.native, ctx.parallel
     stats = {}
-    nstreams = 1 if ctx.events is not None else 2          # see step_wanda: independent accumulations on two streams
-    with schedule_fork(ctx, nstreams) as fk:
+    # one stream: two concurrent DSnoT statistics kernels (256-byte row segments, multi-wave grids) ran 50 % SLOWER than
+    # one after the other (measured), unlike the Wanda statistics in step_wanda
+    with schedule_fork(ctx, 1) as fk:
         for li, (name, R, C, inp) in enumerate(LINEARS):
             st = [torch.zeros(C, device=ctx.dev) for _ in range(4)]       # scaler_row, sum_metric_row, mean, var
             x = inputs[inp]
@@ -370,16 +375,25 @@ def time_method(ctx, method, inputs, steps, warmup, sample_clocks, dist, use_gra
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_ms = []
+
     def timed_loop(step_fn):
         for i in range(warmup):
             step_fn(i)
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [t0]
         t0.record()
         for i in range(steps):
             step_fn(warmup + i)
+            if i + 1 < steps:                # step boundaries (diagnostic: one stalled step shows up in step_ms)
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record()
         t1.record()
+        marks.append(t1)
         barrier()
+        step_ms.clear()
+        step_ms.extend(round(a.elapsed_time(b), 3) for a, b in zip(marks[:-1], marks[1:]))
         ms = torch.tensor([t0.elapsed_time(t1)], device=ctx.dev)
         if ctx.world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -406,7 +420,7 @@ def time_method(ctx, method, inputs, steps, warmup, sample_clocks, dist, use_gra
     ctx.events = None
     out = {"ms_per_step": eager_ms, "eager_ms_per_step": eager_ms, "launches": ctx.launches, "kernels": kern,
            "clocks": clocks, "steps": steps, "cuda_graph": False, "weight_sets": nsets, "world": ctx.world,
-           "calib_batch": ctx.calib_batch, "shared": method.endswith("_shared")}
+           "calib_batch": ctx.calib_batch, "shared": method.endswith("_shared"), "eager_step_ms": list(step_ms)}
 
     # ---- pass B: ONE CUDA graph holding the K timed steps
     if use_graph and method in GRAPH_METHODS:
@@ -520,7 +534,7 @@ def run_gpu(args):
         for m in METHODS:
             if m != args.method:
                 # the millisecond methods get enough steps to average out rank skew; SparseGPT steps are ~0.1 s each
-                r = time_method(ctx, m, inputs, 2 if m.startswith("sparsegpt") else 10, 3, rank == 0, dist, not args.no_graph)
+                r = time_method(ctx, m, inputs, 3 if m.startswith("sparsegpt") else 10, 3, rank == 0, dist, not args.no_graph)
                 others[m] = r
     ctx.H = ctx.U = None
     torch.cuda.empty_cache()
@@ -541,7 +555,8 @@ def run_gpu(args):
             "config": {"workload": f"{WORKLOAD[args.method]} on one InstructBLIP-Vicuna-7B LLM block (7 linears, fp16 "
                                    f"weights, random init), {N_SEQ}x{SEQ_LEN} fp16 calibration tokens per linear",
                        "method": args.method, "calib_batch": args.calib_batch, "cuda_graph": main["cuda_graph"],
-                       "eager_ms_per_step": main["eager_ms_per_step"], "weight_sets": main["weight_sets"],
+                       "eager_ms_per_step": main["eager_ms_per_step"], "eager_step_ms": main["eager_step_ms"],
+                       "weight_sets": main["weight_sets"],
                        "l2": "inputs larger than L2 (12.2 GB of activations per step, fresh weight set per step)",
                        "parallelism": ("tokens/%d + allreduce, rows/%d + allgather" % (world, world)) if world > 1 else "1 GPU"},
             "gpu_launches": main["launches"],
@@ -553,7 +568,8 @@ def run_gpu(args):
         if others:
             out["methods"] = {m: {"value": r["ms_per_step"] / 1e3, "unit": UNIT, "steps": r["steps"],
                                   "cuda_graph": r["cuda_graph"], "eager_ms_per_step": r["eager_ms_per_step"],
-                                  "clocks": r["clocks"], "roofline": roofline_of(r, pk)} for m, r in others.items()}
+                                  "eager_step_ms": r["eager_step_ms"], "clocks": r["clocks"],
+                                  "roofline": roofline_of(r, pk)} for m, r in others.items()}
         if "cuda_graph_error" in main:
             out["config"]["cuda_graph_error"] = main["cuda_graph_error"]
         if world == 1 and args.all_methods and args.method == "wanda_nm":
