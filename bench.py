@@ -329,15 +329,10 @@ def step_sparsegpt(ctx, weights, inputs, shared=False):
     def run(indices):
         mine = [names[i] for i in indices]
         leaders = list(dict.fromkeys(Hof[n] for n in mine))
-        flop = sum(2.0 / 3.0 * shape[l][1] ** 3 for l in leaders)
-        facs = ctx.timed("chol_inv_upper", flop, lambda: schedule.factor_concurrent(
-            [H[l] for l in leaders], 0.01, [U[l] for l in leaders]))
-        fac = dict(zip(leaders, facs))
-        ctx.launches += len(leaders)
-        flop = sum(float(shape[n][0]) * shape[n][1] ** 2 for n in mine)
-        ctx.timed("obs_sweep", flop, lambda: schedule.sweep_concurrent(
-            [(weights[n], *fac[Hof[n]], 0.5, 0, 0) for n in mine]))
-        ctx.launches += sum(5 * ((shape[n][1] + 127) // 128) for n in mine)
+        flop = sum(2.0 / 3.0 * shape[l][1] ** 3 for l in leaders) + sum(float(shape[n][0]) * shape[n][1] ** 2 for n in mine)
+        ctx.timed("sparsegpt_chains", flop, lambda: schedule.sparsegpt_block(
+            [(weights[n], H[Hof[n]], 0.5, 0, 0) for n in mine], 0.01, 128, [U[l] for l in leaders]))
+        ctx.launches += len(leaders) + sum(5 * ((shape[n][1] + 127) // 128) for n in mine)
     parallel.prune_linears_task_parallel([weights[n] for n in names], run, ctx.rank, ctx.world)
     return None
 
@@ -495,6 +490,8 @@ def roofline_of(res, pk):
         "dsnot_refine": ("hbm", "dsnot_walk_kernel + dsnot_apply_kernel: 7 B per weight (latency-bound, see DESIGN.md)"),
         "hessian_accum": ("tensor", "hessian_syrk_kernel (vlmc_hessian_accum): 2*T*C^2 logical flop per call (SYRK executes half)"),
         "chol_inv_upper": ("tensor", "blocked Cholesky + triangular inverse (3xTF32 tcgen05 GEMMs, the chains of the block run concurrently): 2/3 C^3 flop per Hessian"),
+        "sparsegpt_chains": ("tensor", "factorisation (blocked Cholesky + triangular inverse) and OBS sweep chains of the block, pipelined "
+                                       "per Hessian on concurrent streams (3xTF32 tcgen05 GEMMs): 2/3 C^3 + R*C^2 flop"),
         "obs_sweep": ("tensor", "OBS block sweeps + trailing 3xTF32 tcgen05 GEMMs (the chains of the block run concurrently): R*C^2 flop per linear"),
     }[tag]
     bound, desc = info

@@ -276,6 +276,17 @@ int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, const float* U
                    void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * vlmc_obs_sweep that can be enqueued BEFORE the host has looked at the factorisation's status word: fail_flag is that
+ * device word (vlmc_chol_inv_upper's `status`); when it is non-zero at run time the sweep leaves W and keep_mask
+ * untouched (only scratch is written), so the caller can damp, re-factorise and sweep again (sparsegpt_pruner.py:114-128
+ * semantics) without a host round trip on the success path.  fail_flag == NULL: identical to vlmc_obs_sweep.
+ */
+int vlmc_obs_sweep_guarded(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu,
+                           const uint8_t* dead, double sparsity, int prune_n, int prune_m, int blocksize,
+                           uint8_t* keep_mask, int64_t ldm, float* importance_score, const int* fail_flag,
+                           void* ws, size_t ws_bytes, void* stream);
+
+/*
  * K11-K13 in steps, for runs that shard the OUTPUT ROWS of one linear across GPUs (rows are independent given U, except
  * for the unstructured block threshold, which is a k-th value over all rows x 128 columns).  Each rank holds
  * R of the rows_total rows.  `hist` is caller memory, [ceil(C/128)][3][2048] uint32, zero before vlmc_obs_begin

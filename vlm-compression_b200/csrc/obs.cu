@@ -90,6 +90,7 @@ struct ObsParams {
   unsigned int kth;    // unstructured: 1-indexed rank of the threshold value among the R*bs block scores
   int prune_n, prune_m;
   ObsHist* hist;       // this block's three histograms (zero on entry)
+  const int* fail;     // optional device flag: non-zero = the factor U is invalid, leave W and the keep mask untouched
 };
 
 // score of one weight: w^2 / d^2 with the reference's roundings (:183); non-negative, so bit order = value order
@@ -208,6 +209,7 @@ obs_sweep4_kernel(const ObsParams p, int dtype, int vec_ok) {
   __syncthreads();
   const int g = lane >> 3, l = lane & 7, gbase = lane & ~7;
   const int n = p.prune_n;
+  const bool skip_out = p.fail != nullptr && *p.fail != 0;
   const float4* Us4 = reinterpret_cast<const float4*>(Us);
 
   for (int row0 = (blockIdx.x * (kSw4Threads / 32) + warp) * 4; row0 < p.R; row0 += gridDim.x * kSw4RowsPerCta) {
@@ -320,6 +322,7 @@ obs_sweep4_kernel(const ObsParams p, int dtype, int vec_ok) {
         *reinterpret_cast<float4*>(p.Err + (int64_t)row * kOB + col) = make_float4(er[t][0], er[t][1], er[t][2], er[t][3]);
         if (col < bs) {
           *reinterpret_cast<float4*>(w32 + 32 * t) = make_float4(w[t][0], w[t][1], w[t][2], w[t][3]);
+          if (skip_out) continue;          // failed factorisation: only the scratch copies are written
           const int64_t off = (int64_t)row * p.ldw + p.i1 + col;
           if (dtype == VLMC_F32) {
             float* wo = reinterpret_cast<float*>(p.Wout) + off;
@@ -417,6 +420,7 @@ static ObsParams obs_block_params(const ObsLayout& l, void* W, int R, int C, int
   p.kth = (unsigned int)((ull)((double)((ull)rows_total * (ull)p.bs) * sparsity)) + 1u;
   p.prune_n = prune_n; p.prune_m = prune_m;
   p.hist = hist ? reinterpret_cast<ObsHist*>(hist) + blk : l.hist + blk;
+  p.fail = nullptr;
   return p;
 }
 
@@ -462,16 +466,17 @@ extern "C" int vlmc_obs_block_hist(int R, int C, const float* U, int64_t ldu, in
   return check_launch();
 }
 
-extern "C" int vlmc_obs_block_finish(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu, int blk,
-                                     int64_t rows_total, double sparsity, int prune_n, int prune_m, uint8_t* keep_mask,
-                                     int64_t ldm, unsigned int* hist, void* ws, size_t ws_bytes, void* stream) {
-  using namespace vlmc;
+namespace vlmc {
+static int obs_block_finish_impl(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu, int blk,
+                                 int64_t rows_total, double sparsity, int prune_n, int prune_m, uint8_t* keep_mask,
+                                 int64_t ldm, unsigned int* hist, void* ws, size_t ws_bytes, void* stream, const int* fail) {
   int rc = obs_checks(W, dtype, R, C, ldw, U, ldu, sparsity, prune_n, prune_m, kOB, keep_mask, ldm, ws, ws_bytes);
   if (rc) return rc;
   if (blk < 0 || blk * kOB >= C || rows_total < R) return VLMC_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   ObsLayout l = obs_carve(ws, R, C);
   ObsParams p = obs_block_params(l, W, R, C, ldw, U, ldu, blk, rows_total, sparsity, prune_n, prune_m, keep_mask, ldm, hist);
+  p.fail = fail;
   // 8-byte weight stores / 4-byte mask stores need aligned rows; otherwise the kernel stores element by element
   const int esz = elem_size(dtype);
   const int vec_ok = ((ldw * esz) % (4 * esz) == 0) && (((uintptr_t)W) % (4 * esz) == 0) &&
@@ -493,12 +498,20 @@ extern "C" int vlmc_obs_block_finish(void* W, int dtype, int R, int C, int64_t l
   }
   return check_launch();
 }
+}  // namespace vlmc
 
-extern "C" int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu,
-                              const uint8_t* dead, double sparsity, int prune_n, int prune_m, int blocksize,
-                              uint8_t* keep_mask, int64_t ldm, float* importance_score,
-                              void* ws, size_t ws_bytes, void* stream) {
-  using namespace vlmc;
+extern "C" int vlmc_obs_block_finish(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu, int blk,
+                                     int64_t rows_total, double sparsity, int prune_n, int prune_m, uint8_t* keep_mask,
+                                     int64_t ldm, unsigned int* hist, void* ws, size_t ws_bytes, void* stream) {
+  return vlmc::obs_block_finish_impl(W, dtype, R, C, ldw, U, ldu, blk, rows_total, sparsity, prune_n, prune_m, keep_mask, ldm,
+                                     hist, ws, ws_bytes, stream, nullptr);
+}
+
+namespace vlmc {
+static int obs_sweep_impl(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu,
+                          const uint8_t* dead, double sparsity, int prune_n, int prune_m, int blocksize,
+                          uint8_t* keep_mask, int64_t ldm, float* importance_score,
+                          void* ws, size_t ws_bytes, void* stream, const int* fail) {
   int rc = obs_checks(W, dtype, R, C, ldw, U, ldu, sparsity, prune_n, prune_m, blocksize, keep_mask, ldm, ws, ws_bytes);
   if (rc) return rc;
   rc = vlmc_obs_begin(W, dtype, R, C, ldw, U, ldu, dead, importance_score, ws, ws_bytes, stream);
@@ -514,9 +527,27 @@ extern "C" int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, con
         rc = vlmc_obs_block_hist(R, C, U, ldu, blk, pass, R, sparsity, nullptr, ws, ws_bytes, stream);
         if (rc) return rc;
       }
-    rc = vlmc_obs_block_finish(W, dtype, R, C, ldw, U, ldu, blk, R, sparsity, prune_n, prune_m, keep_mask, ldm,
-                               nullptr, ws, ws_bytes, stream);
+    rc = obs_block_finish_impl(W, dtype, R, C, ldw, U, ldu, blk, R, sparsity, prune_n, prune_m, keep_mask, ldm,
+                               nullptr, ws, ws_bytes, stream, fail);
     if (rc) return rc;
   }
   return VLMC_OK;
+}
+}  // namespace vlmc
+
+extern "C" int vlmc_obs_sweep(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu,
+                              const uint8_t* dead, double sparsity, int prune_n, int prune_m, int blocksize,
+                              uint8_t* keep_mask, int64_t ldm, float* importance_score,
+                              void* ws, size_t ws_bytes, void* stream) {
+  return vlmc::obs_sweep_impl(W, dtype, R, C, ldw, U, ldu, dead, sparsity, prune_n, prune_m, blocksize, keep_mask, ldm,
+                              importance_score, ws, ws_bytes, stream, nullptr);
+}
+
+extern "C" int vlmc_obs_sweep_guarded(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu,
+                                      const uint8_t* dead, double sparsity, int prune_n, int prune_m, int blocksize,
+                                      uint8_t* keep_mask, int64_t ldm, float* importance_score, const int* fail_flag,
+                                      void* ws, size_t ws_bytes, void* stream) {
+  if (fail_flag && !vlmc::is_device_ptr(fail_flag)) return VLMC_ERR_NOT_DEVICE;
+  return vlmc::obs_sweep_impl(W, dtype, R, C, ldw, U, ldu, dead, sparsity, prune_n, prune_m, blocksize, keep_mask, ldm,
+                              importance_score, ws, ws_bytes, stream, fail_flag);
 }

@@ -47,8 +47,7 @@ class WrappedGPT:
         self.nsamples += b
 
     def free(self):
-        self.H = None
-        torch.cuda.empty_cache()
+        self.H = None          # dsnot_pruner.py:103-105 (its empty_cache() is left to the end of the block loop, see SparseGPT.free)
 
 
 def return_reorder_indice(input_tensor):

@@ -58,6 +58,8 @@ SIGNATURES = {
     "vlmc_chol_inv_upper": (_i, [_vp, _i, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_gemm_tf32x3": (_i, [_i, _i, _i, _i, _f, _vp, _i64, _vp, _i64, _f, _vp, _i64, _i, _i, _vp]),
     "vlmc_obs_sweep": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp, _d, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "vlmc_obs_sweep_guarded": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp, _d, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _sz,
+                                    _vp]),
     "vlmc_hessian_accum": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _d, _d, _i, _i64, _vp]),
     "vlmc_obs_begin": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "vlmc_obs_block_hist": (_i, [_i, _i, _vp, _i64, _i, _i, _i64, _d, _vp, _vp, _sz, _vp]),
@@ -504,9 +506,11 @@ def gemm_tf32x3(A, B, C=None, alpha=1.0, beta=0.0, b_nk=False, tri=False, kc=0):
     return C
 
 
-def obs_sweep(W, U, sparsity, prune_n=0, prune_m=0, dead=None, blocksize=128, want_mask=False, score=None, keep=None):
+def obs_sweep(W, U, sparsity, prune_n=0, prune_m=0, dead=None, blocksize=128, want_mask=False, score=None, keep=None,
+              fail_flag=None):
     """K11-K13 (sparsegpt_pruner.py:160-215), in place on W.  Returns (keep_mask or None, importance 1-elem tensor).
-    score / keep may be passed in (pre-allocated outputs)."""
+    score / keep may be passed in (pre-allocated outputs).  fail_flag: the int32 status word of chol_inv_upper; when it
+    is non-zero at run time W and keep are left untouched (vlmc_obs_sweep_guarded)."""
     _require_cuda(W, U, dead)
     if W.dim() != 2 or W.stride(1) != 1:
         raise ValueError("W must be a 2-D row-major weight")
@@ -518,12 +522,13 @@ def obs_sweep(W, U, sparsity, prune_n=0, prune_m=0, dead=None, blocksize=128, wa
         score = torch.empty(1, dtype=torch.float32, device=W.device)
     ws = workspace(W, lib.vlmc_workspace_bytes(OP_OBS, R, C, blocksize))
     with torch.cuda.device(W.device):
-        st = lib.vlmc_obs_sweep(W.data_ptr(), _dtype(W), R, C, W.stride(0), U.data_ptr(), U.stride(0),
-                                dead.data_ptr() if dead is not None else None, float(sparsity), int(prune_n),
-                                int(prune_m), int(blocksize), keep.data_ptr() if keep is not None else None,
-                                keep.stride(0) if keep is not None else 0, score.data_ptr(), ws.data_ptr(), ws.numel(),
-                                _stream(W))
-    _check("vlmc_obs_sweep", st)
+        st = lib.vlmc_obs_sweep_guarded(W.data_ptr(), _dtype(W), R, C, W.stride(0), U.data_ptr(), U.stride(0),
+                                        dead.data_ptr() if dead is not None else None, float(sparsity), int(prune_n),
+                                        int(prune_m), int(blocksize), keep.data_ptr() if keep is not None else None,
+                                        keep.stride(0) if keep is not None else 0, score.data_ptr(),
+                                        fail_flag.data_ptr() if fail_flag is not None else None, ws.data_ptr(), ws.numel(),
+                                        _stream(W))
+    _check("vlmc_obs_sweep_guarded", st)
     return keep, score
 
 

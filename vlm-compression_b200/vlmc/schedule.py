@@ -12,7 +12,8 @@ results are bit-identical to the one-after-the-other schedule (tests/test_gpu_pa
                        sync for all status words, the reference's damp-and-retry loop (:114-128) only for the
                        ones that failed
   sweep_concurrent     all OBS sweeps of a block
-  sparsegpt_block      both, for a list of (W, H) items whose H may be shared (q/k/v, gate/up): factorised once
+  sparsegpt_block      both, pipelined per Hessian, for a list of (W, H) items whose H may be shared (q/k/v, gate/up):
+                       factorised once, its sweeps start as soon as it is done (guarded by the status word)
 
 Outputs that outlive the fork (U, dead, scores) are allocated on the caller's stream BEFORE the fork, so the caching
 allocator never hands their memory to another stream; per-stream scratch comes from native.workspace (keyed by stream).
@@ -104,14 +105,55 @@ def sweep_concurrent(items, blocksize=128):
     return scores
 
 
-def sparsegpt_block(items, percdamp=0.01, blocksize=128, Us=None):
+def sparsegpt_block(items, percdamp=0.01, blocksize=128, Us=None, max_retries=64):
     """items: [(W, H, sparsity, prune_n, prune_m)].  Items that hold THE SAME H tensor (linears fed by the same
-    activations) are factorised once.  Returns (scores [n] device tensor, {id(H): (U, dead)})."""
-    distinct, seen = [], {}
-    for _, H, *_ in items:
+    activations) are factorised once.  Returns (scores [n] device tensor, {id(H): (U, dead)}).
+
+    Pipelined: every distinct H is prepared and factorised on its own stream and the sweeps of ITS linears start as soon
+    as that factorisation is done (each on its own stream, behind an event) - they do not wait for the longest
+    factorisation of the block.  The sweeps are enqueued before the host knows whether the factorisation succeeded:
+    they carry its device status word and leave W untouched if it failed (vlmc_obs_sweep_guarded).  One host sync at
+    the end reads all status words; a failed H then goes through the reference's damp-and-retry loop
+    (sparsegpt_pruner.py:114-128) and its linears are swept again.  Same kernels in the same per-chain order as
+    SparseGPT.fasterprune: bit-identical weights."""
+    distinct, seen, members = [], {}, []
+    for i, (_, H, *_rest) in enumerate(items):
         if id(H) not in seen:
             seen[id(H)] = len(distinct)
             distinct.append(H)
-    facs = factor_concurrent(distinct, percdamp, Us)
-    scores = sweep_concurrent([(W, *facs[seen[id(H)]], sp, pn, pm) for W, H, sp, pn, pm in items], blocksize)
-    return scores, {id(H): facs[seen[id(H)]] for H in distinct}
+            members.append([])
+        members[seen[id(H)]].append(i)
+    dev = distinct[0].device
+    nH, n = len(distinct), len(items)
+    Us = [torch.empty_like(H) for H in distinct] if Us is None else Us
+    damps = torch.empty(nH, dtype=torch.float32, device=dev)
+    status = torch.empty(nH, dtype=torch.int32, device=dev)
+    deads = [torch.empty(H.shape[0], dtype=torch.uint8, device=dev) for H in distinct]
+    scores = torch.empty(n, dtype=torch.float32, device=dev)
+    order = sorted(range(nH), key=lambda h: -distinct[h].shape[0])      # longest chain first
+    with Fork(dev, nH + n) as f:
+        for slot, h in enumerate(order):
+            with f.stream(slot):
+                native.hessian_prepare(distinct[h], percdamp, damps[h:h + 1], deads[h])
+                native.chol_inv_upper(distinct[h], Us[h], status[h:h + 1])
+                factored = torch.cuda.Event()
+                factored.record(f.streams[slot])
+            for i in members[h]:
+                W, _, sparsity, pn, pm = items[i]
+                f.streams[nH + i].wait_event(factored)
+                with f.stream(nH + i):
+                    native.obs_sweep(W, Us[h], sparsity, pn, pm, dead=deads[h], blocksize=blocksize,
+                                     score=scores[i:i + 1], fail_flag=status[h:h + 1])
+    failed = [h for h, st in enumerate(status.tolist()) if st != 0]     # the ONE host sync of the block
+    for h in failed:                                                     # :114-128, cumulative damping per retry
+        for _ in range(max_retries):
+            native.hessian_add_damp(distinct[h], damps[h:h + 1])
+            native.chol_inv_upper(distinct[h], Us[h], status[h:h + 1])
+            if status[h].item() == 0:
+                break
+        else:
+            raise RuntimeError("Hessian stayed non-positive-definite after damping")
+        for i in members[h]:
+            W, _, sparsity, pn, pm = items[i]
+            native.obs_sweep(W, Us[h], sparsity, pn, pm, dead=deads[h], blocksize=blocksize, score=scores[i:i + 1])
+    return scores, {id(H): (Us[h], deads[h]) for h, H in enumerate(distinct)}
