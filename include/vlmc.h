@@ -214,6 +214,47 @@ typedef struct vlmc_tensor_item { const void* ptr; int64_t numel; } vlmc_tensor_
 int vlmc_count_nonzero_batch(const vlmc_tensor_item* items, int count, int dtype, unsigned long long* out, void* stream);
 
 /*
+ * K18-K22  Global sparsity allocation on fp32 importance scores.  Replaces the CPU torch.topk / cat /
+ * compare passes of LayerSparsity.get_mask / get_layerwise_mask / global_iterative_pruning and the score build of
+ * compute_importance_scores (layer_single_base_pruner.py:149-190, :192-238, :422-475) and of
+ * BLIPT5GlobalPruner.get_mask / get_layerwise_mask (global_pruner.py:108-148).
+ *
+ * `items` is a HOST array of any length, read during the call (the library walks it 64 tensors per launch).  Tensors are
+ * contiguous, scores fp32 (4-byte aligned is enough).  `segment` groups tensors that share one rank / threshold:
+ * all 0 for the whole-model select, one segment per tensor for the layer-wise variants.
+ *
+ *   vlmc_scores_kth      kth_out[s] = the k[s]-th smallest score (1-based) of segment s, exact, in torch.topk's order
+ *                        (NaN greatest, -0.0 == +0.0): topk(all, k, largest=False)[0][-1] (:168-169); the j-th LARGEST of
+ *                        :157-158 is rank numel - j + 1.  k: DEVICE int64 [nseg], 1 <= k[s] <= numel of the segment.
+ *                        Three counting passes (11/11/10 key bits) over the scores, no host synchronisation.
+ *   vlmc_scores_protect  scores[v >= thr[segment]] = FLT_MAX in place (:160)
+ *   vlmc_scores_mask     out = (v > thr[segment]) as 1.0f / 0.0f (:174, out may be NULL) and, when aux is given,
+ *                        aux *= that mask in aux's dtype (:223-225 `v.data *= masks[k]`: pruned weights become +-0)
+ *   vlmc_scores_sum      out[i] (device double [count]) = sum of items[i].scores, fixed summation order
+ *                        (group_scores += importance_measure[l].sum(), :296)
+ *   vlmc_importance_accum     scores += float(aux)^2 (mode 0, "obd", :456) or |float(aux)| (mode 1, :458); aux = gradient
+ *   vlmc_importance_finalize  out = float(aux)^2 * (scores / nb) (mode 0, :468), |float(aux)| * |scores / nb| (mode 1, :470)
+ *                        or |scores / nb| (mode 2, :473); aux = parameter (unused for mode 2); every product and the
+ *                        division rounded separately like the reference's tensor expression
+ */
+typedef struct vlmc_score_item {
+  float* scores;     /* fp32 scores / accumulator */
+  int64_t numel;
+  int segment;
+  int aux_dtype;     /* vlmc_dtype of aux */
+  void* aux;         /* parameter or gradient tensor of numel elements, or NULL */
+  float* out;        /* fp32 output of numel elements, or NULL */
+} vlmc_score_item;
+size_t vlmc_scores_workspace_bytes(const vlmc_score_item* items, int count, int nseg);
+int vlmc_scores_kth(const vlmc_score_item* items, int count, int nseg, const int64_t* k, float* kth_out,
+                    void* ws, size_t ws_bytes, void* stream);
+int vlmc_scores_protect(const vlmc_score_item* items, int count, int nseg, const float* thr, void* stream);
+int vlmc_scores_mask(const vlmc_score_item* items, int count, int nseg, const float* thr, void* stream);
+int vlmc_scores_sum(const vlmc_score_item* items, int count, double* out, void* ws, size_t ws_bytes, void* stream);
+int vlmc_importance_accum(const vlmc_score_item* items, int count, int mode, void* stream);
+int vlmc_importance_finalize(const vlmc_score_item* items, int count, int mode, double num_batches, void* stream);
+
+/*
  * K3  SparseGPT Hessian accumulation.  Replaces SparseGPT.add_batch, sparsegpt_pruner.py:68-79:
  *   H <- H * n_before/(n_before+b) + (2/(n_before+b)) * X^T X
  * x: [T, C] row-major fp16 / bf16 / fp32 (one add_batch call, T = b * seq_len); H: [C, C] fp32, full and symmetric.

@@ -523,3 +523,99 @@ def dsnot_refine(W32, scaler_row, sum_metric_row, var, sparsity_num=0, prune_n=0
         err = (err + np.where(upd, pm, F32(0))).astype(F32)                         # :742
         err = (err - np.where(upd, rm, F32(0))).astype(F32)                         # :747
     return ~mask, cycles
+
+
+# ---------------------------------------------------------------------------------------------
+# global sparsity allocation (layer_single_base_pruner.py:149-190, :241-420; the
+# same get_mask / get_layerwise_mask at global_pruner.py:108-148)
+# ---------------------------------------------------------------------------------------------
+def kth_smallest(values, k):
+    """torch.topk(values, k, largest=False)[0][-1]: the k-th smallest (1-based), NaN sorted last."""
+    v = np.asarray(values, dtype=F32).ravel()
+    if k < 1:
+        raise IndexError("index -1 is out of bounds for dimension 0 with size 0")   # threshold[-1] of an empty topk
+    return np.sort(v)[k - 1]                                                        # np.sort puts NaN last as well
+
+
+def global_get_mask(scores, p, max_sparsity_per_layer):
+    """LayerSparsity.get_mask (:149-176).  `scores`: dict name -> float32 array, MODIFIED IN PLACE like the
+    reference (:160 writes finfo.max over the protected entries).  Returns (masks, threshold)."""
+    fmax = np.finfo(F32).max
+    for k, v in scores.items():
+        num_to_set = int(v.size * (1 - max_sparsity_per_layer))                     # :153
+        if num_to_set > 0:
+            thr = np.sort(v.ravel())[v.size - num_to_set]                           # :157-158 j-th largest
+            v[v >= thr] = fmax                                                      # :160
+    all_scores = np.concatenate([v.ravel() for v in scores.values()])               # :165
+    thr = kth_smallest(all_scores, int(p * all_scores.size))                        # :168-170
+    return {k: (v > thr).astype(F32) for k, v in scores.items()}, thr               # :173-174
+
+
+def layerwise_get_mask(scores, p):
+    """LayerSparsity.get_layerwise_mask (:178-190): one threshold per tensor."""
+    masks = {}
+    for k, v in scores.items():
+        thr = kth_smallest(v, int(p * v.size))
+        masks[k] = (v > thr).astype(F32)
+    return masks
+
+
+def importance_scores_first_order(params, grads_per_batch, mode="obd"):
+    """compute_importance_scores (:422-475) for one parameter: fp32 running sum of grad^2 (obd) or |grad|, divided by the
+    number of batches, times w^2 - every step rounded to fp32 as the tensor expression does.  ("aobd" and "gradient"
+    take the "obd" branch / the last branch of the reference's `in` tests, :466-473.)"""
+    w = np.asarray(params, dtype=F32)
+    acc = np.zeros_like(w)
+    for g in grads_per_batch:
+        g = np.asarray(g, dtype=F32)
+        acc = (acc + (g * g if mode == "obd" else np.abs(g))).astype(F32)
+    acc = (acc / F32(len(grads_per_batch))).astype(F32)
+    if "obd" in mode:
+        return ((w * w).astype(F32) * acc).astype(F32)
+    return np.abs(acc)
+
+
+def group_sparsity_allocation(total_to_keep, group_scores, group_num_params, max_sparsity_per_layer=0.8):
+    """compute_the_sparsity_per_group (:304-378), with torch's dtypes restated: `scores` float32, parameter counts int64,
+    the kept-parameter vector int64 until the first `+ parameters_to_add` turns it float32 (:318).  The shipped
+    "remove the extra parameters" branch ADDS them (:358, `+=`); that is kept.  Returns the list of group sparsities."""
+    scores = np.asarray(group_scores, dtype=F32).copy()
+    num = np.asarray(group_num_params, dtype=np.int64)
+    floor_keep = np.ceil(num.astype(F32) * F32(1 - max_sparsity_per_layer)).astype(np.int32)     # :309
+    keep = floor_keep.astype(np.int64)
+    while keep.sum() < total_to_keep:                                               # :311
+        total_ratio = scores.sum(dtype=F32)
+        rest = F32(total_to_keep - keep.sum())                                      # 0-dim tensor -> float32 operand
+        with np.errstate(divide="ignore", invalid="ignore"):
+            to_add = np.ceil((scores / total_ratio).astype(F32) * rest).astype(F32)  # :316
+        keep = (keep.astype(F32) + to_add).astype(F32)                              # :318
+        scores[keep >= num.astype(F32)] = 0                                         # :320
+        keep = np.minimum(keep, num.astype(F32))                                    # :322
+        if to_add.sum(dtype=F32) == 0:                                              # :326-342
+            need = F32(total_to_keep) - keep.sum(dtype=F32)
+            while need > 0:
+                idx = np.nonzero(scores > 0)[0]
+                if idx.size == 0:
+                    raise RuntimeError("allocation cannot place the remaining parameters (the reference loops forever)")
+                for i in idx:
+                    can = min(need, F32(num[i]) - keep[i])
+                    keep[i] += can
+                    need -= can
+                    if need == 0:
+                        break
+        if keep.sum(dtype=F32) > total_to_keep:                                     # :344-364
+            need = keep.sum(dtype=F32) - F32(total_to_keep)
+            while need > 0:
+                progressed = False
+                for i in np.argsort(-keep, kind="stable"):
+                    extra = (F32(num[i]) * F32(1 - max_sparsity_per_layer)).astype(np.int32)
+                    can = min(need, keep[i] - F32(extra))
+                    keep[i] += can                                                  # shipped: += (not -=)
+                    need -= can
+                    progressed = progressed or can > 0
+                    if need == 0:
+                        break
+                if not progressed:
+                    raise RuntimeError("allocation cannot remove the extra parameters (the reference loops forever)")
+    ratio = keep.astype(F32) / num.astype(F32)                                      # int64 / int64 is a float32 division too
+    return [float(x) for x in np.clip(F32(1) - ratio, 0, 1).astype(F32)]           # :370-371

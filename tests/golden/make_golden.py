@@ -308,13 +308,143 @@ def gen_reorder(ref):
          rnd_in=rnd.numpy(), rnd_out=ref.dsnot.return_reorder_indice(rnd).numpy())
 
 
+class _AllocModel(nn.Module):
+    """Parameters named like the reference's check() expects (wanda_pruner.py:875-885): two sub-models with blocks."""
+
+    def __init__(self, seed=0):
+        super().__init__()
+        g = torch.Generator().manual_seed(seed)
+
+        def lin(o, i):
+            l = nn.Linear(i, o, bias=False)
+            l.weight.data = torch.randn(o, i, generator=g) * 0.05
+            return l
+        self.t5_model = nn.ModuleDict({"encoder": nn.ModuleDict({"block": nn.ModuleList(
+            [nn.ModuleDict({"q": lin(24, 24), "wi": lin(60, 24), "wo": lin(24, 60)}) for _ in range(3)])})})
+        self.visual_encoder = nn.ModuleDict({"blocks": nn.ModuleList(
+            [nn.ModuleDict({"qkv": lin(48, 16), "fc1": lin(40, 16)}) for _ in range(2)])})
+
+    def forward(self, samples):
+        x = samples["x"]
+        h = x
+        for b in self.t5_model["encoder"]["block"]:
+            h = h + torch.tanh(b["wo"](torch.relu(b["wi"](b["q"](h)))))
+        v = samples["v"]
+        acc = 0
+        for b in self.visual_encoder["blocks"]:
+            acc = acc + b["qkv"](v).pow(2).mean() + b["fc1"](v).abs().mean()
+        return {"loss": h.pow(2).mean() + acc}
+
+
+def gen_layer_sparsity(ref):
+    """LayerSparsity.get_mask / get_layerwise_mask / compute_importance_scores / return_sparsity of the
+    UNMODIFIED reference (layer_single_base_pruner.py:111-475) on seeded inputs."""
+    LS = ref.base.LayerSparsity
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    shapes = {"a.weight": (48, 64), "b.weight": (33, 17), "c.weight": (128, 96), "d.weight": (5, 7)}
+
+    def fresh_scores(kind):
+        gg = torch.Generator().manual_seed({"obd": 21, "ties": 22, "signed": 23}[kind])
+        sc = {}
+        for k, shp in shapes.items():
+            if kind == "obd":        # w^2 * g^2-like: non-negative, wide dynamic range, different scale per tensor
+                t = (torch.randn(shp, generator=gg) ** 2) * (torch.randn(shp, generator=gg) ** 2) * (10.0 ** (len(sc) - 2))
+            elif kind == "ties":     # heavily quantised scores: the threshold value is shared by many entries
+                t = torch.randint(0, 6, shp, generator=gg).float() * 0.25
+            else:                    # signed scores with zeros and negative zeros (blipt5_mag_pruner feeds signed weights)
+                t = torch.randn(shp, generator=gg)
+                t[torch.rand(shp, generator=gg) < 0.1] = 0.0
+                t[torch.rand(shp, generator=gg) < 0.05] = -0.0
+            sc[k] = t.float().contiguous()
+        return sc
+
+    dummy = LS(None, None, None, 1, 0.5, 0.8, "obd_avg")
+    cases = []
+    for kind in ("obd", "ties", "signed"):
+        base = fresh_scores(kind)
+        for k, t in base.items():
+            out[f"scores|{kind}|{k}"] = t.numpy().copy()
+        for p, ms in ((0.5, 0.8), (0.3, 1.0), (0.6, 0.7), (0.05, 0.5)):
+            sc = {k: t.clone() for k, t in base.items()}
+            masks = dummy.get_mask(sc, p, ms)
+            tag = f"{kind}|{p}|{ms}"
+            cases.append(tag)
+            for k in sc:
+                out[f"global|{tag}|{k}"] = np.packbits(masks[k].numpy().astype(bool).ravel())
+                changed = sc[k] != base[k]                    # entries get_mask overwrote with finfo.max (:160)
+                assert bool((sc[k][changed] == torch.finfo(torch.float32).max).all())
+                out[f"global_protected|{tag}|{k}"] = np.packbits(changed.numpy().ravel())
+        saved_cuda = torch.Tensor.cuda
+        torch.Tensor.cuda = lambda self, *a, **k: self          # get_layerwise_mask calls .cuda() (:184)
+        try:
+            for p in (0.5, 0.25):
+                sc = {k: t.clone() for k, t in base.items()}
+                masks = dummy.get_layerwise_mask(sc, p)
+                for k in sc:
+                    out[f"layerwise|{kind}|{p}|{k}"] = np.packbits(masks[k].numpy().astype(bool).ravel())
+        finally:
+            torch.Tensor.cuda = saved_cuda
+    out["global_cases"] = np.array(cases)
+    out["names"] = np.array(list(shapes))
+
+    # compute_importance_scores + return_sparsity through the toy model
+    model = _AllocModel(seed=5)
+    gd = torch.Generator().manual_seed(6)
+    loader = [{"x": torch.randn(4, 24, generator=gd), "v": torch.randn(4, 16, generator=gd), "text_input": ["t"] * 4}
+              for _ in range(3)]
+    loss_func = lambda m, d, cuda_enabled: (m(d)["loss"], len(d["text_input"]))    # utils.py:21-31 without prepare_sample
+    names = [k for k, v in model.named_parameters()]
+    out["model_names"] = np.array(names)
+    for k, v in model.named_parameters():
+        out[f"param|{k}"] = f32(v)
+    for bi, d in enumerate(loader):
+        grads = torch.autograd.grad(model(d)["loss"], list(model.parameters()))
+        for k, gr in zip(names, grads):
+            out[f"grad|{bi}|{k}"] = f32(gr)
+    alloc_cases = []
+    for method in ("obd_avg", "aobd_avg", "gradient_avg", "obd_sum"):
+        for gran in ("layer", "block", "model"):
+            for sparsity, ms in ((0.5, 0.8), (0.6, 0.7)):
+                def group_of(name):
+                    if gran == "layer":
+                        return name
+                    if name.startswith("t5_model"):
+                        return "t5_model" if gran == "model" else ".".join(name.split(".")[:4])
+                    return "visual_encoder" if gran == "model" else ".".join(name.split(".")[:3])
+                mapping = {k: group_of(k) for k in names}
+                ls = LS(model, loader, loss_func, 12, sparsity, ms, method, 1, 1e-3, mapping)
+                res = ls.return_sparsity()
+                tag = f"{method}|{gran}|{sparsity}|{ms}"
+                alloc_cases.append(tag)
+                out[f"alloc|{tag}"] = np.array([res[k] for k in names], dtype=np.float64)
+                if gran == "layer" and sparsity == 0.5:
+                    for k in names:
+                        out[f"importance|{method}|{k}"] = f32(ls.importance_measure[k])
+    # per-model allocation (prune_per_model)
+    mapping = {k: ".".join(k.split(".")[:4]) if k.startswith("t5_model") else ".".join(k.split(".")[:3]) for k in names}
+    ls = LS(model, loader, loss_func, 12, 0.5, 0.8, "obd_avg", 1, 1e-3, mapping, prune_per_model=True,
+            per_model_group=["t5_model", "visual_encoder"], per_model_sparsity=[0.6, 0.4])
+    res = ls.return_sparsity()
+    out["alloc_per_model"] = np.array([res[k] for k in names], dtype=np.float64)
+    out["alloc_cases"] = np.array(alloc_cases)
+
+    # "real" score_compute: global_iterative_pruning with 3 iterations, sparsity of every parameter afterwards
+    # (return_sparsity takes this branch for score_compute "real*", :246-249, but compute_importance_scores then has no
+    # rule to apply, :455 / :466; the loop is driven directly with the "obd" rule)
+    ls = LS(model, loader, loss_func, 12, 0.5, 0.8, "obd_avg", 1, 1e-3, {k: k for k in names})
+    real = ls.global_iterative_pruning(0.5, {k: k for k in names}, iteratation=3, max_sparsity_per_layer=1.0)
+    out["real_sparsity"] = np.array([real[k] for k in names], dtype=np.float64)
+    save("layer_sparsity.npz", **out)
+
+
 def main():
     torch.set_num_threads(8)
     ref = ref_loader.load()
     only = set(sys.argv[1:])
     gens = dict(wanda_stats=gen_wanda_stats, dsnot_stats=gen_dsnot_stats, wanda_toy=gen_wanda_toy,
                 dsnot_toy=gen_dsnot_toy, lora_merge=gen_lora_merge, lora_forward=gen_lora_forward, sparsegpt=gen_sparsegpt,
-                reorder=gen_reorder)
+                reorder=gen_reorder, layer_sparsity=gen_layer_sparsity)
     for name, fn in gens.items():
         if not only or name in only:
             fn(ref)

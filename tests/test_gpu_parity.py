@@ -1148,3 +1148,285 @@ def test_merge_batch_equals_per_linear(native, tag):
         native.sparselora_merge_batch(got, As, Bs, sc, Ms, remask=remask)
         for a, b in zip(ref, got):
             assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------- K18-K22: SURVEY 8f-4, global sparsity allocation
+def _ls_scores_gpu(g, kind):
+    return {str(k): torch.from_numpy(g[f"scores|{kind}|{k}"].copy()).cuda() for k in g["names"]}
+
+
+def _bits(arr, n):
+    return np.unpackbits(arr)[:n].astype(bool)
+
+
+def test_global_get_mask_golden(native):
+    """LayerSparsity.get_mask of the reference (committed fixture): masks and the protected entries, bit for bit."""
+    from vlmc.compression.pruners import layer_sparsity as ls
+    g = gu.load("layer_sparsity.npz")
+    fmax = float(np.finfo(np.float32).max)
+    for tag in g["global_cases"]:
+        kind, p, ms = str(tag).split("|")
+        sc = _ls_scores_gpu(g, kind)
+        before = {k: v.clone() for k, v in sc.items()}
+        masks = ls.get_mask(sc, float(p), float(ms))
+        for k in sc:
+            n = sc[k].numel()
+            assert masks[k].dtype == torch.float32 and masks[k].shape == sc[k].shape
+            assert np.array_equal(masks[k].cpu().numpy().ravel() != 0, _bits(g[f"global|{tag}|{k}"], n)), (tag, k)
+            changed = (sc[k] != before[k]).cpu().numpy().ravel()
+            assert np.array_equal(changed, _bits(g[f"global_protected|{tag}|{k}"], n)), (tag, k)
+            assert bool((sc[k].cpu().numpy().ravel()[changed] == fmax).all())
+
+
+def test_layerwise_get_mask_golden(native):
+    from vlmc.compression.pruners import layer_sparsity as ls
+    g = gu.load("layer_sparsity.npz")
+    for kind in ("obd", "ties", "signed"):
+        for p in (0.5, 0.25):
+            sc = _ls_scores_gpu(g, kind)
+            masks = ls.get_layerwise_mask(sc, p)
+            for k in sc:
+                assert np.array_equal(masks[k].cpu().numpy().ravel() != 0,
+                                      _bits(g[f"layerwise|{kind}|{p}|{k}"], sc[k].numel())), (kind, p, k)
+
+
+@pytest.mark.parametrize("method", ["obd_avg", "aobd_avg", "gradient_avg"])
+def test_importance_scores_golden(native, method):
+    """compute_importance_scores' arithmetic (K22) on the reference's own gradients: bit-exact."""
+    g = gu.load("layer_sparsity.npz")
+    names = [str(k) for k in g["model_names"]]
+    compute = method.split("_")[0]
+    params = [torch.from_numpy(g[f"param|{k}"].copy()).cuda() for k in names]
+    acc = [torch.zeros_like(p) for p in params]
+    for b in range(3):
+        native.importance_accum(acc, [torch.from_numpy(g[f"grad|{b}|{k}"].copy()).cuda() for k in names],
+                                "obd" if compute == "obd" else "abs")
+    out = [torch.empty_like(a) for a in acc]
+    native.importance_finalize(acc, params, out, "obd" if "obd" in compute else "gradient", 3)
+    for k, o in zip(names, out):
+        assert np.array_equal(o.cpu().numpy(), g[f"importance|{method}|{k}"]), k
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_importance_and_mask_half_precision_params(native, dtype):
+    """Gradients / parameters in the model's dtype: up-cast exactly, products rounded like the tensor expression; the
+    fused `param *= mask` leaves kept weights untouched and turns pruned ones into signed zeros (w * 0.0)."""
+    g = torch.Generator().manual_seed(5)
+    shapes = [(37, 53), (1, 7), (300, 129)]
+    params = [(torch.randn(s, generator=g) * 0.05).to(dtype).cuda() for s in shapes]
+    grads = [[(torch.randn(s, generator=g) * 1e-2).to(dtype).cuda() for s in shapes] for _ in range(2)]
+    acc = [torch.zeros(s, device="cuda") for s in shapes]
+    for gb in grads:
+        native.importance_accum(acc, gb, "obd")
+    out = [torch.empty_like(a) for a in acc]
+    native.importance_finalize(acc, params, out, "obd", 2)
+    for i, s in enumerate(shapes):
+        want = oracle.importance_scores_first_order(params[i].float().cpu().numpy(),
+                                                    [gb[i].float().cpu().numpy() for gb in grads], "obd")
+        assert np.array_equal(out[i].cpu().numpy(), want)
+    scores = {str(i): o for i, o in enumerate(out)}
+    want_masks, _ = oracle.global_get_mask({k: v.cpu().numpy().copy() for k, v in scores.items()}, 0.4, 1.0)
+    from vlmc.compression.pruners import layer_sparsity as ls
+    before = [p.clone() for p in params]
+    masks = ls.get_mask(scores, 0.4, 1.0, params={str(i): p for i, p in enumerate(params)})
+    for i, p in enumerate(params):
+        m = want_masks[str(i)].astype(bool)
+        assert np.array_equal(masks[str(i)].cpu().numpy() != 0, m)
+        want_w = (before[i].float() * torch.from_numpy(want_masks[str(i)]).cuda()).to(dtype)
+        assert torch.equal(p.view(torch.int16), want_w.view(torch.int16))          # signed zeros included
+
+
+def test_scores_kth_edge_cases(native):
+    """NaN sorts last, -0.0 == +0.0, infinities, denormals, ranks 1 and numel, unaligned views, one-element tensors, empty
+    tensors in the list, > 64 tensors (several launches), segments mixed across launches."""
+    g = torch.Generator().manual_seed(9)
+    base = torch.randn(70001, generator=g)
+    base[::97] = float("nan")
+    base[1::101] = float("inf")
+    base[2::103] = -float("inf")
+    base[3::107] = -0.0
+    base[4::109] = 0.0
+    base[5::113] = 1e-42
+    dev = base.cuda()
+    flat = np.sort(base.numpy())                                    # NaN last, like torch.topk
+    for k in (1, 2, 35000, 69000, 69500, 70001):
+        got = native.scores_kth([dev], [0], [k]).cpu().numpy()[0]
+        want = flat[k - 1]
+        assert (np.isnan(got) and np.isnan(want)) or got == want, (k, got, want)
+    # many small tensors, odd sizes and alignments, two segments interleaved
+    storage = torch.randn(200000, generator=g).cuda()
+    tensors, segs, off = [], [], 1
+    for i in range(150):
+        n = [0, 1, 3, 17, 1025, 4099][i % 6]
+        tensors.append(storage[off:off + n])
+        segs.append(i % 2)
+        off += n + (i % 3)
+    for s in (0, 1):
+        vals = np.sort(np.concatenate([t.cpu().numpy() for t, sg in zip(tensors, segs) if sg == s]))
+        ks = [1, len(vals) // 3, len(vals)]
+        for k in ks:
+            kk = [1, 1]
+            kk[s] = k
+            got = native.scores_kth(tensors, segs, kk).cpu().numpy()
+            assert got[s] == vals[k - 1] and got[1 - s] == np.sort(np.concatenate(
+                [t.cpu().numpy() for t, sg in zip(tensors, segs) if sg == 1 - s]))[0]
+    with pytest.raises(IndexError):                                 # topk(k=0)[0][-1] on the reference side
+        native.scores_kth([dev], [0], [0])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        native.scores_kth([base], [0], [1])
+    with pytest.raises(TypeError):
+        native.scores_kth([dev.half()], [0], [1])
+
+
+def test_scores_sum_and_zero_fraction(native):
+    from vlmc.compression.pruners import layer_sparsity as ls
+    g = torch.Generator().manual_seed(3)
+    ts = [(torch.randn(n, generator=g) ** 2 * 10.0 ** (i - 2)).cuda() for i, n in enumerate([1, 77, 65536, 65537, 300001])]
+    got = native.scores_sum(ts).cpu().numpy()
+    for t, s in zip(ts, got):
+        want = t.cpu().numpy().astype(np.float64).sum()
+        assert abs(s - want) <= 1e-12 * abs(want)
+    again = native.scores_sum(ts).cpu().numpy()
+    assert np.array_equal(got, again)                               # fixed summation order
+    w = [torch.randn(50, 30, generator=g).half().cuda(), torch.randn(7, generator=g).cuda()]
+    w[0][::3] = 0
+    w[1][2] = -0.0
+    fr = ls.zero_fraction(w)
+    assert abs(fr[0] - float((w[0] == 0).float().sum() / w[0].numel())) < 1e-6 and abs(fr[1] - 1 / 7) < 1e-12
+
+
+class _AllocToy(torch.nn.Module):
+    """Same architecture as tests/golden/make_golden.py::_AllocModel; weights are loaded from the fixture."""
+
+    def __init__(self):
+        super().__init__()
+        nn = torch.nn
+        lin = lambda o, i: nn.Linear(i, o, bias=False)
+        self.t5_model = nn.ModuleDict({"encoder": nn.ModuleDict({"block": nn.ModuleList(
+            [nn.ModuleDict({"q": lin(24, 24), "wi": lin(60, 24), "wo": lin(24, 60)}) for _ in range(3)])})})
+        self.visual_encoder = nn.ModuleDict({"blocks": nn.ModuleList(
+            [nn.ModuleDict({"qkv": lin(48, 16), "fc1": lin(40, 16)}) for _ in range(2)])})
+
+    def forward(self, samples):
+        h = samples["x"]
+        for b in self.t5_model["encoder"]["block"]:
+            h = h + torch.tanh(b["wo"](torch.relu(b["wi"](b["q"](h)))))
+        v = samples["v"]
+        acc = 0
+        for b in self.visual_encoder["blocks"]:
+            acc = acc + b["qkv"](v).pow(2).mean() + b["fc1"](v).abs().mean()
+        return {"loss": h.pow(2).mean() + acc}
+
+
+def _alloc_setup(g):
+    model = _AllocToy()
+    names = [str(k) for k in g["model_names"]]
+    with torch.no_grad():
+        for k, v in model.named_parameters():
+            v.copy_(torch.from_numpy(g[f"param|{k}"]))
+    model = model.cuda()
+    gd = torch.Generator().manual_seed(6)
+    loader = [{"x": torch.randn(4, 24, generator=gd).cuda(), "v": torch.randn(4, 16, generator=gd).cuda(),
+               "text_input": ["t"] * 4} for _ in range(3)]
+    loss_func = lambda m, d, cuda_enabled: (m(d)["loss"], len(d["text_input"]))
+    return model, names, loader, loss_func
+
+
+def test_layer_sparsity_return_sparsity_golden(native):
+    """LayerSparsity.return_sparsity end to end on the GPU (autograd gradients, K22 scores, K21 group sums, the allocation
+    loop) against the reference's result on the same toy model.  The gradients come from a GPU autograd pass instead of a
+    CPU one, so scores differ in the last places; the allocation may move a few parameters between groups."""
+    from vlmc.compression.pruners.layer_single_base_pruner import LayerSparsity
+    g = gu.load("layer_sparsity.npz")
+    model, names, loader, loss_func = _alloc_setup(g)
+    smallest = min(p.numel() for p in model.parameters())
+    for tag in g["alloc_cases"]:
+        method, gran, sparsity, ms = str(tag).split("|")
+
+        def group_of(name):
+            if gran == "layer":
+                return name
+            if name.startswith("t5_model"):
+                return "t5_model" if gran == "model" else ".".join(name.split(".")[:4])
+            return "visual_encoder" if gran == "model" else ".".join(name.split(".")[:3])
+        ls = LayerSparsity(model, loader, loss_func, 12, float(sparsity), float(ms), method, 1, 1e-3,
+                           {k: group_of(k) for k in names})
+        res = ls.return_sparsity()
+        got = np.array([res[k] for k in names])
+        assert np.abs(got - g[f"alloc|{tag}"]).max() <= 3.0 / smallest, (tag, got, g[f"alloc|{tag}"])
+        if gran == "layer" and sparsity == "0.5":
+            for k in names:
+                assert rel_inf(ls.importance_measure[k].cpu().numpy(), g[f"importance|{method}|{k}"]) < 1e-4, (tag, k)
+    ls = LayerSparsity(model, loader, loss_func, 12, 0.5, 0.8, "obd_avg", 1, 1e-3,
+                       {k: ".".join(k.split(".")[:4]) if k.startswith("t5_model") else ".".join(k.split(".")[:3]) for k in names},
+                       prune_per_model=True, per_model_group=["t5_model", "visual_encoder"], per_model_sparsity=[0.6, 0.4])
+    res = ls.return_sparsity()
+    assert np.abs(np.array([res[k] for k in names]) - g["alloc_per_model"]).max() <= 3.0 / smallest
+
+
+def test_global_iterative_pruning_restores_weights_and_reports_sparsity(native):
+    from vlmc.compression.pruners.layer_single_base_pruner import LayerSparsity
+    g = gu.load("layer_sparsity.npz")
+    model, names, loader, loss_func = _alloc_setup(g)
+    before = {k: v.detach().clone() for k, v in model.named_parameters()}
+    ls = LayerSparsity(model, loader, loss_func, 12, 0.5, 0.8, "obd_avg", 1, 1e-3, {k: k for k in names})
+    real = ls.global_iterative_pruning(0.5, {k: k for k in names}, iteratation=3, max_sparsity_per_layer=1.0)
+    got = np.array([real[k] for k in names])
+    total = sum(v.numel() for v in before.values())
+    assert abs(sum(real[k] * before[k].numel() for k in names) / total - 0.5) < 2e-3       # int(p * numel) + ties
+    assert np.abs(got - g["real_sparsity"]).max() < 0.05                                    # GPU vs CPU autograd gradients
+    for k, v in model.named_parameters():
+        assert torch.equal(v.detach(), before[k])                                           # weights restored (:231-235)
+
+
+def test_global_mag_pruner_on_toy_model(native):
+    """blipt5_mag_pruner (global_pruner.py:238-243) through load_pruner: global / per-model / layer-wise thresholds."""
+    import vlmc.compression as comp
+    g = gu.load("layer_sparsity.npz")
+    for is_global, per_model in ((True, False), (True, True), (False, False)):
+        model, names, loader, _ = _alloc_setup(g)
+        w0 = {k: v.detach().clone() for k, v in model.named_parameters()}
+        cfg = dict(t5_prune_spec="3-0.6-1.0-1.0", vit_prune_spec="2-0.6-1.0-1.0", t5_pruning_method="mag",
+                   vit_pruning_method="mag", is_global=is_global, prune_per_model=per_model, iteration=1,
+                   t5_model_prefix="t5_model", vit_model_prefix="visual_encoder")
+        pruner = comp.load_pruner("blipt5_mag_pruner", model, loader, cfg=cfg)
+        model, _ = pruner.prune()
+        scores = {k: w0[k].float().cpu().numpy().copy() for k in names}          # signed weights, as shipped
+        if is_global and not per_model:
+            want, _ = oracle.global_get_mask(scores, 1 - 0.6, 1.0)
+        elif is_global:
+            want = {}
+            for prefix in ("visual_encoder", "t5_model"):
+                part, _ = oracle.global_get_mask({k: v for k, v in scores.items() if k.startswith(prefix)}, 1 - 0.6, 1.0)
+                want.update(part)
+        else:
+            want = oracle.layerwise_get_mask(scores, 1 - 0.6)
+        for k, v in model.named_parameters():
+            assert np.array_equal(v.detach().cpu().numpy(), w0[k].cpu().numpy() * want[k]), (is_global, per_model, k)
+
+
+def test_global_select_full_size_properties(native):
+    """One Vicuna block's worth of scores (202 M, 7 tensors): the threshold splits the population exactly at the rank,
+    protected entries are never pruned, and the per-tensor select agrees with torch.kthvalue."""
+    from vlmc.compression.pruners import layer_sparsity as ls
+    shapes = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    scores = {f"l{i}": (torch.randn(s, generator=g, device="cuda") ** 2) * (torch.randn(s, generator=g, device="cuda") ** 2)
+              * (0.5 + i) for i, s in enumerate(shapes)}
+    total = sum(t.numel() for t in scores.values())
+    k = int(0.5 * total)
+    thr = native.scores_kth(list(scores.values()), [0] * 7, [k])
+    below = sum(int((t < thr).sum()) for t in scores.values())
+    at_or_below = sum(int((t <= thr).sum()) for t in scores.values())
+    assert below < k <= at_or_below
+    per = native.scores_kth(list(scores.values()), list(range(7)), [t.numel() // 3 for t in scores.values()])
+    for i, t in enumerate(scores.values()):
+        assert float(per[i]) == float(torch.kthvalue(t.flatten(), t.numel() // 3).values)
+    masks = ls.get_mask(scores, 0.5, 0.8)
+    kept = sum(int(m.sum()) for m in masks.values())
+    assert abs(kept - (total - k)) <= 8                                   # ties at the threshold only
+    for name, t in scores.items():
+        prot = t == torch.finfo(torch.float32).max
+        assert int(prot.sum()) >= int(t.numel() * (1 - 0.8))
+        assert bool(masks[name][prot].all())
+        assert float(masks[name].mean()) >= 0.2 - 1e-6

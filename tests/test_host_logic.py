@@ -159,3 +159,64 @@ def test_pruned_checkpoint_layout_matches_the_reference_flow(tmp_path, built_lib
     assert checkpoint.load_pruned_vision_model(fresh, str(tmp_path / "vit.pth")) == "visual."
     assert torch.equal(fresh.visual_encoder.blocks[0].attn.qkv.weight, model.visual_encoder.blocks[0].attn.qkv.weight)
     assert not torch.equal(fresh.visual_encoder.blocks[0].mlp.fc1.weight, model.visual_encoder.blocks[0].mlp.fc1.weight)
+
+
+# ---- the allocation loop and the group mapping are host arithmetic ---------------------------------------
+def test_sparsity_allocation_matches_reference_golden(built_lib):
+    import numpy as np
+    import golden_util as gu
+    import test_oracle_vs_golden as og
+    from vlmc.compression.pruners.layer_sparsity import compute_the_sparsity_per_group
+    g = gu.load("layer_sparsity.npz")
+    names = [str(k) for k in g["model_names"]]
+    for tag in g["alloc_cases"]:
+        method, gran, sparsity, ms = str(tag).split("|")
+        imp = og._ls_importance(g, method)
+
+        def group_of(name):
+            if gran == "layer":
+                return name
+            if name.startswith("t5_model"):
+                return "t5_model" if gran == "model" else ".".join(name.split(".")[:4])
+            return "visual_encoder" if gran == "model" else ".".join(name.split(".")[:3])
+        scores, counts = {}, {}
+        for k in names:
+            gk = group_of(k)
+            scores[gk] = scores.get(gk, torch.zeros(())) + torch.tensor(float(imp[k].sum(dtype=np.float64))).float()
+            counts[gk] = counts.get(gk, 0) + imp[k].size
+        if method.endswith("avg"):
+            scores = {k: v / counts[k] for k, v in scores.items()}
+        total_keep = int(sum(counts.values()) * (1 - float(sparsity)))
+        got = compute_the_sparsity_per_group(total_keep, scores, counts, max_sparsity_per_layer=float(ms))
+        want = g[f"alloc|{tag}"]
+        assert max(abs(got[group_of(k)] - w) for k, w in zip(names, want)) < 1e-9, tag
+
+
+def test_layer_to_group_mapping_and_registered_global_pruners(built_lib):
+    from vlmc.common.registry import registry
+    import vlmc.compression  # noqa: F401
+    from vlmc.compression.pruners.layer_single_base_pruner import LayerWiseBasePruner, LayerSparsity, UniformSparsity
+    assert {"blipt5_mag_pruner", "blipt5_aobd_pruner"} <= set(registry.list_pruners())
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.t5_model = nn.ModuleDict({"encoder": nn.ModuleDict({"block": nn.ModuleList(
+                [nn.ModuleDict({"q": nn.Linear(4, 4), "relative_attention_bias": nn.Embedding(3, 4)})])})})
+            self.visual_encoder = nn.ModuleDict({"blocks": nn.ModuleList([nn.ModuleDict({"fc1": nn.Linear(4, 8)})])})
+            self.head = nn.Linear(4, 2)
+    p = LayerWiseBasePruner(M(), [], model_prefix="t5_model")
+    p.t5_model_prefix, p.vit_model_prefix = "t5_model", "visual_encoder"
+    assert p.prunable_parameter_names() == ["t5_model.encoder.block.0.q.weight", "visual_encoder.blocks.0.fc1.weight"]
+    assert p.layer_to_group_mapping("none") == {}
+    assert p.layer_to_group_mapping("model") == {"t5_model.encoder.block.0.q.weight": "t5_model",
+                                                  "visual_encoder.blocks.0.fc1.weight": "visual_encoder"}
+    assert p.layer_to_group_mapping("block") == {"t5_model.encoder.block.0.q.weight": "t5_model.encoder.block.0",
+                                                  "visual_encoder.blocks.0.fc1.weight": "visual_encoder.blocks.0"}
+    assert list(p.layer_to_group_mapping("layer").values()) == p.prunable_parameter_names()
+    with pytest.raises(NotImplementedError):
+        p.layer_to_group_mapping("channel")
+    ls = LayerSparsity(None, None, None, 1, 0.5, 0.8, "obd_avg", layer_to_group_mapping={})
+    assert isinstance(ls.return_sparsity(), UniformSparsity) and ls.return_sparsity()["x"] == 0.5
+    with pytest.raises(AssertionError):            # max_sparsity_per_layer < original_sparsity (:146)
+        LayerSparsity(None, None, None, 1, 0.9, 0.8, "obd_avg")

@@ -1,21 +1,14 @@
 """API shell of the reference's pruner base classes (boundary only, no arithmetic).
 
 Mirrors lavis/compression/pruners/base_pruner.py:7-82 and layer_single_base_pruner.py:10-108:
-constructor arguments, spec parsing, requires_grad bookkeeping around prune().  The ECoFLaP
-LayerSparsity allocation (layer_single_base_pruner.py:240-420) is out of scope;
-with the scripts' `sparsity_ratio_granularity none` it degenerates to the constant lookup kept here.
+constructor arguments, spec parsing, requires_grad bookkeeping around prune().  `LayerSparsity`
+(layer_single_base_pruner.py:111-475) lives in layer_sparsity.py and is re-exported here, where the
+reference defines it; with the scripts' `sparsity_ratio_granularity none` it degenerates to a constant lookup.
 """
 import yaml
 
-
-class UniformSparsity:
-    """layer_single_base_pruner.py:251-255: every key maps to the same sparsity."""
-
-    def __init__(self, sparsity):
-        self.sparsity = sparsity
-
-    def __getitem__(self, key):
-        return self.sparsity
+from vlmc.compression.pruners.layer_sparsity import LayerSparsity, UniformSparsity  # noqa: F401
+from vlmc.compression.pruners.utils import loss_vision_language
 
 
 class BasePruner:
@@ -78,13 +71,39 @@ class LayerWiseBasePruner(BasePruner):
         num_layers, res_keep, attn_keep, ffn_keep = spec.split("-")
         return int(num_layers), float(res_keep), float(attn_keep), float(ffn_keep)
 
+    def prunable_parameter_names(self):
+        """wanda_pruner.py:875-885: 2-D parameters of the transformer blocks of either sub-model."""
+        t5, vit = getattr(self, "t5_model_prefix", self.model_prefix), getattr(self, "vit_model_prefix", self.model_prefix)
+        return [k for k, v in self.model.named_parameters()
+                if len(v.shape) == 2 and ".block" in k and "relative_attention_bias.weight" not in k
+                and (k.startswith(t5) or k.startswith(vit))]
+
+    def layer_to_group_mapping(self, sparsity_ratio_granularity):
+        """wanda_pruner.py:871-920: which parameters share one sparsity ("model" / "block" / "layer")."""
+        if sparsity_ratio_granularity in (None, "none"):
+            return {}
+        t5, vit = getattr(self, "t5_model_prefix", self.model_prefix), getattr(self, "vit_model_prefix", self.model_prefix)
+        if sparsity_ratio_granularity not in ("model", "layer", "block"):
+            raise NotImplementedError
+
+        def group_of(name):
+            if sparsity_ratio_granularity == "layer":
+                return name
+            for prefix, fields in ((t5, 4), (vit, 3)):
+                if name.startswith(prefix):
+                    return prefix if sparsity_ratio_granularity == "model" else ".".join(name.split(".")[:fields])
+            return "other"
+
+        return {k: group_of(k) for k in self.prunable_parameter_names()}
+
     def get_sparsity(self, original_sparsity, sparsity_ratio_granularity=None):
-        """wanda_pruner.py:868-937.  A sparsity_dict yaml wins; granularity none -> constant."""
+        """wanda_pruner.py:865-939.  A sparsity_dict yaml wins; granularity none -> constant; otherwise the ECoFLaP
+        allocation over first-order importance scores (LayerSparsity, scores and selection on the GPU)."""
         if self.sparsity_dict is not None:
             with open(self.sparsity_dict, "r") as f:
                 return yaml.load(f, Loader=yaml.FullLoader)
-        if sparsity_ratio_granularity in (None, "none"):
-            return UniformSparsity(original_sparsity)
-        raise NotImplementedError(
-            "ECoFLaP global sparsity allocation (LayerSparsity) is outside the calibration-and-masking "
-            "path; pass sparsity_ratio_granularity='none' or a precomputed sparsity_dict yaml")
+        sparsity_module = LayerSparsity(
+            self.model, self.data_loader, loss_vision_language, self.num_data_first_stage, original_sparsity,
+            self.max_sparsity_per_layer, self.score_method, self.num_noise, self.noise_eps,
+            self.layer_to_group_mapping(sparsity_ratio_granularity))
+        return sparsity_module.return_sparsity()

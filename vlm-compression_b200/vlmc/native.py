@@ -53,6 +53,13 @@ SIGNATURES = {
     "vlmc_sparselora_lora_grads_workspace_bytes": (_sz, [_i, _i, _i]),
     "vlmc_sparselora_lora_grads": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "vlmc_count_nonzero_batch": (_i, [_vp, _i, _i, _vp, _vp]),
+    "vlmc_scores_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "vlmc_scores_kth": (_i, [_vp, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "vlmc_scores_protect": (_i, [_vp, _i, _i, _vp, _vp]),
+    "vlmc_scores_mask": (_i, [_vp, _i, _i, _vp, _vp]),
+    "vlmc_scores_sum": (_i, [_vp, _i, _vp, _vp, _sz, _vp]),
+    "vlmc_importance_accum": (_i, [_vp, _i, _i, _vp]),
+    "vlmc_importance_finalize": (_i, [_vp, _i, _i, _d, _vp]),
     "vlmc_hessian_prepare": (_i, [_vp, _i, _i64, _f, _vp, _vp, _vp]),
     "vlmc_hessian_add_damp": (_i, [_vp, _i, _i64, _vp, _vp]),
     "vlmc_chol_inv_upper": (_i, [_vp, _i, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
@@ -385,6 +392,118 @@ def count_nonzero(tensors):
                        lib.vlmc_count_nonzero_batch(items, len(chunk), dt, part.data_ptr(), _stream(part)))
                 out[torch.tensor(chunk, device=dev)] = part
     return out
+
+
+# ---- global sparsity allocation on fp32 importance scores (K18-K22) -------------------------------------
+class ScoreItem(ctypes.Structure):
+    _fields_ = [("scores", _vp), ("numel", _i64), ("segment", _i), ("aux_dtype", _i), ("aux", _vp), ("out", _vp)]
+
+
+def _score_items(scores, segments=None, aux=None, outs=None):
+    """Host array of vlmc_score_item for fp32 CUDA score tensors (used in place, so they must be contiguous)."""
+    scores = list(scores)
+    if not scores:
+        raise ValueError("no score tensors given")
+    _require_cuda(*scores)
+    dev = scores[0].device
+    items = (ScoreItem * len(scores))()
+    for i, t in enumerate(scores):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
+            raise TypeError("importance scores must be contiguous float32 tensors on one CUDA device")
+        a = aux[i] if aux is not None else None
+        o = outs[i] if outs is not None else None
+        adt = 0
+        if a is not None:
+            _require_cuda(a)
+            if a.numel() != t.numel() or not a.is_contiguous() or a.device != dev:
+                raise ValueError("parameter / gradient tensors must be contiguous and sized like their scores")
+            adt = _dtype(a)
+        if o is not None:
+            _require_cuda(o)
+            if o.dtype != torch.float32 or o.numel() != t.numel() or not o.is_contiguous() or o.device != dev:
+                raise ValueError("outputs must be contiguous float32 tensors sized like their scores")
+        n = t.numel()
+        items[i] = ScoreItem(t.data_ptr() if n else None, n, int(segments[i]) if segments is not None else 0, adt,
+                             a.data_ptr() if (a is not None and n) else None,
+                             o.data_ptr() if (o is not None and n) else None)
+    return items, dev, scores[0]
+
+
+def scores_kth(scores, segments, k):
+    """K18: exact k-th smallest score (1-based) per segment, torch.topk order (layer_single_base_pruner.py:157-158,
+    :168-170).  scores: fp32 CUDA tensors; segments[i]: segment of scores[i]; k: one rank per segment.  Returns a float32
+    device tensor [nseg]; nothing is synchronised."""
+    k = [int(x) for x in k]
+    nseg = len(k)
+    sizes = [0] * nseg
+    for t, sg in zip(scores, segments):
+        sizes[sg] += t.numel()
+    for ks, n in zip(k, sizes):
+        if ks < 1 or ks > n:
+            # topk(k=0)[0][-1] on the reference side
+            raise IndexError(f"rank {ks} is outside a segment of {n} scores")
+    items, dev, ref = _score_items(scores, segments)
+    lib = load()
+    with torch.cuda.device(dev):
+        kd = torch.tensor(k, dtype=torch.int64, device=dev)
+        out = torch.empty(nseg, dtype=torch.float32, device=dev)
+        nbytes = lib.vlmc_scores_workspace_bytes(items, len(items), nseg)
+        ws = workspace(ref, nbytes)
+        _check("vlmc_scores_kth", lib.vlmc_scores_kth(items, len(items), nseg, kd.data_ptr(), out.data_ptr(),
+                                                      ws.data_ptr(), ws.numel(), _stream(ref)))
+    return out
+
+
+def scores_protect(scores, segments, thr):
+    """K19: scores[v >= thr[segment]] = finfo(float32).max in place (layer_single_base_pruner.py:160)."""
+    items, dev, ref = _score_items(scores, segments)
+    _require_cuda(thr)
+    with torch.cuda.device(dev):
+        _check("vlmc_scores_protect", load().vlmc_scores_protect(items, len(items), thr.numel(), thr.data_ptr(),
+                                                                 _stream(ref)))
+
+
+def scores_mask(scores, segments, thr, outs=None, params=None):
+    """K20: outs[i] = (scores[i] > thr[segment]) as float32 (layer_single_base_pruner.py:174) and, when params is given,
+    params[i] *= that mask in the parameter's dtype (:223-225)."""
+    items, dev, ref = _score_items(scores, segments, aux=params, outs=outs)
+    _require_cuda(thr)
+    with torch.cuda.device(dev):
+        _check("vlmc_scores_mask", load().vlmc_scores_mask(items, len(items), thr.numel(), thr.data_ptr(), _stream(ref)))
+
+
+def scores_sum(scores):
+    """K21: per-tensor sums as a float64 device tensor (layer_single_base_pruner.py:296), fixed summation order."""
+    items, dev, ref = _score_items(scores)
+    lib = load()
+    with torch.cuda.device(dev):
+        out = torch.empty(len(items), dtype=torch.float64, device=dev)
+        nbytes = lib.vlmc_scores_workspace_bytes(items, len(items), 1)
+        ws = workspace(ref, nbytes)
+        _check("vlmc_scores_sum", lib.vlmc_scores_sum(items, len(items), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                      _stream(ref)))
+    return out
+
+
+IMPORTANCE_MODES = {"obd": 0, "abs": 1, "gradient": 2}
+
+
+def importance_accum(accs, grads, mode):
+    """K22a: accs[i] += grads[i].float() ** 2 ("obd") or .abs() ("abs") (layer_single_base_pruner.py:455-458)."""
+    items, dev, ref = _score_items(accs, aux=list(grads))
+    with torch.cuda.device(dev):
+        _check("vlmc_importance_accum", load().vlmc_importance_accum(items, len(items), IMPORTANCE_MODES[mode],
+                                                                     _stream(ref)))
+
+
+def importance_finalize(accs, params, outs, mode, num_batches):
+    """K22b: outs[i] = params[i].float() ** 2 * (accs[i] / num_batches) ("obd"), |w| * |acc / n| ("abs") or |acc / n|
+    ("gradient") (layer_single_base_pruner.py:460-473)."""
+    m = IMPORTANCE_MODES[mode]
+    items, dev, ref = _score_items(accs, aux=None if m == 2 else list(params), outs=list(outs))
+    with torch.cuda.device(dev):
+        _check("vlmc_importance_finalize", load().vlmc_importance_finalize(items, len(items), m, float(num_batches),
+                                                                           _stream(ref)))
 
 
 def _lora_common(W, A, B, keep_mask):
