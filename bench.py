@@ -571,7 +571,9 @@ def run_gpu(args):
             out["config"]["cuda_graph_error"] = main["cuda_graph_error"]
         if world == 1 and args.all_methods and args.method == "wanda_nm":
             out["workloads"] = {"config2_instructblip_flant5xl_wanda_2of4": full_model_wanda_nm(torch, native, dev),
-                                "config5_sparselora_and_hessian_sweep": config5_lora_and_hessian_sweep(torch, native, dev, inputs)}
+                                "config5_sparselora_and_hessian_sweep": config5_lora_and_hessian_sweep(torch, native, dev, inputs),
+                                "f4_global_sparsity_allocation": f4_global_allocation(torch, native, dev,
+                                                                                      cpu=not args.no_cpu_baseline)}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.method)
         print(json.dumps(out), flush=True)
@@ -876,6 +878,59 @@ def config5_lora_and_hessian_sweep(torch, native, dev, inputs):
             sweep[f"C{C}_T{nseq}x{SEQ_LEN}"] = {"ms": t, "logical_tflops": 2.0 * nseq * SEQ_LEN * C * C / t / 1e9}
         del H
     out["hessian_accum_sweep"] = sweep
+    torch.cuda.empty_cache()
+    return out
+
+
+def f4_global_allocation(torch, native, dev, cpu=True):
+    """LayerSparsity on the parameters of one Vicuna-7B block (7 linears, 202 M fp32 scores, 0.81 GB): the
+    first-order score build (K22), the group sums (K21) and get_mask(p = 0.5, max_sparsity_per_layer = 0.8) = per-tensor
+    protection (K18 + K19), the whole-block exact threshold (K18) and masks with the fused `param *= mask` (K20).
+    The reference runs the same on the CPU (v.cpu(), torch.topk over the concatenation); `cpu_reference` times its op
+    sequence (oracle/cpu_port.global_get_mask) on q_proj alone (16.8 M scores) on the host cores."""
+    from vlmc.compression.pruners import layer_sparsity as ls
+    g = torch.Generator(device=dev).manual_seed(13)
+    params = [(torch.randn(R, C, device=dev, generator=g) * 0.02).half() for _, R, C, _ in LINEARS]
+    grads = [(torch.randn(R, C, device=dev, generator=g) * 1e-3).half() for _, R, C, _ in LINEARS]
+    acc = [torch.zeros(p.shape, device=dev) for p in params]
+    scores = [torch.empty_like(a) for a in acc]
+    n = sum(p.numel() for p in params)
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    out = {"scores": n}
+    ms = timed(lambda: native.importance_accum(acc, grads, "obd"))
+    out["importance_accum"] = {"ms": ms, "achieved_gbs": n * 10 / ms / 1e6, "bytes_per_score": 10}
+    ms = timed(lambda: native.importance_finalize(acc, params, scores, "obd", 4))
+    out["importance_finalize"] = {"ms": ms, "achieved_gbs": n * 10 / ms / 1e6, "bytes_per_score": 10}
+    ms = timed(lambda: native.scores_sum(scores))
+    out["scores_sum"] = {"ms": ms, "achieved_gbs": n * 4 / ms / 1e6, "bytes_per_score": 4}
+    ms = timed(lambda: native.scores_kth(scores, [0] * len(scores), [n // 2]))
+    out["scores_kth_global"] = {"ms": ms, "achieved_gbs": n * 12 / ms / 1e6, "bytes_per_score": 12, "passes": 3}
+    named = {name: s for (name, *_), s in zip(LINEARS, scores)}
+    pd = {name: p for (name, *_), p in zip(LINEARS, params)}
+    ms = timed(lambda: ls.get_mask(named, 0.5, 0.8, params=pd))
+    # protect: 3 reads + 1 read/partial write; select: 3 reads; mask: read 4 + write 4 + read/write 2 + 2
+    out["get_mask_protect_select_mask_prune"] = {"ms": ms, "achieved_gbs": n * 40 / ms / 1e6, "bytes_per_score": 40}
+    if cpu:
+        from oracle import cpu_port
+        torch.set_num_threads(os.cpu_count() or 1)
+        gq = torch.Generator().manual_seed(3)
+        sc = {"q_proj": torch.randn(D, D, generator=gq) ** 2 * 1e-6}
+        t0 = time.perf_counter()
+        cpu_port.global_get_mask(sc, 0.5, 0.8)
+        t = time.perf_counter() - t0
+        out["cpu_reference"] = {"seconds_q_proj_only": t, "scores": D * D, "cores": os.cpu_count() or 1, "kind": "port",
+                                "scaled_to_block_s": t * n / (D * D)}
+    del params, grads, acc, scores
     torch.cuda.empty_cache()
     return out
 

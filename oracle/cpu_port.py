@@ -149,3 +149,16 @@ class DSnoTStat:
         self.nsamples += b
         self.scaler_row += torch.norm(inp, p=2, dim=1) ** 2 / self.nsamples
         self.sum_metric_row += torch.sum(inp, dim=1) / self.nsamples
+
+
+def global_get_mask(importance_scores, p, max_sparsity_per_layer):
+    """LayerSparsity.get_mask (layer_single_base_pruner.py:149-176) with the reference's own op sequence on CPU tensors:
+    per-tensor topk + where + index_put for the protected entries, cat of every score, topk, one compare per tensor."""
+    for k, v in importance_scores.items():
+        num_to_set = int(v.numel() * (1 - max_sparsity_per_layer))
+        if num_to_set > 0:
+            threshold = torch.topk(v.flatten(), num_to_set, largest=True)[0][-1]
+            v[torch.where(v >= threshold)] = torch.finfo(v.dtype).max
+    all_scores = torch.cat([t.flatten() for t in importance_scores.values()])
+    threshold = torch.topk(all_scores, int(p * all_scores.numel()), largest=False)[0][-1]
+    return {k: (v > threshold).type(v.dtype) for k, v in importance_scores.items()}

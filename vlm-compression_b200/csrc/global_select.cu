@@ -217,32 +217,99 @@ template <> __device__ __forceinline__ void aux_store<__nv_bfloat16>(void* p, in
 
 enum { kOpProtect = 0, kOpMask = 1, kOpAccum = 2, kOpFinalize = 3 };
 
+// four consecutive elements of the parameter / gradient tensor as floats (16-byte or 8-byte vectors)
+template <typename T> struct Aux4;
+template <> struct Aux4<float> {
+  static __device__ __forceinline__ void load(const void* p, int64_t i, float* f) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i));
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(void* p, int64_t i, const float* f) {
+    __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i), make_float4(f[0], f[1], f[2], f[3]));
+  }
+};
+template <> struct Aux4<__half> {
+  static __device__ __forceinline__ void load(const void* p, int64_t i, float* f) {
+    const uint2 v = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p) + i));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  }
+  static __device__ __forceinline__ void store(void* p, int64_t i, const float* f) {
+    uint2 v;
+    *reinterpret_cast<__half2*>(&v.x) = __floats2half2_rn(f[0], f[1]);
+    *reinterpret_cast<__half2*>(&v.y) = __floats2half2_rn(f[2], f[3]);
+    __stcs(reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p) + i), v);
+  }
+};
+template <> struct Aux4<__nv_bfloat16> {
+  static __device__ __forceinline__ void load(const void* p, int64_t i, float* f) {
+    const uint2 v = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p) + i));
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void store(void* p, int64_t i, const float* f) {
+    uint2 v;
+    *reinterpret_cast<__nv_bfloat162*>(&v.x) = __floats2bfloat162_rn(f[0], f[1]);
+    *reinterpret_cast<__nv_bfloat162*>(&v.y) = __floats2bfloat162_rn(f[2], f[3]);
+    __stcs(reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p) + i), v);
+  }
+};
+
+// one element: sv = score (in/out), av = parameter / gradient (in/out), ov = output
+template <int OP>
+__device__ __forceinline__ void score_elem(float& sv, float& av, float& ov, float thr, int mode, float nb) {
+  if (OP == kOpProtect) {
+    if (sv >= thr) sv = FLT_MAX;
+  } else if (OP == kOpMask) {
+    ov = sv > thr ? 1.0f : 0.0f;
+    av = __fmul_rn(av, ov);
+  } else if (OP == kOpAccum) {
+    sv = __fadd_rn(sv, mode == 0 ? __fmul_rn(av, av) : fabsf(av));
+  } else {
+    const float q = __fdiv_rn(sv, nb);
+    ov = mode == 2 ? fabsf(q) : mode == 0 ? __fmul_rn(__fmul_rn(av, av), q) : __fmul_rn(fabsf(av), fabsf(q));
+  }
+}
+
 template <int OP, typename T>
 __device__ __forceinline__ void score_unit(const ScoreBatch& b, int p, int64_t e0, int64_t e1, float thr, int mode, float nb) {
-  float* __restrict__ s = b.s[p];
+  float* s = b.s[p];
   void* aux = b.aux[p];
   float* out = b.out[p];
+  constexpr bool kWriteS = OP == kOpProtect || OP == kOpAccum;
+  constexpr bool kWriteAux = OP == kOpMask;
+  constexpr bool kWriteOut = OP == kOpMask || OP == kOpFinalize;
+  // 16-byte vectors when every array of this tensor allows it (torch allocations do); units start at multiples of 64 K
+  const bool vec = ((reinterpret_cast<uintptr_t>(s) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(aux) & (4 * sizeof(T) - 1)) == 0);
+  int64_t done = e0;
+  if (vec) {
+    const int64_t n4 = (e1 - e0) >> 2;
 #pragma unroll 4
-  for (int64_t i = e0 + threadIdx.x; i < e1; i += kSelThreads) {
-    if (OP == kOpProtect) {
-      if (s[i] >= thr) s[i] = FLT_MAX;
-    } else if (OP == kOpMask) {
-      const float m = s[i] > thr ? 1.0f : 0.0f;
-      if (out) out[i] = m;
-      if (aux) aux_store<T>(aux, i, __fmul_rn(aux_load<T>(aux, i), m));
-    } else if (OP == kOpAccum) {
-      const float g = aux_load<T>(aux, i);
-      s[i] = __fadd_rn(s[i], mode == 0 ? __fmul_rn(g, g) : fabsf(g));
-    } else {
-      const float q = __fdiv_rn(s[i], nb);
-      float r;
-      if (mode == 2) r = fabsf(q);
-      else {
-        const float w = aux_load<T>(aux, i);
-        r = mode == 0 ? __fmul_rn(__fmul_rn(w, w), q) : __fmul_rn(fabsf(w), fabsf(q));
+    for (int64_t v = threadIdx.x; v < n4; v += kSelThreads) {
+      const int64_t i = e0 + 4 * v;
+      const float4 s4 = __ldcs(reinterpret_cast<const float4*>(s + i));
+      float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+      float av[4] = {0.f, 0.f, 0.f, 0.f}, ov[4];
+      if (aux) Aux4<T>::load(aux, i, av);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) score_elem<OP>(sv[e], av[e], ov[e], thr, mode, nb);
+      if (kWriteS) {
+        if (OP != kOpProtect || sv[0] != s4.x || sv[1] != s4.y || sv[2] != s4.z || sv[3] != s4.w)
+          *reinterpret_cast<float4*>(s + i) = make_float4(sv[0], sv[1], sv[2], sv[3]);
       }
-      out[i] = r;
+      if (kWriteAux && aux) Aux4<T>::store(aux, i, av);
+      if (kWriteOut && out) __stcs(reinterpret_cast<float4*>(out + i), make_float4(ov[0], ov[1], ov[2], ov[3]));
     }
+    done = e0 + 4 * n4;
+  }
+  for (int64_t i = done + threadIdx.x; i < e1; i += kSelThreads) {
+    float sv = s[i], av = aux ? aux_load<T>(aux, i) : 0.f, ov;
+    score_elem<OP>(sv, av, ov, thr, mode, nb);
+    if (kWriteS) s[i] = sv;
+    if (kWriteAux && aux) aux_store<T>(aux, i, av);
+    if (kWriteOut && out) out[i] = ov;
   }
 }
 
