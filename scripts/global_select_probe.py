@@ -26,7 +26,7 @@ def timed(fn, reps=5):
     return sorted(ts)[len(ts) // 2]
 
 
-for blocks in (1, 4):
+for blocks in ((1,) if os.environ.get("VLMC_PROBE_ONE") else (1, 4)):
     params = [(torch.randn(s, device="cuda") * 0.02).half() for _ in range(blocks) for s in shapes]
     grads = [(torch.randn_like(p.float()) * 1e-3).half() for p in params]
     acc = [torch.zeros(p.shape, device="cuda") for p in params]
