@@ -20,13 +20,18 @@ for C in sizes:
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     import time
-    a.record()
-    h0 = time.perf_counter()
-    U, status = native.chol_inv_upper(H, U)
-    h1 = time.perf_counter()
-    b.record()
-    torch.cuda.synchronize()
-    print(f"C={C}: chol_inv_upper {a.elapsed_time(b):.2f} ms (host issue {1e3 * (h1 - h0):.2f} ms) status {status.item()}", flush=True)
+    for la in ("0", "1", "0", "1"):
+        os.environ["VLMC_CHOL_LOOKAHEAD"] = la
+        U, status = native.chol_inv_upper(H, U)
+        torch.cuda.synchronize()
+        a.record()
+        h0 = time.perf_counter()
+        U, status = native.chol_inv_upper(H, U)
+        h1 = time.perf_counter()
+        b.record()
+        torch.cuda.synchronize()
+        print(f"C={C} lookahead={la}: chol_inv_upper {a.elapsed_time(b):.2f} ms (host issue {1e3 * (h1 - h0):.2f} ms) "
+              f"status {status.item()}", flush=True)
     R = 4096
     W = (torch.randn(R, C, device="cuda") * 0.02).half()
     native.obs_sweep(W.clone(), U, 0.5, dead=dead)

@@ -540,6 +540,38 @@ def test_chol_inv_upper_vs_fp64(native, C, T):
     assert rel_inf(U.cpu().numpy(), Uo) < 1e-4
 
 
+@pytest.mark.parametrize("C", [384, 1408, 4096, 4100])
+def test_chol_lookahead_equals_plain_loop(native, C, monkeypatch):
+    """The look-ahead schedule of the blocked Cholesky (next block column on the caller's stream, the rest of the trailing
+    update on a side stream) computes the same GEMM per output element as the plain right-looking loop
+    (VLMC_CHOL_LOOKAHEAD=0): equal factors; also on a non-default caller stream, twice in a row, and for a matrix that is
+    not positive definite (status word, no hang)."""
+    x = acts(2 * C if C <= 1408 else C + 512, C, C + 1, torch.float32).cuda()
+    H = (x.t() @ x) * (2.0 / x.shape[0])                          # any C that is a multiple of 4 (4100: a 4-wide last block)
+    del x
+    damp, _ = native.hessian_prepare(H, 0.01)
+    native.hessian_add_damp(H, damp)
+    monkeypatch.setenv("VLMC_CHOL_LOOKAHEAD", "0")
+    U0, st0 = native.chol_inv_upper(H)
+    torch.cuda.synchronize()
+    monkeypatch.setenv("VLMC_CHOL_LOOKAHEAD", "1")
+    U1, st1 = native.chol_inv_upper(H)
+    torch.cuda.synchronize()
+    assert st0.item() == 0 and st1.item() == 0
+    assert float((U1 - U0).abs().max() / U0.abs().max()) < 1e-6
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        U2, st2 = native.chol_inv_upper(H)
+        U3, st3 = native.chol_inv_upper(H)
+    s.synchronize()
+    assert torch.equal(U2, U1) and torch.equal(U3, U1) and st2.item() == 0 and st3.item() == 0
+    Hbad = H.clone()
+    Hbad[C // 2, C // 2] = -1.0
+    _, stb = native.chol_inv_upper(Hbad)
+    assert stb.item() == native.NOT_POSDEF
+
+
 def test_chol_not_posdef_then_damped(native):
     """Fewer tokens than channels: the first attempt must report NOT_POSDEF, the damped retries must succeed
     (reference: conditional, cumulative damping, sparsegpt_pruner.py:114-128)."""

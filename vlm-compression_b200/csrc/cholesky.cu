@@ -12,6 +12,10 @@
 // GEMMs run on the tensor cores with the 3xTF32 split (gemm3x.cu): fp32-grade accuracy, like the reference's fp32
 // cuSOLVER/cuBLAS path.  A non-positive or NaN pivot
 // sets *status = VLMC_NOT_POSDEF; the caller adds percdamp * mean(diag H) and retries (reference :114-128).
+#include <stdlib.h>
+#include <map>
+#include <mutex>
+#include <utility>
 #include "gemm3x.cuh"
 
 namespace vlmc {
@@ -219,6 +223,31 @@ __global__ void add_diag_kernel(float* H, int64_t ldh, int C, const float* damp)
   if (i < C) H[(int64_t)i * ldh + i] += *damp;
 }
 
+// Side stream + fork/join events of the look-ahead, one set per (device, caller stream): chains that run concurrently on
+// different streams must not share a side stream (their trailing updates would queue behind each other).
+struct ChainSide { cudaStream_t stream; cudaEvent_t solved, updated; };
+
+static bool chol_lookahead_enabled() {
+  const char* e = getenv("VLMC_CHOL_LOOKAHEAD");          // read per call: tests flip it inside one process
+  return !(e && e[0] == '0');
+}
+
+static ChainSide* side_for(cudaStream_t st) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, ChainSide> sides;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(dev, st);
+  auto it = sides.find(key);
+  if (it != sides.end()) return &it->second;
+  ChainSide s;
+  if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cudaEventCreateWithFlags(&s.solved, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s.updated, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return &sides.emplace(key, s).first->second;
+}
+
 size_t chol_workspace_bytes(int C) {
   const int nb = (C + kNB - 1) / kNB;
   const size_t half = (size_t)((nb + 1) / 2) * kNB;
@@ -271,7 +300,16 @@ extern "C" int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U,
   flip_copy_kernel<<<dim3((C + 255) / 256, flip_rows), 256, 0, st>>>(H, ldh, F, ldf, C);
 
   // ---- blocked Cholesky of F (lower), diagonal-block inverses go straight into U (used as Li) ----
+  // Look-ahead (default; VLMC_CHOL_LOOKAHEAD=0 restores the plain right-looking loop): the trailing update of step k is
+  // split into the next block column (A_k, on the caller's stream: all that the next diagonal factor and panel solve
+  // need) and the rest (B_k, on a side stream forked from and joined to the caller's stream with events).  B_k leaves
+  // one SM free, so the one-CTA diagonal factor of step k+1 (55 us, a fifth of a step) runs under it instead of after it:
+  //   caller's stream:  P_k  S_k  [wait B_k-1]  A_k        P = diagonal factor + inverse, S = panel solve
+  //   side stream:      [wait S_k]  B_k                    (B_k after B_k-1 by stream order: same output region)
+  // Same GEMM per output element either way (K = 128, one chunk).
   int rc;
+  ChainSide* side = chol_lookahead_enabled() && nb > 2 ? side_for(st) : nullptr;
+  bool pending_b = false;
   for (int k = 0; k < nb; ++k) {
     const int k0 = k * kNB;
     const int bs = (C - k0 < kNB) ? (C - k0) : kNB;
@@ -284,10 +322,32 @@ extern "C" int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U,
       if (rc) return rc;
       // trailing <- trailing - panel panel^T on the lower tiles
       float* trail = F + (int64_t)(k0 + bs) * ldf + (k0 + bs);
-      rc = gemm3x(true, below, below, bs, -1.f, panel, ldf, panel, ldf, 1.f, trail, ldf, 1, 0, st);
+      const int bs2 = below < kNB ? below : kNB;          // width of the next block column
+      if (!side) {
+        rc = gemm3x(true, below, below, bs, -1.f, panel, ldf, panel, ldf, 1.f, trail, ldf, 1, 0, st);
+        if (rc) return rc;
+        continue;
+      }
+      const int rest = below - bs2;
+      if (rest > 0 && cudaEventRecord(side->solved, st) != cudaSuccess) return check_launch();
+      if (pending_b) {                                     // B_k-1 wrote the block column A_k is about to update
+        if (cudaStreamWaitEvent(st, side->updated, 0) != cudaSuccess) return check_launch();
+        pending_b = false;
+      }
+      rc = gemm3x(true, below, bs2, bs, -1.f, panel, ldf, panel, ldf, 1.f, trail, ldf, 0, 0, st);
       if (rc) return rc;
+      if (rest > 0) {
+        if (cudaStreamWaitEvent(side->stream, side->solved, 0) != cudaSuccess) return check_launch();
+        const float* prest = panel + (int64_t)bs2 * ldf;
+        rc = gemm3x(true, rest, rest, bs, -1.f, prest, ldf, prest, ldf, 1.f, trail + (int64_t)bs2 * ldf + bs2, ldf, 1, 0,
+                    side->stream, 0, false, kNumSMs - 1);
+        if (rc) return rc;
+        if (cudaEventRecord(side->updated, side->stream) != cudaSuccess) return check_launch();
+        pending_b = true;
+      }
     }
   }
+  if (pending_b && cudaStreamWaitEvent(st, side->updated, 0) != cudaSuccess) return check_launch();
   rc = check_launch();
   if (rc) return rc;
 

@@ -376,7 +376,7 @@ template <int TN> constexpr size_t g3_smem() {
 }
 
 template <int TN, bool B_MN, bool CHUNKED, bool A_MN = false>
-static int g3_launch(const CUtensorMap& amap, const CUtensorMap& bmap, G3Params p, cudaStream_t st) {
+static int g3_launch(const CUtensorMap& amap, const CUtensorMap& bmap, G3Params p, cudaStream_t st, int max_ctas = 0) {
   auto kern = gemm3x_kernel<TN, B_MN, CHUNKED, A_MN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -398,7 +398,8 @@ static int g3_launch(const CUtensorMap& amap, const CUtensorMap& bmap, G3Params 
   // fp32 accumulate, A and B TF32, A K-major, B K-major or MN-major, N = TN, M = 128 (cute::UMMA::InstrDescriptor)
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                          ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(kG3M >> 4) << 24);
-  const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
+  const int cap = (max_ctas > 0 && max_ctas < kNumSMs) ? max_ctas : kNumSMs;
+  const int grid = p.ntiles < cap ? p.ntiles : cap;
   kern<<<grid, kG3Threads, g3_smem<TN>(), st>>>(amap, bmap, p, idesc);
   return check_launch();
 }
@@ -419,7 +420,7 @@ static int g3_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t 
 }
 
 int gemm3x(bool b_nk, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb,
-           float beta, float* C, int64_t ldc, int tri, int kc, cudaStream_t st, int kmode, bool a_km) {
+           float beta, float* C, int64_t ldc, int tri, int kc, cudaStream_t st, int kmode, bool a_km, int max_ctas) {
   if (M <= 0 || N <= 0) return VLMC_OK;
   if (K <= 0 || !A || !B || !C) return VLMC_ERR_BAD_ARG;
   // K is the contiguous dimension of a K-major operand only: [K,M] / [K,N] operands take any K
@@ -449,8 +450,8 @@ int gemm3x(bool b_nk, int M, int N, int K, float alpha, const float* A, int64_t 
     return g3_launch<128, true, false, true>(amap, bmap, p, st);
   }
   if (chunked) return b_nk ? g3_launch<128, false, true>(amap, bmap, p, st) : g3_launch<128, true, true>(amap, bmap, p, st);
-  if (TN == 256) return b_nk ? g3_launch<256, false, false>(amap, bmap, p, st) : g3_launch<256, true, false>(amap, bmap, p, st);
-  return b_nk ? g3_launch<128, false, false>(amap, bmap, p, st) : g3_launch<128, true, false>(amap, bmap, p, st);
+  if (TN == 256) return b_nk ? g3_launch<256, false, false>(amap, bmap, p, st, max_ctas) : g3_launch<256, true, false>(amap, bmap, p, st, max_ctas);
+  return b_nk ? g3_launch<128, false, false>(amap, bmap, p, st, max_ctas) : g3_launch<128, true, false>(amap, bmap, p, st, max_ctas);
 }
 
 }  // namespace vlmc

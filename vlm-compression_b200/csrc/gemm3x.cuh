@@ -11,9 +11,12 @@ namespace vlmc {
 //   kmode: structural zeros whose k-slices are skipped.  1: B is [K,N] with B[k][j] == 0 for k < j (lower
 //          triangular); 2: A[i][k] == 0 for k > i (lower triangular).  0: dense
 //   a_km: A is given as a row-major [K,M] array (C = A^T op(B)); needs b_nk = false, kmode = 0; K is then arbitrary
+//   max_ctas: cap of the (persistent) grid, 0 = one CTA per SM; a caller that overlaps this GEMM with a kernel on another
+//          stream leaves SMs free this way
 // Requirements: K, N, lda, ldb, ldc multiples of 4; A, B, C 16-byte aligned.  A or B may alias C only when every
 // output tile reads exactly the operand rows it overwrites (N <= tile width: the panel solve of the Cholesky).
 int gemm3x(bool b_nk, int M, int N, int K, float alpha, const float* A, int64_t lda, const float* B, int64_t ldb,
-           float beta, float* C, int64_t ldc, int tri, int kc, cudaStream_t st, int kmode = 0, bool a_km = false);
+           float beta, float* C, int64_t ldc, int tri, int kc, cudaStream_t st, int kmode = 0, bool a_km = false,
+           int max_ctas = 0);
 
 }  // namespace vlmc
