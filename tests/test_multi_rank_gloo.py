@@ -220,3 +220,43 @@ def _dsnot(rank, out):
 @pytest.mark.parametrize("fn", ["_wanda", "_wanda_packed", "_sparsegpt", "_sparsegpt_linears", "_dsnot"])
 def test_two_ranks(fn, built_lib):
     _run(fn)
+
+
+def _importance_dp(rank, out):
+    """SURVEY 8f-4 across ranks: round-robin batches + ONE all-reduce of the packed accumulator reproduce the sequential
+    loop of compute_importance_scores (layer_single_base_pruner.py:440-463), including its stop rule on ragged batch
+    lengths (no batch is started once accum_samples >= num_samples) and the batch count used as the divisor."""
+    from oracle import oracle
+    from vlmc import parallel
+    g = torch.Generator().manual_seed(21)
+    shapes = [(6, 10), (3, 5)]
+    lens = [4, 4, 2, 4, 1, 4, 4, 3, 4]
+    batches = [{"len": n, "grads": [torch.randn(s, generator=g) * 0.1 for s in shapes]} for n in lens]
+    w = [torch.randn(s, generator=g) for s in shapes]
+    for num_samples in (1, 8, 10, 11, 14, 100):
+        # sequential truth (the reference's loop)
+        used, accum = [], 0
+        for b in batches:
+            if accum >= num_samples:
+                break
+            accum += b["len"]
+            used.append(b)
+        sizes = [int(np.prod(s)) for s in shapes]
+        packed = torch.zeros(sum(sizes))
+        views = [packed[sum(sizes[:i]):sum(sizes[:i + 1])].view(s) for i, s in enumerate(shapes)]
+
+        def accum_fn(grads):                         # stands in for native.importance_accum(acc, grads, "obd")
+            for v, gr in zip(views, grads):
+                v += gr * gr
+        nb = parallel.importance_accumulate_data_parallel(
+            batches, num_samples, lambda d: (d["grads"], d["len"]), accum_fn, packed, rank, WORLD)
+        assert nb == len(used), (num_samples, nb, len(used))
+        for i, s in enumerate(shapes):
+            want = oracle.importance_scores_first_order(w[i].numpy(), [b["grads"][i].numpy() for b in used], "obd")
+            got = (w[i] * w[i]) * (views[i] / nb)
+            assert np.abs(got.numpy() - want).max() <= 1e-6 * np.abs(want).max(), (num_samples, i)
+    out[rank] = "ok"
+
+
+def test_importance_scores_data_parallel():
+    _run("_importance_dp")

@@ -135,7 +135,12 @@ def compute_the_sparsity_per_group(total_parameters_to_keep, group_scores, group
 class LayerSparsity:
     def __init__(self, model, data_loader, loss_func, num_samples, original_sparsity, max_sparsity_per_layer=0.8,
                  score_method="obd_avg", num_noise=1, noise_eps=1e-3, layer_to_group_mapping={},
-                 prune_per_model=False, per_model_group=["t5_model", "visual"], per_model_sparsity=[]):
+                 prune_per_model=False, per_model_group=["t5_model", "visual"], per_model_sparsity=[],
+                 data_parallel=False):
+        # data_parallel (new; the reference runs replicas): with torch.distributed initialised and a loader every rank
+        # iterates identically, calibration batches are dealt round-robin to the ranks and the gradient statistics merged
+        # with one all-reduce (vlmc.parallel.importance_accumulate_data_parallel); the select then runs replicated.
+        self.data_parallel = data_parallel
         self.importance_measure = {}
         self.model = model
         self.data_loader = data_loader
@@ -249,19 +254,39 @@ class LayerSparsity:
                 names.append(k)
                 params.append(v)
         device = next(iter(self.model.parameters())).device
-        acc = [torch.zeros(p.shape, dtype=torch.float32, device=p.device) for p in params]
+        # one packed fp32 buffer, the per-parameter accumulators are views of it (one all-reduce when data-parallel)
+        sizes = [p.numel() for p in params]
+        offsets = [0]
+        for n in sizes:
+            offsets.append(offsets[-1] + (n + 3) // 4 * 4)                            # 16-byte aligned views
+        packed = torch.zeros(offsets[-1], dtype=torch.float32, device=params[0].device)
+        acc = [packed[o:o + n].view(p.shape) for o, n, p in zip(offsets, sizes, params)]
         accum_mode = "obd" if self.score_compute == "obd" else "abs"                  # :455-458
-        accum_samples = 0
-        num_batches = 0
-        for d in self.data_loader:
-            if accum_samples >= self.num_samples:
-                break
+
+        def grads_of(d):
             loss, batch_len = self.loss_func(self.model, d, device != "cpu")
-            accum_samples += batch_len
-            num_batches += 1
             grads = torch.autograd.grad(loss, params)
             assert len(grads) == len(names) == len(params)
+            return grads, batch_len
+
+        def accumulate(grads):
             native.importance_accum(acc, [g.data.contiguous() for g in grads], accum_mode)
+
+        import torch.distributed as dist
+        if self.data_parallel and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from vlmc import parallel
+            num_batches = parallel.importance_accumulate_data_parallel(
+                self.data_loader, self.num_samples, grads_of, accumulate, packed, dist.get_rank(), dist.get_world_size())
+        else:
+            accum_samples = 0
+            num_batches = 0
+            for d in self.data_loader:
+                if accum_samples >= self.num_samples:
+                    break
+                grads, batch_len = grads_of(d)
+                accum_samples += batch_len
+                num_batches += 1
+                accumulate(grads)
         if "obd" in self.score_compute:                                               # also taken by "aobd" (:466)
             final_mode = "obd"
         elif "gradient" in self.score_compute:

@@ -235,3 +235,48 @@ def obs_rows_sharded(weight, U, dead, sweep_fn, rank, world, group=None):
     if e > s:
         sweep_fn(weight[s:e], U, dead, R, lambda t: allreduce_sum(t, group))
     return gather_rows(weight, rank, world, group)
+
+
+def importance_accumulate_data_parallel(batches, num_samples, grads_fn, accum_fn, packed_acc, rank, world, group=None):
+    """SURVEY 8f-4 across ranks: the first-order statistic of LayerSparsity.compute_importance_scores
+    (layer_single_base_pruner.py:440-458) is a plain sum over calibration batches, so batches are dealt round-robin
+    (batch i -> rank i % world) from a loader every rank iterates identically, each rank accumulates its own, and ONE SUM
+    all-reduce of the packed accumulator merges them.  The reference's stop rule - no batch is started once
+    accum_samples >= num_samples (:442-443) - is evaluated on the global, in-order sample count: after every round of
+    `world` batches the ranks exchange their batch lengths and a rank drops a batch the sequential loop would not have
+    started.  grads_fn(batch) -> (grads, batch_len); accum_fn(grads) adds into the views of `packed_acc`.
+    Returns the number of batches that count (the divisor of :463)."""
+    accum_samples, num_batches = 0, 0
+    it = iter(batches)
+    done = False
+    while not done:
+        mine, n_round = None, 0
+        for r in range(world):
+            try:
+                d = next(it)
+            except StopIteration:
+                done = True
+                break
+            n_round += 1
+            if r == rank:
+                mine = d
+        if n_round == 0:
+            break
+        if accum_samples >= num_samples:                     # the sequential loop would have stopped before this round
+            break
+        lens = torch.zeros(world, dtype=torch.int64, device=packed_acc.device)
+        grads = None
+        if mine is not None:
+            grads, blen = grads_fn(mine)
+            lens[rank] = int(blen)
+        allreduce_sum(lens, group)
+        for r, blen in enumerate(lens.tolist()[:n_round]):
+            if accum_samples >= num_samples:
+                done = True
+                break
+            accum_samples += blen
+            num_batches += 1
+            if r == rank:
+                accum_fn(grads)
+    allreduce_sum(packed_acc, group)
+    return num_batches
