@@ -256,6 +256,19 @@ def step_wanda(ctx, weights, inputs, method, shared=False):
             ctx.rank, ctx.world))
         ctx.launches += 7 * 3
         return {n: k for n, (k, _) in zip(names, res)}
+    if ctx.world == 1:
+        # phase 2, per-row top-k on one GPU: one launch per linear (the reference's per-linear API), longest first, dealt
+        # over a few streams: a warp owns whole rows (1-5 per launch), so the tail of one launch - warps that got one row
+        # fewer - is filled by the next linear's rows instead of idling.  Masks are allocated on the caller's stream.
+        nsel = 1 if ctx.events is not None else max(1, int(os.environ.get("VLMC_BENCH_SELECT_STREAMS", "3")))
+        keeps = {name: torch.empty((R, C), dtype=torch.bool, device=ctx.dev) for name, R, C, _ in LINEARS}
+        with schedule_fork(ctx, nsel) as fk:
+            for i, (name, R, C, _) in enumerate(sorted(LINEARS, key=lambda l: -l[1] * l[2])):
+                with fk.stream(i):
+                    ctx.timed("wanda_select", R * C * 5, lambda: native.wanda_rowselect(
+                        weights[name], scalers[name], int(C * 0.5), keep_mask=keeps[name]))
+                ctx.launches += 2
+        return keeps
     for name, R, C, _ in LINEARS:                         # phase 2: score + select + apply on this rank's rows
         def sel(Wr, s, keep, C=C):
             return native.wanda_rowselect(Wr, s, int(C * 0.5), keep_mask=keep)[1]

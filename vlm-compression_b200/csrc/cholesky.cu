@@ -13,6 +13,7 @@
 // cuSOLVER/cuBLAS path.  A non-positive or NaN pivot
 // sets *status = VLMC_NOT_POSDEF; the caller adds percdamp * mean(diag H) and retries (reference :114-128).
 #include <stdlib.h>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -227,7 +228,11 @@ __global__ void add_diag_kernel(float* H, int64_t ldh, int C, const float* damp)
 // different streams must not share a side stream (their trailing updates would queue behind each other).
 struct ChainSide { cudaStream_t stream; cudaEvent_t solved, updated; };
 
+static std::atomic<int> g_chol_lookahead{-1};             // -1: follow VLMC_CHOL_LOOKAHEAD (default on); 0 / 1: set by the host
+
 static bool chol_lookahead_enabled() {
+  const int m = g_chol_lookahead.load();
+  if (m >= 0) return m != 0;
   const char* e = getenv("VLMC_CHOL_LOOKAHEAD");          // read per call: tests flip it inside one process
   return !(e && e[0] == '0');
 }
@@ -271,6 +276,12 @@ extern "C" int vlmc_hessian_add_damp(float* H, int C, int64_t ldh, const float* 
   if (!is_device_ptr(H) || !is_device_ptr(damp)) return VLMC_ERR_NOT_DEVICE;
   add_diag_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(H, ldh, C, damp);
   return check_launch();
+}
+
+extern "C" int vlmc_chol_set_lookahead(int mode) {
+  if (mode < -1 || mode > 1) return VLMC_ERR_BAD_ARG;
+  const int prev = vlmc::g_chol_lookahead.exchange(mode);
+  return prev < 0 ? 2 : prev;
 }
 
 extern "C" int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U, int64_t ldu, int* status,

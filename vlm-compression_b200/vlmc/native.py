@@ -63,6 +63,7 @@ SIGNATURES = {
     "vlmc_hessian_prepare": (_i, [_vp, _i, _i64, _f, _vp, _vp, _vp]),
     "vlmc_hessian_add_damp": (_i, [_vp, _i, _i64, _vp, _vp]),
     "vlmc_chol_inv_upper": (_i, [_vp, _i, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "vlmc_chol_set_lookahead": (_i, [_i]),
     "vlmc_gemm_tf32x3": (_i, [_i, _i, _i, _i, _f, _vp, _i64, _vp, _i64, _f, _vp, _i64, _i, _i, _vp]),
     "vlmc_obs_sweep": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp, _d, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_obs_sweep_guarded": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp, _d, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _sz,
@@ -587,6 +588,23 @@ def hessian_add_damp(H, damp):
     with torch.cuda.device(H.device):
         st = lib.vlmc_hessian_add_damp(H.data_ptr(), H.shape[0], H.stride(0), damp.data_ptr(), _stream(H))
     _check("vlmc_hessian_add_damp", st)
+
+
+class chol_lookahead:
+    """with chol_lookahead(False): ...  Host-side schedule switch of vlmc_chol_inv_upper (include/vlmc.h): callers that
+    enqueue several factorisation chains concurrently turn the look-ahead off for the duration."""
+
+    def __init__(self, on):
+        self.mode = 1 if on else 0
+
+    def __enter__(self):
+        prev = load().vlmc_chol_set_lookahead(self.mode)
+        self.prev = -1 if prev == 2 else prev
+        return self
+
+    def __exit__(self, *exc):
+        load().vlmc_chol_set_lookahead(self.prev)
+        return False
 
 
 def chol_inv_upper(H, U=None, status=None):

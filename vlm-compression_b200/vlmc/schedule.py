@@ -73,7 +73,8 @@ def factor_concurrent(Hs, percdamp=0.01, Us=None, max_retries=64):
     status = torch.empty(n, dtype=torch.int32, device=dev)
     deads = [torch.empty(H.shape[0], dtype=torch.uint8, device=dev) for H in Hs]
     order = sorted(range(n), key=lambda i: -Hs[i].shape[0])      # longest chain first
-    with Fork(dev, n) as f:
+    # several chains at once: the Cholesky look-ahead's side streams only add contention (measured), one chain keeps it
+    with Fork(dev, n) as f, native.chol_lookahead(n == 1):
         for slot, i in enumerate(order):
             with f.stream(slot):
                 native.hessian_prepare(Hs[i], percdamp, damps[i:i + 1], deads[i])
@@ -131,7 +132,7 @@ def sparsegpt_block(items, percdamp=0.01, blocksize=128, Us=None, max_retries=64
     deads = [torch.empty(H.shape[0], dtype=torch.uint8, device=dev) for H in distinct]
     scores = torch.empty(n, dtype=torch.float32, device=dev)
     order = sorted(range(nH), key=lambda h: -distinct[h].shape[0])      # longest chain first
-    with Fork(dev, nH + n) as f:
+    with Fork(dev, nH + n) as f, native.chol_lookahead(nH == 1):       # see factor_concurrent
         for slot, h in enumerate(order):
             with f.stream(slot):
                 native.hessian_prepare(distinct[h], percdamp, damps[h:h + 1], deads[h])
