@@ -298,25 +298,34 @@ def step_dsnot(ctx, weights, inputs, elide=False):
         n_local = next(iter(inputs.values())).shape[0]
         parallel.merge_running_means([t for st in stats.values() for t in st], n_local, n_total=N_SEQ)
     masks = {}
-    for name, R, C, _ in LINEARS:
-        W = weights[name]
-        s, e = parallel.row_range(R, ctx.rank, ctx.world)
-        keep = torch.empty((R, C), dtype=torch.bool, device=ctx.dev)
-        st = stats[name]
-        if elide:      # shipped semantics: the swaps are written back, the mask is the initial selection
-            ctx.timed("wanda_select", (e - s) * C * 5, lambda: native.wanda_rowselect(
-                W[s:e], st[0], round(C * 0.6), keep_mask=keep[s:e]))
-        else:
-            ctx.timed("dsnot_refine", (e - s) * C * 7, lambda: native.dsnot_refine(
-                W[s:e], st[0], st[1], st[3], round(C * 0.6), keep_mask=keep[s:e],
-                reduce_ncycles=parallel.allreduce_max if ctx.world > 1 else None))
-        ctx.launches += 2
-        if ctx.world > 1:      # masks travel as bits; the replicated weights are zeroed locally
-            parallel.exchange_rows_packed(
-                W, keep, native.mask_pack,
-                lambda Wf, bits, kp, rps, stride: native.mask_apply_packed(Wf, bits, kp, True, rps, stride),
-                ctx.rank, ctx.world)
-        masks[name] = keep
+    # one GPU: the per-linear launches are dealt over a few streams, longest first (see step_wanda); several GPUs: one
+    # after the other, each followed by its mask exchange
+    nref = 1
+    if ctx.world == 1 and ctx.events is None:
+        nref = max(1, int(os.environ.get("VLMC_BENCH_SELECT_STREAMS" if elide else "VLMC_BENCH_REFINE_STREAMS", "3")))
+    order = sorted(LINEARS, key=lambda l: -l[1] * l[2]) if nref > 1 else LINEARS
+    keeps = {name: torch.empty((R, C), dtype=torch.bool, device=ctx.dev) for name, R, C, _ in LINEARS}
+    with schedule_fork(ctx, nref) as fk:
+        for li, (name, R, C, _) in enumerate(order):
+            W = weights[name]
+            s, e = parallel.row_range(R, ctx.rank, ctx.world)
+            keep = keeps[name]
+            st = stats[name]
+            with fk.stream(li):
+                if elide:      # shipped semantics: the swaps are written back, the mask is the initial selection
+                    ctx.timed("wanda_select", (e - s) * C * 5, lambda: native.wanda_rowselect(
+                        W[s:e], st[0], round(C * 0.6), keep_mask=keep[s:e]))
+                else:
+                    ctx.timed("dsnot_refine", (e - s) * C * 7, lambda: native.dsnot_refine(
+                        W[s:e], st[0], st[1], st[3], round(C * 0.6), keep_mask=keep[s:e],
+                        reduce_ncycles=parallel.allreduce_max if ctx.world > 1 else None))
+            ctx.launches += 2
+            if ctx.world > 1:      # masks travel as bits; the replicated weights are zeroed locally
+                parallel.exchange_rows_packed(
+                    W, keep, native.mask_pack,
+                    lambda Wf, bits, kp, rps, stride: native.mask_apply_packed(Wf, bits, kp, True, rps, stride),
+                    ctx.rank, ctx.world)
+            masks[name] = keep
     return masks
 
 

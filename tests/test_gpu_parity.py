@@ -449,6 +449,26 @@ def test_composite_wanda_pruner_on_toy_model(native):
     assert min(agree[:2]) > 0.999 and min(agree[:4]) > 0.95   # first ViT block: same fp32 inputs up to fp16 autocast rounding
 
 
+def test_block_rowselect_over_streams_equals_per_linear(native):
+    """wanda_prune_block_rows (one launch per linear, longest first, dealt over three streams) gives the masks, weights and
+    importance scores of wanda_prune_linear called linear by linear; twice in a row (stream-keyed scratch is reused)."""
+    from vlmc.compression.pruners.wanda_pruner import wanda_prune_block_rows, wanda_prune_linear
+    shapes = [(96, 512), (256, 1024), (64, 2048), (160, 512), (32, 4096)]
+    for rep in range(2):
+        mods_a = [torch.nn.Linear(C, R, bias=False).cuda().half() for R, C in shapes]
+        mods_b = [torch.nn.Linear(C, R, bias=False).cuda().half() for R, C in shapes]
+        for a, b in zip(mods_a, mods_b):
+            b.weight.data.copy_(a.weight.data)
+        scal = [scaler(C, 7 + i + rep).cuda() for i, (_, C) in enumerate(shapes)]
+        sp = [0.5, 0.6, 0.25, 0.5, 0.7]
+        want = [wanda_prune_linear(m, s, p) for m, s, p in zip(mods_a, scal, sp)]
+        got = wanda_prune_block_rows(mods_b, scal, sp)
+        torch.cuda.synchronize()
+        for a, b, wa, gb in zip(mods_a, mods_b, want, got):
+            assert torch.equal(a.mask, b.mask) and torch.equal(a.weight.data, b.weight.data)
+            assert float(wa) == float(gb)
+
+
 # ------------------------------------------------------------------------------------------- K3
 def _rel_fro(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)

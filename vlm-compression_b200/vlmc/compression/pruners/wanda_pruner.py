@@ -60,6 +60,33 @@ def wanda_prune_block_nm(modules, scaler_rows, prune_n, prune_m, lora_model=Fals
     return out
 
 
+def wanda_prune_block_rows(modules, scaler_rows, sparsities, lora_model=False, streams=3):
+    """Per-row top-k (wanda_pruner.py:332-341) for the linears of one block: the same one launch per linear as
+    wanda_prune_linear, but longest first and dealt over `streams` side streams - a warp of vlmc_wanda_rowselect owns whole
+    rows, so the tail of one launch (warps that got one row fewer) is filled by the next linear's rows instead of idling
+    (3.37 -> 3.16 ms per Vicuna block).  Masks are allocated on the caller's stream.  Identical masks, weights and scores.
+    Sets module.mask; returns the importance scores as a list of 1-element device tensors (one per module)."""
+    from vlmc.schedule import Fork
+    out = [None] * len(modules)
+    keeps = [torch.empty(m.weight.shape, dtype=torch.bool, device=m.weight.device) for m in modules]
+    means = [torch.empty(1, dtype=torch.float32, device=m.weight.device) for m in modules]
+    order = sorted(range(len(modules)), key=lambda i: -modules[i].weight.numel())
+    by_dev = {}
+    for i in order:
+        by_dev.setdefault(modules[i].weight.device, []).append(i)
+    for dev, idx in by_dev.items():
+        with Fork(dev, max(1, min(streams, len(idx)))) as fk:
+            for slot, i in enumerate(idx):
+                W = modules[i].weight.data
+                with fk.stream(slot):
+                    native.wanda_rowselect(W, scaler_rows[i], int(W.shape[1] * sparsities[i]), zero_w=not lora_model,
+                                           keep_mask=keeps[i], score_mean=means[i])
+    for i, mod in enumerate(modules):
+        setattr(mod, "mask", keeps[i])
+        out[i] = means[i]
+    return out
+
+
 def wanda_prune_linear(module, scaler_row, sparsity, prune_n=0, prune_m=0, lora_model=False, whole_matrix=False):
     """Score + select + apply for one linear (wanda_pruner.py:316-341 / :664-687).
 
@@ -110,6 +137,7 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
         self.vit_model_prefix = vit_model_prefix
         self._pending_scores = []
         self._pending_nm = []
+        self._pending_rows = []
         # linears fed by the same tensor accumulate their statistics once (layerwise.InputSharing); False restores
         # the reference's one-accumulation-per-linear schedule.  The results are identical either way.
         self.share_inputs = share_inputs
@@ -134,6 +162,9 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
             if self.prune_n != 0:                   # n:m: the whole block in one launch (finish_block)
                 self._pending_nm.append((module, wrapper.scaler_row, lora_model))
                 return
+            if not vit:                             # per-row top-k: the block's launches dealt over streams (finish_block)
+                self._pending_rows.append((module, wrapper.scaler_row, sparsity, lora_model))
+                return
             mean = wanda_prune_linear(module, wrapper.scaler_row, sparsity, self.prune_n, self.prune_m,
                                       lora_model=lora_model, whole_matrix=vit)
             self._pending_scores.append((module, mean))
@@ -146,6 +177,12 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
                                          lora_model=self._pending_nm[0][2])
             self._pending_scores.extend(zip(mods, means))
             self._pending_nm = []
+        if self._pending_rows:
+            mods = [m for m, *_ in self._pending_rows]
+            means = wanda_prune_block_rows(mods, [s for _, s, _, _ in self._pending_rows],
+                                           [p for _, _, p, _ in self._pending_rows], lora_model=self._pending_rows[0][3])
+            self._pending_scores.extend(zip(mods, means))
+            self._pending_rows = []
         # one host sync per block instead of the reference's full-matrix .cpu() per linear (:320)
         if self._pending_scores:
             vals = torch.cat([m for _, m in self._pending_scores]).tolist()

@@ -204,9 +204,14 @@ def _select_common(W, scaler_row, keep_mask):
     return lib, R, C, keep_mask, ws, score_mean
 
 
-def wanda_rowselect(W, scaler_row, k, zero_w=True, keep_mask=None):
-    """K4+K5 (wanda_pruner.py:318-341).  Returns (keep_mask bool [R,C], score_mean 1-elem tensor)."""
-    lib, R, C, keep_mask, ws, score_mean = _select_common(W, scaler_row, keep_mask)
+def wanda_rowselect(W, scaler_row, k, zero_w=True, keep_mask=None, score_mean=None):
+    """K4+K5 (wanda_pruner.py:318-341).  Returns (keep_mask bool [R,C], score_mean 1-elem tensor).  keep_mask / score_mean
+    may be passed in (callers that launch on a side stream allocate them on the caller's stream)."""
+    lib, R, C, keep_mask, ws, own_mean = _select_common(W, scaler_row, keep_mask)
+    if score_mean is None:
+        score_mean = own_mean
+    elif not score_mean.is_cuda or score_mean.dtype != torch.float32 or score_mean.numel() != 1:
+        raise ValueError("score_mean must be a 1-element float32 CUDA tensor")
     with torch.cuda.device(W.device):
         st = lib.vlmc_wanda_rowselect(W.data_ptr(), _dtype(W), R, C, W.stride(0), scaler_row.data_ptr(), int(k),
                                       int(bool(zero_w)), keep_mask.data_ptr(), keep_mask.stride(0),
