@@ -357,6 +357,36 @@ def test_threshold_ties_are_kept(native):
         assert np.array_equal(keep.cpu().numpy(), keep_o)
 
 
+def test_threshold_radix_and_counting_forms_agree(native, monkeypatch):
+    """The radix form of K7 (default) and the counting form (VLMC_THRESHOLD_COUNTING=1) pick the same threshold: dead
+    channels (zero scores), infinite and NaN weights (NaN sorts last, like torch.sort), extreme ranks, repeated calls on one
+    workspace."""
+    g = torch.Generator().manual_seed(12)
+    W = (torch.randn(320, 1024, generator=g) * 0.02).half()
+    W[5, 7] = float("inf")
+    W[9, 100] = float("nan")
+    W[:, 64:96] = 0
+    s = scaler(1024, 3)
+    s[200:240] = 0.0
+    n = W.numel()
+    for kg in (0, 1, n // 3, n // 2, n - 3, n - 1):
+        out = {}
+        for form in ("0", "1", "0"):
+            monkeypatch.setenv("VLMC_THRESHOLD_COUNTING", form)
+            Wc = W.clone().cuda()
+            keep, mean = native.wanda_threshold(Wc, s.cuda(), kg)
+            torch.cuda.synchronize()
+            if form in out:
+                assert torch.equal(out[form][0], keep)
+            out[form] = (keep, Wc)
+        assert torch.equal(out["0"][0], out["1"][0]), kg
+        assert torch.equal(out["0"][1].view(torch.int16), out["1"][1].view(torch.int16)), kg
+        sc = W.float().abs() * s.sqrt()
+        thr = torch.sort(sc.flatten())[0][kg]                      # wanda_pruner.py:682-683
+        want = ~(sc < thr)                                         # a NaN threshold (kg = n - 1) prunes nothing
+        assert torch.equal(out["0"][0].cpu(), want), (kg, float(thr), int((out["0"][0].cpu() != want).sum()))
+
+
 def test_threshold_golden_toy(native):
     g = gu.load("wanda_toy_unstructured.npz")
     seen = 0

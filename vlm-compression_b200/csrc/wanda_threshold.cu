@@ -8,6 +8,7 @@
 // afterwards); W (<= 17 MB) stays L2-resident between passes.  The last CTA of a pass folds the counts
 // into the bracket kept in the workspace, so there is no host synchronisation between launches and
 // passes after convergence exit at once (typically 2 passes do work).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace vlmc {
@@ -271,10 +272,11 @@ thr_resolve_kernel(int R, int C, ull k, ThrState* st) {
 template <typename T>
 __global__ void __launch_bounds__(kThrThreads)
 thr_apply_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ sq,
-                 const ThrState* st, int zero_w, uint8_t* __restrict__ mask, int64_t ldm,
+                 const uint32_t* __restrict__ vptr, int zero_w, uint8_t* __restrict__ mask, int64_t ldm,
                  float* __restrict__ part_sum) {
   constexpr int V = Elem<T>::kVec;
-  const uint32_t v = st->v;
+  // a NaN threshold (the rank falls among NaN scores, which sort last) prunes nothing: `W_metric < nan` is all False (:683)
+  const uint32_t v = *vptr > 0x7f800000u ? 0u : *vptr;
   const int cvecs = C / V;
   const int64_t nvec = (int64_t)R * cvecs;
   float lsum = 0.f;
@@ -320,9 +322,125 @@ thr_apply_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* __re
   }
 }
 
+// ---- radix form of the select (default): scores are non-negative floats, so their bit patterns ARE the sort keys
+// (31 bits; NaN above inf like torch.sort).  Three histogram passes (11 / 11 / 9 key bits, shared-memory histogram per CTA
+// flushed into the workspace) find the k-th smallest key exactly; the LAST CTA of a pass (ticket) picks the bin that holds
+// the rank, narrows the prefix and clears the histogram, so a call is init + 3 passes + apply + mean: 6 stream-ordered
+// launches instead of the ~19 of the counting form above (kept behind VLMC_THRESHOLD_COUNTING=1 for A/B runs).
+constexpr int kRdxBins = 2048;
+struct RadixState {
+  ull k_rem;
+  uint32_t prefix;
+  unsigned int ticket;
+  uint32_t v;
+  uint32_t pad;
+  ull hist[kRdxBins];
+};
+
+__global__ void __launch_bounds__(256)
+thr_radix_init_kernel(const float* __restrict__ s, float* __restrict__ sq, int C, RadixState* st, ull k) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) sq[i] = __fsqrt_rn(s[i]);
+  if (i < kRdxBins) st->hist[i] = 0ull;
+  if (i == 0) { st->k_rem = k; st->prefix = 0u; st->ticket = 0u; st->v = 0u; st->pad = 0u; }
+}
+
+template <int PASS>
+__device__ __forceinline__ bool rdx_bin(uint32_t key, uint32_t prefix, uint32_t& bin) {
+  if (PASS == 0) { bin = key >> 20; return true; }                              // keys < 2^31: 11 bits
+  if (PASS == 1) { bin = (key >> 9) & 0x7ffu; return (key >> 20) == prefix; }
+  bin = key & 0x1ffu;
+  return (key >> 9) == prefix;
+}
+
+template <typename T, int PASS>
+__global__ void __launch_bounds__(kThrThreads)
+thr_radix_kernel(const T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ sq, RadixState* st) {
+  constexpr int V = Elem<T>::kVec;
+  constexpr int kPer = kRdxBins / kThrThreads;          // 8 consecutive bins per thread in the resolve step
+  __shared__ uint32_t h[kRdxBins];
+  __shared__ ull part[kThrThreads];
+  __shared__ unsigned int s_last;
+  __shared__ int s_owner;
+  __shared__ ull s_before;
+  for (int i = threadIdx.x; i < kRdxBins; i += kThrThreads) h[i] = 0u;
+  const uint32_t prefix = PASS > 0 ? st->prefix : 0u;
+  __syncthreads();
+  const int cvecs = C / V;
+  const int64_t nvec = (int64_t)R * cvecs;
+  for (int64_t vec = (int64_t)blockIdx.x * kThrThreads + threadIdx.x; vec < nvec;
+       vec += (int64_t)gridDim.x * kThrThreads) {
+    uint32_t keys[V];
+    load_keys<T>(W, ldw, cvecs, vec, sq, keys, nullptr);
+    uint32_t bin;
+#pragma unroll
+    for (int e = 0; e < V; ++e)
+      if (rdx_bin<PASS>(keys[e], prefix, bin)) atomicAdd(&h[bin], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kRdxBins; i += kThrThreads) {
+    const uint32_t c = h[i];
+    if (c) atomicAdd(&st->hist[i], (ull)c);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&st->ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  // last CTA of the pass: the bin that holds rank k_rem
+  __threadfence();
+  ull c[kPer];
+  ull mine = 0;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    c[j] = *reinterpret_cast<volatile ull*>(&st->hist[threadIdx.x * kPer + j]);
+    mine += c[j];
+  }
+  part[threadIdx.x] = mine;
+  __syncthreads();
+  const ull k = st->k_rem;
+  if (threadIdx.x == 0) {
+    ull acc = 0;
+    int o = -1;
+    for (int t = 0; t < kThrThreads; ++t) {
+      if (acc + part[t] >= k) { o = t; break; }
+      acc += part[t];
+    }
+    s_owner = o;            // -1 cannot happen: k <= R * C = total count (checked by the caller)
+    s_before = acc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) st->hist[threadIdx.x * kPer + j] = 0ull;
+  if ((int)threadIdx.x == s_owner) {
+    ull acc = s_before;
+    int bin = -1;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      if (bin < 0) {
+        if (acc + c[j] >= k) bin = j;
+        else acc += c[j];
+      }
+    }
+    if (bin < 0) bin = kPer - 1;                        // unreachable: the owner's chunk holds the rank
+    const uint32_t b = (uint32_t)(threadIdx.x * kPer + bin);
+    const uint32_t np = PASS == 0 ? b : PASS == 1 ? ((prefix << 11) | b) : ((prefix << 9) | b);
+    st->prefix = np;
+    st->k_rem = k - acc;
+    if (PASS == 2) st->v = np;
+  }
+  if (threadIdx.x == 0) st->ticket = 0u;
+}
+
+static bool thr_use_counting() {
+  const char* e = getenv("VLMC_THRESHOLD_COUNTING");
+  return e && e[0] == '1';
+}
+
 size_t threshold_workspace_bytes(int R, int C) {
   return VLMC_WS_COUNTER_BYTES + align_up((size_t)C * sizeof(float), 256) +
-         align_up((size_t)kNumSMs * 8 * sizeof(float), 256) + align_up(sizeof(ThrState), 256);
+         align_up((size_t)kNumSMs * 8 * sizeof(float), 256) + align_up(sizeof(ThrState), 256) +
+         align_up(sizeof(RadixState), 256);
 }
 
 }  // namespace vlmc
@@ -350,21 +468,36 @@ extern "C" int vlmc_wanda_threshold(void* W, int dtype, int R, int C, int64_t ld
   cudaStream_t s = (cudaStream_t)stream;
   const ull k = (ull)k_global + 1;  // 1-indexed rank of the threshold value
 
-  thr_init_kernel<<<1, 32, 0, s>>>(st, (ull)R * (ull)C);
-  sqrt_kernel<<<(C + 255) / 256, 256, 0, s>>>(scaler_row, sq, C);
-  VLMC_DISPATCH_DTYPE(dtype, (thr_seed_kernel<scalar_t><<<1, 32, 0, s>>>(reinterpret_cast<const scalar_t*>(W), ldw, R, C, sq, k, st)));
+  RadixState* rst = reinterpret_cast<RadixState*>(base + align_up(sizeof(ThrState), 256));
   const int64_t nvec = (int64_t)R * (C / V);
   int grid = kNumSMs * 8;
   if ((int64_t)grid * kThrThreads > nvec) grid = (int)((nvec + kThrThreads - 1) / kThrThreads);
-  for (int pass = 0; pass < kThrPasses; ++pass) {
-    VLMC_DISPATCH_DTYPE(dtype, (thr_count_kernel<scalar_t><<<grid, kThrThreads, 0, s>>>(
-                                   reinterpret_cast<const scalar_t*>(W), ldw, R, C, sq, k, st, pass)));
+  const uint32_t* vptr;
+  if (!thr_use_counting()) {
+    const int n_init = C > kRdxBins ? C : kRdxBins;
+    thr_radix_init_kernel<<<(n_init + 255) / 256, 256, 0, s>>>(scaler_row, sq, C, rst, k);
+    VLMC_DISPATCH_DTYPE(dtype, (thr_radix_kernel<scalar_t, 0><<<grid, kThrThreads, 0, s>>>(
+                                   reinterpret_cast<const scalar_t*>(W), ldw, R, C, sq, rst)));
+    VLMC_DISPATCH_DTYPE(dtype, (thr_radix_kernel<scalar_t, 1><<<grid, kThrThreads, 0, s>>>(
+                                   reinterpret_cast<const scalar_t*>(W), ldw, R, C, sq, rst)));
+    VLMC_DISPATCH_DTYPE(dtype, (thr_radix_kernel<scalar_t, 2><<<grid, kThrThreads, 0, s>>>(
+                                   reinterpret_cast<const scalar_t*>(W), ldw, R, C, sq, rst)));
+    vptr = &rst->v;
+  } else {
+    thr_init_kernel<<<1, 32, 0, s>>>(st, (ull)R * (ull)C);
+    sqrt_kernel<<<(C + 255) / 256, 256, 0, s>>>(scaler_row, sq, C);
+    VLMC_DISPATCH_DTYPE(dtype, (thr_seed_kernel<scalar_t><<<1, 32, 0, s>>>(reinterpret_cast<const scalar_t*>(W), ldw, R, C, sq, k, st)));
+    for (int pass = 0; pass < kThrPasses; ++pass) {
+      VLMC_DISPATCH_DTYPE(dtype, (thr_count_kernel<scalar_t><<<grid, kThrThreads, 0, s>>>(
+                                     reinterpret_cast<const scalar_t*>(W), ldw, R, C, sq, k, st, pass)));
+    }
+    VLMC_DISPATCH_DTYPE(dtype, (thr_gather_kernel<scalar_t><<<grid, kThrThreads, 0, s>>>(
+                                   reinterpret_cast<const scalar_t*>(W), ldw, R, C, sq, k, st)));
+    thr_resolve_kernel<<<1, 1024, 0, s>>>(R, C, k, st);
+    vptr = &st->v;
   }
-  VLMC_DISPATCH_DTYPE(dtype, (thr_gather_kernel<scalar_t><<<grid, kThrThreads, 0, s>>>(
-                                 reinterpret_cast<const scalar_t*>(W), ldw, R, C, sq, k, st)));
-  thr_resolve_kernel<<<1, 1024, 0, s>>>(R, C, k, st);
   VLMC_DISPATCH_DTYPE(dtype, (thr_apply_kernel<scalar_t><<<grid, kThrThreads, 0, s>>>(
-                                 reinterpret_cast<scalar_t*>(W), ldw, R, C, sq, st, zero_w, keep_mask, ldm, part)));
+                                 reinterpret_cast<scalar_t*>(W), ldw, R, C, sq, vptr, zero_w, keep_mask, ldm, part)));
   int rc = check_launch();
   if (rc) return rc;
   if (score_mean) return launch_mean_finalize(part, grid, (double)R * (double)C, score_mean, s);
