@@ -1019,10 +1019,54 @@ def cpu_block_seconds(method, threads, budget="small"):
                               f"{Rs}x{Cs} linear ({t_fp:.2f} s) scaled by C^3 + R*C^2 to the 7 linears (extrapolated)")
 
 
+def same_gpu_torch_eager(method):
+    """the reference is torch code that its users run on the GPU that holds the model.  Its op sequence
+    (oracle/cpu_port.py: per-sequence add_batch with the fp32 cast and the strided norm, the Python loop of C/m topk calls
+    or the stable row sort) with every tensor on this B200, torch eager, whole block, timed with CUDA events.  A reported
+    baseline like the CPU figure; only for the Wanda methods; never raises (the bench line must not depend on it)."""
+    try:
+        import torch
+        from oracle import cpu_port
+        if method not in ("wanda_nm", "wanda_unstructured") or not torch.cuda.is_available():
+            return None
+        dev = torch.device("cuda", torch.cuda.current_device())
+        g = torch.Generator(device=dev).manual_seed(5)
+        xs = {inp: torch.randn(8, SEQ_LEN, C, device=dev, generator=g).half() for inp, C in INPUT_DIMS.items()}
+        Ws = {name: (torch.randn(R, C, device=dev, generator=g) * 0.02).half() for name, R, C, _ in LINEARS}
+
+        def block(n_seq):
+            for name, R, C, inp in LINEARS:
+                st = cpu_port.WandaStat(C, device=dev)
+                for j in range(n_seq):
+                    st.add_batch(xs[inp][j % 8].unsqueeze(0))
+                if method == "wanda_nm":
+                    cpu_port.wanda_select(Ws[name], st.scaler_row, 0.5, 2, 4)
+                else:
+                    cpu_port.wanda_select(Ws[name], st.scaler_row, 0.5)
+        block(1)                                           # warm-up: allocator, kernel load
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        block(N_SEQ)
+        b.record()
+        torch.cuda.synchronize()
+        del xs, Ws
+        torch.cuda.empty_cache()
+        return {"value": a.elapsed_time(b) / 1e3, "unit": UNIT, "kind": "port",
+                "sample": f"whole block: {N_SEQ} per-sequence add_batch calls per linear (8 distinct resident sequences reused) + "
+                          "selection of the 7 linears, torch eager on the same B200"}
+    except Exception as e:                                 # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:200]}
+
+
 def cpu_baseline(method):
     threads = os.cpu_count() or 1
     total, sample = cpu_block_seconds(method, threads)
-    return {"value": total, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    out = {"value": total, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    same_gpu = same_gpu_torch_eager(method)
+    if same_gpu is not None:
+        out["same_gpu_torch_eager"] = same_gpu
+    return out
 
 
 def run_reference(args):

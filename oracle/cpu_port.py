@@ -2,7 +2,8 @@
 
 The reference IS torch code run on whatever device holds the model; on the GPU box's host cores this port is
 what `bench.py --impl reference` and the `cpu_baseline` leg time (kind = "port": /root/reference does not
-travel to the GPU box and `lavis` is not importable as a package).  It follows the reference's own op sequence
+travel to the GPU box and `lavis` is not importable as a package).  The same leg also runs the Wanda part once with its
+tensors on the GPU (`cpu_baseline.same_gpu_torch_eager`, SURVEY 8d: the reference as its users run it).  It follows the reference's own op sequence
 (cast, strided norm, stable sort / per-group topk loop, scatter, index_put) so the timing is the reference's
 algorithm, not a tuned rewrite.  Pinned against the golden fixtures in tests/test_oracle_vs_golden.py.
 Never imported by vlmc/.
@@ -13,8 +14,8 @@ import torch
 class WandaStat:
     """wanda_pruner.py:56-81."""
 
-    def __init__(self, columns):
-        self.scaler_row = torch.zeros(columns)
+    def __init__(self, columns, device=None):
+        self.scaler_row = torch.zeros(columns, device=device)    # device: only bench.py's "same GPU, torch eager" figure
         self.nsamples = 0
 
     def add_batch(self, inp):
