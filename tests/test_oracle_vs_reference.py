@@ -172,3 +172,75 @@ def test_importance_scores_live(ref, method, mode):
         assert np.array_equal(got, want[k].numpy()), k
         if mode == "obd":
             assert np.array_equal(oracle.importance_scores_first_order(w, grads, "obd"), got)
+
+
+# ---- the main path on fresh seeds (the committed fixtures hold one seed each) ------------------------------------------
+def _act(shape, seed, dtype):
+    g = torch.Generator().manual_seed(seed)
+    C = shape[-1]
+    gain = torch.exp(torch.rand(C, generator=g) * 2.77 - 1.386)
+    off = torch.randn(C, generator=g) * 0.3
+    return (torch.randn(shape, generator=g) * gain + off).to(dtype)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("seed", [101, 202, 303])
+def test_statistics_live(ref, seed):
+    """Wanda / DSnoT WrappedGPT.add_batch and SparseGPT.add_batch of the reference vs the oracle, mixed call shapes."""
+    rng = np.random.default_rng(seed)
+    C = int(rng.choice([48, 96, 160]))
+    dtype = [torch.float16, torch.bfloat16, torch.float32][seed % 3]
+    lin = torch.nn.Linear(C, 8, bias=False)
+    w, d, sg = ref.wanda.WrappedGPT(lin), ref.dsnot.WrappedGPT(lin), ref.sparsegpt.SparseGPT(lin)
+    s, n = np.zeros(C, np.float32), 0
+    st = dict(scaler_row=np.zeros(C, np.float32), sum_metric_row=np.zeros(C, np.float32), mean=np.zeros(C, np.float32),
+              var=np.zeros(C, np.float32), nsamples=0, ntokens=0)
+    H, nh = np.zeros((C, C), np.float32), 0
+    for call in range(4):
+        shape = [(1, int(rng.integers(8, 70)), C), (int(rng.integers(8, 70)), C), (int(rng.integers(2, 5)), 19, C)][call % 3]
+        x = _act(shape, seed * 10 + call, dtype)
+        for wrapper in (w, d, sg):
+            wrapper.add_batch(x.clone(), None)
+        b = 1 if x.dim() == 2 else x.shape[0]
+        x2 = x.float().numpy().reshape(-1, C)
+        s, n = oracle.wanda_add_batch(s, n, x2, b)
+        st = oracle.dsnot_add_batch(st, x2, b)
+        H, nh = oracle.sparsegpt_add_batch(H, nh, x2, b)
+        assert n == w.nsamples and st["nsamples"] == d.nsamples and st["ntokens"] == d.ntokens and nh == sg.nsamples
+    assert _rel(s, w.scaler_row.numpy()) < 1e-5
+    for k in ("scaler_row", "sum_metric_row"):
+        assert _rel(st[k], getattr(d, k).numpy()) < 1e-5, k
+    for k in ("mean", "var"):
+        assert _rel(st[k], getattr(d, k).numpy().reshape(-1)) < 1e-5, k
+    assert _rel(H, sg.H.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("seed,sparsity,n,m", [(11, 0.5, 0, 0), (12, 0.7, 0, 0), (13, 0.0, 2, 4), (14, 0.0, 4, 8)])
+def test_fasterprune_live(ref, seed, sparsity, n, m):
+    """SparseGPT.fasterprune of the reference vs the oracle on a fresh linear: north_star bars."""
+    g = torch.Generator().manual_seed(seed)
+    R, C = 24, 256
+    lin = torch.nn.Linear(C, R, bias=False)
+    lin.weight.data = (torch.randn(R, C, generator=g) * 0.05).to(torch.bfloat16)
+    W0 = lin.weight.data.float().numpy().copy()
+    sg = ref.sparsegpt.SparseGPT(lin)
+    for i in range(3):
+        sg.add_batch(_act((1, 400, C), seed * 7 + i, torch.bfloat16), None)
+    H = sg.H.numpy().copy()
+    _quiet(sg.fasterprune, sparsity, prune_n=n, prune_m=m, percdamp=0.01, blocksize=128)
+    want = lin.weight.data.float().numpy()
+    got, _, _ = oracle.sparsegpt_fasterprune(W0, "bf16", H, sparsity, n, m)
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-3
+    assert ((got == 0) == (want == 0)).mean() >= 0.999
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_reorder_indice_live(ref, seed):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randn(12, 29, generator=g)
+    t[t.abs() < 0.3] = 0.0
+    assert np.array_equal(oracle.return_reorder_indice(t.numpy()), ref.dsnot.return_reorder_indice(t.clone()).numpy())
