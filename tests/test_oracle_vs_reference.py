@@ -244,3 +244,73 @@ def test_reorder_indice_live(ref, seed):
     t = torch.randn(12, 29, generator=g)
     t[t.abs() < 0.3] = 0.0
     assert np.array_equal(oracle.return_reorder_indice(t.numpy()), ref.dsnot.return_reorder_indice(t.clone()).numpy())
+
+
+# ---- the reference's composite pruners on the toy model with OTHER seeds than the fixtures' ---------------------------
+def _make_golden():
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py")
+    spec = importlib.util.spec_from_file_location("vlmc_make_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class _Npz(dict):
+    """collect_layers() returns a plain dict; golden_util.layer reads an npz (it needs .files)."""
+
+    @property
+    def files(self):
+        return list(self.keys())
+
+
+def _layers(collected):
+    import golden_util as gu
+    collected = _Npz(collected)
+    for key in collected["layers"]:
+        yield str(key), gu.layer(collected, str(key))
+
+
+@pytest.mark.parametrize("seed,n,m", [(3, 0, 0), (4, 2, 4), (5, 4, 8)])
+def test_wanda_composite_live(ref, seed, n, m):
+    """blipt5_wanda_pruner of the reference on a freshly seeded toy model vs the oracle's per-row / whole-matrix / n:m
+    selection fed the reference's own scaler_row: masks bit-exact."""
+    import toy_model
+    mg = _make_golden()
+    cfg = toy_model.pruner_cfg(0.4, 0.5) if n == 0 else toy_model.pruner_cfg(0.5, 0.5, prune_n=n, prune_m=m)
+    model, before, rec = _quiet(mg.run_composite, ref, "wanda", cfg, seed=seed)
+    got = mg.collect_layers(model, before, rec, ["scaler_row"])
+    for key, L in _layers(got):
+        R, C = L["W_before"].shape
+        if n:
+            S = oracle.wanda_scores(L["W_before"], L["scaler_row"])
+            keep, Wp, _ = oracle.wanda_nm(L["W_before"], L["scaler_row"], n, m)
+            # torch.topk ties are implementation-defined (SURVEY F8): on tied groups the pruned score multisets must agree
+            same = (keep == L["mask"]).all(axis=1)
+            for r in np.nonzero(~same)[0]:
+                a = np.sort(np.where(keep[r], np.inf, S[r]).reshape(-1, m), axis=1)
+                b = np.sort(np.where(L["mask"][r], np.inf, S[r]).reshape(-1, m), axis=1)
+                assert np.array_equal(a, b), (key, r)
+        elif key.startswith("visual_encoder"):
+            keep, Wp, _ = oracle.wanda_threshold(L["W_before"], L["scaler_row"], int(R * C * 0.5))
+            assert np.array_equal(keep, L["mask"]), key
+        else:
+            keep, Wp, _ = oracle.wanda_rowselect(L["W_before"], L["scaler_row"], int(C * 0.6))
+            assert np.array_equal(keep, L["mask"]), key
+
+
+def test_dsnot_composite_live(ref):
+    """blipt5_dsnot_pruner of the reference (as shipped, and with the write-back block excised) on a freshly seeded toy
+    model vs oracle.dsnot_refine: masks bit-exact."""
+    import toy_model
+    mg = _make_golden()
+    upstream = ref_loader.load(patch_source={"dsnot_pruner": mg._excise_fixup})
+    for ns, kw in ((ref, dict()), (upstream, dict(ref_fixup=False))):
+        cfg = toy_model.pruner_cfg(0.4, 1.0)
+        model, before, rec = _quiet(mg.run_composite, ns, "dsnot", cfg, seed=9, **mg.DSNOT_TOY)
+        got = mg.collect_layers(model, before, rec, ["scaler_row", "sum_metric_row", "mean", "var"])
+        for key, L in _layers(got):
+            keep, _ = oracle.dsnot_refine(L["W_before"], L["scaler_row"], L["sum_metric_row"], L["var"],
+                                          sparsity_num=round(L["W_before"].shape[1] * 0.6), **kw)
+            assert np.array_equal(keep, L["mask"]), (key, kw)
