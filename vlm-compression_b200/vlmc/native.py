@@ -451,7 +451,8 @@ def scores_kth(scores, segments, k):
     items, dev, ref = _score_items(scores, segments)
     lib = load()
     with torch.cuda.device(dev):
-        kd = torch.tensor(k, dtype=torch.int64, device=dev)
+        # ranks go up through pinned memory: a pageable host-to-device copy would make the call wait for the stream
+        kd = torch.tensor(k, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
         out = torch.empty(nseg, dtype=torch.float32, device=dev)
         nbytes = lib.vlmc_scores_workspace_bytes(items, len(items), nseg)
         ws = workspace(ref, nbytes)
