@@ -26,25 +26,50 @@ constexpr int kPotrfThreads = 128;
 
 // Both flips walk rows with a grid-stride loop (a few hundred CTAs in all): one CTA per row meant 473 k CTAs of 256
 // threads at C = 11008 and 1 ms for a pass that moves 0.7 GB.
+constexpr int kFlipUnroll = 4;    // rows in flight per thread: one 4-byte load per thread left the flips latency-bound
+
 __global__ void __launch_bounds__(256)
 flip_copy_kernel(const float* __restrict__ H, int64_t ldh, float* __restrict__ F, int64_t ldf, int C) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= C) return;
-  for (int i = blockIdx.y; i < C; i += gridDim.y) F[(int64_t)i * ldf + j] = H[(int64_t)(C - 1 - i) * ldh + (C - 1 - j)];
+  for (int i0 = blockIdx.y; i0 < C; i0 += gridDim.y * kFlipUnroll) {
+    float v[kFlipUnroll];
+#pragma unroll
+    for (int u = 0; u < kFlipUnroll; ++u) {
+      const int i = i0 + u * (int)gridDim.y;
+      if (i < C) v[u] = H[(int64_t)(C - 1 - i) * ldh + (C - 1 - j)];
+    }
+#pragma unroll
+    for (int u = 0; u < kFlipUnroll; ++u) {
+      const int i = i0 + u * (int)gridDim.y;
+      if (i < C) F[(int64_t)i * ldf + j] = v[u];
+    }
+  }
 }
 
-// strictly-lower entries of Li move to the mirrored strictly-upper slot; the lower slot is cleared
+// strictly-lower entries of Li move to the mirrored strictly-upper slot; the lower slot is cleared.  In place without a
+// hazard: only strictly-lower entries (and the diagonal) are read, only strictly-upper slots receive values.
 __global__ void __launch_bounds__(256)
 flip_to_upper_kernel(float* __restrict__ U, int64_t ldu, int C) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int i = blockIdx.y; i < C; i += gridDim.y) {
-    if (j < i) {
-      const float v = U[(int64_t)i * ldu + j];
-      U[(int64_t)i * ldu + j] = 0.f;
-      U[(int64_t)(C - 1 - i) * ldu + (C - 1 - j)] = v;
-    } else if (j == i && i < C / 2) {
-      const int64_t a = (int64_t)i * ldu + i, b = (int64_t)(C - 1 - i) * ldu + (C - 1 - i);
-      const float t = U[a]; U[a] = U[b]; U[b] = t;
+  for (int i0 = blockIdx.y; i0 < C; i0 += gridDim.y * kFlipUnroll) {
+    float v[kFlipUnroll];
+#pragma unroll
+    for (int u = 0; u < kFlipUnroll; ++u) {
+      const int i = i0 + u * (int)gridDim.y;
+      v[u] = (i < C && j < i) ? U[(int64_t)i * ldu + j] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kFlipUnroll; ++u) {
+      const int i = i0 + u * (int)gridDim.y;
+      if (i >= C) continue;
+      if (j < i) {
+        U[(int64_t)i * ldu + j] = 0.f;
+        U[(int64_t)(C - 1 - i) * ldu + (C - 1 - j)] = v[u];
+      } else if (j == i && i < C / 2) {
+        const int64_t a = (int64_t)i * ldu + i, b = (int64_t)(C - 1 - i) * ldu + (C - 1 - i);
+        const float t = U[a]; U[a] = U[b]; U[b] = t;
+      }
     }
   }
 }
