@@ -220,3 +220,19 @@ def test_layer_to_group_mapping_and_registered_global_pruners(built_lib):
     assert isinstance(ls.return_sparsity(), UniformSparsity) and ls.return_sparsity()["x"] == 0.5
     with pytest.raises(AssertionError):            # max_sparsity_per_layer < original_sparsity (:146)
         LayerSparsity(None, None, None, 1, 0.9, 0.8, "obd_avg")
+
+
+def test_global_allocation_has_no_cpu_path(built_lib):
+    from vlmc import native
+    from vlmc.compression.pruners import layer_sparsity as ls
+    scores = {"a": torch.rand(8, 8), "b": torch.rand(4, 4)}
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ls.get_mask(scores, 0.5, 1.0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ls.get_layerwise_mask(scores, 0.5)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        native.scores_sum(list(scores.values()))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        native.importance_accum([torch.zeros(4)], [torch.ones(4)], "obd")
+    with pytest.raises(IndexError):                       # topk(k = 0)[0][-1] on the reference side
+        ls.get_mask(scores, 0.0, 1.0)
