@@ -314,3 +314,40 @@ def test_dsnot_composite_live(ref):
             keep, _ = oracle.dsnot_refine(L["W_before"], L["scaler_row"], L["sum_metric_row"], L["var"],
                                           sparsity_num=round(L["W_before"].shape[1] * 0.6), **kw)
             assert np.array_equal(keep, L["mask"]), (key, kw)
+
+
+# ---- zeroth-order (MeZO) estimators of LayerSparsity: host loops, so the product code itself runs here on CPU tensors ----
+def _mezo_setup(dtype, seed):
+    torch.manual_seed(seed)
+    model = torch.nn.Sequential(torch.nn.Linear(10, 16, bias=False), torch.nn.Tanh(), torch.nn.Linear(16, 4, bias=False))
+    model = model.to(dtype)
+    gd = torch.Generator().manual_seed(seed + 1)
+    loader = [{"x": torch.randn(3, 10, generator=gd).to(dtype), "text_input": ["t"] * 3} for _ in range(5)]
+    loss_func = lambda m, d, cuda_enabled: (m(d["x"]).float().pow(2).mean(), len(d["text_input"]))
+    return model, loader, loss_func
+
+
+@pytest.mark.parametrize("method", ["olmezo-gradient_sum", "olmezo-aobd_avg", "olmezo-obd_sum", "lmezo-gradient_sum",
+                                    "lmezo-obd_avg", "mezo-gradient_sum", "mezo-aobd_avg", "mezo-obd_sum"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_zeroth_order_estimators_live(ref, built_lib, method, dtype):
+    """vlmc's LayerSparsity zeroth-order estimators against the reference's under the same numpy / torch seeds: equal
+    scores, and equal parameters afterwards (the +1 / -2 / +1 perturbation does not return exactly in bfloat16)."""
+    from vlmc.compression.pruners.layer_single_base_pruner import LayerSparsity
+    results = []
+    for cls in (ref.base.LayerSparsity, LayerSparsity):
+        model, loader, loss_func = _mezo_setup(dtype, 31)
+        names = [k for k, _ in model.named_parameters()]
+        ls = cls(model, loader, loss_func, 9, 0.5, 0.8, method, 2, 1e-3, {k: k for k in names})
+        np.random.seed(1234)
+        fn = {"olmezo": "compute_importance_scores_mezo_layer_one", "lmezo": "compute_importance_scores_mezo_layer",
+              "mezo": "compute_importance_scores_mezo_diff"}[method.split("-")[0]]
+        scores = _quiet(getattr(ls, fn), {k: k for k in names})
+        results.append(({k: v.detach().clone() for k, v in scores.items()},
+                        {k: v.detach().clone() for k, v in model.named_parameters()}))
+    (want_s, want_p), (got_s, got_p) = results
+    assert list(want_s) == list(got_s)
+    for k in want_s:
+        assert want_s[k].shape == got_s[k].shape and want_s[k].dtype == got_s[k].dtype, k
+        assert torch.equal(want_s[k], got_s[k]), (k, want_s[k].flatten()[:4], got_s[k].flatten()[:4])
+        assert torch.equal(want_p[k], got_p[k]), k

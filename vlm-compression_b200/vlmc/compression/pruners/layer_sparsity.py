@@ -13,9 +13,14 @@ What changes is where the work runs.  The reference moves every gradient and eve
 
 The allocation loop itself (`compute_the_sparsity_per_group`, :304-378) works on one number per group; it is restated
 below with the reference's tensor dtypes, including its quirks (the kept-parameter vector turns float32 after the first
-round, and the "remove the extra parameters" branch adds them, :358).  The zeroth-order (MeZO) estimators
-(:477-end) are forward-only loops over the model and not part of this path: they raise.
+round, and the "remove the extra parameters" branch adds them, :358).
+
+The zeroth-order (MeZO) estimators (:477-729; the scripts' `olmezo-gradient_sum`) are kept as host loops: their cost is two
+model forwards per perturbation, and the perturbation has to be torch's own `torch.normal` stream under the reference's
+seeds (a custom generator could not reproduce its numbers), so there is no kernel to write for them.  They follow the
+reference's order of operations exactly, including the inexact "recover the weight" step in 16-bit parameters.
 """
+import numpy as np
 import torch
 
 from vlmc import native
@@ -198,12 +203,14 @@ class LayerSparsity:
         if mapping is None or len(mapping) == 0:
             return UniformSparsity(original_sparsity)
         if len(self.importance_measure) == 0:
-            if self.score_compute.startswith(("mezo", "lmezo", "olmezo")):
-                raise NotImplementedError(
-                    "the zeroth-order (MeZO) importance estimators (layer_single_base_pruner.py:477-) are forward-only "
-                    "loops over the model, outside the calibration-and-masking path; use a first-order score_method "
-                    "(obd_avg, aobd_avg, gradient_avg) or set importance_measure")
-            self.importance_measure = self.compute_importance_scores(mapping)
+            if self.score_compute.startswith("mezo"):                                 # :263-270, same order of tests
+                self.importance_measure = self.compute_importance_scores_mezo_diff(mapping)
+            elif self.score_compute.startswith("lmezo"):
+                self.importance_measure = self.compute_importance_scores_mezo_layer(mapping)
+            elif self.score_compute.startswith("olmezo"):
+                self.importance_measure = self.compute_importance_scores_mezo_layer_one(mapping)
+            else:
+                self.importance_measure = self.compute_importance_scores(mapping)
 
         groups = {}
         for layer, group in mapping.items():
@@ -297,3 +304,115 @@ class LayerSparsity:
         scores = [torch.empty_like(a) for a in acc]
         native.importance_finalize(acc, [p.data for p in params], scores, final_mode, num_batches)
         return dict(zip(names, scores))
+
+    # ---- zeroth-order estimators (:477-729): host loops over model forwards -------------------------------------------
+    def zo_perturb_parameters(self, params, random_seed=1, scaling_factor=1, zo_eps=1e-3):
+        """theta <- theta + scaling_factor * z * zo_eps with z ~ N(0, 1) drawn from torch's generator seeded with
+        random_seed (:477-491); each product is a tensor op in the parameter's dtype, like the reference."""
+        torch.manual_seed(random_seed)
+        for p in params:
+            noise = torch.normal(mean=0, std=1, size=p.data.size(), device=p.data.device, dtype=p.data.dtype)
+            step = scaling_factor * noise
+            step = step * zo_eps
+            p.data = p.data + step
+
+    def _selected(self, layer_to_group_mapping):
+        names, params = [], []
+        for k, v in self.model.named_parameters():
+            if k in layer_to_group_mapping:
+                names.append(k)
+                params.append(v)
+        return names, params
+
+    def _projected_gradient(self, params, d, device, zo_eps):
+        """One two-point estimate along a fresh direction: (L(theta + eps z) - L(theta - eps z)) / (2 eps); the parameters
+        are stepped +1, -2, +1 like the reference (:632-641), so they come back only up to rounding."""
+        seed = np.random.randint(1000000000)
+        self.zo_perturb_parameters(params, random_seed=seed, scaling_factor=1, zo_eps=zo_eps)
+        with torch.no_grad():
+            loss_plus, batch_len = self.loss_func(self.model, d, device != "cpu")
+        self.zo_perturb_parameters(params, random_seed=seed, scaling_factor=-2, zo_eps=zo_eps)
+        with torch.no_grad():
+            loss_minus, batch_len = self.loss_func(self.model, d, device != "cpu")
+        self.zo_perturb_parameters(params, random_seed=seed, scaling_factor=1, zo_eps=zo_eps)
+        return ((loss_plus - loss_minus) / (2 * zo_eps)).item(), batch_len, seed
+
+    def _zeroth_order_scores(self, prefix, names, params, estimate):
+        """The three score rules shared by the estimators (:565-570, :648-653, :724-729)."""
+        if self.score_compute == prefix + "-gradient":
+            return {k: estimate[k].abs() for k in names}
+        if self.score_compute == prefix + "-aobd":
+            return {k: v.data.float().abs() * estimate[k].abs() for k, v in zip(names, params)}
+        if self.score_compute == prefix + "-obd":
+            return {k: v.data.float() ** 2 * estimate[k] ** 2 for k, v in zip(names, params)}
+        raise UnboundLocalError(f"importance_measure is not defined for score_compute {self.score_compute!r}")
+
+    def _per_layer_estimate(self, layer_to_group_mapping, n_mezo, absolute_each):
+        """:574-646 / :655-722: one parameter tensor at a time, n_mezo directions per batch; the estimate of a layer is one
+        number (a 1-element float32 tensor)."""
+        self.model.eval()
+        names, params = self._selected(layer_to_group_mapping)
+        device = next(iter(self.model.parameters())).device
+        estimate = {}
+        for i, (name, param) in enumerate(zip(names, params)):
+            print(i, name)
+            total = torch.zeros(1, dtype=torch.float32, device=param.device)
+            accum_samples = 0
+            for d in self.data_loader:
+                if accum_samples >= self.num_samples:
+                    break
+                per_batch = 0
+                for _ in range(n_mezo):
+                    if accum_samples >= self.num_samples:
+                        break
+                    g, batch_len, seed = self._projected_gradient([param], d, device, self.noise_eps)
+                    accum_samples += batch_len
+                    torch.manual_seed(seed)                     # the reference re-seeds here (:643, :715)
+                    per_batch += abs(g) if absolute_each else g
+                total = total + torch.tensor([per_batch], dtype=torch.float32, device=param.device).abs()
+            estimate[name] = total
+        print(estimate)
+        return names, params, estimate
+
+    @print_time
+    def compute_importance_scores_mezo_layer_one(self, layer_to_group_mapping):
+        """"olmezo-*" (:655-729): num_noise directions per batch, |projected gradient| summed."""
+        names, params, estimate = self._per_layer_estimate(layer_to_group_mapping, self.num_noise, absolute_each=True)
+        return self._zeroth_order_scores("olmezo", names, params, estimate)
+
+    @print_time
+    def compute_importance_scores_mezo_layer(self, layer_to_group_mapping):
+        """"lmezo-*" (:572-653): 4 directions per batch over 8 samples (the reference overwrites num_samples, :599), the
+        signed projected gradients of a batch are summed before the absolute value."""
+        self.num_samples = 8
+        names, params, estimate = self._per_layer_estimate(layer_to_group_mapping, 4, absolute_each=False)
+        return self._zeroth_order_scores("lmezo", names, params, estimate)
+
+    @print_time
+    def compute_importance_scores_mezo_diff(self, layer_to_group_mapping):
+        """"mezo-*" (:493-570): all selected parameters perturbed together, one zeroth-order SGD step per batch with learning
+        rate 1e-3 / #parameters; the estimate is |theta_end - theta_start| / #batches and the weights are restored."""
+        self.model.eval()
+        names, params = self._selected(layer_to_group_mapping)
+        saved = {k: v.data.clone() for k, v in zip(names, params)}           # stays on the device
+        device = next(iter(self.model.parameters())).device
+        learning_rate = 1 / sum(v.numel() for v in params) * 1e-3
+        accum_samples = 0
+        num_batches = 0
+        for d in self.data_loader:
+            if accum_samples >= self.num_samples:
+                break
+            print(accum_samples)
+            g, batch_len, seed = self._projected_gradient(params, d, device, self.noise_eps)
+            accum_samples += batch_len
+            num_batches += 1
+            torch.manual_seed(seed)
+            for p in params:
+                noise = torch.normal(mean=0, std=1, size=p.data.size(), device=p.data.device, dtype=p.data.dtype)
+                p.data = p.data - g * noise * learning_rate
+        estimate = {}
+        for k, p in zip(names, params):
+            estimate[k] = (p.data - saved[k]).float().abs() / num_batches
+            p.data = saved[k]
+        return self._zeroth_order_scores("mezo", names, params, estimate)
+
