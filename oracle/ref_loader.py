@@ -22,7 +22,7 @@ import types
 REF_ROOT = os.environ.get("VLMC_REFERENCE_ROOT", "/root/reference")
 
 _PRUNER_FILES = ("utils", "base_pruner", "layer_single_base_pruner",
-                 "wanda_pruner", "sparsegpt_pruner", "dsnot_pruner")
+                 "wanda_pruner", "sparsegpt_pruner", "dsnot_pruner", "global_pruner")
 
 
 def available() -> bool:
@@ -58,7 +58,7 @@ _cache = None
 
 
 def load(patch_source=None):
-    """Return a namespace with .wanda, .sparsegpt, .dsnot, .lora, .base (reference modules).
+    """Return a namespace with .wanda, .sparsegpt, .dsnot, .global_pruner, .lora, .base (reference modules).
 
     patch_source: optional {module_short_name: callable(str)->str} applied to the file text
     before exec (used only to excise dsnot_pruner.py:734-740 for the upstream-semantics test).
@@ -107,7 +107,8 @@ def load(patch_source=None):
             mods[short] = mod
         ns = types.SimpleNamespace(
             wanda=mods["wanda_pruner"], sparsegpt=mods["sparsegpt_pruner"], dsnot=mods["dsnot_pruner"],
-            base=mods["layer_single_base_pruner"], lora=lora, registry=_PassThroughRegistry)
+            base=mods["layer_single_base_pruner"], global_pruner=mods["global_pruner"], lora=lora,
+            registry=_PassThroughRegistry)
     finally:
         # leave sys.modules without our fake 'lavis' so nothing else resolves it by accident
         for k in [k for k in sys.modules if k == "lavis" or k.startswith("lavis.")]:

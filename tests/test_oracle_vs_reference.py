@@ -351,3 +351,75 @@ def test_zeroth_order_estimators_live(ref, built_lib, method, dtype):
         assert want_s[k].shape == got_s[k].shape and want_s[k].dtype == got_s[k].dtype, k
         assert torch.equal(want_s[k], got_s[k]), (k, want_s[k].flatten()[:4], got_s[k].flatten()[:4])
         assert torch.equal(want_p[k], got_p[k]), k
+
+
+# ---- global pruners (global_pruner.py): the reference's prune() on CPU vs the numpy oracle's get_mask -------------------
+def _global_toy(seed):
+    mg = _make_golden()
+    model = mg._AllocModel(seed=seed)
+    gd = torch.Generator().manual_seed(seed + 100)
+    loader = [{"x": torch.randn(4, 24, generator=gd), "v": torch.randn(4, 16, generator=gd), "text_input": ["t"] * 4}
+              for _ in range(3)]
+    return model, loader
+
+
+def _prunable(name, v):        # global_pruner.py:213-220
+    return v.dim() == 2 and ".block" in name and "relative_attention_bias.weight" not in name and \
+        (name.startswith("t5_model") or name.startswith("visual_encoder"))
+
+
+@pytest.mark.parametrize("is_global,per_model,iteration", [(True, False, 1), (True, False, 2), (True, True, 1),
+                                                           (False, False, 1), (False, False, 3)])
+def test_global_mag_pruner_live(ref, is_global, per_model, iteration):
+    """blipt5_mag_pruner of the reference, end to end, vs the oracle's masks: the score is the SIGNED up-cast weight
+    (global_pruner.py:242-243), sparsity follows p ** (iterations / i), masks multiply the weights in place."""
+    model, loader = _global_toy(17)
+    w = {k: v.detach().numpy().copy() for k, v in model.named_parameters()}
+    cfg = dict(t5_prune_spec="3-0.6-1.0-1.0", vit_prune_spec="2-0.6-1.0-1.0", t5_pruning_method="mag",
+               vit_pruning_method="mag", is_global=is_global, prune_per_model=per_model, iteration=iteration,
+               t5_model_prefix="t5_model", vit_model_prefix="visual_encoder")
+    pruner = ref.global_pruner.BLIPT5MagPruner(model=model, data_loader=loader, **cfg)
+    _quiet(pruner.prune)
+    names = [k for k, v in model.named_parameters() if _prunable(k, v)]
+    assert len(names) == len(w)                                   # every parameter of the toy is prunable
+    p = 1 - 0.6
+    masks = None
+    for i in range(1, iteration + 1):
+        p_i = p ** (iteration / i)
+        scores = {k: w[k].astype(np.float32).copy() for k in names}
+        if masks is not None:
+            scores = {k: scores[k] * masks[k] for k in names}
+        if is_global and not per_model:
+            masks, _ = oracle.global_get_mask(scores, p_i, 1.0)
+        elif is_global:
+            masks = {}
+            for prefix in ("visual_encoder", "t5_model"):
+                part, _ = oracle.global_get_mask({k: v for k, v in scores.items() if k.startswith(prefix)}, p_i, 1.0)
+                masks.update(part)
+        else:
+            masks = oracle.layerwise_get_mask(scores, p_i)
+        w = {k: w[k] * masks[k] for k in names}
+    for k, v in model.named_parameters():
+        assert np.array_equal(v.detach().numpy(), w[k]), (k, is_global, per_model, iteration)
+
+
+def test_global_aobd_pruner_live(ref):
+    """blipt5_aobd_pruner (global_pruner.py:253-300): |w| * |mean over batches of |grad||, then the global mask."""
+    model, loader = _global_toy(23)
+    w = {k: v.detach().numpy().copy() for k, v in model.named_parameters()}
+    names = list(w)
+    grads = [torch.autograd.grad(model(d)["loss"], list(model.parameters())) for d in loader]
+    acc = {k: np.zeros_like(w[k]) for k in names}
+    for gb in grads:
+        for k, gr in zip(names, gb):
+            acc[k] = (acc[k] + np.abs(gr.numpy())).astype(np.float32)
+    scores = {k: (np.abs(w[k]) * np.abs((acc[k] / np.float32(len(grads))).astype(np.float32))).astype(np.float32)
+              for k in names}
+    cfg = dict(t5_prune_spec="3-0.5-1.0-1.0", vit_prune_spec="2-0.5-1.0-1.0", t5_pruning_method="aobd",
+               vit_pruning_method="aobd", is_global=True, prune_per_model=False, iteration=1, num_samples=12,
+               t5_model_prefix="t5_model", vit_model_prefix="visual_encoder")
+    pruner = ref.global_pruner.BLIPT5AOBDPruner(model=model, data_loader=loader, **cfg)
+    _quiet(pruner.prune)
+    masks, _ = oracle.global_get_mask(scores, 0.5, 1.0)
+    for k, v in model.named_parameters():
+        assert np.array_equal(v.detach().numpy(), w[k] * masks[k]), k
