@@ -196,7 +196,7 @@ def test_layer_to_group_mapping_and_registered_global_pruners(built_lib):
     from vlmc.common.registry import registry
     import vlmc.compression  # noqa: F401
     from vlmc.compression.pruners.layer_single_base_pruner import LayerWiseBasePruner, LayerSparsity, UniformSparsity
-    assert {"blipt5_mag_pruner", "blipt5_aobd_pruner"} <= set(registry.list_pruners())
+    assert {"blipt5_mag_pruner", "blipt5_rand_pruner", "blipt5_aobd_pruner"} <= set(registry.list_pruners())
 
     class M(nn.Module):
         def __init__(self):

@@ -4,7 +4,7 @@ from vlmc.compression.pruners.layer_single_base_pruner import BasePruner  # noqa
 from vlmc.compression.pruners.wanda_pruner import BLIPT5LayerWandaPruner  # noqa: F401
 from vlmc.compression.pruners.sparsegpt_pruner import BLIPT5LayerSparseGPTPruner  # noqa: F401
 from vlmc.compression.pruners.dsnot_pruner import BLIPT5LayerDSnoTPruner  # noqa: F401
-from vlmc.compression.pruners.global_pruner import BLIPT5MagPruner, BLIPT5AOBDPruner  # noqa: F401
+from vlmc.compression.pruners.global_pruner import BLIPT5MagPruner, BLIPT5RandPruner, BLIPT5AOBDPruner  # noqa: F401
 
 __all__ = ["BasePruner", "load_pruner"]
 

@@ -4,7 +4,8 @@ Mirrors lavis/compression/pruners/global_pruner.py: `BLIPT5GlobalPruner` (:47-23
 `get_layerwise_mask`, `global_iterative_pruning`, `prune`, and the registered `blipt5_mag_pruner` (:238-243) and
 `blipt5_aobd_pruner` (:253-300).  The reference builds every score on the CPU and runs torch.topk over the concatenated
 model; here scores stay in HBM and thresholds come from the exact radix select (K18-K20, layer_sparsity.py).
-`blipt5_rand_pruner` (random scores) and `blipt5_mezo_pruner` (forward-only zeroth-order estimates) are not on the path.
+`blipt5_rand_pruner` (:245-250) is the same flow over random scores.  `blipt5_mezo_pruner` (one zeroth-order number per
+layer, so whole layers are pruned) is not mirrored.
 """
 import torch
 
@@ -108,6 +109,17 @@ class BLIPT5MagPruner(BLIPT5GlobalPruner):
         # as shipped (global_pruner.py:242-243) the score is the SIGNED weight, up-cast - not its magnitude.  Only the
         # tensors that will be selected are materialised (the reference copies every parameter and filters afterwards).
         return {k: v.data.float().clone() for k, v in model.named_parameters() if k in dict_layers_to_prune}
+
+
+@registry.register_pruner("blipt5_rand_pruner")
+class BLIPT5RandPruner(BLIPT5GlobalPruner):
+    pruner_name = "blipt5_rand_pruner"
+
+    def compute_importance_scores(self, model, data_loader=None, dict_layers_to_prune={}, loss_func=None):
+        # global_pruner.py:249-250: standard-normal scores (the random baseline).  Drawn on the device that holds the
+        # parameter, so the stream differs from a CPU run of the reference; only the selected tensors are materialised.
+        return {k: torch.randn_like(v.data).float().contiguous() for k, v in model.named_parameters()
+                if k in dict_layers_to_prune}
 
 
 @registry.register_pruner("blipt5_aobd_pruner")
