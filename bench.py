@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--method wanda_nm|wanda_unstructured|sparsegpt|dsnot]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...     # the reference's CPU path (torch port, oracle/cpu_port.py)
+    python bench.py --impl reference ...     # the unmodified reference on the host cores (oracle/ref_arm.py; port fallback)
 
 A "step" prunes ONE Vicuna-7B decoder layer (q,k,v,o 4096x4096; gate,up 11008x4096; down 4096x11008, fp16,
 random init) the way the reference's per-layer wrapper API dictates: for each of the 7 linears, calibration
@@ -958,15 +958,51 @@ def f4_global_allocation(torch, native, dev, cpu=True):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def _ref_available():
+    try:
+        from oracle import ref_loader
+        return ref_loader.available()
+    except Exception:  # noqa: BLE001
+        return False
+
+
 def cpu_block_seconds(method, threads, budget="small"):
-    """The reference's algorithm on host cores (oracle/cpu_port.py) on a bounded sample of the block, scaled to the
-    whole block.  Returns (seconds per block, description of the sample)."""
+    """The reference on the host cores.  When the unmodified reference files are present (build container:
+    /root/reference; GPU box: the verbatim copy under baseline/_ref, oracle/fetch_ref.py) the reference's OWN composite
+    pruner runs the whole block through its public entry point (oracle/ref_arm.py, kind "reference"); otherwise the torch
+    port of its op sequence (oracle/cpu_port.py, kind "port") runs a bounded sample.
+    Returns (seconds per block, description of the sample, kind)."""
     import torch
-    from oracle import cpu_port
     if method.endswith("_shared"):        # the reference has no such mode: its per-linear schedule is the baseline
         method = method[:-len("_shared")]
     if method == "dsnot_elided":
         method = "dsnot"
+    if _ref_available():
+        from oracle import ref_arm
+        if method == "wanda_nm":
+            sec, _ = ref_arm.run_composite("wanda", ref_arm.VICUNA_BLOCK, N_SEQ, SEQ_LEN, torch.float16, 0.5, 2, 4, threads=threads)
+            return sec, (f"the WHOLE block through the unmodified BLIPT5LayerWandaPruner.prune(): {N_SEQ} per-sequence add_batch "
+                         "hook calls per linear + the 2:4 topk loop of the 7 linears (block forwards skipped, 8 distinct "
+                         "resident sequences per input cycled)"), "reference"
+        if method == "wanda_unstructured":
+            sec, _ = ref_arm.run_composite("wanda", ref_arm.VICUNA_BLOCK, N_SEQ, SEQ_LEN, torch.float16, 0.5, threads=threads)
+            return sec, (f"the WHOLE block through the unmodified BLIPT5LayerWandaPruner.prune(): {N_SEQ} per-sequence add_batch "
+                         "hook calls per linear + the stable row sort of the 7 linears"), "reference"
+        if method == "dsnot":
+            rows_div, seqs = 8, 16
+            small = [(n, R // rows_div, C, i) for n, R, C, i in ref_arm.VICUNA_BLOCK]
+            # two runs separate the statistics (linear in sequences) from the refine (linear in rows)
+            t_a, _ = ref_arm.run_composite("dsnot", small, seqs, SEQ_LEN, torch.float16, 0.6, threads=threads)
+            t_b, _ = ref_arm.run_composite("dsnot", small, seqs // 2, SEQ_LEN, torch.float16, 0.6, threads=threads)
+            per_seq = max(t_a - t_b, 0.0) / (seqs // 2)
+            refine = max(t_a - per_seq * seqs, 0.0)
+            return per_seq * N_SEQ + refine * rows_div, (
+                f"unmodified BLIPT5LayerDSnoTPruner.prune() on 1/{rows_div} of the rows of each linear with {seqs} and "
+                f"{seqs // 2} sequences ({t_a:.1f} s, {t_b:.1f} s): statistics scaled to {N_SEQ} sequences, refine scaled x{rows_div} "
+                "(rows are independent; extrapolated)"), "reference"
+        sec, note = ref_arm.sparsegpt_block_seconds(ref_arm.VICUNA_BLOCK, N_SEQ, SEQ_LEN, torch.float16, 0.5, threads=threads)
+        return sec, "unmodified SparseGPT class: " + note, "reference"
+    from oracle import cpu_port
     torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(0)
     xs = {inp: (torch.randn(SEQ_LEN, C, generator=g)).half() for inp, C in INPUT_DIMS.items()}
@@ -994,7 +1030,7 @@ def cpu_block_seconds(method, threads, budget="small"):
         total = t_stats * (N_SEQ / n_sample) + t_sel
         return total, (f"statistics on {n_sample} of {N_SEQ} sequences per linear ({t_stats:.2f} s, scaled x{N_SEQ // n_sample}, "
                        f"extrapolated) + full selection of the 7 linears ({t_sel:.2f} s)"
-                       + ("; DSnoT's swap loop not timed (lower bound)" if method == "dsnot" else ""))
+                       + ("; DSnoT's swap loop not timed (lower bound)" if method == "dsnot" else "")), "port"
     # sparsegpt: Hessian accumulation on 1 sequence for C=4096 and C=11008, fasterprune on a 1024-column problem;
     # both scaled by their flop counts to the 7 linears of the block
     t_h = {}
@@ -1016,20 +1052,42 @@ def cpu_block_seconds(method, threads, budget="small"):
     t_prune = sum(unit * (C ** 3 + R * C ** 2) for _, R, C, _ in LINEARS)
     return t_hess + t_prune, (f"SparseGPT.add_batch on 1 of {N_SEQ} sequences for C=4096 ({t_h[D]:.2f} s) and C=11008 "
                               f"({t_h[FF]:.2f} s) scaled to 7 linears x {N_SEQ} sequences, + fasterprune on a "
-                              f"{Rs}x{Cs} linear ({t_fp:.2f} s) scaled by C^3 + R*C^2 to the 7 linears (extrapolated)")
+                              f"{Rs}x{Cs} linear ({t_fp:.2f} s) scaled by C^3 + R*C^2 to the 7 linears (extrapolated)"), "port"
+
+
+def config1_cpu_reference(threads):
+    """BASELINE.json configs[0]: Wanda 50 % unstructured on one FlanT5-XL encoder block (bf16, 128 x 512 calibration
+    tokens), on the CPU through the unmodified reference, in full."""
+    import torch
+    if not _ref_available():
+        return None
+    from oracle import ref_arm
+    sec, _ = ref_arm.run_composite("wanda", ref_arm.T5XL_ENC_BLOCK, N_SEQ, 512, torch.bfloat16, 0.5, threads=threads)
+    return {"value": sec, "unit": "s/block", "cores": threads, "kind": "reference",
+            "sample": "whole FlanT5-XL encoder block (7 linears) through the unmodified BLIPT5LayerWandaPruner.prune(), "
+                      f"{N_SEQ} x 512 bf16 tokens per linear"}
 
 
 def same_gpu_torch_eager(method):
-    """the reference is torch code that its users run on the GPU that holds the model.  Its op sequence
-    (oracle/cpu_port.py: per-sequence add_batch with the fp32 cast and the strided norm, the Python loop of C/m topk calls
-    or the stable row sort) with every tensor on this B200, torch eager, whole block, timed with CUDA events.  A reported
-    baseline like the CPU figure; only for the Wanda methods; never raises (the bench line must not depend on it)."""
+    """the reference is torch code that its users run on the GPU that holds the model: the unmodified
+    composite pruner (oracle/ref_arm.py) with every tensor on this B200, torch eager, whole block.  Falls back to the port
+    of its op sequence (oracle/cpu_port.py) when the reference files are absent.  A reported baseline like the CPU
+    figure; only for the Wanda methods; never raises (the bench line must not depend on it)."""
     try:
         import torch
-        from oracle import cpu_port
         if method not in ("wanda_nm", "wanda_unstructured") or not torch.cuda.is_available():
             return None
         dev = torch.device("cuda", torch.cuda.current_device())
+        if _ref_available():
+            from oracle import ref_arm
+            nm = (2, 4) if method == "wanda_nm" else (0, 0)
+            ref_arm.run_composite("wanda", ref_arm.VICUNA_BLOCK, 2, SEQ_LEN, torch.float16, 0.5, *nm, device=dev)   # warm-up
+            sec, _ = ref_arm.run_composite("wanda", ref_arm.VICUNA_BLOCK, N_SEQ, SEQ_LEN, torch.float16, 0.5, *nm, device=dev)
+            torch.cuda.empty_cache()
+            return {"value": sec, "unit": UNIT, "kind": "reference",
+                    "sample": f"whole block through the unmodified BLIPT5LayerWandaPruner.prune() with the model on the same B200 "
+                              f"(torch eager): {N_SEQ} per-sequence add_batch hook calls per linear + selection of the 7 linears"}
+        from oracle import cpu_port
         g = torch.Generator(device=dev).manual_seed(5)
         xs = {inp: torch.randn(8, SEQ_LEN, C, device=dev, generator=g).half() for inp, C in INPUT_DIMS.items()}
         Ws = {name: (torch.randn(R, C, device=dev, generator=g) * 0.02).half() for name, R, C, _ in LINEARS}
@@ -1061,8 +1119,8 @@ def same_gpu_torch_eager(method):
 
 def cpu_baseline(method):
     threads = os.cpu_count() or 1
-    total, sample = cpu_block_seconds(method, threads)
-    out = {"value": total, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    total, sample, kind = cpu_block_seconds(method, threads)
+    out = {"value": total, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample}
     same_gpu = same_gpu_torch_eager(method)
     if same_gpu is not None:
         out["same_gpu_torch_eager"] = same_gpu
@@ -1070,26 +1128,35 @@ def cpu_baseline(method):
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the step on all host cores.  A step is the whole
+    block for the Wanda methods; the number of timed steps is capped so the run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    for _ in range(min(args.warmup, 1)):
-        cpu_block_seconds(args.method, threads)
-    vals, sample = [], ""
-    k = max(1, min(args.steps, 3))
-    for _ in range(k):
-        total, sample = cpu_block_seconds(args.method, threads)
+    vals, sample, kind = [], "", "port"
+    t_start = time.perf_counter()
+    warm = 0
+    if args.warmup > 0:
+        total, sample, kind = cpu_block_seconds(args.method, threads)       # one untimed pass: page cache, thread pool
+        warm = 1
+    k = max(1, args.steps)
+    for i in range(k):
+        total, sample, kind = cpu_block_seconds(args.method, threads)
         vals.append(total)
+        spent = time.perf_counter() - t_start
+        if spent + spent / (len(vals) + warm) > 170.0:                     # next step would pass ~3 minutes
+            break
     v = sum(vals) / len(vals)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT,
-        "n_gpus": args.gpus, "steps": k, "warmup": min(args.warmup, 1), "ms_per_step": v * 1e3,
+        "n_gpus": args.gpus, "steps": len(vals), "warmup": warm, "ms_per_step": v * 1e3,
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{WORKLOAD[args.method]} on one InstructBLIP-Vicuna-7B LLM block (7 linears, fp16 weights, "
                                f"random init), {N_SEQ}x{SEQ_LEN} fp16 calibration tokens per linear",
-                   "method": args.method},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": "each step: " + sample},
+                   "method": args.method, "steps_requested": args.steps,
+                   "steps_note": "timed steps capped so that the whole run stays within ~3 minutes"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": "each step: " + sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
 

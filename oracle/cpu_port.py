@@ -1,12 +1,11 @@
 """TEST / BASELINE INFRASTRUCTURE ONLY - multi-threaded CPU port of the reference's path, op for op in torch.
 
-The reference IS torch code run on whatever device holds the model; on the GPU box's host cores this port is
-what `bench.py --impl reference` and the `cpu_baseline` leg time (kind = "port": /root/reference does not
-travel to the GPU box and `lavis` is not importable as a package).  The same leg also runs the Wanda part once with its
-tensors on the GPU (`cpu_baseline.same_gpu_torch_eager`, SURVEY 8d: the reference as its users run it).  It follows the reference's own op sequence
-(cast, strided norm, stable sort / per-group topk loop, scatter, index_put) so the timing is the reference's
-algorithm, not a tuned rewrite.  Pinned against the golden fixtures in tests/test_oracle_vs_golden.py.
-Never imported by vlmc/.
+FALLBACK of `bench.py --impl reference` and the `cpu_baseline` leg (kind = "port"), used only when the unmodified
+reference files are absent (neither /root/reference nor the verbatim copy under baseline/_ref that oracle/fetch_ref.py
+makes; with them the reference's own composite pruner is timed, oracle/ref_arm.py, kind = "reference").  It follows the
+reference's own op sequence (cast, strided norm, stable sort / per-group topk loop, scatter, index_put) so the timing
+is the reference's algorithm, not a tuned rewrite.  Pinned against the golden fixtures the reference produced in
+tests/test_reference_arm.py.  Never imported by vlmc/.
 """
 import torch
 

@@ -4,8 +4,9 @@ The reference package (`lavis`) is not importable as a package in this image (om
 missing and `lavis/datasets/data_utils.py` is absent from the tree), but the seven files on
 the calibration-and-masking path only need torch + transformers.Conv1D once four names are
 stubbed.  This loader is used (a) by `tests/golden/make_golden.py` to generate the committed
-fixtures and (b) by the CPU tests, which skip when `/root/reference` is absent (it never
-travels to the GPU box).  Nothing under `vlmc/` may import this file.
+fixtures and (b) by the CPU tests, which skip when no reference tree is found, and (c) by bench.py's
+`--impl reference` / `cpu_baseline` legs and the live GPU differential tests, which read the verbatim copy
+under `baseline/_ref` (oracle/fetch_ref.py) on the GPU box.  Nothing under `vlmc/` may import this file.
 
 Stubs (and the reference line that needs each):
   lavis.common.registry.registry.register_pruner   wanda_pruner.py:84 (decorator)
@@ -19,7 +20,22 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("VLMC_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _resolve_root():
+    """VLMC_REFERENCE_ROOT, else the reference tree of the build container, else the verbatim copy that
+    oracle/fetch_ref.py leaves under baseline/_ref (git-ignored; it travels to the GPU box with the snapshot)."""
+    env = os.environ.get("VLMC_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")):
+        if os.path.isfile(os.path.join(cand, "lavis/compression/pruners/wanda_pruner.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _resolve_root()
 
 _PRUNER_FILES = ("utils", "base_pruner", "layer_single_base_pruner",
                  "wanda_pruner", "sparsegpt_pruner", "dsnot_pruner", "global_pruner")

@@ -1,7 +1,8 @@
 """Generates the committed golden fixtures by running the UNMODIFIED reference (loaded by path through
 oracle/ref_loader.py) on seeded inputs.  Needs /root/reference, so it only runs in the build container:
 
-    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+    python tests/golden/make_golden.py [name ...]        # rewrites tests/golden/*.npz (all, or the named generators)
+    python tests/golden/make_golden.py --check [name ...] # regenerates in memory, compares with the committed files, exit 1 on a difference
 
 The fixtures pin oracle/oracle.py (tests/test_oracle_vs_golden.py, CPU) and the CUDA kernels
 (tests/test_gpu_parity.py, GPU box, where the reference itself is absent).
@@ -36,8 +37,23 @@ def packw(t):
     return t.numpy().copy()
 
 
+CHECK = False          # --check: regenerate in memory and compare with the committed files, write nothing
+MISMATCH = []
+
+
 def save(name, **arrs):
     path = os.path.join(HERE, name)
+    if CHECK:
+        old = np.load(path, allow_pickle=False)
+        bad = sorted(set(old.files) ^ set(arrs))
+        for k in set(old.files) & set(arrs):
+            a, b = np.asarray(arrs[k]), old[k]
+            if a.shape != b.shape or a.dtype != b.dtype or not np.array_equal(a, b, equal_nan=a.dtype.kind == "f"):
+                bad.append(k)
+        print(f"{name}: {'ok' if not bad else 'DIFFERS in %d of %d arrays: %s' % (len(bad), len(arrs), bad[:6])}")
+        if bad:
+            MISMATCH.append(name)
+        return
     np.savez_compressed(path, **arrs)
     print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
 
@@ -441,13 +457,17 @@ def gen_layer_sparsity(ref):
 def main():
     torch.set_num_threads(8)
     ref = ref_loader.load()
-    only = set(sys.argv[1:])
+    global CHECK
+    CHECK = "--check" in sys.argv[1:]
+    only = set(a for a in sys.argv[1:] if not a.startswith("--"))
     gens = dict(wanda_stats=gen_wanda_stats, dsnot_stats=gen_dsnot_stats, wanda_toy=gen_wanda_toy,
                 dsnot_toy=gen_dsnot_toy, lora_merge=gen_lora_merge, lora_forward=gen_lora_forward, sparsegpt=gen_sparsegpt,
                 reorder=gen_reorder, layer_sparsity=gen_layer_sparsity)
     for name, fn in gens.items():
         if not only or name in only:
             fn(ref)
+    if MISMATCH:
+        sys.exit(f"fixtures differ from the generator: {MISMATCH}")
 
 
 if __name__ == "__main__":
