@@ -14,8 +14,19 @@ def _run(env_extra, *args):
                           text=True, timeout=600)
 
 
-def test_reference_arm_prints_the_contract_line():
-    r = _run({}, "--impl", "reference", "--steps", "1", "--warmup", "0")
+import pytest
+
+
+@pytest.mark.parametrize("kind", ["reference", "port"])
+def test_reference_arm_prints_the_contract_line(kind):
+    """kind "reference": the unmodified reference files (here /root/reference, on the GPU box baseline/_ref) run the whole
+    block; kind "port": they are absent (VLMC_REFERENCE_ROOT points nowhere) and oracle/cpu_port.py times a bounded sample."""
+    sys.path.insert(0, ROOT)
+    from oracle import ref_loader
+    if kind == "reference" and not ref_loader.available():
+        pytest.skip("no reference tree")
+    r = _run({} if kind == "reference" else {"VLMC_REFERENCE_ROOT": "/nonexistent"}, "--impl", "reference", "--steps", "1",
+             "--warmup", "0")
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["higher_is_better"] is False and line["vs_baseline"] is None
@@ -24,7 +35,7 @@ def test_reference_arm_prints_the_contract_line():
     assert line["steps"] == 1 and line["warmup"] == 0 and line["n_gpus"] == 1 and line["data"] == "synthetic"
     assert "workload" in line["config"] and "model" not in line["config"]
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert cb["kind"] == kind and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0
 

@@ -1001,7 +1001,7 @@ def test_shared_inputs_give_the_per_linear_result(native, name, monkeypatch):
         torch.manual_seed(0)                     # the toy model's biases and norms use the global generator
         model = toy_model.ToyBlip(d_llm=296, ff=488, n_llm=2, n_vit=0).eval().cuda()
         pruner = comp.load_pruner(name, model, toy_model.toy_batches(6, device="cuda"),
-                                  cfg=toy_model.pruner_cfg(0.4, 1.0, share_inputs=share))
+                                  cfg=toy_model.pruner_cfg(0.4, 1.0, share_inputs=share, calib_batch=1))
         model, _ = pruner.prune()
         out[share] = (calls["n"], {k: v.detach().clone() for k, v in model.state_dict().items()},
                       {n: m.mask.clone() for n, m in model.named_modules() if hasattr(m, "mask") and torch.is_tensor(m.mask)})
@@ -1013,6 +1013,60 @@ def test_shared_inputs_give_the_per_linear_result(native, name, monkeypatch):
     assert masks_per.keys() == masks_shared.keys()
     for k in masks_per:
         assert torch.equal(masks_per[k], masks_shared[k]), k
+
+
+def test_stacked_chunk_statistics_equal_per_sample_calls(native):
+    """SURVEY 8f-1 (calibration batching): ONE add_batch on K stacked samples gives the statistics of K per-sample calls
+    within 1e-5 - Wanda scaler_row, SparseGPT H, and DSnoT's four vectors (var stays the mean of PER-CALL variances)."""
+    from vlmc.compression.pruners import dsnot_pruner, sparsegpt_pruner, wanda_pruner
+    K, S, C = 5, 96, 320
+    xs = [acts(S, C, 900 + j, torch.float16).cuda().unsqueeze(0) * (1 + 0.3 * j) for j in range(K)]
+    lin = torch.nn.Linear(C, 8, bias=False).cuda().half()
+    for mk, names in ((wanda_pruner.WrappedGPT, ["scaler_row"]), (sparsegpt_pruner.SparseGPT, ["H"]),
+                      (dsnot_pruner.WrappedGPT, ["scaler_row", "sum_metric_row", "mean", "var"])):
+        a, b = mk(lin), mk(lin)
+        for x in xs:
+            a.add_batch(x, None)
+        b._stacked_calls = K
+        b.add_batch(torch.cat(xs, 0), None)
+        assert a.nsamples == b.nsamples == K
+        for n in names:
+            va, vb = getattr(a, n).float().reshape(-1).cpu().numpy(), getattr(b, n).float().reshape(-1).cpu().numpy()
+            assert rel_inf(vb, va) < REL, (mk.__module__, n)
+
+
+@pytest.mark.parametrize("name", ["blipt5_wanda_pruner", "blipt5_dsnot_pruner", "blipt5_sparsegpt_pruner"])
+def test_calibration_batching_in_the_driver(native, name, monkeypatch):
+    """Driver level: with calib_batch = 4 the 6 calibration samples run through every block as chunks of
+    4 + 2 stacked samples, so the statistics kernel runs once per chunk and distinct input; the result agrees with the
+    one-sample-per-forward schedule (calib_batch = 1, the reference's) up to the rounding of the batched block forward."""
+    import toy_model
+    import vlmc.compression as comp
+    calls = {"n": 0}
+    target = {"blipt5_wanda_pruner": "sqnorm_accum", "blipt5_dsnot_pruner": "dsnot_stats",
+              "blipt5_sparsegpt_pruner": "hessian_accum"}[name]
+    real = getattr(native, target)
+
+    def counted(*a, **k):
+        calls["n"] += 1
+        return real(*a, **k)
+    monkeypatch.setattr(native, target, counted)
+    out = {}
+    for cb in (1, 4):
+        calls["n"] = 0
+        torch.manual_seed(0)
+        model = toy_model.ToyBlip(d_llm=296, ff=488, n_llm=2, n_vit=0, llm_dtype=torch.float32).eval().cuda()
+        pruner = comp.load_pruner(name, model, toy_model.toy_batches(6, device="cuda"),
+                                  cfg=toy_model.pruner_cfg(0.4, 1.0, calib_batch=cb))
+        model, _ = pruner.prune()
+        out[cb] = (calls["n"], {n: m.weight.data.clone() for n, m in model.named_modules() if isinstance(m, torch.nn.Linear)
+                                and "llm_model" in n})
+    assert out[1][0] == 2 * 6 * 4 and out[4][0] == 2 * 2 * 4          # layers x chunks x distinct inputs
+    for n, Wa in out[1][1].items():
+        Wb = out[4][1][n]
+        agree = float(((Wa == 0) == (Wb == 0)).float().mean())
+        assert agree > 0.995, (n, agree)
+        assert abs(float((Wa == 0).float().mean()) - float((Wb == 0).float().mean())) < 1e-3
 
 
 @pytest.mark.parametrize("tag,n,m", [("f16", 2, 4), ("bf16", 4, 8), ("f32", 2, 4), ("f16", 1, 2), ("bf16", 5, 16), ("f32", 3, 8)])
@@ -1103,6 +1157,60 @@ def test_qformer_blocks_are_pruned_with_the_per_linear_rule(native):
             mod = layers[i].get_submodule(n)
             assert bool((mod.weight.data[~mod.mask] == 0).all()) and torch.equal(mod.weight.data[mod.mask], W0[(i, n)][mod.mask])
             assert isinstance(mod.weight.importance_score, float)
+
+
+@pytest.mark.parametrize("wdtype,acdtype", [(torch.float32, torch.float16), (torch.float32, torch.bfloat16),
+                                            (torch.float16, torch.bfloat16), (torch.bfloat16, torch.bfloat16)])
+def test_masked_lora_forward_backward_under_autocast(native, wdtype, acdtype):
+    """the masked LoRA forward / backward under torch.autocast with a weight dtype that differs from the
+    autocast dtype (fp32 LoRA'd weights under maybe_autocast(), fp16 weights under bf16 autocast) must train like the
+    reference's plain-autograd expression (lora.py:364-369) does: same output, same gradients, no dtype error."""
+    from vlmc.peft.lora import Linear
+    torch.manual_seed(3)
+    lin = Linear(96, 40, r=4, lora_alpha=16).cuda().to(wdtype)
+    lin.lora_A.float(); lin.lora_B.float()
+    lin.lora_B.weight.data.normal_(0, 0.1)
+    lin.mask = torch.rand(40, 96, device="cuda") < 0.5
+    lin.sparse = True
+    x = torch.randn(2, 7, 96, device="cuda", requires_grad=True)
+    with torch.autocast("cuda", dtype=acdtype):
+        y = lin(x)
+        loss = (y.float() ** 2).sum()
+    loss.backward()
+    got = (y.detach().float(), x.grad.clone(), lin.lora_A.weight.grad.clone(), lin.lora_B.weight.grad.clone())
+    x2 = x.detach().clone().requires_grad_(True)
+    A, B = lin.lora_A.weight.detach().clone().requires_grad_(True), lin.lora_B.weight.detach().clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=acdtype):
+        w_eff = (lin.weight + (B @ A).to(wdtype) * lin.scaling) * lin.mask
+        y2 = torch.nn.functional.linear(x2, w_eff, lin.bias)
+        if y2.dtype != wdtype:
+            y2 = y2.to(wdtype)
+        loss2 = (y2.float() ** 2).sum()
+    loss2.backward()
+    tol = 3e-2 if acdtype == torch.bfloat16 else 5e-3
+    for a, b, nm in zip(got, (y2.detach().float(), x2.grad, A.grad, B.grad), ("y", "dx", "dA", "dB")):
+        assert a.dtype == b.dtype or nm == "y", nm
+        err = float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6))
+        assert err < tol, (nm, err)
+
+
+def test_lora_train_eval_merge_semantics(native):
+    """lora.py:334-358: train(False) with merge_weights folds B@A into W WITHOUT the mask and marks the layer merged,
+    train(True) takes it out again; eval() only flips the flags."""
+    from vlmc.peft.lora import Linear
+    torch.manual_seed(4)
+    lin = Linear(64, 24, r=2, lora_alpha=16, merge_weights=True).cuda().half()
+    lin.lora_A.float(); lin.lora_B.float()
+    lin.lora_B.weight.data.normal_(0, 0.1)
+    W0 = lin.weight.data.clone()
+    want = (W0.float() + (lin.lora_B.weight @ lin.lora_A.weight) * lin.scaling).half()
+    lin.eval()
+    assert not lin.merged and torch.equal(lin.weight.data, W0) and not lin.training and not lin.lora_A.training
+    lin.train(False)
+    assert lin.merged and torch.equal(lin.weight.data, want)
+    lin.train(True)
+    assert not lin.merged and lin.training and lin.lora_A.training
+    assert float((lin.weight.data.float() - W0.float()).abs().max()) <= 2.0 ** -10 * float(W0.abs().max())
 
 
 # ------------------------------------------------------------------------------------------- K15 / K16 (SURVEY 8f-2)

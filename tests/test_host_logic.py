@@ -236,3 +236,30 @@ def test_global_allocation_has_no_cpu_path(built_lib):
         native.importance_accum([torch.zeros(4)], [torch.ones(4)], "obd")
     with pytest.raises(IndexError):                       # topk(k = 0)[0][-1] on the reference side
         ls.get_mask(scores, 0.0, 1.0)
+
+
+def test_stack_calibration_groups_equal_shapes(built_lib):
+    """layerwise.stack_calibration: consecutive samples of equal shape become one chunk, per-sample tensors
+    are concatenated, shared / constant arguments pass through, ragged samples keep the reference's one-by-one schedule."""
+    import torch
+    from vlmc.compression.pruners.layerwise import stack_calibration
+    shared = torch.zeros(1, 4, 8, 8)
+    inps = [torch.full((1, 8, 16), float(j)) for j in range(5)] + [torch.ones(1, 6, 16)]
+    caches = [{"attention_mask": torch.full((1, 1, 8, 8), float(j)), "position_ids": torch.arange(8)[None],
+               "bias": shared, "flag": False, "__args__": (None, torch.full((1, 3), float(j)), 7)} for j in range(5)]
+    caches.append({"attention_mask": torch.zeros(1, 1, 6, 6), "position_ids": torch.arange(6)[None], "bias": shared,
+                   "flag": False, "__args__": (None, torch.zeros(1, 3), 7)})
+    xs, cs, counts = stack_calibration(inps, caches, 4)
+    assert counts == [4, 1, 1] and [tuple(x.shape) for x in xs] == [(4, 8, 16), (1, 8, 16), (1, 6, 16)]
+    assert torch.equal(xs[0][:, 0, 0], torch.arange(4.0))
+    assert cs[0]["attention_mask"].shape == (4, 1, 8, 8) and torch.equal(cs[0]["attention_mask"][:, 0, 0, 0], torch.arange(4.0))
+    assert cs[0]["position_ids"].shape == (4, 8) and cs[0]["bias"] is shared and cs[0]["flag"] is False
+    assert cs[0]["__args__"][0] is None and cs[0]["__args__"][1].shape == (4, 3) and cs[0]["__args__"][2] == 7
+    assert cs[1] is caches[4] and cs[2] is caches[5]
+    # calib_batch = 1: untouched
+    xs1, cs1, counts1 = stack_calibration(inps, caches, 1)
+    assert counts1 == [1] * 6 and all(a is b for a, b in zip(xs1, inps))
+    # a per-sample python argument that differs cannot be stacked: the run is halved until it can
+    caches[1]["flag"] = True
+    _, _, counts2 = stack_calibration(inps, caches, 4)
+    assert counts2[0] == 1 and sum(counts2) == 6

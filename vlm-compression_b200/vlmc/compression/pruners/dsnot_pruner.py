@@ -41,8 +41,15 @@ class WrappedGPT:
         if self.mean.dim() == 1:      # the reference's mean / var become [C, 1] after the first call (:89-93)
             self.mean = self.mean.reshape(-1, 1)
             self.var = self.var.reshape(-1, 1)
-        native.dsnot_stats(inp, self.scaler_row, self.sum_metric_row, self.mean, self.var, self.nsamples, b,
-                           self.ntokens)
+        # a chunk of K stacked calibration samples (layerwise.stack_calibration) is K reference calls: var is the
+        # token-weighted mean of per-CALL biased variances (:92), so the kernel treats the chunk as K segments
+        calls = int(getattr(self, "_stacked_calls", 1) or 1)
+        if calls > 1 and b % calls == 0:
+            native.dsnot_stats(inp, self.scaler_row, self.sum_metric_row, self.mean, self.var, self.nsamples,
+                               b // calls, self.ntokens, nseg=calls)
+        else:
+            native.dsnot_stats(inp, self.scaler_row, self.sum_metric_row, self.mean, self.var, self.nsamples, b,
+                               self.ntokens)
         self.ntokens += ntok
         self.nsamples += b
 

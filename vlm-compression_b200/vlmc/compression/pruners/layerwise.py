@@ -151,6 +151,69 @@ def capture_block_inputs(pruner, model, dataloader, model_prefix, n_samples, mod
     return inps, [None] * len(inps), caches
 
 
+def _stack_values(vals, sizes):
+    """One cache entry of several calibration samples -> the entry of the stacked call, or raises _NotStackable.
+    Tensors whose leading dimension is the sample's batch dimension are concatenated; anything else (None, flags,
+    a tensor shared by every sample) must be the same for all samples."""
+    first = vals[0]
+    if isinstance(first, torch.Tensor):
+        if all(isinstance(v, torch.Tensor) and v.shape == first.shape and v.dtype == first.dtype for v in vals):
+            if all(v is first for v in vals):
+                if first.dim() == 0 or first.shape[0] == 1:
+                    return first                           # one tensor for every sample: broadcasts over the batch
+            if first.dim() >= 1 and all(v.shape[0] == n for v, n in zip(vals, sizes)):
+                return torch.cat(vals, dim=0)
+        raise _NotStackable
+    if isinstance(first, (tuple, list)):
+        if not all(isinstance(v, type(first)) and len(v) == len(first) for v in vals):
+            raise _NotStackable
+        return type(first)(_stack_values([v[i] for v in vals], sizes) for i in range(len(first)))
+    if all((v is first) or (type(v) is type(first) and v == first) for v in vals):
+        return first
+    raise _NotStackable
+
+
+class _NotStackable(Exception):
+    pass
+
+
+def stack_calibration(inps, caches, calib_batch):
+    """Groups consecutive calibration samples of identical shape into chunks of up to `calib_batch` samples
+    (batch the calibration set).  Returns (chunk inputs, chunk caches, samples per chunk).  The block then
+    runs once per chunk and every hook hands its wrapper ONE [K*b, S, C] tensor: one statistics launch (and, for
+    SparseGPT, one read-modify-write of H) per chunk instead of per sample.  Samples that cannot be stacked (ragged
+    sequence lengths, per-sample python arguments) stay chunks of one, i.e. the reference's schedule."""
+    if calib_batch <= 1:
+        return list(inps), list(caches), [1] * len(inps)
+    xs, cs, counts = [], [], []
+    j = 0
+    while j < len(inps):
+        grp = [j]
+        while len(grp) < calib_batch and j + len(grp) < len(inps) and inps[j + len(grp)].shape == inps[j].shape \
+                and inps[j + len(grp)].dtype == inps[j].dtype:
+            grp.append(j + len(grp))
+        cache = None
+        while len(grp) > 1:
+            try:
+                sizes = [inps[g].shape[0] for g in grp]
+                keys = caches[grp[0]].keys()
+                if any(caches[g].keys() != keys for g in grp):
+                    raise _NotStackable
+                cache = {k: _stack_values([caches[g][k] for g in grp], sizes) for k in keys}
+                break
+            except _NotStackable:
+                grp = grp[:len(grp) // 2]                  # retry with a shorter run
+        if len(grp) == 1:
+            xs.append(inps[j])
+            cs.append(caches[j])
+        else:
+            xs.append(torch.cat([inps[g] for g in grp], dim=0))
+            cs.append(cache)
+        counts.append(len(grp))
+        j += len(grp)
+    return xs, cs, counts
+
+
 def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_samples, sparsity_ratio,
                  lora_model, vit, make_wrapper, prune_linear, replay_all_args=False):
     stem = getattr(model, model_prefix, None)
@@ -163,11 +226,20 @@ def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_s
                                                   module_to_process, lora_model, vit, replay_all_args)
     n_samples = min(n_samples, len(inps))
     layers = get_module_recursive(model, module_to_process)
+    expected_nsamples = len(inps) * inps[0].shape[0]
+    # calibration batching: the block runs on chunks of stacked samples (calib_batch = 1 restores the reference's
+    # one-sample-per-forward schedule, wanda_pruner.py:308-311)
+    inps, caches, counts = stack_calibration(inps[:n_samples], caches[:n_samples],
+                                             int(getattr(pruner, "calib_batch", 1) or 1))
+    outs = [None] * len(inps)
+    n_samples = len(inps)                                  # from here on: number of chunks
 
     share = InputSharing() if getattr(pruner, "share_inputs", True) else None
+    current = {"calls": 1}
 
     def run_block(layer):
         for j in range(n_samples):
+            current["calls"] = counts[j]
             if share is not None:
                 share.begin_forward()
             with torch.no_grad():
@@ -190,6 +262,9 @@ def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_s
         def make_hook(nm):
             def hook(_, inp, out):
                 if share is None or share.route(nm, inp[0]):
+                    # DSnoT's var is a mean of PER-CALL variances: its wrapper splits a stacked chunk back into the
+                    # reference's calls (vlmc_dsnot_stats nseg); the other wrappers take any batch size
+                    wrapped[nm]._stacked_calls = current["calls"]
                     wrapped[nm].add_batch(inp[0].data, out.data)
             return hook
         handles = [subset[name].register_forward_hook(make_hook(name)) for name in wrapped]
@@ -202,8 +277,15 @@ def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_s
                 adopt_statistics(wrapped[follower], wrapped[leader])
         for name in subset:
             key = f"{module_to_process}.{i}.{name}.weight"
-            prune_linear(i, name, subset[name], wrapped[name], sparsity_ratio[key],
-                         expected_nsamples=len(inps) * inps[0].shape[0])
+            try:
+                sparsity = sparsity_ratio[key]
+            except KeyError:
+                # the reference reads the per-linear ratio only in its unstructured branch (wanda_pruner.py:333): an
+                # n:m run must not fail on a sparsity_dict that lacks this linear
+                if getattr(pruner, "prune_n", 0) == 0:
+                    raise
+                sparsity = None
+            prune_linear(i, name, subset[name], wrapped[name], sparsity, expected_nsamples=expected_nsamples)
         pruner.finish_block(subset, wrapped)
         run_block(layer)
         inps, outs = outs, inps

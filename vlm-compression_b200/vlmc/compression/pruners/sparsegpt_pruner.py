@@ -91,7 +91,8 @@ class BLIPT5LayerSparseGPTPruner(BLIPT5LayerWandaPruner):
     def _prune_linear(self, vit, lora_model):
         def fn(i, name, module, wrapper, sparsity, expected_nsamples):
             assert wrapper.nsamples == expected_nsamples
-            self._pending.append((wrapper, sparsity))               # pruned together in finish_block
+            # n:m runs never read the ratio (sparsegpt_pruner.py:176-187): a missing sparsity_dict entry arrives as None
+            self._pending.append((wrapper, 0.0 if sparsity is None else sparsity))      # pruned together in finish_block
         return fn
 
     def finish_block(self, subset, wrapped):

@@ -24,15 +24,21 @@ class _MaskedLoRALinear(torch.autograd.Function):
     """y = F.linear(x, W_eff, bias) with W_eff = (W + s*BA) * M (sparse) or W * M + s*BA (lora.py:364-375).
     W_eff is rebuilt in backward (one K15 pass) instead of being kept alive between forward and backward."""
 
+    # custom_fwd / custom_bwd: backward runs under the autocast state of forward, so with fp32 LoRA'd weights under
+    # maybe_autocast(), or fp16 weights under bf16 autocast, gy (autocast dtype) meets w_eff (weight dtype) inside an
+    # autocast region exactly like the reference's plain-autograd F.linear does
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, x, W, A, B, bias, mask, scaling, sparse):
         Af, Bf = A.detach().float(), B.detach().float()
         w_eff = native.sparselora_effective_weight(W.detach(), Af, Bf, scaling, mask, sparse)
         ctx.save_for_backward(x, W, A, B, mask)
         ctx.scaling, ctx.sparse, ctx.has_bias = scaling, sparse, bias is not None
+        ctx.bias_dtype = bias.dtype if bias is not None else None
         return F.linear(x, w_eff, bias)
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gy):
         x, W, A, B, mask = ctx.saved_tensors
         Af, Bf = A.detach().float(), B.detach().float()
@@ -40,7 +46,8 @@ class _MaskedLoRALinear(torch.autograd.Function):
         gy2 = gy.reshape(-1, gy.shape[-1])
         if ctx.needs_input_grad[0]:
             w_eff = native.sparselora_effective_weight(W.detach(), Af, Bf, ctx.scaling, mask, ctx.sparse)
-            gx = (gy2 @ w_eff).reshape(x.shape)
+            gx = (gy2 @ (w_eff if w_eff.dtype == gy2.dtype or torch.is_autocast_enabled() else w_eff.to(gy2.dtype)))
+            gx = gx.reshape(x.shape).to(x.dtype)
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
             G = gy2.t() @ x.reshape(-1, x.shape[-1]).to(gy2.dtype)          # dL/dW_eff, in the layer's dtype like autograd
             if G.dtype != W.dtype:
@@ -48,7 +55,7 @@ class _MaskedLoRALinear(torch.autograd.Function):
             dA, dB = native.sparselora_lora_grads(G.contiguous(), Af, Bf, ctx.scaling, mask, ctx.sparse)
             dA, dB = dA.to(A.dtype), dB.to(B.dtype)
         if ctx.has_bias and ctx.needs_input_grad[4]:
-            gbias = gy2.sum(0)
+            gbias = gy2.sum(0).to(ctx.bias_dtype)
         return gx, None, dA, dB, gbias, None, None, None
 
 
@@ -88,6 +95,38 @@ class Linear(nn.Linear, LoraLayer):
             nn.init.kaiming_uniform_(self.lora_A.weight, a=math.sqrt(5))
             nn.init.zeros_(self.lora_B.weight)
 
+    def _merge_dense_delta(self, sign):
+        """W += sign * scaling * B@A on the whole matrix (lora.py:340-353: train(False) merges WITHOUT the mask)."""
+        if self.fan_in_fan_out:
+            raise NotImplementedError("fan_in_fan_out weights are not on the InstructBLIP path")
+        native.sparselora_merge(self.weight.data, self.lora_A.weight.data.float(), self.lora_B.weight.data.float(),
+                                sign * self.scaling, torch.ones_like(self.mask), remask=False)
+
+    def train(self, mode=True):
+        """lora.py:334-353: with merge_weights, train(False) folds B@A into W and marks the layer merged (the plain
+        F.linear path then runs), train(True) takes it out again."""
+        nn.Linear.train(self, mode)
+        if hasattr(self, "lora_A"):
+            self.lora_A.train(mode)
+            self.lora_B.train(mode)
+        if not mode and self.merge_weights and not self.merged:
+            if self.r > 0:
+                self._merge_dense_delta(+1.0)
+            self.merged = True
+        elif self.merge_weights and self.merged:
+            if self.r > 0:
+                self._merge_dense_delta(-1.0)
+            self.merged = False
+        return self
+
+    def eval(self):
+        """lora.py:355-358: only flips the training flags (no merge, unlike train(False))."""
+        nn.Linear.train(self, False)
+        if hasattr(self, "lora_A"):
+            self.lora_A.train(False)
+            self.lora_B.train(False)
+        return self
+
     def forward(self, x, dense=False):
         previous_dtype = self.weight.dtype
         if dense or self.disable_adapters or not (self.r > 0 and not self.merged):
@@ -99,7 +138,9 @@ class Linear(nn.Linear, LoraLayer):
             if not self.weight.is_cuda:
                 raise RuntimeError("vlmc has no CPU path: the masked LoRA forward needs CUDA tensors "
                                    f"(got device {self.weight.device})")
-            result = _MaskedLoRALinear.apply(x.to(previous_dtype) if x.dtype != previous_dtype else x, self.weight,
+            if x.dtype != previous_dtype and not torch.is_autocast_enabled():
+                x = x.to(previous_dtype)
+            result = _MaskedLoRALinear.apply(x, self.weight,
                                              self.lora_A.weight, self.lora_B.weight, self.bias, self.mask,
                                              float(self.scaling), bool(self.sparse))
         if result.dtype != previous_dtype:
@@ -117,10 +158,9 @@ class Linear(nn.Linear, LoraLayer):
         else:
             # dense-delta branch (lora.py:388-391): W[~mask] = 0 ; W += B@A * scaling  -- same kernel run
             # with an all-ones merge mask after the re-mask
-            self.weight.data[~self.mask] = 0
-            ones = torch.ones_like(self.mask)
             native.sparselora_merge(self.weight.data, self.lora_A.weight.data.float(),
-                                    self.lora_B.weight.data.float(), self.scaling, ones, remask=False)
+                                    self.lora_B.weight.data.float(), 0.0, self.mask, remask=True)       # W[~mask] = 0
+            self._merge_dense_delta(+1.0)
         self.reset_peft()
 
 
