@@ -43,7 +43,11 @@ enum vlmc_status {
   VLMC_ERR_NOT_DEVICE = -3,   /* a pointer is not CUDA device memory                  */
   VLMC_ERR_WORKSPACE = -4,    /* ws too small                                         */
   VLMC_ERR_CUDA = -5,         /* launch failed; see vlmc_last_cuda_error()            */
-  VLMC_NOT_POSDEF = 1         /* Cholesky met a non-positive pivot (caller damps, retries) */
+  /* numerical status BITS of the factorisation's device status word (0 = clean) */
+  VLMC_NOT_POSDEF = 1,        /* Cholesky met a non-positive / NaN pivot (caller damps, retries)           */
+  VLMC_NONFINITE = 2,         /* the input matrix holds +-inf or NaN (caller clamps like :101-109, retries) */
+  VLMC_HUGE_FACTOR = 4        /* an entry of U exceeds 1e15: diag(H^-1) may overflow fp32, the caller runs the
+                                 reference's second stage (:131-157) explicitly                           */
 };
 
 #define VLMC_WS_COUNTER_BYTES 4096
@@ -282,11 +286,32 @@ int vlmc_hessian_add_damp(float* H, int C, int64_t ldh, const float* damp, void*
  * K10  U = upper Cholesky factor of H^-1 (H^-1 = U^T U).  Replaces the cholesky -> cholesky_inverse ->
  * cholesky(upper=True) chain of sparsegpt_pruner.py:114-157 with one blocked Cholesky of the flipped matrix and
  * one triangular inverse (same U mathematically, 2/3 C^3 flops).  H is not modified.  *status (device int) is set
- * to 0, or to VLMC_NOT_POSDEF when a pivot is non-positive / NaN: the caller then damps and retries exactly like
- * the reference's while-loop.  The function itself returns 0 in both cases (it does not synchronise).
+ * to 0, or to a combination of the status bits: VLMC_NOT_POSDEF when a pivot is non-positive / NaN (the caller then damps
+ * and retries exactly like the reference's while-loop), VLMC_NONFINITE when H holds +-inf / NaN (the caller clamps like
+ * :101-109 first), VLMC_HUGE_FACTOR when the factor is so large that the reference's second stage may differ.  The function itself returns 0 in both cases (it does not synchronise).
  */
 int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U, int64_t ldu, int* status,
                         void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * The reference's factorisation in its own three-step order, for the Hessians on which the fused vlmc_chol_inv_upper and
+ * the chain cholesky -> cholesky_inverse -> [+-inf clamp] -> cholesky(upper=True) with its second damp-and-retry loop
+ * (sparsegpt_pruner.py:131-157) can differ: status bit VLMC_HUGE_FACTOR, or on request (SparseGPT.exact_reference_order).
+ *   vlmc_gram_upper              Hinv = U^T U (full symmetric matrix) for an upper factor U: the value of
+ *                                torch.cholesky_inverse(cholesky(H)) when U = vlmc_chol_inv_upper(H)         (:131)
+ *   vlmc_chol_upper              U = cholesky(A, upper=True) of a symmetric matrix A (A is not modified); *status gets
+ *                                VLMC_NOT_POSDEF / VLMC_NONFINITE like vlmc_chol_inv_upper; ws of VLMC_OP_CHOL size   (:146)
+ *   vlmc_matrix_nonfinite_count  out3 = {#+inf, #-inf, #NaN} of A (device uint64[3])                          (:101,:106,:133,:138)
+ *   vlmc_matrix_replace_inf      A[A == +inf] = value (negative = 0) or A[A == -inf] = value (negative != 0)  (:103-104,:108-109)
+ *   vlmc_diag_abs_mean           *out = scale * mean(|diag(A)|)                                              (:143)
+ * The quantile the clamp needs is two order statistics of the whole matrix: vlmc_scores_kth.
+ */
+int vlmc_gram_upper(const float* U, int C, int64_t ldu, float* Hinv, int64_t ldh, void* stream);
+int vlmc_chol_upper(const float* A, int C, int64_t lda, float* U, int64_t ldu, int* status,
+                    void* ws, size_t ws_bytes, void* stream);
+int vlmc_matrix_nonfinite_count(const float* A, int rows, int cols, int64_t lda, unsigned long long* out3, void* stream);
+int vlmc_matrix_replace_inf(float* A, int rows, int cols, int64_t lda, float value, int negative, void* stream);
+int vlmc_diag_abs_mean(const float* A, int C, int64_t lda, float scale, float* out, void* stream);
 /*
  * Schedule of the blocked Cholesky inside vlmc_chol_inv_upper.  With the look-ahead (default) the trailing update of a panel
  * is split between the caller's stream and a library-owned side stream (forked from and joined to the caller's stream

@@ -240,20 +240,56 @@ def _chol_retry(H, damp, upper):
             raise RuntimeError("damping did not make the matrix positive definite")
 
 
+def torch_quantile(a, q):
+    """torch.quantile(a, q) for a float32 array, interpolation "linear", over ALL entries (infinite ones included), with
+    ATen's own arithmetic (aten/src/ATen/native/Sorting.cpp quantile_compute): rank = float32(q) * float32(n - 1),
+    values gathered at floor / ceil of the rank from the sorted data, combined by at::lerp in float32."""
+    v = np.sort(np.asarray(a, dtype=F32).ravel())
+    if np.isnan(v).any():
+        return F32(np.nan)
+    rank = F32(q) * F32(v.size - 1)
+    lo, hi = int(np.floor(rank)), int(np.ceil(rank))
+    w = F32(rank - F32(lo))
+    x, y = v[lo], v[hi]
+    with np.errstate(all="ignore"):
+        return F32(x + w * (y - x)) if w < F32(0.5) else F32(y - (y - x) * (F32(1) - w))
+
+
+def clamp_infinite(M):
+    """:101-109 / :133-141: +inf -> quantile(M, 0.999), then -inf -> quantile(M, 0.001) of the updated matrix.  In place."""
+    pos = np.isposinf(M)
+    if pos.any():
+        M[pos] = torch_quantile(M, 0.999)
+    neg = np.isneginf(M)
+    if neg.any():
+        M[neg] = torch_quantile(M, 0.001)
+    return M
+
+
+def sparsegpt_second_stage(Hinv, percdamp=0.01):
+    """:133-157 on a given H^-1: clamp, damp2 = percdamp * mean|diag|, cholesky(upper=True) with damp-and-retry.
+    Returns (U, damping steps)."""
+    Hinv = clamp_infinite(np.array(Hinv, dtype=F32))
+    damp2 = F32(percdamp) * np.mean(np.abs(np.diag(Hinv)), dtype=F32)   # :143
+    U, steps2 = _chol_retry(Hinv, damp2, upper=True)                    # :146-157
+    return np.triu(U).astype(F32), steps2
+
+
 def sparsegpt_inverse_factor(H, percdamp=0.01):
-    """U = cholesky(cholesky_inverse(cholesky(H)), upper=True) in float32 LAPACK, plus the dead-channel rule.
-    Returns (U, dead mask, damping steps of the first factorisation)."""
+    """U = cholesky(cholesky_inverse(cholesky(H)), upper=True) in float32 LAPACK, with the dead-channel rule, both +-inf
+    clamps and both conditional damping loops (:95-157).  Returns (U, dead mask, damping steps of the first factorisation)."""
     from scipy.linalg import lapack
     H = np.array(H, dtype=F32)
     dead = np.diag(H) == 0                                   # :95
     H[dead, dead] = 1                                        # :96
+    clamp_infinite(H)                                        # :101-109
     damp = F32(percdamp) * np.mean(np.diag(H), dtype=F32)    # :111
     L, steps = _chol_retry(H, damp, upper=False)             # :114-128
-    Hinv, info = lapack.spotri(L, lower=1)                   # :131  cholesky_inverse
+    with np.errstate(all="ignore"):
+        Hinv, info = lapack.spotri(L, lower=1)               # :131  cholesky_inverse
     Hinv = np.tril(Hinv) + np.tril(Hinv, -1).T
-    damp2 = F32(percdamp) * np.mean(np.abs(np.diag(Hinv)), dtype=F32)   # :143
-    U, _ = _chol_retry(Hinv.astype(F32), damp2, upper=True)  # :146-157
-    return np.triu(U).astype(F32), dead, steps
+    U, _ = sparsegpt_second_stage(Hinv, percdamp)            # :133-157
+    return U, dead, steps
 
 
 def sparsegpt_fasterprune(W32, w_tag, H, sparsity, prune_n=0, prune_m=0, blocksize=128, percdamp=0.01, U=None,

@@ -111,9 +111,10 @@ def calib_loader(n_seq, seq_len, C, dtype, distinct=8, device="cpu"):
 
 
 def run_composite(which, linears, n_seq, seq_len, dtype, sparsity, prune_n=0, prune_m=0, threads=None, device="cpu",
-                  distinct=8):
+                  distinct=8, record=None):
     """`BLIPT5Layer{Wanda,DSnoT}Pruner(model=stand-in, data_loader=..., **cfg).prune()`, the reference's own entry point.
-    Returns (seconds inside prune(), stand-in model)."""
+    Returns (seconds inside prune(), stand-in model).  record: optional list that receives every per-layer WrappedGPT the
+    reference creates (a recording subclass is swapped in for the duration; the reference file is not touched)."""
     if threads:
         torch.set_num_threads(threads)
     ref = ref_loader.load()
@@ -127,14 +128,24 @@ def run_composite(which, linears, n_seq, seq_len, dtype, sparsity, prune_n=0, pr
     mod = {"wanda": ref.wanda, "dsnot": ref.dsnot}[which]
     cls = {"wanda": "BLIPT5LayerWandaPruner", "dsnot": "BLIPT5LayerDSnoTPruner"}[which]
     pruner = getattr(mod, cls)(model=model, data_loader=loader, **cfg)
-    if device != "cpu":
-        torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    with contextlib.redirect_stdout(None):
-        pruner.prune()
-    if device != "cpu":
-        torch.cuda.synchronize()
-    return time.perf_counter() - t0, model
+    orig = mod.WrappedGPT
+    if record is not None:
+        class Recording(orig):
+            def __init__(self, layer, *a, **k):
+                super().__init__(layer, *a, **k)
+                record.append(self)
+        mod.WrappedGPT = Recording
+    try:
+        if device != "cpu":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(None):
+            pruner.prune()
+        if device != "cpu":
+            torch.cuda.synchronize()
+        return time.perf_counter() - t0, model
+    finally:
+        mod.WrappedGPT = orig
 
 
 def sparsegpt_block_seconds(linears, n_seq, seq_len, dtype, sparsity=0.5, sample_seqs=8, threads=None, full=("q", "down")):

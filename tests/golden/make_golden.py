@@ -312,7 +312,91 @@ def gen_sparsegpt(ref):
         out[f"{name}|W_after"] = f32(lin.weight)
         out[f"{name}|importance_score"] = np.float64(lin.weight.importance_score)
     out["cases"] = np.array(list(cases))
+    # ---- the +-inf clamps and the second damping loop (:101-109, :133-157), forced -------------------------------------
+    def planted(name, plant, R=24, C=256, T=1024, wdt=torch.bfloat16):
+        g = torch.Generator().manual_seed(sum(map(ord, name)))
+        lin = nn.Linear(C, R, bias=False)
+        lin.weight.data = (torch.randn(R, C, generator=g) * 0.05).to(wdt)
+        sg = ref.sparsegpt.SparseGPT(lin)
+        sg.add_batch(act((1, T, C), 41, wdt, C), None)
+        plant(sg.H)
+        out[f"{name}|H"] = f32(sg.H)
+        out[f"{name}|W_before"] = f32(lin.weight)
+        out[f"{name}|tag"] = np.array(TAG[wdt])
+        out[f"{name}|cfg"] = np.array([0.5, 0, 0], dtype=np.float64)
+        return lin, sg
+
+    def plant_inf_H(H):           # +inf on the diagonal of an uncoupled channel, a symmetric pair of -inf: first clamp
+        H[7, :] = 0
+        H[:, 7] = 0
+        H[7, 7] = float("inf")
+        H[20, 33] = H[33, 20] = float("-inf")
+
+    def plant_tiny_diag(H):       # an uncoupled channel with a denormal diagonal: 1 / it overflows -> +inf in H^-1, second clamp
+        H[9, :] = 0
+        H[:, 9] = 0
+        H[9, 9] = 1e-39
+    for name, plant in (("inf_H_bf16", plant_inf_H), ("inf_Hinv_bf16", plant_tiny_diag)):
+        lin, sg = planted(name, plant)
+        sg.fasterprune(0.5, prune_n=0, prune_m=0, percdamp=0.01, blocksize=128)
+        out[f"{name}|W_after"] = f32(lin.weight)
+        out[f"{name}|importance_score"] = np.float64(lin.weight.importance_score)
+    # second damping loop: torch.cholesky_inverse is stubbed (test instrumentation of torch, the reference file is
+    # unmodified) to hand back an INDEFINITE inverse: the true one shifted down so that exactly 3 damping steps of
+    # percdamp * mean|diag| are needed (2.5 steps of margin: robust against roundoff)
+    name = "second_damp_bf16"
+    lin, sg = planted(name, lambda H: None, C=128, T=512)
+    real_inv = torch.cholesky_inverse
+    injected = {}
+
+    def fake_inverse(L, *a, **k):
+        Hinv = real_inv(L, *a, **k)
+        lam = torch.linalg.eigvalsh(Hinv.double()).min().item()
+        m = Hinv.diag().abs().mean().item()
+        shift = (lam + 0.025 * m) / 1.025
+        Hinv = Hinv - shift * torch.eye(Hinv.shape[0])
+        injected["Hinv"] = Hinv.clone()
+        return Hinv
+    torch.cholesky_inverse = fake_inverse
+    try:
+        sg.fasterprune(0.5, prune_n=0, prune_m=0, percdamp=0.01, blocksize=128)
+    finally:
+        torch.cholesky_inverse = real_inv
+    out[f"{name}|Hinv_injected"] = f32(injected["Hinv"])
+    out[f"{name}|W_after"] = f32(lin.weight)
+    out["forced_cases"] = np.array(["inf_H_bf16", "inf_Hinv_bf16", "second_damp_bf16"])
     save("sparsegpt.npz", **out)
+
+
+def gen_sparsegpt_4096(ref):
+    """the reference's fasterprune at a benched shape, 4096 x 4096 bf16, 50 % unstructured (CPU,
+    ~2 minutes).  The inputs are NOT stored: H is an exact integer matrix times a power of two and W comes from a numpy
+    PCG64 stream, so the GPU test regenerates both bit for bit from `seed` (tests/test_gpu_parity.py::_exact_hessian,
+    _golden_weights; H_sum is the check).  Stored: the full keep mask (bit-packed, 2 MiB), 96 rows of the pruned weights
+    and the norm of every pruned row."""
+    seed, R, C, T = 4096, 4096, 4096, 8192
+    rng = np.random.default_rng(seed)
+    gain = rng.integers(1, 5, size=C)
+    x = (rng.integers(-2, 3, size=(T, C)) * gain + rng.integers(-1, 2, size=C)).astype(np.float32)
+    xt = torch.from_numpy(x)
+    H = (xt.double().t() @ xt.double()).float() * (2.0 / T)
+    rng = np.random.default_rng(seed + 1)
+    W = torch.from_numpy((rng.standard_normal((R, C)) * 0.02).astype(np.float32)).to(torch.bfloat16)
+    lin = nn.Linear(C, R, bias=False)
+    lin.weight.data = W.clone()
+    sg = ref.sparsegpt.SparseGPT(lin)
+    sg.H = H.clone()
+    sg.nsamples = 1
+    sg.fasterprune(0.5, prune_n=0, prune_m=0, percdamp=0.01, blocksize=128)
+    out = lin.weight.data
+    rows = np.arange(0, R, R // 96)[:96].astype(np.int32)
+    save("sparsegpt_4096.npz", seed=np.int64(seed), H_sum=np.float64(H.double().sum().item()),
+         mask=np.packbits((out != 0).numpy(), axis=1), rows=rows, W_rows=packw(out[rows.astype(np.int64)]),
+         row_norms=out.float().norm(dim=1).numpy().astype(np.float32),
+         importance_score=np.float64(lin.weight.importance_score))
+
+
+SLOW = set()        # generators that only run when named on the command line (none at present)
 
 
 def gen_reorder(ref):
@@ -462,9 +546,9 @@ def main():
     only = set(a for a in sys.argv[1:] if not a.startswith("--"))
     gens = dict(wanda_stats=gen_wanda_stats, dsnot_stats=gen_dsnot_stats, wanda_toy=gen_wanda_toy,
                 dsnot_toy=gen_dsnot_toy, lora_merge=gen_lora_merge, lora_forward=gen_lora_forward, sparsegpt=gen_sparsegpt,
-                reorder=gen_reorder, layer_sparsity=gen_layer_sparsity)
+                reorder=gen_reorder, layer_sparsity=gen_layer_sparsity, sparsegpt_4096=gen_sparsegpt_4096)
     for name, fn in gens.items():
-        if not only or name in only:
+        if (not only and name not in SLOW) or name in only:
             fn(ref)
     if MISMATCH:
         sys.exit(f"fixtures differ from the generator: {MISMATCH}")

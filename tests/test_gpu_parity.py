@@ -712,6 +712,197 @@ def test_sparsegpt_full_size_properties(native):
     assert err_obs < 0.8 * err_mag
 
 
+# ------------------------------------------------------------------------------------------- SparseGPT at the benched shapes
+def _xtx_fp64(x, n_total, chunk=8192):
+    """(2 / n_total) X^T X in float64 on the GPU, chunked over tokens (test-only cross-check)."""
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C)
+    H = torch.zeros(C, C, dtype=torch.float64, device=x.device)
+    for t0 in range(0, x2.shape[0], chunk):
+        xc = x2[t0:t0 + chunk].double()
+        H.addmm_(xc.t(), xc)
+    return H * (2.0 / n_total)
+
+
+def _big_acts(n_seq, S, C, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    gain = torch.exp(torch.rand(C, device="cuda", generator=g) * 2.77 - 1.386)
+    off = torch.randn(C, device="cuda", generator=g) * 0.3
+    x = torch.empty(n_seq, S, C, device="cuda", dtype=torch.float16)
+    for j in range(n_seq):
+        x[j] = (torch.randn(S, C, device="cuda", generator=g) * gain + off).half()
+    return x
+
+
+@pytest.mark.parametrize("slab_tokens", [0, 16384])
+def test_hessian_c11008_slab_path_vs_fp64(native, slab_tokens):
+    """the C = 11008 launch the bench times goes through the token-slab path (default slab 65,536
+    tokens for C >= 8192).  T = 3 x 65,536 + 2048 fp16 tokens (three full slabs and a ragged one) in ONE call, with the
+    default slab and with a forced small one, against X^T X in float64: 1e-5 in max norm, Frobenius norm and per element."""
+    C, S = 11008, 2048
+    n_seq = 3 * 32 + 1
+    x = _big_acts(n_seq, S, C, 21)
+    H = torch.zeros(C, C, device="cuda")
+    native.hessian_accum(x, H, 0, n_seq, slab_tokens=slab_tokens)
+    truth = _xtx_fp64(x, n_seq)
+    del x
+    d = (H.double() - truth).abs()
+    scale = float(truth.abs().max())
+    assert float(d.max()) / scale < REL
+    assert float(d.norm() / truth.norm()) < REL
+    big = truth.abs() > 1e-2 * scale
+    assert float((d[big] / truth.abs()[big]).max()) < REL
+    assert torch.equal(H, H.t())
+    # a second call continues the running average (n_before > 0) on the same path
+    x2 = _big_acts(8, S, C, 22)
+    native.hessian_accum(x2, H, n_seq, 8, slab_tokens=slab_tokens)
+    truth2 = truth * (n_seq / (n_seq + 8)) + _xtx_fp64(x2, n_seq + 8)
+    assert float((H.double() - truth2).abs().max() / truth2.abs().max()) < REL
+
+
+@pytest.mark.parametrize("C", [4096, 11008])
+def test_chol_inv_upper_full_size_vs_fp64(native, C):
+    """the factorisation at the benched widths against torch.linalg.cholesky(inv(H.double()),
+    upper=True) on the same GPU (test-only cross-check)."""
+    x = _big_acts(max(2, (3 * C) // 2048), 2048, C, 23)
+    H = torch.zeros(C, C, device="cuda")
+    native.hessian_accum(x, H, 0, x.shape[0])
+    del x
+    H0 = H.clone()
+    U, status = native.chol_inv_upper(H)
+    assert int(status.item()) == 0 and torch.equal(H, H0)
+    assert float(U.tril(-1).abs().max()) == 0.0
+    Uref = torch.linalg.cholesky(torch.linalg.inv(H.double()), upper=True)
+    err = float((U.double() - Uref).abs().max() / Uref.abs().max())
+    print(f"chol_inv_upper C={C}: max-norm error vs fp64 {err:.2e}")
+    assert err < 1e-5
+    # H^-1 = U^T U reproduces the inverse
+    ident = (U.double().t() @ U.double()) @ H.double()
+    assert float((ident - torch.eye(C, dtype=torch.float64, device="cuda")).abs().max()) < 1e-3
+
+
+def _exact_hessian(C, T, seed, device):
+    """A Hessian that every platform reproduces bit for bit: small-integer activations (|x| <= 8) make X^T X an exact
+    integer matrix in any summation order; the 2 / T scale is a power of two."""
+    rng = np.random.default_rng(seed)
+    gain = rng.integers(1, 5, size=C)
+    x = (rng.integers(-2, 3, size=(T, C)) * gain + rng.integers(-1, 2, size=C)).astype(np.float32)
+    xt = torch.from_numpy(x).to(device)
+    H = (xt.double().t() @ xt.double()).float() * (2.0 / T)
+    return H
+
+
+def _golden_weights(R, C, seed):
+    rng = np.random.default_rng(seed)
+    return torch.from_numpy((rng.standard_normal((R, C)) * 0.02).astype(np.float32)).to(torch.bfloat16)
+
+
+def test_sparsegpt_reference_golden_4096(native):
+    """the unmodified reference's fasterprune on a 4096 x 4096 bf16 linear (CPU, generated by
+    tests/golden/make_golden.py sparsegpt_4096; inputs are regenerated here from seeds, see _exact_hessian) replayed
+    through SparseGPT.fasterprune: >= 99.9 % mask agreement on the full mask, <= 1e-3 relative Frobenius on the stored
+    rows and on the per-row norms of all rows."""
+    g = gu.load("sparsegpt_4096.npz")
+    R = C = 4096
+    H = _exact_hessian(C, 8192, int(g["seed"]), "cuda")
+    assert float(H.double().sum()) == float(g["H_sum"])               # the regenerated Hessian is the generator's
+    W = _golden_weights(R, C, int(g["seed"]) + 1).cuda()
+    lin = torch.nn.Linear(C, R, bias=False).cuda().to(torch.bfloat16)
+    lin.weight.data.copy_(W)
+    from vlmc.compression.pruners.sparsegpt_pruner import SparseGPT
+    sg = SparseGPT(lin)
+    sg.H = H
+    sg.nsamples = 1
+    sg.fasterprune(0.5, percdamp=0.01, blocksize=128)
+    got = lin.weight.data.float()
+    keep_ref = torch.from_numpy(np.unpackbits(g["mask"], axis=1)[:, :C].astype(bool)).cuda()
+    agree = float(((got != 0) == keep_ref).float().mean())
+    print(f"4096x4096 reference golden: mask agreement {agree:.6f}")
+    assert agree >= 0.999
+    rows = torch.from_numpy(g["rows"].astype(np.int64)).cuda()
+    ref_rows = torch.from_numpy(gu.unpack_w(g["W_rows"], "bf16")).cuda()
+    assert float((got[rows] - ref_rows).norm() / ref_rows.norm()) < 1e-3
+    ref_norms = torch.from_numpy(g["row_norms"]).cuda()
+    assert float((got.norm(dim=1) - ref_norms).abs().max() / ref_norms.max()) < 1e-3
+
+
+def _live_reference():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("the unmodified reference files are not on this box (oracle/fetch_ref.py -> baseline/_ref)")
+    return ref_loader.load()
+
+
+@pytest.mark.parametrize("R,C,sp,n,m", [(4096, 4096, 0.5, 0, 0), (4096, 4096, 0.0, 2, 4), (1024, 11008, 0.5, 0, 0)])
+def test_sparsegpt_against_the_live_reference_on_this_gpu(native, R, C, sp, n, m):
+    """The unmodified reference's SparseGPT class (baseline/_ref) with its tensors on THIS GPU (torch eager, cuSOLVER) beside
+    vlmc's, same H and W, at the benched widths: <= 1e-3 relative Frobenius, >= 99.9 % mask agreement (north_star)."""
+    ref = _live_reference()
+    x = _big_acts(max(2, (3 * C) // 2048), 2048, C, 29)
+    lin_r = torch.nn.Linear(C, R, bias=False).cuda().half()
+    lin_r.weight.data = (torch.randn(R, C, device="cuda", generator=torch.Generator(device="cuda").manual_seed(31)) * 0.02).half()
+    lin_v = torch.nn.Linear(C, R, bias=False).cuda().half()
+    lin_v.weight.data.copy_(lin_r.weight.data)
+    from vlmc.compression.pruners.sparsegpt_pruner import SparseGPT
+    sr, sv = ref.sparsegpt.SparseGPT(lin_r), SparseGPT(lin_v)
+    for j in range(x.shape[0]):
+        sr.add_batch(x[j:j + 1], None)
+    sv.add_batch(x, None)
+    assert sr.nsamples == sv.nsamples
+    Hr = sr.H
+    assert float((sv.H.double() - Hr.double()).abs().max() / Hr.double().abs().max()) < REL
+    sv.H = Hr.clone()                                   # the sweeps are compared on the SAME Hessian
+    del x
+    sr.fasterprune(sp, prune_n=n, prune_m=m, percdamp=0.01, blocksize=128)
+    sv.fasterprune(sp, prune_n=n, prune_m=m, percdamp=0.01, blocksize=128)
+    a, b = lin_v.weight.data.float(), lin_r.weight.data.float()
+    agree = float(((a == 0) == (b == 0)).float().mean())
+    fro = float((a - b).norm() / b.norm())
+    print(f"live reference {R}x{C} sp={sp} {n}:{m}: mask agreement {agree:.6f}, rel Frobenius {fro:.2e}")
+    if n == 0:
+        assert agree >= 0.999 and fro < 1e-3
+    else:
+        # torch.topk's tie-break inside 2:4 groups is implementation-defined (SURVEY F8): ties are rare on real scores
+        assert agree >= 0.999 and fro < 2e-3
+    assert abs(lin_v.weight.importance_score - lin_r.weight.importance_score) < 1e-3 * abs(lin_r.weight.importance_score)
+
+
+@pytest.mark.parametrize("method", ["wanda", "dsnot"])
+def test_wanda_and_dsnot_against_the_live_reference_on_this_gpu(native, method):
+    """The unmodified composite pruner (baseline/_ref, torch eager on this GPU) on the no-GEMM stand-in block at Vicuna
+    widths (rows cut to 512 per linear to bound the test) beside the vlmc wrappers + kernels on the same weights and
+    activations: statistics within 1e-5, masks bit-exact (the stable per-row sort has no free tie-break)."""
+    _live_reference()
+    from oracle import ref_arm
+    from vlmc.compression.pruners import dsnot_pruner, wanda_pruner
+    linears = [(nm, 512, C, inp) for nm, _, C, inp in ref_arm.VICUNA_BLOCK]
+    n_seq, S = 6, 2048
+    sp = 0.5 if method == "wanda" else 0.6
+    rec = []
+    _, model = ref_arm.run_composite(method, linears, n_seq, S, torch.float16, sp, device="cuda", distinct=3, record=rec)
+    blk = model.llm_model.model.layers[0]
+    by_layer = {id(w.layer): w for w in rec}
+    fresh = ref_arm.NoGemmBlock(linears, S, torch.float16, distinct=3, device="cuda")       # same seeds: same data
+    loader = ref_arm.calib_loader(n_seq, S, 4096, torch.float16, 3, "cuda")
+    stats = ["scaler_row"] if method == "wanda" else ["scaler_row", "sum_metric_row", "mean", "var"]
+    for name, R, C, inp in linears:
+        lin, ref_lin = fresh.linear(name), blk.linear(name)
+        rw = by_layer[id(ref_lin)]
+        wr = wanda_pruner.WrappedGPT(lin) if method == "wanda" else dsnot_pruner.WrappedGPT(lin)
+        for j in range(n_seq):
+            wr.add_batch(loader[j]["x"] if inp == "attn_in" else fresh.acts[inp][j % 3], None)
+        for st in stats:                                   # our statistics against the reference's: 1e-5
+            a, b = getattr(wr, st).reshape(-1).double(), getattr(rw, st).reshape(-1).double()
+            assert float((a - b).abs().max() / b.abs().max()) < REL, (name, st)
+            getattr(wr, st).reshape(-1).copy_(getattr(rw, st).reshape(-1))      # selection on IDENTICAL statistics
+        if method == "wanda":
+            wanda_pruner.wanda_prune_linear(lin, wr.scaler_row, sp)
+        else:
+            dsnot_pruner.dsnot_prune_linear(lin, wr, sp)
+        assert torch.equal(lin.mask, ref_lin.mask), (name, int((lin.mask != ref_lin.mask).sum()))
+        assert torch.equal(lin.weight.data, ref_lin.weight.data), name
+
+
 # ------------------------------------------------------------------------------------------- K8 + K9 DSnoT refine
 def _dsnot_stats(C, seed, positive=False):
     g = torch.Generator().manual_seed(seed)
@@ -1013,6 +1204,112 @@ def test_shared_inputs_give_the_per_linear_result(native, name, monkeypatch):
     assert masks_per.keys() == masks_shared.keys()
     for k in masks_per:
         assert torch.equal(masks_per[k], masks_shared[k]), k
+
+
+# ------------------------------------------------------------------------------------------- K10: clamps + second stage
+def _sg_on(W32, tag, H):
+    from vlmc.compression.pruners.sparsegpt_pruner import SparseGPT
+    R, C = W32.shape
+    lin = torch.nn.Linear(C, R, bias=False).cuda().to(DT[tag])
+    lin.weight.data.copy_(gu.to_torch(W32, tag, "cuda"))
+    sg = SparseGPT(lin)
+    sg.H = torch.from_numpy(np.ascontiguousarray(H)).cuda()
+    sg.nsamples = 1
+    return lin, sg
+
+
+def _close_to_reference(lin, ref):
+    got = lin.weight.data.float().cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-3
+    assert ((got == 0) == (ref == 0)).mean() >= 0.999
+
+
+@pytest.mark.parametrize("name", ["inf_H_bf16", "inf_Hinv_bf16"])
+def test_sparsegpt_inf_clamps_golden(native, name):
+    """sparsegpt_pruner.py:101-109 / :133-141 (VERDICT r1 missing #1): +-inf planted in H takes the first clamp (status bit
+    VLMC_NONFINITE -> quantile clamp -> retry); a denormal diagonal makes H^-1 overflow, the factor is flagged
+    (VLMC_HUGE_FACTOR) and the explicit second stage clamps it.  Weights against the unmodified reference's."""
+    g = gu.load("sparsegpt.npz")
+    lin, sg = _sg_on(g[f"{name}|W_before"], str(g[f"{name}|tag"]), g[f"{name}|H"])
+    Hd = sg.H
+    U, status = native.chol_inv_upper(Hd.clone())
+    want_bit = native.NONFINITE if name == "inf_H_bf16" else native.HUGE_FACTOR
+    assert int(status.item()) & want_bit
+    sg.fasterprune(0.5, percdamp=0.01, blocksize=128)
+    _close_to_reference(lin, g[f"{name}|W_after"])
+
+
+def test_matrix_quantile_equals_torch_quantile(native):
+    """native.matrix_quantile (two order statistics from the radix select + torch's float32 rank arithmetic) is
+    torch.quantile, infinite entries included, and also works past torch's 16 M element limit."""
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for n_side in (96, 512, 2048):
+        A = torch.randn(n_side, n_side, device="cuda", generator=g) * 50
+        A.view(-1)[torch.randint(0, A.numel(), (5,), device="cuda", generator=g)] = float("inf")
+        A.view(-1)[torch.randint(0, A.numel(), (3,), device="cuda", generator=g)] = float("-inf")
+        for q in (0.999, 0.001, 0.5):
+            assert native.matrix_quantile(A, q) == torch.quantile(A, q).item(), (n_side, q)
+        pos, neg, nan = native.matrix_nonfinite_count(A)
+        assert (pos, neg, nan) == (int(torch.isposinf(A).sum()), int(torch.isneginf(A).sum()), 0)
+    A = torch.randn(4200, 4200, device="cuda", generator=g)              # 17.6 M entries: torch.quantile refuses
+    want = torch.sort(A.view(-1))[0]
+    rank = np.float32(0.999) * np.float32(A.numel() - 1)
+    lo = int(np.floor(rank))
+    assert want[lo].item() <= native.matrix_quantile(A, 0.999) <= want[lo + 1].item()
+    A[5, 5] = float("nan")
+    assert native.matrix_nonfinite_count(A)[2] == 1
+
+
+def test_sparsegpt_second_damping_loop_golden(native):
+    """sparsegpt_pruner.py:143-157: the indefinite H^-1 the fixture injected into the reference goes through
+    vlmc_chol_upper with the damp-and-retry loop (3 steps, like the reference), then the sweep: reference weights."""
+    from vlmc import schedule
+    g = gu.load("sparsegpt.npz")
+    name = "second_damp_bf16"
+    Hinv = torch.from_numpy(g[f"{name}|Hinv_injected"].copy()).cuda()
+    U = torch.empty_like(Hinv)
+    steps = schedule.second_stage_from_inverse(Hinv, U, 0.01)
+    assert steps == 3
+    Uo, _ = oracle.sparsegpt_second_stage(g[f"{name}|Hinv_injected"], 0.01)
+    assert rel_inf(U.cpu().numpy(), Uo) < 1e-4
+    W = gu.to_torch(g[f"{name}|W_before"], "bf16", "cuda")
+    native.obs_sweep(W, U, 0.5)
+    ref = g[f"{name}|W_after"]
+    got = W.float().cpu().numpy()
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-3 and ((got == 0) == (ref == 0)).mean() >= 0.999
+
+
+@pytest.mark.parametrize("C", [256, 1000, 2048])
+def test_three_step_order_equals_fused_factor(native, C):
+    """chol_inv_upper (fused) against the reference's explicit order built from vlmc_gram_upper + vlmc_chol_upper, and both
+    against float64: the same U to 1e-5 on a well conditioned Hessian; exact_reference_order prunes to the same weights."""
+    from vlmc import schedule
+    x = acts(4 * C, C, 17, torch.float32).cuda()
+    H = (x.t().double() @ x.double() * (2.0 / x.shape[0])).float()
+    U, st = native.chol_inv_upper(H)
+    assert int(st.item()) == 0
+    U3 = U.clone()
+    assert schedule.second_stage(U3, 0.01) == 0
+    want = torch.linalg.cholesky(torch.linalg.inv(H.double()), upper=True)
+    scale = float(want.abs().max())
+    assert float((U.double() - want).abs().max()) / scale < 2e-5
+    assert float((U3.double() - want).abs().max()) / scale < 2e-5
+    assert bool((torch.tril(U3, -1) == 0).all())
+    A = H.clone()
+    Uc, st = native.chol_upper(A)
+    assert int(st.item()) == 0 and torch.equal(A, H)
+    wantc = torch.linalg.cholesky(H.double(), upper=True)
+    assert float((Uc.double() - wantc).abs().max()) / float(wantc.abs().max()) < 2e-5
+    W = weights(64, C, 5, torch.float16).cuda()
+    lin_a, sg_a = _sg_on(W.float().cpu().numpy(), "f16", H.cpu().numpy())
+    lin_b, sg_b = _sg_on(W.float().cpu().numpy(), "f16", H.cpu().numpy())
+    sg_b.exact_reference_order = True
+    sg_a.fasterprune(0.5)
+    sg_b.fasterprune(0.5)
+    a, b = lin_a.weight.data.float(), lin_b.weight.data.float()
+    assert float(((a == 0) == (b == 0)).float().mean()) >= 0.999
+    assert float((a - b).norm() / a.norm()) < 1e-3
 
 
 def test_stacked_chunk_statistics_equal_per_sample_calls(native):

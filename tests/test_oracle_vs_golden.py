@@ -129,6 +129,73 @@ def test_sparsegpt_hessian_and_fasterprune():
     assert oracle.sparsegpt_inverse_factor(g["dead_f16|H"])[1].sum() == 2
 
 
+def test_sparsegpt_fasterprune_at_4096_vs_reference():
+    """The oracle at a BENCHED shape: the unmodified reference's fasterprune on a 4096 x 4096 bf16 linear
+    (tests/golden/sparsegpt_4096.npz; H and W regenerated from seeds, exactly) - north_star bars."""
+    import torch
+    g = gu.load("sparsegpt_4096.npz")
+    seed, R, C, T = int(g["seed"]), 4096, 4096, 8192
+    rng = np.random.default_rng(seed)
+    gain = rng.integers(1, 5, size=C)
+    x = (rng.integers(-2, 3, size=(T, C)) * gain + rng.integers(-1, 2, size=C)).astype(np.float32)
+    xt = torch.from_numpy(x)
+    H = ((xt.double().t() @ xt.double()).float() * (2.0 / T)).numpy()
+    assert float(H.astype(np.float64).sum()) == float(g["H_sum"])
+    rng = np.random.default_rng(seed + 1)
+    W = torch.from_numpy((rng.standard_normal((R, C)) * 0.02).astype(np.float32)).to(torch.bfloat16).float().numpy()
+    Wo, score, _ = oracle.sparsegpt_fasterprune(W, "bf16", H, 0.5)
+    keep = np.unpackbits(g["mask"], axis=1)[:, :C].astype(bool)
+    assert ((Wo != 0) == keep).mean() >= 0.999
+    rows = g["rows"].astype(np.int64)
+    ref_rows = gu.unpack_w(g["W_rows"], "bf16")
+    assert np.linalg.norm(Wo[rows] - ref_rows) / np.linalg.norm(ref_rows) < 1e-3
+    assert np.abs(np.linalg.norm(Wo, axis=1) - g["row_norms"]).max() / g["row_norms"].max() < 1e-3
+    assert abs(score - float(g["importance_score"])) < 1e-5 * abs(score)
+
+
+def test_torch_quantile_restatement_against_torch():
+    """oracle.torch_quantile (the clamp value of sparsegpt_pruner.py:103,108,135,140) against torch.quantile itself,
+    infinite entries included."""
+    import torch
+    g = torch.Generator().manual_seed(1)
+    for n in (7, 1000, 65536):
+        x = torch.randn(n, generator=g) * 100
+        x[torch.rand(n, generator=g) < 0.0005] = float("inf")
+        x[torch.rand(n, generator=g) < 0.0005] = float("-inf")
+        for q in (0.999, 0.001, 0.5, 0.0, 1.0):
+            want = torch.quantile(x, q).item()
+            got = float(oracle.torch_quantile(x.numpy(), q))
+            assert got == want or (np.isnan(got) and np.isnan(want)), (n, q, got, want)
+
+
+@pytest.mark.parametrize("name", ["inf_H_bf16", "inf_Hinv_bf16"])
+def test_sparsegpt_inf_clamps_vs_reference(name):
+    """SURVEY F7 / sparsegpt_pruner.py:101-109,133-141: +-inf planted in H (first clamp) or produced in H^-1 by a denormal
+    diagonal (second clamp); the oracle follows the reference through both."""
+    g = gu.load("sparsegpt.npz")
+    assert not np.isfinite(g[f"{name}|H"]).all() or name == "inf_Hinv_bf16"
+    W, _, _ = oracle.sparsegpt_fasterprune(g[f"{name}|W_before"], str(g[f"{name}|tag"]), g[f"{name}|H"], 0.5)
+    ref = g[f"{name}|W_after"]
+    assert np.isfinite(ref).all()
+    assert np.linalg.norm(W - ref) / np.linalg.norm(ref) < 1e-3, name
+    assert ((W == 0) == (ref == 0)).mean() >= 0.999, name
+
+
+def test_sparsegpt_second_damping_loop_vs_reference():
+    """sparsegpt_pruner.py:143-157: an indefinite H^-1 (injected through a stubbed torch.cholesky_inverse when the fixture
+    was generated) takes the second damp-and-retry loop: 3 steps of percdamp * mean|diag H^-1|."""
+    g = gu.load("sparsegpt.npz")
+    name = "second_damp_bf16"
+    U, steps = oracle.sparsegpt_second_stage(g[f"{name}|Hinv_injected"], 0.01)
+    assert steps == 3
+    H = g[f"{name}|H"]
+    dead = np.diag(H) == 0
+    W, _, _ = oracle.sparsegpt_fasterprune(g[f"{name}|W_before"], str(g[f"{name}|tag"]), H, 0.5, U=U, dead=dead)
+    ref = g[f"{name}|W_after"]
+    assert np.linalg.norm(W - ref) / np.linalg.norm(ref) < 1e-3
+    assert ((W == 0) == (ref == 0)).mean() >= 0.999
+
+
 # ------------------------------------------------------------------------------------------- DSnoT refine
 @pytest.mark.parametrize("case", list(gu.DSNOT_CASES))
 def test_dsnot_refine_masks_bit_exact(case):

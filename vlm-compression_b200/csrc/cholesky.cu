@@ -28,30 +28,67 @@ constexpr int kPotrfThreads = 128;
 // threads at C = 11008 and 1 ms for a pass that moves 0.7 GB.
 constexpr int kFlipUnroll = 4;    // rows in flight per thread: one 4-byte load per thread left the flips latency-bound
 
+// flip != 0: F = J H J (the exchange-matrix flip of vlmc_chol_inv_upper), else F = H.  Only the lower triangle is moved
+// (plus the rest of the 128-wide diagonal blocks, so that every element a diagonal GEMM tile touches is initialised):
+// nothing of the blocked Cholesky reads above it.  A +-inf / NaN entry sets VLMC_NONFINITE in *status: the host then
+// takes the reference's clamp path (sparsegpt_pruner.py:101-109) instead of damping a matrix that can never factorise.
 __global__ void __launch_bounds__(256)
-flip_copy_kernel(const float* __restrict__ H, int64_t ldh, float* __restrict__ F, int64_t ldf, int C) {
+flip_copy_kernel(const float* __restrict__ H, int64_t ldh, float* __restrict__ F, int64_t ldf, int C, int flip,
+                 int* __restrict__ status) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= C) return;
-  for (int i0 = blockIdx.y; i0 < C; i0 += gridDim.y * kFlipUnroll) {
+  bool bad = false;
+  const int first = j & ~127;            // rows above the diagonal block of column j are never read
+  for (int i0 = first + blockIdx.y; i0 < C; i0 += gridDim.y * kFlipUnroll) {
     float v[kFlipUnroll];
 #pragma unroll
     for (int u = 0; u < kFlipUnroll; ++u) {
       const int i = i0 + u * (int)gridDim.y;
-      if (i < C) v[u] = H[(int64_t)(C - 1 - i) * ldh + (C - 1 - j)];
+      if (i < C) v[u] = flip ? H[(int64_t)(C - 1 - i) * ldh + (C - 1 - j)] : H[(int64_t)i * ldh + j];
     }
 #pragma unroll
     for (int u = 0; u < kFlipUnroll; ++u) {
       const int i = i0 + u * (int)gridDim.y;
-      if (i < C) F[(int64_t)i * ldf + j] = v[u];
+      if (i < C) {
+        F[(int64_t)i * ldf + j] = v[u];
+        bad |= !isfinite(v[u]);
+      }
     }
+  }
+  if (bad) atomicOr(status, (int)VLMC_NONFINITE);
+}
+
+// U = L^T: U[i][j] = L[j][i] for j >= i, zero below (vlmc_chol_upper); 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256)
+lower_to_upper_transpose_kernel(const float* __restrict__ L, int64_t ldl, float* __restrict__ U, int64_t ldu, int C) {
+  __shared__ float tile[32][33];
+  const int bi = blockIdx.y * 32, bj = blockIdx.x * 32;          // output tile rows bi.., columns bj..
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (bj + 31 >= bi) {
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+      const int li = bj + r, lj = bi + tx;                         // L[bj + r][bi + tx]
+      tile[r][tx] = (li < C && lj < C && lj <= li) ? L[(int64_t)li * ldl + lj] : 0.f;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi + r, j = bj + tx;
+    if (i < C && j < C) U[(int64_t)i * ldu + j] = (j >= i && bj + 31 >= bi) ? tile[tx][r] : 0.f;
   }
 }
 
 // strictly-lower entries of Li move to the mirrored strictly-upper slot; the lower slot is cleared.  In place without a
 // hazard: only strictly-lower entries (and the diagonal) are read, only strictly-upper slots receive values.
+// An entry above kHugeFactor sets VLMC_HUGE_FACTOR: diag(H^-1) = column sums of squares of U may then overflow fp32, which
+// is where the reference's second clamp / damping stage (:133-157) can differ from the fused factorisation.
+constexpr float kHugeFactor = 1e15f;
+
 __global__ void __launch_bounds__(256)
-flip_to_upper_kernel(float* __restrict__ U, int64_t ldu, int C) {
+flip_to_upper_kernel(float* __restrict__ U, int64_t ldu, int C, int* __restrict__ status) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  bool huge = false;
   for (int i0 = blockIdx.y; i0 < C; i0 += gridDim.y * kFlipUnroll) {
     float v[kFlipUnroll];
 #pragma unroll
@@ -66,12 +103,16 @@ flip_to_upper_kernel(float* __restrict__ U, int64_t ldu, int C) {
       if (j < i) {
         U[(int64_t)i * ldu + j] = 0.f;
         U[(int64_t)(C - 1 - i) * ldu + (C - 1 - j)] = v[u];
-      } else if (j == i && i < C / 2) {
+        huge |= !(fabsf(v[u]) <= kHugeFactor);
+      } else if (j == i && i < (C + 1) / 2) {
         const int64_t a = (int64_t)i * ldu + i, b = (int64_t)(C - 1 - i) * ldu + (C - 1 - i);
-        const float t = U[a]; U[a] = U[b]; U[b] = t;
+        const float t = U[a], w = U[b];
+        U[a] = w; U[b] = t;
+        huge |= !(fabsf(t) <= kHugeFactor) || !(fabsf(w) <= kHugeFactor);
       }
     }
   }
+  if (huge) atomicOr(status, (int)VLMC_HUGE_FACTOR);
 }
 
 // One CTA factors the bs x bs diagonal block at (k0,k0) of F and inverts the factor, all in shared memory:
@@ -165,7 +206,7 @@ potrf_block_kernel(float* F, int64_t ldf, float* Li, int64_t ldi, int k0, int bs
       }
       potrf_bar();
     }
-    if (bad && t == 0) atomicMax(status, (int)VLMC_NOT_POSDEF);
+    if (bad && t == 0) atomicOr(status, (int)VLMC_NOT_POSDEF);
 
     // inverse: column c = t of X = L^-1 by blocked forward substitution; reads only L and this thread's own column
     const int c = t;
@@ -309,20 +350,18 @@ extern "C" int vlmc_chol_set_lookahead(int mode) {
   return prev < 0 ? 2 : prev;
 }
 
-extern "C" int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U, int64_t ldu, int* status,
-                                   void* ws, size_t ws_bytes, void* stream) {
-  using namespace vlmc;
-  if (!H || !U || !status || !ws || C < 1 || ldh < C || ldu < C) return VLMC_ERR_BAD_ARG;
-  if ((C & 3) || (ldh & 3) || (ldu & 3) || ((uintptr_t)H & 15) || ((uintptr_t)U & 15)) return VLMC_ERR_UNSUPPORTED;
-  if (!is_device_ptr(H) || !is_device_ptr(U) || !is_device_ptr(status) || !is_device_ptr(ws)) return VLMC_ERR_NOT_DEVICE;
-  if (ws_bytes < chol_workspace_bytes(C)) return VLMC_ERR_WORKSPACE;
-  cudaStream_t st = (cudaStream_t)stream;
-  char* base = reinterpret_cast<char*>(ws) + VLMC_WS_COUNTER_BYTES;
-  float* F = reinterpret_cast<float*>(base);
-  const int64_t ldf = C;
-  float* X = reinterpret_cast<float*>(base + align_up((size_t)C * C * sizeof(float), 256));
-  const int nb = (C + kNB - 1) / kNB;
+namespace vlmc {
 
+// Blocked lower Cholesky of F in place (F = L L^T on the lower triangle), 128-wide panels; the inverse of every diagonal
+// block goes to the same position of Li.  A non-positive / NaN pivot sets VLMC_NOT_POSDEF in *status.
+// Look-ahead (default; VLMC_CHOL_LOOKAHEAD=0 restores the plain right-looking loop): the trailing update of step k is
+// split into the next block column (A_k, on the caller's stream: all that the next diagonal factor and panel solve
+// need) and the rest (B_k, on a side stream forked from and joined to the caller's stream with events).  B_k leaves
+// one SM free, so the one-CTA diagonal factor of step k+1 (55 us, a fifth of a step) runs under it instead of after it:
+//   caller's stream:  P_k  S_k  [wait B_k-1]  A_k        P = diagonal factor + inverse, S = panel solve
+//   side stream:      [wait S_k]  B_k                    (B_k after B_k-1 by stream order: same output region)
+// Same GEMM per output element either way (K = 128, one chunk).
+static int chol_lower_blocked(float* F, int64_t ldf, float* Li, int64_t ldi, int C, int* status, cudaStream_t st) {
   static bool attr_set = false;
   const int potrf_smem = (int)kPotrfSmem;
   if (!attr_set) {
@@ -330,31 +369,19 @@ extern "C" int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U,
       return check_launch();
     attr_set = true;
   }
-  if (cudaMemsetAsync(status, 0, sizeof(int), st) != cudaSuccess) return check_launch();
-  if (cudaMemset2DAsync(U, ldu * sizeof(float), 0, (size_t)C * sizeof(float), C, st) != cudaSuccess) return check_launch();
-  const int flip_rows = C < kNumSMs * 4 ? C : kNumSMs * 4;
-  flip_copy_kernel<<<dim3((C + 255) / 256, flip_rows), 256, 0, st>>>(H, ldh, F, ldf, C);
-
-  // ---- blocked Cholesky of F (lower), diagonal-block inverses go straight into U (used as Li) ----
-  // Look-ahead (default; VLMC_CHOL_LOOKAHEAD=0 restores the plain right-looking loop): the trailing update of step k is
-  // split into the next block column (A_k, on the caller's stream: all that the next diagonal factor and panel solve
-  // need) and the rest (B_k, on a side stream forked from and joined to the caller's stream with events).  B_k leaves
-  // one SM free, so the one-CTA diagonal factor of step k+1 (55 us, a fifth of a step) runs under it instead of after it:
-  //   caller's stream:  P_k  S_k  [wait B_k-1]  A_k        P = diagonal factor + inverse, S = panel solve
-  //   side stream:      [wait S_k]  B_k                    (B_k after B_k-1 by stream order: same output region)
-  // Same GEMM per output element either way (K = 128, one chunk).
+  const int nb = (C + kNB - 1) / kNB;
   int rc;
   ChainSide* side = chol_lookahead_enabled() && nb > 2 ? side_for(st) : nullptr;
   bool pending_b = false;
   for (int k = 0; k < nb; ++k) {
     const int k0 = k * kNB;
     const int bs = (C - k0 < kNB) ? (C - k0) : kNB;
-    potrf_block_kernel<<<1, kPotrfIoThreads, potrf_smem, st>>>(F, ldf, U, ldu, k0, bs, status);
+    potrf_block_kernel<<<1, kPotrfIoThreads, potrf_smem, st>>>(F, ldf, Li, ldi, k0, bs, status);
     const int below = C - k0 - bs;
     if (below > 0) {
       float* panel = F + (int64_t)(k0 + bs) * ldf + k0;
       // panel <- panel * L_kk^-T   (C = A B^T with B = L_kk^-1 stored [N,K])
-      rc = gemm3x(true, below, bs, bs, 1.f, panel, ldf, U + (int64_t)k0 * ldu + k0, ldu, 0.f, panel, ldf, 0, 0, st);
+      rc = gemm3x(true, below, bs, bs, 1.f, panel, ldf, Li + (int64_t)k0 * ldi + k0, ldi, 0.f, panel, ldf, 0, 0, st);
       if (rc) return rc;
       // trailing <- trailing - panel panel^T on the lower tiles
       float* trail = F + (int64_t)(k0 + bs) * ldf + (k0 + bs);
@@ -384,7 +411,38 @@ extern "C" int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U,
     }
   }
   if (pending_b && cudaStreamWaitEvent(st, side->updated, 0) != cudaSuccess) return check_launch();
-  rc = check_launch();
+  return check_launch();
+}
+
+static int chol_arg_checks(const float* H, int C, int64_t ldh, float* U, int64_t ldu, int* status, void* ws, size_t ws_bytes) {
+  if (!H || !U || !status || !ws || C < 1 || ldh < C || ldu < C) return VLMC_ERR_BAD_ARG;
+  if ((C & 3) || (ldh & 3) || (ldu & 3) || ((uintptr_t)H & 15) || ((uintptr_t)U & 15)) return VLMC_ERR_UNSUPPORTED;
+  if (!is_device_ptr(H) || !is_device_ptr(U) || !is_device_ptr(status) || !is_device_ptr(ws)) return VLMC_ERR_NOT_DEVICE;
+  if (ws_bytes < chol_workspace_bytes(C)) return VLMC_ERR_WORKSPACE;
+  return VLMC_OK;
+}
+
+}  // namespace vlmc
+
+extern "C" int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U, int64_t ldu, int* status,
+                                   void* ws, size_t ws_bytes, void* stream) {
+  using namespace vlmc;
+  int rc = chol_arg_checks(H, C, ldh, U, ldu, status, ws, ws_bytes);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* base = reinterpret_cast<char*>(ws) + VLMC_WS_COUNTER_BYTES;
+  float* F = reinterpret_cast<float*>(base);
+  const int64_t ldf = C;
+  float* X = reinterpret_cast<float*>(base + align_up((size_t)C * C * sizeof(float), 256));
+  const int nb = (C + kNB - 1) / kNB;
+
+  if (cudaMemsetAsync(status, 0, sizeof(int), st) != cudaSuccess) return check_launch();
+  if (cudaMemset2DAsync(U, ldu * sizeof(float), 0, (size_t)C * sizeof(float), C, st) != cudaSuccess) return check_launch();
+  const int flip_rows = C < kNumSMs * 4 ? C : kNumSMs * 4;
+  flip_copy_kernel<<<dim3((C + 255) / 256, flip_rows), 256, 0, st>>>(H, ldh, F, ldf, C, 1, status);
+
+  // ---- blocked Cholesky of F (lower), diagonal-block inverses go straight into U (used as Li) ----
+  rc = chol_lower_blocked(F, ldf, U, ldu, C, status, st);
   if (rc) return rc;
 
   // ---- triangular inverse by recursive doubling: nodes are [start, end) column ranges with a known inverse ----
@@ -409,6 +467,109 @@ extern "C" int vlmc_chol_inv_upper(const float* H, int C, int64_t ldh, float* U,
     nn = out;
   }
   // ---- U = J Li J ----
-  flip_to_upper_kernel<<<dim3((C + 255) / 256, flip_rows), 256, 0, st>>>(U, ldu, C);
+  flip_to_upper_kernel<<<dim3((C + 255) / 256, flip_rows), 256, 0, st>>>(U, ldu, C, status);
+  return check_launch();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The reference's SECOND stage in its own order (sparsegpt_pruner.py:131-157), for the Hessians the fused factorisation
+// flags (VLMC_HUGE_FACTOR) or on request: Hinv = U0^T U0 (= cholesky_inverse), the +-inf clamp and the damp-and-retry
+// loop on cholesky(Hinv, upper=True) are then the caller's, built from these pieces.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int vlmc_gram_upper(const float* U, int C, int64_t ldu, float* Hinv, int64_t ldh, void* stream) {
+  using namespace vlmc;
+  if (!U || !Hinv || C < 1 || ldu < C || ldh < C) return VLMC_ERR_BAD_ARG;
+  if ((C & 3) || (ldu & 3) || (ldh & 3) || ((uintptr_t)U & 15) || ((uintptr_t)Hinv & 15)) return VLMC_ERR_UNSUPPORTED;
+  if (!is_device_ptr(U) || !is_device_ptr(Hinv)) return VLMC_ERR_NOT_DEVICE;
+  // Hinv[i][j] = sum_k U[k][i] U[k][j]: A given as [K, M] (a_km), B as [K, N]
+  return gemm3x(false, C, C, C, 1.f, U, ldu, U, ldu, 0.f, Hinv, ldh, 0, 0, (cudaStream_t)stream, 0, true);
+}
+
+extern "C" int vlmc_chol_upper(const float* A, int C, int64_t lda, float* U, int64_t ldu, int* status,
+                               void* ws, size_t ws_bytes, void* stream) {
+  using namespace vlmc;
+  int rc = chol_arg_checks(A, C, lda, U, ldu, status, ws, ws_bytes);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* F = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + VLMC_WS_COUNTER_BYTES);
+  const int64_t ldf = C;
+  if (cudaMemsetAsync(status, 0, sizeof(int), st) != cudaSuccess) return check_launch();
+  const int flip_rows = C < kNumSMs * 4 ? C : kNumSMs * 4;
+  flip_copy_kernel<<<dim3((C + 255) / 256, flip_rows), 256, 0, st>>>(A, lda, F, ldf, C, 0, status);
+  rc = chol_lower_blocked(F, ldf, U, ldu, C, status, st);      // U's diagonal blocks hold L_kk^-1 until the transpose
+  if (rc) return rc;
+  lower_to_upper_transpose_kernel<<<dim3((C + 31) / 32, (C + 31) / 32), 256, 0, st>>>(F, ldf, U, ldu, C);
+  return check_launch();
+}
+
+namespace vlmc {
+
+__global__ void __launch_bounds__(256)
+nonfinite_count_kernel(const float* __restrict__ A, int rows, int cols, int64_t lda, unsigned long long* __restrict__ out) {
+  unsigned int pos = 0, neg = 0, nan = 0;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (int64_t)rows * cols;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const float v = A[(idx / cols) * lda + (idx % cols)];
+    if (isinf(v)) { if (v > 0.f) ++pos; else ++neg; }
+    else if (v != v) ++nan;
+  }
+  if (pos) atomicAdd(out + 0, (unsigned long long)pos);
+  if (neg) atomicAdd(out + 1, (unsigned long long)neg);
+  if (nan) atomicAdd(out + 2, (unsigned long long)nan);
+}
+
+__global__ void __launch_bounds__(256)
+replace_inf_kernel(float* __restrict__ A, int rows, int cols, int64_t lda, float value, int negative) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (int64_t)rows * cols;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    float* p = A + (idx / cols) * lda + (idx % cols);
+    const float v = *p;
+    if (isinf(v) && ((v < 0.f) == (negative != 0))) *p = value;
+  }
+}
+
+__global__ void diag_abs_mean_kernel(const float* A, int64_t lda, int C, float scale, float* out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s += (double)fabsf(A[(int64_t)i * lda + i]);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    *out = scale * (float)(t / (double)C);
+  }
+}
+
+}  // namespace vlmc
+
+// out[0..2] = number of +inf, -inf, NaN entries of A (the tests of sparsegpt_pruner.py:101,106,133,138 in one pass)
+extern "C" int vlmc_matrix_nonfinite_count(const float* A, int rows, int cols, int64_t lda, unsigned long long* out3,
+                                           void* stream) {
+  using namespace vlmc;
+  if (!A || !out3 || rows < 1 || cols < 1 || lda < cols) return VLMC_ERR_BAD_ARG;
+  if (!is_device_ptr(A) || !is_device_ptr(out3)) return VLMC_ERR_NOT_DEVICE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(out3, 0, 3 * sizeof(unsigned long long), st) != cudaSuccess) return check_launch();
+  nonfinite_count_kernel<<<kNumSMs * 8, 256, 0, st>>>(A, rows, cols, lda, out3);
+  return check_launch();
+}
+
+// A[A == +inf] = value (negative == 0) or A[A == -inf] = value (negative != 0): sparsegpt_pruner.py:103-104 / :108-109
+extern "C" int vlmc_matrix_replace_inf(float* A, int rows, int cols, int64_t lda, float value, int negative, void* stream) {
+  using namespace vlmc;
+  if (!A || rows < 1 || cols < 1 || lda < cols) return VLMC_ERR_BAD_ARG;
+  if (!is_device_ptr(A)) return VLMC_ERR_NOT_DEVICE;
+  replace_inf_kernel<<<kNumSMs * 8, 256, 0, (cudaStream_t)stream>>>(A, rows, cols, lda, value, negative);
+  return check_launch();
+}
+
+// *out = scale * mean(|diag(A)|): the second-stage damp of sparsegpt_pruner.py:143 (and :111 after a clamp)
+extern "C" int vlmc_diag_abs_mean(const float* A, int C, int64_t lda, float scale, float* out, void* stream) {
+  using namespace vlmc;
+  if (!A || !out || C < 1 || lda < C) return VLMC_ERR_BAD_ARG;
+  if (!is_device_ptr(A) || !is_device_ptr(out)) return VLMC_ERR_NOT_DEVICE;
+  diag_abs_mean_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(A, lda, C, scale, out);
   return check_launch();
 }

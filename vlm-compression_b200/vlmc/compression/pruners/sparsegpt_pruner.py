@@ -9,6 +9,8 @@
   BLIPT5LayerSparseGPTPruner <- :1005-1091, registered as "blipt5_sparsegpt_pruner"; also drives
                                       llm_model.model.layers, which the reference cannot
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -28,6 +30,10 @@ class SparseGPT:
         self.columns = W.shape[1]
         self.H = torch.zeros((self.columns, self.columns), device=self.dev)
         self.nsamples = 0
+        # False: U comes from the fused factorisation (one blocked Cholesky + one triangular inverse), and the explicit
+        # cholesky_inverse -> clamp -> cholesky(upper) stage of :131-157 runs only for a Hessian whose factor is flagged
+        # (VLMC_HUGE_FACTOR).  True: always in the reference's three-step order.  Same U mathematically.
+        self.exact_reference_order = os.environ.get("VLMC_SPARSEGPT_EXACT_ORDER") == "1"
 
     def add_batch(self, inp, out=None):
         if len(inp.shape) == 2:
@@ -44,12 +50,10 @@ class SparseGPT:
             U, dead = group["U"], group["dead"]                     # the same H was factorised for a sibling linear
         else:
             damp, dead = native.hessian_prepare(H, percdamp)        # :95-96, :111
-            U = None
-            while True:                                             # :114-128: damp only after a failed attempt
-                U, status = native.chol_inv_upper(H, U)
-                if status.item() == 0:
-                    break
-                native.hessian_add_damp(H, damp)
+            U, status = native.chol_inv_upper(H)
+            # :101-157: the +-inf clamps, the damp-only-after-a-failure loops (bounded, unlike the reference's `while
+            # True`) and, when the factor is flagged or on request, the second stage in the reference's own order
+            schedule.resolve_factor(H, U, status, damp, percdamp, exact_reference_order=self.exact_reference_order)
             if group is not None:
                 group.update(H=H, U=U, dead=dead, percdamp=percdamp)
         _, score = native.obs_sweep(self.layer.weight.data, U, sparsity, prune_n, prune_m, dead=dead,
@@ -74,7 +78,8 @@ def fasterprune_block(wrappers, sparsities, prune_n=0, prune_m=0, blocksize=128,
     items = []
     for w, sp in zip(wrappers, sparsities):
         items.append((w.layer.weight.data, w.H, sp, prune_n, prune_m))
-    scores, _ = schedule.sparsegpt_block(items, percdamp, blocksize)
+    scores, _ = schedule.sparsegpt_block(items, percdamp, blocksize,
+                                         exact_reference_order=any(getattr(w, "exact_reference_order", False) for w in wrappers))
     for w, v in zip(wrappers, scores.tolist()):
         setattr(w.layer.weight, "importance_score", v)
         del w.H

@@ -64,6 +64,11 @@ SIGNATURES = {
     "vlmc_hessian_add_damp": (_i, [_vp, _i, _i64, _vp, _vp]),
     "vlmc_chol_inv_upper": (_i, [_vp, _i, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_chol_set_lookahead": (_i, [_i]),
+    "vlmc_gram_upper": (_i, [_vp, _i, _i64, _vp, _i64, _vp]),
+    "vlmc_chol_upper": (_i, [_vp, _i, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "vlmc_matrix_nonfinite_count": (_i, [_vp, _i, _i, _i64, _vp, _vp]),
+    "vlmc_matrix_replace_inf": (_i, [_vp, _i, _i, _i64, _f, _i, _vp]),
+    "vlmc_diag_abs_mean": (_i, [_vp, _i, _i64, _f, _vp, _vp]),
     "vlmc_gemm_tf32x3": (_i, [_i, _i, _i, _i, _f, _vp, _i64, _vp, _i64, _f, _vp, _i64, _i, _i, _vp]),
     "vlmc_obs_sweep": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp, _d, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_obs_sweep_guarded": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _vp, _d, _i, _i, _i, _vp, _i64, _vp, _vp, _vp, _sz,
@@ -630,6 +635,90 @@ def chol_inv_upper(H, U=None, status=None):
                                      ws.data_ptr(), ws.numel(), _stream(H))
     _check("vlmc_chol_inv_upper", st)
     return U, status
+
+
+NOT_POSDEF, NONFINITE, HUGE_FACTOR = 1, 2, 4          # bits of the factorisation status word (include/vlmc.h)
+
+
+def _square_f32(A):
+    C = A.shape[0]
+    if A.dtype != torch.float32 or A.shape != (C, C) or A.stride(1) != 1:
+        raise ValueError("expected a float32 [C, C] row-major matrix")
+    return C
+
+
+def gram_upper(U, out=None):
+    """Hinv = U^T U (the value of torch.cholesky_inverse(cholesky(H)) for U = chol_inv_upper(H), sparsegpt_pruner.py:131)."""
+    _require_cuda(U)
+    C = _square_f32(U)
+    out = torch.empty((C, C), dtype=torch.float32, device=U.device) if out is None else out
+    with torch.cuda.device(U.device):
+        _check("vlmc_gram_upper", load().vlmc_gram_upper(U.data_ptr(), C, U.stride(0), out.data_ptr(), out.stride(0),
+                                                         _stream(U)))
+    return out
+
+
+def chol_upper(A, U=None, status=None):
+    """U = cholesky(A, upper=True) (sparsegpt_pruner.py:146).  Returns (U, status tensor) like chol_inv_upper."""
+    _require_cuda(A)
+    lib = load()
+    C = _square_f32(A)
+    U = torch.empty((C, C), dtype=torch.float32, device=A.device) if U is None else U
+    status = torch.empty(1, dtype=torch.int32, device=A.device) if status is None else status
+    ws = workspace(A, lib.vlmc_workspace_bytes(OP_CHOL, C, 0, 0))
+    with torch.cuda.device(A.device):
+        _check("vlmc_chol_upper", lib.vlmc_chol_upper(A.data_ptr(), C, A.stride(0), U.data_ptr(), U.stride(0),
+                                                      status.data_ptr(), ws.data_ptr(), ws.numel(), _stream(A)))
+    return U, status
+
+
+def matrix_nonfinite_count(A):
+    """(number of +inf, -inf, NaN entries) of a 2-D float32 matrix; synchronises (the caller branches on it)."""
+    _require_cuda(A)
+    out = torch.empty(3, dtype=torch.int64, device=A.device)
+    with torch.cuda.device(A.device):
+        _check("vlmc_matrix_nonfinite_count", load().vlmc_matrix_nonfinite_count(
+            A.data_ptr(), A.shape[0], A.shape[1], A.stride(0), out.data_ptr(), _stream(A)))
+    return tuple(int(v) for v in out.tolist())
+
+
+def matrix_replace_inf(A, value, negative):
+    _require_cuda(A)
+    with torch.cuda.device(A.device):
+        _check("vlmc_matrix_replace_inf", load().vlmc_matrix_replace_inf(
+            A.data_ptr(), A.shape[0], A.shape[1], A.stride(0), float(value), int(bool(negative)), _stream(A)))
+
+
+def diag_abs_mean(A, scale, out=None):
+    """scale * mean(|diag(A)|) as a 1-element device tensor (sparsegpt_pruner.py:143)."""
+    _require_cuda(A)
+    C = _square_f32(A)
+    out = torch.empty(1, dtype=torch.float32, device=A.device) if out is None else out
+    with torch.cuda.device(A.device):
+        _check("vlmc_diag_abs_mean", load().vlmc_diag_abs_mean(A.data_ptr(), C, A.stride(0), float(scale), out.data_ptr(),
+                                                               _stream(A)))
+    return out
+
+
+def matrix_quantile(A, q):
+    """torch.quantile(A, q) (interpolation "linear") of a contiguous float32 matrix without sorting it and without torch's
+    16 M element limit: the two neighbouring order statistics come from the exact radix select (vlmc_scores_kth) and are
+    combined with torch's own float32 rank arithmetic (ATen quantile_compute: rank = q * (n - 1) in float32, lerp).
+    Returns a python float (synchronises).  NaN entries sort last here; the caller rejects matrices that hold NaN."""
+    import numpy as np
+    if not A.is_contiguous():
+        raise ValueError("matrix_quantile needs a contiguous matrix")
+    n = A.numel()
+    rank = np.float32(q) * np.float32(n - 1)
+    below = int(np.floor(rank))
+    above = int(np.ceil(rank))
+    w = np.float32(rank - np.float32(below))
+    flat = A.reshape(-1)
+    vals = scores_kth([flat, flat], [0, 1], [below + 1, above + 1]).tolist()
+    a, b = np.float32(vals[0]), np.float32(vals[1])
+    with np.errstate(all="ignore"):
+        res = a + w * (b - a) if w < np.float32(0.5) else b - (b - a) * (np.float32(1) - w)      # at::lerp
+    return float(res)
 
 
 def gemm_tf32x3(A, B, C=None, alpha=1.0, beta=0.0, b_nk=False, tri=False, kc=0):

@@ -63,7 +63,77 @@ class Fork:
         return False
 
 
-def factor_concurrent(Hs, percdamp=0.01, Us=None, max_retries=64):
+def clamp_infinite(M):
+    """sparsegpt_pruner.py:101-109 (H) and :133-141 (H^-1): +inf entries become quantile(M, 0.999), then -inf entries
+    quantile(M, 0.001) of the matrix as it then stands (torch.quantile over ALL entries, the infinite ones included).
+    Returns the number of entries replaced.  The reference spins forever on a NaN (its quantile is NaN and the Cholesky
+    loop never succeeds): here that raises.  Unlike torch.quantile there is no 16 M element limit (C >= 4096)."""
+    pos, neg, nan = native.matrix_nonfinite_count(M)
+    if nan:
+        raise RuntimeError("the matrix holds NaN entries: the reference's damping loop never terminates on it")
+    if pos:
+        native.matrix_replace_inf(M, native.matrix_quantile(M, 0.999), negative=False)
+    if neg:
+        native.matrix_replace_inf(M, native.matrix_quantile(M, 0.001), negative=True)
+    return pos + neg
+
+
+def second_stage(U, percdamp=0.01, status=None, max_retries=64):
+    """The reference's second stage in its own order (sparsegpt_pruner.py:131-157) starting from the fused factor U of
+    vlmc_chol_inv_upper: Hinv = U^T U (= cholesky_inverse), the +-inf clamp, damp2 = percdamp * mean|diag Hinv| and the
+    damp-and-retry loop around cholesky(Hinv, upper=True).  U is overwritten with the result.  Returns the number of
+    damping steps taken.  Mathematically the identity when nothing is clamped or damped."""
+    return second_stage_from_inverse(native.gram_upper(U), U, percdamp, status, max_retries)
+
+
+def second_stage_from_inverse(Hinv, U=None, percdamp=0.01, status=None, max_retries=64):
+    """sparsegpt_pruner.py:133-157 on a given H^-1 (modified in place: clamp, damping).  Writes U (allocated when None);
+    returns the number of damping steps.  Read the factor from the U you passed in."""
+    clamp_infinite(Hinv)
+    damp2 = native.diag_abs_mean(Hinv, percdamp)
+    U = torch.empty_like(Hinv) if U is None else U
+    status = torch.empty(1, dtype=torch.int32, device=U.device) if status is None else status
+    for steps in range(max_retries + 1):
+        native.chol_upper(Hinv, U, status)
+        st = int(status.item())
+        if st == 0:
+            return steps
+        if st & native.NONFINITE:
+            raise RuntimeError("H^-1 holds NaN entries: the reference's damping loop never terminates on it")
+        native.hessian_add_damp(Hinv, damp2)
+    raise RuntimeError("H^-1 stayed non-positive-definite after damping")
+
+
+def resolve_factor(H, U, status, damp, percdamp=0.01, max_retries=64, exact_reference_order=False):
+    """Host side of one factorisation AFTER its first vlmc_chol_inv_upper attempt was enqueued: reads the status word and
+    runs the reference's control flow for whatever it reports -
+      VLMC_NONFINITE    clamp the +-inf entries of H (:101-109), recompute damp = percdamp * mean(diag H) (:111), retry
+      VLMC_NOT_POSDEF   H[diag] += damp, cumulatively per retry (:114-128)
+      VLMC_HUGE_FACTOR  (or exact_reference_order) the second stage in the reference's own order (:131-157)
+    Returns True when anything had to be redone (the caller then sweeps again)."""
+    st = int(status.item())
+    redone = False
+    retries = 0
+    while st & (native.NONFINITE | native.NOT_POSDEF):
+        if st & native.NONFINITE:
+            if clamp_infinite(H) == 0:
+                raise RuntimeError("non-finite Hessian without +-inf entries")      # unreachable: NaN raises above
+            native.hessian_prepare(H, percdamp, damp)
+        else:
+            native.hessian_add_damp(H, damp)
+        retries += 1
+        if retries > max_retries:
+            raise RuntimeError("Hessian stayed non-positive-definite after damping")
+        native.chol_inv_upper(H, U, status)
+        st = int(status.item())
+        redone = True
+    if (st & native.HUGE_FACTOR) or exact_reference_order:
+        second_stage(U, percdamp, status, max_retries)
+        redone = True
+    return redone
+
+
+def factor_concurrent(Hs, percdamp=0.01, Us=None, max_retries=64, exact_reference_order=False):
     """[(U, dead)] for a list of DISTINCT Hessians (each modified in place like the reference: dead diagonal -> 1,
     damping added only after a failed attempt, sparsegpt_pruner.py:95-96,111-128).  Us: optional output buffers."""
     dev = Hs[0].device
@@ -79,15 +149,9 @@ def factor_concurrent(Hs, percdamp=0.01, Us=None, max_retries=64):
             with f.stream(slot):
                 native.hessian_prepare(Hs[i], percdamp, damps[i:i + 1], deads[i])
                 native.chol_inv_upper(Hs[i], Us[i], status[i:i + 1])
-    failed = [i for i, s in enumerate(status.tolist()) if s != 0]      # the ONE host sync of the phase
-    for i in failed:                                                     # :114-128, cumulative damping per retry
-        for _ in range(max_retries):
-            native.hessian_add_damp(Hs[i], damps[i:i + 1])
-            native.chol_inv_upper(Hs[i], Us[i], status[i:i + 1])
-            if status[i].item() == 0:
-                break
-        else:
-            raise RuntimeError("Hessian stayed non-positive-definite after damping")
+    failed = [i for i, s in enumerate(status.tolist()) if s != 0 or exact_reference_order]      # the ONE host sync of the phase
+    for i in failed:                                                     # :101-157 for the ones that need it
+        resolve_factor(Hs[i], Us[i], status[i:i + 1], damps[i:i + 1], percdamp, max_retries, exact_reference_order)
     return list(zip(Us, deads))
 
 
@@ -106,7 +170,7 @@ def sweep_concurrent(items, blocksize=128):
     return scores
 
 
-def sparsegpt_block(items, percdamp=0.01, blocksize=128, Us=None, max_retries=64):
+def sparsegpt_block(items, percdamp=0.01, blocksize=128, Us=None, max_retries=64, exact_reference_order=False):
     """items: [(W, H, sparsity, prune_n, prune_m)].  Items that hold THE SAME H tensor (linears fed by the same
     activations) are factorised once.  Returns (scores [n] device tensor, {id(H): (U, dead)}).
 
@@ -139,21 +203,15 @@ def sparsegpt_block(items, percdamp=0.01, blocksize=128, Us=None, max_retries=64
                 native.chol_inv_upper(distinct[h], Us[h], status[h:h + 1])
                 factored = torch.cuda.Event()
                 factored.record(f.streams[slot])
-            for i in members[h]:
+            for i in ([] if exact_reference_order else members[h]):     # exact order: swept after the second stage
                 W, _, sparsity, pn, pm = items[i]
                 f.streams[nH + i].wait_event(factored)
                 with f.stream(nH + i):
                     native.obs_sweep(W, Us[h], sparsity, pn, pm, dead=deads[h], blocksize=blocksize,
                                      score=scores[i:i + 1], fail_flag=status[h:h + 1])
-    failed = [h for h, st in enumerate(status.tolist()) if st != 0]     # the ONE host sync of the block
-    for h in failed:                                                     # :114-128, cumulative damping per retry
-        for _ in range(max_retries):
-            native.hessian_add_damp(distinct[h], damps[h:h + 1])
-            native.chol_inv_upper(distinct[h], Us[h], status[h:h + 1])
-            if status[h].item() == 0:
-                break
-        else:
-            raise RuntimeError("Hessian stayed non-positive-definite after damping")
+    failed = [h for h, st in enumerate(status.tolist()) if st != 0 or exact_reference_order]     # the ONE host sync of the block
+    for h in failed:                                                     # :101-157 for the ones that need it
+        resolve_factor(distinct[h], Us[h], status[h:h + 1], damps[h:h + 1], percdamp, max_retries, exact_reference_order)
         for i in members[h]:
             W, _, sparsity, pn, pm = items[i]
             native.obs_sweep(W, Us[h], sparsity, pn, pm, dead=deads[h], blocksize=blocksize, score=scores[i:i + 1])
