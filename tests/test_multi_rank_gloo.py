@@ -260,3 +260,45 @@ def _importance_dp(rank, out):
 
 def test_importance_scores_data_parallel():
     _run("_importance_dp")
+
+
+def _driver_merge(rank, out):
+    """layerwise.merge_statistics_across_ranks (data-parallel calibration in the drop-in driver): per-rank running means
+    over strided sample shares merge into the single-rank statistics - Wanda's scaler_row, DSnoT's four vectors (mean /
+    var token-weighted, var = mean of per-call variances) and a SparseGPT Hessian accumulated under the global divisor."""
+    import types
+    from oracle import oracle
+    from vlmc.compression.pruners import layerwise
+    xs, _ = _data(5, n_seq=7)
+    N, C = len(xs), xs[0].shape[1]
+    st_ref = dict(scaler_row=np.zeros(C, np.float32), sum_metric_row=np.zeros(C, np.float32), mean=np.zeros(C, np.float32),
+                  var=np.zeros(C, np.float32), nsamples=0, ntokens=0)
+    H_ref, n = np.zeros((C, C), np.float32), 0
+    for x in xs:
+        st_ref = oracle.dsnot_add_batch(st_ref, x, 1)
+        H_ref, n = oracle.sparsegpt_add_batch(H_ref, n, x, 1)
+    mine = xs[rank::WORLD]
+    st = dict(scaler_row=np.zeros(C, np.float32), sum_metric_row=np.zeros(C, np.float32), mean=np.zeros(C, np.float32),
+              var=np.zeros(C, np.float32), nsamples=0, ntokens=0)
+    H = np.zeros((C, C), np.float64)
+    for x in mine:
+        st = oracle.dsnot_add_batch(st, x, 1)
+        H += (2.0 / N) * x.astype(np.float64).T @ x.astype(np.float64)         # what SparseGPT.add_batch does under _global_n
+    wd = types.SimpleNamespace(scaler_row=torch.from_numpy(st["scaler_row"].copy()), sum_metric_row=torch.from_numpy(st["sum_metric_row"].copy()),
+                               mean=torch.from_numpy(st["mean"].copy()).reshape(-1, 1), var=torch.from_numpy(st["var"].copy()).reshape(-1, 1),
+                               nsamples=st["nsamples"], ntokens=st["ntokens"])
+    ww = types.SimpleNamespace(scaler_row=torch.from_numpy(st["scaler_row"].copy()), nsamples=st["nsamples"])
+    ws = types.SimpleNamespace(H=torch.from_numpy(H.astype(np.float32)), nsamples=st["nsamples"])
+    follower = types.SimpleNamespace(H=ws.H, nsamples=st["nsamples"])          # shares the leader's Hessian: reduced once
+    layerwise.merge_statistics_across_ranks([wd, ww, ws, follower], N)
+    for k in ("scaler_row", "sum_metric_row", "mean", "var"):
+        got = getattr(wd, k).reshape(-1).numpy()
+        assert np.abs(got - st_ref[k]).max() <= 1e-5 * np.abs(st_ref[k]).max(), k
+    assert np.abs(ww.scaler_row.numpy() - st_ref["scaler_row"]).max() <= 1e-5 * np.abs(st_ref["scaler_row"]).max()
+    assert np.abs(ws.H.numpy() - H_ref).max() <= 1e-5 * np.abs(H_ref).max() and follower.H is ws.H
+    assert wd.nsamples == ww.nsamples == ws.nsamples == follower.nsamples == N and wd.ntokens == st_ref["ntokens"]
+    out[rank] = "ok"
+
+
+def test_driver_statistics_merge_across_ranks():
+    _run("_driver_merge")

@@ -149,7 +149,8 @@ def test_sparsegpt_fasterprune_at_4096_vs_reference():
     rows = g["rows"].astype(np.int64)
     ref_rows = gu.unpack_w(g["W_rows"], "bf16")
     assert np.linalg.norm(Wo[rows] - ref_rows) / np.linalg.norm(ref_rows) < 1e-3
-    assert np.abs(np.linalg.norm(Wo, axis=1) - g["row_norms"]).max() / g["row_norms"].max() < 1e-3
+    dn = np.linalg.norm(Wo, axis=1) - g["row_norms"]      # all 4096 rows; one flipped mask entry moves a row norm by ~1e-3
+    assert np.linalg.norm(dn) / np.linalg.norm(g["row_norms"]) < 1e-4 and np.abs(dn).max() / g["row_norms"].max() < 5e-3
     assert abs(score - float(g["importance_score"])) < 1e-5 * abs(score)
 
 

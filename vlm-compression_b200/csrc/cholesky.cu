@@ -292,24 +292,22 @@ __global__ void add_diag_kernel(float* H, int64_t ldh, int C, const float* damp)
 
 // Side stream + fork/join events of the look-ahead, one set per (device, caller stream): chains that run concurrently on
 // different streams must not share a side stream (their trailing updates would queue behind each other).
-struct ChainSide { cudaStream_t stream; cudaEvent_t solved, updated; };
-
 static std::atomic<int> g_chol_lookahead{-1};             // -1: follow VLMC_CHOL_LOOKAHEAD (default on); 0 / 1: set by the host
 
-static bool chol_lookahead_enabled() {
+bool chain_lookahead_enabled() {
   const int m = g_chol_lookahead.load();
   if (m >= 0) return m != 0;
   const char* e = getenv("VLMC_CHOL_LOOKAHEAD");          // read per call: tests flip it inside one process
   return !(e && e[0] == '0');
 }
 
-static ChainSide* side_for(cudaStream_t st) {
+ChainSide* chain_side_for(cudaStream_t st, int user) {
   static std::mutex mu;
-  static std::map<std::pair<int, cudaStream_t>, ChainSide> sides;
+  static std::map<std::pair<std::pair<int, int>, cudaStream_t>, ChainSide> sides;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   std::lock_guard<std::mutex> lock(mu);
-  auto key = std::make_pair(dev, st);
+  auto key = std::make_pair(std::make_pair(dev, user), st);
   auto it = sides.find(key);
   if (it != sides.end()) return &it->second;
   ChainSide s;
@@ -371,7 +369,7 @@ static int chol_lower_blocked(float* F, int64_t ldf, float* Li, int64_t ldi, int
   }
   const int nb = (C + kNB - 1) / kNB;
   int rc;
-  ChainSide* side = chol_lookahead_enabled() && nb > 2 ? side_for(st) : nullptr;
+  ChainSide* side = chain_lookahead_enabled() && nb > 2 ? chain_side_for(st, 0) : nullptr;
   bool pending_b = false;
   for (int k = 0; k < nb; ++k) {
     const int k0 = k * kNB;

@@ -19,4 +19,10 @@ int gemm3x(bool b_nk, int M, int N, int K, float alpha, const float* A, int64_t 
            float beta, float* C, int64_t ldc, int tri, int kc, cudaStream_t st, int kmode = 0, bool a_km = false,
            int max_ctas = 0);
 
+// Side stream + fork/join events of the look-ahead schedules (blocked Cholesky, OBS far updates), one set per
+// (device, caller stream, user): chains that run concurrently on different streams must not share a side stream.
+struct ChainSide { cudaStream_t stream; cudaEvent_t solved, updated; };
+ChainSide* chain_side_for(cudaStream_t st, int user);
+bool chain_lookahead_enabled();       // vlmc_chol_set_lookahead / VLMC_CHOL_LOOKAHEAD
+
 }  // namespace vlmc

@@ -457,7 +457,7 @@ extern "C" int vlmc_hessian_accum(const void* x, int dtype, int64_t T, int C, in
                                   float* H, int64_t ldh, double n_before, double b, int kc, int64_t slab_tokens,
                                   void* stream) {
   using namespace vlmc;
-  if (!x || !H || T < 1 || C < 1 || ldx < C || ldh < C || b <= 0) return VLMC_ERR_BAD_ARG;
+  if (!x || !H || T < 1 || C < 1 || ldx < C || ldh < C || b < 0 || n_before < 0 || n_before + b <= 0) return VLMC_ERR_BAD_ARG;   // b == 0 with n_before == N: plain += (2/N) X^T X (token-sharded accumulation)
   if (dtype == VLMC_F32) {
     // fp32 activations (EVA-ViT qkv / fc1 inputs): fp32 values are not exact tensor-core operands, so the
     // contraction runs as the 3xTF32 split GEMM  H = ratio * H + scale * X^T X  (gemm3x.cu, A and B both = X, [K,M] / [K,N]).

@@ -17,6 +17,7 @@
 //                                shuffle inside the lane group.  Writes the finished columns to the fp16/bf16
 //                                weight, the fp32 working copy, Err1 and the keep mask.
 //   K13  the lazy trailing update on the tensor cores: the 3xTF32 tcgen05 GEMM of gemm3x.cu (fp32-grade accuracy).
+#include <stdlib.h>
 #include "gemm3x.cuh"
 
 namespace vlmc {
@@ -24,6 +25,15 @@ namespace vlmc {
 int launch_mean_finalize(const float* part, int n, double denom, float* out, cudaStream_t st);
 
 constexpr int kOB = 128;            // column block (the reference's blocksize default, the only one the scripts use)
+// Super-block schedule of the lazy update (:210).  The reference subtracts Err1 @ U[i1:i2, i2:] from ALL remaining
+// columns after every 128-column block: a K = 128 GEMM that read-modify-writes the whole fp32 trailing matrix 86 times
+// for down_proj (15.5 GB, the traffic that bounded K13 at 95 TFLOP/s logical).  Here kSB consecutive blocks form a
+// super-block: after a block only the remaining columns of ITS super-block are updated (a small K = 128 GEMM), and the
+// far columns receive the super-block's accumulated errors once, as ONE GEMM with K = kSB * 128 - a quarter of the
+// passes over W32 and four times the arithmetic per byte.  Every output element still receives exactly the same
+// products, summed in fp32 (3xTF32, 128-wide chunks added round-to-nearest); only the order of the chunk sums differs.
+constexpr int kSBMax = 8;
+constexpr int kErrLd = kSBMax * kOB;      // Err is [R, kErrLd]: block b of a super-block writes columns [slot * 128, slot * 128 + 128)
 constexpr int kObsBins = 2048;
 constexpr int kObsThreads = 256;
 constexpr int kObsMaxM = 16;
@@ -84,7 +94,7 @@ struct ObsParams {
   const float* U;
   int64_t ldu;
   int i1, bs;          // column block [i1, i1 + bs)
-  float* Err;          // [R, kOB]
+  float* Err;          // [R, kErrLd], already offset to this block's slot
   uint8_t* keep;       // optional [R, ldm]
   int64_t ldm;
   unsigned int kth;    // unstructured: 1-indexed rank of the threshold value among the R*bs block scores
@@ -319,7 +329,7 @@ obs_sweep4_kernel(const ObsParams p, int dtype, int vec_ok) {
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int col = 32 * t + 4 * l;
-        *reinterpret_cast<float4*>(p.Err + (int64_t)row * kOB + col) = make_float4(er[t][0], er[t][1], er[t][2], er[t][3]);
+        *reinterpret_cast<float4*>(p.Err + (int64_t)row * kErrLd + col) = make_float4(er[t][0], er[t][1], er[t][2], er[t][3]);
         if (col < bs) {
           *reinterpret_cast<float4*>(w32 + 32 * t) = make_float4(w[t][0], w[t][1], w[t][2], w[t][3]);
           if (skip_out) continue;          // failed factorisation: only the scratch copies are written
@@ -369,7 +379,7 @@ static int launch_sweep4(const ObsParams& p, int dtype, int vec_ok, cudaStream_t
 
 size_t obs_workspace_bytes(int R, int C) {
   const int nblk = (C + kOB - 1) / kOB;
-  return VLMC_WS_COUNTER_BYTES + align_up((size_t)R * C * sizeof(float), 256) + align_up((size_t)R * kOB * sizeof(float), 256) +
+  return VLMC_WS_COUNTER_BYTES + align_up((size_t)R * C * sizeof(float), 256) + align_up(2 * (size_t)R * kErrLd * sizeof(float), 256) +
          align_up((size_t)nblk * sizeof(ObsHist), 256) + align_up((size_t)kNumSMs * 64 * sizeof(float), 256);
 }
 
@@ -378,6 +388,16 @@ size_t obs_workspace_bytes(int R, int C) {
 namespace vlmc {
 
 struct ObsLayout { float* W32; float* Err; ObsHist* hist; float* part; };
+
+// blocks per super-block: VLMC_OBS_SUPERBLOCK (1, 2, 4 or 8; default 4; 1 = the reference's block-by-block schedule)
+static int obs_superblock() {
+  const char* e = getenv("VLMC_OBS_SUPERBLOCK");
+  if (e) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) return v;
+  }
+  return 4;
+}
 static ObsLayout obs_carve(void* ws, int R, int C) {
   const int nblk = (C + kOB - 1) / kOB;
   char* base = reinterpret_cast<char*>(ws) + VLMC_WS_COUNTER_BYTES;
@@ -385,7 +405,7 @@ static ObsLayout obs_carve(void* ws, int R, int C) {
   l.W32 = reinterpret_cast<float*>(base);
   base += align_up((size_t)R * C * sizeof(float), 256);
   l.Err = reinterpret_cast<float*>(base);
-  base += align_up((size_t)R * kOB * sizeof(float), 256);
+  base += align_up(2 * (size_t)R * kErrLd * sizeof(float), 256);     // two buffers: super-blocks alternate (look-ahead)
   l.hist = reinterpret_cast<ObsHist*>(base);
   base += align_up((size_t)nblk * sizeof(ObsHist), 256);
   l.part = reinterpret_cast<float*>(base);
@@ -415,7 +435,11 @@ static ObsParams obs_block_params(const ObsLayout& l, void* W, int R, int C, int
   p.W32 = l.W32; p.Wout = W; p.ldw = ldw; p.R = R; p.C = C; p.U = U; p.ldu = ldu;
   p.i1 = blk * kOB;
   p.bs = (C - p.i1 < kOB) ? (C - p.i1) : kOB;
-  p.Err = l.Err; p.keep = keep_mask; p.ldm = ldm;
+  {
+    const int sb = obs_superblock();
+    p.Err = l.Err + (size_t)((blk / sb) & 1) * (size_t)R * kErrLd + (size_t)(blk % sb) * kOB;
+  }
+  p.keep = keep_mask; p.ldm = ldm;
   // int(numel * sparsity) is the 0-indexed rank of the threshold (:184); numel counts the rows of ALL shards
   p.kth = (unsigned int)((ull)((double)((ull)rows_total * (ull)p.bs) * sparsity)) + 1u;
   p.prune_n = prune_n; p.prune_m = prune_m;
@@ -469,7 +493,8 @@ extern "C" int vlmc_obs_block_hist(int R, int C, const float* U, int64_t ldu, in
 namespace vlmc {
 static int obs_block_finish_impl(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu, int blk,
                                  int64_t rows_total, double sparsity, int prune_n, int prune_m, uint8_t* keep_mask,
-                                 int64_t ldm, unsigned int* hist, void* ws, size_t ws_bytes, void* stream, const int* fail) {
+                                 int64_t ldm, unsigned int* hist, void* ws, size_t ws_bytes, void* stream, const int* fail,
+                                 ChainSide* side = nullptr, bool* pending_far = nullptr) {
   int rc = obs_checks(W, dtype, R, C, ldw, U, ldu, sparsity, prune_n, prune_m, kOB, keep_mask, ldm, ws, ws_bytes);
   if (rc) return rc;
   if (blk < 0 || blk * kOB >= C || rows_total < R) return VLMC_ERR_BAD_ARG;
@@ -492,9 +517,47 @@ static int obs_block_finish_impl(void* W, int dtype, int R, int C, int64_t ldw, 
   if (rc) return rc;
   const int i2 = p.i1 + p.bs;
   if (i2 < C) {
-    // K13: W[:, i2:] -= Err1 @ U[i1:i2, i2:]
-    rc = gemm3x(false, R, C - i2, kOB, -1.f, l.Err, kOB, U + (int64_t)p.i1 * ldu + i2, ldu, 1.f, l.W32 + i2, C, 0, 0, st);
-    if (rc) return rc;
+    // K13: W[:, i2:] -= Err1 @ U[i1:i2, i2:], on the super-block schedule (see kSBMax)
+    const int sb = obs_superblock();
+    const int slot = blk % sb;
+    const int sb_i1 = (blk - slot) * kOB;                       // first column of the super-block
+    const int sb_i2 = sb_i1 + sb * kOB < C ? sb_i1 + sb * kOB : C;   // one past its last column
+    if (i2 < sb_i2) {      // near: the rest of this super-block gets this block's errors now
+      rc = gemm3x(false, R, sb_i2 - i2, kOB, -1.f, p.Err, kErrLd, U + (int64_t)p.i1 * ldu + i2, ldu, 1.f, l.W32 + i2, C, 0, 0, st);
+      if (rc) return rc;
+    } else if (sb_i2 < C) {  // far: the super-block is complete, everything behind it gets all of its errors at once
+      // kc = K: one in-TMEM accumulation over the whole super-block (256-wide tiles, no per-chunk register sums); the
+      // round-toward-zero drift of K / 8 * 3 accumulations stays below 1.2e-5 of the update term at K = 512
+      const char* ce = getenv("VLMC_OBS_FAR_CHUNKED");
+      const int K = i2 - sb_i1;
+      const int kc = (ce && ce[0] == '1') ? 0 : K;
+      const float* ErrSB = l.Err + (size_t)((blk / sb) & 1) * (size_t)R * kErrLd;
+      const float* Ufar = U + (int64_t)sb_i1 * ldu + sb_i2;
+      const int behind = C - sb_i2;
+      const int next_cols = sb * kOB < behind ? sb * kOB : behind;      // the next super-block's columns
+      if (!side || behind - next_cols < kOB) {
+        rc = gemm3x(false, R, behind, K, -1.f, ErrSB, kErrLd, Ufar, ldu, 1.f, l.W32 + sb_i2, C, 0, kc, st);
+        if (rc) return rc;
+      } else {
+        // Look-ahead: only the NEXT super-block's columns are needed before its sweeps can start; the rest of the far
+        // update runs on a side stream under them.  far_rest(s - 1) wrote the columns far_near(s) updates, hence the wait;
+        // far_rest(s) reads this super-block's Err buffer, which is not rewritten before super-block s + 2, i.e. after the
+        // wait at the end of super-block s + 1.
+        if (*pending_far) {
+          if (cudaStreamWaitEvent(st, side->updated, 0) != cudaSuccess) return check_launch();
+          *pending_far = false;
+        }
+        if (cudaEventRecord(side->solved, st) != cudaSuccess) return check_launch();
+        rc = gemm3x(false, R, next_cols, K, -1.f, ErrSB, kErrLd, Ufar, ldu, 1.f, l.W32 + sb_i2, C, 0, kc, st);
+        if (rc) return rc;
+        if (cudaStreamWaitEvent(side->stream, side->solved, 0) != cudaSuccess) return check_launch();
+        rc = gemm3x(false, R, behind - next_cols, K, -1.f, ErrSB, kErrLd, Ufar + next_cols, ldu, 1.f,
+                    l.W32 + sb_i2 + next_cols, C, 0, kc, side->stream, 0, false, kNumSMs - 20);
+        if (rc) return rc;
+        if (cudaEventRecord(side->updated, side->stream) != cudaSuccess) return check_launch();
+        *pending_far = true;
+      }
+    }
   }
   return check_launch();
 }
@@ -521,6 +584,11 @@ static int obs_sweep_impl(void* W, int dtype, int R, int C, int64_t ldw, const f
     if (rc) return rc;
   }
   const int nblk = (C + kOB - 1) / kOB;
+  cudaStream_t st = (cudaStream_t)stream;
+  // the far updates run ahead on a side stream for a chain that has the GPU to itself (same switch as the Cholesky's
+  // look-ahead: callers that enqueue several chains concurrently turn it off)
+  ChainSide* side = (chain_lookahead_enabled() && nblk > 2 * obs_superblock()) ? chain_side_for(st, 1) : nullptr;
+  bool pending_far = false;
   for (int blk = 0; blk < nblk; ++blk) {
     if (prune_n == 0)
       for (int pass = 0; pass < 3; ++pass) {
@@ -528,9 +596,10 @@ static int obs_sweep_impl(void* W, int dtype, int R, int C, int64_t ldw, const f
         if (rc) return rc;
       }
     rc = obs_block_finish_impl(W, dtype, R, C, ldw, U, ldu, blk, R, sparsity, prune_n, prune_m, keep_mask, ldm,
-                               nullptr, ws, ws_bytes, stream, fail);
+                               nullptr, ws, ws_bytes, stream, fail, side, &pending_far);
     if (rc) return rc;
   }
+  if (pending_far && cudaStreamWaitEvent(st, side->updated, 0) != cudaSuccess) return check_launch();
   return VLMC_OK;
 }
 }  // namespace vlmc

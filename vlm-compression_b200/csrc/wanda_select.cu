@@ -9,6 +9,7 @@
 //
 // rowselect: one WARP streams a row; only a short candidate list is kept on chip (see the kernel).
 // HBM-bound: 5 B/weight for fp16/bf16 (read W, write W, write mask).
+#include <stdlib.h>
 #include <type_traits>
 #include "common.cuh"
 
@@ -706,9 +707,382 @@ static int sel_common_checks(void* W, int dtype, int R, int C, int64_t ldw, cons
   return VLMC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// rowselect, CTA-per-row form (default).  The warp-per-row kernel above streams a row several times through registers
+// and spends ~38 thread instructions per weight (ncu r01: 109 registers, 24 % of the warps resident, 0.21 of the HBM
+// roofline).  Here a 256-thread CTA owns a row and the row is touched in HBM exactly once:
+//   P1  one 16-byte load per vector (the row stays in REGISTERS for the apply pass), score bits -> shared memory (each
+//       thread only ever reads back its own keys: no barrier), row sum / maximum by shuffle, and - in the same pass - a
+//       shared-memory histogram over LINEAR bins of width (1.25 x the previous row's maximum) / 2048.  Binning by
+//       floor(score * scale) is monotone in the score, so bin order is score order whatever the scale; unlike the
+//       exponent-heavy top bits of the float pattern the bins are evenly loaded (a handful of keys each): no atomic
+//       contention, and the bin of the k-th score holds a few candidates only
+//   P2  warp 0 scans the 2048 counters -> the bin of the k-th smallest score and the rank inside it (and clears them)
+//   P3  the keys of that bin are collected with their columns; EVERY warp then ranks the (<= 32 typical) candidates on
+//       (score, column) - the stable-sort tie-break of torch.sort(stable=True), wanda_pruner.py:332 - so the threshold
+//       pair is known without another barrier
+//   P4  apply from registers + shared memory: prune (key < v) || (key == v && column <= iv); 8-byte mask stores,
+//       16-byte weight stores only for vectors that lose a weight
+// Three CTA barriers per row.  Degenerate rows (all-zero or non-finite scale, more than kRcCand keys in the chosen bin:
+// heavy ties, an outlier row whose k-th score falls in the overflow bin) take an exact radix select on the score bits
+// and then on the column index, in the same shared memory.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kRcThreads = 256;
+constexpr int kRcWarps = kRcThreads / 32;
+constexpr int kRcBins = 2048;
+constexpr int kRcCand = 256;
+constexpr int kRcMaxVec = 8;              // 16-byte vectors per thread held in registers: C <= 256 * 8 * V
+
+struct RcShared {
+  float wsum[kRcWarps];
+  uint32_t wmax[kRcWarps];
+  uint32_t scan[kRcWarps + 2];
+  uint32_t ncand, sel_bin, sel_before, thr_key;
+  int thr_col;
+};
+
+// One warp: bin (among kRcBins counters) that holds the kk-th (1-indexed) entry and the count before it -> sh.sel_bin,
+// sh.sel_before; the counters are cleared on the way.  64 counters per lane.
+__device__ __forceinline__ void rc_scan_warp(uint32_t* hist, uint32_t kk, RcShared& sh) {
+  const int lane = threadIdx.x & 31;
+  constexpr int per = kRcBins / 32;                           // lane owns bins [lane * 64, lane * 64 + 64)
+  // rotated walk: at step j lane reads word (j + lane) % 64 of its segment -> bank (j + lane) % 32: conflict-free
+  uint32_t local = 0;
+#pragma unroll 16
+  for (int j = 0; j < per; ++j) local += hist[lane * per + ((j + lane) & (per - 1))];
+  uint32_t incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const uint32_t excl = incl - local;
+  // the segment that holds rank kk is walked by ALL lanes together: two bins per lane, one more 32-wide scan each
+  const uint32_t owner_mask = __ballot_sync(0xffffffffu, excl < kk && kk <= incl);
+  const int owner = __ffs(owner_mask) - 1;                    // exactly one lane when 1 <= kk <= total
+  if (owner >= 0) {
+    const uint32_t base = __shfl_sync(0xffffffffu, excl, owner);
+    uint32_t run = base;
+#pragma unroll
+    for (int h = 0; h < per / 32; ++h) {
+      const uint32_t c = hist[owner * per + h * 32 + lane];
+      uint32_t inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      const uint32_t before = run + inc - c;
+      if (before < kk && kk <= before + c) { sh.sel_bin = owner * per + h * 32 + lane; sh.sel_before = before; }
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncwarp();
+#pragma unroll 16
+  for (int j = 0; j < per; ++j) hist[lane * per + ((j + lane) & (per - 1))] = 0;
+}
+
+// All threads: same result in registers (used by the exact path only; two barriers inside)
+__device__ __forceinline__ void rc_find_bin(uint32_t* hist, uint32_t kk, RcShared& sh, uint32_t& bin, uint32_t& before) {
+  __syncthreads();
+  if (threadIdx.x < 32) rc_scan_warp(hist, kk, sh);
+  __syncthreads();
+  bin = sh.sel_bin;
+  before = sh.sel_before;
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(kRcThreads, NV <= 4 ? 3 : 2)
+rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ sq, int k, int zero_w,
+                     uint8_t* __restrict__ mask, int64_t ldm, float* __restrict__ row_sum) {
+  constexpr int V = Elem<T>::kVec;
+  extern __shared__ __align__(16) uint32_t rc_smem[];
+  const int nvec = C / V;
+  // key planes: plane q holds elements 4q..4q+3 of every vector as one uint4 per vector (conflict-free 16-byte accesses)
+  uint32_t* keys = rc_smem;                                   // [V / 4][nvec][4]
+  uint32_t* hist = keys + (size_t)C;                          // [kRcBins]
+  uint32_t* cand_key = hist + kRcBins;                        // [kRcCand]
+  uint32_t* cand_col = cand_key + kRcCand;                    // [kRcCand]
+  __shared__ RcShared sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int b = tid; b < kRcBins; b += kRcThreads) hist[b] = 0;
+  if (tid == 0) sh.ncand = 0;
+
+  auto load_row = [&](int row, uint4 (&wv)[NV]) {
+    const T* wrow = W + (int64_t)row * ldw;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int vi = tid + u * kRcThreads;
+      if (vi < nvec) wv[u] = ld_stream(wrow + (int64_t)vi * V);
+    }
+  };
+  auto bin_of = [](uint32_t key, float scale) -> uint32_t {
+    const float x = __fmul_rn(__uint_as_float(key), scale);
+    const uint32_t b = (uint32_t)x;                           // x >= 0 (or NaN -> 0); monotone in key
+    return b < (uint32_t)kRcBins ? b : (uint32_t)kRcBins - 1;
+  };
+
+  // scale of the first row of this CTA: from its own maximum (one extra pass over the registers)
+  float scale = 0.f;
+  {
+    const int row = blockIdx.x;
+    if (row < R) {
+      uint4 wv[NV];
+      load_row(row, wv);
+      uint32_t lmax = 0;
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const int vi = tid + u * kRcThreads;
+        if (vi < nvec) {
+          float f[V];
+          Elem<T>::unpack(wv[u], f);
+#pragma unroll
+          for (int q = 0; q < V / 4; ++q) {
+            const float4 sv = __ldg(reinterpret_cast<const float4*>(sq + vi * V) + q);
+            const float se[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t kq = __float_as_uint(__fmul_rn(fabsf(f[q * 4 + e]), se[e])) & 0x7fffffffu;
+              lmax = kq > lmax ? kq : lmax;
+            }
+          }
+        }
+      }
+      lmax = __reduce_max_sync(0xffffffffu, lmax);
+      if (lane == 0) sh.wmax[warp] = lmax;
+    }
+    __syncthreads();
+    uint32_t rmax = 0;
+#pragma unroll
+    for (int w = 0; w < kRcWarps; ++w) rmax = sh.wmax[w] > rmax ? sh.wmax[w] : rmax;
+    if (rmax > 0u && rmax < 0x7f800000u) scale = (float)kRcBins / (1.25f * __uint_as_float(rmax));
+    __syncthreads();
+  }
+
+  for (int row = blockIdx.x; row < R; row += gridDim.x) {
+    T* wrow = W + (int64_t)row * ldw;
+    uint4 wv[NV];
+    load_row(row, wv);
+    // ---- P1: score, keys -> smem, row sum / max, linear-bin histogram
+    float lsum = 0.f;
+    uint32_t lmax = 0;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int vi = tid + u * kRcThreads;
+      if (vi < nvec) {
+        float f[V];
+        Elem<T>::unpack(wv[u], f);
+#pragma unroll
+        for (int q = 0; q < V / 4; ++q) {
+          const float4 sv = __ldg(reinterpret_cast<const float4*>(sq + vi * V) + q);
+          const float se[4] = {sv.x, sv.y, sv.z, sv.w};
+          uint32_t kq[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float sc = __fmul_rn(fabsf(f[q * 4 + e]), se[e]);
+            kq[e] = __float_as_uint(sc) & 0x7fffffffu;
+            lsum += sc;
+            lmax = kq[e] > lmax ? kq[e] : lmax;
+            atomicAdd(&hist[bin_of(kq[e], scale)], 1u);
+          }
+          *reinterpret_cast<uint4*>(keys + ((size_t)q * nvec + vi) * 4) = make_uint4(kq[0], kq[1], kq[2], kq[3]);
+        }
+      }
+    }
+    lsum = warp_sum(lsum);
+    lmax = __reduce_max_sync(0xffffffffu, lmax);
+    if (lane == 0) { sh.wsum[warp] = lsum; sh.wmax[warp] = lmax; }
+    __syncthreads();                                           // barrier A: histogram, partial sums
+    uint32_t rmax = 0;
+#pragma unroll
+    for (int w = 0; w < kRcWarps; ++w) rmax = sh.wmax[w] > rmax ? sh.wmax[w] : rmax;
+    if (tid == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRcWarps; ++w) t += sh.wsum[w];
+      row_sum[row] = t;
+      sh.ncand = 0;
+    }
+    const bool select = k > 0 && k < C;
+    // ---- P2: the bin of the k-th smallest score
+    if (warp == 0) rc_scan_warp(hist, select ? (uint32_t)k : 1u, sh);
+    __syncthreads();                                           // barrier B: sel_bin / sel_before, counters cleared
+    uint32_t thr_key = 0;
+    int thr_col = -1;                                          // prune (key < thr_key) || (key == thr_key && col <= thr_col)
+    if (k >= C) {
+      thr_key = 0xffffffffu;
+    } else if (k > 0) {
+      const uint32_t b_sel = sh.sel_bin;
+      const uint32_t kk = (uint32_t)k - sh.sel_before;         // 1-indexed rank inside the bin
+      // ---- P3: collect the bin's keys
+#pragma unroll
+      for (int u = 0; u < NV; ++u) {
+        const int vi = tid + u * kRcThreads;
+        if (vi < nvec) {
+#pragma unroll
+          for (int q = 0; q < V / 4; ++q) {
+            const uint4 kq = *reinterpret_cast<const uint4*>(keys + ((size_t)q * nvec + vi) * 4);
+            const uint32_t ke[4] = {kq.x, kq.y, kq.z, kq.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (bin_of(ke[e], scale) == b_sel) {
+                const uint32_t pos = atomicAdd(&sh.ncand, 1u);
+                if (pos < (uint32_t)kRcCand) { cand_key[pos] = ke[e]; cand_col[pos] = (uint32_t)(vi * V + q * 4 + e); }
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();                                         // barrier C: candidate list
+      const uint32_t nc = sh.ncand;
+      if (nc <= (uint32_t)kRcCand) {
+        // every warp ranks the candidates itself: the threshold pair lands in registers without another barrier
+        uint32_t fk = 0, fc = 0;
+        bool found = false;
+        for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
+          const uint32_t i = c0 + lane;
+          const uint32_t mk = i < nc ? cand_key[i] : 0xffffffffu, mc = i < nc ? cand_col[i] : 0xffffffffu;
+          uint32_t rank = 0;
+          for (uint32_t j = 0; j < nc; ++j) {
+            const uint32_t ok = cand_key[j], oc = cand_col[j];
+            rank += (ok < mk || (ok == mk && oc < mc)) ? 1u : 0u;
+          }
+          const bool hit = i < nc && rank == kk - 1;
+          const uint32_t ball = __ballot_sync(0xffffffffu, hit);
+          if (ball) {
+            const int src = __ffs(ball) - 1;
+            fk = __shfl_sync(0xffffffffu, mk, src);
+            fc = __shfl_sync(0xffffffffu, mc, src);
+            found = true;
+          }
+        }
+        (void)found;
+        thr_key = fk;
+        thr_col = (int)fc;
+      } else {
+        // ---- exact radix select on the score bits (31 significant bits: 11 + 11 + 9), then on the column index
+        uint32_t prefix = 0, kr = (uint32_t)k, before = 0, bsel = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const int shift = pass == 0 ? 20 : (pass == 1 ? 9 : 0);
+          const uint32_t himask = pass == 0 ? 0u : (pass == 1 ? 0xfff00000u : 0xfffffe00u);
+          const uint32_t bmask = pass == 2 ? 0x1ffu : 0x7ffu;
+          for (int j = tid; j < C; j += kRcThreads) {
+            const uint32_t key = keys[j];
+            if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & bmask], 1u);
+          }
+          rc_find_bin(hist, kr, sh, bsel, before);
+          kr -= before;
+          prefix |= bsel << shift;
+        }
+        // prefix = the k-th smallest key; kr = how many of the keys equal to it are pruned (lowest columns first)
+        uint32_t cprefix = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {                  // columns < 2^22: 11 + 11 bits
+          const int shift = pass == 0 ? 11 : 0;
+          for (int j = tid; j < C; j += kRcThreads) {
+            if (keys[j] == prefix) {
+              const int plane = j / (nvec * 4), rem = j - plane * nvec * 4;
+              const uint32_t col = (uint32_t)((rem >> 2) * V + plane * 4 + (rem & 3));
+              if (pass == 0 || (col >> 11) == cprefix) atomicAdd(&hist[(col >> shift) & 0x7ffu], 1u);
+            }
+          }
+          rc_find_bin(hist, kr, sh, bsel, before);
+          kr -= before;
+          if (pass == 0) cprefix = bsel;
+        }
+        thr_key = prefix;
+        thr_col = (int)((cprefix << 11) | bsel);
+      }
+    }
+
+    // ---- P4: apply
+    uint8_t* mrow = mask + (int64_t)row * ldm;
+#pragma unroll
+    for (int u = 0; u < NV; ++u) {
+      const int vi = tid + u * kRcThreads;
+      if (vi < nvec) {
+        float f[V];
+        Elem<T>::unpack(wv[u], f);
+        uint32_t mb[V / 4];
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < V / 4; ++q) {
+          const uint4 kq = *reinterpret_cast<const uint4*>(keys + ((size_t)q * nvec + vi) * 4);
+          const uint32_t ke[4] = {kq.x, kq.y, kq.z, kq.w};
+          uint32_t bytes = 0;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = vi * V + q * 4 + e;
+            const bool pruned = ke[e] < thr_key || (ke[e] == thr_key && col <= thr_col);
+            if (pruned) { f[q * 4 + e] = 0.f; any = true; }
+            bytes |= (pruned ? 0u : 1u) << (8 * e);
+          }
+          mb[q] = bytes;
+        }
+        if (V == 8) st_stream8(mrow + (int64_t)vi * V, make_uint2(mb[0], mb[V / 4 - 1]));
+        else st_stream4(mrow + (int64_t)vi * V, mb[0]);
+        if (zero_w && any) st_stream(wrow + (int64_t)vi * V, Elem<T>::pack(f));
+      }
+    }
+    // next row's scale: this row's maximum (rows of one matrix share sq and the weight distribution)
+    scale = (rmax > 0u && rmax < 0x7f800000u) ? (float)kRcBins / (1.25f * __uint_as_float(rmax)) : 0.f;
+  }
+}
+
+template <typename T>
+static bool rowselect_cta_fits(int C) {
+  constexpr int V = Elem<T>::kVec;
+  const size_t smem = ((size_t)C + kRcBins + 2 * kRcCand) * sizeof(uint32_t);
+  return C / V <= kRcThreads * kRcMaxVec && smem <= 200 * 1024 && C < (1 << 22);
+}
+
+template <typename T, int NV>
+static int launch_rowselect_cta_nv(void* W, int R, int C, int64_t ldw, const float* sq, int k, int zero_w,
+                                   uint8_t* mask, int64_t ldm, float* row_sum, cudaStream_t st) {
+  auto kern = rowselect_cta_kernel<T, NV>;
+  const size_t smem = ((size_t)C + kRcBins + 2 * kRcCand) * sizeof(uint32_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess)
+      return check_launch();
+    attr_set = true;
+  }
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRcThreads, smem);
+  if (per_sm < 1) per_sm = 1;
+  // every CTA gets the same number of rows (a ragged last wave would idle part of the grid)
+  const int resident = kNumSMs * per_sm;
+  const int rows_per_cta = (R + resident - 1) / resident;
+  int grid = (R + rows_per_cta - 1) / rows_per_cta;
+  if (grid < 1) grid = 1;
+  kern<<<grid, kRcThreads, smem, st>>>(reinterpret_cast<T*>(W), ldw, R, C, sq, k, zero_w, mask, ldm, row_sum);
+  return check_launch();
+}
+
+template <typename T>
+static int launch_rowselect_cta(void* W, int R, int C, int64_t ldw, const float* sq, int k, int zero_w,
+                                uint8_t* mask, int64_t ldm, float* row_sum, cudaStream_t st) {
+  constexpr int V = Elem<T>::kVec;
+  const int nv = (C / V + kRcThreads - 1) / kRcThreads;
+#define VLMC_RC(NV) return launch_rowselect_cta_nv<T, NV>(W, R, C, ldw, sq, k, zero_w, mask, ldm, row_sum, st)
+  if (nv <= 1) VLMC_RC(1);
+  if (nv <= 2) VLMC_RC(2);
+  if (nv <= 3) VLMC_RC(3);
+  if (nv <= 4) VLMC_RC(4);
+  if (nv <= 6) VLMC_RC(6);
+  VLMC_RC(8);
+#undef VLMC_RC
+}
+
 template <typename T>
 static int launch_rowselect(void* W, int R, int C, int64_t ldw, const float* sq, int k, int zero_w,
                             uint8_t* mask, int64_t ldm, float* row_sum, uint32_t* seed, cudaStream_t st) {
+  {
+    const char* legacy = getenv("VLMC_ROWSELECT_LEGACY");      // A/B switch: the warp-per-row streaming kernel
+    if (!(legacy && legacy[0] == '1') && rowselect_cta_fits<T>(C))
+      return launch_rowselect_cta<T>(W, R, C, ldw, sq, k, zero_w, mask, ldm, row_sum, st);
+  }
   auto kern = rowselect_kernel<T>;
   rowselect_seed_kernel<T><<<1, 32, 0, st>>>(reinterpret_cast<const T*>(W), ldw, R, C, sq, k, seed);
   int per_sm = 1;

@@ -95,6 +95,65 @@ def adopt_statistics(follower, leader):
     follower._shared = group
 
 
+def _dist_info(pruner):
+    """(rank, world) when the pruner runs data-parallel: torch.distributed is initialised with more than one
+    rank AND the pruner asked for it (data_parallel=True; the reference's scripts launch replicas that each prune the
+    whole model redundantly, so the default keeps that behaviour)."""
+    import torch.distributed as dist
+    if getattr(pruner, "data_parallel", False) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def merge_statistics_across_ranks(wrappers, n_total):
+    """Data-parallel calibration: every rank accumulated the running means of ITS samples; merge them into the statistics
+    of the whole calibration set.  Per distinct wrapper: the small vectors (scaler_row, sum_metric_row: sample-weighted;
+    mean, var: token-weighted) travel in ONE packed all-reduce per block; a Hessian was accumulated with the divisor of
+    the whole set from the start (SparseGPT.add_batch under `_global_n`) and is all-reduced in place.  Afterwards the state
+    on every rank is what one rank would have accumulated over all samples (to rounding: sums in another order)."""
+    import torch.distributed as dist
+    seen, uniq = set(), []
+    for w in wrappers:
+        key = id(getattr(w, "H", None)) if getattr(w, "H", None) is not None else id(getattr(w, "scaler_row", None))
+        if key not in seen:
+            seen.add(key)
+            uniq.append(w)
+    parts, meta = [], []
+    for w in uniq:
+        if getattr(w, "H", None) is not None:
+            dist.all_reduce(w.H, op=dist.ReduceOp.SUM)
+            continue
+        dev = w.scaler_row.device
+        for attr, weight in (("scaler_row", float(w.nsamples)), ("sum_metric_row", float(w.nsamples)),
+                             ("mean", float(getattr(w, "ntokens", 0))), ("var", float(getattr(w, "ntokens", 0)))):
+            t = getattr(w, attr, None)
+            if t is None:
+                continue
+            parts.append(t.reshape(-1).float() * weight)
+            parts.append(torch.full((1,), weight, device=dev))
+            meta.append((w, attr, t.numel()))
+        if hasattr(w, "ntokens"):
+            parts.append(torch.full((1,), float(w.ntokens), device=dev))
+            meta.append((w, "__ntokens__", 0))
+    if parts:
+        flat = torch.cat(parts)
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        off = 0
+        for w, attr, k in meta:
+            if attr == "__ntokens__":
+                w._ntokens_total = flat[off:off + 1]
+                off += 1
+                continue
+            t = getattr(w, attr)
+            t.copy_((flat[off:off + k] / flat[off + k]).reshape(t.shape))
+            off += k + 1
+    for w in wrappers:
+        w.nsamples = n_total
+        if hasattr(w, "_ntokens_total"):
+            w.ntokens = int(round(float(w._ntokens_total.item())))
+            del w._ntokens_total
+
+
 def capture_block_inputs(pruner, model, dataloader, model_prefix, n_samples, module_to_process, lora_model, vit,
                          replay_all_args=False):
     """Swap block 0 for a catcher and run the model until n_samples inputs are recorded.
@@ -227,6 +286,11 @@ def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_s
     n_samples = min(n_samples, len(inps))
     layers = get_module_recursive(model, module_to_process)
     expected_nsamples = len(inps) * inps[0].shape[0]
+    # data-parallel calibration: rank r keeps samples r, r + world, ...; the statistics are merged per block
+    rank, world = _dist_info(pruner)
+    if world > 1:
+        inps, caches = inps[:n_samples][rank::world], caches[:n_samples][rank::world]
+        n_samples = len(inps)
     # calibration batching: the block runs on chunks of stacked samples (calib_batch = 1 restores the reference's
     # one-sample-per-forward schedule, wanda_pruner.py:308-311)
     inps, caches, counts = stack_calibration(inps[:n_samples], caches[:n_samples],
@@ -256,6 +320,9 @@ def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_s
         layer = layers[i]
         subset = find_layers(layer)
         wrapped = {name: make_wrapper(subset[name]) for name in subset}
+        if world > 1:
+            for w in wrapped.values():
+                w._global_n = expected_nsamples      # Hessians accumulate with the divisor of the whole set
         if share is not None:
             share.leader, share.leaders = {}, set()
 
@@ -275,6 +342,8 @@ def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_s
             share.begin_forward()                       # drop the references to the last sample's activations
             for follower, leader in share.leader.items():
                 adopt_statistics(wrapped[follower], wrapped[leader])
+        if world > 1:
+            merge_statistics_across_ranks(list(wrapped.values()), expected_nsamples)
         for name in subset:
             key = f"{module_to_process}.{i}.{name}.weight"
             try:

@@ -39,7 +39,14 @@ class SparseGPT:
         if len(inp.shape) == 2:
             inp = inp.unsqueeze(0)
         b = inp.shape[0]
-        native.hessian_accum(inp, self.H, self.nsamples, b)
+        N = getattr(self, "_global_n", None)
+        if N is None:
+            native.hessian_accum(inp, self.H, self.nsamples, b)
+        else:
+            # data-parallel calibration (layerwise.prune_blocks): this rank sees a share of the N samples; its partial sum
+            # carries the divisor of the WHOLE set from the start - first call H = (2/N) X^T X, later calls
+            # H += (2/N) X^T X - so the ranks' Hessians simply add (one all-reduce, no rescaling pass over C^2 floats)
+            native.hessian_accum(inp, self.H, 0 if self.nsamples == 0 else N, N if self.nsamples == 0 else 0)
         self.nsamples += b
 
     def fasterprune(self, sparsity, prune_n=0, prune_m=0, blocksize=128, percdamp=.01):
@@ -101,10 +108,30 @@ class BLIPT5LayerSparseGPTPruner(BLIPT5LayerWandaPruner):
         return fn
 
     def finish_block(self, subset, wrapped):
+        from vlmc import parallel
+        from vlmc.compression.pruners.layerwise import _dist_info
         pending, self._pending = getattr(self, "_pending", []), []
         if pending:
-            fasterprune_block([w for w, _ in pending], [s for _, s in pending], prune_n=self.prune_n,
-                              prune_m=self.prune_m, percdamp=0.01, blocksize=128)
+            rank, world = _dist_info(self)
+            if world > 1:
+                # data-parallel run: every rank holds the merged Hessians; WHOLE linears are dealt to the ranks (longest
+                # chain first), each rank runs its chains concurrently, the pruned weights are broadcast from their owners
+                ws = [w for w, _ in pending]
+                scores = torch.zeros(len(ws), dtype=torch.float32, device=ws[0].layer.weight.device)
+
+                def run(indices):
+                    fasterprune_block([ws[i] for i in indices], [pending[i][1] for i in indices], prune_n=self.prune_n,
+                                      prune_m=self.prune_m, percdamp=0.01, blocksize=128)
+                    for i in indices:
+                        scores[i] = ws[i].layer.weight.importance_score
+                parallel.prune_linears_task_parallel([w.layer.weight.data for w in ws], run, rank, world)
+                parallel.allreduce_sum(scores)
+                for w, v in zip(ws, scores.tolist()):
+                    setattr(w.layer.weight, "importance_score", v)
+                    w.H = None
+            else:
+                fasterprune_block([w for w, _ in pending], [s for _, s in pending], prune_n=self.prune_n,
+                                  prune_m=self.prune_m, percdamp=0.01, blocksize=128)
             for w, _ in pending:
                 w.free()
 

@@ -116,7 +116,8 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
                  sparsity_ratio_granularity=None, max_sparsity_per_layer=0.8, score_method="obd_avg",
                  num_data_first_stage=128, num_noise=1, sparsity_dict=None, noise_eps=1e-3,
                  prune_per_model=False, peft_postfix="", prune_n=0, prune_m=0, share_inputs=True,
-                 qformer_prune_spec=None, qformer_model_prefix="Qformer", calib_batch=16, **kwargs):
+                 qformer_prune_spec=None, qformer_model_prefix="Qformer", calib_batch=16, data_parallel=False,
+                 **kwargs):
         super().__init__(model=model, data_loader=data_loader, prune_spec=None, is_strct_pruning=is_strct_pruning,
                          importance_scores_cache=importance_scores_cache,
                          keep_indices_or_masks_cache=keep_indices_or_masks_cache, is_global=is_global,
@@ -145,6 +146,10 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
         # linear gets ONE add_batch per chunk (layerwise.stack_calibration); 1 = one sample per forward like the
         # reference (wanda_pruner.py:308-311).  Statistics agree to rounding (tests: 1e-5), masks on tie-free data.
         self.calib_batch = calib_batch
+        # True (and torch.distributed initialised with > 1 rank): the ranks split the calibration samples, merge the
+        # statistics with one all-reduce per block and end up with identical pruned replicas.  False: every
+        # rank prunes its replica on its own, like the reference's torchrun launch does.
+        self.data_parallel = data_parallel
         # EXTENSION (no reference behaviour to match): the reference never prunes the Q-Former (its pruners
         # walk visual_encoder.blocks, t5/llm layers or OPT layers only).  With a "<layers>-<keep>-1.0-1.0" spec the 12
         # BertLayers under <prefix>.bert.encoder.layer are pruned with the same per-linear rule as the language model.
