@@ -77,6 +77,33 @@ def peaks():
     return {"hbm": 6650.0, "tensor": 1650.0, "tensor_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def measure_tf32_peak(torch, dev, n=8192, reps=5):
+    """"TF32 peak not yet measured - the builder must measure it".  torch.matmul of two fp32 n^3 matrices
+    with allow_tf32 (cuBLAS TF32 tensor-core GEMM), best of `reps`, CUDA events: dense TF32 TFLOP/s of THIS GPU, the
+    denominator for the 3xTF32 GEMMs of K10 / K13 (executed flop = 3 x logical)."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize()
+            t = e0.elapsed_time(e1)
+            best = t if best is None or t < best else best
+        del a, b, c
+        return 2.0 * n ** 3 / best / 1e9
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled through NVML DURING the timed region (a few ms period)."""
 
@@ -221,8 +248,25 @@ def step_wanda(ctx, weights, inputs, method, shared=False):
     # alternate between two streams so that the ramp-up of one launch covers the drain + finalize of the previous one
     # (each stream has its own scratch).  Per-span events (eager pass only) need the launches on one stream.
     nstreams = 1 if ctx.events is not None else 2
+    batch_stats = ctx.world > 1 or os.environ.get("VLMC_BENCH_STATS_BATCH") == "1"
+    if batch_stats:
+        # several GPUs: a rank's share of a linear is a 40-100 us launch; ONE multi-tensor launch for the block has one
+        # ramp-up and one drain (vlmc_sqnorm_accum_batch).  Partial sums carry the divisor of the whole set (0, N_SEQ).
+        xs, ss = [], []
+        for leader, members in groups:
+            _, C, inp = shape[leader]
+            sl = flat[off:off + C]
+            off += C
+            xs.append(inputs[inp])
+            ss.append(sl)
+            for m in members:
+                scalers[m] = sl
+        n_local = xs[0].shape[0]
+        nb, bb = (0, N_SEQ) if ctx.world > 1 else (0, n_local)
+        ctx.timed("sqnorm_accum", sum(x.numel() * 2 for x in xs), lambda: native.sqnorm_accum_batch(xs, ss, nb, bb))
+        ctx.launches += 1
     with schedule_fork(ctx, nstreams) as fk:
-        for gi, (leader, members) in enumerate(groups):
+        for gi, (leader, members) in enumerate(groups if not batch_stats else []):
             _, C, inp = shape[leader]
             s = flat[off:off + C]
             off += C
@@ -435,7 +479,7 @@ def time_method(ctx, method, inputs, steps, warmup, sample_clocks, dist, use_gra
         k["work"] += work
         k["spans"] += 1
     ctx.events = None
-    out = {"ms_per_step": eager_ms, "eager_ms_per_step": eager_ms, "launches": ctx.launches, "kernels": kern,
+    out = {"ms_per_step": eager_ms, "eager_ms_per_step": eager_ms, "launches": ctx.launches, "kernels": kern, "method": method,
            "clocks": clocks, "steps": steps, "cuda_graph": False, "weight_sets": nsets, "world": ctx.world,
            "calib_batch": ctx.calib_batch, "shared": method.endswith("_shared"), "eager_step_ms": list(step_ms)}
 
@@ -486,18 +530,20 @@ def time_method(ctx, method, inputs, steps, warmup, sample_clocks, dist, use_gra
 
 
 def ncu_traffic(tag, res):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/ncu_traffic.json),
-    averaged over the launches of one step; None when no capture matches the timed launches."""
-    if tag != "sqnorm_accum" or res.get("world", 1) != 1 or res.get("calib_batch") != N_SEQ:
+    """DRAM bytes (read + write) of the span `tag` per step, from the committed ncu capture of the same bench command
+    (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py from `ncu --metrics dram__bytes_read.sum,
+    dram__bytes_write.sum`), divided by the spans per step: per launch like `achieved`.  None when no capture matches the
+    timed configuration (several GPUs, another calibration batch)."""
+    if res.get("world", 1) != 1 or res.get("calib_batch") != N_SEQ:
         return None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            cap = json.load(f)["sqnorm_accum"]["bytes_per_launch"]
-        dims = [INPUT_DIMS[inp] for _, _, _, inp in LINEARS]
-        if res.get("shared"):
-            dims = list(INPUT_DIMS.values())
-        return sum(cap[f"T{N_SEQ * SEQ_LEN}_C{c}"] for c in dims) / len(dims)
-    except (OSError, KeyError, ValueError):
+            cap = json.load(f)
+        method = res.get("method", "")
+        per_step = cap["per_step_bytes"][method][tag]
+        spans_per_step = res["kernels"][tag]["spans"] / max(res["steps"], 1)
+        return per_step / max(spans_per_step, 1)
+    except (OSError, KeyError, ValueError, TypeError):
         return None
 
 
@@ -523,10 +569,26 @@ def roofline_of(res, pk):
     else:
         achieved = k["work"] / (k["ms"] * 1e-3) / 1e12
         peak, unit = pk["tensor"], "TFLOP/s"
-    return {"bound": bound, "kernel": desc, "achieved": achieved, "peak": peak, "peak_source": pk["source"],
-            "unit": unit, "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(tag, res), "spans": k["spans"],
-            "avg_span_ms": k["ms"] / max(k["spans"], 1), "share_of_step": k["ms"] / total,
-            "spans_ms_per_step": {t: v["ms"] / res["steps"] for t, v in res["kernels"].items()}}
+    out = {"bound": bound, "kernel": desc, "achieved": achieved, "peak": peak, "peak_source": pk["source"],
+           "unit": unit, "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(tag, res), "spans": k["spans"],
+           "avg_span_ms": k["ms"] / max(k["spans"], 1), "share_of_step": k["ms"] / total,
+           "spans_ms_per_step": {t: v["ms"] / res["steps"] for t, v in res["kernels"].items()}}
+    if tag == "hessian_accum":
+        # the SYRK executes the upper 256 x 256 tiles only: executed flop next to the logical (full-square) figure
+        ex = 0.0
+        for _, _, C, _ in LINEARS:
+            nt = (C + 255) // 256
+            ex += 2.0 * N_SEQ * SEQ_LEN * (nt * (nt + 1) // 2) * 256.0 * 256.0
+        logical = sum(2.0 * N_SEQ * SEQ_LEN * C * C for _, _, C, _ in LINEARS)
+        out["executed_tflops"] = achieved * ex / logical
+        out["executed_frac_of_peak"] = out["executed_tflops"] / peak
+        out["note"] = "achieved = LOGICAL flop (full square, SURVEY 8d); the SYRK executes the upper tiles only: executed_tflops"
+    if tag in ("sparsegpt_chains", "chol_inv_upper", "obs_sweep") and pk.get("tf32"):
+        # 3xTF32: three tensor-core MMAs per logical product; quoted against the TF32 peak measured on this GPU
+        out["executed_tf32_tflops"] = 3.0 * achieved
+        out["tf32_peak_measured"] = pk["tf32"]
+        out["executed_frac_of_tf32_peak"] = 3.0 * achieved / pk["tf32"]
+    return out
 
 
 def run_gpu(args):
@@ -546,6 +608,15 @@ def run_gpu(args):
     s0, s1 = parallel.sample_range(N_SEQ, rank, world)
     inputs = make_inputs(torch, dev, s1 - s0, seed=1000 + 17 * rank)
     ctx = Ctx(torch, native, parallel, dev, rank, world, args.calib_batch)
+    if args.one_step:
+        # for `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` (scripts/ncu_traffic.py): exactly one eager step
+        # of --method on a fresh weight set, nothing else; never a bench value
+        w = make_block(torch, dev, seed=0)
+        torch.cuda.synchronize()
+        run_step(ctx, args.method, w, inputs)
+        torch.cuda.synchronize()
+        print(json.dumps({"one_step": args.method}), flush=True)
+        return
 
     main = time_method(ctx, args.method, inputs, args.steps, args.warmup, rank == 0, dist, not args.no_graph)
     others = {}
@@ -555,6 +626,16 @@ def run_gpu(args):
                 # the millisecond methods get enough steps to average out rank skew; SparseGPT steps are ~0.1 s each
                 r = time_method(ctx, m, inputs, 3 if m.startswith("sparsegpt") else 10, 3, rank == 0, dist, not args.no_graph)
                 others[m] = r
+    # the headline hands all 128 sequences to ONE add_batch per linear; the reference's hooks call once
+    # per sequence and vlmc's driver once per chunk of 16 stacked sequences (layerwise.stack_calibration).  Same step,
+    # eager launches (hooks cannot be graph-captured), for both.
+    calib = {}
+    if args.all_methods and world == 1:
+        for cb in (1, 16):
+            c2 = Ctx(torch, native, parallel, dev, rank, world, cb)
+            r = time_method(c2, args.method, inputs, 3, 3, False, dist, use_graph=False)
+            calib[str(cb)] = {"eager_ms_per_step": r["eager_ms_per_step"], "add_batch_calls_per_linear": N_SEQ // cb,
+                              "launches": r["launches"]}
     ctx.H = ctx.U = None
     torch.cuda.empty_cache()
 
@@ -579,6 +660,10 @@ def run_gpu(args):
 
     if rank == 0:
         pk = peaks()
+        try:
+            pk["tf32"] = measure_tf32_peak(torch, dev)
+        except Exception:  # noqa: BLE001
+            pk["tf32"] = None
         out = {
             "metric": METRIC, "value": main["ms_per_step"] / 1e3, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
@@ -596,7 +681,13 @@ def run_gpu(args):
             "e2e": {"value": e2e["ms"] / 1e3, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                     "d2h_bytes_per_step": e2e["d2h"]},
             "roofline": roofline_of(main, pk),
+            "peaks": {"hbm_gbs": pk["hbm"], "bf16_tflops": pk["tensor"], "bf16_tflops_sustained": pk["tensor_sustained"],
+                      "tf32_tflops_measured_here": pk.get("tf32"), "source": pk["source"]},
         }
+        if calib:
+            out["config"]["calib_batch_sweep"] = dict(calib, note="seconds per block of the same step with 1 / 16 sequences per "
+                                                      "add_batch call (eager launches): 1 = the reference's per-sample hooks, 16 = what "
+                                                      "vlmc's drop-in driver issues (calib_batch default)")
         if others:
             out["methods"] = {m: {"value": r["ms_per_step"] / 1e3, "unit": UNIT, "steps": r["steps"],
                                   "cuda_graph": r["cuda_graph"], "eager_ms_per_step": r["eager_ms_per_step"],
@@ -754,20 +845,38 @@ def run_e2e_sharded(torch, native, parallel, dev, args, rank, world, host_in, ho
     n_local = next(iter(host_in.values())).shape[0]
     dev_in = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host_in.items()}
 
+    # every rank moves 1 / world of the block over ITS PCIe link: its calibration sequences, its row shard of the weights
+    # up (the replicas are completed over NVLink with one all-gather per linear) and its row shard of the pruned weights
+    # and masks down - together the host receives exactly one copy of the result (every rank used to
+    # upload all weights and download all results through one host)
+    shard = {name: parallel.row_range(r, rank, world) for name, r, c, _ in LINEARS}
+    even = all(r % world == 0 for _, r, _, _ in LINEARS)
+    h2d = sum(h.numel() * 2 for h in host_in.values()) + sum((shard[n][1] - shard[n][0]) * c * 2 for n, r, c, _ in LINEARS)
+    d2h = sum((shard[n][1] - shard[n][0]) * c * (3 if args.method.split("_")[0] != "sparsegpt" else 2) for n, r, c, _ in LINEARS)
+    if not even:
+        h2d = sum(h.numel() * 2 for h in host_in.values()) + sum(w.numel() * 2 for w in host_w.values())
+
     def step():
+        dW = {name: torch.empty(r, c, dtype=torch.float16, device=dev) for name, r, c, _ in LINEARS}
         with torch.cuda.stream(copy_stream):
-            dW = {name: host_w[name].to(dev, non_blocking=True) for name in host_w}
+            for name in host_w:
+                a, b = shard[name] if even else (0, host_w[name].shape[0])
+                dW[name][a:b].copy_(host_w[name][a:b], non_blocking=True)
             for k in host_in:
                 for j in range(0, n_local, chunk):
                     dev_in[k][j:j + chunk].copy_(host_in[k][j:j + chunk], non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(copy_stream)
         main.wait_event(ready)
+        if even:
+            for name in host_w:
+                parallel.gather_rows(dW[name], rank, world)
         masks = run_step(ctx, args.method, dW, dev_in)
         for name in host_w:
-            host_out_w[name].copy_(dW[name], non_blocking=True)
+            a, b = shard[name]
+            host_out_w[name][a:b].copy_(dW[name][a:b], non_blocking=True)
             if masks:
-                host_out_m[name].copy_(masks[name], non_blocking=True)
+                host_out_m[name][a:b].copy_(masks[name][a:b], non_blocking=True)
 
     step()
     torch.cuda.synchronize()
@@ -1363,6 +1472,7 @@ def main():
     ap.add_argument("--calib-batch", type=int, default=N_SEQ,
                     help="sequences per add_batch call (reference hooks use 1; the wrapper API takes any b)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--one-step", action="store_true", help="run ONE eager step of --method and exit (ncu traffic captures)")
     ap.add_argument("--no-full-model", action="store_true", help="skip the whole-model runs through load_pruner().prune()")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only (no CUDA-graph replay pass)")
     ap.add_argument("--no-other-methods", dest="all_methods", action="store_false",

@@ -81,6 +81,18 @@ int vlmc_sqnorm_accum(const void* x, int dtype, int64_t T, int C, int64_t ldx,
                       void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * K1 for several linears in ONE launch (the 7 accumulations of a transformer block, or a rank's share of them when the
+ * calibration tokens are sharded over GPUs): same arithmetic and the same deterministic combine as vlmc_sqnorm_accum per
+ * item, one ramp-up and one drain.  count <= 16, one dtype per launch; ws of vlmc_sqnorm_accum_batch_workspace_bytes.
+ */
+typedef struct vlmc_stats_item {
+  const void* x; int64_t T; int C; int64_t ldx;
+  float* scaler_row; double n_before; double b;
+} vlmc_stats_item;
+size_t vlmc_sqnorm_accum_batch_workspace_bytes(const vlmc_stats_item* items, int count, int dtype);
+int vlmc_sqnorm_accum_batch(const vlmc_stats_item* items, int count, int dtype, void* ws, size_t ws_bytes, void* stream);
+
+/*
  * K2  DSnoT calibration statistics.  Replaces WrappedGPT.add_batch, dsnot_pruner.py:79-101.
  * x is treated as `nseg` consecutive add_batch calls of S rows each, every one with leading
  * batch dimension b_per_seg (nseg = 1 reproduces a single reference call exactly):

@@ -96,6 +96,31 @@ def test_sqnorm_batched_equals_per_sample(native):
     assert rel_elem(s1.cpu().numpy(), truth.cpu().numpy()) < REL
 
 
+def test_sqnorm_batch_equals_per_linear(native):
+    """vlmc_sqnorm_accum_batch (the accumulations of a block in ONE launch) against vlmc_sqnorm_accum per linear: the same
+    statistics to fp32 rounding of the final combine (the row chunking differs), mixed widths, a running update
+    (n_before > 0) and the token-sharded form (n_before = N, b = 0: a plain += sum / N)."""
+    shapes = [(3, 512, 4096), (3, 512, 4096), (3, 512, 11008), (3, 257, 1408)]
+    xs = [acts(b * S, C, 70 + i, torch.float16).cuda().view(b, S, C) for i, (b, S, C) in enumerate(shapes)]
+    for n_before, b in ((0, 3), (5, 3), (8, 0)):
+        ref = [torch.full((C,), 0.25, device="cuda") for _, _, C in shapes]
+        got = [r.clone() for r in ref]
+        for x, r in zip(xs, ref):
+            native.sqnorm_accum(x, r, n_before, b) if b > 0 else native.sqnorm_accum_batch([x], [r], n_before, b)
+        native.sqnorm_accum_batch(xs, got, n_before, b)
+        torch.cuda.synchronize()
+        for r, g, x in zip(ref, got, xs):
+            assert rel_inf(g.cpu().numpy(), r.cpu().numpy()) < 1e-6
+            if b == 0:      # += sum_t x^2 / n_before
+                want = 0.25 + (x.float() ** 2).sum((0, 1)).double() / n_before
+                assert rel_inf(g.cpu().numpy(), want.cpu().numpy()) < REL
+    a2 = [torch.zeros(C, device="cuda") for _, _, C in shapes]
+    b2 = [torch.zeros(C, device="cuda") for _, _, C in shapes]
+    native.sqnorm_accum_batch(xs, a2, 0, 3)
+    native.sqnorm_accum_batch(xs, b2, 0, 3)
+    assert all(torch.equal(u, v) for u, v in zip(a2, b2))            # deterministic
+
+
 def test_sqnorm_strided_rows_and_determinism(native):
     big = acts(300, 2 * 1024, 3, torch.bfloat16).cuda()
     x = big[:, :1024]                        # ldx = 2048 != C

@@ -12,7 +12,7 @@
 //                                           reference's backward (W dtype, then fp32): one read of G + mask per output,
 //                                           fp32 accumulation in a fixed order (deterministic)
 // The two dense GEMMs of the step (y = x W_eff^T, G = dy^T x) stay library GEMMs (cuBLAS through torch).
-#include "common.cuh"
+#include "lora_tile.cuh"
 
 namespace vlmc {
 
@@ -23,56 +23,58 @@ template <> __device__ __forceinline__ float round_dt<float>(float v) { return v
 template <> __device__ __forceinline__ float round_dt<__half>(float v) { return __half2float(__float2half_rn(v)); }
 template <> __device__ __forceinline__ float round_dt<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
+template <typename T> __device__ __forceinline__ float2 round_dt2(float2 v);
+template <> __device__ __forceinline__ float2 round_dt2<float>(float2 v) { return v; }
+template <> __device__ __forceinline__ float2 round_dt2<__half>(float2 v) { return __half22float2(__floats2half2_rn(v.x, v.y)); }
+template <> __device__ __forceinline__ float2 round_dt2<__nv_bfloat16>(float2 v) { return __bfloat1622float2(__floats2bfloat162_rn(v.x, v.y)); }
+
 // ---- K15 -------------------------------------------------------------------------------------------------
-template <typename T, int RK>
-__global__ void __launch_bounds__(kFwdThreads)
+// Same streaming tile loop as K14 (lora_tile.cuh): A staged in shared memory once per unit, four rows in flight per thread.
+template <typename T>
+__global__ void __launch_bounds__(kLtThreads, 5)
 lora_effective_weight_kernel(const T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ A,
                              const float* __restrict__ B, int rank, float scaling, const uint8_t* __restrict__ mask,
-                             int64_t ldm, int sparse, T* __restrict__ out, int64_t ldo) {
+                             int64_t ldm, int sparse, T* __restrict__ out, int64_t ldo, int coltiles, int units) {
   constexpr int V = Elem<T>::kVec;
-  const int col = (blockIdx.x * kFwdThreads + threadIdx.x) * V;
-  if (col >= C) return;
-  float a[RK > 0 ? RK : 1][V];
-  if (RK > 0) {
-#pragma unroll
-    for (int kk = 0; kk < RK; ++kk)
-#pragma unroll
-      for (int e = 0; e < V; ++e) a[kk][e] = kk < rank ? A[(int64_t)kk * C + col + e] : 0.f;
-  }
-  for (int row = blockIdx.y; row < R; row += gridDim.y) {
-    const uint4 wv = ld_stream(W + (int64_t)row * ldw + col);
-    const uint8_t* mp = mask + (int64_t)row * ldm + col;
-    uint32_t mb[2];
-    if (V == 8) { const uint2 t = *reinterpret_cast<const uint2*>(mp); mb[0] = t.x; mb[1] = t.y; }
-    else { mb[0] = *reinterpret_cast<const uint32_t*>(mp); mb[1] = 0; }
-    float f[V], acc[V];
-    Elem<T>::unpack(wv, f);
-#pragma unroll
-    for (int e = 0; e < V; ++e) acc[e] = 0.f;
-    const float* brow = B + (int64_t)row * rank;
-    if (RK > 0) {
-#pragma unroll
-      for (int kk = 0; kk < RK; ++kk) {
-        const float b = kk < rank ? __ldg(brow + kk) : 0.f;
-#pragma unroll
-        for (int e = 0; e < V; ++e) acc[e] = fmaf(b, a[kk][e], acc[e]);   // k ascending, like SGEMM
-      }
-    } else {
-      for (int kk = 0; kk < rank; ++kk) {
-        const float b = __ldg(brow + kk);
-#pragma unroll
-        for (int e = 0; e < V; ++e) acc[e] = fmaf(b, __ldg(A + (int64_t)kk * C + col + e), acc[e]);
-      }
+  extern __shared__ __align__(16) float4 lt_sA[];
+  // contiguous span of units per CTA, column tile major / row blocks fastest: A is staged once or twice per CTA
+  const int rowblocks = (R + kLtUnitRows - 1) / kLtUnitRows;
+  const int u0 = (int)((int64_t)blockIdx.x * units / gridDim.x), u1 = (int)((int64_t)(blockIdx.x + 1) * units / gridDim.x);
+  int staged_ct = -1;
+  for (int unit = u0; unit < u1; ++unit) {
+    const int ct = unit / rowblocks, rb = unit - ct * rowblocks;
+    const int col0 = ct * kLtThreads * V;
+    if (ct != staged_ct) {
+      __syncthreads();
+      lt_stage_a<T>(lt_sA, A, rank, C, col0);
+      __syncthreads();
+      staged_ct = ct;
     }
+    const int col = col0 + threadIdx.x * V;
+    if (col >= C) continue;
+    const int row_end = (rb + 1) * kLtUnitRows < R ? (rb + 1) * kLtUnitRows : R;
+    lt_rows<T>(W, ldw, out, ldo, col, rb * kLtUnitRows, row_end, B, rank, mask, ldm, lt_sA,
+               [&](float (&f)[V], const float (&acc)[V], const uint32_t (&mb)[2]) {
+                 // (B @ A).to(dtype) -> * scaling (rounded in dtype) -> W + . (rounded in dtype) -> * mask (exact).
+                 // The three roundings run on PAIRS (packed f32 -> 2 x 16-bit -> f32 conversions are full rate; the
+                 // scalar F2F form is a quarter-rate instruction and made this kernel conversion-bound: 6 per weight)
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const bool keep = (mb[e / 4] >> (8 * (e % 4))) & 0xffu;
-      // (B @ A).to(dtype) -> * scaling (rounded in dtype) -> W + . (rounded in dtype) -> * mask (exact)
-      const float d = round_dt<T>(__fmul_rn(round_dt<T>(acc[e]), scaling));
-      if (sparse) f[e] = keep ? round_dt<T>(__fadd_rn(f[e], d)) : 0.f;
-      else f[e] = round_dt<T>(__fadd_rn(keep ? f[e] : 0.f, d));
-    }
-    st_stream(out + (int64_t)row * ldo + col, Elem<T>::pack(f));
+                 for (int e = 0; e < V; e += 2) {
+                   const bool k0 = (mb[e / 4] >> (8 * (e % 4))) & 0xffu, k1 = (mb[(e + 1) / 4] >> (8 * ((e + 1) % 4))) & 0xffu;
+                   float2 d = round_dt2<T>(make_float2(acc[e], acc[e + 1]));
+                   d = round_dt2<T>(make_float2(__fmul_rn(d.x, scaling), __fmul_rn(d.y, scaling)));
+                   float2 r;
+                   if (sparse) {
+                     r = round_dt2<T>(make_float2(__fadd_rn(f[e], d.x), __fadd_rn(f[e + 1], d.y)));
+                     f[e] = k0 ? r.x : 0.f;
+                     f[e + 1] = k1 ? r.y : 0.f;
+                   } else {
+                     r = round_dt2<T>(make_float2(__fadd_rn(k0 ? f[e] : 0.f, d.x), __fadd_rn(k1 ? f[e + 1] : 0.f, d.y)));
+                     f[e] = r.x;
+                     f[e + 1] = r.y;
+                   }
+                 }
+               });
   }
 }
 
@@ -216,20 +218,29 @@ extern "C" int vlmc_sparselora_effective_weight(const void* W, int dtype, int R,
     return VLMC_ERR_UNSUPPORTED;
   if (!is_device_ptr(W) || !is_device_ptr(A) || !is_device_ptr(B) || !is_device_ptr(keep_mask) || !is_device_ptr(out))
     return VLMC_ERR_NOT_DEVICE;
-  const int coltiles = (C / V + kFwdThreads - 1) / kFwdThreads;
-  int rowblocks = (kNumSMs * 16 + coltiles - 1) / coltiles;
-  if (rowblocks > R) rowblocks = R;
-  if (rowblocks > 65535) rowblocks = 65535;
-  dim3 grid(coltiles, rowblocks);
+  if (rank > kLtMaxRank) return VLMC_ERR_UNSUPPORTED;
+  if (((uintptr_t)A & 15) != 0 || C % 4 != 0) return VLMC_ERR_UNSUPPORTED;
+  const int coltiles = (C / V + kLtThreads - 1) / kLtThreads;
+  const int64_t units64 = (int64_t)coltiles * ((R + kLtUnitRows - 1) / kLtUnitRows);
+  if (units64 > 0x7fffffff) return VLMC_ERR_UNSUPPORTED;
+  const int units = (int)units64;
   cudaStream_t st = (cudaStream_t)stream;
-#define VLMC_EFF(RK)                                                                                              \
-  VLMC_DISPATCH_DTYPE(dtype, (lora_effective_weight_kernel<scalar_t, RK><<<grid, kFwdThreads, 0, st>>>(          \
-                                 reinterpret_cast<const scalar_t*>(W), ldw, R, C, A, B, rank, scaling, keep_mask, \
-                                 ldm, sparse, reinterpret_cast<scalar_t*>(out), ldo)))
-  if (rank <= 4) { VLMC_EFF(4); }
-  else if (rank <= 8) { VLMC_EFF(8); }
-  else { VLMC_EFF(0); }
-#undef VLMC_EFF
+  VLMC_DISPATCH_DTYPE(dtype, {
+    auto kern = lora_effective_weight_kernel<scalar_t>;
+    const size_t smem = lt_smem_bytes<scalar_t>(rank);
+    static size_t attr = 0;
+    if (smem > attr) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lt_smem_bytes<scalar_t>(kLtMaxRank)) != cudaSuccess)
+        return check_launch();
+      attr = lt_smem_bytes<scalar_t>(kLtMaxRank);
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLtThreads, smem);
+    int grid = kNumSMs * (per_sm < 1 ? 1 : per_sm);
+    if (grid > units) grid = units;
+    kern<<<grid, kLtThreads, smem, st>>>(reinterpret_cast<const scalar_t*>(W), ldw, R, C, A, B, rank, scaling, keep_mask, ldm,
+                                         sparse, reinterpret_cast<scalar_t*>(out), ldo, coltiles, units);
+  });
   return check_launch();
 }
 

@@ -42,16 +42,14 @@ struct StatsParams {
 template <bool DSNOT> struct StatsOcc { static constexpr int kBlocksPerSM = DSNOT ? 4 : 8; };
 
 template <typename T, bool DSNOT, int kCX>
-__global__ void __launch_bounds__(kStatsThreads, StatsOcc<DSNOT>::kBlocksPerSM)
-colstats_kernel(const StatsParams p) {
+__device__ __forceinline__ void colstats_body(const StatsParams& p, const int ct, const int64_t chunk) {
   constexpr int V = Elem<T>::kVec;
   constexpr int kRY = kStatsThreads / kCX;
   const int tx = threadIdx.x % kCX;
   const int ty = threadIdx.x / kCX;
-  const int col0 = (blockIdx.x * kCX + tx) * V;
+  const int col0 = (ct * kCX + tx) * V;
   const bool col_ok = col0 < p.C;
   const int64_t nchunks = p.nseg * p.chunks_per_seg;
-  const int64_t chunk = blockIdx.y;
   const int64_t seg = chunk / p.chunks_per_seg;
   const int64_t cis = chunk % p.chunks_per_seg;
   const int64_t r0 = seg * p.S + cis * (int64_t)p.rows_per_chunk;
@@ -144,7 +142,7 @@ colstats_kernel(const StatsParams p) {
   __shared__ unsigned int s_ticket;
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[blockIdx.x], 1u);
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.tickets[ct], 1u);
   __syncthreads();
   if (s_ticket != (unsigned int)(nchunks - 1)) return;
   __threadfence();
@@ -152,7 +150,7 @@ colstats_kernel(const StatsParams p) {
   const double n_after = p.n_before + p.b_per_seg * (double)p.nseg;
   const float ratio = (float)(p.n_before / n_after);
   const float n_after_f = (float)n_after;
-  const int tile_c0 = blockIdx.x * kCX * V;
+  const int tile_c0 = ct * kCX * V;
   for (int c = tile_c0 + threadIdx.x; c < tile_c0 + kCX * V && c < p.C; c += kStatsThreads) {
     if (!DSNOT) {
       // the partials of all chunks, added in chunk order; loads are issued 16 at a time so the (serial, last-CTA) tail
@@ -215,7 +213,27 @@ colstats_kernel(const StatsParams p) {
       p.sum_row[c] = __fadd_rn(m, __fdiv_rn((float)tot_s, n_after_f));
     }
   }
-  if (threadIdx.x == 0) p.tickets[blockIdx.x] = 0u;  // leave the workspace clean
+  if (threadIdx.x == 0) p.tickets[ct] = 0u;  // leave the workspace clean
+}
+
+template <typename T, bool DSNOT, int kCX>
+__global__ void __launch_bounds__(kStatsThreads, StatsOcc<DSNOT>::kBlocksPerSM)
+colstats_kernel(const StatsParams p) {
+  colstats_body<T, DSNOT, kCX>(p, blockIdx.x, blockIdx.y);
+}
+
+// Several accumulations in ONE launch (the linears of a block): blockIdx.z picks the item, CTAs outside an item's own
+// (column tiles x chunks) rectangle exit at once.  On 8 GPUs a rank's share of a linear is a 40-100 us launch that spends
+// a fifth of its time ramping up and draining; one launch for the block has one ramp and one drain.
+constexpr int kStatsBatchMax = 16;
+struct StatsBatch { StatsParams it[kStatsBatchMax]; int coltiles[kStatsBatchMax]; int nchunks[kStatsBatchMax]; };
+
+template <typename T, bool DSNOT, int kCX>
+__global__ void __launch_bounds__(kStatsThreads, StatsOcc<DSNOT>::kBlocksPerSM)
+colstats_batch_kernel(const __grid_constant__ StatsBatch b) {
+  const int item = blockIdx.z;
+  if ((int)blockIdx.x >= b.coltiles[item] || (int)blockIdx.y >= b.nchunks[item]) return;
+  colstats_body<T, DSNOT, kCX>(b.it[item], blockIdx.x, blockIdx.y);
 }
 
 struct StatsPlan {
@@ -229,12 +247,12 @@ struct StatsPlan {
 // vs 5.93 / 7.09 with 64 lanes; DSnoT 16 lanes 4.93 / 6.16 TB/s vs 3.77 / 5.28 with 64.
 template <bool DSNOT> struct StatsTile { static constexpr int kCX = DSNOT ? 16 : 32; };
 
-static StatsPlan plan_stats(int dtype, int64_t nseg, int64_t S, int C, int kinds, int blocks_per_sm = 8) {
+static StatsPlan plan_stats(int dtype, int64_t nseg, int64_t S, int C, int kinds, int blocks_per_sm = 8, int64_t target = 0) {
   StatsPlan pl;
   const int V = dtype == VLMC_F32 ? 4 : 8;
   const int kCX = kinds == 3 ? StatsTile<true>::kCX : StatsTile<false>::kCX, kRY = kStatsThreads / kCX;
   pl.coltiles = (C + kCX * V - 1) / (kCX * V);
-  const int64_t target_ctas = (int64_t)kNumSMs * blocks_per_sm;  // exactly one resident wave
+  const int64_t target_ctas = target > 0 ? target : (int64_t)kNumSMs * blocks_per_sm;  // exactly one resident wave
   int64_t want = target_ctas / pl.coltiles;
   if (want < 1) want = 1;
   int64_t cps = want / nseg;
@@ -295,6 +313,62 @@ extern "C" int vlmc_sqnorm_accum(const void* x, int dtype, int64_t T, int C, int
                                  void* ws, size_t ws_bytes, void* stream) {
   return vlmc::launch_stats<false>(x, dtype, 1, T, C, ldx, scaler_row, nullptr, nullptr, nullptr,
                                    n_before, b, 0.0, ws, ws_bytes, stream);
+}
+
+extern "C" size_t vlmc_sqnorm_accum_batch_workspace_bytes(const vlmc_stats_item* items, int count, int dtype) {
+  using namespace vlmc;
+  if (!items || count < 1 || count > kStatsBatchMax) return 0;
+  size_t total = 0;
+  for (int i = 0; i < count; ++i) total += align_up(stats_workspace_bytes(0, items[i].T, items[i].C, 1), 256);
+  return total;
+}
+
+extern "C" int vlmc_sqnorm_accum_batch(const vlmc_stats_item* items, int count, int dtype, void* ws, size_t ws_bytes,
+                                       void* stream) {
+  using namespace vlmc;
+  if (!items || !ws || count < 1 || count > kStatsBatchMax) return VLMC_ERR_BAD_ARG;
+  if (dtype != VLMC_F32 && dtype != VLMC_F16 && dtype != VLMC_BF16) return VLMC_ERR_BAD_ARG;
+  if (!is_device_ptr(ws)) return VLMC_ERR_NOT_DEVICE;
+  const int V = dtype == VLMC_F32 ? 4 : 8;
+  double total_elems = 0.0;
+  for (int i = 0; i < count; ++i) {
+    const vlmc_stats_item& s = items[i];
+    if (!s.x || !s.scaler_row || s.T < 1 || s.C < 1 || s.ldx < s.C || s.b < 0 || s.n_before < 0 || s.n_before + s.b <= 0) return VLMC_ERR_BAD_ARG;
+    if (s.C % V != 0 || s.ldx % V != 0 || ((uintptr_t)s.x & 15) != 0) return VLMC_ERR_UNSUPPORTED;
+    if (!is_device_ptr(s.x) || !is_device_ptr(s.scaler_row)) return VLMC_ERR_NOT_DEVICE;
+    total_elems += (double)s.T * (double)s.C;
+  }
+  StatsBatch b;
+  char* base = reinterpret_cast<char*>(ws);
+  size_t used = 0;
+  int max_ct = 1, max_ch = 1;
+  const int64_t wave = (int64_t)kNumSMs * StatsOcc<false>::kBlocksPerSM;
+  for (int i = 0; i < count; ++i) {
+    const vlmc_stats_item& s = items[i];
+    // every item gets the share of ONE resident wave that its bytes have in the launch
+    int64_t target = (int64_t)((double)wave * ((double)s.T * (double)s.C / total_elems));
+    if (target < 1) target = 1;
+    StatsPlan pl = plan_stats(dtype, 1, s.T, s.C, 1, StatsOcc<false>::kBlocksPerSM, target);
+    if (pl.coltiles * sizeof(unsigned int) > VLMC_WS_COUNTER_BYTES || pl.nchunks > 65535) return VLMC_ERR_UNSUPPORTED;
+    const size_t need = align_up(pl.bytes, 256);
+    if (used + need > ws_bytes) return VLMC_ERR_WORKSPACE;
+    StatsParams& p = b.it[i];
+    p.x = s.x; p.ldx = s.ldx; p.C = s.C; p.S = s.T; p.nseg = 1;
+    p.chunks_per_seg = pl.chunks_per_seg; p.rows_per_chunk = pl.rows_per_chunk;
+    p.tickets = reinterpret_cast<unsigned int*>(base + used);
+    p.part = reinterpret_cast<float*>(base + used + VLMC_WS_COUNTER_BYTES);
+    p.scaler_row = s.scaler_row; p.sum_row = nullptr; p.mean = nullptr; p.var = nullptr;
+    p.n_before = s.n_before; p.b_per_seg = s.b; p.ntok_before = 0.0;
+    b.coltiles[i] = pl.coltiles;
+    b.nchunks[i] = (int)pl.nchunks;
+    max_ct = pl.coltiles > max_ct ? pl.coltiles : max_ct;
+    max_ch = (int)pl.nchunks > max_ch ? (int)pl.nchunks : max_ch;
+    used += need;
+  }
+  dim3 grid(max_ct, max_ch, count);
+  cudaStream_t st = (cudaStream_t)stream;
+  VLMC_DISPATCH_DTYPE(dtype, (colstats_batch_kernel<scalar_t, false, StatsTile<false>::kCX><<<grid, kStatsThreads, 0, st>>>(b)));
+  return check_launch();
 }
 
 extern "C" int vlmc_dsnot_stats(const void* x, int dtype, int64_t nseg, int64_t S, int C, int64_t ldx,

@@ -727,18 +727,20 @@ static int sel_common_checks(void* W, int dtype, int R, int C, int64_t ldw, cons
 // heavy ties, an outlier row whose k-th score falls in the overflow bin) take an exact radix select on the score bits
 // and then on the column index, in the same shared memory.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kRcThreads = 256;
+constexpr int kRcThreads = 128;           // 4 warps per row: the per-row bookkeeping (scan, ranking, barriers) is amortised
+                                          // over 32+ weights per thread, and 5 independent rows are resident per SM
 constexpr int kRcWarps = kRcThreads / 32;
 constexpr int kRcBins = 2048;
 constexpr int kRcCand = 256;
-constexpr int kRcMaxVec = 8;              // 16-byte vectors per thread held in registers: C <= 256 * 8 * V
+constexpr int kRcWin = 6;                 // candidates are collected in pass 1 from bins [predicted - 6, predicted + 6]
+constexpr int kRcMaxVec = 16;             // 16-byte vectors per thread held in registers: C <= 128 * 16 * V
 
 struct RcShared {
   float wsum[kRcWarps];
   uint32_t wmax[kRcWarps];
   uint32_t scan[kRcWarps + 2];
   uint32_t ncand, sel_bin, sel_before, thr_key;
-  int thr_col;
+  int thr_col, ties_simple, in_window;
 };
 
 // One warp: bin (among kRcBins counters) that holds the kk-th (1-indexed) entry and the count before it -> sh.sel_bin,
@@ -791,8 +793,49 @@ __device__ __forceinline__ void rc_find_bin(uint32_t* hist, uint32_t kk, RcShare
   before = sh.sel_before;
 }
 
-template <typename T, int NV>
-__global__ void __launch_bounds__(kRcThreads, NV <= 4 ? 3 : 2)
+// bin of a score as the low bits of (min(score * scale, 2047) + 2^23): round-to-nearest instead of floor - still monotone
+// in the score - with full-rate FMUL / FMNMX / FADD instead of a quarter-rate F2I; a NaN score lands in the last bin
+constexpr uint32_t kRcMagic = 0x4B000000u;                   // bits of 8388608.0f
+__device__ __forceinline__ uint32_t rc_binbits(uint32_t key, float scale) {
+  const float x = fminf(__fmul_rn(__uint_as_float(key), scale), (float)(kRcBins - 1));
+  return __float_as_uint(__fadd_rn(x, 8388608.0f));            // kRcMagic | bin
+}
+
+// scores of one 16-byte vector of weights: key[e] = bits(|w[e]| * sq[col + e]) (non-negative floats order like their bits)
+template <typename T>
+__device__ __forceinline__ void rc_keys(const uint4& wv, const float* __restrict__ sqv, uint32_t (&key)[Elem<T>::kVec]) {
+  constexpr int V = Elem<T>::kVec;
+  float f[V];
+  Elem<T>::unpack(wv, f);
+#pragma unroll
+  for (int q = 0; q < V / 4; ++q) {
+    const float4 sv = __ldg(reinterpret_cast<const float4*>(sqv) + q);
+    key[4 * q] = __float_as_uint(__fmul_rn(fabsf(f[4 * q]), sv.x));
+    key[4 * q + 1] = __float_as_uint(__fmul_rn(fabsf(f[4 * q + 1]), sv.y));
+    key[4 * q + 2] = __float_as_uint(__fmul_rn(fabsf(f[4 * q + 2]), sv.z));
+    key[4 * q + 3] = __float_as_uint(__fmul_rn(fabsf(f[4 * q + 3]), sv.w));
+  }
+}
+
+// zero the pruned elements of a packed vector without unpacking it: pm bit e = element e is pruned
+template <typename T>
+__device__ __forceinline__ uint4 rc_zero(const uint4& wv, uint32_t pm) {
+  uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+  if (Elem<T>::kVec == 8) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t keep = ((pm >> (2 * i)) & 1u ? 0u : 0x0000ffffu) | ((pm >> (2 * i + 1)) & 1u ? 0u : 0xffff0000u);
+      w[i] &= keep;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = (pm >> i) & 1u ? 0u : w[i];
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <typename T, int NV, bool FULL>      // FULL: C / V == NV * 128, no bounds checks on the vectors
+__global__ void __launch_bounds__(kRcThreads, NV <= 4 ? 5 : (NV <= 8 ? 4 : 3))
 rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ sq, int k, int zero_w,
                      uint8_t* __restrict__ mask, int64_t ldm, float* __restrict__ row_sum) {
   constexpr int V = Elem<T>::kVec;
@@ -803,54 +846,40 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
   uint32_t* hist = keys + (size_t)C;                          // [kRcBins]
   uint32_t* cand_key = hist + kRcBins;                        // [kRcCand]
   uint32_t* cand_col = cand_key + kRcCand;                    // [kRcCand]
+  uint32_t* cand_bin = cand_col + kRcCand;                    // [kRcCand]  kRcMagic | bin
   __shared__ RcShared sh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int b = tid; b < kRcBins; b += kRcThreads) hist[b] = 0;
   if (tid == 0) sh.ncand = 0;
 
+#define RC_HAS(u) (FULL || (u) < NV - 1 || tid + (u) * kRcThreads < nvec)
   auto load_row = [&](int row, uint4 (&wv)[NV]) {
     const T* wrow = W + (int64_t)row * ldw;
 #pragma unroll
-    for (int u = 0; u < NV; ++u) {
-      const int vi = tid + u * kRcThreads;
-      if (vi < nvec) wv[u] = ld_stream(wrow + (int64_t)vi * V);
-    }
-  };
-  auto bin_of = [](uint32_t key, float scale) -> uint32_t {
-    const float x = __fmul_rn(__uint_as_float(key), scale);
-    const uint32_t b = (uint32_t)x;                           // x >= 0 (or NaN -> 0); monotone in key
-    return b < (uint32_t)kRcBins ? b : (uint32_t)kRcBins - 1;
+    for (int u = 0; u < NV; ++u)
+      if (RC_HAS(u)) wv[u] = ld_stream(wrow + (int64_t)(tid + u * kRcThreads) * V);
   };
 
   // scale of the first row of this CTA: from its own maximum (one extra pass over the registers)
   float scale = 0.f;
   {
     const int row = blockIdx.x;
+    uint32_t lmax = 0;
     if (row < R) {
       uint4 wv[NV];
       load_row(row, wv);
-      uint32_t lmax = 0;
 #pragma unroll
       for (int u = 0; u < NV; ++u) {
-        const int vi = tid + u * kRcThreads;
-        if (vi < nvec) {
-          float f[V];
-          Elem<T>::unpack(wv[u], f);
+        if (RC_HAS(u)) {
+          uint32_t key[V];
+          rc_keys<T>(wv[u], sq + (tid + u * kRcThreads) * V, key);
 #pragma unroll
-          for (int q = 0; q < V / 4; ++q) {
-            const float4 sv = __ldg(reinterpret_cast<const float4*>(sq + vi * V) + q);
-            const float se[4] = {sv.x, sv.y, sv.z, sv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t kq = __float_as_uint(__fmul_rn(fabsf(f[q * 4 + e]), se[e])) & 0x7fffffffu;
-              lmax = kq > lmax ? kq : lmax;
-            }
-          }
+          for (int e = 0; e < V; ++e) lmax = key[e] > lmax ? key[e] : lmax;
         }
       }
-      lmax = __reduce_max_sync(0xffffffffu, lmax);
-      if (lane == 0) sh.wmax[warp] = lmax;
     }
+    lmax = __reduce_max_sync(0xffffffffu, lmax);
+    if (lane == 0) sh.wmax[warp] = lmax;
     __syncthreads();
     uint32_t rmax = 0;
 #pragma unroll
@@ -858,190 +887,266 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
     if (rmax > 0u && rmax < 0x7f800000u) scale = (float)kRcBins / (1.25f * __uint_as_float(rmax));
     __syncthreads();
   }
+  // predicted bin of the k-th score: unknown for the first row (an empty window: that row takes the collect pass)
+  uint32_t win_lo = 1, win_span = 0;                           // window = bins [win_lo, win_lo + win_span), as kRcMagic | bin
 
   for (int row = blockIdx.x; row < R; row += gridDim.x) {
     T* wrow = W + (int64_t)row * ldw;
     uint4 wv[NV];
     load_row(row, wv);
-    // ---- P1: score, keys -> smem, row sum / max, linear-bin histogram
+    // ---- P1: score, keys -> smem, row sum / max, linear-bin histogram, candidates of the predicted window
     float lsum = 0.f;
     uint32_t lmax = 0;
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
-      const int vi = tid + u * kRcThreads;
-      if (vi < nvec) {
-        float f[V];
-        Elem<T>::unpack(wv[u], f);
+      if (RC_HAS(u)) {
+        const int vi = tid + u * kRcThreads;
+        uint32_t key[V];
+        rc_keys<T>(wv[u], sq + vi * V, key);
+        bool any = false;
+        uint32_t bb[V];
 #pragma unroll
-        for (int q = 0; q < V / 4; ++q) {
-          const float4 sv = __ldg(reinterpret_cast<const float4*>(sq + vi * V) + q);
-          const float se[4] = {sv.x, sv.y, sv.z, sv.w};
-          uint32_t kq[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float sc = __fmul_rn(fabsf(f[q * 4 + e]), se[e]);
-            kq[e] = __float_as_uint(sc) & 0x7fffffffu;
-            lsum += sc;
-            lmax = kq[e] > lmax ? kq[e] : lmax;
-            atomicAdd(&hist[bin_of(kq[e], scale)], 1u);
-          }
-          *reinterpret_cast<uint4*>(keys + ((size_t)q * nvec + vi) * 4) = make_uint4(kq[0], kq[1], kq[2], kq[3]);
+        for (int e = 0; e < V; ++e) {
+          lsum += __uint_as_float(key[e]);
+          lmax = key[e] > lmax ? key[e] : lmax;
+          bb[e] = rc_binbits(key[e], scale);
+          atomicAdd(&hist[bb[e] & (uint32_t)(kRcBins - 1)], 1u);
+          any |= (bb[e] - win_lo) < win_span;
         }
+        if (any) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            if ((bb[e] - win_lo) < win_span) {
+              const uint32_t pos = atomicAdd(&sh.ncand, 1u);
+              if (pos < (uint32_t)kRcCand) { cand_key[pos] = key[e]; cand_col[pos] = (uint32_t)(vi * V + e); cand_bin[pos] = bb[e]; }
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < V / 4; ++q)
+          *reinterpret_cast<uint4*>(keys + ((size_t)q * nvec + vi) * 4) = make_uint4(key[4 * q], key[4 * q + 1], key[4 * q + 2], key[4 * q + 3]);
       }
     }
     lsum = warp_sum(lsum);
     lmax = __reduce_max_sync(0xffffffffu, lmax);
     if (lane == 0) { sh.wsum[warp] = lsum; sh.wmax[warp] = lmax; }
-    __syncthreads();                                           // barrier A: histogram, partial sums
+    __syncthreads();                                           // barrier A: histogram, candidates, partial sums
     uint32_t rmax = 0;
 #pragma unroll
     for (int w = 0; w < kRcWarps; ++w) rmax = sh.wmax[w] > rmax ? sh.wmax[w] : rmax;
-    if (tid == 0) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < kRcWarps; ++w) t += sh.wsum[w];
-      row_sum[row] = t;
-      sh.ncand = 0;
-    }
     const bool select = k > 0 && k < C;
-    // ---- P2: the bin of the k-th smallest score
-    if (warp == 0) rc_scan_warp(hist, select ? (uint32_t)k : 1u, sh);
-    __syncthreads();                                           // barrier B: sel_bin / sel_before, counters cleared
-    uint32_t thr_key = 0;
-    int thr_col = -1;                                          // prune (key < thr_key) || (key == thr_key && col <= thr_col)
-    if (k >= C) {
-      thr_key = 0xffffffffu;
-    } else if (k > 0) {
-      const uint32_t b_sel = sh.sel_bin;
-      const uint32_t kk = (uint32_t)k - sh.sel_before;         // 1-indexed rank inside the bin
-      // ---- P3: collect the bin's keys
+    // ---- P2 (warp 0): the bin of the k-th smallest score; when it lies in the window, the exact threshold pair too
+    if (warp == 0) {
+      if (lane == 0) {
+        float t = 0.f;
 #pragma unroll
-      for (int u = 0; u < NV; ++u) {
-        const int vi = tid + u * kRcThreads;
-        if (vi < nvec) {
-#pragma unroll
-          for (int q = 0; q < V / 4; ++q) {
-            const uint4 kq = *reinterpret_cast<const uint4*>(keys + ((size_t)q * nvec + vi) * 4);
-            const uint32_t ke[4] = {kq.x, kq.y, kq.z, kq.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (bin_of(ke[e], scale) == b_sel) {
-                const uint32_t pos = atomicAdd(&sh.ncand, 1u);
-                if (pos < (uint32_t)kRcCand) { cand_key[pos] = ke[e]; cand_col[pos] = (uint32_t)(vi * V + q * 4 + e); }
-              }
-            }
-          }
-        }
+        for (int w = 0; w < kRcWarps; ++w) t += sh.wsum[w];
+        row_sum[row] = t;
       }
-      __syncthreads();                                         // barrier C: candidate list
+      rc_scan_warp(hist, select ? (uint32_t)k : 1u, sh);
+      __syncwarp();
+      const uint32_t want = kRcMagic | sh.sel_bin;
       const uint32_t nc = sh.ncand;
-      if (nc <= (uint32_t)kRcCand) {
-        // every warp ranks the candidates itself: the threshold pair lands in registers without another barrier
+      const bool inwin = select && (want - win_lo) < win_span && nc <= (uint32_t)kRcCand;
+      if (inwin) {
+        // rank the candidates of bin `want` on (score, column): the stable-sort order; rank kk - 1 is the threshold
+        const uint32_t kk = (uint32_t)k - sh.sel_before;
         uint32_t fk = 0, fc = 0;
-        bool found = false;
         for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
           const uint32_t i = c0 + lane;
-          const uint32_t mk = i < nc ? cand_key[i] : 0xffffffffu, mc = i < nc ? cand_col[i] : 0xffffffffu;
+          const bool mine = i < nc && cand_bin[i] == want;
+          const uint32_t mk = mine ? cand_key[i] : 0xffffffffu, mc = mine ? cand_col[i] : 0xffffffffu;
           uint32_t rank = 0;
-          for (uint32_t j = 0; j < nc; ++j) {
-            const uint32_t ok = cand_key[j], oc = cand_col[j];
-            rank += (ok < mk || (ok == mk && oc < mc)) ? 1u : 0u;
+          if (__any_sync(0xffffffffu, mine)) {
+            for (uint32_t j = 0; j < nc; ++j) {
+              const uint32_t ok = cand_key[j], oc = cand_col[j];
+              rank += (cand_bin[j] == want && (ok < mk || (ok == mk && oc < mc))) ? 1u : 0u;
+            }
           }
-          const bool hit = i < nc && rank == kk - 1;
-          const uint32_t ball = __ballot_sync(0xffffffffu, hit);
+          const uint32_t ball = __ballot_sync(0xffffffffu, mine && rank == kk - 1);
           if (ball) {
             const int src = __ffs(ball) - 1;
             fk = __shfl_sync(0xffffffffu, mk, src);
             fc = __shfl_sync(0xffffffffu, mc, src);
-            found = true;
           }
         }
-        (void)found;
-        thr_key = fk;
-        thr_col = (int)fc;
+        uint32_t kept_eq = 0;                                  // an equal key at a higher column stays: P4 needs the column
+        for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
+          const uint32_t i = c0 + lane;
+          kept_eq |= __ballot_sync(0xffffffffu, i < nc && cand_key[i] == fk && cand_col[i] > fc);
+        }
+        if (lane == 0) { sh.thr_key = fk; sh.thr_col = (int)fc; sh.ties_simple = kept_eq == 0; }
+      }
+      if (lane == 0) { sh.in_window = inwin ? 1 : 0; sh.ncand = 0; }
+    }
+    __syncthreads();                                           // barrier B: sel_bin / threshold, counters cleared
+    uint32_t thr_key = 0;
+    int thr_col = -1;                                          // prune (key < thr_key) || (key == thr_key && col <= thr_col)
+    bool ties_simple = true;                                   // every key equal to thr_key is pruned: one compare in P4
+    const uint32_t b_sel = sh.sel_bin;
+    if (k >= C) {
+      thr_key = 0xffffffffu;
+    } else if (k > 0) {
+      if (sh.in_window) {
+        thr_key = sh.thr_key; thr_col = sh.thr_col; ties_simple = sh.ties_simple != 0;
       } else {
-        // ---- exact radix select on the score bits (31 significant bits: 11 + 11 + 9), then on the column index
-        uint32_t prefix = 0, kr = (uint32_t)k, before = 0, bsel = 0;
-#pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-          const int shift = pass == 0 ? 20 : (pass == 1 ? 9 : 0);
-          const uint32_t himask = pass == 0 ? 0u : (pass == 1 ? 0xfff00000u : 0xfffffe00u);
-          const uint32_t bmask = pass == 2 ? 0x1ffu : 0x7ffu;
-          for (int j = tid; j < C; j += kRcThreads) {
-            const uint32_t key = keys[j];
-            if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & bmask], 1u);
-          }
-          rc_find_bin(hist, kr, sh, bsel, before);
-          kr -= before;
-          prefix |= bsel << shift;
-        }
-        // prefix = the k-th smallest key; kr = how many of the keys equal to it are pruned (lowest columns first)
-        uint32_t cprefix = 0;
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {                  // columns < 2^22: 11 + 11 bits
-          const int shift = pass == 0 ? 11 : 0;
-          for (int j = tid; j < C; j += kRcThreads) {
-            if (keys[j] == prefix) {
-              const int plane = j / (nvec * 4), rem = j - plane * nvec * 4;
-              const uint32_t col = (uint32_t)((rem >> 2) * V + plane * 4 + (rem & 3));
-              if (pass == 0 || (col >> 11) == cprefix) atomicAdd(&hist[(col >> shift) & 0x7ffu], 1u);
+        // ---- the window missed (first row of the CTA, a row unlike its predecessor): collect the bin's keys now
+        const uint32_t want = kRcMagic | b_sel;
+        const uint32_t kk = (uint32_t)k - sh.sel_before;       // 1-indexed rank inside the bin
+#pragma unroll
+        for (int u = 0; u < NV; ++u) {
+          if (RC_HAS(u)) {
+            const int vi = tid + u * kRcThreads;
+            uint32_t ke[V];
+            bool any = false;
+#pragma unroll
+            for (int q = 0; q < V / 4; ++q) {
+              const uint4 kq = *reinterpret_cast<const uint4*>(keys + ((size_t)q * nvec + vi) * 4);
+              ke[4 * q] = kq.x; ke[4 * q + 1] = kq.y; ke[4 * q + 2] = kq.z; ke[4 * q + 3] = kq.w;
+            }
+#pragma unroll
+            for (int e = 0; e < V; ++e) any |= rc_binbits(ke[e], scale) == want;
+            if (any) {
+#pragma unroll
+              for (int e = 0; e < V; ++e) {
+                if (rc_binbits(ke[e], scale) == want) {
+                  const uint32_t pos = atomicAdd(&sh.ncand, 1u);
+                  if (pos < (uint32_t)kRcCand) { cand_key[pos] = ke[e]; cand_col[pos] = (uint32_t)(vi * V + e); }
+                }
+              }
             }
           }
-          rc_find_bin(hist, kr, sh, bsel, before);
-          kr -= before;
-          if (pass == 0) cprefix = bsel;
         }
-        thr_key = prefix;
-        thr_col = (int)((cprefix << 11) | bsel);
+        __syncthreads();                                       // candidate list
+        const uint32_t nc = sh.ncand;
+        __syncthreads();
+        if (tid == 0) sh.ncand = 0;
+        if (nc <= (uint32_t)kRcCand) {
+          uint32_t fk = 0, fc = 0;
+          for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
+            const uint32_t i = c0 + lane;
+            const uint32_t mk = i < nc ? cand_key[i] : 0xffffffffu, mc = i < nc ? cand_col[i] : 0xffffffffu;
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < nc; ++j) {
+              const uint32_t ok = cand_key[j], oc = cand_col[j];
+              rank += (ok < mk || (ok == mk && oc < mc)) ? 1u : 0u;
+            }
+            const uint32_t ball = __ballot_sync(0xffffffffu, i < nc && rank == kk - 1);
+            if (ball) {
+              const int src = __ffs(ball) - 1;
+              fk = __shfl_sync(0xffffffffu, mk, src);
+              fc = __shfl_sync(0xffffffffu, mc, src);
+            }
+          }
+          thr_key = fk;
+          thr_col = (int)fc;
+          uint32_t kept_eq = 0;
+          for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
+            const uint32_t i = c0 + lane;
+            kept_eq |= __ballot_sync(0xffffffffu, i < nc && cand_key[i] == fk && cand_col[i] > fc);
+          }
+          ties_simple = kept_eq == 0;
+          __syncthreads();                                     // everyone has read the list before the next row refills it
+        } else {
+          // ---- exact radix select on the score bits (31 significant bits: 11 + 11 + 9), then on the column index
+          uint32_t prefix = 0, kr = (uint32_t)k, before = 0, bsel = 0;
+#pragma unroll 1
+          for (int pass = 0; pass < 3; ++pass) {
+            const int shift = pass == 0 ? 20 : (pass == 1 ? 9 : 0);
+            const uint32_t himask = pass == 0 ? 0u : (pass == 1 ? 0xfff00000u : 0xfffffe00u);
+            const uint32_t bmask = pass == 2 ? 0x1ffu : 0x7ffu;
+            for (int j = tid; j < C; j += kRcThreads) {
+              const uint32_t key = keys[j];
+              if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & bmask], 1u);
+            }
+            rc_find_bin(hist, kr, sh, bsel, before);
+            kr -= before;
+            prefix |= bsel << shift;
+          }
+          // prefix = the k-th smallest key; kr = how many of the keys equal to it are pruned (lowest columns first)
+          uint32_t cprefix = 0;
+#pragma unroll 1
+          for (int pass = 0; pass < 2; ++pass) {                // columns < 2^22: 11 + 11 bits
+            const int shift = pass == 0 ? 11 : 0;
+            for (int j = tid; j < C; j += kRcThreads) {
+              if (keys[j] == prefix) {
+                const int plane = j / (nvec * 4), rem = j - plane * nvec * 4;
+                const uint32_t col = (uint32_t)((rem >> 2) * V + plane * 4 + (rem & 3));
+                if (pass == 0 || (col >> 11) == cprefix) atomicAdd(&hist[(col >> shift) & 0x7ffu], 1u);
+              }
+            }
+            rc_find_bin(hist, kr, sh, bsel, before);
+            kr -= before;
+            if (pass == 0) cprefix = bsel;
+          }
+          thr_key = prefix;
+          thr_col = (int)((cprefix << 11) | bsel);
+          ties_simple = false;
+          __syncthreads();
+        }
       }
     }
 
-    // ---- P4: apply
+    // ---- P4: apply (weights are zeroed in their packed form; no unpack / repack)
     uint8_t* mrow = mask + (int64_t)row * ldm;
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
-      const int vi = tid + u * kRcThreads;
-      if (vi < nvec) {
-        float f[V];
-        Elem<T>::unpack(wv[u], f);
-        uint32_t mb[V / 4];
-        bool any = false;
+      if (RC_HAS(u)) {
+        const int vi = tid + u * kRcThreads;
+        uint32_t pm = 0;                                       // bit e: element e pruned
 #pragma unroll
         for (int q = 0; q < V / 4; ++q) {
           const uint4 kq = *reinterpret_cast<const uint4*>(keys + ((size_t)q * nvec + vi) * 4);
           const uint32_t ke[4] = {kq.x, kq.y, kq.z, kq.w};
-          uint32_t bytes = 0;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int col = vi * V + q * 4 + e;
-            const bool pruned = ke[e] < thr_key || (ke[e] == thr_key && col <= thr_col);
-            if (pruned) { f[q * 4 + e] = 0.f; any = true; }
-            bytes |= (pruned ? 0u : 1u) << (8 * e);
+            bool pruned;
+            if (ties_simple) pruned = k > 0 && ke[e] <= thr_key;
+            else pruned = ke[e] < thr_key || (ke[e] == thr_key && vi * V + q * 4 + e <= thr_col);
+            pm |= (pruned ? 1u : 0u) << (q * 4 + e);
           }
-          mb[q] = bytes;
         }
-        if (V == 8) st_stream8(mrow + (int64_t)vi * V, make_uint2(mb[0], mb[V / 4 - 1]));
-        else st_stream4(mrow + (int64_t)vi * V, mb[0]);
-        if (zero_w && any) st_stream(wrow + (int64_t)vi * V, Elem<T>::pack(f));
+        // mask bytes: 1 = kept
+        const uint32_t m0 = (~pm) & 0xfu, m1 = ((~pm) >> 4) & 0xfu;
+        const uint32_t b0 = (m0 & 1u) | ((m0 & 2u) << 7) | ((m0 & 4u) << 14) | ((m0 & 8u) << 21);
+        if (V == 8) {
+          const uint32_t b1 = (m1 & 1u) | ((m1 & 2u) << 7) | ((m1 & 4u) << 14) | ((m1 & 8u) << 21);
+          st_stream8(mrow + (int64_t)vi * V, make_uint2(b0, b1));
+        } else {
+          st_stream4(mrow + (int64_t)vi * V, b0);
+        }
+        if (zero_w && pm) st_stream(wrow + (int64_t)vi * V, rc_zero<T>(wv[u], pm));
       }
     }
-    // next row's scale: this row's maximum (rows of one matrix share sq and the weight distribution)
-    scale = (rmax > 0u && rmax < 0x7f800000u) ? (float)kRcBins / (1.25f * __uint_as_float(rmax)) : 0.f;
+    // next row: scale from this row's maximum, window around where this row's k-th score WOULD fall under that scale
+    // (rows of one matrix share sq and the weight distribution; a miss only costs the collect pass)
+    const float nscale = (rmax > 0u && rmax < 0x7f800000u) ? (float)kRcBins / (1.25f * __uint_as_float(rmax)) : 0.f;
+    if (select && nscale > 0.f && thr_key < 0x7f800000u) {
+      const uint32_t pb = rc_binbits(thr_key, nscale) & (uint32_t)(kRcBins - 1);
+      const uint32_t lo = pb > (uint32_t)kRcWin ? pb - kRcWin : 0u;
+      const uint32_t hi = pb + kRcWin < (uint32_t)kRcBins ? pb + kRcWin : (uint32_t)kRcBins - 1;
+      win_lo = kRcMagic | lo;
+      win_span = hi - lo + 1;
+    } else {
+      win_lo = 1; win_span = 0;
+    }
+    scale = nscale;
   }
+#undef RC_HAS
 }
 
 template <typename T>
 static bool rowselect_cta_fits(int C) {
   constexpr int V = Elem<T>::kVec;
-  const size_t smem = ((size_t)C + kRcBins + 2 * kRcCand) * sizeof(uint32_t);
+  const size_t smem = ((size_t)C + kRcBins + 3 * kRcCand) * sizeof(uint32_t);
   return C / V <= kRcThreads * kRcMaxVec && smem <= 200 * 1024 && C < (1 << 22);
 }
 
-template <typename T, int NV>
+template <typename T, int NV, bool FULL>
 static int launch_rowselect_cta_nv(void* W, int R, int C, int64_t ldw, const float* sq, int k, int zero_w,
                                    uint8_t* mask, int64_t ldm, float* row_sum, cudaStream_t st) {
-  auto kern = rowselect_cta_kernel<T, NV>;
-  const size_t smem = ((size_t)C + kRcBins + 2 * kRcCand) * sizeof(uint32_t);
+  auto kern = rowselect_cta_kernel<T, NV, FULL>;
+  const size_t smem = ((size_t)C + kRcBins + 3 * kRcCand) * sizeof(uint32_t);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess)
@@ -1065,13 +1170,17 @@ static int launch_rowselect_cta(void* W, int R, int C, int64_t ldw, const float*
                                 uint8_t* mask, int64_t ldm, float* row_sum, cudaStream_t st) {
   constexpr int V = Elem<T>::kVec;
   const int nv = (C / V + kRcThreads - 1) / kRcThreads;
-#define VLMC_RC(NV) return launch_rowselect_cta_nv<T, NV>(W, R, C, ldw, sq, k, zero_w, mask, ldm, row_sum, st)
+  const bool full = (C / V) % kRcThreads == 0;
+#define VLMC_RC(NV)                                                                                               \
+  return full ? launch_rowselect_cta_nv<T, NV, true>(W, R, C, ldw, sq, k, zero_w, mask, ldm, row_sum, st)         \
+              : launch_rowselect_cta_nv<T, NV, false>(W, R, C, ldw, sq, k, zero_w, mask, ldm, row_sum, st)
   if (nv <= 1) VLMC_RC(1);
   if (nv <= 2) VLMC_RC(2);
-  if (nv <= 3) VLMC_RC(3);
   if (nv <= 4) VLMC_RC(4);
-  if (nv <= 6) VLMC_RC(6);
-  VLMC_RC(8);
+  if (nv <= 5) VLMC_RC(5);
+  if (nv <= 8) VLMC_RC(8);
+  if (nv <= 11) VLMC_RC(11);
+  VLMC_RC(16);
 #undef VLMC_RC
 }
 

@@ -39,6 +39,8 @@ SIGNATURES = {
     "vlmc_last_cuda_error": (_i, []),
     "vlmc_workspace_bytes": (_sz, [_i, _i64, _i64, _i64]),
     "vlmc_sqnorm_accum": (_i, [_vp, _i, _i64, _i, _i64, _vp, _d, _d, _vp, _sz, _vp]),
+    "vlmc_sqnorm_accum_batch_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "vlmc_sqnorm_accum_batch": (_i, [_vp, _i, _i, _vp, _sz, _vp]),
     "vlmc_dsnot_stats": (_i, [_vp, _i, _i64, _i64, _i, _i64, _vp, _vp, _vp, _vp, _d, _d, _d, _vp, _sz, _vp]),
     "vlmc_wanda_rowselect": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_wanda_nm": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
@@ -174,6 +176,36 @@ def sqnorm_accum(x, scaler_row, n_before, b):
         st = lib.vlmc_sqnorm_accum(x2.data_ptr(), _dtype(x2), T, C, x2.stride(0), scaler_row.data_ptr(),
                                    float(n_before), float(b), ws.data_ptr(), ws.numel(), _stream(x2))
     _check("vlmc_sqnorm_accum", st)
+
+
+class StatsItem(ctypes.Structure):
+    _fields_ = [("x", _vp), ("T", _i64), ("C", _i), ("ldx", _i64), ("scaler_row", _vp), ("n_before", _d), ("b", _d)]
+
+
+def sqnorm_accum_batch(xs, scaler_rows, n_before, b):
+    """K1 for several linears in ONE launch (vlmc_sqnorm_accum_batch): xs[i] -> scaler_rows[i], the same n_before / b for
+    all (the linears of a block see the same calibration samples).  Same results as sqnorm_accum per item."""
+    xs = [_rows2d(x) for x in xs]
+    _require_cuda(*xs, *scaler_rows)
+    lib = load()
+    out = None
+    by_dtype = {}
+    for i, x in enumerate(xs):
+        by_dtype.setdefault(_dtype(x), []).append(i)
+    for dt, idx in by_dtype.items():
+        for c0 in range(0, len(idx), 16):
+            chunk = idx[c0:c0 + 16]
+            items = (StatsItem * len(chunk))()
+            for j, i in enumerate(chunk):
+                x = xs[i]
+                items[j] = StatsItem(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), scaler_rows[i].data_ptr(),
+                                     float(n_before), float(b))
+            need = lib.vlmc_sqnorm_accum_batch_workspace_bytes(items, len(chunk), dt)
+            ws = workspace(xs[chunk[0]], need)
+            with torch.cuda.device(xs[chunk[0]].device):
+                _check("vlmc_sqnorm_accum_batch", lib.vlmc_sqnorm_accum_batch(items, len(chunk), dt, ws.data_ptr(), ws.numel(),
+                                                                              _stream(xs[chunk[0]])))
+    return out
 
 
 def dsnot_stats(x, scaler_row, sum_row, mean, var, n_before, b_per_seg, ntok_before, nseg=1):
