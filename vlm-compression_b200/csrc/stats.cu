@@ -356,6 +356,8 @@ extern "C" int vlmc_sqnorm_accum_batch(const vlmc_stats_item* items, int count, 
     p.x = s.x; p.ldx = s.ldx; p.C = s.C; p.S = s.T; p.nseg = 1;
     p.chunks_per_seg = pl.chunks_per_seg; p.rows_per_chunk = pl.rows_per_chunk;
     p.tickets = reinterpret_cast<unsigned int*>(base + used);
+    // this item's ticket words sit where an earlier (single) launch kept partial sums: clear them
+    if (cudaMemsetAsync(base + used, 0, VLMC_WS_COUNTER_BYTES, (cudaStream_t)stream) != cudaSuccess) return check_launch();
     p.part = reinterpret_cast<float*>(base + used + VLMC_WS_COUNTER_BYTES);
     p.scaler_row = s.scaler_row; p.sum_row = nullptr; p.mean = nullptr; p.var = nullptr;
     p.n_before = s.n_before; p.b_per_seg = s.b; p.ntok_before = 0.0;

@@ -740,7 +740,7 @@ struct RcShared {
   uint32_t wmax[kRcWarps];
   uint32_t scan[kRcWarps + 2];
   uint32_t ncand, sel_bin, sel_before, thr_key;
-  int thr_col, ties_simple, in_window;
+  int thr_col;
 };
 
 // One warp: bin (among kRcBins counters) that holds the kk-th (1-indexed) entry and the count before it -> sh.sel_bin,
@@ -846,13 +846,12 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
   uint32_t* hist = keys + (size_t)C;                          // [kRcBins]
   uint32_t* cand_key = hist + kRcBins;                        // [kRcCand]
   uint32_t* cand_col = cand_key + kRcCand;                    // [kRcCand]
-  uint32_t* cand_bin = cand_col + kRcCand;                    // [kRcCand]  kRcMagic | bin
   __shared__ RcShared sh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int b = tid; b < kRcBins; b += kRcThreads) hist[b] = 0;
   if (tid == 0) sh.ncand = 0;
 
-#define RC_HAS(u) (FULL || (u) < NV - 1 || tid + (u) * kRcThreads < nvec)
+#define RC_HAS(u) (FULL || tid + (u) * kRcThreads < nvec)
   auto load_row = [&](int row, uint4 (&wv)[NV]) {
     const T* wrow = W + (int64_t)row * ldw;
 #pragma unroll
@@ -860,7 +859,11 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
       if (RC_HAS(u)) wv[u] = ld_stream(wrow + (int64_t)(tid + u * kRcThreads) * V);
   };
 
-  // scale of the first row of this CTA: from its own maximum (one extra pass over the registers)
+  // Bin scale.  Rows of one matrix share sq and the weight distribution, so the previous row's threshold predicts this
+  // row's: scale = 1024 / previous threshold puts the k-th score near the MIDDLE of the 2048 bins with ~0.1 % of its value
+  // per bin (2-3 keys per bin at C = 4096), and everything above twice the threshold in the last bin, which is never
+  // counted (the k-th score is found below it, or the row takes the exact path).  The first row of a CTA has no
+  // predecessor: its scale comes from its own maximum (coarser: more candidates, same result).
   float scale = 0.f;
   {
     const int row = blockIdx.x;
@@ -887,40 +890,24 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
     if (rmax > 0u && rmax < 0x7f800000u) scale = (float)kRcBins / (1.25f * __uint_as_float(rmax));
     __syncthreads();
   }
-  // predicted bin of the k-th score: unknown for the first row (an empty window: that row takes the collect pass)
-  uint32_t win_lo = 1, win_span = 0;                           // window = bins [win_lo, win_lo + win_span), as kRcMagic | bin
 
   for (int row = blockIdx.x; row < R; row += gridDim.x) {
     T* wrow = W + (int64_t)row * ldw;
     uint4 wv[NV];
     load_row(row, wv);
-    // ---- P1: score, keys -> smem, row sum / max, linear-bin histogram, candidates of the predicted window
+    // ---- P1: score, keys -> smem, row sum, linear-bin histogram (the last bin is not counted)
     float lsum = 0.f;
-    uint32_t lmax = 0;
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
       if (RC_HAS(u)) {
         const int vi = tid + u * kRcThreads;
         uint32_t key[V];
         rc_keys<T>(wv[u], sq + vi * V, key);
-        bool any = false;
-        uint32_t bb[V];
 #pragma unroll
         for (int e = 0; e < V; ++e) {
           lsum += __uint_as_float(key[e]);
-          lmax = key[e] > lmax ? key[e] : lmax;
-          bb[e] = rc_binbits(key[e], scale);
-          atomicAdd(&hist[bb[e] & (uint32_t)(kRcBins - 1)], 1u);
-          any |= (bb[e] - win_lo) < win_span;
-        }
-        if (any) {
-#pragma unroll
-          for (int e = 0; e < V; ++e) {
-            if ((bb[e] - win_lo) < win_span) {
-              const uint32_t pos = atomicAdd(&sh.ncand, 1u);
-              if (pos < (uint32_t)kRcCand) { cand_key[pos] = key[e]; cand_col[pos] = (uint32_t)(vi * V + e); cand_bin[pos] = bb[e]; }
-            }
-          }
+          const uint32_t bin = rc_binbits(key[e], scale) & (uint32_t)(kRcBins - 1);
+          if (bin != (uint32_t)(kRcBins - 1)) atomicAdd(&hist[bin], 1u);
         }
 #pragma unroll
         for (int q = 0; q < V / 4; ++q)
@@ -928,71 +915,36 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
       }
     }
     lsum = warp_sum(lsum);
-    lmax = __reduce_max_sync(0xffffffffu, lmax);
-    if (lane == 0) { sh.wsum[warp] = lsum; sh.wmax[warp] = lmax; }
-    __syncthreads();                                           // barrier A: histogram, candidates, partial sums
-    uint32_t rmax = 0;
-#pragma unroll
-    for (int w = 0; w < kRcWarps; ++w) rmax = sh.wmax[w] > rmax ? sh.wmax[w] : rmax;
+    if (lane == 0) sh.wsum[warp] = lsum;
+    __syncthreads();                                           // barrier A: histogram, partial sums
     const bool select = k > 0 && k < C;
-    // ---- P2 (warp 0): the bin of the k-th smallest score; when it lies in the window, the exact threshold pair too
+    // ---- P2 (warp 0): the bin of the k-th smallest score
     if (warp == 0) {
       if (lane == 0) {
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < kRcWarps; ++w) t += sh.wsum[w];
         row_sum[row] = t;
+        sh.sel_bin = (uint32_t)(kRcBins - 1);                  // stays there when the k-th score is not below the last bin
+        sh.sel_before = 0;
+        sh.ncand = 0;                                          // every thread is past barrier A: done with the previous row's list
       }
-      rc_scan_warp(hist, select ? (uint32_t)k : 1u, sh);
       __syncwarp();
-      const uint32_t want = kRcMagic | sh.sel_bin;
-      const uint32_t nc = sh.ncand;
-      const bool inwin = select && (want - win_lo) < win_span && nc <= (uint32_t)kRcCand;
-      if (inwin) {
-        // rank the candidates of bin `want` on (score, column): the stable-sort order; rank kk - 1 is the threshold
-        const uint32_t kk = (uint32_t)k - sh.sel_before;
-        uint32_t fk = 0, fc = 0;
-        for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
-          const uint32_t i = c0 + lane;
-          const bool mine = i < nc && cand_bin[i] == want;
-          const uint32_t mk = mine ? cand_key[i] : 0xffffffffu, mc = mine ? cand_col[i] : 0xffffffffu;
-          uint32_t rank = 0;
-          if (__any_sync(0xffffffffu, mine)) {
-            for (uint32_t j = 0; j < nc; ++j) {
-              const uint32_t ok = cand_key[j], oc = cand_col[j];
-              rank += (cand_bin[j] == want && (ok < mk || (ok == mk && oc < mc))) ? 1u : 0u;
-            }
-          }
-          const uint32_t ball = __ballot_sync(0xffffffffu, mine && rank == kk - 1);
-          if (ball) {
-            const int src = __ffs(ball) - 1;
-            fk = __shfl_sync(0xffffffffu, mk, src);
-            fc = __shfl_sync(0xffffffffu, mc, src);
-          }
-        }
-        uint32_t kept_eq = 0;                                  // an equal key at a higher column stays: P4 needs the column
-        for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
-          const uint32_t i = c0 + lane;
-          kept_eq |= __ballot_sync(0xffffffffu, i < nc && cand_key[i] == fk && cand_col[i] > fc);
-        }
-        if (lane == 0) { sh.thr_key = fk; sh.thr_col = (int)fc; sh.ties_simple = kept_eq == 0; }
-      }
-      if (lane == 0) { sh.in_window = inwin ? 1 : 0; sh.ncand = 0; }
+      rc_scan_warp(hist, select ? (uint32_t)k : 1u, sh);
     }
-    __syncthreads();                                           // barrier B: sel_bin / threshold, counters cleared
+    __syncthreads();                                           // barrier B: sel_bin / sel_before, counters cleared
     uint32_t thr_key = 0;
     int thr_col = -1;                                          // prune (key < thr_key) || (key == thr_key && col <= thr_col)
     bool ties_simple = true;                                   // every key equal to thr_key is pruned: one compare in P4
-    const uint32_t b_sel = sh.sel_bin;
     if (k >= C) {
       thr_key = 0xffffffffu;
     } else if (k > 0) {
-      if (sh.in_window) {
-        thr_key = sh.thr_key; thr_col = sh.thr_col; ties_simple = sh.ties_simple != 0;
-      } else {
-        // ---- the window missed (first row of the CTA, a row unlike its predecessor): collect the bin's keys now
-        const uint32_t want = kRcMagic | b_sel;
-        const uint32_t kk = (uint32_t)k - sh.sel_before;       // 1-indexed rank inside the bin
+      const uint32_t b_sel = sh.sel_bin;
+      const uint32_t want = kRcMagic | b_sel;
+      const uint32_t kk = (uint32_t)k - sh.sel_before;         // 1-indexed rank inside the bin
+      bool exact_path = b_sel == (uint32_t)(kRcBins - 1);      // not found below the uncounted bin (uniform across the CTA)
+      if (!exact_path) {
+        // ---- P3: collect the bin's keys (a few per row: one branch per vector, taken by few threads)
 #pragma unroll
         for (int u = 0; u < NV; ++u) {
           if (RC_HAS(u)) {
@@ -1017,11 +969,10 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
             }
           }
         }
-        __syncthreads();                                       // candidate list
+        __syncthreads();                                       // barrier C: candidate list
         const uint32_t nc = sh.ncand;
-        __syncthreads();
-        if (tid == 0) sh.ncand = 0;
         if (nc <= (uint32_t)kRcCand) {
+          // every warp ranks the (few) candidates itself: the threshold pair lands in registers without another barrier
           uint32_t fk = 0, fc = 0;
           for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
             const uint32_t i = c0 + lane;
@@ -1040,50 +991,55 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
           }
           thr_key = fk;
           thr_col = (int)fc;
-          uint32_t kept_eq = 0;
+          uint32_t kept_eq = 0;                                // an equal key at a higher column stays: P4 needs the column
           for (uint32_t c0 = 0; c0 < nc; c0 += 32) {
             const uint32_t i = c0 + lane;
             kept_eq |= __ballot_sync(0xffffffffu, i < nc && cand_key[i] == fk && cand_col[i] > fc);
           }
           ties_simple = kept_eq == 0;
-          __syncthreads();                                     // everyone has read the list before the next row refills it
         } else {
-          // ---- exact radix select on the score bits (31 significant bits: 11 + 11 + 9), then on the column index
-          uint32_t prefix = 0, kr = (uint32_t)k, before = 0, bsel = 0;
-#pragma unroll 1
-          for (int pass = 0; pass < 3; ++pass) {
-            const int shift = pass == 0 ? 20 : (pass == 1 ? 9 : 0);
-            const uint32_t himask = pass == 0 ? 0u : (pass == 1 ? 0xfff00000u : 0xfffffe00u);
-            const uint32_t bmask = pass == 2 ? 0x1ffu : 0x7ffu;
-            for (int j = tid; j < C; j += kRcThreads) {
-              const uint32_t key = keys[j];
-              if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & bmask], 1u);
-            }
-            rc_find_bin(hist, kr, sh, bsel, before);
-            kr -= before;
-            prefix |= bsel << shift;
-          }
-          // prefix = the k-th smallest key; kr = how many of the keys equal to it are pruned (lowest columns first)
-          uint32_t cprefix = 0;
-#pragma unroll 1
-          for (int pass = 0; pass < 2; ++pass) {                // columns < 2^22: 11 + 11 bits
-            const int shift = pass == 0 ? 11 : 0;
-            for (int j = tid; j < C; j += kRcThreads) {
-              if (keys[j] == prefix) {
-                const int plane = j / (nvec * 4), rem = j - plane * nvec * 4;
-                const uint32_t col = (uint32_t)((rem >> 2) * V + plane * 4 + (rem & 3));
-                if (pass == 0 || (col >> 11) == cprefix) atomicAdd(&hist[(col >> shift) & 0x7ffu], 1u);
-              }
-            }
-            rc_find_bin(hist, kr, sh, bsel, before);
-            kr -= before;
-            if (pass == 0) cprefix = bsel;
-          }
-          thr_key = prefix;
-          thr_col = (int)((cprefix << 11) | bsel);
-          ties_simple = false;
-          __syncthreads();
+          exact_path = true;
         }
+      }
+      if (exact_path) {
+        // ---- exact radix select on the score bits (31 significant bits: 11 + 11 + 9), then on the column index
+        __syncthreads();
+        for (int b = tid; b < kRcBins; b += kRcThreads) hist[b] = 0;      // the last bin was never scanned
+        uint32_t prefix = 0, kr = (uint32_t)k, before = 0, bsel = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const int shift = pass == 0 ? 20 : (pass == 1 ? 9 : 0);
+          const uint32_t himask = pass == 0 ? 0u : (pass == 1 ? 0xfff00000u : 0xfffffe00u);
+          const uint32_t bmask = pass == 2 ? 0x1ffu : 0x7ffu;
+          __syncthreads();
+          for (int j = tid; j < C; j += kRcThreads) {
+            const uint32_t key = keys[j];
+            if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & bmask], 1u);
+          }
+          rc_find_bin(hist, kr, sh, bsel, before);
+          kr -= before;
+          prefix |= bsel << shift;
+        }
+        // prefix = the k-th smallest key; kr = how many of the keys equal to it are pruned (lowest columns first)
+        uint32_t cprefix = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {                  // columns < 2^22: 11 + 11 bits
+          const int shift = pass == 0 ? 11 : 0;
+          __syncthreads();
+          for (int j = tid; j < C; j += kRcThreads) {
+            if (keys[j] == prefix) {
+              const int plane = j / (nvec * 4), rem = j - plane * nvec * 4;
+              const uint32_t col = (uint32_t)((rem >> 2) * V + plane * 4 + (rem & 3));
+              if (pass == 0 || (col >> 11) == cprefix) atomicAdd(&hist[(col >> shift) & 0x7ffu], 1u);
+            }
+          }
+          rc_find_bin(hist, kr, sh, bsel, before);
+          kr -= before;
+          if (pass == 0) cprefix = bsel;
+        }
+        thr_key = prefix;
+        thr_col = (int)((cprefix << 11) | bsel);
+        ties_simple = false;
       }
     }
 
@@ -1118,19 +1074,8 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
         if (zero_w && pm) st_stream(wrow + (int64_t)vi * V, rc_zero<T>(wv[u], pm));
       }
     }
-    // next row: scale from this row's maximum, window around where this row's k-th score WOULD fall under that scale
-    // (rows of one matrix share sq and the weight distribution; a miss only costs the collect pass)
-    const float nscale = (rmax > 0u && rmax < 0x7f800000u) ? (float)kRcBins / (1.25f * __uint_as_float(rmax)) : 0.f;
-    if (select && nscale > 0.f && thr_key < 0x7f800000u) {
-      const uint32_t pb = rc_binbits(thr_key, nscale) & (uint32_t)(kRcBins - 1);
-      const uint32_t lo = pb > (uint32_t)kRcWin ? pb - kRcWin : 0u;
-      const uint32_t hi = pb + kRcWin < (uint32_t)kRcBins ? pb + kRcWin : (uint32_t)kRcBins - 1;
-      win_lo = kRcMagic | lo;
-      win_span = hi - lo + 1;
-    } else {
-      win_lo = 1; win_span = 0;
-    }
-    scale = nscale;
+    // next row's scale: this row's threshold in the middle of the bins
+    if (select && thr_key > 0u && thr_key < 0x7f800000u) scale = (float)(kRcBins / 2) / __uint_as_float(thr_key);
   }
 #undef RC_HAS
 }
@@ -1138,7 +1083,7 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
 template <typename T>
 static bool rowselect_cta_fits(int C) {
   constexpr int V = Elem<T>::kVec;
-  const size_t smem = ((size_t)C + kRcBins + 3 * kRcCand) * sizeof(uint32_t);
+  const size_t smem = ((size_t)C + kRcBins + 2 * kRcCand) * sizeof(uint32_t);
   return C / V <= kRcThreads * kRcMaxVec && smem <= 200 * 1024 && C < (1 << 22);
 }
 
@@ -1146,7 +1091,7 @@ template <typename T, int NV, bool FULL>
 static int launch_rowselect_cta_nv(void* W, int R, int C, int64_t ldw, const float* sq, int k, int zero_w,
                                    uint8_t* mask, int64_t ldm, float* row_sum, cudaStream_t st) {
   auto kern = rowselect_cta_kernel<T, NV, FULL>;
-  const size_t smem = ((size_t)C + kRcBins + 3 * kRcCand) * sizeof(uint32_t);
+  const size_t smem = ((size_t)C + kRcBins + 2 * kRcCand) * sizeof(uint32_t);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess)
@@ -1170,9 +1115,8 @@ static int launch_rowselect_cta(void* W, int R, int C, int64_t ldw, const float*
                                 uint8_t* mask, int64_t ldm, float* row_sum, cudaStream_t st) {
   constexpr int V = Elem<T>::kVec;
   const int nv = (C / V + kRcThreads - 1) / kRcThreads;
-  const bool full = (C / V) % kRcThreads == 0;
 #define VLMC_RC(NV)                                                                                               \
-  return full ? launch_rowselect_cta_nv<T, NV, true>(W, R, C, ldw, sq, k, zero_w, mask, ldm, row_sum, st)         \
+  return (C / V == (NV) * kRcThreads) ? launch_rowselect_cta_nv<T, NV, true>(W, R, C, ldw, sq, k, zero_w, mask, ldm, row_sum, st)         \
               : launch_rowselect_cta_nv<T, NV, false>(W, R, C, ldw, sq, k, zero_w, mask, ldm, row_sum, st)
   if (nv <= 1) VLMC_RC(1);
   if (nv <= 2) VLMC_RC(2);

@@ -73,14 +73,16 @@ def return_reorder_indice(input_tensor):
 
 def dsnot_prune_linear(module, wrapper, sparsity, prune_n=0, prune_m=0, lora_model=False, initial_method="wanda",
                        pow_of_var_regrowing=1.0, max_cycle_time=100, update_threshold=0.1, without_same_sign=True,
-                       without_DSnoT=False, ref_fixup=True, argmin_rule=1, reduce_ncycles=None, elide_noop_swaps=False):
+                       without_DSnoT=False, ref_fixup=True, argmin_rule=1, reduce_ncycles=None, elide_noop_swaps=True):
     """One linear (dsnot_pruner.py:359-755).  Sets module.mask (True = kept), zeroes pruned weights unless lora_model.
     Returns the executed cycle count (1-elem int tensor) or None when nothing ran.
 
     elide_noop_swaps: with the shipped reference semantics (ref_fixup) every unstructured swap is written back by
     :734-740, and the candidates always come from the initial kept / pruned sets, so the final mask IS the initial
-    selection (tests assert the equality).  True skips the cycle loop and runs the initial selection only -
-    same mask, same weights, no cycle count.  Off by default: the default path executes what the reference executes."""
+    selection (tests assert the equality on every fixture and at Vicuna size).  True (default) skips the cycle
+    loop and runs the initial selection only - same mask, same weights, no cycle count: nothing the loop computes is
+    observable in the shipped semantics.  False executes the loop (vlmc_dsnot_refine) exactly as the reference does; the
+    upstream semantics (ref_fixup=False) and the n:m branch always execute it."""
     W = module.weight.data
     C = W.shape[1]
     if prune_n == 0:
@@ -109,7 +111,7 @@ class BLIPT5LayerDSnoTPruner(BLIPT5LayerWandaPruner):
 
     def __init__(self, model, data_loader, initial_method="wanda", skip_layer=None, skip_sub_layer=None,
                  pow_of_var_regrowing=1., max_cycle_time=1e2, update_threshold=0.1, without_same_sign=True,
-                 without_DSnoT=False, upstream_semantics=False, elide_noop_swaps=False, **kwargs):
+                 without_DSnoT=False, upstream_semantics=False, elide_noop_swaps=True, **kwargs):
         super().__init__(model, data_loader, **kwargs)
         self.pow_of_var_regrowing = pow_of_var_regrowing
         self.without_same_sign = without_same_sign
