@@ -730,9 +730,9 @@ static int sel_common_checks(void* W, int dtype, int R, int C, int64_t ldw, cons
 constexpr int kRcThreads = 128;           // 4 warps per row: the per-row bookkeeping (scan, ranking, barriers) is amortised
                                           // over 32+ weights per thread, and 5 independent rows are resident per SM
 constexpr int kRcWarps = kRcThreads / 32;
-constexpr int kRcBins = 2048;
+constexpr int kRcBins = 1024;           // counters per row: the scan by one warp is on every row's critical path
+constexpr int kRcHist = 2048;            // counters allocated: the exact path's radix select uses all of them (11-bit digits)
 constexpr int kRcCand = 256;
-constexpr int kRcWin = 6;                 // candidates are collected in pass 1 from bins [predicted - 6, predicted + 6]
 constexpr int kRcMaxVec = 16;             // 16-byte vectors per thread held in registers: C <= 128 * 16 * V
 
 struct RcShared {
@@ -743,11 +743,12 @@ struct RcShared {
   int thr_col;
 };
 
-// One warp: bin (among kRcBins counters) that holds the kk-th (1-indexed) entry and the count before it -> sh.sel_bin,
+// One warp: bin (among NB counters) that holds the kk-th (1-indexed) entry and the count before it -> sh.sel_bin,
 // sh.sel_before; the counters are cleared on the way.  64 counters per lane.
+template <int NB>
 __device__ __forceinline__ void rc_scan_warp(uint32_t* hist, uint32_t kk, RcShared& sh) {
   const int lane = threadIdx.x & 31;
-  constexpr int per = kRcBins / 32;                           // lane owns bins [lane * 64, lane * 64 + 64)
+  constexpr int per = NB / 32;                                // lane owns bins [lane * per, lane * per + per)
   // rotated walk: at step j lane reads word (j + lane) % 64 of its segment -> bank (j + lane) % 32: conflict-free
   uint32_t local = 0;
 #pragma unroll 16
@@ -787,18 +788,23 @@ __device__ __forceinline__ void rc_scan_warp(uint32_t* hist, uint32_t kk, RcShar
 // All threads: same result in registers (used by the exact path only; two barriers inside)
 __device__ __forceinline__ void rc_find_bin(uint32_t* hist, uint32_t kk, RcShared& sh, uint32_t& bin, uint32_t& before) {
   __syncthreads();
-  if (threadIdx.x < 32) rc_scan_warp(hist, kk, sh);
+  if (threadIdx.x < 32) rc_scan_warp<kRcHist>(hist, kk, sh);
   __syncthreads();
   bin = sh.sel_bin;
   before = sh.sel_before;
 }
 
-// bin of a score as the low bits of (min(score * scale, 2047) + 2^23): round-to-nearest instead of floor - still monotone
-// in the score - with full-rate FMUL / FMNMX / FADD instead of a quarter-rate F2I; a NaN score lands in the last bin
+// bin word of a score: bits(min(fma(score, scale, 2^23), 2^23 + kRcBins - 1)) = kRcMagic | bin.  Round-to-nearest of a
+// monotone function of the score (still monotone), one FFMA + one FMNMX; a NaN score lands in the last bin (fminf)
 constexpr uint32_t kRcMagic = 0x4B000000u;                   // bits of 8388608.0f
 __device__ __forceinline__ uint32_t rc_binbits(uint32_t key, float scale) {
-  const float x = fminf(__fmul_rn(__uint_as_float(key), scale), (float)(kRcBins - 1));
-  return __float_as_uint(__fadd_rn(x, 8388608.0f));            // kRcMagic | bin
+  return __float_as_uint(fminf(__fmaf_rn(__uint_as_float(key), scale, 8388608.0f), 8388608.0f + (float)(kRcBins - 1)));
+}
+
+__device__ __forceinline__ uint32_t rc_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
 }
 
 // scores of one 16-byte vector of weights: key[e] = bits(|w[e]| * sq[col + e]) (non-negative floats order like their bits)
@@ -843,12 +849,12 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
   const int nvec = C / V;
   // key planes: plane q holds elements 4q..4q+3 of every vector as one uint4 per vector (conflict-free 16-byte accesses)
   uint32_t* keys = rc_smem;                                   // [V / 4][nvec][4]
-  uint32_t* hist = keys + (size_t)C;                          // [kRcBins]
-  uint32_t* cand_key = hist + kRcBins;                        // [kRcCand]
+  uint32_t* hist = keys + (size_t)C;                          // [kRcHist]; the fast path uses the first kRcBins
+  uint32_t* cand_key = hist + kRcHist;                        // [kRcCand]
   uint32_t* cand_col = cand_key + kRcCand;                    // [kRcCand]
   __shared__ RcShared sh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int b = tid; b < kRcBins; b += kRcThreads) hist[b] = 0;
+  for (int b = tid; b < kRcHist; b += kRcThreads) hist[b] = 0;
   if (tid == 0) sh.ncand = 0;
 
 #define RC_HAS(u) (FULL || tid + (u) * kRcThreads < nvec)
@@ -895,7 +901,7 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
     T* wrow = W + (int64_t)row * ldw;
     uint4 wv[NV];
     load_row(row, wv);
-    // ---- P1: score, keys -> smem, row sum, linear-bin histogram (the last bin is not counted)
+    // ---- P1: score, keys -> smem, row sum, linear-bin histogram
     float lsum = 0.f;
 #pragma unroll
     for (int u = 0; u < NV; ++u) {
@@ -906,8 +912,7 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
 #pragma unroll
         for (int e = 0; e < V; ++e) {
           lsum += __uint_as_float(key[e]);
-          const uint32_t bin = rc_binbits(key[e], scale) & (uint32_t)(kRcBins - 1);
-          if (bin != (uint32_t)(kRcBins - 1)) atomicAdd(&hist[bin], 1u);
+          atomicAdd(&hist[rc_binbits(key[e], scale) - kRcMagic], 1u);      // no branch: the last bin is counted too
         }
 #pragma unroll
         for (int q = 0; q < V / 4; ++q)
@@ -930,7 +935,7 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
         sh.ncand = 0;                                          // every thread is past barrier A: done with the previous row's list
       }
       __syncwarp();
-      rc_scan_warp(hist, select ? (uint32_t)k : 1u, sh);
+      rc_scan_warp<kRcBins>(hist, select ? (uint32_t)k : 1u, sh);
     }
     __syncthreads();                                           // barrier B: sel_bin / sel_before, counters cleared
     uint32_t thr_key = 0;
@@ -942,7 +947,7 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
       const uint32_t b_sel = sh.sel_bin;
       const uint32_t want = kRcMagic | b_sel;
       const uint32_t kk = (uint32_t)k - sh.sel_before;         // 1-indexed rank inside the bin
-      bool exact_path = b_sel == (uint32_t)(kRcBins - 1);      // not found below the uncounted bin (uniform across the CTA)
+      bool exact_path = b_sel == (uint32_t)(kRcBins - 1);      // the k-th score is in the overflow bin (uniform across the CTA)
       if (!exact_path) {
         // ---- P3: collect the bin's keys (a few per row: one branch per vector, taken by few threads)
 #pragma unroll
@@ -956,8 +961,11 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
               const uint4 kq = *reinterpret_cast<const uint4*>(keys + ((size_t)q * nvec + vi) * 4);
               ke[4 * q] = kq.x; ke[4 * q + 1] = kq.y; ke[4 * q + 2] = kq.z; ke[4 * q + 3] = kq.w;
             }
+            // membership test without the clamp: an unclamped value above the last bin, a clamped one and a NaN all differ
+            // from `want` (which is below the last bin here): one FFMA + one FSETP per key, the OR rides on the compare
+            const float wantf = __uint_as_float(want);
 #pragma unroll
-            for (int e = 0; e < V; ++e) any |= rc_binbits(ke[e], scale) == want;
+            for (int e = 0; e < V; ++e) any |= __fmaf_rn(__uint_as_float(ke[e]), scale, 8388608.0f) == wantf;
             if (any) {
 #pragma unroll
               for (int e = 0; e < V; ++e) {
@@ -1004,7 +1012,7 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
       if (exact_path) {
         // ---- exact radix select on the score bits (31 significant bits: 11 + 11 + 9), then on the column index
         __syncthreads();
-        for (int b = tid; b < kRcBins; b += kRcThreads) hist[b] = 0;      // the last bin was never scanned
+        for (int b = tid; b < kRcHist; b += kRcThreads) hist[b] = 0;
         uint32_t prefix = 0, kr = (uint32_t)k, before = 0, bsel = 0;
 #pragma unroll 1
         for (int pass = 0; pass < 3; ++pass) {
@@ -1045,33 +1053,66 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
 
     // ---- P4: apply (weights are zeroed in their packed form; no unpack / repack)
     uint8_t* mrow = mask + (int64_t)row * ldm;
+    if (ties_simple && k > 0 && k < C) {
+      // Fast form: pruned <=> key <= thr_key, both below 2^31, so the sign of (thr_key - key) is the keep bit.  PRMT in its
+      // sign-replicating mode (selector nibble 8 | byte) turns that sign straight into the AND mask of the packed weight
+      // and into the mask bytes: ~3 instructions per weight instead of a compare / select / shift chain.
 #pragma unroll
-    for (int u = 0; u < NV; ++u) {
-      if (RC_HAS(u)) {
-        const int vi = tid + u * kRcThreads;
-        uint32_t pm = 0;                                       // bit e: element e pruned
+      for (int u = 0; u < NV; ++u) {
+        if (RC_HAS(u)) {
+          const int vi = tid + u * kRcThreads;
+          uint32_t d[V];
 #pragma unroll
-        for (int q = 0; q < V / 4; ++q) {
-          const uint4 kq = *reinterpret_cast<const uint4*>(keys + ((size_t)q * nvec + vi) * 4);
-          const uint32_t ke[4] = {kq.x, kq.y, kq.z, kq.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            bool pruned;
-            if (ties_simple) pruned = k > 0 && ke[e] <= thr_key;
-            else pruned = ke[e] < thr_key || (ke[e] == thr_key && vi * V + q * 4 + e <= thr_col);
-            pm |= (pruned ? 1u : 0u) << (q * 4 + e);
+          for (int q = 0; q < V / 4; ++q) {
+            const uint4 kq = *reinterpret_cast<const uint4*>(keys + ((size_t)q * nvec + vi) * 4);
+            d[4 * q] = thr_key - kq.x; d[4 * q + 1] = thr_key - kq.y; d[4 * q + 2] = thr_key - kq.z; d[4 * q + 3] = thr_key - kq.w;
           }
+          uint32_t w[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
+          if (V == 8) {
+            uint32_t km[4];                                      // bytes {s(2i), s(2i), s(2i+1), s(2i+1)}, s = 0xff kept / 0x00 pruned
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { km[i] = rc_prmt(d[2 * i], d[2 * i + 1], 0xFFBBu); w[i] &= km[i]; }
+            const uint32_t b0 = rc_prmt(km[0], km[1], 0x6420u) & 0x01010101u;
+            const uint32_t b1 = rc_prmt(km[2], km[3], 0x6420u) & 0x01010101u;
+            st_stream8(mrow + (int64_t)vi * V, make_uint2(b0, b1));
+          } else {
+            uint32_t km[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { km[i] = rc_prmt(d[i], 0u, 0xBBBBu); w[i] &= km[i]; }
+            const uint32_t t01 = rc_prmt(km[0], km[1], 0x0040u), t23 = rc_prmt(km[2], km[3], 0x0040u);
+            st_stream4(mrow + (int64_t)vi * V, rc_prmt(t01, t23, 0x5410u) & 0x01010101u);
+          }
+          if (zero_w) st_stream(wrow + (int64_t)vi * V, make_uint4(w[0], w[1], w[2], w[3]));
         }
-        // mask bytes: 1 = kept
-        const uint32_t m0 = (~pm) & 0xfu, m1 = ((~pm) >> 4) & 0xfu;
-        const uint32_t b0 = (m0 & 1u) | ((m0 & 2u) << 7) | ((m0 & 4u) << 14) | ((m0 & 8u) << 21);
-        if (V == 8) {
-          const uint32_t b1 = (m1 & 1u) | ((m1 & 2u) << 7) | ((m1 & 4u) << 14) | ((m1 & 8u) << 21);
-          st_stream8(mrow + (int64_t)vi * V, make_uint2(b0, b1));
-        } else {
-          st_stream4(mrow + (int64_t)vi * V, b0);
+      }
+    } else {
+      // general form: ties at the threshold split by column, k == 0 (nothing pruned), k >= C (everything pruned)
+#pragma unroll 1
+      for (int u = 0; u < NV; ++u) {
+        if (RC_HAS(u)) {
+          const int vi = tid + u * kRcThreads;
+          uint32_t pm = 0;                                       // bit e: element e pruned
+#pragma unroll
+          for (int q = 0; q < V / 4; ++q) {
+            const uint4 kq = *reinterpret_cast<const uint4*>(keys + ((size_t)q * nvec + vi) * 4);
+            const uint32_t ke[4] = {kq.x, kq.y, kq.z, kq.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const bool pruned = k > 0 && (ke[e] < thr_key || (ke[e] == thr_key && vi * V + q * 4 + e <= thr_col));
+              pm |= (pruned ? 1u : 0u) << (q * 4 + e);
+            }
+          }
+          const uint32_t m0 = (~pm) & 0xfu, m1 = ((~pm) >> 4) & 0xfu;
+          const uint32_t b0 = (m0 & 1u) | ((m0 & 2u) << 7) | ((m0 & 4u) << 14) | ((m0 & 8u) << 21);
+          if (V == 8) {
+            const uint32_t b1 = (m1 & 1u) | ((m1 & 2u) << 7) | ((m1 & 4u) << 14) | ((m1 & 8u) << 21);
+            st_stream8(mrow + (int64_t)vi * V, make_uint2(b0, b1));
+          } else {
+            st_stream4(mrow + (int64_t)vi * V, b0);
+          }
+          // wv[u] is indexed dynamically here (no unroll): re-read the vector instead (L2 hit, rare path)
+          if (zero_w && pm) st_stream(wrow + (int64_t)vi * V, rc_zero<T>(*reinterpret_cast<const uint4*>(wrow + (int64_t)vi * V), pm));
         }
-        if (zero_w && pm) st_stream(wrow + (int64_t)vi * V, rc_zero<T>(wv[u], pm));
       }
     }
     // next row's scale: this row's threshold in the middle of the bins
@@ -1083,7 +1124,7 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
 template <typename T>
 static bool rowselect_cta_fits(int C) {
   constexpr int V = Elem<T>::kVec;
-  const size_t smem = ((size_t)C + kRcBins + 2 * kRcCand) * sizeof(uint32_t);
+  const size_t smem = ((size_t)C + kRcHist + 2 * kRcCand) * sizeof(uint32_t);
   return C / V <= kRcThreads * kRcMaxVec && smem <= 200 * 1024 && C < (1 << 22);
 }
 
@@ -1091,7 +1132,7 @@ template <typename T, int NV, bool FULL>
 static int launch_rowselect_cta_nv(void* W, int R, int C, int64_t ldw, const float* sq, int k, int zero_w,
                                    uint8_t* mask, int64_t ldm, float* row_sum, cudaStream_t st) {
   auto kern = rowselect_cta_kernel<T, NV, FULL>;
-  const size_t smem = ((size_t)C + kRcBins + 2 * kRcCand) * sizeof(uint32_t);
+  const size_t smem = ((size_t)C + kRcHist + 2 * kRcCand) * sizeof(uint32_t);
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)) != cudaSuccess)
