@@ -1005,6 +1005,33 @@ def test_dsnot_refine_vs_oracle(native, R, C, tag, p, kw):
     assert np.array_equal(Wp, np.where(keep_o, W, np.float32(0)))
 
 
+@pytest.mark.parametrize("R,C,tag,p,kw", [
+    (512, 4096, "f16", 0.6, dict(ref_fixup=False)),
+    (192, 11008, "f16", 0.6, dict(ref_fixup=False)),
+    (256, 2048, "bf16", 0.5, dict(ref_fixup=False, without_same_sign=False)),
+    (128, 1408, "f32", 0.5, dict(ref_fixup=False, update_threshold=0.01)),
+    (128, 4096, "f16", 0.6, dict(ref_fixup=True)),
+    (64, 1024, "f16", 0.7, dict(ref_fixup=False, pow_of_var=0.0, max_cycle_time=64)),
+])
+def test_dsnot_walk2_equals_walk1(native, R, C, tag, p, kw, monkeypatch):
+    """The 5-pass walk kernel (candidate lists + per-warp bitonic sort, rows it cannot take handed back) against the
+    original one on the same inputs: masks, weights and the executed cycle count must be identical."""
+    W = weights(R, C, 51, DT[tag]).float().numpy()
+    scal, summ, var = _dsnot_stats(C, 52)
+    k = round(C * p)
+    monkeypatch.setenv("VLMC_DSNOT_WALK_V1", "1")
+    keep1, ncyc1, Wp1 = _run_dsnot(native, W, tag, scal, summ, var, k, **kw)
+    monkeypatch.setenv("VLMC_DSNOT_WALK_V1", "0")
+    keep2, ncyc2, Wp2 = _run_dsnot(native, W, tag, scal, summ, var, k, **kw)
+    ws = native.workspace(torch.empty(1, device="cuda"), 4)
+    handed_back = int(ws[:4].view(torch.int32).item())
+    print(f"walk2 {R}x{C} {tag}: {handed_back} of {R} rows handed back to the original kernel, {ncyc2} cycles")
+    assert ncyc1 == ncyc2
+    assert np.array_equal(keep1, keep2), int((keep1 != keep2).sum())
+    assert np.array_equal(Wp1, Wp2)
+    assert handed_back <= R // 8
+
+
 def test_dsnot_refine_pointer_leaves_its_sign_class(native):
     """All-positive DSnoT metric on the kept side and few negatives among the pruned: the prune pointer walks through
     the reorder filler (wanda_res_indices[0]) into the far end of the positive list and the regrow pointer into the

@@ -21,6 +21,7 @@
 //                               SURVEY F4), writes the bool mask and the zeroed weights.
 // Latency-bound (one thread walks <= 128 dependent steps per row), not HBM-bound: 2 B/weight read in pass 1,
 // 5 B/weight in pass 2.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace vlmc {
@@ -40,7 +41,11 @@ struct DsParams {
   int k, prune_n, prune_m;
   float pow_var; int max_cycle; float thr; int without_same_sign, initial_magnitude, argmin_rule;
   uint32_t* row_v; int* row_iv; int* row_stop; int* walk; int* ncycles;
+  const int* rows; const int* nrows;     // optional: walk only rows[0 .. *nrows) (the rows the fast kernel handed back)
+  int* fb_rows; int* fb_count;           // fast kernel: rows it could not take
 };
+
+constexpr int kDsSkipTail = 1 << 30;     // row_stop flag: nothing after the stop cycle is observable, the walk record ends there
 
 struct DsShared {
   uint32_t hist[kDsBins];
@@ -75,7 +80,8 @@ __device__ __forceinline__ uint32_t sortable(float f) {
 }
 __device__ __forceinline__ float sgnf(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 
-__device__ __forceinline__ uint32_t block_sum(uint32_t v, DsShared& sh) {
+template <class SH>
+__device__ __forceinline__ uint32_t block_sum(uint32_t v, SH& sh) {
   v = __reduce_add_sync(0xffffffffu, v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) sh.warp_tot[threadIdx.x >> 5] = v;
@@ -84,7 +90,8 @@ __device__ __forceinline__ uint32_t block_sum(uint32_t v, DsShared& sh) {
   for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh.warp_tot[w];
   return t;
 }
-__device__ __forceinline__ double block_sum(double v, DsShared& sh) {
+template <class SH>
+__device__ __forceinline__ double block_sum(double v, SH& sh) {
   v = warp_sum(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) sh.dred[threadIdx.x >> 5] = v;
@@ -156,8 +163,8 @@ __device__ bool radix_kth(F f, int n, uint32_t k, DsShared& sh, uint32_t& v, uin
 }
 
 // smallest q with #{included i <= q : key == v} >= need   (stable order among ties: lowest index first)
-template <class F>
-__device__ int tie_bound(F f, int n, uint32_t v, uint32_t need, DsShared& sh) {
+template <class F, class SH>
+__device__ int tie_bound(F f, int n, uint32_t v, uint32_t need, SH& sh) {
   int lo = -1, hi = n - 1;
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -263,7 +270,9 @@ dsnot_walk_kernel(const DsParams p) {
   const int C = p.C, maxc = p.max_cycle;
   const bool nm = p.prune_n != 0;
 
-  for (int row = blockIdx.x; row < p.R; row += gridDim.x) {
+  const int nrows = p.rows ? *p.nrows : p.R;
+  for (int ri = blockIdx.x; ri < nrows; ri += gridDim.x) {
+    const int row = p.rows ? p.rows[ri] : ri;
     const T* wrow = reinterpret_cast<const T*>(p.W) + (int64_t)row * p.ldw;
     __syncthreads();
     for (int c = tid; c < C; c += nthreads) {
@@ -430,6 +439,402 @@ dsnot_walk_kernel(const DsParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// dsnot_walk2_kernel: the unstructured walk with 5 passes over the row instead of ~17.
+//
+// The old kernel runs one 3-pass radix select + collect + rank sort over ALL C columns for each of the four orderings
+// (115 k warp instructions per 4096-column row, ncu).  What the loop can read is tiny and lies at known places:
+//   prune orderings   the smallest kept scores, i.e. the ranks k+1 .. k+N of the SAME score order the initial selection
+//                     uses: one more 2-level select gives a cut-off with ~3 max_cycle kept columns below it
+//   regrow orderings  the two ends of (pruned ? metric / var : 0): the first histogram of that key tells which bins hold
+//                     the max_cycle smallest / largest
+// so one classification pass appends those few hundred columns to candidate lists, and FOUR WARPS finish the four lists
+// on their own (no CTA barrier): a 256-bin linear re-binning of the candidates' narrow key range picks whole bins up to
+// max_cycle entries (<= 128), a register bitonic sort on (key, column) pairs puts them in the stable-sort order.
+// Rows where any of that does not fit (a sign class with fewer than max_cycle candidates: the pointer would leave its
+// class and need the far lists / filler; heavy ties; more candidates than a list holds) are handed back and go
+// through dsnot_walk_kernel - same results either way (tests run both on the same inputs).
+// The cycle loop stops at the row's stop cycle: with both sign classes >= max_cycle the pruned / regrown columns of
+// different cycles are distinct, so the writes of a non-updating cycle (kept stays kept, pruned stays pruned) are
+// no-ops and the apply pass may skip them (kDsSkipTail).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kW2Kept = 1024;        // candidate capacity: kept columns just above the threshold
+constexpr int kW2End = 512;          // candidate capacity: each end of the regrow ordering
+constexpr int kW2Bins = 256;         // per-warp linear re-binning
+
+struct DsShared2 {
+  uint32_t hist[kDsBins];            // block histograms; later the four per-warp 256-bin ones
+  uint32_t warp_tot[32];
+  double dred[32];
+  unsigned long long ckey[4][kDsCap];
+  int lists[4][kDsCap];              // L_NEG, L_POS (prune), then head, tail (regrow): columns
+  float listsD[4][kDsCap];
+  int walk[2 * kDsCap];
+  uint16_t ckept[kW2Kept];           // column | 0x8000 when the DSnoT metric is negative
+  uint16_t chead[kW2End], ctail[kW2End];
+  uint32_t nkept, nhead, ntail;
+  uint32_t t_bin[2], t_before[2], t_count[2];
+  uint32_t bmin, bmax;
+  int fail;
+};
+
+// bins of sh.hist (2048 counters, 8 per thread) that hold the ranks k0 (and k1 when ntargets == 2), 1-indexed
+__device__ void ds2_scan(DsShared2& sh, uint32_t k0, uint32_t k1, int ntargets) {
+  const int tid = threadIdx.x;
+  uint32_t c[8], local = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { c[j] = sh.hist[tid * 8 + j]; local += c[j]; }
+  uint32_t incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += t;
+  }
+  if ((tid & 31) == 31) sh.warp_tot[tid >> 5] = incl;
+  __syncthreads();
+  uint32_t wbase = 0;
+  for (int w = 0; w < (tid >> 5); ++w) wbase += sh.warp_tot[w];
+  incl += wbase;
+  const uint32_t excl = incl - local;
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const uint32_t kk = t == 0 ? k0 : k1;
+    if (t < ntargets && excl < kk && kk <= incl) {
+      uint32_t run = excl;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (kk <= run + c[j]) { sh.t_bin[t] = tid * 8 + j; sh.t_before[t] = run; sh.t_count[t] = c[j]; break; }
+        run += c[j];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void ds2_cmpx(unsigned long long& a, unsigned long long& b, bool asc) {
+  if ((a > b) == asc) { const unsigned long long t = a; a = b; b = t; }
+}
+
+// ascending bitonic sort of 128 keys held four per lane (element index = 4 * lane + j)
+__device__ __forceinline__ void ds2_sort128(unsigned long long (&v)[4], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 128; k <<= 1) {
+#pragma unroll
+    for (int d = k >> 1; d >= 1; d >>= 1) {
+      if (d >= 4) {
+        const int ld = d >> 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool asc = ((4 * lane + j) & k) == 0;
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, v[j], ld);
+          const bool keep_min = ((lane & ld) == 0) == asc;
+          v[j] = keep_min ? (v[j] < other ? v[j] : other) : (v[j] > other ? v[j] : other);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if ((j & d) == 0) ds2_cmpx(v[j], v[j | d], ((4 * lane + j) & k) == 0);
+      }
+    }
+  }
+}
+
+// One warp: the `want` smallest candidates in (key, ord) order -> out[0 .. want).  f(entry, key, ord) -> included.
+// Keys of included entries lie in [lo, lo + (256 << shift)).  Returns false when the list cannot be built here.
+template <class F>
+__device__ bool ds2_warp_list(F f, const uint16_t* cand, int n, uint32_t lo, int shift, int want, uint32_t* whist,
+                              unsigned long long* ckey, int lane) {
+  for (int b = lane; b < kW2Bins; b += 32) whist[b] = 0;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    uint32_t key, ord;
+    if (f(cand[i], key, ord)) {
+      uint32_t bin = (key - lo) >> shift;
+      if (bin > (uint32_t)(kW2Bins - 1)) bin = kW2Bins - 1;
+      atomicAdd(&whist[bin], 1u);
+    }
+  }
+  __syncwarp();
+  uint32_t c[8], local = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { c[j] = whist[lane * 8 + j]; local += c[j]; }
+  uint32_t incl = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total < (uint32_t)want) return false;
+  const uint32_t excl = incl - local;
+  int tb = 0;
+  if (excl < (uint32_t)want && (uint32_t)want <= incl) {
+    uint32_t run = excl;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if ((uint32_t)want <= run + c[j]) { tb = lane * 8 + j; break; }
+      run += c[j];
+    }
+  }
+  const uint32_t owner = __ballot_sync(0xffffffffu, excl < (uint32_t)want && (uint32_t)want <= incl);
+  tb = __shfl_sync(0xffffffffu, tb, __ffs(owner) - 1);
+  int cnt = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    uint32_t key = 0, ord = 0;
+    bool ok = false;
+    if (i < n && f(cand[i], key, ord)) {
+      uint32_t bin = (key - lo) >> shift;
+      if (bin > (uint32_t)(kW2Bins - 1)) bin = kW2Bins - 1;
+      ok = bin <= (uint32_t)tb;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+    const int slot = cnt + __popc(bal & ((1u << lane) - 1u));
+    if (ok && slot < kDsCap) ckey[slot] = ((unsigned long long)key << 32) | ord;
+    cnt += __popc(bal);
+  }
+  if (cnt > kDsCap) return false;
+  __syncwarp();
+  unsigned long long v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = (4 * lane + j < cnt) ? ckey[4 * lane + j] : ~0ull;
+  ds2_sort128(v, lane);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) ckey[4 * lane + j] = v[j];
+  __syncwarp();
+  return true;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kDsThreads, 4)
+dsnot_walk2_kernel(const DsParams p) {
+  extern __shared__ __align__(16) uint32_t ds_dyn[];
+  uint32_t* keyA = ds_dyn;                                   // [C] wanda score bits, pruned marker
+  float* dm = reinterpret_cast<float*>(ds_dyn + p.C);        // [C] DSnoT metric, later the regrow sort key
+  uint32_t* keyR = ds_dyn + p.C;
+  __shared__ DsShared2 sh;
+  constexpr int V = Elem<T>::kVec;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.C, maxc = p.max_cycle, k = p.k;
+  const uint32_t Nk = (uint32_t)(3 * maxc + 16);              // kept candidates wanted: both sign classes then hold >= maxc
+
+  for (int row = blockIdx.x; row < p.R; row += gridDim.x) {
+    const T* wrow = reinterpret_cast<const T*>(p.W) + (int64_t)row * p.ldw;
+    __syncthreads();
+    for (int b = tid; b < kDsBins; b += kDsThreads) sh.hist[b] = 0;
+    if (tid == 0) { sh.fail = 0; sh.nkept = 0; sh.nhead = 0; sh.ntail = 0; sh.bmin = 0xffffffffu; sh.bmax = 0; }
+    __syncthreads();
+    // ---- pass 1: scores, DSnoT metric, histogram of the score's bits [20, 31) ----
+    for (int c0 = tid * V; c0 < C; c0 += kDsThreads * V) {
+      float f[V];
+      Elem<T>::unpack(ld_stream(wrow + c0), f);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const int c = c0 + e;
+        const uint32_t key = __float_as_uint(__fmul_rn(fabsf(f[e]), __fsqrt_rn(p.scaler_row[c])));
+        keyA[c] = key;
+        dm[c] = __fmul_rn(f[e], p.sum_row[c]);
+        atomicAdd(&sh.hist[key >> 20], 1u);
+      }
+    }
+    __syncthreads();
+    // ---- exact k-th smallest (v, iv) and the 22-bit cut-off of rank k + Nk (three light passes) ----
+    const uint32_t kq = (uint32_t)k + Nk < (uint32_t)C ? (uint32_t)k + Nk : (uint32_t)C;
+    ds2_scan(sh, (uint32_t)k, kq, 2);
+    const uint32_t b0 = sh.t_bin[0], bq0 = sh.t_bin[1];
+    uint32_t kk = (uint32_t)k - sh.t_before[0];
+    const uint32_t kkq = kq - sh.t_before[1];
+    __syncthreads();
+    for (int b = tid; b < kDsBins; b += kDsThreads) sh.hist[b] = 0;
+    __syncthreads();
+    for (int c = tid; c < C; c += kDsThreads) {
+      const uint32_t key = keyA[c];
+      if ((key >> 20) == b0) atomicAdd(&sh.hist[(key >> 9) & 0x7ffu], 1u);
+    }
+    __syncthreads();
+    uint32_t bq1 = 0;
+    if (bq0 == b0) {                                           // both ranks in one top-level bin: one histogram serves both
+      ds2_scan(sh, kk, kkq, 2);
+      bq1 = sh.t_bin[1];
+    } else {
+      ds2_scan(sh, kk, 0, 1);
+    }
+    const uint32_t b1 = sh.t_bin[0];
+    kk -= sh.t_before[0];
+    __syncthreads();
+    if (bq0 != b0) {
+      for (int b = tid; b < kDsBins; b += kDsThreads) sh.hist[b] = 0;
+      __syncthreads();
+      for (int c = tid; c < C; c += kDsThreads) {
+        const uint32_t key = keyA[c];
+        if ((key >> 20) == bq0) atomicAdd(&sh.hist[(key >> 9) & 0x7ffu], 1u);
+      }
+      __syncthreads();
+      ds2_scan(sh, kkq, 0, 1);
+      bq1 = sh.t_bin[0];
+      __syncthreads();
+    }
+    const uint32_t vq22 = (bq0 << 11) | bq1;                   // kept columns with (key >> 9) <= vq22 are the candidates
+    for (int b = tid; b < kDsBins; b += kDsThreads) sh.hist[b] = 0;
+    __syncthreads();
+    const uint32_t pre22 = (b0 << 11) | b1;
+    for (int c = tid; c < C; c += kDsThreads) {
+      const uint32_t key = keyA[c];
+      if ((key >> 9) == pre22) atomicAdd(&sh.hist[key & 0x1ffu], 1u);
+    }
+    __syncthreads();
+    ds2_scan(sh, kk, 0, 1);
+    const uint32_t v = (pre22 << 9) | sh.t_bin[0];
+    const uint32_t need = kk - sh.t_before[0], ce = sh.t_count[0];
+    __syncthreads();
+    int iv = C;
+    if (need < ce) iv = tie_bound([&](int i, uint32_t& key) { key = keyA[i]; return true; }, C, v, need, sh);
+    __syncthreads();
+    for (int b = tid; b < kDsBins; b += kDsThreads) sh.hist[b] = 0;
+    __syncthreads();
+
+    // ---- pass 2: classify; reconstruction error; regrow key + its histogram; kept candidates ----
+    double esum = 0.0;
+    uint32_t lmin = 0xffffffffu, lmax = 0;
+    for (int c0 = 0; c0 < C; c0 += kDsThreads) {
+      const int c = c0 + tid;
+      bool cand = false;
+      uint32_t entry = 0;
+      if (c < C) {
+        const uint32_t key = keyA[c];
+        const float d = dm[c];
+        const bool pruned = key < v || (key == v && c <= iv);
+        float mval = 0.f;
+        if (pruned) { esum += (double)d; keyA[c] = kPrunedKey; mval = d; }
+        if (p.pow_var != 0.f) mval = __fdiv_rn(mval, p.pow_var == 1.f ? p.var[c] : powf(p.var[c], p.pow_var));
+        const uint32_t kr = sortable(mval);
+        keyR[c] = kr;
+        const uint32_t br = kr >> 21;
+        atomicAdd(&sh.hist[br], 1u);
+        lmin = br < lmin ? br : lmin;
+        lmax = br > lmax ? br : lmax;
+        cand = !pruned && (key >> 9) <= vq22 && d != 0.f;       // a kept column with a zero metric belongs to neither class
+        entry = (uint32_t)c | (d < 0.f ? 0x8000u : 0u);
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, cand);
+      if (bal) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&sh.nkept, (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const uint32_t slot = base + __popc(bal & ((1u << lane) - 1u));
+        if (cand && slot < (uint32_t)kW2Kept) sh.ckept[slot] = (uint16_t)entry;
+      }
+    }
+    lmin = __reduce_min_sync(0xffffffffu, lmin);
+    lmax = __reduce_max_sync(0xffffffffu, lmax);
+    if (lane == 0) { atomicMin(&sh.bmin, lmin); atomicMax(&sh.bmax, lmax); }
+    const float err0 = (float)block_sum(esum, sh);             // :601 (barriers inside: histogram, candidates, bmin / bmax complete)
+    __syncthreads();
+    // ---- the two ends of the regrow ordering: bins holding the maxc smallest / largest keys ----
+    ds2_scan(sh, (uint32_t)maxc, (uint32_t)(C - maxc + 1), 2);
+    const uint32_t bh = sh.t_bin[0], bt = sh.t_bin[1];
+    const uint32_t n_head = sh.t_before[0] + sh.t_count[0];    // columns with bin <= bh
+    const uint32_t n_tail = (uint32_t)C - sh.t_before[1];      // columns with bin >= bt
+    const uint32_t bmin = sh.bmin, bmax = sh.bmax, nkept = sh.nkept;
+    bool ok = nkept <= (uint32_t)kW2Kept && n_head <= (uint32_t)kW2End && n_tail <= (uint32_t)kW2End;
+    __syncthreads();
+    if (ok) {
+      for (int c0 = 0; c0 < C; c0 += kDsThreads) {
+        const int c = c0 + tid;
+        const uint32_t br = c < C ? keyR[c] >> 21 : 0u;
+        const bool ih = c < C && br <= bh, it = c < C && br >= bt;
+        const uint32_t balh = __ballot_sync(0xffffffffu, ih), balt = __ballot_sync(0xffffffffu, it);
+        if (balh) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&sh.nhead, (uint32_t)__popc(balh));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (ih) sh.chead[base + __popc(balh & ((1u << lane) - 1u))] = (uint16_t)c;
+        }
+        if (balt) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&sh.ntail, (uint32_t)__popc(balt));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (it) sh.ctail[base + __popc(balt & ((1u << lane) - 1u))] = (uint16_t)c;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- four warps, four lists ----
+    if (ok && warp < 4) {
+      uint32_t* whist = sh.hist + warp * kW2Bins;
+      bool good;
+      if (warp < 2) {
+        const uint32_t want_neg = warp == 0 ? 0x8000u : 0u;
+        const uint32_t hi = (vq22 << 9) | 0x1ffu;
+        const uint32_t range = hi - v;
+        const int shift = range < (uint32_t)kW2Bins ? 0 : 32 - __clz(range) - 8;
+        good = ds2_warp_list([&](uint16_t e, uint32_t& key, uint32_t& ord) {
+                               ord = e & 0x7fffu; key = keyA[ord]; return (uint32_t)(e & 0x8000u) == want_neg; },
+                             sh.ckept, (int)nkept, v, shift, maxc, whist, sh.ckey[warp], lane);
+      } else if (warp == 2) {
+        const uint32_t lo = bmin << 21, hi = (bh << 21) | 0x1fffffu;
+        const uint32_t range = hi - lo;
+        const int shift = range < (uint32_t)kW2Bins ? 0 : 32 - __clz(range) - 8;
+        good = ds2_warp_list([&](uint16_t e, uint32_t& key, uint32_t& ord) { ord = e; key = keyR[e]; return true; },
+                             sh.chead, (int)n_head, lo, shift, maxc, whist, sh.ckey[warp], lane);
+      } else {
+        // descending keys, ties by descending column: ascending order of (~key, C - 1 - column)
+        const uint32_t lo = ~((bmax << 21) | 0x1fffffu), hi = ~(bt << 21);
+        const uint32_t range = hi - lo;
+        const int shift = range < (uint32_t)kW2Bins ? 0 : 32 - __clz(range) - 8;
+        good = ds2_warp_list([&](uint16_t e, uint32_t& key, uint32_t& ord) { ord = (uint32_t)(C - 1) - e; key = ~keyR[e]; return true; },
+                             sh.ctail, (int)n_tail, lo, shift, maxc, whist, sh.ckey[warp], lane);
+      }
+      if (!good) atomicOr(&sh.fail, 1);
+      else {
+        for (int i = lane; i < maxc; i += 32) {
+          const uint32_t ord = (uint32_t)(sh.ckey[warp][i] & 0xffffffffull);
+          const int col = warp == 3 ? (C - 1 - (int)ord) : (int)ord;
+          sh.lists[warp][i] = col;
+          sh.listsD[warp][i] = dsnot_metric<T>(wrow, p.sum_row, col);
+        }
+      }
+    }
+    __syncthreads();
+    if (!ok || sh.fail) {
+      if (tid == 0) p.fb_rows[atomicAdd(p.fb_count, 1)] = row;
+      continue;
+    }
+    // ---- the cycle loop, one thread; ends at the row's stop cycle ----
+    if (tid == 0) {
+      float err = err0;
+      const float sign0 = sgnf(err0);
+      bool upd = true;
+      int stop = 0;
+      int hR = 0, tR = 0, hP = 0, tP = 0;
+      for (int c = 1; c <= maxc; ++c) {
+        const int l = err > 0.f ? 3 : 2;                       // :654 regrow from the tail / head
+        const int e = l == 3 ? tR++ : hR++;
+        const int rg = sh.lists[l][e];
+        const float rm = sh.listsD[l][e];
+        int pr; float pm;
+        if (err < 0.f) { pr = sh.lists[1][tP]; pm = sh.listsD[1][tP]; ++tP; }     // :683 the positive class, from its far end
+        else { pr = sh.lists[0][hP]; pm = sh.listsD[0][hP]; ++hP; }
+        const float after = __fsub_rn(__fadd_rn(err, pm), rm); // :713
+        const bool big = fabsf(err) > p.thr;
+        if (p.without_same_sign) upd = upd && big;             // :717-720
+        else upd = upd && big && (sign0 == sgnf(after));       // :722-729
+        sh.walk[2 * (c - 1)] = pr;
+        sh.walk[2 * (c - 1) + 1] = rg;
+        if (!upd) { stop = c; break; }
+        err = __fadd_rn(err, pm); err = __fsub_rn(err, rm);    // :742-751
+      }
+      p.row_v[row] = v;
+      p.row_iv[row] = iv;
+      p.row_stop[row] = stop | kDsSkipTail;
+      atomicMax(p.ncycles, stop == 0 ? maxc : stop);
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * maxc; i += kDsThreads) p.walk[(int64_t)row * 2 * maxc + i] = sh.walk[i];
+  }
+}
+
 struct DsApplyParams {
   void* W; int64_t ldw; int R, C;
   const float* scaler_row;
@@ -483,8 +888,11 @@ dsnot_apply_kernel(const DsApplyParams p) {
     }
     __syncthreads();
     if (tid == 0) {
-      const int stop = p.row_stop[row];
-      for (int c = 1; c <= ncyc; ++c) {
+      const int stop_raw = p.row_stop[row];
+      const int stop = stop_raw & ~kDsSkipTail;
+      int last = ncyc;
+      if ((stop_raw & kDsSkipTail) && stop > 0 && stop - 1 < last) last = stop - 1;   // later cycles change nothing (walk2)
+      for (int c = 1; c <= last; ++c) {
         const int pr = s_walk[2 * (c - 1)], rg = s_walk[2 * (c - 1) + 1];
         const bool upd = stop == 0 || c < stop;
         if (p.ref_fixup && p.prune_n == 0) { pm[pr] = 0; pm[rg] = 1; }   // :731-740 net effect
@@ -521,14 +929,14 @@ dsnot_apply_kernel(const DsApplyParams p) {
 }
 
 static size_t ds_state_bytes(int R, int max_cycle) {
-  return align_up((size_t)R * 4, 256) * 3 + align_up((size_t)R * 2 * max_cycle * 4, 256);
+  return align_up((size_t)R * 4, 256) * 4 + align_up((size_t)R * 2 * max_cycle * 4, 256);
 }
 size_t dsnot_refine_workspace_bytes(int R, int max_cycle) {
   if (max_cycle <= 0 || max_cycle > kDsCap) max_cycle = kDsCap;
   return VLMC_WS_COUNTER_BYTES + ds_state_bytes(R, max_cycle);
 }
 
-struct DsState { uint32_t* row_v; int* row_iv; int* row_stop; int* walk; };
+struct DsState { uint32_t* row_v; int* row_iv; int* row_stop; int* fb_rows; int* fb_count; int* walk; };
 static DsState ds_carve(void* ws, int R) {
   char* base = reinterpret_cast<char*>(ws) + VLMC_WS_COUNTER_BYTES;
   const size_t step = align_up((size_t)R * 4, 256);
@@ -536,7 +944,9 @@ static DsState ds_carve(void* ws, int R) {
   s.row_v = reinterpret_cast<uint32_t*>(base);
   s.row_iv = reinterpret_cast<int*>(base + step);
   s.row_stop = reinterpret_cast<int*>(base + 2 * step);
-  s.walk = reinterpret_cast<int*>(base + 3 * step);
+  s.fb_rows = reinterpret_cast<int*>(base + 3 * step);
+  s.fb_count = reinterpret_cast<int*>(ws);                  // first word of the counter area
+  s.walk = reinterpret_cast<int*>(base + 4 * step);
   return s;
 }
 
@@ -590,10 +1000,30 @@ extern "C" int vlmc_dsnot_refine_walk(const void* W, int dtype, int R, int C, in
   p.thr = update_threshold; p.without_same_sign = without_same_sign; p.initial_magnitude = initial_magnitude;
   p.argmin_rule = argmin_rule;
   p.row_v = s.row_v; p.row_iv = s.row_iv; p.row_stop = s.row_stop; p.walk = s.walk; p.ncycles = ncycles;
+  p.rows = nullptr; p.nrows = nullptr; p.fb_rows = s.fb_rows; p.fb_count = s.fb_count;
   if (cudaMemsetAsync(ncycles, 0, sizeof(int), st) != cudaSuccess) return check_launch();
   const size_t smem = (size_t)C * 8;
   int grid = 1;
+  // The 5-pass kernel takes the unstructured Wanda-initialised walk; rows it cannot take (and every other configuration)
+  // go through dsnot_walk_kernel.  VLMC_DSNOT_WALK_V1=1 forces the old kernel for every row (A/B runs, tests).
+  const char* v1e = getenv("VLMC_DSNOT_WALK_V1");
+  const bool fast = !(v1e && v1e[0] == '1') && prune_n == 0 && !initial_magnitude && k > 0 && C < 32768 &&
+                    C >= 2 * max_cycle_time && C - k >= 2 * max_cycle_time;
+  if (fast) {
+    if (cudaMemsetAsync(s.fb_count, 0, sizeof(int), st) != cudaSuccess) return check_launch();
+#define VLMC_DS_WALK2(TT) { rc = ds_grid(dsnot_walk2_kernel<TT>, smem, R, &grid); if (rc) return rc; \
+                            dsnot_walk2_kernel<TT><<<grid, kDsThreads, smem, st>>>(p); }
+    switch (dtype) {
+      case VLMC_F32: VLMC_DS_WALK2(float); break;
+      case VLMC_F16: VLMC_DS_WALK2(__half); break;
+      default: VLMC_DS_WALK2(__nv_bfloat16); break;
+    }
+#undef VLMC_DS_WALK2
+    if (check_launch() != VLMC_OK) return VLMC_ERR_CUDA;
+    p.rows = s.fb_rows; p.nrows = s.fb_count;                // second launch: only the rows handed back (usually none)
+  }
 #define VLMC_DS_WALK(TT) { rc = ds_grid(dsnot_walk_kernel<TT>, smem, R, &grid); if (rc) return rc; \
+                           if (fast && grid > kNumSMs) grid = kNumSMs; \
                            dsnot_walk_kernel<TT><<<grid, kDsThreads, smem, st>>>(p); }
   switch (dtype) {
     case VLMC_F32: VLMC_DS_WALK(float); break;
