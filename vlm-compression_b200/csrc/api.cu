@@ -7,7 +7,7 @@ size_t stats_workspace_bytes(int dsnot, int64_t T, int C, int64_t nseg);
 size_t threshold_workspace_bytes(int R, int C);
 size_t chol_workspace_bytes(int C);
 size_t obs_workspace_bytes(int R, int C);
-size_t dsnot_refine_workspace_bytes(int R, int max_cycle);
+size_t dsnot_refine_workspace_bytes(int R, int C, int max_cycle);
 }  // namespace vlmc
 
 extern "C" int vlmc_version(void) { return VLMC_ABI_VERSION; }
@@ -43,7 +43,7 @@ extern "C" size_t vlmc_workspace_bytes(int op, int64_t d0, int64_t d1, int64_t d
     case VLMC_OP_HESSIAN: return VLMC_WS_COUNTER_BYTES;
     case VLMC_OP_CHOL: return chol_workspace_bytes((int)d0);
     case VLMC_OP_OBS: return obs_workspace_bytes((int)d0, (int)d1);
-    case VLMC_OP_DSNOT_REFINE: return dsnot_refine_workspace_bytes((int)d0, (int)d2);
+    case VLMC_OP_DSNOT_REFINE: return dsnot_refine_workspace_bytes((int)d0, (int)d1, (int)d2);
     default: return 0;
   }
 }

@@ -41,6 +41,7 @@ struct DsParams {
   int k, prune_n, prune_m;
   float pow_var; int max_cycle; float thr; int without_same_sign, initial_magnitude, argmin_rule;
   uint32_t* row_v; int* row_iv; int* row_stop; int* walk; int* ncycles;
+  const float* sq;                       // sqrt(scaler_row) (fast kernel)
   const int* rows; const int* nrows;     // optional: walk only rows[0 .. *nrows) (the rows the fast kernel handed back)
   int* fb_rows; int* fb_count;           // fast kernel: rows it could not take
 };
@@ -479,11 +480,20 @@ struct DsShared2 {
 };
 
 // bins of sh.hist (2048 counters, 8 per thread) that hold the ranks k0 (and k1 when ntargets == 2), 1-indexed
-__device__ void ds2_scan(DsShared2& sh, uint32_t k0, uint32_t k1, int ntargets) {
+__device__ void ds2_scan(DsShared2& sh, uint32_t k0, uint32_t k1, int ntargets, bool extent = false) {
   const int tid = threadIdx.x;
   uint32_t c[8], local = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) { c[j] = sh.hist[tid * 8 + j]; local += c[j]; }
+  if (extent && local) {                                       // first / last non-empty bin -> sh.bmin / sh.bmax
+    int first = 7, last = 0;
+#pragma unroll
+    for (int j = 7; j >= 0; --j) if (c[j]) first = j;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (c[j]) last = j;
+    atomicMin(&sh.bmin, (uint32_t)(tid * 8 + first));
+    atomicMax(&sh.bmax, (uint32_t)(tid * 8 + last));
+  }
   uint32_t incl = local;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -606,6 +616,11 @@ __device__ bool ds2_warp_list(F f, const uint16_t* cand, int n, uint32_t lo, int
   return true;
 }
 
+__global__ void ds_sqrt_kernel(const float* __restrict__ s, float* __restrict__ out, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C) out[i] = __fsqrt_rn(s[i]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kDsThreads, 4)
 dsnot_walk2_kernel(const DsParams p) {
@@ -627,14 +642,21 @@ dsnot_walk2_kernel(const DsParams p) {
     __syncthreads();
     // ---- pass 1: scores, DSnoT metric, histogram of the score's bits [20, 31) ----
     for (int c0 = tid * V; c0 < C; c0 += kDsThreads * V) {
-      float f[V];
+      float f[V], sqv[V], smv[V];
       Elem<T>::unpack(ld_stream(wrow + c0), f);
+#pragma unroll
+      for (int q = 0; q < V / 4; ++q) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.sq + c0) + q);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.sum_row + c0) + q);
+        sqv[4 * q] = a.x; sqv[4 * q + 1] = a.y; sqv[4 * q + 2] = a.z; sqv[4 * q + 3] = a.w;
+        smv[4 * q] = b.x; smv[4 * q + 1] = b.y; smv[4 * q + 2] = b.z; smv[4 * q + 3] = b.w;
+      }
 #pragma unroll
       for (int e = 0; e < V; ++e) {
         const int c = c0 + e;
-        const uint32_t key = __float_as_uint(__fmul_rn(fabsf(f[e]), __fsqrt_rn(p.scaler_row[c])));
+        const uint32_t key = __float_as_uint(__fmul_rn(fabsf(f[e]), sqv[e]));
         keyA[c] = key;
-        dm[c] = __fmul_rn(f[e], p.sum_row[c]);
+        dm[c] = __fmul_rn(f[e], smv[e]);
         atomicAdd(&sh.hist[key >> 20], 1u);
       }
     }
@@ -696,43 +718,37 @@ dsnot_walk2_kernel(const DsParams p) {
 
     // ---- pass 2: classify; reconstruction error; regrow key + its histogram; kept candidates ----
     double esum = 0.0;
-    uint32_t lmin = 0xffffffffu, lmax = 0;
-    for (int c0 = 0; c0 < C; c0 += kDsThreads) {
-      const int c = c0 + tid;
-      bool cand = false;
-      uint32_t entry = 0;
-      if (c < C) {
-        const uint32_t key = keyA[c];
-        const float d = dm[c];
-        const bool pruned = key < v || (key == v && c <= iv);
-        float mval = 0.f;
-        if (pruned) { esum += (double)d; keyA[c] = kPrunedKey; mval = d; }
-        if (p.pow_var != 0.f) mval = __fdiv_rn(mval, p.pow_var == 1.f ? p.var[c] : powf(p.var[c], p.pow_var));
-        const uint32_t kr = sortable(mval);
-        keyR[c] = kr;
-        const uint32_t br = kr >> 21;
-        atomicAdd(&sh.hist[br], 1u);
-        lmin = br < lmin ? br : lmin;
-        lmax = br > lmax ? br : lmax;
-        cand = !pruned && (key >> 9) <= vq22 && d != 0.f;       // a kept column with a zero metric belongs to neither class
-        entry = (uint32_t)c | (d < 0.f ? 0x8000u : 0u);
+    const bool pow1 = p.pow_var == 1.f, pow0 = p.pow_var == 0.f;
+    for (int c = tid; c < C; c += kDsThreads) {
+      const uint32_t key = keyA[c];
+      const float d = dm[c];
+      const bool pruned = key < v || (key == v && c <= iv);
+      uint32_t kr;
+      if (pruned) {
+        esum += (double)d;
+        keyA[c] = kPrunedKey;
+        float mval = d;
+        if (!pow0) mval = __fdiv_rn(mval, pow1 ? p.var[c] : powf(p.var[c], p.pow_var));
+        kr = sortable(mval);
+      } else {
+        // 0 / var without the divide (a zero numerator takes the slow path of the IEEE division): 0 unless var is 0 or NaN
+        kr = 0x80000000u;
+        if (!pow0) {
+          const float vv = pow1 ? p.var[c] : powf(p.var[c], p.pow_var);
+          if (vv == 0.f || vv != vv) kr = 0xffffffffu;         // 0/0 and 0/NaN are NaN: sorts last
+        }
+        if ((key >> 9) <= vq22 && d != 0.f) {                  // a kept column with a zero metric belongs to neither class
+          const uint32_t slot = atomicAdd(&sh.nkept, 1u);
+          if (slot < (uint32_t)kW2Kept) sh.ckept[slot] = (uint16_t)((uint32_t)c | (d < 0.f ? 0x8000u : 0u));
+        }
       }
-      const uint32_t bal = __ballot_sync(0xffffffffu, cand);
-      if (bal) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(&sh.nkept, (uint32_t)__popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const uint32_t slot = base + __popc(bal & ((1u << lane) - 1u));
-        if (cand && slot < (uint32_t)kW2Kept) sh.ckept[slot] = (uint16_t)entry;
-      }
+      keyR[c] = kr;
+      atomicAdd(&sh.hist[kr >> 21], 1u);
     }
-    lmin = __reduce_min_sync(0xffffffffu, lmin);
-    lmax = __reduce_max_sync(0xffffffffu, lmax);
-    if (lane == 0) { atomicMin(&sh.bmin, lmin); atomicMax(&sh.bmax, lmax); }
-    const float err0 = (float)block_sum(esum, sh);             // :601 (barriers inside: histogram, candidates, bmin / bmax complete)
+    const float err0 = (float)block_sum(esum, sh);             // :601 (barriers inside: histogram and candidates complete)
     __syncthreads();
     // ---- the two ends of the regrow ordering: bins holding the maxc smallest / largest keys ----
-    ds2_scan(sh, (uint32_t)maxc, (uint32_t)(C - maxc + 1), 2);
+    ds2_scan(sh, (uint32_t)maxc, (uint32_t)(C - maxc + 1), 2, true);
     const uint32_t bh = sh.t_bin[0], bt = sh.t_bin[1];
     const uint32_t n_head = sh.t_before[0] + sh.t_count[0];    // columns with bin <= bh
     const uint32_t n_tail = (uint32_t)C - sh.t_before[1];      // columns with bin >= bt
@@ -740,23 +756,10 @@ dsnot_walk2_kernel(const DsParams p) {
     bool ok = nkept <= (uint32_t)kW2Kept && n_head <= (uint32_t)kW2End && n_tail <= (uint32_t)kW2End;
     __syncthreads();
     if (ok) {
-      for (int c0 = 0; c0 < C; c0 += kDsThreads) {
-        const int c = c0 + tid;
-        const uint32_t br = c < C ? keyR[c] >> 21 : 0u;
-        const bool ih = c < C && br <= bh, it = c < C && br >= bt;
-        const uint32_t balh = __ballot_sync(0xffffffffu, ih), balt = __ballot_sync(0xffffffffu, it);
-        if (balh) {
-          uint32_t base = 0;
-          if (lane == 0) base = atomicAdd(&sh.nhead, (uint32_t)__popc(balh));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (ih) sh.chead[base + __popc(balh & ((1u << lane) - 1u))] = (uint16_t)c;
-        }
-        if (balt) {
-          uint32_t base = 0;
-          if (lane == 0) base = atomicAdd(&sh.ntail, (uint32_t)__popc(balt));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (it) sh.ctail[base + __popc(balt & ((1u << lane) - 1u))] = (uint16_t)c;
-        }
+      for (int c = tid; c < C; c += kDsThreads) {
+        const uint32_t br = keyR[c] >> 21;
+        if (br <= bh) sh.chead[atomicAdd(&sh.nhead, 1u)] = (uint16_t)c;
+        if (br >= bt) sh.ctail[atomicAdd(&sh.ntail, 1u)] = (uint16_t)c;
       }
     }
     __syncthreads();
@@ -928,16 +931,16 @@ dsnot_apply_kernel(const DsApplyParams p) {
   }
 }
 
-static size_t ds_state_bytes(int R, int max_cycle) {
-  return align_up((size_t)R * 4, 256) * 4 + align_up((size_t)R * 2 * max_cycle * 4, 256);
+static size_t ds_state_bytes(int R, int C, int max_cycle) {
+  return align_up((size_t)R * 4, 256) * 4 + align_up((size_t)C * 4, 256) + align_up((size_t)R * 2 * max_cycle * 4, 256);
 }
-size_t dsnot_refine_workspace_bytes(int R, int max_cycle) {
+size_t dsnot_refine_workspace_bytes(int R, int C, int max_cycle) {
   if (max_cycle <= 0 || max_cycle > kDsCap) max_cycle = kDsCap;
-  return VLMC_WS_COUNTER_BYTES + ds_state_bytes(R, max_cycle);
+  return VLMC_WS_COUNTER_BYTES + ds_state_bytes(R, C, max_cycle);
 }
 
-struct DsState { uint32_t* row_v; int* row_iv; int* row_stop; int* fb_rows; int* fb_count; int* walk; };
-static DsState ds_carve(void* ws, int R) {
+struct DsState { uint32_t* row_v; int* row_iv; int* row_stop; int* fb_rows; int* fb_count; float* sq; int* walk; };
+static DsState ds_carve(void* ws, int R, int C) {
   char* base = reinterpret_cast<char*>(ws) + VLMC_WS_COUNTER_BYTES;
   const size_t step = align_up((size_t)R * 4, 256);
   DsState s;
@@ -946,7 +949,8 @@ static DsState ds_carve(void* ws, int R) {
   s.row_stop = reinterpret_cast<int*>(base + 2 * step);
   s.fb_rows = reinterpret_cast<int*>(base + 3 * step);
   s.fb_count = reinterpret_cast<int*>(ws);                  // first word of the counter area
-  s.walk = reinterpret_cast<int*>(base + 4 * step);
+  s.sq = reinterpret_cast<float*>(base + 4 * step);          // sqrt(scaler_row), written by the walk, read by the apply pass
+  s.walk = reinterpret_cast<int*>(base + 4 * step + align_up((size_t)C * 4, 256));
   return s;
 }
 
@@ -960,7 +964,7 @@ static int ds_common_checks(const void* W, int dtype, int R, int C, int64_t ldw,
   if (C % V != 0 || ldw % V != 0 || ((uintptr_t)W & 15) != 0) return VLMC_ERR_UNSUPPORTED;
   if (C < max_cycle) return VLMC_ERR_UNSUPPORTED;     // the reference indexes out of bounds here
   if (!is_device_ptr(W) || !is_device_ptr(ws)) return VLMC_ERR_NOT_DEVICE;
-  if (ws_bytes < dsnot_refine_workspace_bytes(R, max_cycle)) return VLMC_ERR_WORKSPACE;
+  if (ws_bytes < dsnot_refine_workspace_bytes(R, C, max_cycle)) return VLMC_ERR_WORKSPACE;
   return VLMC_OK;
 }
 
@@ -993,7 +997,7 @@ extern "C" int vlmc_dsnot_refine_walk(const void* W, int dtype, int R, int C, in
   if (!is_device_ptr(scaler_row) || !is_device_ptr(sum_metric_row) || !is_device_ptr(var) || !is_device_ptr(ncycles))
     return VLMC_ERR_NOT_DEVICE;
   cudaStream_t st = (cudaStream_t)stream;
-  DsState s = ds_carve(ws, R);
+  DsState s = ds_carve(ws, R, C);
   DsParams p;
   p.W = W; p.ldw = ldw; p.R = R; p.C = C; p.scaler_row = scaler_row; p.sum_row = sum_metric_row; p.var = var;
   p.k = prune_n ? 0 : k; p.prune_n = prune_n; p.prune_m = prune_m; p.pow_var = pow_of_var; p.max_cycle = max_cycle_time;
@@ -1008,9 +1012,11 @@ extern "C" int vlmc_dsnot_refine_walk(const void* W, int dtype, int R, int C, in
   // go through dsnot_walk_kernel.  VLMC_DSNOT_WALK_V1=1 forces the old kernel for every row (A/B runs, tests).
   const char* v1e = getenv("VLMC_DSNOT_WALK_V1");
   const bool fast = !(v1e && v1e[0] == '1') && prune_n == 0 && !initial_magnitude && k > 0 && C < 32768 &&
-                    C >= 2 * max_cycle_time && C - k >= 2 * max_cycle_time;
+                    C >= 2 * max_cycle_time && C - k >= 2 * max_cycle_time && ((uintptr_t)sum_metric_row & 15) == 0;
+  p.sq = s.sq;
   if (fast) {
     if (cudaMemsetAsync(s.fb_count, 0, sizeof(int), st) != cudaSuccess) return check_launch();
+    ds_sqrt_kernel<<<(C + 255) / 256, 256, 0, st>>>(scaler_row, s.sq, C);
 #define VLMC_DS_WALK2(TT) { rc = ds_grid(dsnot_walk2_kernel<TT>, smem, R, &grid); if (rc) return rc; \
                             dsnot_walk2_kernel<TT><<<grid, kDsThreads, smem, st>>>(p); }
     switch (dtype) {
@@ -1046,7 +1052,7 @@ extern "C" int vlmc_dsnot_refine_apply(void* W, int dtype, int R, int C, int64_t
   if (ldm % V != 0 || ((uintptr_t)keep_mask & 7) != 0) return VLMC_ERR_UNSUPPORTED;
   if (!is_device_ptr(scaler_row) || !is_device_ptr(ncycles) || !is_device_ptr(keep_mask)) return VLMC_ERR_NOT_DEVICE;
   cudaStream_t st = (cudaStream_t)stream;
-  DsState s = ds_carve(ws, R);
+  DsState s = ds_carve(ws, R, C);
   DsApplyParams p;
   p.W = W; p.ldw = ldw; p.R = R; p.C = C; p.scaler_row = scaler_row; p.prune_n = prune_n; p.prune_m = prune_m;
   p.initial_magnitude = initial_magnitude; p.max_cycle = max_cycle_time; p.ref_fixup = ref_fixup; p.zero_w = zero_w;
