@@ -22,6 +22,7 @@
 // Latency-bound (one thread walks <= 128 dependent steps per row), not HBM-bound: 2 B/weight read in pass 1,
 // 5 B/weight in pass 2.
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 
 namespace vlmc {
@@ -633,6 +634,16 @@ dsnot_walk2_kernel(const DsParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = p.C, maxc = p.max_cycle, k = p.k;
   const uint32_t Nk = (uint32_t)(3 * maxc + 16);              // kept candidates wanted: both sign classes then hold >= maxc
+  // histogram of (key >> bshift) & bmask over the scores whose bits above pshift equal `prefix` (four keys per load)
+  auto light_pass = [&](int pshift, uint32_t prefix, int bshift, uint32_t bmask) {
+    for (int c4 = tid * 4; c4 < C; c4 += kDsThreads * 4) {
+      const uint4 kq = *reinterpret_cast<const uint4*>(keyA + c4);
+      const uint32_t ke[4] = {kq.x, kq.y, kq.z, kq.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if ((ke[e] >> pshift) == prefix) atomicAdd(&sh.hist[(ke[e] >> bshift) & bmask], 1u);
+    }
+  };
 
   for (int row = blockIdx.x; row < p.R; row += gridDim.x) {
     const T* wrow = reinterpret_cast<const T*>(p.W) + (int64_t)row * p.ldw;
@@ -670,10 +681,7 @@ dsnot_walk2_kernel(const DsParams p) {
     __syncthreads();
     for (int b = tid; b < kDsBins; b += kDsThreads) sh.hist[b] = 0;
     __syncthreads();
-    for (int c = tid; c < C; c += kDsThreads) {
-      const uint32_t key = keyA[c];
-      if ((key >> 20) == b0) atomicAdd(&sh.hist[(key >> 9) & 0x7ffu], 1u);
-    }
+    light_pass(20, b0, 9, 0x7ffu);
     __syncthreads();
     uint32_t bq1 = 0;
     if (bq0 == b0) {                                           // both ranks in one top-level bin: one histogram serves both
@@ -688,10 +696,7 @@ dsnot_walk2_kernel(const DsParams p) {
     if (bq0 != b0) {
       for (int b = tid; b < kDsBins; b += kDsThreads) sh.hist[b] = 0;
       __syncthreads();
-      for (int c = tid; c < C; c += kDsThreads) {
-        const uint32_t key = keyA[c];
-        if ((key >> 20) == bq0) atomicAdd(&sh.hist[(key >> 9) & 0x7ffu], 1u);
-      }
+      light_pass(20, bq0, 9, 0x7ffu);
       __syncthreads();
       ds2_scan(sh, kkq, 0, 1);
       bq1 = sh.t_bin[0];
@@ -701,10 +706,7 @@ dsnot_walk2_kernel(const DsParams p) {
     for (int b = tid; b < kDsBins; b += kDsThreads) sh.hist[b] = 0;
     __syncthreads();
     const uint32_t pre22 = (b0 << 11) | b1;
-    for (int c = tid; c < C; c += kDsThreads) {
-      const uint32_t key = keyA[c];
-      if ((key >> 9) == pre22) atomicAdd(&sh.hist[key & 0x1ffu], 1u);
-    }
+    light_pass(9, pre22, 0, 0x1ffu);
     __syncthreads();
     ds2_scan(sh, kk, 0, 1);
     const uint32_t v = (pre22 << 9) | sh.t_bin[0];
@@ -718,33 +720,36 @@ dsnot_walk2_kernel(const DsParams p) {
 
     // ---- pass 2: classify; reconstruction error; regrow key + its histogram; kept candidates ----
     double esum = 0.0;
-    const bool pow1 = p.pow_var == 1.f, pow0 = p.pow_var == 0.f;
-    for (int c = tid; c < C; c += kDsThreads) {
-      const uint32_t key = keyA[c];
-      const float d = dm[c];
-      const bool pruned = key < v || (key == v && c <= iv);
-      uint32_t kr;
-      if (pruned) {
-        esum += (double)d;
-        keyA[c] = kPrunedKey;
-        float mval = d;
-        if (!pow0) mval = __fdiv_rn(mval, pow1 ? p.var[c] : powf(p.var[c], p.pow_var));
-        kr = sortable(mval);
-      } else {
-        // 0 / var without the divide (a zero numerator takes the slow path of the IEEE division): 0 unless var is 0 or NaN
-        kr = 0x80000000u;
-        if (!pow0) {
-          const float vv = pow1 ? p.var[c] : powf(p.var[c], p.pow_var);
-          if (vv == 0.f || vv != vv) kr = 0xffffffffu;         // 0/0 and 0/NaN are NaN: sorts last
+    // POW: 1 = divide by var (the default pow_of_var_regrowing), 0 = no division, 2 = divide by var^pow
+    auto pass2 = [&](auto pow_tag) {
+      constexpr int POW = decltype(pow_tag)::value;
+      for (int c = tid; c < C; c += kDsThreads) {
+        const uint32_t key = keyA[c];
+        const float d = dm[c];
+        const bool pruned = key < v || (key == v && c <= iv);
+        float vv = 1.f;
+        if (POW == 1) vv = p.var[c];
+        if (POW == 2) vv = powf(p.var[c], p.pow_var);
+        uint32_t kr;
+        if (pruned) {
+          esum += (double)d;
+          keyA[c] = kPrunedKey;
+          kr = sortable(POW == 0 ? d : __fdiv_rn(d, vv));
+        } else {
+          // 0 / var without the divide (a zero numerator takes the slow path of the IEEE division): 0 unless var is 0 or NaN
+          kr = (POW != 0 && (vv == 0.f || vv != vv)) ? 0xffffffffu : 0x80000000u;
+          if ((key >> 9) <= vq22 && d != 0.f) {                // a kept column with a zero metric belongs to neither class
+            const uint32_t slot = atomicAdd(&sh.nkept, 1u);
+            if (slot < (uint32_t)kW2Kept) sh.ckept[slot] = (uint16_t)((uint32_t)c | (d < 0.f ? 0x8000u : 0u));
+          }
         }
-        if ((key >> 9) <= vq22 && d != 0.f) {                  // a kept column with a zero metric belongs to neither class
-          const uint32_t slot = atomicAdd(&sh.nkept, 1u);
-          if (slot < (uint32_t)kW2Kept) sh.ckept[slot] = (uint16_t)((uint32_t)c | (d < 0.f ? 0x8000u : 0u));
-        }
+        keyR[c] = kr;
+        atomicAdd(&sh.hist[kr >> 21], 1u);
       }
-      keyR[c] = kr;
-      atomicAdd(&sh.hist[kr >> 21], 1u);
-    }
+    };
+    if (p.pow_var == 1.f) pass2(std::integral_constant<int, 1>{});
+    else if (p.pow_var == 0.f) pass2(std::integral_constant<int, 0>{});
+    else pass2(std::integral_constant<int, 2>{});
     const float err0 = (float)block_sum(esum, sh);             // :601 (barriers inside: histogram and candidates complete)
     __syncthreads();
     // ---- the two ends of the regrow ordering: bins holding the maxc smallest / largest keys ----
@@ -804,25 +809,24 @@ dsnot_walk2_kernel(const DsParams p) {
       if (tid == 0) p.fb_rows[atomicAdd(p.fb_count, 1)] = row;
       continue;
     }
-    // ---- the cycle loop, one thread; ends at the row's stop cycle ----
+    // ---- the cycle loop, one thread; ends at the row's stop cycle.  The head entry of each of the four lists sits in
+    //      registers and is refilled as soon as it is consumed, so the shared-memory latency overlaps the error update ----
     if (tid == 0) {
       float err = err0;
       const float sign0 = sgnf(err0);
-      bool upd = true;
       int stop = 0;
       int hR = 0, tR = 0, hP = 0, tP = 0;
+      int cN = sh.lists[0][0], cP = sh.lists[1][0], cH = sh.lists[2][0], cT = sh.lists[3][0];
+      float dN = sh.listsD[0][0], dP = sh.listsD[1][0], dH = sh.listsD[2][0], dT = sh.listsD[3][0];
       for (int c = 1; c <= maxc; ++c) {
-        const int l = err > 0.f ? 3 : 2;                       // :654 regrow from the tail / head
-        const int e = l == 3 ? tR++ : hR++;
-        const int rg = sh.lists[l][e];
-        const float rm = sh.listsD[l][e];
-        int pr; float pm;
-        if (err < 0.f) { pr = sh.lists[1][tP]; pm = sh.listsD[1][tP]; ++tP; }     // :683 the positive class, from its far end
-        else { pr = sh.lists[0][hP]; pm = sh.listsD[0][hP]; ++hP; }
-        const float after = __fsub_rn(__fadd_rn(err, pm), rm); // :713
+        int rg, pr; float rm, pm;
+        if (err > 0.f) { rg = cT; rm = dT; ++tR; cT = sh.lists[3][tR & (kDsCap - 1)]; dT = sh.listsD[3][tR & (kDsCap - 1)]; }   // :654
+        else { rg = cH; rm = dH; ++hR; cH = sh.lists[2][hR & (kDsCap - 1)]; dH = sh.listsD[2][hR & (kDsCap - 1)]; }
+        if (err < 0.f) { pr = cP; pm = dP; ++tP; cP = sh.lists[1][tP & (kDsCap - 1)]; dP = sh.listsD[1][tP & (kDsCap - 1)]; }   // :683
+        else { pr = cN; pm = dN; ++hP; cN = sh.lists[0][hP & (kDsCap - 1)]; dN = sh.listsD[0][hP & (kDsCap - 1)]; }
         const bool big = fabsf(err) > p.thr;
-        if (p.without_same_sign) upd = upd && big;             // :717-720
-        else upd = upd && big && (sign0 == sgnf(after));       // :722-729
+        bool upd = big;                                        // :717-720
+        if (!p.without_same_sign) upd = big && (sign0 == sgnf(__fsub_rn(__fadd_rn(err, pm), rm)));   // :713, :722-729
         sh.walk[2 * (c - 1)] = pr;
         sh.walk[2 * (c - 1) + 1] = rg;
         if (!upd) { stop = c; break; }
