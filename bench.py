@@ -560,8 +560,8 @@ def roofline_of(res, pk):
     info = {
         "sqnorm_accum": ("hbm", "colstats_kernel<half,0> (vlmc_sqnorm_accum): T*C*2 B per launch"),
         "dsnot_stats": ("hbm", "colstats_kernel<half,1> (vlmc_dsnot_stats): T*C*2 B per launch"),
-        "wanda_select": ("hbm", "nm_batch_kernel (all linears of the block in one launch) / rowselect_kernel: 5 B per weight"),
-        "dsnot_refine": ("hbm", "dsnot_walk_kernel + dsnot_apply_kernel: 7 B per weight (latency-bound, see DESIGN.md)"),
+        "wanda_select": ("hbm", "nm_batch_kernel (all linears of the block in one launch) / rowselect_cta_kernel: 5 B per weight"),
+        "dsnot_refine": ("hbm", "dsnot_walk2_kernel + dsnot_apply_kernel: 7 B per weight (latency / issue-bound, see DESIGN.md)"),
         "hessian_accum": ("tensor", "hessian_syrk_kernel (vlmc_hessian_accum): 2*T*C^2 logical flop per call (SYRK executes half)"),
         "chol_inv_upper": ("tensor", "blocked Cholesky + triangular inverse (3xTF32 tcgen05 GEMMs, the chains of the block run concurrently): 2/3 C^3 flop per Hessian"),
         "sparsegpt_chains": ("tensor", "factorisation (blocked Cholesky + triangular inverse) and OBS sweep chains of the block, pipelined "
@@ -1218,7 +1218,10 @@ def config5_lora_and_hessian_sweep(torch, native, dev, inputs):
             b.record()
             torch.cuda.synchronize()
             t = a.elapsed_time(b)
-            sweep[f"C{C}_T{nseq}x{SEQ_LEN}"] = {"ms": t, "logical_tflops": 2.0 * nseq * SEQ_LEN * C * C / t / 1e9}
+            nt = (C + 255) // 256                          # the SYRK executes the upper 256 x 256 tiles only
+            executed = 2.0 * nseq * SEQ_LEN * (nt * (nt + 1) // 2) * 256.0 * 256.0
+            sweep[f"C{C}_T{nseq}x{SEQ_LEN}"] = {"ms": t, "logical_tflops": 2.0 * nseq * SEQ_LEN * C * C / t / 1e9,
+                                                  "executed_tflops": executed / t / 1e9}
         del H
     out["hessian_accum_sweep"] = sweep
     torch.cuda.empty_cache()

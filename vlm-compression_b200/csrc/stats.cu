@@ -37,6 +37,62 @@ struct StatsParams {
   double n_before, b_per_seg, ntok_before;
 };
 
+// sm_100a mixed-precision FP32 ops with 16-bit operands (FHFMA / FHADD, PTX fma.rn.f32.f16 / sub.rn.f32.f16 and the .bf16
+// forms): the half of a packed register is an operand selector (.H1), so a 16-bit activation enters the fp32 accumulation
+// without an unpack instruction.  Same values as unpack + fmaf / fsub: the product of two 11-bit significands is exact in
+// fp32, one rounding at the end.
+template <typename T> struct Mix;
+template <> struct Mix<__half> {
+  __device__ static __forceinline__ float sq_acc(unsigned short a, float c) { float d; asm("fma.rn.f32.f16 %0, %1, %1, %2;" : "=f"(d) : "h"(a), "f"(c)); return d; }
+  __device__ static __forceinline__ float sub(unsigned short a, float c) { float d; asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(a), "f"(c)); return d; }
+};
+template <> struct Mix<__nv_bfloat16> {
+  __device__ static __forceinline__ float sq_acc(unsigned short a, float c) { float d; asm("fma.rn.f32.bf16 %0, %1, %1, %2;" : "=f"(d) : "h"(a), "f"(c)); return d; }
+  __device__ static __forceinline__ float sub(unsigned short a, float c) { float d; asm("sub.rn.f32.bf16 %0, %1, %2;" : "=f"(d) : "h"(a), "f"(c)); return d; }
+};
+template <> struct Mix<float> {   // never used (fp32 activations take the plain path); keeps the template well-formed
+  __device__ static __forceinline__ float sq_acc(unsigned short, float c) { return c; }
+  __device__ static __forceinline__ float sub(unsigned short, float c) { return c; }
+};
+
+// one 16-byte vector into the per-column accumulators
+template <typename T, bool DSNOT>
+__device__ __forceinline__ void colstats_accum(const uint4& v, float (&a0)[Elem<T>::kVec], float (&a1)[Elem<T>::kVec],
+                                               const float (&x0)[Elem<T>::kVec]) {
+  constexpr int V = Elem<T>::kVec;
+  // Wanda's kernel keeps the unpack + fmaf form: it lives in 32 registers (8 CTAs per SM) and the FHFMA form spilled there
+  if (sizeof(T) == 2 && DSNOT) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const unsigned short lo = (unsigned short)(w[q] & 0xffffu), hi = (unsigned short)(w[q] >> 16);
+      constexpr int kLast = V - 1;
+      const int i0 = (2 * q) & kLast, i1 = (2 * q + 1) & kLast;      // V == 8 here; the mask keeps the fp32 instantiation in bounds
+      if (DSNOT) {
+        const float d0 = Mix<T>::sub(lo, x0[i0]), d1 = Mix<T>::sub(hi, x0[i1]);
+        a0[i0] += d0; a1[i0] = fmaf(d0, d0, a1[i0]);
+        a0[i1] += d1; a1[i1] = fmaf(d1, d1, a1[i1]);
+      } else {
+        a1[i0] = Mix<T>::sq_acc(lo, a1[i0]);
+        a1[i1] = Mix<T>::sq_acc(hi, a1[i1]);
+      }
+    }
+  } else {
+    float f[V];
+    Elem<T>::unpack(v, f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      if (DSNOT) {
+        const float d = f[i] - x0[i];
+        a0[i] += d;
+        a1[i] = fmaf(d, d, a1[i]);
+      } else {
+        a1[i] = fmaf(f[i], f[i], a1[i]);
+      }
+    }
+  }
+}
+
 // resident CTAs per SM the grid is sized for (one full wave, no tail): the Wanda variant fits 32 registers
 // (8 x 256 threads = 64 warps / SM); the DSnoT variant carries 3x the per-thread state
 template <bool DSNOT> struct StatsOcc { static constexpr int kBlocksPerSM = DSNOT ? 4 : 8; };
@@ -75,35 +131,11 @@ __device__ __forceinline__ void colstats_body(const StatsParams& p, const int ct
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream(xp + (r + u * kRY) * p.ldx);
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        float f[V];
-        Elem<T>::unpack(v[u], f);
-#pragma unroll
-        for (int i = 0; i < V; ++i) {
-          if (DSNOT) {
-            float d = f[i] - x0[i];
-            a0[i] += d;
-            a1[i] = fmaf(d, d, a1[i]);
-          } else {
-            a1[i] = fmaf(f[i], f[i], a1[i]);
-          }
-        }
-      }
+      for (int u = 0; u < kUnroll; ++u) colstats_accum<T, DSNOT>(v[u], a0, a1, x0);
     }
     for (; r < r1; r += kRY) {
       uint4 v = ld_stream(xp + r * p.ldx);
-      float f[V];
-      Elem<T>::unpack(v, f);
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        if (DSNOT) {
-          float d = f[i] - x0[i];
-          a0[i] += d;
-          a1[i] = fmaf(d, d, a1[i]);
-        } else {
-          a1[i] = fmaf(f[i], f[i], a1[i]);
-        }
-      }
+      colstats_accum<T, DSNOT>(v, a0, a1, x0);
     }
   }
 

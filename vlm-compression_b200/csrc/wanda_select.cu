@@ -870,12 +870,15 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
   // per bin (2-3 keys per bin at C = 4096), and everything above twice the threshold in the last bin, which is never
   // counted (the k-th score is found below it, or the row takes the exact path).  The first row of a CTA has no
   // predecessor: its scale comes from its own maximum (coarser: more candidates, same result).
+  // Rows of <= 5 vectors per thread are double-buffered in registers: the next row's loads are issued before this row is
+  // processed, so the ~1 us of HBM latency per row (a fifth of a 4096-column row's time at 5 CTAs per SM) is not exposed.
+  constexpr bool kPrefetch = NV <= 5;
+  uint4 wv[NV];
   float scale = 0.f;
   {
     const int row = blockIdx.x;
     uint32_t lmax = 0;
     if (row < R) {
-      uint4 wv[NV];
       load_row(row, wv);
 #pragma unroll
       for (int u = 0; u < NV; ++u) {
@@ -899,8 +902,17 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
 
   for (int row = blockIdx.x; row < R; row += gridDim.x) {
     T* wrow = W + (int64_t)row * ldw;
-    uint4 wv[NV];
-    load_row(row, wv);
+    uint4 nx[kPrefetch ? NV : 1];
+    if (kPrefetch) {                                           // wv holds this row (first row: loaded by the prologue)
+      if (row + (int)gridDim.x < R) {
+        const T* nrow = W + (int64_t)(row + gridDim.x) * ldw;
+#pragma unroll
+        for (int u = 0; u < NV; ++u)
+          if (RC_HAS(u)) nx[kPrefetch ? u : 0] = ld_stream(nrow + (int64_t)(tid + u * kRcThreads) * V);
+      }
+    } else if (row != (int)blockIdx.x) {
+      load_row(row, wv);
+    }
     // ---- P1: score, keys -> smem, row sum, linear-bin histogram
     float lsum = 0.f;
 #pragma unroll
@@ -1114,6 +1126,10 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
           if (zero_w && pm) st_stream(wrow + (int64_t)vi * V, rc_zero<T>(*reinterpret_cast<const uint4*>(wrow + (int64_t)vi * V), pm));
         }
       }
+    }
+    if (kPrefetch) {
+#pragma unroll
+      for (int u = 0; u < NV; ++u) wv[u] = nx[kPrefetch ? u : 0];
     }
     // next row's scale: this row's threshold in the middle of the bins
     if (select && thr_key > 0u && thr_key < 0x7f800000u) scale = (float)(kRcBins / 2) / __uint_as_float(thr_key);
