@@ -95,7 +95,13 @@ __device__ __forceinline__ void colstats_accum(const uint4& v, float (&a0)[Elem<
 
 // resident CTAs per SM the grid is sized for (one full wave, no tail): the Wanda variant fits 32 registers
 // (8 x 256 threads = 64 warps / SM); the DSnoT variant carries 3x the per-thread state
-template <bool DSNOT> struct StatsOcc { static constexpr int kBlocksPerSM = DSNOT ? 4 : 8; };
+template <bool DSNOT> struct StatsOcc {
+  static constexpr int kBlocksPerSM = DSNOT ? 3 : 8;
+  // 16-byte loads in flight per thread.  The DSnoT variant is bound by bytes in flight (ncu r02ab: long-scoreboard stalls
+  // 16 per issue, 4.9 TB/s): its 24 registers of per-column state leave room for 4 loads at 4 CTAs per SM = 64 KB per SM in
+  // flight against the 128 KB of the Wanda variant; 8 loads at 3 CTAs per SM put 96 KB in flight.
+  static constexpr int kLoads = DSNOT ? 8 : 4;
+};
 
 template <typename T, bool DSNOT, int kCX>
 __device__ __forceinline__ void colstats_body(const StatsParams& p, const int ct, const int64_t chunk) {
@@ -126,12 +132,13 @@ __device__ __forceinline__ void colstats_body(const StatsParams& p, const int ct
       Elem<T>::unpack(v, x0);
     }
     int64_t r = r0 + ty;
-    for (; r + (kUnroll - 1) * kRY < r1; r += kUnroll * kRY) {
-      uint4 v[kUnroll];
+    constexpr int kU = StatsOcc<DSNOT>::kLoads;
+    for (; r + (kU - 1) * kRY < r1; r += kU * kRY) {
+      uint4 v[kU];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) v[u] = ld_stream(xp + (r + u * kRY) * p.ldx);
+      for (int u = 0; u < kU; ++u) v[u] = ld_stream(xp + (r + u * kRY) * p.ldx);
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) colstats_accum<T, DSNOT>(v[u], a0, a1, x0);
+      for (int u = 0; u < kU; ++u) colstats_accum<T, DSNOT>(v[u], a0, a1, x0);
     }
     for (; r < r1; r += kRY) {
       uint4 v = ld_stream(xp + r * p.ldx);
@@ -290,6 +297,8 @@ static StatsPlan plan_stats(int dtype, int64_t nseg, int64_t S, int C, int kinds
   int64_t cps = want / nseg;
   if (cps < 1) cps = 1;
   const int64_t min_rows = kRY * kUnroll * 2;
+  // (splitting the segments of a multi-wave DSnoT grid into 2-3 chunks to fill the last wave was measured: 0.47 -> 0.69 ms
+  // at C = 4096 - the per-chunk set-up and the longer last-CTA merge cost more than the 8 % idle tail)
   int64_t max_cps = (S + min_rows - 1) / min_rows;
   if (cps > max_cps) cps = max_cps;
   if (cps < 1) cps = 1;
@@ -302,9 +311,10 @@ static StatsPlan plan_stats(int dtype, int64_t nseg, int64_t S, int C, int kinds
 
 size_t stats_workspace_bytes(int dsnot, int64_t T, int C, int64_t nseg) {
   if (nseg < 1) nseg = 1;
-  // dtype only changes the tile count; take the fp32 plan (more tiles, fewer chunks) as the bound
-  size_t a = plan_stats(VLMC_F32, nseg, T / nseg, C, dsnot ? 3 : 1).bytes;
-  size_t b = plan_stats(VLMC_F16, nseg, T / nseg, C, dsnot ? 3 : 1).bytes;
+  // dtype only changes the tile count; take the larger of the fp32 and the 16-bit plan (same occupancy as the launch)
+  const int bps = dsnot ? StatsOcc<true>::kBlocksPerSM : StatsOcc<false>::kBlocksPerSM;
+  size_t a = plan_stats(VLMC_F32, nseg, T / nseg, C, dsnot ? 3 : 1, bps).bytes;
+  size_t b = plan_stats(VLMC_F16, nseg, T / nseg, C, dsnot ? 3 : 1, bps).bytes;
   return a > b ? a : b;
 }
 
