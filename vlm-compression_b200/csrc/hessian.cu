@@ -22,6 +22,7 @@
 //   warp 2      TMEM allocator   512 columns = 2 accumulator buffers (chunk n+1 overlaps the drain of chunk n)
 //   warps 4-11  epilogue         tcgen05.ld -> fp32 register accumulators -> fused H update (+ mirror)
 #include <cstdlib>
+#include <stdlib.h>
 #include "tc.cuh"
 #include "gemm3x.cuh"
 
@@ -517,7 +518,12 @@ extern "C" int vlmc_hessian_accum(const void* x, int dtype, int64_t T, int C, in
     p.nbi = nb2; p.nbj = nb2;
     p.ntiles = nb2 * (nb2 + 1) / 2;
   }
-  const int grid = use_pair ? 2 * (p.ntiles < kNumSMs / 2 ? p.ntiles : kNumSMs / 2) : (p.ntiles < kNumSMs ? p.ntiles : kNumSMs);
+  // VLMC_HESS_MAX_SMS (read per call): SMs this accumulation may occupy.  A caller that runs latency-bound chains on other
+  // streams at the same time (the overlapped SparseGPT block schedule) leaves them a few SMs this way: the persistent grid
+  // would otherwise hold every SM until the launch ends.
+  int sm_cap = kNumSMs;
+  if (const char* e = getenv("VLMC_HESS_MAX_SMS")) { const int v = atoi(e); if (v >= 2 && v < kNumSMs) sm_cap = v; }
+  const int grid = use_pair ? 2 * (p.ntiles < sm_cap / 2 ? p.ntiles : sm_cap / 2) : (p.ntiles < sm_cap ? p.ntiles : sm_cap);
 
   // Long calibration sets are processed in slabs of tokens, all tiles per slab: the CTAs of a wave then read the
   // same slab of X at about the same time and the operand re-reads (each column block feeds ~C/256 tiles) hit in
