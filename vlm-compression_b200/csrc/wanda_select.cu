@@ -749,10 +749,14 @@ template <int NB>
 __device__ __forceinline__ void rc_scan_warp(uint32_t* hist, uint32_t kk, RcShared& sh) {
   const int lane = threadIdx.x & 31;
   constexpr int per = NB / 32;                                // lane owns bins [lane * per, lane * per + per)
-  // rotated walk: at step j lane reads word (j + lane) % 64 of its segment -> bank (j + lane) % 32: conflict-free
+  // rotated walk in 16-byte steps: at step j lane reads vector (j + lane) % (per / 4) of its segment; the eight lanes of a
+  // quarter warp (one LDS.128 phase) then hit eight different 16-byte bank groups: conflict-free
   uint32_t local = 0;
-#pragma unroll 16
-  for (int j = 0; j < per; ++j) local += hist[lane * per + ((j + lane) & (per - 1))];
+#pragma unroll
+  for (int j = 0; j < per / 4; ++j) {
+    const uint4 q = *reinterpret_cast<const uint4*>(hist + lane * per + ((j + lane) & (per / 4 - 1)) * 4);
+    local += q.x + q.y + q.z + q.w;
+  }
   uint32_t incl = local;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -781,8 +785,9 @@ __device__ __forceinline__ void rc_scan_warp(uint32_t* hist, uint32_t kk, RcShar
     }
   }
   __syncwarp();
-#pragma unroll 16
-  for (int j = 0; j < per; ++j) hist[lane * per + ((j + lane) & (per - 1))] = 0;
+#pragma unroll
+  for (int j = 0; j < per / 4; ++j)
+    *reinterpret_cast<uint4*>(hist + lane * per + ((j + lane) & (per / 4 - 1)) * 4) = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // All threads: same result in registers (used by the exact path only; two barriers inside)
@@ -841,7 +846,7 @@ __device__ __forceinline__ uint4 rc_zero(const uint4& wv, uint32_t pm) {
 }
 
 template <typename T, int NV, bool FULL>      // FULL: C / V == NV * 128, no bounds checks on the vectors
-__global__ void __launch_bounds__(kRcThreads, NV <= 4 ? 5 : (NV <= 8 ? 4 : 3))
+__global__ void __launch_bounds__(kRcThreads, NV <= 4 ? 6 : (NV <= 8 ? 4 : 3))
 rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ sq, int k, int zero_w,
                      uint8_t* __restrict__ mask, int64_t ldm, float* __restrict__ row_sum) {
   constexpr int V = Elem<T>::kVec;
@@ -870,9 +875,10 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
   // per bin (2-3 keys per bin at C = 4096), and everything above twice the threshold in the last bin, which is never
   // counted (the k-th score is found below it, or the row takes the exact path).  The first row of a CTA has no
   // predecessor: its scale comes from its own maximum (coarser: more candidates, same result).
-  // Rows of <= 5 vectors per thread are double-buffered in registers: the next row's loads are issued before this row is
-  // processed, so the ~1 us of HBM latency per row (a fifth of a 4096-column row's time at 5 CTAs per SM) is not exposed.
-  constexpr bool kPrefetch = NV <= 5;
+  // (Double-buffering the next row's vectors in registers was measured: 38.0 -> 38.3 us at 4096^2 - with 5-6 CTAs per SM the
+  // HBM latency of a row's loads is already covered by the other CTAs - and it costs 10 registers; the code path stays for
+  // experiments.)
+  constexpr bool kPrefetch = false;
   uint4 wv[NV];
   float scale = 0.f;
   {
