@@ -714,6 +714,27 @@ def test_obs_sweep_vs_oracle_same_factor(native, R, C, sp, n, m):
         assert bool((per_block >= int(R * 128 * sp) + 1).all())     # `<=` threshold: at least k+1 per block (:185)
 
 
+@pytest.mark.parametrize("R,C,sp,tag", [(96, 512, 0.5, "bf16"), (300, 1408, 0.6, "f16"), (4096, 1024, 0.5, "f16"), (1000, 640, 0.3, "f32")])
+def test_obs_fused_block_kernel_equals_the_three_pass_launches(native, R, C, sp, tag, monkeypatch):
+    """The cooperative kernel that runs the three histogram passes and the sweep of a block in one launch against the
+    separate launches: same threshold, same arithmetic -> identical weights, masks and importance score."""
+    x = acts(4 * C, C, R, torch.bfloat16).cuda()
+    H = torch.zeros(C, C, device="cuda")
+    native.hessian_accum(x, H, 0, 1)
+    U, dead, _ = _factor(native, H)
+    W0 = weights(R, C, 78, DT[tag], 0.05).cuda()
+    outs = []
+    for fused in ("0", "1"):
+        monkeypatch.setenv("VLMC_OBS_FUSED", fused)
+        W = W0.clone()
+        keep, score = native.obs_sweep(W, U, sp, 0, 0, dead=dead, want_mask=True)
+        torch.cuda.synchronize()
+        outs.append((W, keep, score.item()))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    assert outs[0][2] == outs[1][2]
+
+
 def test_sparsegpt_full_size_properties(native):
     """Vicuna-7B q_proj size: 2:4 structure exact, unstructured per-block counts, output error no worse than
     magnitude pruning at the same sparsity (the point of the OBS compensation)."""

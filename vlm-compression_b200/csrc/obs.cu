@@ -18,6 +18,7 @@
 //                                weight, the fp32 working copy, Err1 and the keep mask.
 //   K13  the lazy trailing update on the tensor cores: the 3xTF32 tcgen05 GEMM of gemm3x.cu (fp32-grade accuracy).
 #include <stdlib.h>
+#include <cooperative_groups.h>
 #include "gemm3x.cuh"
 
 namespace vlmc {
@@ -362,6 +363,191 @@ obs_sweep4_kernel(const ObsParams p, int dtype, int vec_ok) {
   }
 }
 
+// K11 + K12 in ONE launch for the unstructured sweep: a cooperative grid in which every warp owns four
+// rows for the whole block.  The block scores (16 per lane) are computed once and stay in registers through the three
+// histogram passes of the exact radix select; between the passes the grid meets at a grid barrier (the CTAs' shared-memory
+// histograms flushed to the block's global one, every CTA then finds the chosen bin itself), then the 128-step sweep runs on
+// the same registers.  Replaces three obs_hist_kernel launches, their three passes over the fp32 working copy and the
+// 3 x find_bin prologue of obs_sweep4_kernel; same arithmetic per element, same threshold, bit-identical results.
+// Needs every CTA resident at once: launched with cudaLaunchCooperativeKernel, R <= 32 * (resident CTAs).
+__global__ void __launch_bounds__(kSw4Threads, 3)
+obs_block_fused_kernel(const ObsParams p, int dtype, int vec_ok) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) float Us[];                  // [kOB][kOB] U1 tile, zero padded, then the CTA histogram
+  unsigned int* sh_hist = reinterpret_cast<unsigned int*>(Us + kOB * kOB);   // [kObsBins]
+  __shared__ unsigned int s_scan[32];
+  __shared__ __align__(16) float s_d[kOB];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bs = p.bs;
+#pragma unroll 4
+  for (int idx = tid; idx < kOB * kOB / 4; idx += kSw4Threads) {
+    const int i = idx / (kOB / 4), j = (idx % (kOB / 4)) * 4;
+    float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < bs && j < bs && j + 3 >= i) u = *reinterpret_cast<const float4*>(p.U + (int64_t)(p.i1 + i) * p.ldu + p.i1 + j);
+    *reinterpret_cast<float4*>(Us + i * kOB + j) = u;
+  }
+  if (tid < kOB) s_d[tid] = tid < bs ? p.U[(int64_t)(p.i1 + tid) * p.ldu + p.i1 + tid] : 1.f;
+  for (int b = tid; b < kObsBins; b += kSw4Threads) sh_hist[b] = 0;
+  __syncthreads();
+  const int g = lane >> 3, l = lane & 7, gbase = lane & ~7;
+  const bool skip_out = p.fail != nullptr && *p.fail != 0;
+  const float4* Us4 = reinterpret_cast<const float4*>(Us);
+
+  const int row = (blockIdx.x * (kSw4Threads / 32) + warp) * 4 + g;
+  const bool valid = row < p.R;
+  float* w32 = p.W32 + (int64_t)row * p.C + p.i1 + 4 * l;
+  float w[4][4];
+  uint32_t key[4][4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool in = valid && 32 * t + 4 * l < bs;
+    if (in) x = *reinterpret_cast<const float4*>(w32 + 32 * t);
+    w[t][0] = x.x; w[t][1] = x.y; w[t][2] = x.z; w[t][3] = x.w;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float d = s_d[32 * t + 4 * l + e];
+      key[t][e] = in ? obs_key(w[t][e], __fmul_rn(d, d)) : 0xffffffffu;      // 0xffffffff: not an element of the block
+    }
+  }
+  // ---- exact k-th smallest block score: 11 / 11 / 10-bit radix select, three grid-wide rounds ----
+  unsigned int b1 = 0, b2 = 0, before = 0, kk = p.kth;
+#pragma unroll 1
+  for (int pass = 0; pass < 3; ++pass) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t k = key[t][e];
+        if (k == 0xffffffffu) continue;                        // (a NaN score has other bits: obs_key never yields all ones)
+        if (pass == 0) atomicAdd(&sh_hist[k >> 21], 1u);
+        else if (pass == 1) { if ((k >> 21) == b1) atomicAdd(&sh_hist[(k >> 10) & 0x7ffu], 1u); }
+        else { if ((k >> 21) == b1 && ((k >> 10) & 0x7ffu) == b2) atomicAdd(&sh_hist[k & 0x3ffu], 1u); }
+      }
+    __syncthreads();
+    for (int b = tid; b < kObsBins; b += kSw4Threads) {
+      const unsigned int c = sh_hist[b];
+      if (c) { atomicAdd(&p.hist->h[pass][b], c); sh_hist[b] = 0; }
+    }
+    __threadfence();
+    grid.sync();
+    unsigned int bin;
+    obs_find_bin<kSw4Threads>(p.hist->h[pass], kk, s_scan, bin, before);
+    kk -= before;
+    if (pass == 0) b1 = bin; else if (pass == 1) b2 = bin; else before = bin;      // `before` carries b3 out of the loop
+    __syncthreads();
+  }
+  const uint32_t v = (b1 << 21) | (b2 << 10) | before;          // the k-th smallest block score, exactly (:184)
+  uint32_t mbits = 0;                                            // bit 4 t + e: column 32 t + 4 l + e of this row is pruned
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (key[t][e] != 0xffffffffu && key[t][e] <= v) mbits |= 1u << (4 * t + e);           // `<=` (:185)
+
+  float er[4][4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) er[t][e] = 0.f;
+#pragma unroll
+  for (int t0 = 0; t0 < 4; ++t0) {
+    if (32 * t0 < bs) {
+#pragma unroll 1
+      for (int li = 0; li < 8; ++li) {
+        const int ib = 32 * t0 + 4 * li;
+        if (ib >= bs) break;
+        const uint32_t pm = __shfl_sync(0xffffffffu, mbits, gbase + li);
+        const float4 d4 = *reinterpret_cast<const float4*>(s_d + ib);
+        const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = ib + e;
+          const float wi = __shfl_sync(0xffffffffu, w[t0][e], gbase + li);
+          const bool pruned = (pm >> (4 * t0 + e)) & 1u;
+          const float quot = __fdiv_rn(wi, dd[e]);
+          const float err = pruned ? quot : 0.f;
+#pragma unroll
+          for (int t = t0; t < 4; ++t) {
+            const float4 u = Us4[i * (kOB / 4) + 8 * t + l];
+            w[t][0] = __fsub_rn(w[t][0], __fmul_rn(err, u.x)); w[t][1] = __fsub_rn(w[t][1], __fmul_rn(err, u.y));
+            w[t][2] = __fsub_rn(w[t][2], __fmul_rn(err, u.z)); w[t][3] = __fsub_rn(w[t][3], __fmul_rn(err, u.w));
+          }
+          if (l == li && pruned) { w[t0][e] = 0.f; er[t0][e] = err; }
+        }
+      }
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int col = 32 * t + 4 * l;
+      *reinterpret_cast<float4*>(p.Err + (int64_t)row * kErrLd + col) = make_float4(er[t][0], er[t][1], er[t][2], er[t][3]);
+      if (col < bs) {
+        *reinterpret_cast<float4*>(w32 + 32 * t) = make_float4(w[t][0], w[t][1], w[t][2], w[t][3]);
+        if (skip_out) continue;
+        const int64_t off = (int64_t)row * p.ldw + p.i1 + col;
+        if (dtype == VLMC_F32) {
+          float* wo = reinterpret_cast<float*>(p.Wout) + off;
+          if (vec_ok) *reinterpret_cast<float4*>(wo) = make_float4(w[t][0], w[t][1], w[t][2], w[t][3]);
+          else { wo[0] = w[t][0]; wo[1] = w[t][1]; wo[2] = w[t][2]; wo[3] = w[t][3]; }
+        } else if (dtype == VLMC_F16) {
+          __half* wo = reinterpret_cast<__half*>(p.Wout) + off;
+          const __half2 a = __floats2half2_rn(w[t][0], w[t][1]), b = __floats2half2_rn(w[t][2], w[t][3]);
+          if (vec_ok) *reinterpret_cast<uint2*>(wo) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+          else { wo[0] = __low2half(a); wo[1] = __high2half(a); wo[2] = __low2half(b); wo[3] = __high2half(b); }
+        } else {
+          __nv_bfloat16* wo = reinterpret_cast<__nv_bfloat16*>(p.Wout) + off;
+          const __nv_bfloat162 a = __floats2bfloat162_rn(w[t][0], w[t][1]), b = __floats2bfloat162_rn(w[t][2], w[t][3]);
+          if (vec_ok) *reinterpret_cast<uint2*>(wo) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+          else { wo[0] = __low2bfloat16(a); wo[1] = __high2bfloat16(a); wo[2] = __low2bfloat16(b); wo[3] = __high2bfloat16(b); }
+        }
+        if (p.keep) {
+          uint8_t* kp = p.keep + (int64_t)row * p.ldm + p.i1 + col;
+          const uint32_t mb = (mbits >> (4 * t)) & 0xfu;
+          const uint32_t bytes = ((mb & 1u) ? 0u : 1u) | ((mb & 2u) ? 0u : 0x100u) | ((mb & 4u) ? 0u : 0x10000u) | ((mb & 8u) ? 0u : 0x1000000u);
+          if (vec_ok) *reinterpret_cast<uint32_t*>(kp) = bytes;
+          else { kp[0] = bytes & 1u; kp[1] = (bytes >> 8) & 1u; kp[2] = (bytes >> 16) & 1u; kp[3] = (bytes >> 24) & 1u; }
+        }
+      }
+    }
+  }
+}
+
+// resident CTAs of the fused kernel on this device (0: cooperative launch not available)
+static int obs_fused_capacity() {
+  static int cap = -1;
+  if (cap >= 0) return cap;
+  const size_t smem = (size_t)kOB * kOB * sizeof(float) + kObsBins * sizeof(unsigned int);
+  int dev = 0, coop = 0, per_sm = 0;
+  cap = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return cap; }
+  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) { cudaGetLastError(); return cap; }
+  if (cudaFuncSetAttribute(obs_block_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return cap; }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, obs_block_fused_kernel, kSw4Threads, smem) != cudaSuccess) { cudaGetLastError(); return cap; }
+  cap = per_sm * kNumSMs;
+  return cap;
+}
+
+// VLMC_OBS_FUSED=0 keeps the three histogram launches + obs_sweep4_kernel (A/B runs, tests)
+static bool obs_fused_enabled(int R) {
+  const char* e = getenv("VLMC_OBS_FUSED");
+  if (e && e[0] == '0') return false;
+  const int ctas = (R + kSw4RowsPerCta - 1) / kSw4RowsPerCta;
+  return ctas <= obs_fused_capacity();
+}
+
+static int launch_fused(const ObsParams& p, int dtype, int vec_ok, cudaStream_t st) {
+  const size_t smem = (size_t)kOB * kOB * sizeof(float) + kObsBins * sizeof(unsigned int);
+  const int grid = (p.R + kSw4RowsPerCta - 1) / kSw4RowsPerCta;
+  ObsParams pp = p;
+  void* args[] = {&pp, &dtype, &vec_ok};
+  if (cudaLaunchCooperativeKernel((const void*)obs_block_fused_kernel, dim3(grid), dim3(kSw4Threads), args, smem, st) != cudaSuccess)
+    return check_launch();
+  return check_launch();
+}
+
 template <int M>
 static int launch_sweep4(const ObsParams& p, int dtype, int vec_ok, cudaStream_t st) {
   auto kern = obs_sweep4_kernel<M>;
@@ -494,7 +680,7 @@ namespace vlmc {
 static int obs_block_finish_impl(void* W, int dtype, int R, int C, int64_t ldw, const float* U, int64_t ldu, int blk,
                                  int64_t rows_total, double sparsity, int prune_n, int prune_m, uint8_t* keep_mask,
                                  int64_t ldm, unsigned int* hist, void* ws, size_t ws_bytes, void* stream, const int* fail,
-                                 ChainSide* side = nullptr, bool* pending_far = nullptr) {
+                                 ChainSide* side = nullptr, bool* pending_far = nullptr, bool fused = false) {
   int rc = obs_checks(W, dtype, R, C, ldw, U, ldu, sparsity, prune_n, prune_m, kOB, keep_mask, ldm, ws, ws_bytes);
   if (rc) return rc;
   if (blk < 0 || blk * kOB >= C || rows_total < R) return VLMC_ERR_BAD_ARG;
@@ -507,7 +693,7 @@ static int obs_block_finish_impl(void* W, int dtype, int R, int C, int64_t ldw, 
   const int vec_ok = ((ldw * esz) % (4 * esz) == 0) && (((uintptr_t)W) % (4 * esz) == 0) &&
                      (!keep_mask || ((ldm % 4 == 0) && (((uintptr_t)keep_mask) % 4 == 0)));
   switch (prune_n == 0 ? 0 : prune_m) {
-    case 0: rc = launch_sweep4<0>(p, dtype, vec_ok, st); break;
+    case 0: rc = fused ? launch_fused(p, dtype, vec_ok, st) : launch_sweep4<0>(p, dtype, vec_ok, st); break;
     case 2: rc = launch_sweep4<2>(p, dtype, vec_ok, st); break;
     case 4: rc = launch_sweep4<4>(p, dtype, vec_ok, st); break;
     case 8: rc = launch_sweep4<8>(p, dtype, vec_ok, st); break;
@@ -589,14 +775,19 @@ static int obs_sweep_impl(void* W, int dtype, int R, int C, int64_t ldw, const f
   // look-ahead: callers that enqueue several chains concurrently turn it off)
   ChainSide* side = (chain_lookahead_enabled() && nblk > 2 * obs_superblock()) ? chain_side_for(st, 1) : nullptr;
   bool pending_far = false;
+  // Histogram passes + sweep of a block in one cooperative launch - for a chain that has the GPU to itself (the same switch
+  // as the look-ahead: vlmc.schedule turns it off while it enqueues several chains).  A cooperative grid starts only when ALL
+  // its CTAs fit at once, so next to other chains' kernels it waits for a drained GPU: measured on B200, 4096^2 sweep alone
+  // 2.50 -> 2.18 ms, 4096 x 11008 8.02 -> 7.84 ms, the 7 sweeps of a block on concurrent streams 17.4 -> 17.9 ms.
+  const bool fused = prune_n == 0 && chain_lookahead_enabled() && obs_fused_enabled(R);
   for (int blk = 0; blk < nblk; ++blk) {
-    if (prune_n == 0)
+    if (prune_n == 0 && !fused)
       for (int pass = 0; pass < 3; ++pass) {
         rc = vlmc_obs_block_hist(R, C, U, ldu, blk, pass, R, sparsity, nullptr, ws, ws_bytes, stream);
         if (rc) return rc;
       }
     rc = obs_block_finish_impl(W, dtype, R, C, ldw, U, ldu, blk, R, sparsity, prune_n, prune_m, keep_mask, ldm,
-                               nullptr, ws, ws_bytes, stream, fail, side, &pending_far);
+                               nullptr, ws, ws_bytes, stream, fail, side, &pending_far, fused);
     if (rc) return rc;
   }
   if (pending_far && cudaStreamWaitEvent(st, side->updated, 0) != cudaSuccess) return check_launch();
