@@ -848,6 +848,7 @@ struct DsApplyParams {
   int prune_n, prune_m, initial_magnitude, max_cycle, ref_fixup, zero_w;
   const uint32_t* row_v; const int* row_iv; const int* row_stop; const int* walk; const int* ncycles;
   uint8_t* mask; int64_t ldm;
+  const float* sq;        // sqrt(scaler_row), written by the walk entry point into the shared workspace
 };
 
 template <typename T>
@@ -871,12 +872,24 @@ dsnot_apply_kernel(const DsApplyParams p) {
       for (int col = tid * V; col < C; col += nthreads * V) {
         float f[V];
         Elem<T>::unpack(ld_stream(wrow + col), f);
+        uint32_t pb[V / 4] = {};
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-          const float aw = fabsf(f[e]);
-          const uint32_t key = __float_as_uint(p.initial_magnitude ? aw : __fmul_rn(aw, __fsqrt_rn(p.scaler_row[col + e])));
-          pm[col + e] = (key < v || (key == v && (col + e) <= iv)) ? 1 : 0;
+        for (int q = 0; q < V / 4; ++q) {
+          float sv[4] = {1.f, 1.f, 1.f, 1.f};
+          if (!p.initial_magnitude) {
+            const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.sq + col) + q);
+            sv[0] = s4.x; sv[1] = s4.y; sv[2] = s4.z; sv[3] = s4.w;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float aw = fabsf(f[4 * q + e]);
+            const uint32_t key = __float_as_uint(p.initial_magnitude ? aw : __fmul_rn(aw, sv[e]));
+            const bool pr = key < v || (key == v && (col + 4 * q + e) <= iv);
+            pb[q] |= (pr ? 1u : 0u) << (8 * e);
+          }
         }
+        if (V == 8) *reinterpret_cast<uint2*>(pm + col) = make_uint2(pb[0], pb[V / 4 - 1]);
+        else *reinterpret_cast<uint32_t*>(pm + col) = pb[0];
       }
     } else {
       const int m = p.prune_m;
@@ -909,25 +922,23 @@ dsnot_apply_kernel(const DsApplyParams p) {
     __syncthreads();
     uint8_t* mrow = p.mask + (int64_t)row * p.ldm;
     for (int col = tid * V; col < C; col += nthreads * V) {
-      uint32_t mb[V / 4] = {};
-      bool any = false;
-#pragma unroll
-      for (int e = 0; e < V; ++e) {
-        const bool pr = pm[col + e] != 0;
-        any |= pr;
-        mb[e / 4] |= (pr ? 0u : 1u) << (8 * (e % 4));
-      }
-      if (V == 8) st_stream8(mrow + col, make_uint2(mb[0], mb[V / 4 - 1]));
-      else st_stream4(mrow + col, mb[0]);
-      if (p.zero_w && any) {
+      // pm bytes are 0 / 1: the mask bytes are their complement; x * 0xff turns them into the byte masks of the weights
+      uint32_t pb[2];
+      if (V == 8) { const uint2 t = *reinterpret_cast<const uint2*>(pm + col); pb[0] = t.x; pb[1] = t.y; }
+      else { pb[0] = *reinterpret_cast<const uint32_t*>(pm + col); pb[1] = 0; }
+      if (V == 8) st_stream8(mrow + col, make_uint2(pb[0] ^ 0x01010101u, pb[1] ^ 0x01010101u));
+      else st_stream4(mrow + col, pb[0] ^ 0x01010101u);
+      if (p.zero_w && (pb[0] | pb[1])) {
         uint4 wv = *reinterpret_cast<const uint4*>(wrow + col);
         uint32_t* wr = reinterpret_cast<uint32_t*>(&wv);
         if (sizeof(T) == 4) {
-#pragma unroll
-          for (int e = 0; e < V; ++e) if (pm[col + e]) wr[e] = 0u;
+          const uint32_t x = pb[0] * 0xffu;
+          wr[0] &= ~__byte_perm(x, 0u, 0x0000); wr[1] &= ~__byte_perm(x, 0u, 0x1111);
+          wr[2] &= ~__byte_perm(x, 0u, 0x2222); wr[3] &= ~__byte_perm(x, 0u, 0x3333);
         } else {
-#pragma unroll
-          for (int e = 0; e < V; ++e) if (pm[col + e]) wr[e / 2] &= (e & 1) ? 0x0000ffffu : 0xffff0000u;
+          const uint32_t x0 = pb[0] * 0xffu, x1 = pb[1] * 0xffu;
+          wr[0] &= ~__byte_perm(x0, 0u, 0x1100); wr[1] &= ~__byte_perm(x0, 0u, 0x3322);
+          wr[2] &= ~__byte_perm(x1, 0u, 0x1100); wr[3] &= ~__byte_perm(x1, 0u, 0x3322);
         }
         st_stream(wrow + col, wv);
       }
@@ -1018,9 +1029,9 @@ extern "C" int vlmc_dsnot_refine_walk(const void* W, int dtype, int R, int C, in
   const bool fast = !(v1e && v1e[0] == '1') && prune_n == 0 && !initial_magnitude && k > 0 && C < 32768 &&
                     C >= 2 * max_cycle_time && C - k >= 2 * max_cycle_time && ((uintptr_t)sum_metric_row & 15) == 0;
   p.sq = s.sq;
+  ds_sqrt_kernel<<<(C + 255) / 256, 256, 0, st>>>(scaler_row, s.sq, C);      // also read by vlmc_dsnot_refine_apply
   if (fast) {
     if (cudaMemsetAsync(s.fb_count, 0, sizeof(int), st) != cudaSuccess) return check_launch();
-    ds_sqrt_kernel<<<(C + 255) / 256, 256, 0, st>>>(scaler_row, s.sq, C);
 #define VLMC_DS_WALK2(TT) { rc = ds_grid(dsnot_walk2_kernel<TT>, smem, R, &grid); if (rc) return rc; \
                             dsnot_walk2_kernel<TT><<<grid, kDsThreads, smem, st>>>(p); }
     switch (dtype) {
@@ -1061,7 +1072,7 @@ extern "C" int vlmc_dsnot_refine_apply(void* W, int dtype, int R, int C, int64_t
   p.W = W; p.ldw = ldw; p.R = R; p.C = C; p.scaler_row = scaler_row; p.prune_n = prune_n; p.prune_m = prune_m;
   p.initial_magnitude = initial_magnitude; p.max_cycle = max_cycle_time; p.ref_fixup = ref_fixup; p.zero_w = zero_w;
   p.row_v = s.row_v; p.row_iv = s.row_iv; p.row_stop = s.row_stop; p.walk = s.walk; p.ncycles = ncycles;
-  p.mask = keep_mask; p.ldm = ldm;
+  p.mask = keep_mask; p.ldm = ldm; p.sq = s.sq;
   const size_t smem = align_up((size_t)C, 16);
   int grid = 1;
 #define VLMC_DS_APPLY(TT) { rc = ds_grid(dsnot_apply_kernel<TT>, smem, R, &grid); if (rc) return rc; \
