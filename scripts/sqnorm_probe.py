@@ -1,0 +1,34 @@
+"""vlmc_sqnorm_accum at the bench shapes with the block-cyclic row order on / off.  python scripts/sqnorm_probe.py"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "vlm-compression_b200"))
+import torch
+from vlmc import native
+native.load()
+dev = "cuda"
+T = 128 * 2048
+for C in (4096, 11008):
+    x = torch.empty(128, 2048, C, device=dev, dtype=torch.float16)
+    for j in range(128):
+        x[j] = torch.randn(2048, C, device=dev).half()
+    x2 = torch.empty_like(x); x2.copy_(x)          # two buffers alternate: 2 x 2.1 GB >> L2
+    ref = None
+    for cyc in ("0", "1", "0", "1"):
+        os.environ["VLMC_STATS_CYCLIC"] = cyc
+        s = torch.zeros(C, device=dev)
+        native.sqnorm_accum(x, s, 0, 128)
+        if ref is None:
+            ref = s.clone()
+        err = float(((s - ref).abs() / ref.abs()).max())
+        for _ in range(2):
+            native.sqnorm_accum(x2, s, 128, 128)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(10):
+            native.sqnorm_accum(x if i % 2 == 0 else x2, s, 128, 128)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        print(f"C={C} cyclic={cyc}: {ms * 1e3:8.1f} us  {T * C * 2 / ms / 1e6:7.1f} GB/s  max rel diff vs contiguous {err:.1e}", flush=True)
+    del x, x2
