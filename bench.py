@@ -248,10 +248,14 @@ def step_wanda(ctx, weights, inputs, method, shared=False):
     # alternate between two streams so that the ramp-up of one launch covers the drain + finalize of the previous one
     # (each stream has its own scratch).  Per-span events (eager pass only) need the launches on one stream.
     nstreams = 1 if ctx.events is not None else 2
-    batch_stats = ctx.world > 1 or os.environ.get("VLMC_BENCH_STATS_BATCH") == "1"
+    # ONE multi-tensor launch for the statistics of the block (vlmc_sqnorm_accum_batch): one ramp-up and one drain instead of
+    # seven.  Several GPUs: a rank's share of a linear is a 40-100 us launch.  One GPU (r02): 2.92 -> 2.68-2.71 ms per block
+    # (18.66 GB in 2.55 ms = 7.3 TB/s; a 0.33 ms launch at C = 4096 loses ~6 % to its own ramp and drain, A/B on one box).
+    # VLMC_BENCH_STATS_BATCH=0 restores one launch per linear on two alternating streams; the calibration-batch sweep
+    # (calib_batch < 128: several add_batch calls per linear) always uses per-linear launches.
+    batch_stats = ctx.world > 1 or (ctx.calib_batch >= N_SEQ and os.environ.get("VLMC_BENCH_STATS_BATCH") != "0")
     if batch_stats:
-        # several GPUs: a rank's share of a linear is a 40-100 us launch; ONE multi-tensor launch for the block has one
-        # ramp-up and one drain (vlmc_sqnorm_accum_batch).  Partial sums carry the divisor of the whole set (0, N_SEQ).
+        # Partial sums carry the divisor of the whole set (0, N_SEQ) on several GPUs.
         xs, ss = [], []
         for leader, members in groups:
             _, C, inp = shape[leader]
@@ -558,7 +562,8 @@ def roofline_of(res, pk):
     total = res["eager_ms_per_step"] * res["steps"]      # spans were timed in the eager pass
     tag, k = max(res["kernels"].items(), key=lambda kv: kv[1]["ms"])
     info = {
-        "sqnorm_accum": ("hbm", "colstats_kernel<half,0> (vlmc_sqnorm_accum): T*C*2 B per launch"),
+        "sqnorm_accum": ("hbm", "colstats_batch_kernel<half,0> (vlmc_sqnorm_accum_batch: the block's statistics in one launch) / "
+                                "colstats_kernel<half,0> (vlmc_sqnorm_accum): T*C*2 B per tensor"),
         "dsnot_stats": ("hbm", "colstats_kernel<half,1> (vlmc_dsnot_stats): T*C*2 B per launch"),
         "wanda_select": ("hbm", "nm_batch_kernel (all linears of the block in one launch) / rowselect_cta_kernel: 5 B per weight"),
         "dsnot_refine": ("hbm", "dsnot_walk2_kernel + dsnot_apply_kernel: 7 B per weight (latency / issue-bound, see DESIGN.md)"),
@@ -684,6 +689,10 @@ def run_gpu(args):
                        "eager_ms_per_step": main["eager_ms_per_step"], "eager_step_ms": main["eager_step_ms"],
                        "graph_ms_per_step": main.get("graph_ms_per_step"), "weight_sets": main["weight_sets"],
                        "l2": "inputs larger than L2 (12.2 GB of activations per step, fresh weight set per step)",
+                       "statistics_launch": ("one launch per linear, two alternating streams"
+                                             if (os.environ.get("VLMC_BENCH_STATS_BATCH") == "0" and world == 1) or args.calib_batch < N_SEQ
+                                             else "one multi-tensor launch per block (vlmc_sqnorm_accum_batch)")
+                       if args.method.startswith("wanda") else "one launch per linear",
                        "parallelism": ("tokens/%d + allreduce, rows/%d + allgather" % (world, world)) if world > 1 else "1 GPU"},
             "gpu_launches": main["launches"],
             "clocks": main["clocks"],
