@@ -18,8 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def tag_of(kernel):
     k = kernel
-    if "colstats_kernel" in k:
-        m = re.search(r"colstats_kernel<[^,]+,\s*\(?(?:bool\))?\s*(\w+)", k)
+    if "colstats_kernel" in k or "colstats_batch_kernel" in k:
+        m = re.search(r"colstats_(?:batch_)?kernel<[^,]+,\s*\(?(?:bool\))?\s*(\w+)", k)
         d = m.group(1) if m else "0"
         return "dsnot_stats" if d in ("1", "true") else "sqnorm_accum"
     if "hessian_syrk" in k:

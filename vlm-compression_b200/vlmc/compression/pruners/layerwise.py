@@ -300,6 +300,9 @@ def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_s
 
     share = InputSharing() if getattr(pruner, "share_inputs", True) else None
     current = {"calls": 1}
+    # wrappers that can take the statistics of a whole block forward in one launch (WrappedGPT.add_batch_many): their hooks
+    # only record (wrapper, input); the launch is issued when the forward returns
+    deferred = [] if getattr(pruner, "batch_statistics", False) else None
 
     def run_block(layer):
         for j in range(n_samples):
@@ -315,6 +318,13 @@ def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_s
                     kw = dict(caches[j])
                     out = layer(inps[j], *kw.pop("__args__", ()), **kw)
                     outs[j] = out if vit else out[0]
+            if deferred:
+                for w, x, ver in deferred:
+                    if x._version != ver:        # the model wrote into a linear's input after the linear ran
+                        raise RuntimeError("an activation was modified in place between its linear and the end of the block "
+                                           "forward: run this model with batch_statistics=False")
+                type(deferred[0][0]).add_batch_many([(w, x.data) for w, x, _ in deferred])
+                del deferred[:]
 
     for i in range(len(layers)):
         layer = layers[i]
@@ -332,7 +342,10 @@ def prune_blocks(pruner, model, dataloader, model_prefix, module_to_process, n_s
                     # DSnoT's var is a mean of PER-CALL variances: its wrapper splits a stacked chunk back into the
                     # reference's calls (vlmc_dsnot_stats nseg); the other wrappers take any batch size
                     wrapped[nm]._stacked_calls = current["calls"]
-                    wrapped[nm].add_batch(inp[0].data, out.data)
+                    if deferred is not None and hasattr(wrapped[nm], "add_batch_many"):
+                        deferred.append((wrapped[nm], inp[0], inp[0]._version))
+                    else:
+                        wrapped[nm].add_batch(inp[0].data, out.data)
             return hook
         handles = [subset[name].register_forward_hook(make_hook(name)) for name in wrapped]
         run_block(layer)

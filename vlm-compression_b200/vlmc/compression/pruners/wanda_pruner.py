@@ -39,6 +39,23 @@ class WrappedGPT:
         native.sqnorm_accum(inp, self.scaler_row, self.nsamples, b)
         self.nsamples += b
 
+    @staticmethod
+    def add_batch_many(pairs):
+        """[(wrapper, inp)] of one block forward -> ONE multi-tensor launch per run of equal (nsamples, b) (in practice:
+        one per block forward; vlmc_sqnorm_accum_batch).  Same update as add_batch on each pair."""
+        groups = {}
+        for w, inp in pairs:
+            if len(inp.shape) == 2:
+                inp = inp.unsqueeze(0)
+            groups.setdefault((w.nsamples, inp.shape[0], inp.device), []).append((w, inp))
+        for (n, b, _), items in groups.items():
+            if len(items) == 1:
+                items[0][0].add_batch(items[0][1])
+                continue
+            native.sqnorm_accum_batch([x for _, x in items], [w.scaler_row for w, _ in items], n, b)
+            for w, _ in items:
+                w.nsamples += b
+
 
 def wanda_prune_block_nm(modules, scaler_rows, prune_n, prune_m, lora_model=False):
     """n:m score + select + apply for ALL linears of one block in one launch per dtype (vlmc_wanda_nm_batch); the
@@ -117,7 +134,7 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
                  num_data_first_stage=128, num_noise=1, sparsity_dict=None, noise_eps=1e-3,
                  prune_per_model=False, peft_postfix="", prune_n=0, prune_m=0, share_inputs=True,
                  qformer_prune_spec=None, qformer_model_prefix="Qformer", calib_batch=16, data_parallel=False,
-                 **kwargs):
+                 batch_statistics=True, **kwargs):
         super().__init__(model=model, data_loader=data_loader, prune_spec=None, is_strct_pruning=is_strct_pruning,
                          importance_scores_cache=importance_scores_cache,
                          keep_indices_or_masks_cache=keep_indices_or_masks_cache, is_global=is_global,
@@ -146,6 +163,10 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
         # linear gets ONE add_batch per chunk (layerwise.stack_calibration); 1 = one sample per forward like the
         # reference (wanda_pruner.py:308-311).  Statistics agree to rounding (tests: 1e-5), masks on tie-free data.
         self.calib_batch = calib_batch
+        # the Wanda statistics of the linears a block forward reaches are accumulated by ONE multi-tensor launch after the
+        # forward (vlmc_sqnorm_accum_batch) instead of one launch per hook; False: one launch per hook.  Statistics agree
+        # to rounding (the partial sums are chunked differently), like calib_batch.
+        self.batch_statistics = batch_statistics
         # True (and torch.distributed initialised with > 1 rank): the ranks split the calibration samples, merge the
         # statistics with one all-reduce per block and end up with identical pruned replicas.  False: every
         # rank prunes its replica on its own, like the reference's torchrun launch does.
