@@ -331,8 +331,20 @@ def step_dsnot(ctx, weights, inputs, elide=False):
     stats = {}
     # one stream: two concurrent DSnoT statistics kernels (256-byte row segments, multi-wave grids) ran 50 % SLOWER than
     # one after the other (measured), unlike the Wanda statistics in step_wanda
+    if os.environ.get("VLMC_BENCH_STATS_BATCH") != "0":
+        # ONE launch for the 7 wrappers (vlmc_dsnot_stats_batch, r02): per item the plan and the results of vlmc_dsnot_stats;
+        # the grid walks the calls with the linears interleaved, so q / k / v (gate / up) read a call's activations at
+        # the same time and the repeats hit in L2
+        xs = []
+        for name, R, C, inp in LINEARS:
+            stats[name] = [torch.zeros(C, device=ctx.dev) for _ in range(4)]   # scaler_row, sum_metric_row, mean, var
+            xs.append(inputs[inp])
+        n_local = xs[0].shape[0]
+        ctx.timed("dsnot_stats", sum(x.numel() * 2 for x in xs), lambda: native.dsnot_stats_batch(
+            xs, [stats[name] for name, *_ in LINEARS], 0, 1, 0, nseg=n_local))
+        ctx.launches += 1
     with schedule_fork(ctx, 1) as fk:
-        for li, (name, R, C, inp) in enumerate(LINEARS):
+        for li, (name, R, C, inp) in enumerate(LINEARS if not stats else []):
             st = [torch.zeros(C, device=ctx.dev) for _ in range(4)]       # scaler_row, sum_metric_row, mean, var
             x = inputs[inp]
             n_local = x.shape[0]
@@ -564,7 +576,8 @@ def roofline_of(res, pk):
     info = {
         "sqnorm_accum": ("hbm", "colstats_batch_kernel<half,0> (vlmc_sqnorm_accum_batch: the block's statistics in one launch) / "
                                 "colstats_kernel<half,0> (vlmc_sqnorm_accum): T*C*2 B per tensor"),
-        "dsnot_stats": ("hbm", "colstats_kernel<half,1> (vlmc_dsnot_stats): T*C*2 B per launch"),
+        "dsnot_stats": ("hbm", "colstats_batch_kernel<half,1> (vlmc_dsnot_stats_batch: the block's 7 wrappers in one launch) / "
+                               "colstats_kernel<half,1> (vlmc_dsnot_stats): T*C*2 B per tensor"),
         "wanda_select": ("hbm", "nm_batch_kernel (all linears of the block in one launch) / rowselect_cta_kernel: 5 B per weight"),
         "dsnot_refine": ("hbm", "dsnot_walk2_kernel + dsnot_apply_kernel: 7 B per weight (latency / issue-bound, see DESIGN.md)"),
         "hessian_accum": ("tensor", "hessian_syrk_kernel (vlmc_hessian_accum): 2*T*C^2 logical flop per call (SYRK executes half)"),

@@ -107,6 +107,19 @@ int vlmc_dsnot_stats(const void* x, int dtype, int64_t nseg, int64_t S, int C, i
                      void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * K2 for several linears in ONE launch (the 7 wrappers of a transformer block): the same plan, partial sums and results as
+ * vlmc_dsnot_stats per item.  The grid is ordered so that linears fed the same activations (q / k / v, gate / up) work on the
+ * same call at the same time: the repeated reads hit in L2.  count <= 16, one dtype per launch.
+ */
+typedef struct vlmc_dsnot_stats_item {
+  const void* x; int64_t nseg; int64_t S; int C; int64_t ldx;
+  float* scaler_row; float* sum_row; float* mean; float* var;
+  double n_before; double b_per_seg; double ntok_before;
+} vlmc_dsnot_stats_item;
+size_t vlmc_dsnot_stats_batch_workspace_bytes(const vlmc_dsnot_stats_item* items, int count, int dtype);
+int vlmc_dsnot_stats_batch(const vlmc_dsnot_stats_item* items, int count, int dtype, void* ws, size_t ws_bytes, void* stream);
+
+/*
  * K4+K5  Wanda score + per-row unstructured selection.  Replaces wanda_pruner.py:318-341
  * (LLM path): S = |W| * sqrt(scaler_row) in fp32; in every row the k smallest scores are
  * pruned, ties going to the LOWER column (torch.sort(stable=True), :332).  k = int(C * p)

@@ -973,6 +973,50 @@ def test_wanda_and_dsnot_against_the_live_reference_on_this_gpu(native, method):
 
 
 # ------------------------------------------------------------------------------------------- K8 + K9 DSnoT refine
+def test_dsnot_stats_batch_equals_per_linear_launches(native):
+    """vlmc_dsnot_stats_batch (one launch for the wrappers of a block, linears interleaved per call) against one
+    vlmc_dsnot_stats launch per wrapper: same plan per item -> identical state, bit for bit; second call continues the
+    running means."""
+    nseg, S = 6, 384
+    shapes = [512, 512, 512, 1408, 1408]                     # q / k / v share one input, the last two another
+    xa, xb = acts(nseg * S, 512, 3, torch.float16).cuda().view(nseg, S, 512), acts(nseg * S, 1408, 4, torch.float16).cuda().view(nseg, S, 1408)
+    xs = [xa, xa, xa, xb, xb]
+    one = [[torch.zeros(C, device="cuda") for _ in range(4)] for C in shapes]
+    many = [[torch.zeros(C, device="cuda") for _ in range(4)] for C in shapes]
+    ntok = 0
+    for rep in range(2):
+        for x, st in zip(xs, one):
+            native.dsnot_stats(x, st[0], st[1], st[2], st[3], rep * nseg, 1, ntok, nseg=nseg)
+        native.dsnot_stats_batch(xs, many, rep * nseg, 1, ntok, nseg=nseg)
+        ntok += nseg * S
+    torch.cuda.synchronize()
+    for a, b in zip(one, many):
+        for t, u in zip(a, b):
+            assert torch.equal(t, u)
+
+
+def test_driver_batch_statistics_match_per_hook_launches(native):
+    """Drop-in driver: the statistics of a block forward in one launch (batch_statistics) against one launch per hook -
+    Wanda (statistics to rounding: the partial sums are chunked differently, masks equal on this tie-free data) and
+    DSnoT (bit-identical state, identical masks and weights)."""
+    import toy_model
+    import vlmc.compression as comp
+    for name in ("blipt5_wanda_pruner", "blipt5_dsnot_pruner"):
+        out = {}
+        for batch in (False, True):
+            torch.manual_seed(0)
+            model = toy_model.ToyBlip(d_llm=296, ff=488, n_llm=2, n_vit=0).eval().cuda()
+            pruner = comp.load_pruner(name, model, toy_model.toy_batches(6, device="cuda"),
+                                      cfg=toy_model.pruner_cfg(0.4, 1.0, batch_statistics=batch, calib_batch=2))
+            model, _ = pruner.prune()
+            out[batch] = ({k: v.detach().clone() for k, v in model.state_dict().items()},
+                          {n: m.mask.clone() for n, m in model.named_modules() if hasattr(m, "mask") and torch.is_tensor(m.mask)})
+        for k in out[False][1]:
+            assert torch.equal(out[False][1][k], out[True][1][k]), (name, k)
+        for k in out[False][0]:
+            assert torch.equal(out[False][0][k], out[True][0][k]), (name, k)
+
+
 def _dsnot_stats(C, seed, positive=False):
     g = torch.Generator().manual_seed(seed)
     scal = (torch.exp(torch.rand(C, generator=g) * 4 - 2) * 50).float()

@@ -270,9 +270,13 @@ struct StatsBatch { StatsParams it[kStatsBatchMax]; int coltiles[kStatsBatchMax]
 template <typename T, bool DSNOT, int kCX>
 __global__ void __launch_bounds__(kStatsThreads, StatsOcc<DSNOT>::kBlocksPerSM)
 colstats_batch_kernel(const __grid_constant__ StatsBatch b) {
-  const int item = blockIdx.z;
-  if ((int)blockIdx.x >= b.coltiles[item] || (int)blockIdx.y >= b.nchunks[item]) return;
-  colstats_body<T, DSNOT, kCX>(b.it[item], blockIdx.x, blockIdx.y);
+  // Wanda: one resident wave, grid (column tiles, chunks, items).  DSnoT: a multi-wave grid (one chunk per call and column
+  // tile), grid (column tiles, ITEMS, chunks): CTAs are dispatched x-fastest, so the linears that read the same
+  // activations (q / k / v, gate / up) work on the same call at the same time and the repeats hit in L2.
+  const int item = DSNOT ? blockIdx.y : blockIdx.z;
+  const int chunk = DSNOT ? blockIdx.z : blockIdx.y;
+  if ((int)blockIdx.x >= b.coltiles[item] || chunk >= b.nchunks[item]) return;
+  colstats_body<T, DSNOT, kCX>(b.it[item], blockIdx.x, chunk);
 }
 
 struct StatsPlan {
@@ -412,6 +416,58 @@ extern "C" int vlmc_sqnorm_accum_batch(const vlmc_stats_item* items, int count, 
   dim3 grid(max_ct, max_ch, count);
   cudaStream_t st = (cudaStream_t)stream;
   VLMC_DISPATCH_DTYPE(dtype, (colstats_batch_kernel<scalar_t, false, StatsTile<false>::kCX><<<grid, kStatsThreads, 0, st>>>(b)));
+  return check_launch();
+}
+
+extern "C" size_t vlmc_dsnot_stats_batch_workspace_bytes(const vlmc_dsnot_stats_item* items, int count, int dtype) {
+  using namespace vlmc;
+  (void)dtype;
+  if (!items || count < 1 || count > kStatsBatchMax) return 0;
+  size_t total = 0;
+  for (int i = 0; i < count; ++i)
+    total += align_up(stats_workspace_bytes(1, items[i].nseg * items[i].S, items[i].C, items[i].nseg), 256);
+  return total;
+}
+
+extern "C" int vlmc_dsnot_stats_batch(const vlmc_dsnot_stats_item* items, int count, int dtype, void* ws, size_t ws_bytes,
+                                      void* stream) {
+  using namespace vlmc;
+  if (!items || !ws || count < 1 || count > kStatsBatchMax) return VLMC_ERR_BAD_ARG;
+  if (dtype != VLMC_F32 && dtype != VLMC_F16 && dtype != VLMC_BF16) return VLMC_ERR_BAD_ARG;
+  if (!is_device_ptr(ws)) return VLMC_ERR_NOT_DEVICE;
+  const int V = dtype == VLMC_F32 ? 4 : 8;
+  StatsBatch b;
+  char* base = reinterpret_cast<char*>(ws);
+  size_t used = 0;
+  int max_ct = 1, max_ch = 1;
+  for (int i = 0; i < count; ++i) {
+    const vlmc_dsnot_stats_item& s = items[i];
+    if (!s.x || !s.scaler_row || !s.sum_row || !s.mean || !s.var || s.nseg < 1 || s.S < 1 || s.C < 1 || s.ldx < s.C)
+      return VLMC_ERR_BAD_ARG;
+    if (s.C % V != 0 || s.ldx % V != 0 || ((uintptr_t)s.x & 15) != 0) return VLMC_ERR_UNSUPPORTED;
+    if (!is_device_ptr(s.x) || !is_device_ptr(s.scaler_row)) return VLMC_ERR_NOT_DEVICE;
+    // the plan of the single-tensor call: identical partial sums, identical results
+    StatsPlan pl = plan_stats(dtype, s.nseg, s.S, s.C, 3, StatsOcc<true>::kBlocksPerSM);
+    if (pl.coltiles * sizeof(unsigned int) > VLMC_WS_COUNTER_BYTES || pl.nchunks > 65535) return VLMC_ERR_UNSUPPORTED;
+    const size_t need = align_up(pl.bytes, 256);
+    if (used + need > ws_bytes) return VLMC_ERR_WORKSPACE;
+    StatsParams& p = b.it[i];
+    p.x = s.x; p.ldx = s.ldx; p.C = s.C; p.S = s.S; p.nseg = s.nseg;
+    p.chunks_per_seg = pl.chunks_per_seg; p.rows_per_chunk = pl.rows_per_chunk;
+    p.tickets = reinterpret_cast<unsigned int*>(base + used);
+    if (cudaMemsetAsync(base + used, 0, VLMC_WS_COUNTER_BYTES, (cudaStream_t)stream) != cudaSuccess) return check_launch();
+    p.part = reinterpret_cast<float*>(base + used + VLMC_WS_COUNTER_BYTES);
+    p.scaler_row = s.scaler_row; p.sum_row = s.sum_row; p.mean = s.mean; p.var = s.var;
+    p.n_before = s.n_before; p.b_per_seg = s.b_per_seg; p.ntok_before = s.ntok_before;
+    b.coltiles[i] = pl.coltiles;
+    b.nchunks[i] = (int)pl.nchunks;
+    max_ct = pl.coltiles > max_ct ? pl.coltiles : max_ct;
+    max_ch = (int)pl.nchunks > max_ch ? (int)pl.nchunks : max_ch;
+    used += need;
+  }
+  dim3 grid(max_ct, count, max_ch);
+  cudaStream_t st = (cudaStream_t)stream;
+  VLMC_DISPATCH_DTYPE(dtype, (colstats_batch_kernel<scalar_t, true, StatsTile<true>::kCX><<<grid, kStatsThreads, 0, st>>>(b)));
   return check_launch();
 }
 

@@ -53,6 +53,32 @@ class WrappedGPT:
         self.ntokens += ntok
         self.nsamples += b
 
+    @staticmethod
+    def add_batch_many(pairs):
+        """[(wrapper, inp)] of one block forward -> ONE launch per run of equal (nsamples, batch, calls) (in practice one per
+        block forward; vlmc_dsnot_stats_batch).  The same update as add_batch on each pair, bit for bit."""
+        groups = {}
+        for w, inp in pairs:
+            if len(inp.shape) == 2:
+                inp = inp.unsqueeze(0)
+            calls = int(getattr(w, "_stacked_calls", 1) or 1)
+            if not (calls > 1 and inp.shape[0] % calls == 0):
+                calls = 1
+            groups.setdefault((w.nsamples, inp.shape[0], calls, inp.device), []).append((w, inp))
+        for (n, b, calls, _), items in groups.items():
+            if len(items) == 1:
+                items[0][0].add_batch(items[0][1])
+                continue
+            for w, _ in items:
+                if w.mean.dim() == 1:
+                    w.mean = w.mean.reshape(-1, 1)
+                    w.var = w.var.reshape(-1, 1)
+            native.dsnot_stats_batch([x for _, x in items], [(w.scaler_row, w.sum_metric_row, w.mean, w.var) for w, _ in items],
+                                     n, b // calls, [w.ntokens for w, _ in items], nseg=calls)
+            for w, x in items:
+                w.ntokens += x.numel() // x.shape[-1]
+                w.nsamples += b
+
     def free(self):
         self.H = None          # dsnot_pruner.py:103-105 (its empty_cache() is left to the end of the block loop, see SparseGPT.free)
 

@@ -41,6 +41,8 @@ SIGNATURES = {
     "vlmc_sqnorm_accum": (_i, [_vp, _i, _i64, _i, _i64, _vp, _d, _d, _vp, _sz, _vp]),
     "vlmc_sqnorm_accum_batch_workspace_bytes": (_sz, [_vp, _i, _i]),
     "vlmc_sqnorm_accum_batch": (_i, [_vp, _i, _i, _vp, _sz, _vp]),
+    "vlmc_dsnot_stats_batch_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "vlmc_dsnot_stats_batch": (_i, [_vp, _i, _i, _vp, _sz, _vp]),
     "vlmc_dsnot_stats": (_i, [_vp, _i, _i64, _i64, _i, _i64, _vp, _vp, _vp, _vp, _d, _d, _d, _vp, _sz, _vp]),
     "vlmc_wanda_rowselect": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_wanda_nm": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
@@ -206,6 +208,41 @@ def sqnorm_accum_batch(xs, scaler_rows, n_before, b):
                 _check("vlmc_sqnorm_accum_batch", lib.vlmc_sqnorm_accum_batch(items, len(chunk), dt, ws.data_ptr(), ws.numel(),
                                                                               _stream(xs[chunk[0]])))
     return out
+
+
+class DsnotStatsItem(ctypes.Structure):
+    _fields_ = [("x", _vp), ("nseg", _i64), ("S", _i64), ("C", _i), ("ldx", _i64), ("scaler_row", _vp), ("sum_row", _vp),
+                ("mean", _vp), ("var", _vp), ("n_before", _d), ("b_per_seg", _d), ("ntok_before", _d)]
+
+
+def dsnot_stats_batch(xs, states, n_before, b_per_seg, ntok_before, nseg=1):
+    """K2 for several linears in ONE launch (vlmc_dsnot_stats_batch).  states[i] = (scaler_row, sum_row, mean, var); the
+    same n_before / b_per_seg / nseg for all (the linears of a block see the same calibration calls); ntok_before may be
+    a list (per item).  Same results as dsnot_stats per item, bit for bit."""
+    xs = [_rows2d(x) for x in xs]
+    _require_cuda(*xs, *[t for st in states for t in st])
+    lib = load()
+    if not isinstance(ntok_before, (list, tuple)):
+        ntok_before = [ntok_before] * len(xs)
+    by_dtype = {}
+    for i, x in enumerate(xs):
+        if x.shape[0] % nseg:
+            raise ValueError("rows must divide evenly into segments")
+        by_dtype.setdefault(_dtype(x), []).append(i)
+    for dt, idx in by_dtype.items():
+        for c0 in range(0, len(idx), 16):
+            chunk = idx[c0:c0 + 16]
+            items = (DsnotStatsItem * len(chunk))()
+            for j, i in enumerate(chunk):
+                x, st = xs[i], states[i]
+                items[j] = DsnotStatsItem(x.data_ptr(), int(nseg), x.shape[0] // nseg, x.shape[1], x.stride(0),
+                                          st[0].data_ptr(), st[1].data_ptr(), st[2].data_ptr(), st[3].data_ptr(),
+                                          float(n_before), float(b_per_seg), float(ntok_before[i]))
+            need = lib.vlmc_dsnot_stats_batch_workspace_bytes(items, len(chunk), dt)
+            ws = workspace(xs[chunk[0]], need)
+            with torch.cuda.device(xs[chunk[0]].device):
+                _check("vlmc_dsnot_stats_batch", lib.vlmc_dsnot_stats_batch(items, len(chunk), dt, ws.data_ptr(), ws.numel(),
+                                                                            _stream(xs[chunk[0]])))
 
 
 def dsnot_stats(x, scaler_row, sum_row, mean, var, n_before, b_per_seg, ntok_before, nseg=1):
