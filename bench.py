@@ -597,6 +597,14 @@ def roofline_of(res, pk):
            "unit": unit, "frac": achieved / peak if achieved else None, "traffic": ncu_traffic(tag, res), "spans": k["spans"],
            "avg_span_ms": k["ms"] / max(k["spans"], 1), "share_of_step": k["ms"] / total,
            "spans_ms_per_step": {t: v["ms"] / res["steps"] for t, v in res["kernels"].items()}}
+    if bound == "hbm" and out["traffic"] and k["spans"]:
+        alg = k["work"] / k["spans"]                     # algorithmic bytes per launch
+        out["traffic_over_algorithmic"] = out["traffic"] / alg
+        out["dram_achieved"] = out["traffic"] / (out["avg_span_ms"] * 1e-3) / 1e9       # GB/s that actually crossed the HBM interface
+        if out["traffic"] < 0.9 * alg:
+            out["note"] = ("the block's statistics are ONE launch: linears fed the same activations (q / k / v, gate / up) read "
+                           "them at the same time, so the repeats hit in L2 - DRAM traffic is below the algorithmic bytes and "
+                           "`achieved` (algorithmic bytes / time) can exceed the copy peak; `dram_achieved` = traffic / time")
     if tag == "hessian_accum":
         # the SYRK executes the upper 256 x 256 tiles only: executed flop next to the logical (full-square) figure
         ex = 0.0
