@@ -1,4 +1,4 @@
-"""vlmc_sqnorm_accum at the bench shapes with the block-cyclic row order on / off.  python scripts/sqnorm_probe.py"""
+"""vlmc_sqnorm_accum (single tensor) at the bench shapes for several VLMC_STATS_WAVES.  python scripts/sqnorm_probe.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "vlm-compression_b200"))
@@ -13,8 +13,8 @@ for C in (4096, 11008):
         x[j] = torch.randn(2048, C, device=dev).half()
     x2 = torch.empty_like(x); x2.copy_(x)          # two buffers alternate: 2 x 2.1 GB >> L2
     ref = None
-    for cyc in ("0", "1", "0", "1"):
-        os.environ["VLMC_STATS_CYCLIC"] = cyc
+    for waves in ("1", "4", "16", "32", "1", "32"):
+        os.environ["VLMC_STATS_WAVES"] = waves
         s = torch.zeros(C, device=dev)
         native.sqnorm_accum(x, s, 0, 128)
         if ref is None:
@@ -30,5 +30,5 @@ for C in (4096, 11008):
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 10
-        print(f"C={C} cyclic={cyc}: {ms * 1e3:8.1f} us  {T * C * 2 / ms / 1e6:7.1f} GB/s  max rel diff vs contiguous {err:.1e}", flush=True)
+        print(f"C={C} waves={waves}: {ms * 1e3:8.1f} us  {T * C * 2 / ms / 1e6:7.1f} GB/s  max rel diff vs one wave {err:.1e}", flush=True)
     del x, x2
