@@ -601,6 +601,15 @@ def roofline_of(res, pk):
         alg = k["work"] / k["spans"]                     # algorithmic bytes per launch
         out["traffic_over_algorithmic"] = out["traffic"] / alg
         out["dram_achieved"] = out["traffic"] / (out["avg_span_ms"] * 1e-3) / 1e9       # GB/s that actually crossed the HBM interface
+        if tag in ("sqnorm_accum", "dsnot_stats") and not res.get("shared") and res.get("n_gpus", 1) >= 1:
+            # SURVEY 8(d) asks to say which figure is used: `achieved` / `frac` count the activations once per LINEAR (the
+            # per-linear API, 18.66 GB per block at 1 GPU); the four DISTINCT input tensors are 12.21 GB
+            dims = {}
+            for _, _, C, inp in LINEARS:
+                dims[inp] = C
+            frac_distinct = sum(dims.values()) / float(sum(C for _, _, C, _ in LINEARS))
+            out["achieved_on_distinct_bytes"] = achieved * frac_distinct
+            out["frac_on_distinct_bytes"] = achieved * frac_distinct / peak
         if out["traffic"] < 0.9 * alg:
             out["note"] = ("the block's statistics are ONE launch: linears fed the same activations (q / k / v, gate / up) read "
                            "them at the same time, so the repeats hit in L2 - DRAM traffic is below the algorithmic bytes and "

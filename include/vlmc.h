@@ -223,6 +223,19 @@ int vlmc_sparselora_effective_weight(const void* W, int dtype, int R, int C, int
                                      int64_t ldm, int sparse, void* out, int64_t ldo, void* stream);
 
 /*
+ * K23  SparseLoRA masked training forward as one kernel (lora.py:359-382, F.linear(x, <the K15 weight expression>, bias)):
+ *   y[T, R] = x[T, C] . W_eff[R, C]^T (+ bias[R]),  W_eff as vlmc_sparselora_effective_weight defines it (same roundings,
+ * bit-identical operand), built on chip per 128 x 64 weight slice and fed to tcgen05 - no effective weight reaches HBM.
+ * x, W, bias, y share `dtype` (VLMC_F16 or VLMC_BF16; VLMC_F32 returns VLMC_ERR_UNSUPPORTED - the caller keeps K15 + a
+ * library GEMM there); fp32 accumulation, y rounded once to dtype (after the bias).  bias may be NULL.  rank <= 16;
+ * C, R, ldx, ldw, ldy multiples of 8, ldm a multiple of 16, 16-byte aligned bases (TMA).
+ */
+int vlmc_sparselora_linear_forward(const void* x, int dtype, int64_t T, int C, int64_t ldx, const void* W, int R,
+                                   int64_t ldw, const float* A, const float* B, int rank, float scaling,
+                                   const uint8_t* keep_mask, int64_t ldm, int sparse, const void* bias, void* y,
+                                   int64_t ldy, void* stream);
+
+/*
  * K16  LoRA gradients of that forward.  G [R, C] (W's dtype) is the gradient w.r.t. the effective weight
  * (dy^T x, a library GEMM).  The reference's autograd masks G (sparse only), scales it in W's dtype, casts to fp32 and
  * runs two rank-r GEMMs; here  E = float(round_dtype(G * mask * scaling)),  dB [R, rank] = E A^T,

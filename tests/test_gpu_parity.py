@@ -1729,6 +1729,98 @@ def test_lora_forward_vicuna_size_properties(native):
     assert float((dA - B.T @ E).abs().max()) <= 1e-4 * float(dA.abs().max())
 
 
+# ------------------------------------------------------------------------------------------- K23 (fused)
+def _ll_case(R, C, r, tag, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    W = (torch.randn(R, C, device="cuda", generator=g) * 0.05).to(DT[tag])
+    A = torch.randn(r, C, device="cuda", generator=g) * 0.1
+    B = torch.randn(R, r, device="cuda", generator=g) * 0.1
+    mask = torch.rand(R, C, device="cuda", generator=g) < 0.5
+    return W, A, B, mask
+
+
+@pytest.mark.parametrize("tag,r,sparse", [("bf16", 8, True), ("f16", 4, True), ("bf16", 16, False), ("f16", 8, False),
+                                          ("f16", 12, True), ("bf16", 1, True)])
+def test_lora_linear_fused_operand_is_k15_bit_exact(native, tag, r, sparse):
+    """x = identity: every output is ONE product 1.0 * W_eff[r, c] accumulated with zeros, so the fused kernel's output is
+    its on-chip operand: equal, bit for bit, to K15's effective weight (the oracle-pinned kernel).  Ragged R (3 feature
+    tiles, the last one partial) and C (partial last k-slice), several units per CTA chain."""
+    R, C = 328, 528                       # the mask's row pitch must be a multiple of 16 bytes (TMA)
+    W, A, B, mask = _ll_case(R, C, r, tag, 7 + r)
+    x = torch.eye(C, device="cuda", dtype=DT[tag])
+    W0 = W.clone()
+    y = native.sparselora_linear_forward(x, W, A, B, 1.75, mask, sparse)
+    weff = native.sparselora_effective_weight(W, A, B, 1.75, mask, sparse)
+    assert torch.equal(W, W0)
+    assert y.shape == (C, R) and torch.equal(y, weff.t())
+    assert float(weff.float().abs().max()) > 0
+
+
+@pytest.mark.parametrize("tag", ["bf16", "f16"])
+@pytest.mark.parametrize("T,R,C,r", [(1, 8, 16, 2), (100, 136, 208, 8), (513, 264, 1024, 8), (1300, 1408, 1408, 16),
+                                     (640, 4096, 4096, 8)])
+def test_lora_linear_fused_vs_fp64(native, tag, T, R, C, r):
+    """y against the fp64 product of the same operands (x, K15's W_eff, bias): output rounding of the dtype + an fp32
+    accumulation bound proportional to sum |x| |w| (2e-5: tensor-core accumulation truncates); and against the library
+    GEMM on the same operands to 2 ulp of the dtype.  Token counts that leave 1-3 of the unit's four token tiles empty."""
+    W, A, B, mask = _ll_case(R, C, r, tag, T + R)
+    x = (torch.randn(T, C, device="cuda") * 0.5).to(DT[tag])
+    bias = (torch.randn(R, device="cuda") * 0.1).to(DT[tag])
+    ulp = {"bf16": 2.0 ** -8, "f16": 2.0 ** -11}[tag]
+    for sparse in (True, False):
+        for b in (None, bias):
+            y = native.sparselora_linear_forward(x, W, A, B, 2.0, mask, sparse, bias=b)
+            weff = native.sparselora_effective_weight(W, A, B, 2.0, mask, sparse)
+            ref = x.double() @ weff.double().t()
+            if b is not None:
+                ref = ref + b.double()
+            bound = ulp * ref.abs() + 2e-5 * (x.double().abs() @ weff.double().abs().t()) + 1e-7
+            assert bool(((y.double() - ref).abs() <= bound).all()), (sparse, b is not None, float(((y.double() - ref).abs() / bound).max()))
+            lib = torch.nn.functional.linear(x, weff, b)
+            assert float((y.float() - lib.float()).abs().max()) <= 2 * ulp * float(lib.float().abs().max())
+
+
+def test_lora_linear_fused_3d_input_and_rejections(native):
+    W, A, B, mask = _ll_case(256, 512, 8, "bf16", 3)
+    x = (torch.randn(3, 7, 512, device="cuda")).bfloat16()
+    y = native.sparselora_linear_forward(x, W, A, B, 2.0, mask, True)
+    assert y.shape == (3, 7, 256)
+    weff = native.sparselora_effective_weight(W, A, B, 2.0, mask, True)
+    assert float((y.float() - torch.nn.functional.linear(x, weff).float()).abs().max()) <= 2.0 ** -7 * float(y.float().abs().max())
+    assert native.sparselora_linear_forward(x[:, :0], W, A, B, 2.0, mask, True).shape == (3, 0, 256)          # no tokens
+    with pytest.raises(native.VlmcError):                                                                     # fp32 layers: K15 + GEMM
+        native.sparselora_linear_forward(x.float(), W.float(), A, B, 2.0, mask, True)
+    assert not native.sparselora_linear_forward_supported(x.float(), W.float(), mask, 8)
+    assert native.sparselora_linear_forward_supported(x, W, mask, 8)
+    Wr, Ar, Br, mr = _ll_case(64, 520, 8, "bf16", 4)                                                          # mask pitch 520: not TMA-able
+    assert not native.sparselora_linear_forward_supported(x[..., :520].contiguous(), Wr, mr, 8)
+    with pytest.raises(native.VlmcError):
+        native.sparselora_linear_forward(torch.zeros(4, 520, device="cuda").bfloat16(), Wr, Ar, Br, 2.0, mr, True)
+
+
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_lora_linear_module_fused_switch(native, fused, monkeypatch):
+    """vlmc.peft.lora.Linear with VLMC_LORA_FUSED=1 (K23) and =0 (K15 + library GEMM) give outputs within 2 ulp of each
+    other and the same gradients (the backward is shared)."""
+    from vlmc.peft.lora import Linear as LoraLinear
+    monkeypatch.setenv("VLMC_LORA_FUSED", fused)
+    torch.manual_seed(5)
+    R, C = 264, 336
+    lin = LoraLinear(C, R, r=8, lora_alpha=16, bias=True).cuda()
+    lin.weight.data = (torch.randn(R, C, device="cuda") * 0.05).bfloat16()
+    lin.bias.data = (torch.randn(R, device="cuda") * 0.1).bfloat16()
+    lin.lora_B.weight.data.normal_(0, 0.1)
+    lin.mask = torch.rand(R, C, device="cuda") < 0.5
+    lin.sparse = True
+    x = (torch.randn(5, 9, C, device="cuda") * 0.5).bfloat16().requires_grad_(True)
+    y = lin(x)
+    y.backward(torch.ones_like(y))
+    delta = (lin.lora_B.weight @ lin.lora_A.weight).bfloat16() * lin.scaling
+    want = torch.nn.functional.linear(x.detach(), (lin.weight + delta) * lin.mask, lin.bias)
+    assert float((y.float() - want.float()).abs().max()) <= 2e-2 * float(want.float().abs().max())
+    assert x.grad is not None and lin.lora_A.weight.grad is not None and lin.lora_B.weight.grad is not None
+
+
 # ------------------------------------------------------------------------------------------- K17 (SURVEY 8f-3)
 def test_count_nonzero_matches_the_reference_expression(native):
     """vlmc_count_nonzero_batch against evaluate_old.py:331-334, sum((param != 0).float().sum()): mixed dtypes, ragged

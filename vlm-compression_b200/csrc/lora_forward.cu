@@ -18,16 +18,6 @@ namespace vlmc {
 
 constexpr int kFwdThreads = 128;
 
-template <typename T> __device__ __forceinline__ float round_dt(float v);
-template <> __device__ __forceinline__ float round_dt<float>(float v) { return v; }
-template <> __device__ __forceinline__ float round_dt<__half>(float v) { return __half2float(__float2half_rn(v)); }
-template <> __device__ __forceinline__ float round_dt<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
-
-template <typename T> __device__ __forceinline__ float2 round_dt2(float2 v);
-template <> __device__ __forceinline__ float2 round_dt2<float>(float2 v) { return v; }
-template <> __device__ __forceinline__ float2 round_dt2<__half>(float2 v) { return __half22float2(__floats2half2_rn(v.x, v.y)); }
-template <> __device__ __forceinline__ float2 round_dt2<__nv_bfloat16>(float2 v) { return __bfloat1622float2(__floats2bfloat162_rn(v.x, v.y)); }
-
 // ---- K15 -------------------------------------------------------------------------------------------------
 // Same streaming tile loop as K14 (lora_tile.cuh): A staged in shared memory once per unit, four rows in flight per thread.
 template <typename T>
@@ -54,27 +44,7 @@ lora_effective_weight_kernel(const T* __restrict__ W, int64_t ldw, int R, int C,
     if (col >= C) continue;
     const int row_end = (rb + 1) * kLtUnitRows < R ? (rb + 1) * kLtUnitRows : R;
     lt_rows<T>(W, ldw, out, ldo, col, rb * kLtUnitRows, row_end, B, rank, mask, ldm, lt_sA,
-               [&](float (&f)[V], const float (&acc)[V], const uint32_t (&mb)[2]) {
-                 // (B @ A).to(dtype) -> * scaling (rounded in dtype) -> W + . (rounded in dtype) -> * mask (exact).
-                 // The three roundings run on PAIRS (packed f32 -> 2 x 16-bit -> f32 conversions are full rate; the
-                 // scalar F2F form is a quarter-rate instruction and made this kernel conversion-bound: 6 per weight)
-#pragma unroll
-                 for (int e = 0; e < V; e += 2) {
-                   const bool k0 = (mb[e / 4] >> (8 * (e % 4))) & 0xffu, k1 = (mb[(e + 1) / 4] >> (8 * ((e + 1) % 4))) & 0xffu;
-                   float2 d = round_dt2<T>(make_float2(acc[e], acc[e + 1]));
-                   d = round_dt2<T>(make_float2(__fmul_rn(d.x, scaling), __fmul_rn(d.y, scaling)));
-                   float2 r;
-                   if (sparse) {
-                     r = round_dt2<T>(make_float2(__fadd_rn(f[e], d.x), __fadd_rn(f[e + 1], d.y)));
-                     f[e] = k0 ? r.x : 0.f;
-                     f[e + 1] = k1 ? r.y : 0.f;
-                   } else {
-                     r = round_dt2<T>(make_float2(__fadd_rn(k0 ? f[e] : 0.f, d.x), __fadd_rn(k1 ? f[e + 1] : 0.f, d.y)));
-                     f[e] = r.x;
-                     f[e + 1] = r.y;
-                   }
-                 }
-               });
+               [&](float (&f)[V], const float (&acc)[V], const uint32_t (&mb)[2]) { lt_effective<T>(f, acc, mb, scaling, sparse); });
   }
 }
 

@@ -23,6 +23,43 @@ template <typename T> constexpr size_t lt_smem_bytes(int rank) {
   return (size_t)rank * Elem<T>::kVec * kLtThreads * sizeof(float);
 }
 
+// ---- the reference's roundings of the effective weight (lora.py:364-375), shared by K15 and K23 ----
+template <typename T> __device__ __forceinline__ float round_dt(float v);
+template <> __device__ __forceinline__ float round_dt<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_dt<__half>(float v) { return __half2float(__float2half_rn(v)); }
+template <> __device__ __forceinline__ float round_dt<__nv_bfloat16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+template <typename T> __device__ __forceinline__ float2 round_dt2(float2 v);
+template <> __device__ __forceinline__ float2 round_dt2<float>(float2 v) { return v; }
+template <> __device__ __forceinline__ float2 round_dt2<__half>(float2 v) { return __half22float2(__floats2half2_rn(v.x, v.y)); }
+template <> __device__ __forceinline__ float2 round_dt2<__nv_bfloat16>(float2 v) { return __bfloat1622float2(__floats2bfloat162_rn(v.x, v.y)); }
+
+// f[V] (the weights, widened) <- the effective weight from the rank-r dot acc and the mask bytes mb:
+//   sparse:  round(W + d) * mask      not sparse:  round(W * mask + d)      d = round(round(acc) * scaling)
+// (B @ A).to(dtype) -> * scaling (rounded in dtype) -> W + . (rounded in dtype) -> * mask (exact).  The three roundings
+// run on PAIRS (packed f32 -> 2 x 16-bit -> f32 conversions are full rate; the scalar F2F form is a quarter-rate
+// instruction and made K15 conversion-bound: 6 per weight).
+template <typename T, int V = Elem<T>::kVec>
+__device__ __forceinline__ void lt_effective(float (&f)[V], const float (&acc)[V], const uint32_t (&mb)[2], float scaling,
+                                             int sparse) {
+#pragma unroll
+  for (int e = 0; e < V; e += 2) {
+    const bool k0 = (mb[e / 4] >> (8 * (e % 4))) & 0xffu, k1 = (mb[(e + 1) / 4] >> (8 * ((e + 1) % 4))) & 0xffu;
+    float2 d = round_dt2<T>(make_float2(acc[e], acc[e + 1]));
+    d = round_dt2<T>(make_float2(__fmul_rn(d.x, scaling), __fmul_rn(d.y, scaling)));
+    float2 r;
+    if (sparse) {
+      r = round_dt2<T>(make_float2(__fadd_rn(f[e], d.x), __fadd_rn(f[e + 1], d.y)));
+      f[e] = k0 ? r.x : 0.f;
+      f[e + 1] = k1 ? r.y : 0.f;
+    } else {
+      r = round_dt2<T>(make_float2(__fadd_rn(k0 ? f[e] : 0.f, d.x), __fadd_rn(k1 ? f[e + 1] : 0.f, d.y)));
+      f[e] = r.x;
+      f[e + 1] = r.y;
+    }
+  }
+}
+
 // stage A[0:rank, col0 : col0 + 1024) -> sA[(kk * V/4 + q) * 128 + t] = A[kk][col0 + t * V + 4q .. +3]  (zero past C)
 template <typename T>
 __device__ __forceinline__ void lt_stage_a(float4* sA, const float* __restrict__ A, int rank, int C, int col0) {

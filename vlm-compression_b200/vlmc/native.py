@@ -54,6 +54,7 @@ SIGNATURES = {
     "vlmc_sparselora_merge": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _f, _vp, _i64, _i, _vp]),
     "vlmc_sparselora_merge_batch": (_i, [_vp, _i, _i, _i, _vp]),
     "vlmc_sparselora_effective_weight": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _f, _vp, _i64, _i, _vp, _i64, _vp]),
+    "vlmc_sparselora_linear_forward": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i, _i64, _vp, _vp, _i, _f, _vp, _i64, _i, _vp, _vp, _i64, _vp]),
     "vlmc_sparselora_lora_grads_workspace_bytes": (_sz, [_i, _i, _i]),
     "vlmc_sparselora_lora_grads": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "vlmc_count_nonzero_batch": (_i, [_vp, _i, _i, _vp, _vp]),
@@ -615,6 +616,41 @@ def sparselora_effective_weight(W, A, B, scaling, keep_mask, sparse=True, out=No
                                                      int(bool(sparse)), out.data_ptr(), out.stride(0), _stream(W))
     _check("vlmc_sparselora_effective_weight", st)
     return out
+
+
+def sparselora_linear_forward_supported(x, W, keep_mask, rank):
+    """True when K23 takes the call: 16-bit layer dtype, x in that dtype, TMA-compatible pitches."""
+    R, C = W.shape
+    return (W.dtype in (torch.float16, torch.bfloat16) and x.dtype == W.dtype and W.is_cuda and 1 <= rank <= 16 and
+            C % 8 == 0 and R % 8 == 0 and W.stride(1) == 1 and W.stride(0) % 8 == 0 and keep_mask.stride(1) == 1 and
+            keep_mask.stride(0) % 16 == 0 and W.data_ptr() % 16 == 0 and keep_mask.data_ptr() % 16 == 0)
+
+
+def sparselora_linear_forward(x, W, A, B, scaling, keep_mask, sparse=True, bias=None, out=None):
+    """K23 (lora.py:359-382): y = F.linear(x, W_eff, bias) with W_eff = (W + s*BA) * M or W * M + s*BA built on chip
+    (never written to HBM).  x [..., C] and W [R, C] in fp16 / bf16; returns y [..., R] in that dtype."""
+    R, C, rank, A, B = _lora_common(W, A, B, keep_mask)
+    _require_cuda(x)
+    if x.dtype != W.dtype or x.shape[-1] != C:
+        raise ValueError("x must be [..., C] in the layer's dtype")
+    x2 = x.reshape(-1, C)
+    if x2.stride(1) != 1 or x2.stride(0) % 8 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    Tn = x2.shape[0]
+    if bias is not None:
+        bias = bias.to(W.dtype).contiguous()
+    y = out if out is not None else torch.empty((Tn, R), dtype=W.dtype, device=W.device)
+    _require_cuda(y)
+    if Tn == 0:
+        return y.reshape(*x.shape[:-1], R)
+    with torch.cuda.device(W.device):
+        st = load().vlmc_sparselora_linear_forward(x2.data_ptr(), _dtype(W), Tn, C, x2.stride(0), W.data_ptr(), R, W.stride(0),
+                                                   A.data_ptr(), B.data_ptr(), rank, float(scaling), keep_mask.data_ptr(),
+                                                   keep_mask.stride(0), int(bool(sparse)),
+                                                   bias.data_ptr() if bias is not None else None, y.data_ptr(), y.stride(0),
+                                                   _stream(W))
+    _check("vlmc_sparselora_linear_forward", st)
+    return y.reshape(*x.shape[:-1], R)
 
 
 def sparselora_lora_grads(G, A, B, scaling, keep_mask, sparse=True):

@@ -5,9 +5,12 @@ Kept verbatim from the reference interface: `mask` (registered bool buffer, True
 merge() + the re-mask of train.py:634-637 run as ONE kernel (vlmc_sparselora_merge, K14).
 The masked training forward (lora.py:359-382) builds its weight with ONE kernel per step
 (vlmc_sparselora_effective_weight, K15) instead of ~5 elementwise passes over [R, C], and its backward gets the LoRA
-gradients from vlmc_sparselora_lora_grads (K16); the two dense GEMMs of a step stay library GEMMs.
+gradients from vlmc_sparselora_lora_grads (K16); the two dense GEMMs of a step stay library GEMMs.  With
+VLMC_LORA_FUSED=1 the forward is ONE kernel (vlmc_sparselora_linear_forward, K23: the effective weight is built on chip in
+front of tcgen05 and never written to HBM) - measured slower than K15 + cuBLAS on a B200, hence opt-in.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -18,6 +21,18 @@ from vlmc import native
 
 def transpose(weight, fan_in_fan_out):
     return weight.T if fan_in_fan_out else weight
+
+
+def _use_fused(x, W, mask, rank):
+    """K23 (one fused kernel) or K15 + library GEMM (default).  VLMC_LORA_FUSED=1 selects K23 when the layer is 16-bit
+    and its pitches are TMA-compatible.  It is opt-in: on a B200 the fused kernel measured 1.2-2.7x SLOWER than K15 +
+    cuBLAS at every SparseLoRA shape (re-deriving the effective weight in front of the tensor core costs
+    one K15 pass per 512 tokens, and the 128 x 128 single-CTA MMA shape is shared-memory bound)."""
+    if os.environ.get("VLMC_LORA_FUSED", "0") != "1" or not native.sparselora_linear_forward_supported(x, W, mask, rank):
+        return False
+    if torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") != W.dtype:
+        return False                       # F.linear would run in the autocast dtype: keep the reference's behaviour
+    return True
 
 
 class _MaskedLoRALinear(torch.autograd.Function):
@@ -31,10 +46,14 @@ class _MaskedLoRALinear(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, x, W, A, B, bias, mask, scaling, sparse):
         Af, Bf = A.detach().float(), B.detach().float()
-        w_eff = native.sparselora_effective_weight(W.detach(), Af, Bf, scaling, mask, sparse)
         ctx.save_for_backward(x, W, A, B, mask)
         ctx.scaling, ctx.sparse, ctx.has_bias = scaling, sparse, bias is not None
         ctx.bias_dtype = bias.dtype if bias is not None else None
+        if _use_fused(x, W, mask, Af.shape[0]):
+            # K23: the effective weight is built on chip, slice by slice, in front of the tensor core - nothing dense is
+            # written to HBM.  Same operand bits as K15 (test_lora_linear_fused_operand_is_k15_bit_exact).
+            return native.sparselora_linear_forward(x, W.detach(), Af, Bf, scaling, mask, sparse, bias=bias)
+        w_eff = native.sparselora_effective_weight(W.detach(), Af, Bf, scaling, mask, sparse)
         return F.linear(x, w_eff, bias)
 
     @staticmethod
