@@ -398,6 +398,85 @@ extern "C" int vlmc_chol_set_lookahead(int mode) {
 
 namespace vlmc {
 
+// Panels per super-panel of the two-level schedule below (VLMC_CHOL_SUPERPANEL = 1 / 2 / 4 / 8, read per call; 1 = the plain
+// right-looking loop with one K = 128 trailing update per panel).
+static int chol_superpanel() {
+  if (const char* e = getenv("VLMC_CHOL_SUPERPANEL")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) return v;
+  }
+  return 1;       // measured on B200 (scripts/chol_sp_probe.py): 2 / 4 / 8 are SLOWER than the plain loop, see below
+}
+
+// Two-level right-looking schedule (experiment, off by default: C = 4096 3.20 -> 3.38 ms, C = 11008 15.0-15.7 -> 16.4-16.7 ms
+// for sp = 2 / 4 / 8, profiles/r02ax_chol_sp_probe.log - the K = sp * 128 update runs on the register-summing 128-wide tiles,
+// which cost more than the passes over the trailing matrix they save; results differ from the plain loop by 4e-7).  The plain loop read-modify-writes the whole fp32 trailing matrix once per 128-wide
+// panel (K = 128: 13.9 GB of traffic and 5.7 of the 17.3 ms at C = 11008, a 3xTF32 GEMM that is all epilogue).  Here `sp`
+// panels form a super-panel: a panel's update goes at once only to the remaining columns of ITS super-panel (<= (sp - 1) * 128
+// wide), and the matrix behind the super-panel receives all of its panels in ONE update with K = sp * 128 (a quarter of the
+// passes at sp = 4; the same products per output element, the chunks of 128 summed round-to-nearest in fp32 registers before
+// the one subtraction instead of four subtractions).  Look-ahead as in the plain loop, at super-panel granularity: the columns of the
+// NEXT super-panel are updated on the caller's stream, the rest on the side stream under the next super-panel's factor.
+static int chol_lower_superpanel(float* F, int64_t ldf, float* Li, int64_t ldi, int C, int* status, cudaStream_t st, int sp,
+                                 int potrf_smem) {
+  const int nb = (C + kNB - 1) / kNB;
+  int rc;
+  ChainSide* side = chain_lookahead_enabled() && nb > 2 * sp ? chain_side_for(st, 0) : nullptr;
+  bool pending_b = false;
+  for (int s0 = 0; s0 < nb; s0 += sp) {
+    const int s1 = s0 + sp < nb ? s0 + sp : nb;                  // panels [s0, s1)
+    const int e = s1 * kNB < C ? s1 * kNB : C;                   // one past the super-panel's last column
+    for (int k = s0; k < s1; ++k) {
+      const int k0 = k * kNB;
+      const int bs = (C - k0 < kNB) ? (C - k0) : kNB;
+      potrf_block_kernel<<<1, kPotrfIoThreads, potrf_smem, st>>>(F, ldf, Li, ldi, k0, bs, status);
+      const int below = C - k0 - bs;
+      if (below <= 0) continue;
+      float* panel = F + (int64_t)(k0 + bs) * ldf + k0;
+      rc = gemm3x(true, below, bs, bs, 1.f, panel, ldf, Li + (int64_t)k0 * ldi + k0, ldi, 0.f, panel, ldf, 0, 0, st);
+      if (rc) return rc;
+      const int cols_in = e - (k0 + bs);                          // what is left of this super-panel
+      if (cols_in > 0) {
+        rc = gemm3x(true, below, cols_in, bs, -1.f, panel, ldf, panel, ldf, 1.f, F + (int64_t)(k0 + bs) * ldf + (k0 + bs), ldf,
+                    1, 0, st);
+        if (rc) return rc;
+      }
+    }
+    const int rows_rem = C - e;
+    if (rows_rem <= 0) continue;
+    const float* P = F + (int64_t)e * ldf + (int64_t)s0 * kNB;    // L[e:, super-panel columns]
+    const int K = e - s0 * kNB;
+    float* trail = F + (int64_t)e * ldf + e;
+    const int next_cols = sp * kNB < rows_rem ? sp * kNB : rows_rem;
+    const int rest = rows_rem - next_cols;
+    if (!side || rest <= 0) {
+      if (pending_b) {
+        if (cudaStreamWaitEvent(st, side->updated, 0) != cudaSuccess) return check_launch();
+        pending_b = false;
+      }
+      rc = gemm3x(true, rows_rem, rows_rem, K, -1.f, P, ldf, P, ldf, 1.f, trail, ldf, 1, 0, st);
+      if (rc) return rc;
+      continue;
+    }
+    if (cudaEventRecord(side->solved, st) != cudaSuccess) return check_launch();
+    if (pending_b) {                                             // the previous rest-update wrote what this one updates
+      if (cudaStreamWaitEvent(st, side->updated, 0) != cudaSuccess) return check_launch();
+      pending_b = false;
+    }
+    rc = gemm3x(true, rows_rem, next_cols, K, -1.f, P, ldf, P, ldf, 1.f, trail, ldf, 1, 0, st);
+    if (rc) return rc;
+    if (cudaStreamWaitEvent(side->stream, side->solved, 0) != cudaSuccess) return check_launch();
+    const float* Prest = P + (int64_t)next_cols * ldf;
+    rc = gemm3x(true, rest, rest, K, -1.f, Prest, ldf, Prest, ldf, 1.f, trail + (int64_t)next_cols * ldf + next_cols, ldf, 1, 0,
+                side->stream, 0, false, kNumSMs - 1);
+    if (rc) return rc;
+    if (cudaEventRecord(side->updated, side->stream) != cudaSuccess) return check_launch();
+    pending_b = true;
+  }
+  if (pending_b && cudaStreamWaitEvent(st, side->updated, 0) != cudaSuccess) return check_launch();
+  return check_launch();
+}
+
 // Blocked lower Cholesky of F in place (F = L L^T on the lower triangle), 128-wide panels; the inverse of every diagonal
 // block goes to the same position of Li.  A non-positive / NaN pivot sets VLMC_NOT_POSDEF in *status.
 // Look-ahead (default; VLMC_CHOL_LOOKAHEAD=0 restores the plain right-looking loop): the trailing update of step k is
@@ -417,6 +496,8 @@ static int chol_lower_blocked(float* F, int64_t ldf, float* Li, int64_t ldi, int
   }
   const int nb = (C + kNB - 1) / kNB;
   int rc;
+  const int sp = chol_superpanel();
+  if (sp > 1 && nb > sp) return chol_lower_superpanel(F, ldf, Li, ldi, C, status, st, sp, potrf_smem);
   ChainSide* side = chain_lookahead_enabled() && nb > 2 ? chain_side_for(st, 0) : nullptr;
   bool pending_b = false;
   for (int k = 0; k < nb; ++k) {
