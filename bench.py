@@ -298,11 +298,17 @@ def step_wanda(ctx, weights, inputs, method, shared=False):
             return lambda Wr, keep: native.wanda_rowselect(Wr, scalers[name], int(C * 0.5), keep_mask=keep)[1]
         names = [n for n, *_ in LINEARS]
         total = sum(R * C for _, R, C, _ in LINEARS)
+        def sel_batch(Wrs, keeps_r):        # the row shards of all linears in one call (one launch per distinct row length)
+            return native.wanda_rowselect_batch(Wrs, [scalers[n] for n in names], [int(C * 0.5) for _, _, C, _ in LINEARS],
+                                                keep_masks=keeps_r)[1]
+        batch = sel_batch if os.environ.get("VLMC_BENCH_SELECT_BATCH") != "0" else None
         res = ctx.timed("wanda_select", total * 5, lambda: parallel.prune_block_rows_packed(
             [weights[n] for n in names], [make_sel(n, C) for n, _, C, _ in LINEARS], native.mask_pack,
             lambda W, bits, keep, rps, stride: native.mask_apply_packed(W, bits, keep, True, rps, stride),
-            ctx.rank, ctx.world))
-        ctx.launches += 7 * 3
+            ctx.rank, ctx.world, select_batch_fn=batch, pack_batch_fn=native.mask_pack_batch if batch else None,
+            apply_batch_fn=(lambda Ws, bits, keeps, rps, stride: native.mask_apply_packed_batch(
+                Ws, bits, keeps, True, rps, stride)) if batch else None))
+        ctx.launches += 5 if batch else 7 * 3
         return {n: k for n, (k, _) in zip(names, res)}
     if ctx.world == 1:
         # phase 2, per-row top-k on one GPU: one launch per linear (the reference's per-linear API), longest first, dealt
@@ -310,6 +316,15 @@ def step_wanda(ctx, weights, inputs, method, shared=False):
         # fewer - is filled by the next linear's rows instead of idling.  Masks are allocated on the caller's stream.
         nsel = 1 if ctx.events is not None else max(1, int(os.environ.get("VLMC_BENCH_SELECT_STREAMS", "3")))
         keeps = {name: torch.empty((R, C), dtype=torch.bool, device=ctx.dev) for name, R, C, _ in LINEARS}
+        if os.environ.get("VLMC_BENCH_SELECT_BATCH") != "0":
+            # ONE call for the block (vlmc_wanda_rowselect_batch): the linears of equal row length share a launch whose CTAs
+            # walk the concatenated rows - 2 launches instead of 7, 25-30 rows per CTA instead of 5.  Same masks and weights.
+            names = [n for n, *_ in LINEARS]
+            ctx.timed("wanda_select", sum(R * C for _, R, C, _ in LINEARS) * 5, lambda: native.wanda_rowselect_batch(
+                [weights[n] for n in names], [scalers[n] for n in names], [int(C * 0.5) for _, _, C, _ in LINEARS],
+                keep_masks=[keeps[n] for n in names]))
+            ctx.launches += 3
+            return keeps
         with schedule_fork(ctx, nsel) as fk:
             for i, (name, R, C, _) in enumerate(sorted(LINEARS, key=lambda l: -l[1] * l[2])):
                 with fk.stream(i):

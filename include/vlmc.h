@@ -162,6 +162,16 @@ int vlmc_wanda_nm_batch(const vlmc_select_item* items, int count, int dtype, int
                         void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * K4+K5 for up to 16 linears in one call (wanda_pruner.py:332-341 runs per linear; a block's linears are independent):
+ * items of equal C share ONE launch whose CTAs walk the concatenated rows (a Vicuna block: 2 launches instead of 7, 25-30
+ * rows per CTA instead of 5).  k[i] (HOST array) = rows' prune count of item i.  Same masks, weights and score means as
+ * vlmc_wanda_rowselect per item, bit for bit.  `items` and `k` are read during the call.
+ */
+size_t vlmc_wanda_rowselect_batch_workspace_bytes(const vlmc_select_item* items, int count);
+int vlmc_wanda_rowselect_batch(const vlmc_select_item* items, const int* k, int count, int dtype, int zero_w,
+                               void* ws, size_t ws_bytes, void* stream);
+
+/*
  * K4+K7  Wanda score + whole-matrix threshold (ViT path).  Replaces wanda_pruner.py:682-683:
  *   thres = sort(S.flatten())[k_global];  prune S < thres   (strict: ties are kept)
  * k_global = int(R * C * p) computed by the caller.
@@ -186,6 +196,16 @@ int vlmc_mask_pack(const uint8_t* keep_mask, int R, int C, int64_t ldm, uint8_t*
 int vlmc_mask_apply_packed(void* W, int dtype, int R, int C, int64_t ldw, const uint8_t* bits, int64_t ldb,
                            int rows_per_seg, int64_t seg_stride, uint8_t* keep_mask, int64_t ldm, int zero_w,
                            void* stream);
+
+/* The same for up to 16 matrices per launch (`items` is a HOST array read during the call): the masks of all linears of a
+ * block are packed before, and expanded after, ONE all-gather.  Same results as the per-matrix calls. */
+typedef struct vlmc_pack_item { const uint8_t* keep_mask; int R; int C; int64_t ldm; uint8_t* bits; int64_t ldb; } vlmc_pack_item;
+typedef struct vlmc_apply_item {
+  void* W; int R; int C; int64_t ldw; const uint8_t* bits; int64_t ldb; int rows_per_seg; int64_t seg_stride;
+  uint8_t* keep_mask; int64_t ldm;
+} vlmc_apply_item;
+int vlmc_mask_pack_batch(const vlmc_pack_item* items, int count, void* stream);
+int vlmc_mask_apply_packed_batch(const vlmc_apply_item* items, int count, int dtype, int zero_w, void* stream);
 
 /*
  * K14  SparseLoRA masked merge.  Replaces Linear.merge() (sparse branch), lora.py:384-387,

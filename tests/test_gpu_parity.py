@@ -333,6 +333,69 @@ def test_mask_pack_and_apply_packed(native, R, C, tag):
     assert torch.equal(big[2:2 + R].cpu(), keep) and not bool(big[:2].any()) and not bool(big[2 + R:].any())
 
 
+@pytest.mark.parametrize("tag", ["f16", "f32"])
+def test_mask_pack_and_apply_batch_equal_per_matrix_calls(native, tag):
+    """vlmc_mask_pack_batch / vlmc_mask_apply_packed_batch (all linears of a block in one launch each) against the per-matrix
+    calls and numpy.packbits: mixed shapes, row-shard views, the [rank][row shard] layout of an all-gather."""
+    shapes = [(40, 4096), (16, 1408), (24, 2048), (8, 4096), (1376, 1024)]
+    g = torch.Generator().manual_seed(3)
+    keeps = [(torch.rand(R, C, generator=g) < 0.5).cuda() for R, C in shapes]
+    bits = [torch.zeros(R, C // 8, dtype=torch.uint8, device="cuda") for R, C in shapes]
+    native.mask_pack_batch(keeps, bits)
+    for k, b in zip(keeps, bits):
+        assert np.array_equal(b.cpu().numpy(), np.packbits(k.cpu().numpy().astype(np.uint8), axis=1, bitorder="little"))
+        assert torch.equal(b, native.mask_pack(k))
+    # two "ranks": every matrix split in two row shards, segments laid out [rank][matrix shard]
+    sizes = [(R // 2) * (C // 8) for R, C in shapes]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+    gathered = torch.zeros(2 * offs[-1], dtype=torch.uint8, device="cuda")
+    for r in range(2):
+        for i, (R, C) in enumerate(shapes):
+            gathered[r * offs[-1] + offs[i]: r * offs[-1] + offs[i + 1]] = bits[i][r * R // 2:(r + 1) * R // 2].reshape(-1)
+    Ws = [weights(R, C, 9 + i, DT[tag]).cuda() for i, (R, C) in enumerate(shapes)]
+    one = [w.clone() for w in Ws]
+    k_one = [torch.empty_like(k) for k in keeps]
+    for i, (R, C) in enumerate(shapes):
+        native.mask_apply_packed(one[i], gathered[offs[i]:], k_one[i], True, rows_per_seg=R // 2, seg_stride=offs[-1])
+    bat = [w.clone() for w in Ws]
+    k_bat = [torch.empty_like(k) for k in keeps]
+    native.mask_apply_packed_batch(bat, [gathered[offs[i]:] for i in range(len(shapes))], k_bat, True,
+                                   [R // 2 for R, _ in shapes], offs[-1])
+    for i in range(len(shapes)):
+        assert torch.equal(k_bat[i], keeps[i]) and torch.equal(k_one[i], keeps[i])
+        assert torch.equal(bat[i], one[i]) and torch.equal(bat[i], torch.where(keeps[i], Ws[i], torch.zeros_like(Ws[i])))
+
+
+def test_rowselect_block_rows_packed_batched_equals_unsharded(native):
+    """parallel.prune_block_rows_packed with the batched select / pack / apply calls, two ranks simulated in lock-step on one
+    GPU (the all-gather replaced by concatenating the two ranks' bit buffers): masks and weights equal the unsharded
+    per-linear selection."""
+    from vlmc import parallel
+    shapes = [(64, 1024), (32, 2816), (128, 1024)]
+    W0 = [weights(R, C, 21 + i, torch.float16).cuda() for i, (R, C) in enumerate(shapes)]
+    ss = [scaler(C, 31 + i).cuda() for i, (_, C) in enumerate(shapes)]
+    ks = [C // 2 for _, C in shapes]
+    full = [w.clone() for w in W0]
+    keep_full = [native.wanda_rowselect(w, s, k)[0] for w, s, k in zip(full, ss, ks)]
+    sizes = [(R // 2) * (C // 8) for R, C in shapes]
+    offs = np.concatenate([[0], np.cumsum(sizes)]).tolist()
+    reps, keeps, mine = [], [], []
+    for r in range(2):
+        Wr = [w.clone() for w in W0]
+        kr = [torch.zeros(R, C, dtype=torch.bool, device="cuda") for R, C in shapes]
+        rng = [parallel.row_range(R, r, 2) for R, _ in shapes]
+        native.wanda_rowselect_batch([w[a:b] for w, (a, b) in zip(Wr, rng)], ss, ks, keep_masks=[k[a:b] for k, (a, b) in zip(kr, rng)])
+        buf = torch.zeros(offs[-1], dtype=torch.uint8, device="cuda")
+        native.mask_pack_batch([k[a:b] for k, (a, b) in zip(kr, rng)],
+                               [buf[offs[i]:offs[i + 1]].view(rng[i][1] - rng[i][0], shapes[i][1] // 8) for i in range(3)])
+        reps.append(Wr); keeps.append(kr); mine.append(buf)
+    allbits = torch.cat(mine)
+    for r in range(2):
+        native.mask_apply_packed_batch(reps[r], [allbits[offs[i]:] for i in range(3)], keeps[r], True, [R // 2 for R, _ in shapes], offs[-1])
+        for i in range(3):
+            assert torch.equal(keeps[r][i], keep_full[i]) and torch.equal(reps[r][i], full[i])
+
+
 def test_nm_row_shards_with_packed_exchange_equal_full(native):
     """Two row shards selected separately, exchanged as bits, equal the unsharded 2:4 selection (mask and weights)."""
     R, C = 256, 4096
@@ -1727,6 +1790,51 @@ def test_lora_forward_vicuna_size_properties(native):
     E = (G * mask).float() * 2.0
     assert float((dB - E @ A.T).abs().max()) <= 1e-4 * float(dB.abs().max())
     assert float((dA - B.T @ E).abs().max()) <= 1e-4 * float(dA.abs().max())
+
+
+# ------------------------------------------------------------------------------------------- K4/K5 batch
+@pytest.mark.parametrize("tag", ["f16", "bf16", "f32"])
+def test_rowselect_batch_equals_per_linear_launches(native, tag):
+    """vlmc_wanda_rowselect_batch (linears of equal row length share a launch, CTAs walk the concatenated rows) against one
+    vlmc_wanda_rowselect per linear: masks, pruned weights and score means bit for bit.  Mixed row lengths (three groups),
+    ragged C (partial vectors per thread), rows with heavy ties, k = 0 and k = C, per-linear sparsities, zero_w on / off."""
+    shapes = [(300, 1024), (64, 2816), (517, 1024), (40, 1000), (128, 1024), (33, 2816), (8, 1000)]
+    fracs = [0.5, 0.5, 0.3, 0.7, 0.0, 1.0, 0.5]
+    Ws, ss, ks = [], [], []
+    for i, ((R, C), f) in enumerate(zip(shapes, fracs)):
+        W = weights(R, C, 50 + i, torch.float32)
+        if i == 2:
+            W[::3] = W[::3].abs().clamp_min(0.01).round(decimals=2)        # heavy ties inside rows
+            W[5] = 0.25
+        Ws.append(W.to(DT[tag]).cuda())
+        ss.append(scaler(C, 70 + i).cuda())
+        ks.append(int(C * f))
+    for zero_w in (True, False):
+        one = [w.clone() for w in Ws]
+        ref = [native.wanda_rowselect(w, s, k, zero_w=zero_w) for w, s, k in zip(one, ss, ks)]
+        bat = [w.clone() for w in Ws]
+        keeps, means = native.wanda_rowselect_batch(bat, ss, ks, zero_w=zero_w)
+        for i in range(len(Ws)):
+            assert torch.equal(keeps[i], ref[i][0]), i
+            assert torch.equal(bat[i], one[i]), i
+            assert torch.equal(means[i:i + 1], ref[i][1].reshape(1)), i
+            assert int((~keeps[i]).sum(1).min()) == ks[i] == int((~keeps[i]).sum(1).max())
+            if not zero_w:
+                assert torch.equal(bat[i], Ws[i])
+
+
+def test_rowselect_batch_vicuna_block_properties(native):
+    """The seven linears of a Vicuna block in one call: exactly k pruned per row, pruned scores <= kept scores."""
+    shapes = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]
+    Ws = [(torch.randn(R, C, device="cuda") * 0.02).half() for R, C in shapes]
+    ss = [(torch.rand(C, device="cuda") * 50 + 0.1) for _, C in shapes]
+    W0 = [w.clone() for w in Ws]
+    keeps, means = native.wanda_rowselect_batch(Ws, ss, [C // 2 for _, C in shapes])
+    for w, w0, s, k, (R, C) in zip(Ws, W0, ss, keeps, shapes):
+        assert int((~k).sum(1).min()) == C // 2 == int((~k).sum(1).max())
+        assert torch.equal(w, w0 * k)
+        score = w0.float().abs() * s.sqrt()
+        assert bool((score.masked_fill(k, -1).amax(1) <= score.masked_fill(~k, float("inf")).amin(1)).all())
 
 
 # ------------------------------------------------------------------------------------------- K23 (SURVEY 8f-2, fused)

@@ -845,10 +845,16 @@ __device__ __forceinline__ uint4 rc_zero(const uint4& wv, uint32_t pm) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// Up to kRcBatchMax matrices of ONE row length per launch (vlmc_wanda_rowselect_batch: the linears of a block that share
+// C): the CTAs walk the concatenated rows with a fixed stride, so a CTA sees 25-30 rows instead of 5 (the first row of
+// a CTA and of every matrix it enters has no predecessor to take its bin scale from), and a block costs 2 launches, not 7.
+constexpr int kRcBatchMax = 16;
+struct RcItem { void* W; int64_t ldw; const float* sq; int k; uint8_t* mask; int64_t ldm; float* row_sum; };
+struct RcBatch { RcItem it[kRcBatchMax]; int row_begin[kRcBatchMax + 1]; int count; };
+
 template <typename T, int NV, bool FULL>      // FULL: C / V == NV * 128, no bounds checks on the vectors
 __global__ void __launch_bounds__(kRcThreads, NV <= 4 ? 6 : (NV <= 8 ? 4 : 3))
-rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* __restrict__ sq, int k, int zero_w,
-                     uint8_t* __restrict__ mask, int64_t ldm, float* __restrict__ row_sum) {
+rowselect_cta_kernel(const __grid_constant__ RcBatch bt, int C, int zero_w) {
   constexpr int V = Elem<T>::kVec;
   extern __shared__ __align__(16) uint32_t rc_smem[];
   const int nvec = C / V;
@@ -863,29 +869,31 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
   if (tid == 0) sh.ncand = 0;
 
 #define RC_HAS(u) (FULL || tid + (u) * kRcThreads < nvec)
-  auto load_row = [&](int row, uint4 (&wv)[NV]) {
-    const T* wrow = W + (int64_t)row * ldw;
-#pragma unroll
-    for (int u = 0; u < NV; ++u)
-      if (RC_HAS(u)) wv[u] = ld_stream(wrow + (int64_t)(tid + u * kRcThreads) * V);
-  };
-
   // Bin scale.  Rows of one matrix share sq and the weight distribution, so the previous row's threshold predicts this
   // row's: scale = 1024 / previous threshold puts the k-th score near the MIDDLE of the 2048 bins with ~0.1 % of its value
   // per bin (2-3 keys per bin at C = 4096), and everything above twice the threshold in the last bin, which is never
-  // counted (the k-th score is found below it, or the row takes the exact path).  The first row of a CTA has no
-  // predecessor: its scale comes from its own maximum (coarser: more candidates, same result).
+  // counted (the k-th score is found below it, or the row takes the exact path).  The first row a CTA takes of a matrix
+  // has no predecessor: its scale comes from its own maximum (coarser: more candidates, same result).
   // (Double-buffering the next row's vectors in registers was measured: 38.0 -> 38.3 us at 4096^2 - with 5-6 CTAs per SM the
-  // HBM latency of a row's loads is already covered by the other CTAs - and it costs 10 registers; the code path stays for
-  // experiments.)
-  constexpr bool kPrefetch = false;
+  // HBM latency of a row's loads is already covered by the other CTAs - and it costs 10 registers; dropped.)
   uint4 wv[NV];
   float scale = 0.f;
-  {
-    const int row = blockIdx.x;
-    uint32_t lmax = 0;
-    if (row < R) {
-      load_row(row, wv);
+  int item = -1, cur = 0;
+  const int total_rows = bt.row_begin[bt.count];
+
+  for (int vrow = blockIdx.x; vrow < total_rows; vrow += gridDim.x) {
+    while (vrow >= bt.row_begin[cur + 1]) ++cur;
+    const RcItem& im = bt.it[cur];
+    const int row = vrow - bt.row_begin[cur];
+    const int k = im.k;
+    const float* __restrict__ sq = im.sq;
+    T* wrow = reinterpret_cast<T*>(im.W) + (int64_t)row * im.ldw;
+#pragma unroll
+    for (int u = 0; u < NV; ++u)
+      if (RC_HAS(u)) wv[u] = ld_stream(wrow + (int64_t)(tid + u * kRcThreads) * V);
+    if (cur != item) {                                          // first row of this CTA in this matrix: scale from the row's maximum
+      item = cur;
+      uint32_t lmax = 0;
 #pragma unroll
       for (int u = 0; u < NV; ++u) {
         if (RC_HAS(u)) {
@@ -895,29 +903,14 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
           for (int e = 0; e < V; ++e) lmax = key[e] > lmax ? key[e] : lmax;
         }
       }
-    }
-    lmax = __reduce_max_sync(0xffffffffu, lmax);
-    if (lane == 0) sh.wmax[warp] = lmax;
-    __syncthreads();
-    uint32_t rmax = 0;
+      lmax = __reduce_max_sync(0xffffffffu, lmax);
+      if (lane == 0) sh.wmax[warp] = lmax;
+      __syncthreads();
+      uint32_t rmax = 0;
 #pragma unroll
-    for (int w = 0; w < kRcWarps; ++w) rmax = sh.wmax[w] > rmax ? sh.wmax[w] : rmax;
-    if (rmax > 0u && rmax < 0x7f800000u) scale = (float)kRcBins / (1.25f * __uint_as_float(rmax));
-    __syncthreads();
-  }
-
-  for (int row = blockIdx.x; row < R; row += gridDim.x) {
-    T* wrow = W + (int64_t)row * ldw;
-    uint4 nx[kPrefetch ? NV : 1];
-    if (kPrefetch) {                                           // wv holds this row (first row: loaded by the prologue)
-      if (row + (int)gridDim.x < R) {
-        const T* nrow = W + (int64_t)(row + gridDim.x) * ldw;
-#pragma unroll
-        for (int u = 0; u < NV; ++u)
-          if (RC_HAS(u)) nx[kPrefetch ? u : 0] = ld_stream(nrow + (int64_t)(tid + u * kRcThreads) * V);
-      }
-    } else if (row != (int)blockIdx.x) {
-      load_row(row, wv);
+      for (int w = 0; w < kRcWarps; ++w) rmax = sh.wmax[w] > rmax ? sh.wmax[w] : rmax;
+      scale = (rmax > 0u && rmax < 0x7f800000u) ? (float)kRcBins / (1.25f * __uint_as_float(rmax)) : 0.f;
+      __syncthreads();
     }
     // ---- P1: score, keys -> smem, row sum, linear-bin histogram
     float lsum = 0.f;
@@ -947,7 +940,7 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < kRcWarps; ++w) t += sh.wsum[w];
-        row_sum[row] = t;
+        im.row_sum[row] = t;
         sh.sel_bin = (uint32_t)(kRcBins - 1);                  // stays there when the k-th score is not below the last bin
         sh.sel_before = 0;
         sh.ncand = 0;                                          // every thread is past barrier A: done with the previous row's list
@@ -1070,7 +1063,7 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
     }
 
     // ---- P4: apply (weights are zeroed in their packed form; no unpack / repack)
-    uint8_t* mrow = mask + (int64_t)row * ldm;
+    uint8_t* mrow = im.mask + (int64_t)row * im.ldm;
     if (ties_simple && k > 0 && k < C) {
       // Fast form: pruned <=> key <= thr_key, both below 2^31, so the sign of (thr_key - key) is the keep bit.  PRMT in its
       // sign-replicating mode (selector nibble 8 | byte) turns that sign straight into the AND mask of the packed weight
@@ -1133,10 +1126,6 @@ rowselect_cta_kernel(T* __restrict__ W, int64_t ldw, int R, int C, const float* 
         }
       }
     }
-    if (kPrefetch) {
-#pragma unroll
-      for (int u = 0; u < NV; ++u) wv[u] = nx[kPrefetch ? u : 0];
-    }
     // next row's scale: this row's threshold in the middle of the bins
     if (select && thr_key > 0u && thr_key < 0x7f800000u) scale = (float)(kRcBins / 2) / __uint_as_float(thr_key);
   }
@@ -1151,8 +1140,7 @@ static bool rowselect_cta_fits(int C) {
 }
 
 template <typename T, int NV, bool FULL>
-static int launch_rowselect_cta_nv(void* W, int R, int C, int64_t ldw, const float* sq, int k, int zero_w,
-                                   uint8_t* mask, int64_t ldm, float* row_sum, cudaStream_t st) {
+static int launch_rowselect_cta_nv(const RcBatch& bt, int C, int zero_w, cudaStream_t st) {
   auto kern = rowselect_cta_kernel<T, NV, FULL>;
   const size_t smem = ((size_t)C + kRcHist + 2 * kRcCand) * sizeof(uint32_t);
   static bool attr_set = false;
@@ -1165,22 +1153,22 @@ static int launch_rowselect_cta_nv(void* W, int R, int C, int64_t ldw, const flo
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRcThreads, smem);
   if (per_sm < 1) per_sm = 1;
   // every CTA gets the same number of rows (a ragged last wave would idle part of the grid)
+  const int R = bt.row_begin[bt.count];
   const int resident = kNumSMs * per_sm;
   const int rows_per_cta = (R + resident - 1) / resident;
   int grid = (R + rows_per_cta - 1) / rows_per_cta;
   if (grid < 1) grid = 1;
-  kern<<<grid, kRcThreads, smem, st>>>(reinterpret_cast<T*>(W), ldw, R, C, sq, k, zero_w, mask, ldm, row_sum);
+  kern<<<grid, kRcThreads, smem, st>>>(bt, C, zero_w);
   return check_launch();
 }
 
 template <typename T>
-static int launch_rowselect_cta(void* W, int R, int C, int64_t ldw, const float* sq, int k, int zero_w,
-                                uint8_t* mask, int64_t ldm, float* row_sum, cudaStream_t st) {
+static int launch_rowselect_cta(const RcBatch& bt, int C, int zero_w, cudaStream_t st) {
   constexpr int V = Elem<T>::kVec;
   const int nv = (C / V + kRcThreads - 1) / kRcThreads;
 #define VLMC_RC(NV)                                                                                               \
-  return (C / V == (NV) * kRcThreads) ? launch_rowselect_cta_nv<T, NV, true>(W, R, C, ldw, sq, k, zero_w, mask, ldm, row_sum, st)         \
-              : launch_rowselect_cta_nv<T, NV, false>(W, R, C, ldw, sq, k, zero_w, mask, ldm, row_sum, st)
+  return (C / V == (NV) * kRcThreads) ? launch_rowselect_cta_nv<T, NV, true>(bt, C, zero_w, st)                   \
+                                      : launch_rowselect_cta_nv<T, NV, false>(bt, C, zero_w, st)
   if (nv <= 1) VLMC_RC(1);
   if (nv <= 2) VLMC_RC(2);
   if (nv <= 4) VLMC_RC(4);
@@ -1191,13 +1179,20 @@ static int launch_rowselect_cta(void* W, int R, int C, int64_t ldw, const float*
 #undef VLMC_RC
 }
 
+static bool rowselect_legacy() {
+  const char* legacy = getenv("VLMC_ROWSELECT_LEGACY");        // A/B switch: the warp-per-row streaming kernel
+  return legacy && legacy[0] == '1';
+}
+
 template <typename T>
 static int launch_rowselect(void* W, int R, int C, int64_t ldw, const float* sq, int k, int zero_w,
                             uint8_t* mask, int64_t ldm, float* row_sum, uint32_t* seed, cudaStream_t st) {
-  {
-    const char* legacy = getenv("VLMC_ROWSELECT_LEGACY");      // A/B switch: the warp-per-row streaming kernel
-    if (!(legacy && legacy[0] == '1') && rowselect_cta_fits<T>(C))
-      return launch_rowselect_cta<T>(W, R, C, ldw, sq, k, zero_w, mask, ldm, row_sum, st);
+  if (!rowselect_legacy() && rowselect_cta_fits<T>(C)) {
+    RcBatch bt;
+    bt.count = 1;
+    bt.row_begin[0] = 0; bt.row_begin[1] = R;
+    bt.it[0] = RcItem{W, ldw, sq, k, mask, ldm, row_sum};
+    return launch_rowselect_cta<T>(bt, C, zero_w, st);
   }
   auto kern = rowselect_kernel<T>;
   rowselect_seed_kernel<T><<<1, 32, 0, st>>>(reinterpret_cast<const T*>(W), ldw, R, C, sq, k, seed);
@@ -1233,6 +1228,98 @@ extern "C" int vlmc_wanda_rowselect(void* W, int dtype, int R, int C, int64_t ld
   VLMC_DISPATCH_DTYPE(dtype, rc = (launch_rowselect<scalar_t>(W, R, C, ldw, sq, k, zero_w, keep_mask, ldm, row_sum, seed, st)));
   if (rc) return rc;
   if (score_mean) return launch_mean_finalize(row_sum, R, (double)R * (double)C, score_mean, st);
+  return VLMC_OK;
+}
+
+namespace vlmc {
+// sqrt(scaler_row) of every item in one launch: grid (column chunks, items)
+struct SqrtBatch { const float* in[kRcBatchMax]; float* out[kRcBatchMax]; int C[kRcBatchMax]; };
+__global__ void __launch_bounds__(256) sqrt_vec_batch_kernel(const __grid_constant__ SqrtBatch b) {
+  const int i = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+  if (j < b.C[i]) b.out[i][j] = sqrtf(b.in[i][j]);
+}
+static size_t rowselect_item_ws_floats(int R, int C) { return (size_t)((R + 3) & ~3) + (size_t)((C + 3) & ~3) + 8; }
+}  // namespace vlmc
+
+extern "C" size_t vlmc_wanda_rowselect_batch_workspace_bytes(const vlmc_select_item* items, int count) {
+  using namespace vlmc;
+  if (!items || count < 1) return 0;
+  size_t fl = 0;
+  for (int i = 0; i < count; ++i) fl += rowselect_item_ws_floats(items[i].R, items[i].C);
+  return VLMC_WS_COUNTER_BYTES + fl * sizeof(float);
+}
+
+extern "C" int vlmc_wanda_rowselect_batch(const vlmc_select_item* items, const int* k, int count, int dtype, int zero_w,
+                                          void* ws, size_t ws_bytes, void* stream) {
+  using namespace vlmc;
+  if (!items || !k || count < 1 || count > kRcBatchMax) return VLMC_ERR_BAD_ARG;
+  if (ws_bytes < vlmc_wanda_rowselect_batch_workspace_bytes(items, count)) return VLMC_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* base = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + VLMC_WS_COUNTER_BYTES);
+  float* row_sum[kRcBatchMax];
+  float* sq[kRcBatchMax];
+  SqrtBatch sb;
+  NmBatchOut o;
+  int maxC = 0;
+  bool any_mean = false, fits = !rowselect_legacy();
+  o.begin[0] = 0;
+  for (int i = 0; i < count; ++i) {
+    const vlmc_select_item& s = items[i];
+    int rc = sel_common_checks(s.W, dtype, s.R, s.C, s.ldw, s.scaler_row, s.keep_mask, s.ldm, ws);
+    if (rc) return rc;
+    if (k[i] < 0) return VLMC_ERR_BAD_ARG;
+    if (s.score_mean && !is_device_ptr(s.score_mean)) return VLMC_ERR_NOT_DEVICE;
+    row_sum[i] = base;                                   // the row sums of all items are contiguous: one finalize launch
+    base += (s.R + 3) & ~3;
+    o.begin[i + 1] = o.begin[i] + ((s.R + 3) & ~3);
+    o.out[i] = s.score_mean;
+    o.denom[i] = (double)s.R * (double)s.C;
+    any_mean |= s.score_mean != nullptr;
+    maxC = s.C > maxC ? s.C : maxC;
+    VLMC_DISPATCH_DTYPE(dtype, fits = fits && rowselect_cta_fits<scalar_t>(s.C));
+  }
+  for (int i = 0; i < count; ++i) {
+    sq[i] = base;
+    base += ((items[i].C + 3) & ~3) + 8;
+    sb.in[i] = items[i].scaler_row; sb.out[i] = sq[i]; sb.C[i] = items[i].C;
+  }
+  if (!fits) {                                           // rows too long for shared memory / the legacy switch: one by one
+    for (int i = 0; i < count; ++i) {
+      const vlmc_select_item& s = items[i];
+      int rc = vlmc_wanda_rowselect(s.W, dtype, s.R, s.C, s.ldw, s.scaler_row, k[i], zero_w, s.keep_mask, s.ldm, s.score_mean,
+                                    ws, ws_bytes, stream);
+      if (rc) return rc;
+    }
+    return VLMC_OK;
+  }
+  if (any_mean) {                                        // padding rows of the contiguous row-sum array must read as zero
+    if (cudaMemsetAsync(row_sum[0], 0, (size_t)o.begin[count] * sizeof(float), st) != cudaSuccess) return check_launch();
+  }
+  sqrt_vec_batch_kernel<<<dim3((maxC + 255) / 256, count), 256, 0, st>>>(sb);
+  // one launch per distinct row length (a Vicuna block: C = 4096 x 6, C = 11008 x 1)
+  bool done[kRcBatchMax] = {};
+  for (int i = 0; i < count; ++i) {
+    if (done[i]) continue;
+    RcBatch bt;
+    bt.count = 0;
+    bt.row_begin[0] = 0;
+    for (int j = i; j < count; ++j) {
+      if (done[j] || items[j].C != items[i].C) continue;
+      const vlmc_select_item& s = items[j];
+      if ((int64_t)bt.row_begin[bt.count] + s.R > 0x7fffffff) return VLMC_ERR_UNSUPPORTED;
+      bt.it[bt.count] = RcItem{s.W, s.ldw, sq[j], k[j], s.keep_mask, s.ldm, row_sum[j]};
+      bt.row_begin[bt.count + 1] = bt.row_begin[bt.count] + s.R;
+      ++bt.count;
+      done[j] = true;
+    }
+    int rc;
+    VLMC_DISPATCH_DTYPE(dtype, rc = (launch_rowselect_cta<scalar_t>(bt, items[i].C, zero_w, st)));
+    if (rc) return rc;
+  }
+  if (any_mean) {
+    mean_finalize_batch_kernel<<<count, 256, 0, st>>>(row_sum[0], o);
+    return check_launch();
+  }
   return VLMC_OK;
 }
 

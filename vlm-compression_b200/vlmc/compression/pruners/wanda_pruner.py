@@ -5,6 +5,8 @@ with the statistics and the mask selection running in sm_100a kernels (include/v
   BLIPT5LayerWandaPruner      <- wanda_pruner.py:796-1044 (registered as "blipt5_wanda_pruner")
   per-linear score + select   <- wanda_pruner.py:316-341 (LLM/T5: per-row, K5/K6), :664-687 (ViT: K7/K6)
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -91,6 +93,16 @@ def wanda_prune_block_rows(modules, scaler_rows, sparsities, lora_model=False, s
     by_dev = {}
     for i in order:
         by_dev.setdefault(modules[i].weight.device, []).append(i)
+    for dev, idx in list(by_dev.items()):
+        # ONE call per device and dtype (vlmc_wanda_rowselect_batch: the linears of equal row length share a launch whose
+        # CTAs walk the concatenated rows); VLMC_ROWSELECT_BATCH=0 restores one launch per linear on side streams
+        if os.environ.get("VLMC_ROWSELECT_BATCH") != "0" and len({modules[i].weight.dtype for i in idx}) == 1:
+            _, mm = native.wanda_rowselect_batch([modules[i].weight.data for i in idx], [scaler_rows[i] for i in idx],
+                                                 [int(modules[i].weight.shape[1] * sparsities[i]) for i in idx],
+                                                 zero_w=not lora_model, keep_masks=[keeps[i] for i in idx])
+            for j, i in enumerate(idx):
+                means[i] = mm[j:j + 1]
+            del by_dev[dev]
     for dev, idx in by_dev.items():
         with Fork(dev, max(1, min(streams, len(idx)))) as fk:
             for slot, i in enumerate(idx):

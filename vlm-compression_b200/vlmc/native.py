@@ -48,9 +48,13 @@ SIGNATURES = {
     "vlmc_wanda_nm": (_i, [_vp, _i, _i, _i, _i64, _vp, _i, _i, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_wanda_nm_batch_workspace_bytes": (_sz, [_vp, _i, _i, _i]),
     "vlmc_wanda_nm_batch": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "vlmc_wanda_rowselect_batch_workspace_bytes": (_sz, [_vp, _i]),
+    "vlmc_wanda_rowselect_batch": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "vlmc_wanda_threshold": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _vp, _i64, _vp, _vp, _sz, _vp]),
     "vlmc_mask_pack": (_i, [_vp, _i, _i, _i64, _vp, _i64, _vp]),
     "vlmc_mask_apply_packed": (_i, [_vp, _i, _i, _i, _i64, _vp, _i64, _i, _i64, _vp, _i64, _i, _vp]),
+    "vlmc_mask_pack_batch": (_i, [_vp, _i, _vp]),
+    "vlmc_mask_apply_packed_batch": (_i, [_vp, _i, _i, _i, _vp]),
     "vlmc_sparselora_merge": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _f, _vp, _i64, _i, _vp]),
     "vlmc_sparselora_merge_batch": (_i, [_vp, _i, _i, _i, _vp]),
     "vlmc_sparselora_effective_weight": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _f, _vp, _i64, _i, _vp, _i64, _vp]),
@@ -342,6 +346,40 @@ def wanda_nm_batch(Ws, scaler_rows, n, m, zero_w=True, keep_masks=None):
     return keep_masks, means
 
 
+def wanda_rowselect_batch(Ws, scaler_rows, ks, zero_w=True, keep_masks=None):
+    """K4+K5 for several linears in ONE call (vlmc_wanda_rowselect_batch: one launch per distinct row length).  Ws: list of
+    2-D weights (or row shards) of one dtype on one device; ks: rows' prune count per linear.  Returns ([keep_mask],
+    score_means [len(Ws)] device tensor); same masks, weights and means as len(Ws) calls of wanda_rowselect."""
+    if not Ws:
+        return [], None
+    dev, dt = Ws[0].device, Ws[0].dtype
+    _require_cuda(*Ws, *scaler_rows)
+    if keep_masks is None:
+        keep_masks = [torch.empty(W.shape, dtype=torch.bool, device=dev) for W in Ws]
+    out_masks, means_all = list(keep_masks), torch.empty(len(Ws), dtype=torch.float32, device=dev)
+    lib = load()
+    for c0 in range(0, len(Ws), 16):
+        sl = slice(c0, min(c0 + 16, len(Ws)))
+        n = sl.stop - sl.start
+        items = (SelectItem * n)()
+        karr = (ctypes.c_int * n)(*[int(k) for k in ks[sl]])
+        for i, (W, s, k) in enumerate(zip(Ws[sl], scaler_rows[sl], keep_masks[sl])):
+            if W.dim() != 2 or W.stride(1) != 1 or W.dtype != dt or W.device != dev:
+                raise ValueError("weights must be 2-D row-major tensors of one dtype on one device")
+            if k.dtype != torch.bool or k.shape != W.shape or k.stride(1) != 1:
+                raise ValueError("keep_mask must be a bool tensor shaped like W")
+            if s.dtype != torch.float32 or s.numel() != W.shape[1]:
+                raise ValueError("scaler_row must be float32 [C]")
+            items[i] = SelectItem(W.data_ptr(), W.stride(0), W.shape[0], W.shape[1], s.data_ptr(), k.data_ptr(), k.stride(0),
+                                  means_all[c0 + i:c0 + i + 1].data_ptr())
+        ws = workspace(Ws[0], lib.vlmc_wanda_rowselect_batch_workspace_bytes(items, n))
+        with torch.cuda.device(dev):
+            st = lib.vlmc_wanda_rowselect_batch(items, karr, n, _dtype(Ws[0]), int(bool(zero_w)), ws.data_ptr(), ws.numel(),
+                                                _stream(Ws[0]))
+        _check("vlmc_wanda_rowselect_batch", st)
+    return out_masks, means_all
+
+
 def wanda_threshold(W, scaler_row, k_global, zero_w=True, keep_mask=None):
     """K4+K7 (wanda_pruner.py:682-683)."""
     lib, R, C, keep_mask, ws, score_mean = _select_common(W, scaler_row, keep_mask)
@@ -380,6 +418,51 @@ def mask_apply_packed(W, bits, keep_mask=None, zero_w=True, rows_per_seg=0, seg_
                                            keep_mask.stride(0) if keep_mask is not None else 0, int(zero_w), _stream(W))
     _check("vlmc_mask_apply_packed", st)
     return keep_mask
+
+
+class PackItem(ctypes.Structure):
+    """vlmc_pack_item (include/vlmc.h)."""
+    _fields_ = [("keep_mask", _vp), ("R", _i), ("C", _i), ("ldm", _i64), ("bits", _vp), ("ldb", _i64)]
+
+
+class ApplyItem(ctypes.Structure):
+    """vlmc_apply_item (include/vlmc.h)."""
+    _fields_ = [("W", _vp), ("R", _i), ("C", _i), ("ldw", _i64), ("bits", _vp), ("ldb", _i64), ("rows_per_seg", _i),
+                ("seg_stride", _i64), ("keep_mask", _vp), ("ldm", _i64)]
+
+
+def mask_pack_batch(keep_masks, bits_list):
+    """mask_pack for up to 16 (keep_mask [R, C], bits [R, C // 8]) pairs per launch; same bits."""
+    _require_cuda(*keep_masks, *bits_list)
+    lib = load()
+    for c0 in range(0, len(keep_masks), 16):
+        ks, bs = keep_masks[c0:c0 + 16], bits_list[c0:c0 + 16]
+        items = (PackItem * len(ks))()
+        for i, (k, b) in enumerate(zip(ks, bs)):
+            items[i] = PackItem(k.data_ptr(), k.shape[0], k.shape[1], k.stride(0), b.data_ptr(), b.stride(0))
+        with torch.cuda.device(ks[0].device):
+            st = lib.vlmc_mask_pack_batch(items, len(ks), _stream(ks[0]))
+        _check("vlmc_mask_pack_batch", st)
+    return bits_list
+
+
+def mask_apply_packed_batch(Ws, bits_list, keep_masks, zero_w=True, rows_per_seg=None, seg_stride=0):
+    """mask_apply_packed for up to 16 matrices of one dtype per launch.  bits_list[i] is the flat uint8 buffer (or view) that
+    holds matrix i's bits in the [segment][row shard] layout; rows_per_seg[i] rows per segment, seg_stride bytes apart."""
+    _require_cuda(*Ws, *bits_list, *keep_masks)
+    lib = load()
+    for c0 in range(0, len(Ws), 16):
+        ws_, bs, ks = Ws[c0:c0 + 16], bits_list[c0:c0 + 16], keep_masks[c0:c0 + 16]
+        items = (ApplyItem * len(ws_))()
+        for i, (W, b, k) in enumerate(zip(ws_, bs, ks)):
+            R, C = W.shape
+            rps = int(rows_per_seg[c0 + i]) if rows_per_seg is not None else 0
+            items[i] = ApplyItem(W.data_ptr(), R, C, W.stride(0), b.data_ptr(), b.stride(0) if b.dim() == 2 else C // 8, rps,
+                                 int(seg_stride), k.data_ptr() if k is not None else None, k.stride(0) if k is not None else 0)
+        with torch.cuda.device(ws_[0].device):
+            st = lib.vlmc_mask_apply_packed_batch(items, len(ws_), _dtype(ws_[0]), int(bool(zero_w)), _stream(ws_[0]))
+        _check("vlmc_mask_apply_packed_batch", st)
+    return keep_masks
 
 
 def sparselora_merge(W, A, B, scaling, keep_mask, remask=True):

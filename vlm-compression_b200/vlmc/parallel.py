@@ -102,13 +102,18 @@ def exchange_rows_packed(weight, keep, pack_fn, apply_fn, rank, world, group=Non
     return keep
 
 
-def prune_block_rows_packed(weights, select_fns, pack_fn, apply_fn, rank, world, group=None):
+def prune_block_rows_packed(weights, select_fns, pack_fn, apply_fn, rank, world, group=None, select_batch_fn=None,
+                            pack_batch_fn=None, apply_batch_fn=None):
     """Phase 2 for ALL linears of a block with ONE collective.  Every rank runs select_fns[i](W_rows, keep_rows) ->
     score_mean on its row shard of weights[i] (mask bytes + zeroed rows, in place), packs those mask rows to bits
     (pack_fn(keep_rows, bits_out)), all ranks all-gather the bits of all linears in one call (1 bit per weight: the
     weights are replicated, only the decision travels) and expand them with apply_fn(W, bits, keep,
     rows_per_seg, seg_stride), which also zeroes the pruned weights of the local replica.  Returns [(keep [R, C] bool, score_mean)].
-    Needs R % world == 0 and C % 16 == 0 for every linear (callers fall back to prune_linear_row_sharded otherwise)."""
+    Needs R % world == 0 and C % 16 == 0 for every linear (callers fall back to prune_linear_row_sharded otherwise).
+    select_batch_fn(W_rows_list, keep_rows_list) -> score means [len] (optional): selects on ALL row shards in one call
+    (vlmc_wanda_rowselect_batch) instead of one select_fns[i] call per linear; same results.  pack_batch_fn(keep_rows_list,
+    bits_list) and apply_batch_fn(weights, bits_views, keeps, rows_per_seg_list, seg_stride) (optional) do the same for the
+    packing and the expand-and-zero pass: one launch each instead of one per linear."""
     dev = weights[0].device
     shapes = [tuple(w.shape) for w in weights]
     assert all(R % world == 0 and C % 16 == 0 for R, C in shapes)
@@ -118,21 +123,33 @@ def prune_block_rows_packed(weights, select_fns, pack_fn, apply_fn, rank, world,
         offs.append(offs[-1] + n)
     mine = torch.empty(offs[-1], dtype=torch.uint8, device=dev)
     keeps, means = [], torch.zeros(len(weights), dtype=torch.float32, device=dev)
+    ranges = [row_range(R, rank, world) for R, _ in shapes]
+    keeps = [torch.empty((R, C), dtype=torch.bool, device=dev) for R, C in shapes]
+    if select_batch_fn is not None:
+        m_all = select_batch_fn([w[s:e] for w, (s, e) in zip(weights, ranges)], [k[s:e] for k, (s, e) in zip(keeps, ranges)])
+        means = m_all.reshape(-1) * (1.0 / float(world))          # R % world == 0: every shard is exactly 1 / world of its rows
     for i, (w, (R, C)) in enumerate(zip(weights, shapes)):
-        s, e = row_range(R, rank, world)
-        keep = torch.empty((R, C), dtype=torch.bool, device=dev)
-        m = select_fns[i](w[s:e], keep[s:e])
-        means[i:i + 1] = m.reshape(1) * (float(e - s) / float(R))
-        pack_fn(keep[s:e], mine[offs[i]:offs[i + 1]].view(e - s, C // 8))
-        keeps.append(keep)
+        s, e = ranges[i]
+        keep = keeps[i]
+        if select_batch_fn is None:
+            m = select_fns[i](w[s:e], keep[s:e])
+            means[i:i + 1] = m.reshape(1) * (float(e - s) / float(R))
+        if pack_batch_fn is None:
+            pack_fn(keep[s:e], mine[offs[i]:offs[i + 1]].view(e - s, C // 8))
+    if pack_batch_fn is not None:
+        pack_batch_fn([k[s:e] for k, (s, e) in zip(keeps, ranges)],
+                      [mine[offs[i]:offs[i + 1]].view(ranges[i][1] - ranges[i][0], shapes[i][1] // 8) for i in range(len(weights))])
     if dist.is_initialized() and world > 1:
         allbits = torch.empty(world * offs[-1], dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allbits, mine, group=group)
         dist.all_reduce(means, op=dist.ReduceOp.SUM, group=group)
         # buffer layout [rank][linear shard]: ONE expand-and-zero call per linear covers the rows of every rank
         # (re-applying the own shard is idempotent)
-        for i, (w, (R, C)) in enumerate(zip(weights, shapes)):
-            apply_fn(w, allbits[offs[i]:], keeps[i], R // world, offs[-1])
+        if apply_batch_fn is not None:
+            apply_batch_fn(weights, [allbits[offs[i]:] for i in range(len(weights))], keeps, [R // world for R, _ in shapes], offs[-1])
+        else:
+            for i, (w, (R, C)) in enumerate(zip(weights, shapes)):
+                apply_fn(w, allbits[offs[i]:], keeps[i], R // world, offs[-1])
     return [(k, means[i:i + 1]) for i, k in enumerate(keeps)]
 
 
