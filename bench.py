@@ -380,6 +380,23 @@ def step_dsnot(ctx, weights, inputs, elide=False):
         nref = max(1, int(os.environ.get("VLMC_BENCH_SELECT_STREAMS" if elide else "VLMC_BENCH_REFINE_STREAMS", "3")))
     order = sorted(LINEARS, key=lambda l: -l[1] * l[2]) if nref > 1 else LINEARS
     keeps = {name: torch.empty((R, C), dtype=torch.bool, device=ctx.dev) for name, R, C, _ in LINEARS}
+    if elide and os.environ.get("VLMC_BENCH_SELECT_BATCH") != "0" and all(R % ctx.world == 0 for _, R, _, _ in LINEARS):
+        # shipped semantics (the mask is the initial selection): the block's selections as ONE batched call, like step_wanda
+        names = [n for n, *_ in LINEARS]
+        ks = [round(C * 0.6) for _, _, C, _ in LINEARS]
+        total = sum(R * C for _, R, C, _ in LINEARS)
+        if ctx.world == 1:
+            ctx.timed("wanda_select", total * 5, lambda: native.wanda_rowselect_batch(
+                [weights[n] for n in names], [stats[n][0] for n in names], ks, keep_masks=[keeps[n] for n in names]))
+            ctx.launches += 3
+            return keeps
+        res = ctx.timed("wanda_select", total * 5, lambda: parallel.prune_block_rows_packed(
+            [weights[n] for n in names], [None] * len(names), native.mask_pack, None, ctx.rank, ctx.world,
+            select_batch_fn=lambda Wrs, kr: native.wanda_rowselect_batch(Wrs, [stats[n][0] for n in names], ks, keep_masks=kr)[1],
+            pack_batch_fn=native.mask_pack_batch,
+            apply_batch_fn=lambda Ws, bits, kp, rps, stride: native.mask_apply_packed_batch(Ws, bits, kp, True, rps, stride)))
+        ctx.launches += 5
+        return {n: k for n, (k, _) in zip(names, res)}
     with schedule_fork(ctx, nref) as fk:
         for li, (name, R, C, _) in enumerate(order):
             W = weights[name]
