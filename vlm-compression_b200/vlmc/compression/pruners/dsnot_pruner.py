@@ -5,6 +5,8 @@
   dsnot_prune_linear        <- :359-755    initial mask + prune/regrow cycles (vlmc_dsnot_refine_walk/_apply, K8+K9)
   BLIPT5LayerDSnoTPruner    <- :1599-1863  registered as "blipt5_dsnot_pruner"
 """
+import os
+
 import torch
 
 from vlmc import native
@@ -158,6 +160,13 @@ class BLIPT5LayerDSnoTPruner(BLIPT5LayerWandaPruner):
     def _prune_linear(self, vit, lora_model):
         def fn(i, name, module, wrapper, sparsity, expected_nsamples):
             assert wrapper.nsamples == expected_nsamples          # :360
+            if (self.prune_n == 0 and sparsity != 0. and (self.without_DSnoT or (self.elide_noop_swaps and not self.upstream_semantics))
+                    and os.environ.get("VLMC_ROWSELECT_BATCH") != "0"):
+                # the initial selection IS the result (dsnot_prune_linear, elide_noop_swaps): the block's selections go
+                # through ONE batched call in finish_block, with DSnoT's rounded prune count (:562) and no importance score
+                scal = wrapper.scaler_row if self.initial_method == "wanda" else torch.ones_like(wrapper.scaler_row)
+                self._pending_rows.append((module, scal, sparsity, lora_model, round(module.weight.shape[1] * sparsity), False))
+                return
             dsnot_prune_linear(module, wrapper, sparsity, self.prune_n, self.prune_m, lora_model=lora_model,
                                initial_method=self.initial_method, pow_of_var_regrowing=self.pow_of_var_regrowing,
                                max_cycle_time=self.max_cycle_time, update_threshold=self.update_threshold,

@@ -79,13 +79,17 @@ def wanda_prune_block_nm(modules, scaler_rows, prune_n, prune_m, lora_model=Fals
     return out
 
 
-def wanda_prune_block_rows(modules, scaler_rows, sparsities, lora_model=False, streams=3):
+def wanda_prune_block_rows(modules, scaler_rows, sparsities, lora_model=False, streams=3, ks=None):
     """Per-row top-k (wanda_pruner.py:332-341) for the linears of one block: the same one launch per linear as
     wanda_prune_linear, but longest first and dealt over `streams` side streams - a warp of vlmc_wanda_rowselect owns whole
     rows, so the tail of one launch (warps that got one row fewer) is filled by the next linear's rows instead of idling
     (3.37 -> 3.16 ms per Vicuna block).  Masks are allocated on the caller's stream.  Identical masks, weights and scores.
-    Sets module.mask; returns the importance scores as a list of 1-element device tensors (one per module)."""
+    Sets module.mask; returns the importance scores as a list of 1-element device tensors (one per module).
+    ks[i] (optional) overrides the rows' prune count int(C * sparsity) of module i (DSnoT rounds it)."""
     from vlmc.schedule import Fork
+
+    def kof(i):
+        return int(ks[i]) if ks is not None and ks[i] is not None else int(modules[i].weight.shape[1] * sparsities[i])
     out = [None] * len(modules)
     keeps = [torch.empty(m.weight.shape, dtype=torch.bool, device=m.weight.device) for m in modules]
     means = [torch.empty(1, dtype=torch.float32, device=m.weight.device) for m in modules]
@@ -98,7 +102,7 @@ def wanda_prune_block_rows(modules, scaler_rows, sparsities, lora_model=False, s
         # CTAs walk the concatenated rows); VLMC_ROWSELECT_BATCH=0 restores one launch per linear on side streams
         if os.environ.get("VLMC_ROWSELECT_BATCH") != "0" and len({modules[i].weight.dtype for i in idx}) == 1:
             _, mm = native.wanda_rowselect_batch([modules[i].weight.data for i in idx], [scaler_rows[i] for i in idx],
-                                                 [int(modules[i].weight.shape[1] * sparsities[i]) for i in idx],
+                                                 [kof(i) for i in idx],
                                                  zero_w=not lora_model, keep_masks=[keeps[i] for i in idx])
             for j, i in enumerate(idx):
                 means[i] = mm[j:j + 1]
@@ -108,7 +112,7 @@ def wanda_prune_block_rows(modules, scaler_rows, sparsities, lora_model=False, s
             for slot, i in enumerate(idx):
                 W = modules[i].weight.data
                 with fk.stream(slot):
-                    native.wanda_rowselect(W, scaler_rows[i], int(W.shape[1] * sparsities[i]), zero_w=not lora_model,
+                    native.wanda_rowselect(W, scaler_rows[i], kof(i), zero_w=not lora_model,
                                            keep_mask=keeps[i], score_mean=means[i])
     for i, mod in enumerate(modules):
         setattr(mod, "mask", keeps[i])
@@ -205,7 +209,7 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
                 self._pending_nm.append((module, wrapper.scaler_row, lora_model))
                 return
             if not vit:                             # per-row top-k: the block's launches dealt over streams (finish_block)
-                self._pending_rows.append((module, wrapper.scaler_row, sparsity, lora_model))
+                self._pending_rows.append((module, wrapper.scaler_row, sparsity, lora_model, None, True))
                 return
             mean = wanda_prune_linear(module, wrapper.scaler_row, sparsity, self.prune_n, self.prune_m,
                                       lora_model=lora_model, whole_matrix=vit)
@@ -220,10 +224,11 @@ class BLIPT5LayerWandaPruner(LayerWiseBasePruner):
             self._pending_scores.extend(zip(mods, means))
             self._pending_nm = []
         if self._pending_rows:
-            mods = [m for m, *_ in self._pending_rows]
-            means = wanda_prune_block_rows(mods, [s for _, s, _, _ in self._pending_rows],
-                                           [p for _, _, p, _ in self._pending_rows], lora_model=self._pending_rows[0][3])
-            self._pending_scores.extend(zip(mods, means))
+            # entries: (module, scaler_row, sparsity, lora_model, k override or None, importance score wanted)
+            mods = [e[0] for e in self._pending_rows]
+            means = wanda_prune_block_rows(mods, [e[1] for e in self._pending_rows], [e[2] for e in self._pending_rows],
+                                           lora_model=self._pending_rows[0][3], ks=[e[4] for e in self._pending_rows])
+            self._pending_scores.extend((m, v) for m, v, e in zip(mods, means, self._pending_rows) if e[5])
             self._pending_rows = []
         # one host sync per block instead of the reference's full-matrix .cpu() per linear (:320)
         if self._pending_scores:
