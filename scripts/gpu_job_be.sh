@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 2 --steps 5 --warmup 3 --no-full-model --no-cpu-baseline > gpurun_out/r02final4_bench_wanda_nm_2gpu.json 2> gpurun_out/r02final4_bench_2gpu.err
+tail -3 gpurun_out/r02final4_bench_2gpu.err
+python - <<PY
+import json
+d=[json.loads(l) for l in open('gpurun_out/r02final4_bench_wanda_nm_2gpu.json') if l.startswith('{')][-1]
+print("headline", round(d["value"]*1e3,3), "ms  e2e", d["e2e"]["value"])
+for m,v in d["methods"].items(): print(" ", m, round(v["value"]*1e3,3) if v.get("value") else v, v.get("roofline",{}).get("spans_ms_per_step"))
+PY
