@@ -633,22 +633,25 @@ def roofline_of(res, pk):
         alg = k["work"] / k["spans"]                     # algorithmic bytes per launch
         out["traffic_over_algorithmic"] = out["traffic"] / alg
         out["dram_achieved"] = out["traffic"] / (out["avg_span_ms"] * 1e-3) / 1e9       # GB/s that actually crossed the HBM interface
-        if tag in ("sqnorm_accum", "dsnot_stats") and not res.get("shared") and out["traffic"] < 0.9 * alg:
-            # "18.66 GB per-linear, 12.21 GB if the 4 distinct inputs are de-duplicated - report which".  The block's
-            # statistics are ONE launch in which the linears fed the same activations (q / k / v, gate / up) read them at the same
-            # time, so the repeats hit in L2 and DRAM sees the distinct tensors only (`traffic`).  `achieved` / `frac` are therefore
-            # quoted on the DISTINCT bytes (what the memory system has to deliver); the per-linear figure is kept beside them.
-            dims = {}
-            for _, _, C, inp in LINEARS:
-                dims[inp] = C
-            frac_distinct = sum(dims.values()) / float(sum(C for _, _, C, _ in LINEARS))
-            out["achieved_per_linear_bytes"] = achieved
-            out["frac_per_linear_bytes"] = achieved / peak
-            out["achieved"] = achieved * frac_distinct
-            out["frac"] = achieved * frac_distinct / peak
-            out["bytes_basis"] = ("distinct activation tensors of the block (12.21 of the 18.66 GB per-linear bytes at 1 GPU); "
-                                  "`*_per_linear_bytes` count every linear's read; `dram_achieved` = measured DRAM traffic / time")
-            out["traffic_over_algorithmic"] = out["traffic"] / (alg * frac_distinct)
+    batched = os.environ.get("VLMC_BENCH_STATS_BATCH") != "0" and (res.get("world", 1) > 1 or res.get("calib_batch", 0) >= N_SEQ)
+    if bound == "hbm" and tag in ("sqnorm_accum", "dsnot_stats") and not res.get("shared") and batched:
+        # "18.66 GB per-linear, 12.21 GB if the 4 distinct inputs are de-duplicated - report which".  The block's
+        # statistics are ONE launch in which the linears fed the same activations (q / k / v, gate / up) read them at the same
+        # time, so the repeats hit in L2 and DRAM sees the distinct tensors only (`traffic`, when a capture matches).  `achieved` /
+        # `frac` are therefore quoted on the DISTINCT bytes (what the memory system has to deliver); the per-linear figure is
+        # kept beside them.
+        dims = {}
+        for _, _, C, inp in LINEARS:
+            dims[inp] = C
+        frac_distinct = sum(dims.values()) / float(sum(C for _, _, C, _ in LINEARS))
+        out["achieved_per_linear_bytes"] = achieved
+        out["frac_per_linear_bytes"] = achieved / peak
+        out["achieved"] = achieved * frac_distinct
+        out["frac"] = achieved * frac_distinct / peak
+        out["bytes_basis"] = ("distinct activation tensors of the block (12.21 of the 18.66 GB per-linear bytes at 1 GPU); "
+                              "`*_per_linear_bytes` count every linear's read; `dram_achieved` = measured DRAM traffic / time")
+        if out.get("traffic") and k["spans"]:
+            out["traffic_over_algorithmic"] = out["traffic"] / (k["work"] / k["spans"] * frac_distinct)
     if tag == "hessian_accum":
         # the SYRK executes the upper 256 x 256 tiles only: executed flop next to the logical (full-square) figure
         ex = 0.0
