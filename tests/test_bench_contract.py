@@ -44,3 +44,28 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--impl", "reference", "--gpus", "2", "--steps", "1",
              "--warmup", "0")
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_statistics_roofline_is_quoted_on_distinct_bytes_when_batched(monkeypatch):
+    """SURVEY 8(d) asks to say which byte count the roofline uses: with the block's statistics as ONE launch the linears fed
+    the same activations share them through L2, so `achieved` / `frac` count the four distinct tensors (12.21 of the 18.66 GB)
+    and the per-linear figure sits beside them; with one launch per linear, or shared inputs, nothing is rescaled."""
+    sys.path.insert(0, ROOT)
+    import bench
+    pk = {"hbm": 6545.0, "tensor": 1688.0, "tensor_sustained": 1408.0, "source": "test"}
+
+    def res(world=1, calib_batch=bench.N_SEQ, shared=False):
+        return {"method": "wanda_nm", "steps": 10, "eager_ms_per_step": 2.05, "shared": shared, "world": world, "calib_batch": calib_batch,
+                "kernels": {"sqnorm_accum": {"ms": 18.3, "work": 18.66e9 * 10, "spans": 10},
+                            "wanda_select": {"ms": 1.86, "work": 1.012e9 * 10, "spans": 10}}}
+    monkeypatch.delenv("VLMC_BENCH_STATS_BATCH", raising=False)
+    r = bench.roofline_of(res(), pk)
+    distinct = (3 * 4096 + 11008) / (6 * 4096 + 11008)
+    assert abs(r["frac_per_linear_bytes"] - 18.66e9 / 1.83e-3 / 1e9 / 6545.0) < 1e-9
+    assert abs(r["frac"] - r["frac_per_linear_bytes"] * distinct) < 1e-12 and r["frac"] < 1.1 and "bytes_basis" in r
+    assert bench.roofline_of(res(world=2), pk)["frac"] == r["frac"]                       # batched at every N > 1
+    for plain in (res(calib_batch=16), res(shared=True)):
+        q = bench.roofline_of(plain, pk)
+        assert "frac_per_linear_bytes" not in q and abs(q["frac"] - r["frac_per_linear_bytes"]) < 1e-9
+    monkeypatch.setenv("VLMC_BENCH_STATS_BATCH", "0")
+    assert "frac_per_linear_bytes" not in bench.roofline_of(res(), pk)
