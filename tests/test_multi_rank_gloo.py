@@ -106,6 +106,31 @@ def _wanda_packed(rank, out):
     for (keep, mean), W, (keep_ref, W_ref, mean_ref) in zip(res, Wt, refs):
         assert np.array_equal(keep.numpy(), keep_ref) and np.array_equal(W.numpy(), W_ref)
         assert abs(mean.item() - mean_ref) < 1e-5 * mean_ref
+
+    # the batched calls (vlmc_wanda_rowselect_batch / vlmc_mask_pack_batch / vlmc_mask_apply_packed_batch on the GPU): one
+    # select, one pack and one expand call for ALL linears around the same single all-gather - same results
+    calls = {"select": 0, "pack": 0, "apply": 0}
+
+    def select_batch(W_rows, keep_rows):
+        calls["select"] += 1
+        return torch.cat([make_select(i)(w, k) for i, (w, k) in enumerate(zip(W_rows, keep_rows))])
+
+    def pack_batch(keep_rows_list, bits_list):
+        calls["pack"] += 1
+        for k, b in zip(keep_rows_list, bits_list):
+            pack(k, b)
+
+    def apply_batch(Wfs, bits_views, keeps, rows_per_seg, seg_stride):
+        calls["apply"] += 1
+        for Wf, b, k, rps in zip(Wfs, bits_views, keeps, rows_per_seg):
+            apply(Wf, b, k, rps, seg_stride)
+    Wt = [torch.from_numpy(W.copy()) for W in Ws]
+    res = parallel.prune_block_rows_packed(Wt, [None] * 3, None, None, rank, WORLD, select_batch_fn=select_batch,
+                                           pack_batch_fn=pack_batch, apply_batch_fn=apply_batch)
+    assert calls == {"select": 1, "pack": 1, "apply": 1}
+    for (keep, mean), W, (keep_ref, W_ref, mean_ref) in zip(res, Wt, refs):
+        assert np.array_equal(keep.numpy(), keep_ref) and np.array_equal(W.numpy(), W_ref)
+        assert abs(mean.item() - mean_ref) < 1e-5 * mean_ref
     out[rank] = "ok"
 
 
