@@ -1888,6 +1888,27 @@ def test_lora_linear_fused_vs_fp64(native, tag, T, R, C, r):
             assert float((y.float() - lib.float()).abs().max()) <= 2 * ulp * float(lib.float().abs().max())
 
 
+@pytest.mark.parametrize("key", [k for k in LORA_FWD_KEYS if not k.startswith("f32")])
+def test_lora_linear_fused_reference_golden(native, key):
+    """The reference's own lora.Linear forward output y (committed fixture, generated by tests/golden/make_golden.py from the
+    unmodified lora.py) through K23: within 2 ulp of the layer dtype (the reference accumulates on the CPU in another order).
+    C = 72: a partial last k-slice; the mask is handed over as a view with a 16-byte-multiple row pitch (TMA)."""
+    g = gu.load("lora_forward.npz")
+    tag, sparse = key.split("_")[0], key.endswith("sparse")
+    ulp = {"bf16": 2.0 ** -8, "f16": 2.0 ** -11}[tag]
+    W = torch.from_numpy(g[f"{key}|W"]).to(DT[tag]).cuda()
+    A, B = torch.from_numpy(g[f"{key}|A"]).cuda(), torch.from_numpy(g[f"{key}|B"]).cuda()
+    R, C = W.shape
+    mbuf = torch.zeros(R, (C + 15) // 16 * 16, dtype=torch.bool, device="cuda")
+    mask = mbuf[:, :C]
+    mask.copy_(torch.from_numpy(g[f"{key}|mask"]))
+    x = torch.from_numpy(g[f"{key}|x"]).to(DT[tag]).cuda()
+    assert native.sparselora_linear_forward_supported(x, W, mask, A.shape[0])
+    y = native.sparselora_linear_forward(x, W, A, B, float(g[f"{key}|scaling"]), mask, sparse)
+    want = torch.from_numpy(g[f"{key}|y"]).cuda()
+    assert float((y.float() - want).abs().max()) <= 2 * ulp * float(want.abs().max())
+
+
 def test_lora_linear_fused_3d_input_and_rejections(native):
     W, A, B, mask = _ll_case(256, 512, 8, "bf16", 3)
     x = (torch.randn(3, 7, 512, device="cuda")).bfloat16()
