@@ -188,6 +188,17 @@ def sparselora_effective_weight(W32, w_tag, A, B, scaling, keep_mask, sparse=Tru
     return round_to_dtype((np.where(keep_mask, W32, F32(0)) + d).astype(F32), w_tag)
 
 
+def sparselora_linear_forward(x32, W32, w_tag, A, B, scaling, keep_mask, sparse=True, bias32=None):
+    """Linear.forward with r > 0, not merged (lora.py:359-382): F.linear(x, <the effective weight above>, bias) in W's
+    dtype - float64 accumulation of the exact products (the truth a kernel with fp32 accumulation is compared with), bias
+    added before the ONE rounding to the dtype.  K23 (vlmc_sparselora_linear_forward) computes exactly this."""
+    weff = sparselora_effective_weight(W32, w_tag, A, B, scaling, keep_mask, sparse).astype(np.float64)
+    y = np.asarray(x32, dtype=np.float64) @ weff.T
+    if bias32 is not None:
+        y = y + np.asarray(bias32, dtype=np.float64)
+    return round_to_dtype(y.astype(F32), w_tag)
+
+
 def sparselora_lora_grads(G32, w_tag, A, B, scaling, keep_mask, sparse=True):
     """Autograd of that expression w.r.t. lora_A / lora_B given G = dL/dW_eff (in W's dtype): mask (sparse only), scale
     in W's dtype, cast to float32, dB = E A^T, dA = B^T E.  Returned in float64-accumulated float32 (the truth the

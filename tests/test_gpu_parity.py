@@ -1907,6 +1907,10 @@ def test_lora_linear_fused_reference_golden(native, key):
     y = native.sparselora_linear_forward(x, W, A, B, float(g[f"{key}|scaling"]), mask, sparse)
     want = torch.from_numpy(g[f"{key}|y"]).cuda()
     assert float((y.float() - want).abs().max()) <= 2 * ulp * float(want.abs().max())
+    # and against the numpy oracle of the same expression (float64 accumulation, one rounding): 1 ulp of the output
+    yo = oracle.sparselora_linear_forward(g[f"{key}|x"], g[f"{key}|W"], tag, g[f"{key}|A"], g[f"{key}|B"],
+                                          float(g[f"{key}|scaling"]), g[f"{key}|mask"], sparse)
+    assert np.abs(y.float().cpu().numpy() - yo).max() <= ulp * np.abs(yo).max()
 
 
 def test_lora_linear_fused_3d_input_and_rejections(native):

@@ -267,6 +267,10 @@ def test_lora_forward():
                 err = np.abs(weff - ref) / np.maximum(np.abs(ref), 1e-3)
                 assert err.max() <= 2 * ulp, (k, err.max())
                 worst = max(worst, float((weff != ref).mean()))
+                # the whole forward (K23's oracle): the reference's y within 2 ulp of the dtype (its CPU GEMM adds in another order)
+                y = oracle.sparselora_linear_forward(g[f"{k}|x"], g[f"{k}|W"], tag, g[f"{k}|A"], g[f"{k}|B"], scaling, mask, sparse)
+                # (fp32 layers: the reference's SGEMM also ACCUMULATES in fp32 over C = 72 products: 8 ulp)
+                assert np.abs(y - g[f"{k}|y"]).max() <= (8 if tag == "f32" else 2) * ulp * np.abs(g[f"{k}|y"]).max(), k
                 dA, dB = oracle.sparselora_lora_grads(g[f"{k}|G"], tag, g[f"{k}|A"], g[f"{k}|B"], scaling, mask, sparse)
                 for got, want in ((dA, g[f"{k}|dA"]), (dB, g[f"{k}|dB"])):
                     assert np.abs(got - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-6), k
